@@ -1,0 +1,179 @@
+"""Generate the golden vectors under tests/golden/ from the REAL reference.
+
+Run in the build container only (needs the read-only reference checkout):
+
+    python tests/golden/make_golden.py [/root/reference]
+
+The reference package cannot be imported as a whole (``rl/__init__.py`` pulls in
+``gym``), so the four hot-path files are loaded by path with a stub ``rl``
+package.  Nothing here is copied into the repo: only the
+seeded inputs and the reference's outputs are stored, as ``*.npz``.  The GPU box
+never runs this script and never sees the reference.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from ppo_b200 import synthetic  # noqa: E402
+
+
+def load_reference(root="/root/reference"):
+    """Import rl.returns / rl.returns_truncated / rl.vtrace / rl.tvf from the reference checkout."""
+    def by_path(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(root, rel))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+
+    pkg = types.ModuleType("rl")
+    pkg.__path__ = []
+    sys.modules["rl"] = pkg
+    cfg = types.ModuleType("rl.config")
+    cfg.args = types.SimpleNamespace()
+    sys.modules["rl.config"] = cfg
+    sys.modules["rl.utils"] = types.ModuleType("rl.utils")
+    ro = types.ModuleType("rl.rollout")
+
+    class RunnerModule:  # stand-in for rl/rollout.py:91-113
+        def __init__(self, parent):
+            self.runner = parent
+
+    ro.RunnerModule = RunnerModule
+    sys.modules["rl.rollout"] = ro
+    pkg.config, pkg.utils, pkg.rollout = cfg, sys.modules["rl.utils"], ro
+    returns = by_path("rl.returns", "rl/returns.py")
+    truncated = by_path("rl.returns_truncated", "rl/returns_truncated.py")
+    vtrace = by_path("rl.vtrace", "rl/vtrace.py")
+    tvf = by_path("rl.tvf", "rl/tvf.py")
+    pkg.returns, pkg.returns_truncated, pkg.vtrace, pkg.tvf = returns, truncated, vtrace, tvf
+    return types.SimpleNamespace(returns=returns, truncated=truncated, vtrace=vtrace, tvf=tvf)
+
+
+def tvf_test_inputs(steps, envs, n_req, n_val, seed):
+    """Seeded version of the reference's own estimator test data (tests/test_tvf.py:14-24)."""
+    rng = np.random.RandomState(seed)
+    return {
+        'gamma': 0.9997,
+        'rewards': rng.randint(-1, 3, size=[steps, envs]).astype('float32'),
+        'dones': rng.randint(0, 101, size=[steps, envs]) >= 98,
+        'required_horizons': np.geomspace(1, 1024, num=n_req).astype('int32'),
+        'value_sample_horizons': np.geomspace(1, 1024, num=n_val).astype('int32') - 1,
+        'value_samples': _zero_h0(rng.normal(0.1, 0.4, [steps + 1, envs, n_val]).astype('float32')),
+    }
+
+
+def _zero_h0(vs):
+    vs[:, :, 0] *= 0
+    return vs
+
+
+def main():
+    root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+    ref = load_reference(root)
+    out = {}
+
+    # ---- GAE / TD(lambda) / bootstrapped returns (rl/returns.py)
+    r, d, v = synthetic.rollout(24, 12, seed=11)
+    out["gae_in_rewards"], out["gae_in_dones"], out["gae_in_values"] = r, d, v
+    out["gae_bool"] = ref.returns.gae(r, v[:-1], v[-1], d, 0.999, 0.95)
+    out["gae_f32done"] = ref.returns.gae(r, v[:-1], v[-1], d.astype(np.float32), 0.999, 0.95)
+    out["gae_noterm"] = ref.returns.gae(r, v[:-1], v[-1], None, 0.99, 0.9)
+    out["tdl_bool"] = ref.returns.td_lambda(r, v[:-1], v[-1], d, 0.999, 0.8)
+    out["boot_scalar"] = ref.returns.calculate_bootstrapped_returns(r, d, v[-1], 0.999)
+    garr = np.random.RandomState(5).uniform(0.9, 1.0, size=r.shape).astype(np.float32)
+    out["boot_in_gamma_arr"] = garr
+    out["boot_array"] = ref.returns.calculate_bootstrapped_returns(r, d, v[-1], garr)
+    # known answer from rl/unit_tests.py:203-210
+    kr = np.asarray([1, 0, 2, 4, 6], dtype=np.float32)[:, None]
+    kd = np.asarray([0, 0, 1, 0, 0], dtype=np.float32)[:, None]
+    kv = np.asarray([0, 0.5, 0.5, 3, 4], dtype=np.float32)[:, None]
+    out["gae_kat"] = ref.returns.gae(kr, kv, np.asarray(5, dtype=np.float32), kd, gamma=0.5, lamb=1.0)
+
+    # ---- advantage normalisation: rl/rollout.py:1887-1897 is inline trainer code that cannot be
+    # imported (rl/rollout.py needs gym and removed NumPy aliases); the three lines are evaluated here.
+    adv = out["gae_bool"]
+    flat = adv.reshape(-1).copy()
+    out["advnorm"] = (flat - flat.mean()) / (flat.std() + 1e-8)
+    out["advnorm_clip"] = np.clip(out["advnorm"], -1.5, +1.5)
+
+    # ---- TVF estimator (rl/returns_truncated.py), the reference's own test shapes scaled down
+    args = tvf_test_inputs(48, 6, 16, 32, seed=3)
+    for key, val in args.items():
+        out["tvf_in_" + key] = np.asarray(val)
+    fast = ref.truncated._calculate_sampled_return_multi_fast
+    slow = ref.truncated._calculate_sampled_return_multi_reference
+    for n in (1, 8, 48):
+        out[f"tvf_fast_n{n}"] = fast(n_step_list=[n], **args)
+        out[f"tvf_slow_n{n}"] = slow(n_step_list=[n], **args)
+    lamb = 1 - 1 / 20
+    w = np.asarray([lamb ** x for x in range(48)], dtype=np.float32)
+    samples = np.random.RandomState(9).choice(range(1, 49), [16, 8], replace=True, p=w / w.sum())
+    out["tvf_in_samples"] = samples
+    out["tvf_fast_samples"] = fast(n_step_samples=samples, **args)
+    out["tvf_slow_samples"] = slow(n_step_samples=samples, **args)
+    out["tvf_fast_samples_log"] = fast(n_step_samples=samples, use_log_interpolation=True, **args)
+    for dist, mode in [("fixed", "standard"), ("exponential", "standard"), ("exponential", "advanced"),
+                       ("uniform", "advanced"), ("hyperbolic", "clipped"), ("quadratic", "adaptive"),
+                       ("exponential", "mcx"), ("exponential", "full")]:
+        out[f"tvf_gre_{dist}_{mode}"] = ref.truncated.get_return_estimate(
+            dist, mode, n_step=6, max_samples=5, seed=17, **args)
+
+    # production-like horizons: required == value horizons == get_value_head_horizons (rl/tvf.py:250-262)
+    hz = ref.tvf.get_value_head_horizons(32, 1000)
+    r2, d2, _ = synthetic.rollout(40, 5, seed=21)
+    vs2 = synthetic.value_samples(40, 5, len(hz), seed=21)
+    out["prod_in_horizons"], out["prod_in_rewards"], out["prod_in_dones"], out["prod_in_vs"] = hz, r2, d2, vs2
+    out["prod_adv"] = ref.truncated.get_return_estimate(
+        "exponential", "advanced", 0.99997, r2, d2, hz, hz, vs2, n_step=20, max_samples=8, seed=1)
+    out["prod_fixed"] = ref.truncated.get_return_estimate(
+        "fixed", "advanced", 0.99997, r2, d2, hz, hz, vs2, n_step=40, max_samples=8, seed=1)
+    out["prod_adv_log"] = ref.truncated.get_return_estimate(
+        "exponential", "advanced", 0.99997, r2, d2, hz, hz, vs2, n_step=20, max_samples=8,
+        use_log_interpolation=True, seed=1)
+
+    # ---- rl/tvf.py free functions
+    out["heads_128_30000"] = ref.tvf.get_value_head_horizons(128, 30000)
+    hw, cw = ref.tvf.get_value_head_horizons(16, 100, include_weight=True)
+    out["heads_16_100"], out["heads_16_100_w"] = hw, cw
+    out["heads_lin_9_64"] = ref.tvf.get_value_head_horizons(9, 64, spacing="linear")
+    kh = np.asarray([0, 1, 2, 10, 100])
+    kvals = np.asarray([0, 5, 10, -1, 2])[None, :].repeat(11, axis=0)
+    ktgt = np.asarray([-100, -1, 0, 1, 2, 3, 4, 99, 100, 101, 200])
+    out["hinterp_kat"] = ref.tvf.horizon_interpolate(kh, kvals, ktgt)  # tests/test_tvf.py:121-129
+    rng = np.random.RandomState(31)
+    hv = rng.normal(0, 1, [7, 9, len(hz)]).astype(np.float32)
+    ht = rng.randint(-5, 1100, size=[7, 9])
+    out["hinterp_in_values"], out["hinterp_in_targets"] = hv, ht
+    out["hinterp"] = ref.tvf.horizon_interpolate(hz, hv, ht)
+    rv = np.cumsum(np.abs(rng.normal(0, 1, [20, len(hz)])), axis=1).astype(np.float32)
+    rv[:, 0] = 0
+    out["redis_in_values"] = rv
+    out["redis_down"] = ref.tvf.get_rediscounted_value_estimate(rv, 0.9999, 0.999, hz)
+    out["redis_up"] = ref.tvf.get_rediscounted_value_estimate(rv, 0.99, 0.9999, hz)
+    out["redis_same"] = np.asarray(ref.tvf.get_rediscounted_value_estimate(rv, 0.99, 0.99, hz))
+
+    # ---- V-trace (rl/vtrace.py)
+    beh, tgt, act = synthetic.policies(14, 6, n_actions=5, seed=41)
+    r3, d3, v3 = synthetic.rollout(14, 6, seed=41)
+    out["vt_in_beh"], out["vt_in_tgt"], out["vt_in_act"] = beh, tgt, act
+    out["vt_in_rewards"], out["vt_in_dones"], out["vt_in_values"] = r3, d3, v3
+    vs, adv, cs = ref.vtrace.importance_sampling_v_trace(beh, tgt, act, r3, d3, v3[:-1], v3[-1], 0.99, 0.9)
+    out["vt_vs"], out["vt_adv"], out["vt_cs"] = vs, adv, cs
+    vs, adv, cs = ref.vtrace.importance_sampling_v_trace(beh, beh, act, r3, d3, v3[:-1], v3[-1], 0.99, 1.0)
+    out["vt_onpolicy_vs"], out["vt_onpolicy_adv"] = vs, adv
+    out["vt_trust"] = ref.vtrace.v_trace_trust_region(beh, tgt)
+
+    path = os.path.join(HERE, "reference_vectors.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,142 @@
+"""CPU: the oracle restatement must reproduce the real reference bit-for-bit on the golden vectors.
+
+The vectors were produced by tests/golden/make_golden.py, which imports the unmodified reference.
+Unless a tolerance is written in a test, comparisons are exact (np.array_equal).
+"""
+import numpy as np
+import pytest
+
+import oracle
+
+
+def same(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and a.dtype == b.dtype and np.array_equal(a, b)
+
+
+def test_gae_family(golden):
+    g = golden
+    r, d, v = g["gae_in_rewards"], g["gae_in_dones"], g["gae_in_values"]
+    assert same(oracle.gae(r, v[:-1], v[-1], d, 0.999, 0.95), g["gae_bool"])
+    assert same(oracle.gae(r, v[:-1], v[-1], d.astype(np.float32), 0.999, 0.95), g["gae_f32done"])
+    assert same(oracle.gae(r, v[:-1], v[-1], None, 0.99, 0.9), g["gae_noterm"])
+    assert same(oracle.td_lambda(r, v[:-1], v[-1], d, 0.999, 0.8), g["tdl_bool"])
+    assert same(oracle.calculate_bootstrapped_returns(r, d, v[-1], 0.999), g["boot_scalar"])
+    assert same(oracle.calculate_bootstrapped_returns(r, d, v[-1], g["boot_in_gamma_arr"]), g["boot_array"])
+
+
+def test_gae_known_answer():
+    # rl/unit_tests.py:203-210
+    r = np.asarray([1, 0, 2, 4, 6], dtype=np.float32)[:, None]
+    d = np.asarray([0, 0, 1, 0, 0], dtype=np.float32)[:, None]
+    v = np.asarray([0, 0.5, 0.5, 3, 4], dtype=np.float32)[:, None]
+    res = oracle.gae(r, v, np.asarray(5, dtype=np.float32), d, gamma=0.5, lamb=1.0)
+    assert np.max(np.abs(res - np.asarray([1.5, 0.5, 1.5, 5.25, 4.5])[:, None])) < 1e-6
+
+
+def test_advantage_normalisation(golden):
+    assert same(oracle.normalize_advantages(golden["gae_bool"], 1e-8), golden["advnorm"])
+    assert same(oracle.normalize_advantages(golden["gae_bool"], 1e-8, 1.5), golden["advnorm_clip"])
+
+
+def _tvf_args(g):
+    keys = ['gamma', 'rewards', 'dones', 'required_horizons', 'value_sample_horizons', 'value_samples']
+    a = {k: g["tvf_in_" + k] for k in keys}
+    a['gamma'] = float(a['gamma'])
+    return a
+
+
+@pytest.mark.parametrize("n", [1, 8, 48])
+def test_tvf_fixed_lists(golden, n):
+    a = _tvf_args(golden)
+    assert same(oracle.sampled_return_multi(n_step_list=[n], **a), golden[f"tvf_fast_n{n}"])
+    assert same(oracle.sampled_return_slow(n_step_list=[n], **a), golden[f"tvf_slow_n{n}"])
+
+
+def test_tvf_sample_tables(golden):
+    a = _tvf_args(golden)
+    s = golden["tvf_in_samples"]
+    assert same(oracle.sampled_return_multi(n_step_samples=s, **a), golden["tvf_fast_samples"])
+    assert same(oracle.sampled_return_slow(n_step_samples=s, **a), golden["tvf_slow_samples"])
+    assert same(oracle.sampled_return_multi(n_step_samples=s, use_log_interpolation=True, **a),
+                golden["tvf_fast_samples_log"])
+    # the reference's own acceptance criterion, tests/test_tvf.py:46
+    ref = golden["tvf_slow_samples"]
+    assert np.abs(ref - golden["tvf_fast_samples"]).max() <= 1e-5 * ref.max()
+
+
+@pytest.mark.parametrize("dist,mode", [("fixed", "standard"), ("exponential", "standard"),
+                                       ("exponential", "advanced"), ("uniform", "advanced"),
+                                       ("hyperbolic", "clipped"), ("quadratic", "adaptive"),
+                                       ("exponential", "mcx"), ("exponential", "full")])
+def test_tvf_dispatcher(golden, dist, mode):
+    a = _tvf_args(golden)
+    got = oracle.get_return_estimate(dist, mode, n_step=6, max_samples=5, seed=17, **a)
+    assert same(got, golden[f"tvf_gre_{dist}_{mode}"])
+
+
+def test_tvf_dispatcher_rejects_unknown(golden):
+    a = _tvf_args(golden)
+    with pytest.raises(ValueError):
+        oracle.get_return_estimate("nope", "standard", **a)
+    with pytest.raises(ValueError):
+        oracle.get_return_estimate("uniform", "nope", **a)
+
+
+def test_tvf_production_horizons(golden):
+    g = golden
+    hz, r, d, vs = g["prod_in_horizons"], g["prod_in_rewards"], g["prod_in_dones"], g["prod_in_vs"]
+    assert same(oracle.get_value_head_horizons(32, 1000), hz)
+    got = oracle.get_return_estimate("exponential", "advanced", 0.99997, r, d, hz, hz, vs,
+                                     n_step=20, max_samples=8, seed=1)
+    assert same(got, g["prod_adv"])
+    got = oracle.get_return_estimate("fixed", "advanced", 0.99997, r, d, hz, hz, vs,
+                                     n_step=40, max_samples=8, seed=1)
+    assert same(got, g["prod_fixed"])
+    got = oracle.get_return_estimate("exponential", "advanced", 0.99997, r, d, hz, hz, vs,
+                                     n_step=20, max_samples=8, use_log_interpolation=True, seed=1)
+    assert same(got, g["prod_adv_log"])
+
+
+def test_head_horizons(golden):
+    assert same(oracle.get_value_head_horizons(128, 30000), golden["heads_128_30000"])
+    h, w = oracle.get_value_head_horizons(16, 100, include_weight=True)
+    assert same(h, golden["heads_16_100"]) and same(w, golden["heads_16_100_w"])
+    assert same(oracle.get_value_head_horizons(9, 64, spacing="linear"), golden["heads_lin_9_64"])
+
+
+def test_horizon_interpolate(golden):
+    # tests/test_tvf.py:121-129 known answer
+    kh = np.asarray([0, 1, 2, 10, 100])
+    kv = np.asarray([0, 5, 10, -1, 2])[None, :].repeat(11, axis=0)
+    kt = np.asarray([-100, -1, 0, 1, 2, 3, 4, 99, 100, 101, 200])
+    res = oracle.horizon_interpolate(kh, kv, kt)
+    expected = [0, 0, 0, 5, 10, (7 / 8) * 10 + (1 / 8) * -1, (6 / 8) * 10 + (2 / 8) * -1, 1.96666667, 2, 2, 2]
+    assert np.max(np.abs(np.asarray(expected) - res)) < 1e-6
+    assert same(res, golden["hinterp_kat"])
+    hz = golden["prod_in_horizons"]
+    assert same(oracle.horizon_interpolate(hz, golden["hinterp_in_values"], golden["hinterp_in_targets"]),
+                golden["hinterp"])
+
+
+def test_rediscount(golden):
+    hz, rv = golden["prod_in_horizons"], golden["redis_in_values"]
+    assert same(oracle.get_rediscounted_value_estimate(rv, 0.9999, 0.999, hz), golden["redis_down"])
+    assert same(oracle.get_rediscounted_value_estimate(rv, 0.99, 0.9999, hz), golden["redis_up"])
+    assert same(oracle.get_rediscounted_value_estimate(rv, 0.99, 0.99, hz), golden["redis_same"])
+
+
+def test_vtrace(golden):
+    g = golden
+    beh, tgt, act = g["vt_in_beh"], g["vt_in_tgt"], g["vt_in_act"]
+    r, d, v = g["vt_in_rewards"], g["vt_in_dones"], g["vt_in_values"]
+    vs, adv, cs = oracle.importance_sampling_v_trace(beh, tgt, act, r, d, v[:-1], v[-1], 0.99, 0.9)
+    assert same(vs, g["vt_vs"]) and same(adv, g["vt_adv"]) and same(cs, g["vt_cs"])
+    vs, adv, _ = oracle.importance_sampling_v_trace(beh, beh, act, r, d, v[:-1], v[-1], 0.99, 1.0)
+    assert same(vs, g["vt_onpolicy_vs"]) and same(adv, g["vt_onpolicy_adv"])
+    assert same(oracle.v_trace_trust_region(beh, tgt), g["vt_trust"])
+    # on-policy identities of rl/unit_tests.py:61-87 (float32 rounding tolerance 1e-5 relative)
+    ret = oracle.calculate_bootstrapped_returns(r, d, v[-1], 0.99)
+    gae = oracle.gae(r, v[:-1], v[-1], d, 0.99, 1.0)
+    assert np.abs(vs - ret).max() <= 1e-5 * np.abs(ret).max()
+    assert np.abs(adv - gae).max() <= 1e-5 * np.abs(gae).max()
