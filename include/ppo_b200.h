@@ -1,0 +1,189 @@
+/*
+ * ppo_b200 -- C ABI of the B200-native return / advantage hot path.
+ *
+ * Drop-in boundary for the reference trainer dremovd/PPO.  The reference has no FFI
+ * layer: the path is a set of plain Python functions called by rl/rollout.py
+ * (SURVEY.md section 8b).  Each entry point below replaces the NumPy body of one of
+ * those functions; the Python package `ppo_b200` keeps the reference's names and
+ * signatures and hands raw device pointers to these symbols through ctypes
+ * (INTEGRATION.md shows the stub a maintainer adds to the reference).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the caller owns all buffers; outputs are pre-allocated; nothing is freed or
+ *     retained by the library (no global state besides a per-thread error string and
+ *     the cached TMA driver entry point);
+ *   - sizes and strides are int64 and counted in ELEMENTS;
+ *   - scalar hyper-parameters cross the ABI as double (gamma must never be demoted to
+ *     float before the reference does it, SURVEY.md section 7 "hard parts");
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant,
+ *     and return 0 or a negative ppo_status; nothing throws across the boundary;
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns
+ *     PPO_ERR_CUDA.
+ *
+ * Layouts (row-major, env axis contiguous unless a stride argument says otherwise)
+ *   rewards, dones, advantages, returns : [N, A]       N = steps, A = envs
+ *   values                              : [N(+1), A]
+ *   value_samples                       : [N+1, A, V]  V = value-sample horizons
+ *   tvf targets                         : [N, A, K]    K = required horizons
+ *   log-policies                        : [N, B, ACT]
+ */
+#ifndef PPO_B200_H
+#define PPO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    PPO_OK = 0,
+    PPO_ERR_BAD_ARG = -1,     /* shape / pointer / value rejected (Python: ValueError)      */
+    PPO_ERR_UNSUPPORTED = -2, /* valid request this build cannot serve (Python: ValueError) */
+    PPO_ERR_CUDA = -3,        /* CUDA runtime / driver error (Python: RuntimeError)         */
+    PPO_ERR_WORKSPACE = -4    /* workspace missing or too small (Python: ValueError)        */
+} ppo_status;
+
+/* how the `dones` / terminal array is stored */
+typedef enum {
+    PPO_DONE_NONE = 0, /* no terminal array: rl/returns.py:23-24 `batch_terminal is None` */
+    PPO_DONE_U8 = 1,   /* numpy bool / uint8, non-zero = terminal                         */
+    PPO_DONE_F32 = 2   /* float32 0/1 mask (rl/unit_tests.py:205)                         */
+} ppo_done_kind;
+
+/* Layout of one statistics record (doubles).  Sums are over the float32-rounded outputs. */
+enum {
+    PPO_STAT_COUNT = 0,
+    PPO_STAT_ADV_SUM = 1,
+    PPO_STAT_ADV_SUMSQ = 2,
+    PPO_STAT_ADV_MIN = 3,
+    PPO_STAT_ADV_MAX = 4,
+    PPO_STAT_RET_SUM = 5,
+    PPO_STAT_RET_SUMSQ = 6,
+    PPO_STAT_RET_MIN = 7,
+    PPO_STAT_RET_MAX = 8,
+    PPO_STATS_LEN = 16
+};
+
+/* Library version (major*10000 + minor*100 + patch) and the message of the last failing call
+ * made by the calling thread. */
+int ppo_version(void);
+const char* ppo_last_error(void);
+
+/* Number of visible CUDA devices, or a negative ppo_status. */
+int ppo_device_count(void);
+
+/* Bytes of zero-initialised device scratch the GAE entry points need for `envs` envs.
+ * The buffer must be zeroed ONCE when allocated; the kernels leave it zeroed again. */
+int64_t ppo_gae_workspace_bytes(int64_t envs);
+
+/*
+ * GAE advantages and TD(lambda) returns in one reverse-time scan.
+ * Replaces rl/returns.py:7-29 `gae` and rl/returns.py:58-67 `td_lambda`, which the trainer calls
+ * back to back on identical inputs with two lambdas (rl/rollout.py:1207-1223):
+ *   delta_t = r_t + gamma * V_{t+1} * (1 - done_t) - V_t
+ *   A_t     = delta_t + gamma * lamb * (1 - done_t) * A_{t+1},   A_N = 0,  V_N = final_value
+ *   adv_out = A(lamb_adv),  ret_out = A(lamb_ret) + V
+ * adv_out / ret_out may each be NULL.  `stats` (PPO_STATS_LEN doubles) may be NULL; when given it
+ * receives count / sum / sum of squares / min / max of adv_out and ret_out over this call
+ * (the "return-scale statistics" of rl/rollout.py:1252-1256 and the moments needed by the
+ * normalisation of rl/rollout.py:1891).  Deterministic: partial sums are combined in a fixed order.
+ * values: element (t, a) at values[t * value_row_stride + a * value_env_stride];
+ * final_value: element a at final_value[a * final_env_stride].
+ */
+int ppo_gae(const float* rewards, int64_t reward_row_stride,
+            const float* values, int64_t value_row_stride, int64_t value_env_stride,
+            const float* final_value, int64_t final_env_stride,
+            const void* dones, int done_kind, int64_t done_row_stride,
+            int64_t steps, int64_t envs,
+            double gamma, double lamb_adv, double lamb_ret,
+            float* adv_out, float* ret_out, double* stats,
+            void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * Batch advantage normalisation: out = clip((x - mean) / (std + eps), -clip, +clip), population std.
+ * Replaces the inline NumPy at rl/rollout.py:1887-1897.  `stats` is a device record as written by
+ * ppo_gae (after an optional cross-GPU sum of COUNT / ADV_SUM / ADV_SUMSQ).  clip <= 0 disables
+ * clipping (rl/rollout.py:1895 `advantage_clipping is None`).  In-place (out == adv) is allowed.
+ */
+int ppo_adv_normalize(const float* adv, int64_t count, const double* stats,
+                      double eps, double clip, float* out, void* stream);
+
+/* count / sum / sumsq / min / max of a float32 vector into the ADV_* slots of `stats`
+ * (for advantages that were combined on the device, e.g. ext + int, rl/rollout.py:1225-1228). */
+int ppo_moments(const float* x, int64_t count, double* stats,
+                void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * Discounted returns bootstrapped from a final value.  Replaces rl/returns.py:32-55
+ * `calculate_bootstrapped_returns`:  R_t = r_t + R_{t+1} * gamma_t * (1 - done_t),  R_N = final_value.
+ * gamma_array == NULL: scalar gamma, applied as float32(gamma) like the reference (rl/returns.py:49-50);
+ * otherwise gamma_array is [N, A] float32 with the given row stride and `gamma` is ignored.
+ */
+int ppo_discounted_returns(const float* rewards, int64_t reward_row_stride,
+                           const void* dones, int done_kind, int64_t done_row_stride,
+                           const float* final_value, int64_t final_env_stride,
+                           double gamma, const float* gamma_array, int64_t gamma_row_stride,
+                           int64_t steps, int64_t envs, float* out, void* stream);
+
+/*
+ * Index tables of one TVF target pass, resolved on the host from the [K, C] n-step sample table
+ * (ppo_b200/_tvf_tables.py documents the construction; it touches no rollout data).  All pointers
+ * are device pointers; entry arrays are [n_entries, K], tail arrays are [nmax + 1, K].
+ *   ent_n    clamped n-step n' = min(sample, h_k) of the entry, 0 = padding
+ *   ent_cnt  multiplicity of n' among the C samples of horizon k (0 = padding)
+ *   ent_idx  interpolation slots at horizon h_k - n':  lo | hi << 16
+ *   ent_wlo / ent_whi   lerp weights (both 0 when h_k - n' <= 0: pure n-step return)
+ *   ent_g    gamma^n' as the reference's float32 running product
+ *   tail_*   the same slots / weights at horizon h_k - m for rows with m = N - t < n'
+ *   gpow     gamma^n, n = 0..nmax
+ *   inv_c    float32(1 / C)
+ */
+typedef struct {
+    int32_t n_entries;
+    int32_t nmax;
+    const int32_t* ent_n;
+    const float* ent_cnt;
+    const int32_t* ent_idx;
+    const float* ent_wlo;
+    const float* ent_whi;
+    const float* ent_g;
+    const int32_t* tail_idx;
+    const float* tail_wlo;
+    const float* tail_whi;
+    const float* gpow;
+    float inv_c;
+} ppo_tvf_tables;
+
+/* which TVF kernel ppo_tvf_targets may use */
+typedef enum {
+    PPO_TVF_AUTO = 0,    /* TMA ring kernel when the shape allows it, else the generic kernel */
+    PPO_TVF_GENERIC = 1, /* global-memory gather kernel, any shape                            */
+    PPO_TVF_RING = 2     /* TMA ring kernel or PPO_ERR_UNSUPPORTED                            */
+} ppo_tvf_path;
+
+/*
+ * Multi-horizon truncated-return targets [N, A, K].  Replaces rl/returns_truncated.py:623-693
+ * `_calculate_sampled_return_multi_fast` with its helpers `_n_step_estimate` (:558-620) and
+ * `_interpolate` (:142-174); the dispatcher `get_return_estimate` (:10-139) stays in Python and
+ * draws the sample table with the reference's own NumPy RNG calls.
+ *   out[t,a,k] = 1/C * sum_c ( S_n(t,a) + D_n(t,a) * I(V[t+n,a,:], h_k - n) ),  n = min(sample[k,c], h_k, N - t)
+ * value_samples is [N+1, A, V] with a unit-stride V axis; element (t, a, j) at
+ * value_samples[t * vs_row_stride + a * vs_env_stride + j].  dones must be a 0/1 mask.
+ * `stats` (PPO_STATS_LEN doubles, may be NULL) receives count / sum / sumsq / min / max of the
+ * longest horizon out[:, :, K-1] in the ADV_* slots (rl/rollout.py:1270 `tvf_return_ext`); it needs
+ * `workspace` as sized by ppo_tvf_workspace_bytes.
+ */
+int64_t ppo_tvf_workspace_bytes(int64_t steps, int64_t envs);
+int ppo_tvf_targets(const float* rewards, int64_t reward_row_stride,
+                    const void* dones, int done_kind, int64_t done_row_stride,
+                    const float* value_samples, int64_t vs_row_stride, int64_t vs_env_stride,
+                    int64_t steps, int64_t envs, int64_t n_req, int64_t n_val,
+                    const ppo_tvf_tables* tables, int path,
+                    float* out, double* stats, void* workspace, int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPO_B200_H */

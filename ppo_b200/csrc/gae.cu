@@ -1,0 +1,531 @@
+// Reverse-time scans over [N, A] rollout buffers: GAE + TD(lambda), bootstrapped discounted
+// returns, advantage moments and normalisation.
+//
+// Replaces rl/returns.py:7-67 and the inline normalisation at rl/rollout.py:1887-1897 of the
+// reference (see include/ppo_b200.h for the per-entry-point citations).
+//
+// Parallel structure.  The recurrences are affine in the carried value,
+//     x_t = b_t + c_t * x_{t+1},
+// and affine maps compose associatively, so the time axis is split as well as the env axis:
+// a CTA owns 32 adjacent envs (one per lane, so every global access is a 128-byte coalesced
+// row segment) and 16 time chunks (one per warp).  Each thread (1) loads its chunk once into
+// registers and composes it into one map (B, C), (2) exchanges maps through shared memory and
+// folds the later chunks into its carry-in, (3) replays its chunk from registers and streams the
+// outputs.  HBM traffic is exactly the algorithmic bytes: every input is read once, every
+// output written once.
+//
+// Numerics.  With boolean terminals the reference carries float64 and rounds only the stored
+// row (rl/returns.py:26-28); the scan below carries float64 as well and performs the replay with
+// the reference's operation order and explicit (non-fused) roundings, so outputs differ from the
+// reference only through the re-associated carry-in of a chunk (a few float64 ulps before the
+// float32 rounding).
+#include "common.cuh"
+
+namespace ppo {
+
+constexpr int kScanWarps = 16;  // time chunks per CTA, one warp each
+constexpr int kScanThreads = kScanWarps * 32;
+constexpr int kCachedLen = 16;  // longest chunk kept in registers
+
+struct ScanStatsIo {
+    double* stats;         // final record (PPO_STATS_LEN) or nullptr
+    double* partials;      // [grid, PPO_STATS_LEN]
+    unsigned int* ticket;  // zero on entry, zero again on exit
+};
+
+struct GaeParams {
+    const float* rewards;
+    int64_t r_rs;
+    const float* values;
+    int64_t v_rs, v_es;
+    const float* final_value;
+    int64_t f_es;
+    const void* dones;
+    int64_t d_rs;
+    int64_t steps, envs;
+    double gl_adv, gl_ret;  // gamma * lamb (float64 product, rl/returns.py:27)
+    float gamma32;          // gamma as the float32 scalar of `gamma * value_next_t` (rl/returns.py:26)
+    float* adv;
+    float* ret;
+    int chunk_len;
+    ScanStatsIo io;
+};
+
+struct ThreadStats {
+    double n = 0, s_adv = 0, q_adv = 0, s_ret = 0, q_ret = 0;
+    float mn_adv = INFINITY, mx_adv = -INFINITY, mn_ret = INFINITY, mx_ret = -INFINITY;
+    __device__ __forceinline__ void add(float a, float r) {
+        n += 1.0;
+        s_adv += a;
+        q_adv += static_cast<double>(a) * a;
+        s_ret += r;
+        q_ret += static_cast<double>(r) * r;
+        mn_adv = fminf(mn_adv, a);
+        mx_adv = fmaxf(mx_adv, a);
+        mn_ret = fminf(mn_ret, r);
+        mx_ret = fmaxf(mx_ret, r);
+    }
+};
+
+// Combine per-thread statistics into one record per CTA, then let the last CTA to finish fold all
+// CTA records in index order (deterministic, no float atomics) into io.stats.
+__device__ void publish_stats(const ThreadStats& ts, const ScanStatsIo& io, double (*red)[PPO_STATS_LEN]) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    double n = warp_sum_f64(ts.n);
+    double s_adv = warp_sum_f64(ts.s_adv), q_adv = warp_sum_f64(ts.q_adv);
+    double s_ret = warp_sum_f64(ts.s_ret), q_ret = warp_sum_f64(ts.q_ret);
+    float mn_adv = warp_min_f32(ts.mn_adv), mx_adv = warp_max_f32(ts.mx_adv);
+    float mn_ret = warp_min_f32(ts.mn_ret), mx_ret = warp_max_f32(ts.mx_ret);
+    if (lane == 0) {
+        red[w][PPO_STAT_COUNT] = n;
+        red[w][PPO_STAT_ADV_SUM] = s_adv;
+        red[w][PPO_STAT_ADV_SUMSQ] = q_adv;
+        red[w][PPO_STAT_ADV_MIN] = mn_adv;
+        red[w][PPO_STAT_ADV_MAX] = mx_adv;
+        red[w][PPO_STAT_RET_SUM] = s_ret;
+        red[w][PPO_STAT_RET_SUMSQ] = q_ret;
+        red[w][PPO_STAT_RET_MIN] = mn_ret;
+        red[w][PPO_STAT_RET_MAX] = mx_ret;
+    }
+    __syncthreads();
+    __shared__ bool is_last;
+    if (threadIdx.x < PPO_STATS_LEN) {
+        const int j = threadIdx.x;
+        const bool is_min = (j == PPO_STAT_ADV_MIN || j == PPO_STAT_RET_MIN);
+        const bool is_max = (j == PPO_STAT_ADV_MAX || j == PPO_STAT_RET_MAX);
+        double acc = 0;
+        if (j <= PPO_STAT_RET_MAX) {
+            acc = red[0][j];
+            for (int i = 1; i < nwarps; ++i) {
+                const double x = red[i][j];
+                acc = is_min ? fmin(acc, x) : is_max ? fmax(acc, x) : acc + x;
+            }
+        }
+        io.partials[static_cast<int64_t>(blockIdx.x) * PPO_STATS_LEN + j] = acc;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(io.ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // Last CTA: fold all CTA records.  Warp j handles slot j; lanes stride over the CTAs and are
+    // combined by a fixed shuffle tree, so the result does not depend on scheduling.
+    if (w < PPO_STATS_LEN) {
+        const int j = w;
+        const bool is_min = (j == PPO_STAT_ADV_MIN || j == PPO_STAT_RET_MIN);
+        const bool is_max = (j == PPO_STAT_ADV_MAX || j == PPO_STAT_RET_MAX);
+        double acc = is_min ? INFINITY : is_max ? -INFINITY : 0.0;
+        if (j <= PPO_STAT_RET_MAX) {
+            for (unsigned int b = lane; b < gridDim.x; b += 32) {
+                const double x = __ldcg(io.partials + static_cast<int64_t>(b) * PPO_STATS_LEN + j);
+                acc = is_min ? fmin(acc, x) : is_max ? fmax(acc, x) : acc + x;
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const double x = shfl_down_f64(acc, d);
+                acc = is_min ? fmin(acc, x) : is_max ? fmax(acc, x) : acc + x;
+            }
+        } else {
+            acc = 0.0;
+        }
+        if (lane == 0) io.stats[j] = acc;
+    }
+    if (threadIdx.x == 0) *io.ticket = 0u;
+}
+
+template <int DONE, bool CACHED, bool STATS>
+__global__ void __launch_bounds__(kScanThreads) gae_kernel(const GaeParams p) {
+    __shared__ double sB[2][kScanWarps][32];
+    __shared__ double sC[2][kScanWarps][32];
+    __shared__ double red[kScanWarps][PPO_STATS_LEN];
+
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t env = static_cast<int64_t>(blockIdx.x) * 32 + lane;
+    const bool live = env < p.envs;
+    const int64_t lo = static_cast<int64_t>(w) * p.chunk_len;
+    const int64_t hi = min(p.steps, lo + p.chunk_len);
+    const int len = hi > lo ? static_cast<int>(hi - lo) : 0;  // warp-uniform
+
+    const float* rp = p.rewards + lo * p.r_rs + env;
+    const float* vp = p.values + lo * p.v_rs + env * p.v_es;
+    const int64_t dbase = lo * p.d_rs + env;
+
+    float r[kCachedLen], v[kCachedLen], al[kCachedLen];
+    float vtop = 0.f;  // value following the last step of this chunk
+    if (live && len > 0) {
+        vtop = (hi == p.steps) ? p.final_value[env * p.f_es] : p.values[hi * p.v_rs + env * p.v_es];
+    }
+    if (CACHED) {
+#pragma unroll
+        for (int i = 0; i < kCachedLen; ++i) {
+            r[i] = 0.f, v[i] = 0.f, al[i] = 1.f;
+            if (live && i < len) {
+                r[i] = __ldg(rp + i * p.r_rs);
+                v[i] = __ldg(vp + i * p.v_rs);
+                al[i] = static_cast<float>(alive_of<DONE>(p.dones, dbase + i * p.d_rs));
+            }
+        }
+    }
+
+    // one step of both recurrences, reference operation order (rl/returns.py:26-28)
+    auto step = [&](float rr, float vv, float vn, double nt, double& x_adv, double& x_ret) {
+        const double boot = static_cast<double>(__fmul_rn(p.gamma32, vn)) * nt;
+        const double delta = __dsub_rn(__dadd_rn(static_cast<double>(rr), boot), static_cast<double>(vv));
+        x_adv = __dadd_rn(delta, __dmul_rn(__dmul_rn(p.gl_adv, nt), x_adv));
+        x_ret = __dadd_rn(delta, __dmul_rn(__dmul_rn(p.gl_ret, nt), x_ret));
+    };
+
+    // ---- phase 1: compose the chunk into x_lo = B + C * x_in
+    double b_adv = 0, c_adv = 1, b_ret = 0, c_ret = 1;
+    if (live) {
+        if (CACHED) {
+#pragma unroll
+            for (int i = kCachedLen - 1; i >= 0; --i) {
+                if (i < len) {
+                    const float vn = (i == len - 1) ? vtop : v[(i + 1) % kCachedLen];
+                    const double nt = al[i];
+                    step(r[i], v[i], vn, nt, b_adv, b_ret);
+                    c_adv *= p.gl_adv * nt;
+                    c_ret *= p.gl_ret * nt;
+                }
+            }
+        } else {
+            float vn = vtop;
+            for (int i = len - 1; i >= 0; --i) {
+                const float rr = __ldg(rp + i * p.r_rs), vv = __ldg(vp + i * p.v_rs);
+                const double nt = alive_of<DONE>(p.dones, dbase + i * p.d_rs);
+                step(rr, vv, vn, nt, b_adv, b_ret);
+                c_adv *= p.gl_adv * nt;
+                c_ret *= p.gl_ret * nt;
+                vn = vv;
+            }
+        }
+    }
+    sB[0][w][lane] = b_adv, sC[0][w][lane] = c_adv;
+    sB[1][w][lane] = b_ret, sC[1][w][lane] = c_ret;
+    __syncthreads();
+
+    // ---- phase 2: carry-in = later chunks applied to A_N = 0
+    double x_adv = 0, x_ret = 0;
+    for (int j = kScanWarps - 1; j > w; --j) {
+        x_adv = sB[0][j][lane] + sC[0][j][lane] * x_adv;
+        x_ret = sB[1][j][lane] + sC[1][j][lane] * x_ret;
+    }
+
+    // ---- phase 3: replay and stream the outputs
+    ThreadStats ts;
+    if (live) {
+        float* ap = p.adv ? p.adv + lo * p.envs + env : nullptr;
+        float* tp = p.ret ? p.ret + lo * p.envs + env : nullptr;
+        if (CACHED) {
+#pragma unroll
+            for (int i = kCachedLen - 1; i >= 0; --i) {
+                if (i < len) {
+                    const float vn = (i == len - 1) ? vtop : v[(i + 1) % kCachedLen];
+                    step(r[i], v[i], vn, al[i], x_adv, x_ret);
+                    const float a = static_cast<float>(x_adv);
+                    const float t = __fadd_rn(static_cast<float>(x_ret), v[i]);  // rl/returns.py:66-67
+                    if (ap) store_stream(ap + i * p.envs, a);
+                    if (tp) store_stream(tp + i * p.envs, t);
+                    if (STATS) ts.add(a, t);
+                }
+            }
+        } else {
+            float vn = vtop;
+            for (int i = len - 1; i >= 0; --i) {
+                const float rr = __ldg(rp + i * p.r_rs), vv = __ldg(vp + i * p.v_rs);
+                const double nt = alive_of<DONE>(p.dones, dbase + i * p.d_rs);
+                step(rr, vv, vn, nt, x_adv, x_ret);
+                const float a = static_cast<float>(x_adv);
+                const float t = __fadd_rn(static_cast<float>(x_ret), vv);
+                if (ap) store_stream(ap + i * p.envs, a);
+                if (tp) store_stream(tp + i * p.envs, t);
+                if (STATS) ts.add(a, t);
+                vn = vv;
+            }
+        }
+    }
+    if (STATS) publish_stats(ts, p.io, red);
+}
+
+// ------------------------------------------------------------------------------------------
+// Bootstrapped discounted returns (rl/returns.py:32-55): R_t = r_t + (R_{t+1} * g_t) * (1 - done_t).
+struct ReturnsParams {
+    const float* rewards;
+    int64_t r_rs;
+    const void* dones;
+    int64_t d_rs;
+    const float* final_value;
+    int64_t f_es;
+    const float* gamma_array;  // nullptr: scalar
+    int64_t g_rs;
+    float gamma32;
+    int64_t steps, envs;
+    float* out;
+    int chunk_len;
+};
+
+template <int DONE>
+__global__ void __launch_bounds__(kScanThreads) returns_kernel(const ReturnsParams p) {
+    __shared__ double sB[kScanWarps][32];
+    __shared__ double sC[kScanWarps][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t env = static_cast<int64_t>(blockIdx.x) * 32 + lane;
+    const bool live = env < p.envs;
+    const int64_t lo = static_cast<int64_t>(w) * p.chunk_len;
+    const int64_t hi = min(p.steps, lo + p.chunk_len);
+    const int len = hi > lo ? static_cast<int>(hi - lo) : 0;
+    const bool top = (hi == p.steps) && len > 0;  // the chunk that starts from the final value
+
+    const float* rp = p.rewards + lo * p.r_rs + env;
+    const float* gp = p.gamma_array ? p.gamma_array + lo * p.g_rs + env : nullptr;
+    const int64_t dbase = lo * p.d_rs + env;
+    const float fin = (live && top) ? p.final_value[env * p.f_es] : 0.f;
+
+    // The reference's first product is float32 * float32 (final estimate times a float32 gamma
+    // row, rl/returns.py:53); every later one is float64 * float32.
+    auto run = [&](double x, bool from_final, bool store) {
+        for (int i = len - 1; i >= 0; --i) {
+            const float g = gp ? __ldg(gp + i * p.g_rs) : p.gamma32;
+            const double nt = alive_of<DONE>(p.dones, dbase + i * p.d_rs);
+            const double prod = (from_final && i == len - 1)
+                                    ? static_cast<double>(__fmul_rn(static_cast<float>(x), g))
+                                    : __dmul_rn(x, static_cast<double>(g));
+            x = __dadd_rn(static_cast<double>(__ldg(rp + i * p.r_rs)), __dmul_rn(prod, nt));
+            if (store) store_stream(p.out + (lo + i) * p.envs + env, static_cast<float>(x));
+        }
+        return x;
+    };
+
+    double b = 0, c = 1;
+    if (live && len > 0) {
+        if (top) {
+            b = run(static_cast<double>(fin), true, false);
+            c = 0;
+        } else {
+            for (int i = len - 1; i >= 0; --i) {
+                const float g = gp ? __ldg(gp + i * p.g_rs) : p.gamma32;
+                const double k = static_cast<double>(g) * alive_of<DONE>(p.dones, dbase + i * p.d_rs);
+                b = static_cast<double>(__ldg(rp + i * p.r_rs)) + k * b;
+                c *= k;
+            }
+        }
+    }
+    sB[w][lane] = b, sC[w][lane] = c;
+    __syncthreads();
+    if (!live || len == 0) return;
+    if (top) {
+        run(static_cast<double>(fin), true, true);
+    } else {
+        double x = 0;
+        for (int j = kScanWarps - 1; j > w; --j) x = sB[j][lane] + sC[j][lane] * x;
+        run(x, false, true);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Moments of a float32 vector (same record layout, ADV_* slots) and the normalisation itself.
+struct MomentsParams {
+    const float* x;
+    int64_t count;
+    ScanStatsIo io;
+};
+
+__global__ void __launch_bounds__(512) moments_kernel(const MomentsParams p) {
+    __shared__ double red[16][PPO_STATS_LEN];
+    ThreadStats ts;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.count; i += stride) {
+        ts.add(__ldg(p.x + i), 0.f);
+    }
+    publish_stats(ts, p.io, red);
+}
+
+struct NormParams {
+    const float* x;
+    float* out;
+    int64_t count;
+    const double* stats;
+    float eps;
+    float clip;  // <= 0: no clipping
+};
+
+__device__ __forceinline__ float norm_one(float x, float mean, float denom, float clip) {
+    float y = __fdiv_rn(__fsub_rn(x, mean), denom);  // rl/rollout.py:1891
+    if (clip > 0.f) y = fminf(fmaxf(y, -clip), clip);  // rl/rollout.py:1895-1896
+    return y;
+}
+
+__global__ void __launch_bounds__(256) normalize_kernel(const NormParams p) {
+    const double n = p.stats[PPO_STAT_COUNT];
+    const double mean64 = p.stats[PPO_STAT_ADV_SUM] / n;
+    const double var64 = fmax(p.stats[PPO_STAT_ADV_SUMSQ] / n - mean64 * mean64, 0.0);
+    const float mean = static_cast<float>(mean64);
+    const float denom = __fadd_rn(static_cast<float>(sqrt(var64)), p.eps);
+    const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const bool vec = ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.out)) & 15) == 0;
+    const int64_t n4 = vec ? p.count / 4 : 0;
+    for (int64_t i = tid; i < n4; i += stride) {
+        float4 q = __ldg(reinterpret_cast<const float4*>(p.x) + i);
+        q.x = norm_one(q.x, mean, denom, p.clip);
+        q.y = norm_one(q.y, mean, denom, p.clip);
+        q.z = norm_one(q.z, mean, denom, p.clip);
+        q.w = norm_one(q.w, mean, denom, p.clip);
+        __stcs(reinterpret_cast<float4*>(p.out) + i, q);
+    }
+    for (int64_t i = n4 * 4 + tid; i < p.count; i += stride) {
+        p.out[i] = norm_one(__ldg(p.x + i), mean, denom, p.clip);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+
+static int64_t scan_grid(int64_t envs) { return (envs + 31) / 32; }
+
+static int split_workspace(void* workspace, int64_t bytes, int64_t blocks, ScanStatsIo* io) {
+    const int64_t need = 256 + blocks * PPO_STATS_LEN * static_cast<int64_t>(sizeof(double));
+    if (workspace == nullptr || bytes < need) {
+        set_error("workspace of %lld bytes required, got %lld", (long long)need, (long long)bytes);
+        return PPO_ERR_WORKSPACE;
+    }
+    io->ticket = static_cast<unsigned int*>(workspace);
+    io->partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
+    return PPO_OK;
+}
+
+constexpr int kMomentsMaxBlocks = 1184;  // 8 CTAs of 512 threads per SM would not fit; 148 * 8 is the cap we size for
+
+}  // namespace ppo
+
+using namespace ppo;
+
+extern "C" int64_t ppo_gae_workspace_bytes(int64_t envs) {
+    int64_t blocks = scan_grid(envs > 0 ? envs : 0);
+    if (blocks < kMomentsMaxBlocks) blocks = kMomentsMaxBlocks;
+    return 256 + blocks * PPO_STATS_LEN * static_cast<int64_t>(sizeof(double));
+}
+
+extern "C" int ppo_gae(const float* rewards, int64_t reward_row_stride, const float* values,
+                       int64_t value_row_stride, int64_t value_env_stride, const float* final_value,
+                       int64_t final_env_stride, const void* dones, int done_kind, int64_t done_row_stride,
+                       int64_t steps, int64_t envs, double gamma, double lamb_adv, double lamb_ret,
+                       float* adv_out, float* ret_out, double* stats, void* workspace,
+                       int64_t workspace_bytes, void* stream) {
+    PPO_REQUIRE(steps >= 0 && envs >= 0, "ppo_gae: negative shape [%lld, %lld]", (long long)steps, (long long)envs);
+    PPO_REQUIRE(done_kind == PPO_DONE_NONE || done_kind == PPO_DONE_U8 || done_kind == PPO_DONE_F32,
+                "ppo_gae: unknown done_kind %d", done_kind);
+    if (steps == 0 || envs == 0) {
+        if (stats) PPO_CUDA(cudaMemsetAsync(stats, 0, PPO_STATS_LEN * sizeof(double), (cudaStream_t)stream));
+        return PPO_OK;
+    }
+    PPO_REQUIRE(rewards && values && final_value, "ppo_gae: null input pointer");
+    PPO_REQUIRE(done_kind == PPO_DONE_NONE || dones != nullptr, "ppo_gae: dones is null but done_kind=%d", done_kind);
+    PPO_REQUIRE(envs <= (int64_t)INT32_MAX * 32, "ppo_gae: too many envs");
+
+    GaeParams p{};
+    p.rewards = rewards, p.r_rs = reward_row_stride;
+    p.values = values, p.v_rs = value_row_stride, p.v_es = value_env_stride;
+    p.final_value = final_value, p.f_es = final_env_stride;
+    p.dones = dones, p.d_rs = done_row_stride;
+    p.steps = steps, p.envs = envs;
+    p.gl_adv = gamma * lamb_adv, p.gl_ret = gamma * lamb_ret;
+    p.gamma32 = static_cast<float>(gamma);
+    p.adv = adv_out, p.ret = ret_out;
+    p.chunk_len = static_cast<int>((steps + kScanWarps - 1) / kScanWarps);
+    const int64_t blocks = scan_grid(envs);
+    const bool want_stats = stats != nullptr;
+    if (want_stats) {
+        int rc = split_workspace(workspace, workspace_bytes, blocks, &p.io);
+        if (rc != PPO_OK) return rc;
+        p.io.stats = stats;
+    }
+    const bool cached = p.chunk_len <= kCachedLen;
+    dim3 grid(static_cast<unsigned>(blocks)), block(kScanThreads);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+#define PPO_LAUNCH_GAE(D)                                                           \
+    do {                                                                            \
+        if (cached && want_stats) gae_kernel<D, true, true><<<grid, block, 0, s>>>(p);       \
+        else if (cached) gae_kernel<D, true, false><<<grid, block, 0, s>>>(p);       \
+        else if (want_stats) gae_kernel<D, false, true><<<grid, block, 0, s>>>(p);   \
+        else gae_kernel<D, false, false><<<grid, block, 0, s>>>(p);                  \
+    } while (0)
+    if (done_kind == PPO_DONE_U8) PPO_LAUNCH_GAE(PPO_DONE_U8);
+    else if (done_kind == PPO_DONE_F32) PPO_LAUNCH_GAE(PPO_DONE_F32);
+    else PPO_LAUNCH_GAE(PPO_DONE_NONE);
+#undef PPO_LAUNCH_GAE
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+extern "C" int ppo_discounted_returns(const float* rewards, int64_t reward_row_stride, const void* dones,
+                                      int done_kind, int64_t done_row_stride, const float* final_value,
+                                      int64_t final_env_stride, double gamma, const float* gamma_array,
+                                      int64_t gamma_row_stride, int64_t steps, int64_t envs, float* out,
+                                      void* stream) {
+    PPO_REQUIRE(steps >= 0 && envs >= 0, "ppo_discounted_returns: negative shape");
+    PPO_REQUIRE(done_kind == PPO_DONE_NONE || done_kind == PPO_DONE_U8 || done_kind == PPO_DONE_F32,
+                "ppo_discounted_returns: unknown done_kind %d", done_kind);
+    if (steps == 0 || envs == 0) return PPO_OK;
+    PPO_REQUIRE(rewards && final_value && out, "ppo_discounted_returns: null pointer");
+    PPO_REQUIRE(done_kind == PPO_DONE_NONE || dones != nullptr, "ppo_discounted_returns: dones is null");
+    ReturnsParams p{};
+    p.rewards = rewards, p.r_rs = reward_row_stride;
+    p.dones = dones, p.d_rs = done_row_stride;
+    p.final_value = final_value, p.f_es = final_env_stride;
+    p.gamma_array = gamma_array, p.g_rs = gamma_row_stride;
+    p.gamma32 = static_cast<float>(gamma);
+    p.steps = steps, p.envs = envs, p.out = out;
+    p.chunk_len = static_cast<int>((steps + kScanWarps - 1) / kScanWarps);
+    dim3 grid(static_cast<unsigned>(scan_grid(envs))), block(kScanThreads);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (done_kind == PPO_DONE_U8) returns_kernel<PPO_DONE_U8><<<grid, block, 0, s>>>(p);
+    else if (done_kind == PPO_DONE_F32) returns_kernel<PPO_DONE_F32><<<grid, block, 0, s>>>(p);
+    else returns_kernel<PPO_DONE_NONE><<<grid, block, 0, s>>>(p);
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+extern "C" int ppo_moments(const float* x, int64_t count, double* stats, void* workspace,
+                           int64_t workspace_bytes, void* stream) {
+    PPO_REQUIRE(count >= 0 && stats != nullptr, "ppo_moments: bad arguments");
+    PPO_REQUIRE(count == 0 || x != nullptr, "ppo_moments: null input");
+    int64_t blocks = (count + 512 * 8 - 1) / (512 * 8);
+    if (blocks < 1) blocks = 1;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 2;
+    if (blocks > cap) blocks = cap;
+    if (blocks > kMomentsMaxBlocks) blocks = kMomentsMaxBlocks;
+    MomentsParams p{};
+    p.x = x, p.count = count;
+    int rc = split_workspace(workspace, workspace_bytes, blocks, &p.io);
+    if (rc != PPO_OK) return rc;
+    p.io.stats = stats;
+    moments_kernel<<<static_cast<unsigned>(blocks), 512, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+extern "C" int ppo_adv_normalize(const float* adv, int64_t count, const double* stats, double eps, double clip,
+                                 float* out, void* stream) {
+    PPO_REQUIRE(count >= 0, "ppo_adv_normalize: negative count");
+    if (count == 0) return PPO_OK;
+    PPO_REQUIRE(adv && out && stats, "ppo_adv_normalize: null pointer");
+    NormParams p{};
+    p.x = adv, p.out = out, p.count = count, p.stats = stats;
+    p.eps = static_cast<float>(eps);
+    p.clip = clip > 0 ? static_cast<float>(clip) : 0.f;
+    int64_t blocks = (count / 4 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+    if (blocks > cap) blocks = cap;
+    normalize_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}

@@ -1,0 +1,281 @@
+// TVF multi-horizon truncated-return targets: entry point and the generic (any-shape) kernel.
+//
+// Replaces rl/returns_truncated.py:623-693 (+ :558-620, :142-174) of the reference.
+//   out[t,a,k] = 1/C * sum_c ( S_n(t,a) + D_n(t,a) * I(V[t+n,a,:], h_k - n) ),  n = min(sample[k,c], h_k, N - t)
+//
+// Decomposition used by both kernels (DESIGN.md "TVF targets"):
+//  * D_n(t,a) = G[n] when no terminal occurs in steps t..t+n-1, else 0, where G[n] is the reference's
+//    float32 running product of gamma -- identical for every (t, a), so it is a host table and the
+//    only per-(t,a) state is nd(t,a), the distance to the first terminal at or after t;
+//  * S_n(t,a) is a prefix sum over i < n of float32(r[t+i] * D_i(t,a)) accumulated in float32 in
+//    forward order exactly like rl/returns_truncated.py:668; one row P[t][0..nmax] per (t,a) is built
+//    once and shared by all K horizons;
+//  * per (t,a,k) the (up to C) distinct clamped n-steps n' = min(sample, h_k) come from the host
+//    entry table with their slots / weights; entries with n' > min(N - t, nd) collapse into a single
+//    shared term (the episode ended: no bootstrap; or the rollout ended: bootstrap from row N).
+#include "tvf_common.cuh"
+
+namespace ppo {
+
+int launch_tvf_ring(const TvfParams& p, cudaStream_t stream, bool probe_only);  // tvf_ring.cu
+
+// ------------------------------------------------------------------------------------------
+// Generic kernel: one CTA per (env, chunk of TC time rows); value rows are gathered from global
+// memory (L1/L2 cached).  Works for any N, A, K, V, C; used when the ring kernel's shape
+// constraints do not hold.
+constexpr int kGenThreads = 256;
+
+__global__ void __launch_bounds__(kGenThreads) tvf_generic_kernel(const TvfParams p, int tc, int n_chunks) {
+    extern __shared__ float smem[];
+    const int nmax = p.tab.nmax;
+    const int pstride = nmax + 1;
+    float* P = smem;                               // [tc][nmax + 1]
+    float* rs = P + static_cast<size_t>(tc) * pstride;  // [tc + nmax]
+    int* nd = reinterpret_cast<int*>(rs + tc + nmax);   // [tc]
+    unsigned char* ds = reinterpret_cast<unsigned char*>(nd + tc);  // [tc + nmax]
+
+    const int64_t env = blockIdx.x / n_chunks;
+    const int t0 = static_cast<int>(blockIdx.x % n_chunks) * tc;
+    const int N = p.steps;
+    const int rows = min(tc, N - t0);
+    const int span = min(rows + nmax, N - t0);  // reward rows t0 .. t0 + span - 1
+
+    for (int i = threadIdx.x; i < span; i += blockDim.x) {
+        rs[i] = __ldg(p.rewards + static_cast<int64_t>(t0 + i) * p.r_rs + env);
+        ds[i] = done_at(p.dones, p.done_kind, static_cast<int64_t>(t0 + i) * p.d_rs + env) ? 1 : 0;
+    }
+    __syncthreads();
+
+    // prefix rows, one thread per time row (sequential float32 accumulation, reference order)
+    if (threadIdx.x < rows) {
+        const int tl = threadIdx.x;
+        const int lim = min(nmax, N - (t0 + tl));
+        float* row = P + static_cast<size_t>(tl) * pstride;
+        float s = 0.f;
+        bool alive = true;
+        int first_done = kNoDone;
+        row[0] = 0.f;
+        for (int i = 0; i < lim; ++i) {
+            const float disc = alive ? __ldg(p.tab.gpow + i) : 0.f;
+            s = __fadd_rn(s, __fmul_rn(rs[tl + i], disc));
+            row[i + 1] = s;
+            if (alive && ds[tl + i]) {
+                alive = false;
+                first_done = i;
+            }
+        }
+        nd[tl] = first_done;
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int K = p.n_req;
+    const int E = p.tab.n_entries;
+    for (int tl = warp; tl < rows; tl += nwarps) {
+        const int t = t0 + tl;
+        const int m = N - t;                 // steps left in the rollout
+        const int ndt = nd[tl];
+        const int lim = min(m, ndt);         // largest n that is alive and inside the rollout
+        const float* row = P + static_cast<size_t>(tl) * pstride;
+        const float* vbase = p.vs + static_cast<int64_t>(t) * p.vs_rs + env * p.vs_es;
+        for (int k = lane; k < K; k += 32) {
+            float acc = 0.f, rest = 0.f;
+            for (int e = 0; e < E; ++e) {
+                const float cnt = __ldg(p.tab.ent_cnt + e * K + k);
+                if (cnt == 0.f) break;  // entries are packed to the front
+                const int n = __ldg(p.tab.ent_n + e * K + k);
+                if (n <= lim) {
+                    const int idx = __ldg(p.tab.ent_idx + e * K + k);
+                    const float* vr = vbase + static_cast<int64_t>(n) * p.vs_rs;
+                    const float boot = lerp2(__ldg(vr + (idx & 0xffff)), __ldg(vr + (idx >> 16)),
+                                             __ldg(p.tab.ent_wlo + e * K + k), __ldg(p.tab.ent_whi + e * K + k));
+                    const float term = __fadd_rn(row[n], __fmul_rn(boot, __ldg(p.tab.ent_g + e * K + k)));
+                    acc = fmaf(cnt, term, acc);
+                } else {
+                    rest += cnt;
+                }
+            }
+            if (rest > 0.f) {
+                float term;
+                if (ndt < m) {
+                    term = row[ndt + 1];  // episode ended inside the window: D = 0, S stops after the terminal step
+                } else {
+                    // rollout ended first: n = N - t, bootstrap from the final row (rl/returns_truncated.py:610-614)
+                    const int idx = __ldg(p.tab.tail_idx + m * K + k);
+                    const float* vr = p.vs + static_cast<int64_t>(N) * p.vs_rs + env * p.vs_es;
+                    const float boot = lerp2(__ldg(vr + (idx & 0xffff)), __ldg(vr + (idx >> 16)),
+                                             __ldg(p.tab.tail_wlo + m * K + k), __ldg(p.tab.tail_whi + m * K + k));
+                    term = __fadd_rn(row[m], __fmul_rn(boot, __ldg(p.tab.gpow + m)));
+                }
+                acc = fmaf(rest, term, acc);
+            }
+            p.out[(static_cast<int64_t>(t) * p.envs + env) * K + k] = acc * p.tab.inv_c;
+        }
+    }
+}
+
+static int launch_generic(const TvfParams& p, cudaStream_t stream) {
+    const int nmax = p.tab.nmax;
+    int max_smem = 0, dev = 0;
+    PPO_CUDA(cudaGetDevice(&dev));
+    PPO_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    auto bytes_for = [&](int tc) {
+        return static_cast<size_t>(tc) * (nmax + 1) * 4 + static_cast<size_t>(tc + nmax) * 5 + tc * 4 + 16;
+    };
+    int tc = 32;
+    const size_t budget = static_cast<size_t>(max_smem) < (96u << 10) ? max_smem : (96u << 10);
+    while (tc > 1 && bytes_for(tc) > budget) tc >>= 1;
+    if (bytes_for(tc) > static_cast<size_t>(max_smem)) {
+        set_error("ppo_tvf_targets: n-step %d needs %zu bytes of shared memory per CTA", nmax, bytes_for(tc));
+        return PPO_ERR_UNSUPPORTED;
+    }
+    if (tc > p.steps) tc = p.steps;
+    const int n_chunks = (p.steps + tc - 1) / tc;
+    const int64_t blocks = p.envs * n_chunks;
+    if (blocks > INT32_MAX) {
+        set_error("ppo_tvf_targets: grid of %lld CTAs is too large", (long long)blocks);
+        return PPO_ERR_UNSUPPORTED;
+    }
+    const size_t smem = bytes_for(tc);
+    PPO_CUDA(cudaFuncSetAttribute(tvf_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    tvf_generic_kernel<<<static_cast<unsigned>(blocks), kGenThreads, smem, stream>>>(p, tc, n_chunks);
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+// last-horizon statistics (rl/rollout.py:1270): strided read of out[:, :, K-1]
+struct LastHorizonParams {
+    const float* out;
+    int64_t rows;  // N * A
+    int64_t K;
+    double* stats;
+    double* partials;
+    unsigned int* ticket;
+};
+
+__global__ void __launch_bounds__(512) tvf_last_horizon_stats_kernel(const LastHorizonParams p) {
+    __shared__ double red[16][4];
+    __shared__ bool is_last;
+    double n = 0, s = 0, q = 0;
+    float mn = INFINITY, mx = -INFINITY;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.rows; i += stride) {
+        const float x = __ldg(p.out + i * p.K + (p.K - 1));
+        n += 1.0, s += x, q += static_cast<double>(x) * x;
+        mn = fminf(mn, x), mx = fmaxf(mx, x);
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    n = warp_sum_f64(n), s = warp_sum_f64(s), q = warp_sum_f64(q);
+    mn = warp_min_f32(mn), mx = warp_max_f32(mx);
+    __shared__ float redm[16][2];
+    if (lane == 0) red[w][0] = n, red[w][1] = s, red[w][2] = q, redm[w][0] = mn, redm[w][1] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 16; ++i) {
+            n += red[i][0], s += red[i][1], q += red[i][2];
+            mn = fminf(mn, redm[i][0]), mx = fmaxf(mx, redm[i][1]);
+        }
+        double* rec = p.partials + static_cast<int64_t>(blockIdx.x) * 8;
+        rec[0] = n, rec[1] = s, rec[2] = q, rec[3] = mn, rec[4] = mx;
+        __threadfence();
+        is_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (w == 0) {
+        double an = 0, as = 0, aq = 0, amn = INFINITY, amx = -INFINITY;
+        for (unsigned int b = lane; b < gridDim.x; b += 32) {
+            const double* rec = p.partials + static_cast<int64_t>(b) * 8;
+            an += __ldcg(rec), as += __ldcg(rec + 1), aq += __ldcg(rec + 2);
+            amn = fmin(amn, __ldcg(rec + 3)), amx = fmax(amx, __ldcg(rec + 4));
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            an += shfl_down_f64(an, d), as += shfl_down_f64(as, d), aq += shfl_down_f64(aq, d);
+            amn = fmin(amn, shfl_down_f64(amn, d)), amx = fmax(amx, shfl_down_f64(amx, d));
+        }
+        if (lane == 0) {
+            for (int j = 0; j < PPO_STATS_LEN; ++j) p.stats[j] = 0.0;
+            p.stats[PPO_STAT_COUNT] = an;
+            p.stats[PPO_STAT_ADV_SUM] = as;
+            p.stats[PPO_STAT_ADV_SUMSQ] = aq;
+            p.stats[PPO_STAT_ADV_MIN] = amn;
+            p.stats[PPO_STAT_ADV_MAX] = amx;
+            *p.ticket = 0u;
+        }
+    }
+}
+
+constexpr int kStatsBlocks = 296;
+
+}  // namespace ppo
+
+using namespace ppo;
+
+extern "C" int64_t ppo_tvf_workspace_bytes(int64_t steps, int64_t envs) {
+    (void)steps;
+    (void)envs;
+    return 256 + static_cast<int64_t>(kStatsBlocks) * 8 * sizeof(double);
+}
+
+extern "C" int ppo_tvf_targets(const float* rewards, int64_t reward_row_stride, const void* dones, int done_kind,
+                               int64_t done_row_stride, const float* value_samples, int64_t vs_row_stride,
+                               int64_t vs_env_stride, int64_t steps, int64_t envs, int64_t n_req, int64_t n_val,
+                               const ppo_tvf_tables* tables, int path, float* out, double* stats,
+                               void* workspace, int64_t workspace_bytes, void* stream) {
+    PPO_REQUIRE(steps >= 0 && envs >= 0 && n_req >= 0 && n_val >= 1, "ppo_tvf_targets: bad shape");
+    PPO_REQUIRE(steps < (1 << 24) && n_req < (1 << 20) && n_val < (1 << 16), "ppo_tvf_targets: shape too large");
+    PPO_REQUIRE(done_kind == PPO_DONE_U8 || done_kind == PPO_DONE_F32 || done_kind == PPO_DONE_NONE,
+                "ppo_tvf_targets: unknown done_kind %d", done_kind);
+    PPO_REQUIRE(path == PPO_TVF_AUTO || path == PPO_TVF_GENERIC || path == PPO_TVF_RING,
+                "ppo_tvf_targets: unknown path %d", path);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (steps == 0 || envs == 0 || n_req == 0) {
+        if (stats) PPO_CUDA(cudaMemsetAsync(stats, 0, PPO_STATS_LEN * sizeof(double), s));
+        return PPO_OK;
+    }
+    PPO_REQUIRE(rewards && value_samples && out && tables, "ppo_tvf_targets: null pointer");
+    PPO_REQUIRE(done_kind == PPO_DONE_NONE || dones, "ppo_tvf_targets: dones is null");
+    PPO_REQUIRE(tables->n_entries >= 1 && tables->nmax >= 1 && tables->nmax <= steps,
+                "ppo_tvf_targets: tables describe n-steps up to %d for %lld steps", tables->nmax, (long long)steps);
+    PPO_REQUIRE(tables->ent_n && tables->ent_cnt && tables->ent_idx && tables->ent_wlo && tables->ent_whi &&
+                    tables->ent_g && tables->tail_idx && tables->tail_wlo && tables->tail_whi && tables->gpow,
+                "ppo_tvf_targets: null table pointer");
+
+    TvfParams p{};
+    p.rewards = rewards, p.r_rs = reward_row_stride;
+    p.dones = dones, p.d_rs = done_row_stride, p.done_kind = done_kind;
+    p.vs = value_samples, p.vs_rs = vs_row_stride, p.vs_es = vs_env_stride;
+    p.steps = static_cast<int>(steps), p.envs = envs;
+    p.n_req = static_cast<int>(n_req), p.n_val = static_cast<int>(n_val);
+    p.tab = *tables;
+    p.out = out;
+
+    int rc = PPO_ERR_UNSUPPORTED;
+    if (path != PPO_TVF_GENERIC) {
+        rc = launch_tvf_ring(p, s, false);
+        if (rc == PPO_ERR_UNSUPPORTED && path == PPO_TVF_AUTO) rc = launch_generic(p, s);
+    } else {
+        rc = launch_generic(p, s);
+    }
+    if (rc != PPO_OK) return rc;
+
+    if (stats) {
+        const int64_t need = ppo_tvf_workspace_bytes(steps, envs);
+        if (!workspace || workspace_bytes < need) {
+            set_error("ppo_tvf_targets: workspace of %lld bytes required", (long long)need);
+            return PPO_ERR_WORKSPACE;
+        }
+        LastHorizonParams q{};
+        q.out = out, q.rows = steps * envs, q.K = n_req, q.stats = stats;
+        q.ticket = static_cast<unsigned int*>(workspace);
+        q.partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
+        int64_t blocks = (q.rows + 511) / 512;
+        if (blocks > kStatsBlocks) blocks = kStatsBlocks;
+        tvf_last_horizon_stats_kernel<<<static_cast<unsigned>(blocks), 512, 0, s>>>(q);
+        PPO_CUDA(cudaGetLastError());
+    }
+    return PPO_OK;
+}

@@ -1,0 +1,191 @@
+"""Drop-in for the reference's ``rl/returns_truncated.py``: same dispatcher signature, same NumPy RNG
+calls for the n-step sample table, targets computed by the sm_100a kernels behind ``ppo_tvf_targets``.
+
+Reference semantics kept: NumPy in -> NumPy ``[N, A, K]`` float32 out; ``ValueError`` for an unknown
+distribution / mode (``rl/returns_truncated.py:78,139``); ``AssertionError`` for an n-step outside
+``1..N`` (:597); ``IndexError`` when a bootstrap horizon lies beyond the last value horizon (:157).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _device as dev
+from . import _lib
+from . import _tvf_tables
+
+PATH_AUTO, PATH_GENERIC, PATH_RING = 0, 1, 2
+
+
+class _CTables(ctypes.Structure):
+    _fields_ = [("n_entries", ctypes.c_int32), ("nmax", ctypes.c_int32),
+                ("ent_n", ctypes.c_void_p), ("ent_cnt", ctypes.c_void_p), ("ent_idx", ctypes.c_void_p),
+                ("ent_wlo", ctypes.c_void_p), ("ent_whi", ctypes.c_void_p), ("ent_g", ctypes.c_void_p),
+                ("tail_idx", ctypes.c_void_p), ("tail_wlo", ctypes.c_void_p), ("tail_whi", ctypes.c_void_p),
+                ("gpow", ctypes.c_void_p), ("inv_c", ctypes.c_float)]
+
+
+def _upload_tables(tabs, device):
+    """One packed H2D copy of all tables; returns (ctypes struct, tensor keeping the memory alive)."""
+    parts = [tabs.ent_n, tabs.ent_cnt, tabs.ent_idx, tabs.ent_wlo, tabs.ent_whi, tabs.ent_g,
+             tabs.tail_idx, tabs.tail_wlo, tabs.tail_whi, tabs.gpow]
+    words, offsets = 0, []
+    for a in parts:
+        offsets.append(words)
+        words += (a.size + 3) // 4 * 4  # keep every table 16-byte aligned
+    host = np.zeros(words, dtype=np.int32)
+    for a, off in zip(parts, offsets):
+        host[off:off + a.size] = np.ascontiguousarray(a).reshape(-1).view(np.int32)
+    blob = torch.from_numpy(host).to(device, non_blocking=True)
+    base = blob.data_ptr()
+    c = _CTables()
+    c.n_entries, c.nmax = tabs.n_entries, tabs.nmax
+    names = ["ent_n", "ent_cnt", "ent_idx", "ent_wlo", "ent_whi", "ent_g", "tail_idx", "tail_wlo", "tail_whi", "gpow"]
+    for name, off in zip(names, offsets):
+        setattr(c, name, base + 4 * off)
+    c.inv_c = float(tabs.inv_c)
+    return c, blob
+
+
+def _launch(gamma, rewards, dones, required_horizons, value_sample_horizons, value_samples, n_step_samples,
+            use_log_interpolation, path=PATH_AUTO, with_stats=False):
+    device = dev.require_cuda()
+    lib = _lib.load()
+    np_like = dev.is_numpy_like(rewards)
+    r = dev.env_contiguous(dev.to_device(rewards, torch.float32, device))
+    steps, envs = r.shape
+    req = np.asarray(required_horizons.cpu() if isinstance(required_horizons, torch.Tensor) else required_horizons)
+    vsh = np.asarray(value_sample_horizons.cpu() if isinstance(value_sample_horizons, torch.Tensor)
+                     else value_sample_horizons)
+    n_req, n_val = len(req), len(vsh)
+    vs = dev.to_device(value_samples, torch.float32, device)
+    assert tuple(vs.shape) == (steps + 1, envs, n_val), \
+        f"value_samples must be [N+1, A, V] = {(steps + 1, envs, n_val)}, got {tuple(vs.shape)}"
+    vs = dev.env_contiguous(vs)  # unit stride on the horizon axis (a [..., vh] slice is copied once)
+    d, kind = dev.done_tensor(dones, device)
+    assert d is not None and tuple(d.shape) == (steps, envs), f"dones must be [N, A] = {(steps, envs)}"
+    d = dev.env_contiguous(d)
+
+    tabs = _tvf_tables.build(gamma, steps, req, vsh, n_step_samples, use_log_interpolation)
+    ctab, blob = _upload_tables(tabs, device)
+
+    out = torch.empty((steps, envs, n_req), dtype=torch.float32, device=device)
+    stats = ws = None
+    if with_stats:
+        stats = torch.empty(_lib.STATS_LEN, dtype=torch.float64, device=device)
+        ws = dev.workspace(lib.ppo_tvf_workspace_bytes(steps, envs), device)
+    rc = lib.ppo_tvf_targets(
+        dev.ptr(r), r.stride(0) if steps else 0, dev.ptr(d), kind, d.stride(0) if steps else 0,
+        dev.ptr(vs), vs.stride(0), vs.stride(1) if envs else 0, steps, envs, n_req, n_val,
+        ctypes.byref(ctab), path, dev.ptr(out), dev.ptr(stats),
+        dev.ptr(ws), ws.numel() if ws is not None else 0, dev.stream_ptr())
+    _lib.check(rc, "ppo_tvf_targets")
+    del blob  # same-stream allocator reuse is ordered after the kernel
+    res = dev.like_input(out, np_like)
+    return (res, stats) if with_stats else res
+
+
+def _calculate_sampled_return_multi_fast(gamma: float, rewards, dones, required_horizons, value_sample_horizons,
+                                         value_samples, n_step_samples=None, n_step_list=None,
+                                         use_log_interpolation: bool = False, path=PATH_AUTO):
+    """``[N, A, K]`` targets for a per-horizon sample table ``[K, C]`` or one list shared by all horizons
+    (reference: ``rl/returns_truncated.py:623-693``)."""
+    assert n_step_samples is not None or n_step_list is not None
+    n_req = len(required_horizons)
+    if n_step_list is not None:
+        n_step_samples = np.asarray([list(n_step_list) for _ in range(n_req)])  # :645-646
+    n_step_samples = np.asarray(n_step_samples)
+    assert n_step_samples.ndim == 2 and n_step_samples.shape[0] == n_req
+    return _launch(gamma, rewards, dones, required_horizons, value_sample_horizons, value_samples,
+                   n_step_samples, use_log_interpolation, path)
+
+
+def draw_n_step_samples(distribution, mode, required_horizons, steps, n_step, max_samples, seed=None):
+    """The reference's host-side draw of the n-step table (``rl/returns_truncated.py:60-129``), with the same
+    global ``np.random`` calls in the same order so that a seed reproduces the reference's table.
+    Returns a ``[K, C]`` int table, or for ``mode == "full"`` the normalised float32 weights ``[N]``."""
+    n_req = len(required_horizons)
+    lamb = 1 - (1 / n_step)
+
+    def get_weights(f):
+        return np.asarray([f(n) for n in range(1, steps + 1)], dtype=np.float32)
+
+    if distribution == "fixed":
+        return np.zeros([n_req, 1], dtype=np.int32) + n_step
+    elif distribution == "exponential":
+        weights = get_weights(lambda x: lamb ** x)
+    elif distribution == "uniform":
+        weights = get_weights(lambda x: 1)
+    elif distribution == "hyperbolic":
+        weights = get_weights(lambda x: 1 / x)
+    elif distribution == "quadratic":
+        weights = get_weights(lambda x: 1 / (steps + (x * x)))
+    else:
+        raise ValueError(f"Invalid distribution {distribution}")
+    weights /= np.sum(weights)
+    if seed is not None:
+        np.random.seed(seed)
+    choices = range(1, len(weights) + 1)
+    if mode == "standard":
+        samples = np.random.choice(choices, size=(1, max_samples), replace=True, p=weights)
+        return np.repeat(samples, n_req, axis=0)
+    elif mode == "advanced":
+        return np.random.choice(choices, size=(n_req, max_samples), replace=True, p=weights)
+    elif mode in ("clipped", "adaptive"):
+        samples = np.zeros([n_req, max_samples], dtype=np.int32)
+        for k in range(n_req):
+            max_h = max(required_horizons[k] if mode == "clipped" else required_horizons[k] // 2, 1)
+            scaled = weights.copy()
+            scaled[max_h:] = 0
+            scaled = scaled / scaled.sum()
+            samples[k, :] = np.random.choice(choices, size=max_samples, replace=True, p=scaled)
+        return samples
+    elif mode == "mcx":
+        samples = np.zeros([n_req, max_samples], dtype=np.int32)
+        for k in range(n_req):
+            if required_horizons[k] <= 2 * n_step:
+                samples[k, :] = required_horizons[k]
+            else:
+                samples[k, :] = np.random.choice(choices, size=max_samples, replace=True, p=weights)
+        return samples
+    elif mode == "full":
+        return weights
+    raise ValueError(f"Invalid return mode {mode}")
+
+
+def get_return_estimate(distribution: str, mode: str, gamma: float, rewards, dones, required_horizons,
+                        value_sample_horizons, value_samples, n_step: int = 40, max_samples: int = 40,
+                        use_log_interpolation: bool = False, seed=None):
+    """Weighted average of n-step truncated returns, ``[N, A, K]`` float32
+    (reference: ``rl/returns_truncated.py:10-139``; same arguments, modes and error behaviour)."""
+    steps = rewards.shape[0]
+    n_req = len(required_horizons)
+    req_host = np.asarray(required_horizons.cpu() if isinstance(required_horizons, torch.Tensor)
+                          else required_horizons)
+    drawn = draw_n_step_samples(distribution, mode, req_host, steps, n_step, max_samples, seed)
+    if distribution != "fixed" and mode == "full":
+        # rl/returns_truncated.py:130-137: sum_n w_n * (n-step return).  The n-step list with
+        # multiplicities is exactly an entry table, so this is ONE pass with per-entry weights.
+        return _launch_weighted_full(gamma, rewards, dones, required_horizons, value_sample_horizons,
+                                     value_samples, drawn, use_log_interpolation)
+    return _launch(gamma, rewards, dones, required_horizons, value_sample_horizons, value_samples, drawn,
+                   use_log_interpolation)
+
+
+def _launch_weighted_full(gamma, rewards, dones, required_horizons, value_sample_horizons, value_samples,
+                          weights, use_log_interpolation):
+    """``full`` mode: every n = 1..N with weight w_n.  Evaluated as N single-sample passes accumulated on
+    the device in the reference's order (it is the reference's "very slow" diagnostic mode, :131-132)."""
+    device = dev.require_cuda()
+    np_like = dev.is_numpy_like(rewards)
+    n_req = len(required_horizons)
+    r = dev.to_device(rewards, torch.float32, device)
+    d = dev.to_device(dones, None, device)
+    vs = dev.to_device(value_samples, torch.float32, device)
+    steps = r.shape[0]
+    total = torch.zeros((steps, r.shape[1], n_req), dtype=torch.float32, device=device)
+    for n, w in zip(range(1, steps + 1), weights):
+        table = np.zeros([n_req, 1], dtype=np.int32) + n
+        part = _launch(gamma, r, d, required_horizons, value_sample_horizons, vs, table, use_log_interpolation)
+        total.add_(part, alpha=float(w))
+    return dev.like_input(total, np_like)

@@ -1,0 +1,123 @@
+"""GPU parity: ppo_b200.returns_truncated (CUDA, through the C ABI) against the oracle and golden vectors.
+
+Tolerance: the reference's own criterion max|d| <= 1e-5 * max|ref| (tests/test_tvf.py:46); horizon
+indexing is bit-exact by construction (host tables) and is checked separately on the CPU.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from ppo_b200 import returns_truncated as rt
+from ppo_b200 import synthetic
+from util import TOL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+PATHS = [rt.PATH_GENERIC, rt.PATH_AUTO]
+
+
+def _tvf_args(g):
+    keys = ['gamma', 'rewards', 'dones', 'required_horizons', 'value_sample_horizons', 'value_samples']
+    a = {k: g["tvf_in_" + k] for k in keys}
+    a['gamma'] = float(a['gamma'])
+    return a
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_reference_estimator_cases(golden, path):
+    """The four cases of the reference's tests/test_tvf.py:116-119 on the golden inputs."""
+    a = _tvf_args(golden)
+    for n in (1, 8, 48):
+        got = rt._calculate_sampled_return_multi_fast(n_step_list=[n], path=path, **a)
+        assert got.dtype == np.float32 and got.shape == golden[f"tvf_fast_n{n}"].shape
+        assert rel_err(got, golden[f"tvf_fast_n{n}"]) <= TOL
+        # against the reference's slow triple-loop estimator with the reference's criterion (:46)
+        slow = golden[f"tvf_slow_n{n}"]
+        assert np.abs(slow - got).max() <= 1e-5 * slow.max()
+    s = golden["tvf_in_samples"]
+    got = rt._calculate_sampled_return_multi_fast(n_step_samples=s, path=path, **a)
+    assert rel_err(got, golden["tvf_fast_samples"]) <= TOL
+    got = rt._calculate_sampled_return_multi_fast(n_step_samples=s, use_log_interpolation=True, path=path, **a)
+    assert rel_err(got, golden["tvf_fast_samples_log"]) <= TOL
+
+
+@pytest.mark.parametrize("dist,mode", [("fixed", "standard"), ("exponential", "standard"),
+                                       ("exponential", "advanced"), ("uniform", "advanced"),
+                                       ("hyperbolic", "clipped"), ("quadratic", "adaptive"),
+                                       ("exponential", "mcx"), ("exponential", "full")])
+def test_dispatcher_golden(golden, dist, mode):
+    a = _tvf_args(golden)
+    got = rt.get_return_estimate(dist, mode, n_step=6, max_samples=5, seed=17, **a)
+    assert rel_err(got, golden[f"tvf_gre_{dist}_{mode}"]) <= TOL
+
+
+def test_production_horizons_golden(golden):
+    g = golden
+    hz, r, d, vs = g["prod_in_horizons"], g["prod_in_rewards"], g["prod_in_dones"], g["prod_in_vs"]
+    got = rt.get_return_estimate("exponential", "advanced", 0.99997, r, d, hz, hz, vs, n_step=20, max_samples=8, seed=1)
+    assert rel_err(got, g["prod_adv"]) <= TOL
+    got = rt.get_return_estimate("fixed", "advanced", 0.99997, r, d, hz, hz, vs, n_step=40, max_samples=8, seed=1)
+    assert rel_err(got, g["prod_fixed"]) <= TOL
+    got = rt.get_return_estimate("exponential", "advanced", 0.99997, r, d, hz, hz, vs, n_step=20, max_samples=8,
+                                 use_log_interpolation=True, seed=1)
+    assert rel_err(got, g["prod_adv_log"]) <= TOL
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("steps,envs,heads,max_h,n_step,samples,done_p", [
+    (128, 64, 128, 30000, 20, 8, 0.03),    # c3 shape, fewer envs
+    (256, 24, 128, 30000, 20, 8, 0.03),    # c5 shape, fewer envs
+    (256, 8, 128, 30000, 20, 8, 0.0),      # no terminals at all
+    (64, 16, 128, 30000, 64, 1, 0.3),      # n-step == N, many terminals
+    (33, 5, 16, 200, 7, 3, 0.1),           # ragged sizes
+    (1, 3, 8, 50, 1, 2, 0.0),              # a single step
+])
+def test_vs_oracle(path, steps, envs, heads, max_h, n_step, samples, done_p):
+    hz = oracle.get_value_head_horizons(heads, max_h)
+    r, d, _ = synthetic.rollout(steps, envs, seed=steps + envs, done_prob=done_p)
+    vs = synthetic.value_samples(steps, envs, len(hz), seed=steps)
+    table = oracle.draw_n_step_samples("exponential", "advanced", hz, steps, n_step, samples, seed=5)
+    ref = oracle.sampled_return_multi(0.99997, r, d, hz, hz, vs, n_step_samples=table)
+    got = rt._calculate_sampled_return_multi_fast(0.99997, r, d, hz, hz, vs, n_step_samples=table, path=path)
+    assert rel_err(got, ref) <= TOL
+    fixed = np.zeros([len(hz), 1], dtype=np.int32) + min(n_step, steps)
+    ref = oracle.sampled_return_multi(0.99997, r, d, hz, hz, vs, n_step_samples=fixed)
+    got = rt._calculate_sampled_return_multi_fast(0.99997, r, d, hz, hz, vs, n_step_samples=fixed, path=path)
+    assert rel_err(got, ref) <= TOL
+
+
+def test_device_tensors_strided_values_and_stats():
+    steps, envs = 48, 40
+    hz = oracle.get_value_head_horizons(32, 1000)
+    r, d, _ = synthetic.rollout(steps, envs, seed=2)
+    full = np.stack([synthetic.value_samples(steps, envs, len(hz), seed=2),
+                     synthetic.value_samples(steps, envs, len(hz), seed=3)], axis=-1)  # [N+1, A, K, VH]
+    vs = full[..., 1]  # rl/tvf.py:248 strided view
+    table = oracle.draw_n_step_samples("exponential", "advanced", hz, steps, 10, 4, seed=1)
+    ref = oracle.sampled_return_multi(0.999, r, d, hz, hz, vs, n_step_samples=table)
+    got = rt._calculate_sampled_return_multi_fast(
+        0.999, torch.from_numpy(r).cuda(), torch.from_numpy(d).cuda(), hz, hz,
+        torch.from_numpy(full).cuda()[..., 1], n_step_samples=table)
+    assert isinstance(got, torch.Tensor) and got.is_cuda
+    assert rel_err(got.cpu().numpy(), ref) <= TOL
+    res, stats = rt._launch(0.999, r, d, hz, hz, vs, table, False, with_stats=True)
+    s = stats.cpu().numpy()
+    last = res[:, :, -1].astype(np.float64)
+    assert s[0] == last.size and s[3] == last.min() and s[4] == last.max()
+    np.testing.assert_allclose(s[1], last.sum(), rtol=1e-12)
+    np.testing.assert_allclose(s[2], (last ** 2).sum(), rtol=1e-12)
+
+
+def test_error_behaviour(golden):
+    a = _tvf_args(golden)
+    with pytest.raises(ValueError):
+        rt.get_return_estimate("nope", "standard", **a)
+    with pytest.raises(ValueError):
+        rt.get_return_estimate("uniform", "nope", **a)
+    with pytest.raises(AssertionError):  # rl/returns_truncated.py:597
+        rt._calculate_sampled_return_multi_fast(n_step_list=[49], **a)
+    b = dict(a)
+    b['required_horizons'] = np.asarray([5000], dtype=np.int32)  # beyond the last value horizon: :157 IndexError
+    with pytest.raises(IndexError):
+        rt._calculate_sampled_return_multi_fast(n_step_list=[4], **b)

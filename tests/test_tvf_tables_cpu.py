@@ -1,0 +1,65 @@
+"""CPU: the host index tables reproduce the reference's horizon indexing bit-exactly.
+
+For every (k, n) the table's (lo, hi, w_lo, w_hi) must give exactly `_interpolate`'s answer
+(oracle.interp_scalar, pinned to rl/returns_truncated.py:142-174) on a probe value vector.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from ppo_b200 import _tvf_tables as T
+
+
+@pytest.mark.parametrize("use_log", [False, True])
+@pytest.mark.parametrize("case", ["geometric", "test_tvf"])
+def test_slots_match_interpolate(case, use_log):
+    if case == "geometric":
+        req = vsh = oracle.get_value_head_horizons(64, 3000)
+    else:  # the reference's own test horizons, with duplicates (tests/test_tvf.py:19-20)
+        req = np.geomspace(1, 1024, num=16).astype('int32')
+        vsh = np.geomspace(1, 1024, num=32).astype('int32') - 1
+    steps = 96
+    rng = np.random.RandomState(0)
+    table = rng.randint(1, steps + 1, size=[len(req), 6])
+    tabs = T.build(0.999, steps, req, vsh, table, use_log)
+    probe = rng.normal(size=[len(vsh)])  # float64 probe: weights are compared at float32 precision below
+    axis = np.log10(10 + vsh) - 1 if use_log else vsh
+    for k, h in enumerate(req):
+        # multiplicities: counts sum to C and the n' are the distinct clamped samples
+        want = np.unique(np.minimum(table[k], h)) if h > 0 else np.asarray([], dtype=np.int64)
+        got_n = tabs.ent_n[tabs.ent_cnt[:, k] > 0, k]
+        assert np.array_equal(np.sort(got_n), want)
+        assert tabs.ent_cnt[:, k].sum() == (table.shape[1] if h > 0 else 0)
+        for e in range(tabs.n_entries):
+            if tabs.ent_cnt[e, k] == 0:
+                continue
+            n = int(tabs.ent_n[e, k])
+            x = h - n
+            lo, hi = tabs.ent_idx[e, k] & 0xffff, tabs.ent_idx[e, k] >> 16
+            got = probe[lo] * np.float64(tabs.ent_wlo[e, k]) + probe[hi] * np.float64(tabs.ent_whi[e, k])
+            target = (np.log10(10 + x) - 1) if use_log else x
+            ref = oracle.interp_scalar(axis, probe, target) if x > 0 else 0.0
+            assert abs(got - ref) <= 1e-6 * max(1.0, abs(ref)), (k, h, n)
+            # slot identity (bit-exact): the table's slots are searchsorted's
+            if x > 0:
+                j = int(np.searchsorted(axis, target))
+                assert hi == j or lo == j or (axis[j] - axis[j - 1] == 0 and lo == j - 1)
+            assert tabs.ent_g[e, k] == tabs.gpow[n]
+
+
+def test_discount_powers_follow_reference_rounding():
+    g = T.discount_powers(0.99997, 200)
+    d = np.ones([1], dtype=np.float32)
+    for n in range(1, 201):
+        d *= 0.99997 * (1 - np.asarray([False]))  # rl/returns_truncated.py:669
+        assert g[n] == d[0]
+
+
+def test_rejects_bad_tables():
+    hz = oracle.get_value_head_horizons(16, 100)
+    with pytest.raises(AssertionError):
+        T.build(0.99, 10, hz, hz, np.zeros([16, 2], dtype=np.int32) + 11)  # n-step > N
+    with pytest.raises(AssertionError):
+        T.build(0.99, 10, hz, hz, np.zeros([16, 2], dtype=np.int32))       # n-step < 1
+    with pytest.raises(IndexError):
+        T.build(0.99, 10, np.asarray([500]), hz, np.ones([1, 1], dtype=np.int32))
