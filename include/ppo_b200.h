@@ -137,6 +137,8 @@ int ppo_discounted_returns(const float* rewards, int64_t reward_row_stride,
  *   ent_wlo / ent_whi   lerp weights (both 0 when h_k - n' <= 0: pure n-step return)
  *   ent_g    gamma^n' as the reference's float32 running product
  *   tail_*   the same slots / weights at horizon h_k - m for rows with m = N - t < n'
+ *   tail_cwlo / tail_cwhi   tail weights folded with gamma^m and the summed multiplicity of the
+ *            entries with n' > m (so the run-off-the-end bootstrap is one fused term per target)
  *   gpow     gamma^n, n = 0..nmax
  *   inv_c    float32(1 / C)
  */
@@ -152,6 +154,8 @@ typedef struct {
     const int32_t* tail_idx;
     const float* tail_wlo;
     const float* tail_whi;
+    const float* tail_cwlo;
+    const float* tail_cwhi;
     const float* gpow;
     float inv_c;
 } ppo_tvf_tables;
@@ -182,6 +186,25 @@ int ppo_tvf_targets(const float* rewards, int64_t reward_row_stride,
                     int64_t steps, int64_t envs, int64_t n_req, int64_t n_val,
                     const ppo_tvf_tables* tables, int path,
                     float* out, double* stats, void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * V-trace value targets, rho-weighted advantages and c weights.  Replaces rl/vtrace.py:44-114
+ * `importance_sampling_v_trace` (rho-bar = c-bar = 1 as hard-coded there):
+ *   rho_t = min(1, exp(log pi(a_t) - log mu(a_t))),  c_t = lamb * rho_t,  g_t = gamma * (1 - done_t)
+ *   acc_t = rho_t (r_t + g_t V_{t+1} - V_t) + g_t c_t acc_{t+1};  vs = acc + V;  adv_t = rho_t (r_t + g_t vs_{t+1} - V_t)
+ * log-policies are contiguous [N, B, ACT]; actions [N, B] are int32 (action_bytes 4) or int64 (8) and may be
+ * negative with NumPy semantics; every other array is contiguous [N, B] / [B].  cs_out may be NULL.
+ */
+int ppo_vtrace(const float* behaviour_log_policy, const float* target_log_policy,
+               const void* actions, int action_bytes, const float* rewards,
+               const void* dones, int done_kind, const float* values, const float* final_value,
+               int64_t steps, int64_t batch, int64_t n_actions, double gamma, double lamb,
+               float* vs_out, float* adv_out, float* cs_out, void* stream);
+
+/* Trust-region weight 1 / (1 + KL(pi || pi_hat)) per row, pi_hat = min(mu, pi) renormalised over the
+ * actions.  Replaces rl/vtrace.py:3-39 `v_trace_trust_region`; rows = N * B, contiguous [rows, ACT]. */
+int ppo_vtrace_trust_region(const float* behaviour_log_policy, const float* target_log_policy,
+                            int64_t rows, int64_t n_actions, float* out, void* stream);
 
 #ifdef __cplusplus
 }

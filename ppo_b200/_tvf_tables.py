@@ -21,7 +21,7 @@ import numpy as np
 
 class TvfTables:
     __slots__ = ("n_entries", "nmax", "ent_n", "ent_cnt", "ent_idx", "ent_wlo", "ent_whi", "ent_g",
-                 "tail_idx", "tail_wlo", "tail_whi", "gpow", "inv_c", "n_req", "n_val", "steps")
+                 "tail_idx", "tail_wlo", "tail_whi", "tail_cwlo", "tail_cwhi", "gpow", "inv_c", "n_req", "n_val", "steps")
 
 
 def _lerp_slots(axis, n_val, targets, positive):
@@ -135,6 +135,11 @@ def build(gamma, steps, required_horizons, value_sample_horizons, n_step_samples
     tabs.gpow = discount_powers(gamma, nmax)
     tabs.ent_g = tabs.gpow[ent_n]
     tabs.tail_idx, tabs.tail_wlo, tabs.tail_whi = tail_idx, t_wlo, t_whi
+    # folded form for the slab kernel: (sum of multiplicities of the entries with n' > m) * gamma^m * weight
+    beyond = (ent_n[None, :, :].astype(np.int64) > ms[:, :, None]) * ent_cnt[None, :, :].astype(np.float64)
+    scale = beyond.sum(axis=1) * tabs.gpow.astype(np.float64)[:, None]      # [nmax + 1, K]
+    tabs.tail_cwlo = (t_wlo.astype(np.float64) * scale).astype(np.float32)
+    tabs.tail_cwhi = (t_whi.astype(np.float64) * scale).astype(np.float32)
     tabs.inv_c = np.float32(1 / n_smp)                   # :618 `returns *= 1 / len(target_n_steps)`
     tabs.n_req, tabs.n_val, tabs.steps = n_req, n_val, steps
     return tabs

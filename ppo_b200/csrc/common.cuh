@@ -69,6 +69,13 @@ __device__ __forceinline__ double alive_of(const void* dones, int64_t idx) {
     }
 }
 
+// (1 - done) as a float32 mask with a runtime kind (rl/vtrace.py:78 `np.asarray(1 - dones, dtype=np.float32)`)
+__device__ __forceinline__ float alive_f32(const void* dones, int kind, int64_t idx) {
+    if (kind == PPO_DONE_U8) return static_cast<const unsigned char*>(dones)[idx] ? 0.f : 1.f;
+    if (kind == PPO_DONE_F32) return 1.0f - static_cast<const float*>(dones)[idx];
+    return 1.f;
+}
+
 // streaming store: outputs are written once and not re-read by the producing kernel
 __device__ __forceinline__ void store_stream(float* p, float v) { __stcs(p, v); }
 

@@ -17,7 +17,8 @@
 
 namespace ppo {
 
-int launch_tvf_ring(const TvfParams& p, cudaStream_t stream, bool probe_only);  // tvf_ring.cu
+int launch_tvf_ring(const TvfParams& p, const float* tail_cwlo, const float* tail_cwhi, cudaStream_t stream,
+                    bool probe_only);  // tvf_ring.cu
 
 // ------------------------------------------------------------------------------------------
 // Generic kernel: one CTA per (env, chunk of TC time rows); value rows are gathered from global
@@ -255,7 +256,7 @@ extern "C" int ppo_tvf_targets(const float* rewards, int64_t reward_row_stride, 
 
     int rc = PPO_ERR_UNSUPPORTED;
     if (path != PPO_TVF_GENERIC) {
-        rc = launch_tvf_ring(p, s, false);
+        rc = launch_tvf_ring(p, tables->tail_cwlo, tables->tail_cwhi, s, false);
         if (rc == PPO_ERR_UNSUPPORTED && path == PPO_TVF_AUTO) rc = launch_generic(p, s);
     } else {
         rc = launch_generic(p, s);

@@ -22,13 +22,14 @@ class _CTables(ctypes.Structure):
                 ("ent_n", ctypes.c_void_p), ("ent_cnt", ctypes.c_void_p), ("ent_idx", ctypes.c_void_p),
                 ("ent_wlo", ctypes.c_void_p), ("ent_whi", ctypes.c_void_p), ("ent_g", ctypes.c_void_p),
                 ("tail_idx", ctypes.c_void_p), ("tail_wlo", ctypes.c_void_p), ("tail_whi", ctypes.c_void_p),
+                ("tail_cwlo", ctypes.c_void_p), ("tail_cwhi", ctypes.c_void_p),
                 ("gpow", ctypes.c_void_p), ("inv_c", ctypes.c_float)]
 
 
 def _upload_tables(tabs, device):
     """One packed H2D copy of all tables; returns (ctypes struct, tensor keeping the memory alive)."""
     parts = [tabs.ent_n, tabs.ent_cnt, tabs.ent_idx, tabs.ent_wlo, tabs.ent_whi, tabs.ent_g,
-             tabs.tail_idx, tabs.tail_wlo, tabs.tail_whi, tabs.gpow]
+             tabs.tail_idx, tabs.tail_wlo, tabs.tail_whi, tabs.tail_cwlo, tabs.tail_cwhi, tabs.gpow]
     words, offsets = 0, []
     for a in parts:
         offsets.append(words)
@@ -40,7 +41,8 @@ def _upload_tables(tabs, device):
     base = blob.data_ptr()
     c = _CTables()
     c.n_entries, c.nmax = tabs.n_entries, tabs.nmax
-    names = ["ent_n", "ent_cnt", "ent_idx", "ent_wlo", "ent_whi", "ent_g", "tail_idx", "tail_wlo", "tail_whi", "gpow"]
+    names = ["ent_n", "ent_cnt", "ent_idx", "ent_wlo", "ent_whi", "ent_g", "tail_idx", "tail_wlo", "tail_whi",
+             "tail_cwlo", "tail_cwhi", "gpow"]
     for name, off in zip(names, offsets):
         setattr(c, name, base + 4 * off)
     c.inv_c = float(tabs.inv_c)

@@ -71,7 +71,7 @@ def test_production_horizons_golden(golden):
     (256, 8, 128, 30000, 20, 8, 0.0),      # no terminals at all
     (64, 16, 128, 30000, 64, 1, 0.3),      # n-step == N, many terminals
     (33, 5, 16, 200, 7, 3, 0.1),           # ragged sizes
-    (1, 3, 8, 50, 1, 2, 0.0),              # a single step
+    (1, 3, 8, 50, 2, 2, 0.0),              # a single step
 ])
 def test_vs_oracle(path, steps, envs, heads, max_h, n_step, samples, done_p):
     hz = oracle.get_value_head_horizons(heads, max_h)
