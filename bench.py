@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Benchmark of the return / advantage hot path (BASELINE.json metric: return targets/s, % of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" is one full pass of the return stage over one synthetic rollout of
+256 steps x 4096 envs x 128 horizons PER GPU (weak scaling; 8 GPUs = BASELINE config 5, 32768 envs):
+GAE advantages + TD(lambda) returns + their statistics -> all-reduce of {count, sum, sumsq} (N > 1) ->
+advantage normalisation -> 128-horizon TVF targets (exponential / advanced, 8 samples, n_step 20) + statistics
+of the longest horizon.  ``value`` counts steps x envs x horizons TVF targets per second over all ranks
+(the 2 x steps x envs GAE outputs of the same pass are not counted).
+
+Prints ONE JSON line (rank 0).  ``--impl reference`` times the CPU arm: the NumPy oracle (a restatement of
+the reference, pinned to it by tests/golden) on the host cores; nothing else in this file executes ``oracle/``
+except the ``cpu_baseline`` leg.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+STEPS, ENVS_PER_GPU, HORIZONS, MAX_HORIZON = 256, 4096, 128, 30000
+GAMMA, LAMBDA_POLICY, LAMBDA_VALUE = 0.999, 0.95, 0.95
+TVF_GAMMA, N_STEP, SAMPLES, SAMPLE_SEED = 0.99997, 20, 8, 1
+METRIC = "return targets (steps x envs x horizons) per second, full pass: GAE + adv-norm + 128-horizon TVF targets"
+UNIT = "targets/s"
+
+
+def config(n_gpus):
+    return {
+        "workload": f"full return pass, {STEPS} steps x {ENVS_PER_GPU} envs x {HORIZONS} horizons per GPU "
+                    f"(total {ENVS_PER_GPU * n_gpus} envs; 8 GPUs = BASELINE config 5)",
+        "steps": STEPS, "envs_per_gpu": ENVS_PER_GPU, "envs_total": ENVS_PER_GPU * n_gpus, "horizons": HORIZONS,
+        "max_horizon": MAX_HORIZON, "gae": {"gamma": GAMMA, "lambda_policy": LAMBDA_POLICY, "lambda_value": LAMBDA_VALUE},
+        "tvf": {"gamma": TVF_GAMMA, "distribution": "exponential", "mode": "advanced", "n_step": N_STEP,
+                "samples": SAMPLES, "seed": SAMPLE_SEED},
+        "sharding": f"env axis over {n_gpus} rank(s), all-reduce of 3 float64 advantage moments" if n_gpus > 1
+                    else "single GPU, no collective",
+        "l2": "per-step working set 1.1 GB per GPU exceeds the 126 MB L2, no explicit flush",
+        "sample_table": "drawn on the host with the reference's NumPy RNG calls; resolved index tables uploaded "
+                        "before the device-timed region, rebuilt and uploaded every step inside the e2e region",
+    }
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def _oracle_pass(rewards, dones, values, value_samples, horizons):
+    """One full pass with the NumPy oracle (reference algorithm)."""
+    import oracle
+    adv = oracle.gae(rewards, values[:-1], values[-1], dones, GAMMA, LAMBDA_POLICY)
+    ret = oracle.td_lambda(rewards, values[:-1], values[-1], dones, GAMMA, LAMBDA_VALUE)
+    norm = oracle.normalize_advantages(adv)
+    tvf = oracle.get_return_estimate("exponential", "advanced", TVF_GAMMA, rewards, dones, horizons, horizons,
+                                     value_samples, n_step=N_STEP, max_samples=SAMPLES, seed=SAMPLE_SEED)
+    return adv, ret, norm, tvf
+
+
+def _cpu_inputs(envs, seed):
+    import oracle
+    from ppo_b200 import synthetic
+    hz = oracle.get_value_head_horizons(HORIZONS, MAX_HORIZON)
+    r, d, v = synthetic.rollout(STEPS, envs, seed=seed)
+    vs = synthetic.value_samples(STEPS, envs, len(hz), seed=seed)
+    return r, d, v, vs, hz
+
+
+_WORKER = {}
+
+
+def _worker_init(envs, seed_base):
+    import multiprocessing
+    ident = multiprocessing.current_process()._identity
+    _WORKER["data"] = _cpu_inputs(envs, seed_base + (ident[0] if ident else 0))
+
+
+def _worker_step(_):
+    r, d, v, vs, hz = _WORKER["data"]
+    t0 = time.perf_counter()
+    _oracle_pass(r, d, v, vs, hz)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline_single(envs=1024):
+    """The oracle on ONE host core over a bounded sample (256 steps x `envs` envs x 128 horizons)."""
+    r, d, v, vs, hz = _cpu_inputs(envs, seed=0)
+    t0 = time.perf_counter()
+    _oracle_pass(r, d, v, vs, hz)
+    dt = time.perf_counter() - t0
+    return {"value": STEPS * envs * HORIZONS / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"one full pass of the NumPy oracle over {STEPS} steps x {envs} envs x {HORIZONS} horizons "
+                      f"({envs}/{ENVS_PER_GPU} of the per-GPU workload), {dt:.2f} s, single-threaded like the reference; "
+                      f"host has {os.cpu_count()} logical cores"}
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference on all usable host cores (one process per core, envs are
+    independent).  Each step is a bounded sample: every worker runs one full pass over its own 256-env rollout
+    (256 envs = the reference's default agent count, rl/config.py:791)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    workers = max(1, min(cores, 16))
+    warmup = min(args.warmup, 1)
+    # bounded sample: ~3.4 M targets/s per core -> 256 steps x e envs x 128 horizons take ~e / 104 s; keep the whole
+    # run near two minutes, never more than the reference's default 256 agents per call (rl/config.py:791)
+    envs_per_worker = int(104 * 120 / (args.steps + warmup))
+    envs_per_worker = max(16, min(256, envs_per_worker // 16 * 16))
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers, initializer=_worker_init, initargs=(envs_per_worker, 1000)) as pool:
+        for _ in range(warmup):
+            pool.map(_worker_step, range(workers), chunksize=1)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_worker_step, range(workers), chunksize=1)
+        dt = time.perf_counter() - t0
+    sample_envs = envs_per_worker * workers
+    value = STEPS * sample_envs * HORIZONS * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
+                         "sample": f"each step = one full oracle pass over {STEPS} steps x {sample_envs} envs x {HORIZONS} "
+                                   f"horizons ({workers} processes x {envs_per_worker} envs), host has {cores} usable cores; "
+                                   f"warm-up capped at {warmup} step(s)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while a timed region runs."""
+
+    def __init__(self, index, period=0.002):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # NVML missing: report it rather than guessing
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": getattr(self, "err", "nvml unavailable")}
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from ppo_b200 import _lib, rollout
+    from ppo_b200 import returns_truncated as rt
+    from ppo_b200 import tvf as tvf_mod
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run for N > 1"
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    _lib.load()
+
+    steps, envs, n_h = STEPS, ENVS_PER_GPU, HORIZONS
+    hz = tvf_mod.get_value_head_horizons(n_h, MAX_HORIZON)
+    assert len(hz) == n_h
+
+    # ---- synthetic rollout of this rank (seed = rank), distributions of the reference's tests (tests/test_tvf.py:17-24)
+    g = torch.Generator(device=device)
+    g.manual_seed(rank)
+    rewards = torch.randint(-1, 3, (steps, envs), device=device, generator=g).float()
+    dones = (torch.rand((steps, envs), device=device, generator=g) < 3 / 101).view(torch.uint8)
+    value_samples = torch.randn((steps + 1, envs, n_h), device=device, generator=g) * 0.4 + 0.1
+    value_samples[:, :, 0] = 0
+    values = value_samples[:, :, -1]  # rl/tvf.py:325-340: the value estimate GAE uses is the longest horizon
+
+    samples = rt.draw_n_step_samples("exponential", "advanced", hz, steps, N_STEP, SAMPLES, seed=SAMPLE_SEED)
+    rp = rollout.ReturnPass(steps, envs, hz, GAMMA, TVF_GAMMA, LAMBDA_POLICY, LAMBDA_VALUE)
+    tabs = rp.set_samples(samples)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for _ in range(args.warmup):
+        rp.run(rewards, values, dones, value_samples)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin.record()
+    for i in range(args.steps):
+        rp.run(rewards, values, dones, value_samples, tvf_events=evs[i])
+    t_end.record()
+    barrier()
+    total_ms = t_begin.elapsed_time(t_end)
+    tvf_ms = [e[0].elapsed_time(e[1]) for e in evs]
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    targets_per_step = steps * envs * n_h * world
+    value = targets_per_step / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API with pinned host buffers
+    host_in = {
+        "rewards": rewards.cpu().pin_memory(), "values": values.contiguous().cpu().pin_memory(),
+        "dones": dones.view(torch.bool).cpu().pin_memory(), "value_samples": value_samples.cpu().pin_memory(),
+    }
+    host_out = {
+        "advantage": torch.empty((steps, envs), dtype=torch.float32).pin_memory(),
+        "ext_returns": torch.empty((steps, envs), dtype=torch.float32).pin_memory(),
+        "advantages": torch.empty(steps * envs, dtype=torch.float32).pin_memory(),
+        "tvf_returns": torch.empty((steps, envs, n_h), dtype=torch.float32).pin_memory(),
+    }
+    tvf_kw = dict(value_samples=host_in["value_samples"], horizons=hz, gamma=TVF_GAMMA, mode="advanced",
+                  distribution="exponential", n_step=N_STEP, max_samples=SAMPLES, seed=SAMPLE_SEED)
+
+    def e2e_step():
+        return rollout.calculate_returns(host_in["rewards"], host_in["values"], host_in["dones"], GAMMA,
+                                         LAMBDA_POLICY, LAMBDA_VALUE, tvf=tvf_kw, out=host_out)
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()  # returns after the results have landed in host_out (stream synchronised inside)
+    barrier()
+    e2e_s = time.perf_counter() - w0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    clocks = sampler.stop()
+    h2d = sum(t.numel() * t.element_size() for t in host_in.values()) * world
+    d2h = sum(t.numel() * t.element_size() for t in host_out.values()) * world
+    e2e_value = targets_per_step * e2e_steps / e2e_s
+    # the e2e results must equal the device-resident ones (same inputs, same sample table)
+    same = bool(torch.equal(host_out["tvf_returns"], rp.tvf_returns.cpu()))
+
+    # ---- roofline of the dominant kernel (TVF targets), from CUDA events inside the timed region
+    alg_bytes = 4 * (steps + 1) * envs * n_h + 4 * steps * envs * n_h + 5 * steps * envs
+    tvf_avg_ms = sum(tvf_ms) / len(tvf_ms)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    achieved = alg_bytes / (tvf_avg_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "tvf_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "tvf slab kernel (ppo_tvf_targets)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": tvf_avg_ms,
+                "kernel_share_of_step": tvf_avg_ms / ms_per_step,
+                "units_per_launch": f"{steps} x {envs} x {n_h} targets at 8.06 B/target"}
+
+    if rank == 0:
+        cpu = cpu_baseline_single() if world == 1 and not args.no_cpu_baseline else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config(world), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "matches_resident": same,
+                    "api": "ppo_b200.rollout.calculate_returns(pinned host tensors, out=pinned host tensors)"},
+            "gpu_launches": rp.kernel_launches_per_pass * args.steps,
+            "roofline": roofline,
+            "tvf_tables": {"entries_per_horizon": int(tabs.n_entries), "nmax": int(tabs.nmax)},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~15 s oracle timing (development)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -187,6 +187,11 @@ int ppo_tvf_targets(const float* rewards, int64_t reward_row_stride,
                     const ppo_tvf_tables* tables, int path,
                     float* out, double* stats, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* count / sum / sumsq / min / max of the longest horizon targets[:, K-1] of a [rows, K] target buffer into the
+ * ADV_* slots of `stats` (rl/rollout.py:1270 `tvf_return_ext`); what ppo_tvf_targets runs when `stats` is given. */
+int ppo_tvf_last_horizon_stats(const float* targets, int64_t rows, int64_t n_req, double* stats,
+                               void* workspace, int64_t workspace_bytes, void* stream);
+
 /*
  * V-trace value targets, rho-weighted advantages and c weights.  Replaces rl/vtrace.py:44-114
  * `importance_sampling_v_trace` (rho-bar = c-bar = 1 as hard-coded there):

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "ppo_tvf_workspace_bytes": (c_i64, [c_i64, c_i64]),
     "ppo_tvf_targets": (c_int, [c_ptr, c_i64, c_ptr, c_int, c_i64, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
                                 c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "ppo_tvf_last_horizon_stats": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
     "ppo_vtrace": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_i64, c_i64, c_i64,
                            c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ppo_vtrace_trust_region": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),

@@ -263,20 +263,31 @@ extern "C" int ppo_tvf_targets(const float* rewards, int64_t reward_row_stride, 
     }
     if (rc != PPO_OK) return rc;
 
-    if (stats) {
-        const int64_t need = ppo_tvf_workspace_bytes(steps, envs);
-        if (!workspace || workspace_bytes < need) {
-            set_error("ppo_tvf_targets: workspace of %lld bytes required", (long long)need);
-            return PPO_ERR_WORKSPACE;
-        }
-        LastHorizonParams q{};
-        q.out = out, q.rows = steps * envs, q.K = n_req, q.stats = stats;
-        q.ticket = static_cast<unsigned int*>(workspace);
-        q.partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
-        int64_t blocks = (q.rows + 511) / 512;
-        if (blocks > kStatsBlocks) blocks = kStatsBlocks;
-        tvf_last_horizon_stats_kernel<<<static_cast<unsigned>(blocks), 512, 0, s>>>(q);
-        PPO_CUDA(cudaGetLastError());
+    if (stats) return ppo_tvf_last_horizon_stats(out, steps * envs, n_req, stats, workspace, workspace_bytes, stream);
+    return PPO_OK;
+}
+
+extern "C" int ppo_tvf_last_horizon_stats(const float* targets, int64_t rows, int64_t n_req, double* stats,
+                                          void* workspace, int64_t workspace_bytes, void* stream) {
+    PPO_REQUIRE(rows >= 0 && n_req >= 1 && stats, "ppo_tvf_last_horizon_stats: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (rows == 0) {
+        PPO_CUDA(cudaMemsetAsync(stats, 0, PPO_STATS_LEN * sizeof(double), s));
+        return PPO_OK;
     }
+    PPO_REQUIRE(targets, "ppo_tvf_last_horizon_stats: null targets");
+    const int64_t need = ppo_tvf_workspace_bytes(0, 0);
+    if (!workspace || workspace_bytes < need) {
+        set_error("ppo_tvf_last_horizon_stats: workspace of %lld bytes required", (long long)need);
+        return PPO_ERR_WORKSPACE;
+    }
+    LastHorizonParams q{};
+    q.out = targets, q.rows = rows, q.K = n_req, q.stats = stats;
+    q.ticket = static_cast<unsigned int*>(workspace);
+    q.partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
+    int64_t blocks = (q.rows + 511) / 512;
+    if (blocks > kStatsBlocks) blocks = kStatsBlocks;
+    tvf_last_horizon_stats_kernel<<<static_cast<unsigned>(blocks), 512, 0, s>>>(q);
+    PPO_CUDA(cudaGetLastError());
     return PPO_OK;
 }

@@ -292,7 +292,7 @@ tvf_ring_kernel(const RingParams q, const __grid_constant__ CUtensorMap vmap) {
             for (int e = 0; e < nenv; ++e) {
                 const int env = static_cast<int>(env0 + e);
                 for (int c = 0; c < q.cpe; ++c) {
-                    mbar_wait_sleep(&empty[slot], par ^ 1);
+                    mbar_wait(&empty[slot], par ^ 1);
                     mbar_arrive_expect_tx(&full[slot], CHUNK);
                     tma_load_3d(ring + static_cast<size_t>(slot) * CHUNK, &vmap, &full[slot], 0, env, c * kRC + 1);
                     if (++slot == q.nslot) slot = 0, par ^= 1;
@@ -327,13 +327,17 @@ tvf_ring_kernel(const RingParams q, const __grid_constant__ CUtensorMap vmap) {
                 }
             }
         };
+        uint32_t* my_dm = reinterpret_cast<uint32_t*>(my_ds);  // done bitmask words, bit r%32 of word r/32
+        const int dm_words = q.npad / 32;
         auto store_cols = [&](int buf) {
 #pragma unroll
             for (int i = 0; i < kColRegs; ++i) {
                 const int row = i * 32 + lane;
-                if (row < N) {  // rows >= N stay zero: the prefix rows continue as constants past the rollout
-                    my_rs[buf * q.npad + row] = cr[i];
-                    my_ds[buf * q.npad + row] = static_cast<unsigned char>((cd[i / 4] >> (8 * (i % 4))) & 0xffu);
+                const uint32_t dn = (cd[i / 4] >> (8 * (i % 4))) & 0xffu;
+                const uint32_t word = __ballot_sync(0xffffffffu, dn != 0);
+                if (i * 32 < N) {  // rows >= N stay zero: the prefix rows continue as constants past the rollout
+                    if (row < N) my_rs[buf * q.npad + row] = cr[i];
+                    if (lane == 0) my_dm[buf * dm_words + i] = word;
                 }
             }
             __syncwarp();
@@ -353,24 +357,35 @@ tvf_ring_kernel(const RingParams q, const __grid_constant__ CUtensorMap vmap) {
             mbar_wait_sleep(&pempty[s], (use & 1) ^ 1);
             const int t = j * kTC + lane;  // rows past the rollout read zero rewards
             const float* r_col = my_rs + cur * q.npad + t;
-            const unsigned char* d_col = my_ds + cur * q.npad + t;
             float* row = myP + static_cast<size_t>(lane) * PS;
-            float acc = 0.f;
-            bool alive = true;
+            // distance to the first terminal at or after t (only terminals inside the n-step window matter)
             int first_done = kNoDone;
+            {
+                const uint32_t* dm = my_dm + cur * dm_words + j;
+                uint32_t m = dm[0] & (0xffffffffu << lane);
+                const int words = (nmax + 31 + 31) / 32;
+                int base = -lane;
+                for (int w = 0; w < words; ++w) {
+                    if (first_done == kNoDone && m != 0u) first_done = base + __ffs(m) - 1;
+                    base += 32;
+                    m = (j + w + 1 < dm_words) ? dm[w + 1] : 0u;
+                }
+            }
+            // S_n(t) = sum_{i<n} float32(r[t+i] * D_i), D_i = gamma^i while no terminal lies in t..t+i-1, else 0:
+            // float32 accumulation in forward order like rl/returns_truncated.py:668; adding r * 0 is a no-op,
+            // so the sum simply stops growing after the terminal step and the row continues as a constant.
+            float acc = 0.f;
             row[0] = 0.f;
-            for (int i0 = 0; i0 < nmax; i0 += 4) {
-                float rr[4];
-                unsigned char dd[4];
+            for (int i0 = 0; i0 < nmax; i0 += 8) {
+                float rr[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) rr[u] = r_col[i0 + u], dd[u] = d_col[i0 + u];
+                for (int u = 0; u < 8; ++u) rr[u] = r_col[i0 + u];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 8; ++u) {
                     if (i0 + u < nmax) {
-                        const float disc = alive ? gpow_s[i0 + u] : 0.f;
-                        acc = __fadd_rn(acc, __fmul_rn(rr[u], disc));
+                        const float x = __fmul_rn(rr[u], gpow_s[i0 + u]);
+                        if (i0 + u <= first_done) acc = __fadd_rn(acc, x);
                         row[i0 + u + 1] = acc;
-                        if (alive && dd[u]) alive = false, first_done = i0 + u;
                     }
                 }
             }
@@ -452,7 +467,7 @@ int launch_tvf_ring(const TvfParams& p, const float* tail_wlo, const float* tail
     q.cpe = (N + kRC - 1) / kRC;
     q.ncht = (N + kTC - 1) / kTC;
     const int ps = nmax <= 128 ? 129 : 257;
-    q.npad = (N + 31) / 32 * 32 + 256 + 32;  // reward rows are read as r_col[t + i], i < nmax + 3, zero past N
+    q.npad = (N + 31) / 32 * 32 + 256 + 32;  // reward rows are read as r_col[t + i], i < nmax + 7, zero past N
     int kb = 1;
     while (kb * 32 < K) kb <<= 1;
     q.kb = kb;

@@ -50,7 +50,7 @@ def _upload_tables(tabs, device):
 
 
 def _launch(gamma, rewards, dones, required_horizons, value_sample_horizons, value_samples, n_step_samples,
-            use_log_interpolation, path=PATH_AUTO, with_stats=False):
+            use_log_interpolation, path=PATH_AUTO, with_stats=False, keep_on_device=False):
     device = dev.require_cuda()
     lib = _lib.load()
     np_like = dev.is_numpy_like(rewards)
@@ -83,7 +83,7 @@ def _launch(gamma, rewards, dones, required_horizons, value_sample_horizons, val
         dev.ptr(ws), ws.numel() if ws is not None else 0, dev.stream_ptr())
     _lib.check(rc, "ppo_tvf_targets")
     del blob  # same-stream allocator reuse is ordered after the kernel
-    res = dev.like_input(out, np_like)
+    res = out if keep_on_device else dev.like_input(out, np_like)
     return (res, stats) if with_stats else res
 
 

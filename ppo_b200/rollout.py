@@ -1,0 +1,266 @@
+"""The return / advantage stage of ``Runner.calculate_returns`` and the batch advantage normalisation
+of ``Runner.train_policy`` (reference: ``rl/rollout.py:1182-1285`` and ``:1886-1900``), as free
+functions over rollout buffers, with the env axis optionally sharded over ``torch.distributed`` ranks.
+
+Envs are independent, so each rank owns a contiguous block of envs of every ``[N, A, ...]`` buffer and
+runs the same kernels on its block.  The only exchange is the sum of ``{count, sum, sum of squares}``
+of the raw advantages (three float64, plus min / max for the logged statistics) before the
+normalisation: one NCCL all-reduce over NVLink.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _device as dev
+from . import _lib
+from . import returns as _returns
+from . import returns_truncated as _rt
+
+
+def shard_envs(array, rank, world, axis=1):
+    """Contiguous env block of ``array`` owned by ``rank`` (even split, remainder to the low ranks)."""
+    n = array.shape[axis]
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    index = [slice(None)] * array.ndim
+    index[axis] = slice(lo, hi)
+    return array[tuple(index)]
+
+
+_SUM_SLOTS = [_lib.STAT_COUNT, _lib.STAT_ADV_SUM, _lib.STAT_ADV_SUMSQ, _lib.STAT_RET_SUM, _lib.STAT_RET_SUMSQ]
+_MIN_SLOTS = [_lib.STAT_ADV_MIN, _lib.STAT_RET_MIN]
+_MAX_SLOTS = [_lib.STAT_ADV_MAX, _lib.STAT_RET_MAX]
+
+
+def merge_stats(records):
+    """Combine statistics records of disjoint env blocks: sums are added, min / max are reduced."""
+    stack = torch.stack(list(records))
+    merged = torch.zeros_like(stack[0])
+    merged[_SUM_SLOTS] = stack[:, _SUM_SLOTS].sum(dim=0)
+    merged[_MIN_SLOTS] = stack[:, _MIN_SLOTS].min(dim=0).values
+    merged[_MAX_SLOTS] = stack[:, _MAX_SLOTS].max(dim=0).values
+    return merged
+
+
+def allreduce_stats(stats, group=None):
+    """Combine per-rank statistics records in place across ``group`` (same result as :func:`merge_stats`)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return stats
+    sums, mins, maxs = stats[_SUM_SLOTS], stats[_MIN_SLOTS], stats[_MAX_SLOTS]
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(mins, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(maxs, op=dist.ReduceOp.MAX, group=group)
+    stats[_SUM_SLOTS], stats[_MIN_SLOTS], stats[_MAX_SLOTS] = sums, mins, maxs
+    return stats
+
+
+def allreduce_moments(stats, group=None):
+    """The one exchange the normalisation needs: sum of {count, sum, sum of squares} (3 x float64)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return stats
+    dist.all_reduce(stats[_lib.STAT_COUNT:_lib.STAT_ADV_SUMSQ + 1], op=dist.ReduceOp.SUM, group=group)
+    return stats
+
+
+def moments(x):
+    """Device statistics record (count / sum / sumsq / min / max in the ADV slots) of a float32 array."""
+    device = dev.require_cuda()
+    lib = _lib.load()
+    t = dev.to_device(x, torch.float32, device).contiguous()
+    stats = torch.empty(_lib.STATS_LEN, dtype=torch.float64, device=device)
+    ws = dev.workspace(lib.ppo_gae_workspace_bytes(0), device)
+    rc = lib.ppo_moments(dev.ptr(t), t.numel(), dev.ptr(stats), dev.ptr(ws), ws.numel(), dev.stream_ptr())
+    _lib.check(rc, "ppo_moments")
+    return stats
+
+
+def normalize_advantages(advantage, epsilon=1e-8, clipping=None, stats=None, group=None, out=None):
+    """``(adv - mean) / (std + eps)`` over the whole (global) batch, optional clip; returns the flattened
+    float32 vector like ``rl/rollout.py:1887-1897``.  ``stats`` is the record returned by
+    ``returns.gae_td_lambda(..., with_stats=True)`` (local to this rank); it is summed over ``group``."""
+    device = dev.require_cuda()
+    lib = _lib.load()
+    np_like = dev.is_numpy_like(advantage)
+    adv = dev.to_device(advantage, torch.float32, device).contiguous()
+    if stats is None:
+        stats = moments(adv)
+    else:
+        stats = stats.clone()
+    allreduce_moments(stats, group)
+    if out is None:
+        out = torch.empty(adv.numel(), dtype=torch.float32, device=device)
+    rc = lib.ppo_adv_normalize(dev.ptr(adv), adv.numel(), dev.ptr(stats), float(epsilon),
+                               float(clipping) if clipping is not None else 0.0, dev.ptr(out), dev.stream_ptr())
+    _lib.check(rc, "ppo_adv_normalize")
+    return dev.like_input(out, np_like)
+
+
+def calculate_returns(ext_rewards, ext_value_estimates, terminals, gamma, lambda_policy=0.95, lambda_value=0.95,
+                      advantage_epsilon=1e-8, advantage_clipping=None, tvf=None, group=None, out=None):
+    """One pass of the return stage (``rl/rollout.py:1182-1285`` + ``:1886-1897``) over this rank's envs.
+
+    ``ext_value_estimates`` is ``[N+1, A]`` (row N is the final estimate, ``rl/rollout.py:1207-1214``).
+    ``tvf`` (optional) is a dict with ``value_samples [N+1, A, K]``, ``horizons [K]``, ``gamma`` and the
+    ``get_return_estimate`` keywords (``mode``, ``distribution``, ``n_step``, ``max_samples``,
+    ``use_log_interpolation``, ``seed``), mirroring ``TVFRunnerModule.calculate_tvf_returns``.
+    Returns a dict: ``advantage`` (raw), ``ext_returns``, ``advantages`` (normalised, flattened),
+    ``stats`` (global record on the device) and, with ``tvf``, ``tvf_returns`` and ``tvf_stats``.
+    Host inputs may be NumPy arrays (NumPy out) or CPU tensors, ideally pinned; ``out`` (optional) maps result
+    names to pre-allocated pinned CPU tensors that receive the results by asynchronous copies, and the call
+    returns after one stream synchronisation -- the zero-allocation host path for a trainer whose rollout
+    buffers live in pinned memory.
+    """
+    np_like = dev.is_numpy_like(ext_rewards)
+    device = dev.require_cuda()
+    values = dev.to_device(ext_value_estimates, torch.float32, device)
+    steps = values.shape[0] - 1
+    adv, ret, stats = _returns._gae_launch(ext_rewards, values[:steps], values[steps], terminals, gamma,
+                                           lambda_policy, lambda_value, True, True, True)
+    local = stats.clone()
+    allreduce_stats(stats, group)
+    norm = torch.empty(adv.numel(), dtype=torch.float32, device=device)
+    lib = _lib.load()
+    rc = lib.ppo_adv_normalize(dev.ptr(adv), adv.numel(), dev.ptr(stats), float(advantage_epsilon),
+                               float(advantage_clipping) if advantage_clipping is not None else 0.0,
+                               dev.ptr(norm), dev.stream_ptr())
+    _lib.check(rc, "ppo_adv_normalize")
+    def deliver(name, tensor):
+        if out is not None and name in out:
+            out[name].copy_(tensor.view(out[name].shape), non_blocking=True)
+            return out[name]
+        return dev.like_input(tensor, np_like)
+
+    result = {
+        "advantage": deliver("advantage", adv),
+        "ext_returns": deliver("ext_returns", ret),
+        "advantages": deliver("advantages", norm),
+        "stats": stats,
+        "local_stats": local,
+    }
+    if tvf is not None:
+        kw = dict(tvf)
+        vs = kw.pop("value_samples")
+        hz = kw.pop("horizons")
+        g = kw.pop("gamma")
+        mode = kw.pop("mode", "advanced")
+        distribution = kw.pop("distribution", "exponential")
+        samples = _rt.draw_n_step_samples(distribution, mode, np.asarray(hz), steps, kw.pop("n_step", 40),
+                                          kw.pop("max_samples", 40), kw.pop("seed", None))
+        if distribution != "fixed" and mode == "full":
+            raise ValueError("calculate_returns: use returns_truncated.get_return_estimate for mode='full'")
+        targets, tstats = _rt._launch(g, ext_rewards, terminals, hz, hz, vs, samples,
+                                      kw.pop("use_log_interpolation", False), with_stats=True,
+                                      keep_on_device=out is not None and "tvf_returns" in out)
+        allreduce_stats(tstats, group)
+        result["tvf_returns"] = deliver("tvf_returns", targets) if out is not None and "tvf_returns" in out else targets
+        result["tvf_stats"] = tstats
+    if out is not None:
+        torch.cuda.current_stream().synchronize()
+    return result
+
+
+class ReturnPass:
+    """Device-resident form of the return stage for one rank's env block: buffers stay in HBM, outputs
+    and workspaces are allocated once, and ``run()`` is exactly the launches of one pass
+    (``rl/rollout.py:1207-1236`` + ``:1891``):
+
+      1. ``ppo_gae``            advantages (lambda_policy) + TD(lambda) returns (lambda_value) + statistics
+      2. all-reduce (sum) of {count, sum, sum of squares} of the raw advantages -- only when sharded
+      3. ``ppo_adv_normalize``  normalised (optionally clipped) advantages
+      4. ``ppo_tvf_targets``    [N, A, K] truncated-return targets + statistics of the longest horizon
+
+    ``set_samples`` resolves an n-step sample table (host integers only) and uploads it; the reference
+    draws a new table every rollout (``rl/returns_truncated.py:85-129``), so call it per pass when the
+    table changes.  All launches go to the current CUDA stream; nothing synchronises.
+    """
+
+    def __init__(self, steps, envs, horizons, gamma, tvf_gamma, lambda_policy=0.95, lambda_value=0.95,
+                 advantage_epsilon=1e-8, advantage_clipping=None, use_log_interpolation=False, group=None,
+                 tvf_path=_rt.PATH_AUTO, device=None):
+        self.device = device or dev.require_cuda()
+        self.lib = _lib.load()
+        self.steps, self.envs = int(steps), int(envs)
+        self.horizons = np.asarray(horizons)
+        self.n_h = len(self.horizons)
+        self.gamma, self.tvf_gamma = float(gamma), float(tvf_gamma)
+        self.lambda_policy, self.lambda_value = float(lambda_policy), float(lambda_value)
+        self.eps = float(advantage_epsilon)
+        self.clip = float(advantage_clipping) if advantage_clipping is not None else 0.0
+        self.use_log = bool(use_log_interpolation)
+        self.group = group
+        self.tvf_path = tvf_path
+        self.sharded = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.advantage = torch.empty((self.steps, self.envs), **f32)
+        self.ext_returns = torch.empty((self.steps, self.envs), **f32)
+        self.advantages = torch.empty(self.steps * self.envs, **f32)
+        self.tvf_returns = torch.empty((self.steps, self.envs, self.n_h), **f32)
+        self.stats = torch.zeros(_lib.STATS_LEN, dtype=torch.float64, device=self.device)
+        self.tvf_stats = torch.zeros(_lib.STATS_LEN, dtype=torch.float64, device=self.device)
+        self._moments = self.stats[_lib.STAT_COUNT:_lib.STAT_ADV_SUMSQ + 1]
+        self.ws_gae = torch.zeros(max(int(self.lib.ppo_gae_workspace_bytes(self.envs)), 1 << 12),
+                                  dtype=torch.uint8, device=self.device)
+        self.ws_tvf = torch.zeros(max(int(self.lib.ppo_tvf_workspace_bytes(self.steps, self.envs)), 1 << 12),
+                                  dtype=torch.uint8, device=self.device)
+        self._ctab = self._blob = None
+        self.kernel_launches_per_pass = 4
+
+    def set_samples(self, n_step_samples):
+        tabs = _rt._tvf_tables.build(self.tvf_gamma, self.steps, self.horizons, self.horizons, n_step_samples,
+                                     self.use_log)
+        self._ctab, self._blob = _rt._upload_tables(tabs, self.device)
+        return tabs
+
+    def run(self, rewards, values, dones, value_samples, tvf_events=None):
+        """``rewards [N, A] f32``, ``values [N+1, A] f32`` (row N = final estimate; any strides with a
+        unit-stride env axis or a strided view of the value-sample buffer), ``dones [N, A] uint8``,
+        ``value_samples [N+1, A, K] f32`` -- all CUDA tensors of this rank's env block."""
+        assert self._ctab is not None, "call set_samples() first"
+        lib, s = self.lib, dev.stream_ptr()
+        n, a, k = self.steps, self.envs, self.n_h
+        rc = lib.ppo_gae(rewards.data_ptr(), rewards.stride(0), values.data_ptr(), values.stride(0), values.stride(1),
+                         values[n].data_ptr(), values.stride(1), dones.data_ptr(), _lib.DONE_U8, dones.stride(0),
+                         n, a, self.gamma, self.lambda_policy, self.lambda_value,
+                         self.advantage.data_ptr(), self.ext_returns.data_ptr(), self.stats.data_ptr(),
+                         self.ws_gae.data_ptr(), self.ws_gae.numel(), s)
+        _lib.check(rc, "ppo_gae")
+        if self.sharded:
+            dist.all_reduce(self._moments, op=dist.ReduceOp.SUM, group=self.group)
+        rc = lib.ppo_adv_normalize(self.advantage.data_ptr(), n * a, self.stats.data_ptr(), self.eps, self.clip,
+                                   self.advantages.data_ptr(), s)
+        _lib.check(rc, "ppo_adv_normalize")
+        if tvf_events is not None:  # (start, mid, end): target kernel between start..mid, statistics mid..end
+            tvf_events[0].record()
+        rc = lib.ppo_tvf_targets(rewards.data_ptr(), rewards.stride(0), dones.data_ptr(), _lib.DONE_U8, dones.stride(0),
+                                 value_samples.data_ptr(), value_samples.stride(0), value_samples.stride(1),
+                                 n, a, k, k, ctypes.byref(self._ctab), self.tvf_path, self.tvf_returns.data_ptr(),
+                                 0, 0, 0, s)
+        _lib.check(rc, "ppo_tvf_targets")
+        if tvf_events is not None:
+            tvf_events[1].record()
+        rc = lib.ppo_tvf_last_horizon_stats(self.tvf_returns.data_ptr(), n * a, k, self.tvf_stats.data_ptr(),
+                                            self.ws_tvf.data_ptr(), self.ws_tvf.numel(), s)
+        _lib.check(rc, "ppo_tvf_last_horizon_stats")
+        if tvf_events is not None:
+            tvf_events[2].record()
+        return self
+
+
+def stats_summary(stats):
+    """mean / std / min / max of the advantages and returns from a statistics record (host floats),
+    the quantities the reference logs at ``rl/rollout.py:1252-1256``."""
+    s = stats.detach().cpu().numpy()
+    n = max(s[_lib.STAT_COUNT], 1.0)
+
+    def ms(total, sq):
+        mean = total / n
+        return mean, float(np.sqrt(max(sq / n - mean * mean, 0.0)))
+
+    adv_mean, adv_std = ms(s[_lib.STAT_ADV_SUM], s[_lib.STAT_ADV_SUMSQ])
+    ret_mean, ret_std = ms(s[_lib.STAT_RET_SUM], s[_lib.STAT_RET_SUMSQ])
+    return {"count": int(s[_lib.STAT_COUNT]),
+            "adv_mean": adv_mean, "adv_std": adv_std, "adv_min": s[_lib.STAT_ADV_MIN], "adv_max": s[_lib.STAT_ADV_MAX],
+            "ret_mean": ret_mean, "ret_std": ret_std, "ret_min": s[_lib.STAT_RET_MIN], "ret_max": s[_lib.STAT_RET_MAX]}

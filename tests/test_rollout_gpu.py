@@ -1,0 +1,109 @@
+"""GPU parity of the return stage (ppo_b200.rollout): fused GAE + TD(lambda) + statistics, advantage
+normalisation (rl/rollout.py:1887-1897) and the device-resident ReturnPass against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from ppo_b200 import returns_truncated as rt
+from ppo_b200 import rollout, synthetic
+from util import TOL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def test_advantage_normalisation_golden(golden):
+    adv = golden["gae_bool"]
+    assert rel_err(rollout.normalize_advantages(adv), golden["advnorm"]) <= TOL
+    got = rollout.normalize_advantages(adv, epsilon=1e-8, clipping=1.5)
+    assert rel_err(got, golden["advnorm_clip"]) <= TOL
+    assert got.min() >= -1.5 and got.max() <= 1.5
+
+
+@pytest.mark.parametrize("steps,envs", [(256, 4096), (128, 128), (17, 5), (1, 1)])
+def test_normalise_vs_oracle(steps, envs):
+    r, d, v = synthetic.rollout(steps, envs, seed=envs)
+    adv = oracle.gae(r, v[:-1], v[-1], d, 0.999, 0.95)
+    ref = oracle.normalize_advantages(adv)
+    got = rollout.normalize_advantages(adv)
+    assert got.shape == ref.shape and got.dtype == np.float32
+    if steps * envs > 1:
+        assert rel_err(got, ref) <= TOL
+    clipped = rollout.normalize_advantages(adv, clipping=0.5)
+    assert rel_err(clipped, oracle.normalize_advantages(adv, clipping=0.5)) <= TOL
+
+
+def test_calculate_returns_matches_oracle():
+    steps, envs = 96, 160
+    hz = oracle.get_value_head_horizons(64, 3000)
+    r, d, v = synthetic.rollout(steps, envs, seed=21)
+    vs = synthetic.value_samples(steps, envs, len(hz), seed=21)
+    res = rollout.calculate_returns(r, v, d, 0.999, 0.95, 0.9, advantage_clipping=2.0,
+                                    tvf=dict(value_samples=vs, horizons=hz, gamma=0.9999, mode="advanced",
+                                             distribution="exponential", n_step=12, max_samples=6, seed=4))
+    adv = oracle.gae(r, v[:-1], v[-1], d, 0.999, 0.95)
+    assert rel_err(res["advantage"], adv) <= TOL
+    assert rel_err(res["ext_returns"], oracle.td_lambda(r, v[:-1], v[-1], d, 0.999, 0.9)) <= TOL
+    assert rel_err(res["advantages"], oracle.normalize_advantages(adv, clipping=2.0)) <= TOL
+    ref = oracle.get_return_estimate("exponential", "advanced", 0.9999, r, d, hz, hz, vs, n_step=12, max_samples=6, seed=4)
+    assert rel_err(res["tvf_returns"], ref) <= TOL
+    summary = rollout.stats_summary(res["stats"])
+    assert summary["count"] == adv.size
+    np.testing.assert_allclose(summary["adv_mean"], adv.astype(np.float64).mean(), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(summary["adv_std"], adv.astype(np.float64).std(), rtol=1e-9)
+    t = rollout.stats_summary(res["tvf_stats"])
+    last = np.asarray(res["tvf_returns"])[:, :, -1].astype(np.float64)
+    assert t["adv_min"] == last.min() and t["adv_max"] == last.max()
+
+
+def test_return_pass_resident_and_pinned_out():
+    steps, envs = 64, 200
+    hz = oracle.get_value_head_horizons(128, 30000)
+    r, d, _ = synthetic.rollout(steps, envs, seed=33)
+    vs = synthetic.value_samples(steps, envs, len(hz), seed=33)
+    v = vs[:, :, -1]  # the trainer's value estimate is the longest horizon of the TVF buffer (rl/tvf.py:325-340)
+    table = rt.draw_n_step_samples("exponential", "advanced", hz, steps, 20, 8, seed=1)
+    dr, dd, dvs = torch.from_numpy(r).cuda(), torch.from_numpy(d).cuda().view(torch.uint8), torch.from_numpy(vs).cuda()
+    rp = rollout.ReturnPass(steps, envs, hz, 0.999, 0.99997, 0.95, 0.9)
+    rp.set_samples(table)
+    for _ in range(2):  # twice: tickets and workspaces must be left reusable
+        rp.run(dr, dvs[:, :, -1], dd, dvs)
+    torch.cuda.synchronize()
+    adv = oracle.gae(r, v[:-1], v[-1], d, 0.999, 0.95)
+    assert rel_err(rp.advantage.cpu().numpy(), adv) <= TOL
+    assert rel_err(rp.ext_returns.cpu().numpy(), oracle.td_lambda(r, v[:-1], v[-1], d, 0.999, 0.9)) <= TOL
+    assert rel_err(rp.advantages.cpu().numpy(), oracle.normalize_advantages(adv)) <= TOL
+    ref = oracle.sampled_return_multi(0.99997, r, d, hz, hz, vs, n_step_samples=table)
+    assert rel_err(rp.tvf_returns.cpu().numpy(), ref) <= TOL
+    # the host path with pinned buffers delivers the same bits as the resident pass
+    out = {"advantage": torch.empty((steps, envs)).pin_memory(), "tvf_returns": torch.empty((steps, envs, len(hz))).pin_memory()}
+    res = rollout.calculate_returns(torch.from_numpy(r).pin_memory(), torch.from_numpy(np.ascontiguousarray(v)).pin_memory(),
+                                    torch.from_numpy(d).pin_memory(), 0.999, 0.95, 0.9,
+                                    tvf=dict(value_samples=torch.from_numpy(vs).pin_memory(), horizons=hz, gamma=0.99997,
+                                             mode="advanced", distribution="exponential", n_step=20, max_samples=8, seed=1),
+                                    out=out)
+    assert res["tvf_returns"] is out["tvf_returns"]
+    assert torch.equal(out["tvf_returns"], rp.tvf_returns.cpu())
+    assert torch.equal(out["advantage"], rp.advantage.cpu())
+
+
+def test_env_sharding_is_exact_on_one_gpu():
+    """Two env shards processed separately + summed moments == the unsharded pass (the N > 1 data path without NCCL)."""
+    steps, envs = 80, 130
+    r, d, v = synthetic.rollout(steps, envs, seed=8)
+    full = rollout.calculate_returns(r, v, d, 0.999, 0.95, 0.95)
+    parts, stats = [], []
+    for rank in range(2):
+        rs, vs_, ds = (rollout.shard_envs(x, rank, 2) for x in (r, v, d))
+        res = rollout.calculate_returns(np.ascontiguousarray(rs), np.ascontiguousarray(vs_), np.ascontiguousarray(ds),
+                                        0.999, 0.95, 0.95)
+        parts.append(res)
+        stats.append(res["local_stats"])
+    merged = rollout.merge_stats(stats)
+    assert np.array_equal(np.concatenate([p["advantage"] for p in parts], axis=1), full["advantage"])
+    s_full, s_merged = full["stats"].cpu().numpy(), merged.cpu().numpy()
+    assert s_full[0] == s_merged[0] and s_full[3] == s_merged[3] and s_full[4] == s_merged[4]
+    np.testing.assert_allclose(s_merged[1:3], s_full[1:3], rtol=1e-12)
+    norm = [rollout.normalize_advantages(p["advantage"], stats=merged) for p in parts]
+    got = np.concatenate([n.reshape(steps, -1) for n in norm], axis=1).reshape(-1)
+    assert rel_err(got, full["advantages"]) <= 1e-6
