@@ -18,6 +18,8 @@
 //                   (constant), so the reward part of every entry is a plain table read
 //   warp 18         TMA producer (one elected lane)
 // HBM traffic = value rows read once + targets written once + the reward/done columns.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "tma.cuh"
@@ -37,6 +39,7 @@ constexpr int kColRegs = kMaxSteps / 32;
 struct RingParams {
     TvfParams p;
     int nslot, menv, cpe, ncht, npad, kb;
+    int dbg;  // development switches (PPO_TVF_DEBUG): 1 no stores, 2 no TMA loads, 4 no scan loop, 8 no entry loop
     uint32_t slab_bytes;
     uint32_t pt_buf_bytes;      // one prefix table: (nmax + 1) rows of TC + 4 floats
     int64_t env_base, env_rem;  // even split of the env axis over the grid
@@ -119,6 +122,7 @@ __device__ __forceinline__ void eval_group(const RingParams& q, const LaneEntrie
     }
 
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (!(q.dbg & 8))
 #pragma unroll
     for (int i = 0; i < E; ++i) {
         const float4 s = lds_f32x4(pt + static_cast<uint32_t>(L.soff[i]));
@@ -156,7 +160,7 @@ __device__ __forceinline__ void eval_group(const RingParams& q, const LaneEntrie
             }
         }
     }
-    if (k_ok) {
+    if (k_ok && !(q.dbg & 1)) {
         const float inv_c = p.tab.inv_c;
         const int64_t ostride = p.envs * static_cast<int64_t>(K);
         __stcs(o, a0 * inv_c);
@@ -315,6 +319,11 @@ tvf_ring_kernel(const RingParams q, const __grid_constant__ CUtensorMap vmap) {
                 const int env = static_cast<int>(env0 + e);
                 for (int c = 0; c < q.cpe; ++c) {
                     mbar_wait(&empty[slot], par ^ 1);
+                    if (q.dbg & 2) {
+                        mbar_arrive(&full[slot]);
+                        if (++slot == q.nslot) slot = 0, par ^= 1;
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&full[slot], CHUNK);
                     tma_load_3d(ring + static_cast<size_t>(slot) * CHUNK, &vmap, &full[slot], 0, env, c * kRC + 1);
                     if (++slot == q.nslot) slot = 0, par ^= 1;
@@ -400,7 +409,7 @@ tvf_ring_kernel(const RingParams q, const __grid_constant__ CUtensorMap vmap) {
                 // float32 accumulation in forward order like rl/returns_truncated.py:668; adding r * 0 is a no-op,
                 // so the sum simply stops growing after the terminal step and the row continues as a constant.
                 float acc = 0.f;
-                for (int i0 = 0; i0 < nmax; i0 += 8) {
+                for (int i0 = 0; i0 < ((q.dbg & 4) ? 1 : nmax); i0 += 8) {
                     float rr[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) rr[u] = r_col[i0 + u];
@@ -526,6 +535,10 @@ int launch_tvf_ring(const TvfParams& p, const float* tail_wlo, const float* tail
 
     RingParams q{};
     q.p = p;
+    {
+        const char* d = getenv("PPO_TVF_DEBUG");
+        q.dbg = d ? atoi(d) : 0;
+    }
     q.tail_wlo = tail_wlo, q.tail_whi = tail_whi;
     int kb = 1;
     while (kb * 32 < K) kb <<= 1;
