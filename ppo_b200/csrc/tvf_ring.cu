@@ -12,11 +12,14 @@
 //   warps 0-15      consumers: lane <-> horizon k (entry constants live in registers for the whole
 //                   kernel); a warp evaluates groups of 4 consecutive time rows; per (4 rows, k, entry)
 //                   one 16-byte prefix read and eight slab reads; results stream to HBM as 128-byte rows
-//   warps 16-17     prefix-sum ("scan") warps: PT[n][t] = S_n(t,a) and the bootstrap limit of row t for
-//                   TC rows at a time, double buffered, one lane per time row, float32 accumulation in
-//                   reference order; rows are continued past a terminal / past the rollout end
-//                   (constant), so the reward part of every entry is a plain table read
-//   warp 18         TMA producer (one elected lane)
+//   warps 16-19     prefix-sum ("scan") warps: PT[n][t] = S_n(t,a) and the bootstrap limit of row t for
+//                   blocks of 32 rows, through a ring of 4 tables (warp w owns ring slot w), one lane per
+//                   time row, float32 accumulation in reference order; rows are continued past a
+//                   terminal / past the rollout end (constant), so the reward part of every entry is a
+//                   plain table read.  The reward / done columns of an env are staged in shared memory
+//                   two envs ahead with 4-byte cp.async copies (no registers, no stall on their latency)
+//   warp 20         TMA producer (one elected lane)
+// Every hand-off is an mbarrier ring, so no role ever waits for a whole-CTA barrier.
 // HBM traffic = value rows read once + targets written once + the reward/done columns.
 #include <stdlib.h>
 
@@ -27,26 +30,28 @@
 
 namespace ppo {
 
-constexpr int kRC = 16;            // value rows per TMA chunk
+constexpr int kRC = 64;            // value rows per TMA chunk
+constexpr int kTB = 32;            // time rows per prefix-table block
+constexpr int kPRing = 4;          // prefix-table ring slots (block g of the env-major sequence uses slot g % kPRing)
+constexpr int kColRing = 4;        // reward/done column ring (envs)
 constexpr int kTG = 4;             // consecutive time rows evaluated together by a consumer warp
 constexpr int kConsumerWarps = 16;
-constexpr int kRingScanWarps = 2;
+constexpr int kRingScanWarps = 2;  // warp w fills blocks g = w, w + 2, ...
 constexpr int kRingThreads = (1 + kRingScanWarps + kConsumerWarps) * 32;
 constexpr int kEMax = 8;           // entries per horizon kept in registers
-constexpr int kMaxSteps = 512;     // reward/done columns are prefetched through registers
-constexpr int kColRegs = kMaxSteps / 32;
+constexpr int kMaxSteps = 512;
 
 struct RingParams {
     TvfParams p;
-    int nslot, menv, cpe, ncht, npad, kb;
+    int nslot, menv, cpe, nblk, npad, kb;
     int dbg;  // development switches (PPO_TVF_DEBUG): 1 no stores, 2 no TMA loads, 4 no scan loop, 8 no entry loop
     uint32_t slab_bytes;
-    uint32_t pt_buf_bytes;      // one prefix table: (nmax + 1) rows of TC + 4 floats
+    uint32_t pt_buf_bytes;      // one prefix table: (nmax + 1) rows of kTB + 4 floats
     int64_t env_base, env_rem;  // even split of the env axis over the grid
     const float* tail_wlo;      // [nmax + 1, K] weights of the bootstrap from the final row (see launch)
     const float* tail_whi;
     // shared-memory offsets (bytes)
-    uint32_t off_p, off_nd, off_rs, off_ds, off_gpow, off_bar, smem_total;
+    uint32_t off_p, off_lim, off_colr, off_cold, off_dm, off_gpow, off_bar, smem_total;
 };
 
 // explicit shared-window loads: 32-bit address register + immediate offset
@@ -82,7 +87,7 @@ struct ConsumerCtx {
 // Entry constants of one lane (= one horizon), registers for the whole kernel.
 template <int E>
 struct LaneEntries {
-    int soff[E];    // n * (TC + 4) * 4: byte offset of prefix row n; also the unit the row limits are stored in
+    int soff[E];    // n * (kTB + 4) * 4: byte offset of prefix row n; also the unit the row limits are stored in
     int voff[E];    // (n - 1) * row bytes + lo * 4: byte offset of the bootstrap pair relative to slab row t
     float cnt[E];   // multiplicity
     float wlo[E];   // multiplicity * gamma^n * lerp weights
@@ -91,12 +96,12 @@ struct LaneEntries {
 };
 
 // One group of kTG consecutive time rows for 32 horizons.  TAIL: some window reaches past the rollout.
-template <int V, int TC, int E, bool TAIL>
+template <int V, int E, bool TAIL>
 __device__ __forceinline__ void eval_group(const RingParams& q, const LaneEntries<E>& L, uint32_t pt, uint32_t lim_addr,
                                            uint32_t vrow, uint32_t cap, uint32_t fin, int t, int rows_left, int k,
                                            bool k_ok, float* o) {
     constexpr int RB = V * 4;
-    constexpr int TCP4 = (TC + 4) * 4;
+    constexpr int TCP4 = (kTB + 4) * 4;
     const TvfParams& p = q.p;
     const int N = p.steps, K = p.n_req, nmax = p.tab.nmax;
     // lim[u] = min(N - t, first terminal) in prefix-row units: an entry bootstraps inside the rollout iff soff <= lim
@@ -172,10 +177,10 @@ __device__ __forceinline__ void eval_group(const RingParams& q, const LaneEntrie
 
 // Consumer warp body, E = number of live entry slots of this warp's 32 horizons (compile time, so
 // the evaluation of one 4-row group is straight-line code the scheduler can overlap freely).
-template <int V, int TC, int E>
+template <int V, int E>
 __device__ __forceinline__ void consume(const RingParams& q, const ConsumerCtx& c) {
     constexpr int RB = V * 4;
-    constexpr int TCP4 = (TC + 4) * 4;
+    constexpr int TCP4 = (kTB + 4) * 4;
     const TvfParams& p = q.p;
     const int N = p.steps, K = p.n_req, nmax = p.tab.nmax;
     const int lane = c.lane;
@@ -212,7 +217,7 @@ __device__ __forceinline__ void consume(const RingParams& q, const ConsumerCtx& 
     }
 
     const int64_t ostride = p.envs * static_cast<int64_t>(K);
-    uint32_t pf_par0 = 0, pf_par1 = 0;
+    uint32_t blk = 0;  // global prefix-block counter (env-major): ring slot blk % kPRing, use blk / kPRing
 
     for (int e = 0; e < c.nenv; ++e) {
         const int64_t env = c.env0 + e;
@@ -224,35 +229,34 @@ __device__ __forceinline__ void consume(const RingParams& q, const ConsumerCtx& 
         const int slot0 = slab * q.cpe;
         float* out_env = p.out + env * K + k;
         int waited = 0, released = 0;  // chunks of this env
-        for (int j = 0; j < q.ncht; ++j) {
-            const int gsel = (e * q.ncht + j) & 1;
-            if (gsel == 0) mbar_wait(&c.pfull[0], pf_par0), pf_par0 ^= 1;
-            else mbar_wait(&c.pfull[1], pf_par1), pf_par1 ^= 1;
+        for (int j = 0; j < q.nblk; ++j, ++blk) {
+            const uint32_t ps = blk % kPRing;
+            mbar_wait(&c.pfull[ps], (blk / kPRing) & 1);
 
-            const int t_hi = min(N, j * TC + TC - 1 + nmax);
+            const int t_hi = min(N, j * kTB + kTB - 1 + nmax);
             const int cneed = (t_hi - 1) / kRC;
             while (waited <= cneed) {
                 mbar_wait(&c.full[slot0 + waited], fpar);
                 ++waited;
             }
 
-            const int rows = min(TC, N - j * TC);
-            const uint32_t pt_buf = c.p_a + static_cast<uint32_t>(gsel) * q.pt_buf_bytes;
-            const uint32_t lim_buf = c.lim_a + static_cast<uint32_t>(gsel * TC) * 4u;
+            const int rows = min(kTB, N - j * kTB);
+            const uint32_t pt_buf = c.p_a + ps * q.pt_buf_bytes;
+            const uint32_t lim_buf = c.lim_a + ps * (kTB * 4u);
             for (int tl = tg * kTG; tl < rows; tl += ntg * kTG) {
-                const int t = j * TC + tl;
+                const int t = j * kTB + tl;
                 const uint32_t pt = pt_buf + static_cast<uint32_t>(tl) * 4u;
                 const uint32_t lim_addr = lim_buf + static_cast<uint32_t>(tl) * 4u;
                 const uint32_t vrow = slab_a + static_cast<uint32_t>(t) * RB;
                 float* o = out_env + static_cast<int64_t>(t) * ostride;
                 if (t + (kTG - 1) + nmax > N)  // warp-uniform
-                    eval_group<V, TC, E, true>(q, L, pt, lim_addr, vrow, cap, fin, t, rows - tl, k, k_ok, o);
+                    eval_group<V, E, true>(q, L, pt, lim_addr, vrow, cap, fin, t, rows - tl, k, k_ok, o);
                 else
-                    eval_group<V, TC, E, false>(q, L, pt, lim_addr, vrow, cap, fin, t, rows - tl, k, k_ok, o);
+                    eval_group<V, E, false>(q, L, pt, lim_addr, vrow, cap, fin, t, rows - tl, k, k_ok, o);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&c.pempty[gsel]);
-            const int rel_end = (j == q.ncht - 1) ? q.cpe : min(q.cpe, ((j + 1) * TC) / kRC);
+            if (lane == 0) mbar_arrive(&c.pempty[ps]);
+            const int rel_end = (j == q.nblk - 1) ? q.cpe : min(q.cpe, ((j + 1) * kTB) / kRC);
             while (released < rel_end) {
                 if (lane == 0) mbar_arrive(&c.empty[slot0 + released]);
                 ++released;
@@ -261,28 +265,31 @@ __device__ __forceinline__ void consume(const RingParams& q, const ConsumerCtx& 
     }
 }
 
-// V = value horizons (row of V floats), TC = time rows per prefix chunk
-template <int V, int TC>
+// V = value horizons (row of V floats)
+template <int V>
 __global__ void __launch_bounds__(kRingThreads, 1)
 tvf_ring_kernel(const RingParams q, const __grid_constant__ CUtensorMap vmap) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int RB = V * 4;               // bytes per value row
     constexpr uint32_t CHUNK = kRC * RB;    // bytes per TMA chunk
-    constexpr int TCP = TC + 4;             // pitch (floats) of one prefix-table row
+    constexpr int TCP = kTB + 4;            // pitch (floats) of one prefix-table row
     const TvfParams& p = q.p;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = p.steps, K = p.n_req, nmax = p.tab.nmax;
 
     unsigned char* ring = smem;
-    float* PT = reinterpret_cast<float*>(smem + q.off_p);       // [2][nmax + 1][TCP]
-    int* lim_s = reinterpret_cast<int*>(smem + q.off_nd);       // [2][TC]
-    float* rs = reinterpret_cast<float*>(smem + q.off_rs);      // [scan warp][2][npad]
-    unsigned char* ds = smem + q.off_ds;                        // [scan warp][2][npad / 32] done bitmask words
-    float* gpow_s = reinterpret_cast<float*>(smem + q.off_gpow);  // [nmax + 8]
+    float* PT = reinterpret_cast<float*>(smem + q.off_p);          // [kPRing][nmax + 1][TCP]
+    int* lim_s = reinterpret_cast<int*>(smem + q.off_lim);         // [kPRing][kTB]
+    float* col_r = reinterpret_cast<float*>(smem + q.off_colr);    // [kColRing][npad] rewards, zero past N
+    uint32_t* col_d = reinterpret_cast<uint32_t*>(smem + q.off_cold);  // [kColRing][npad] raw done words
+    uint32_t* dm_s = reinterpret_cast<uint32_t*>(smem + q.off_dm);     // [scan warp][npad / 32] done bitmask
+    float* gpow_s = reinterpret_cast<float*>(smem + q.off_gpow);   // [nmax + 8]
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + q.off_bar);
     uint64_t* empty = full + q.nslot;
     uint64_t* pfull = empty + q.nslot;
-    uint64_t* pempty = pfull + 2;
+    uint64_t* pempty = pfull + kPRing;
+    uint64_t* cfull = pempty + kPRing;
+    uint64_t* cempty = cfull + kColRing;
 
     const int64_t b = blockIdx.x;
     const int nenv = static_cast<int>(q.env_base + (b < q.env_rem ? 1 : 0));
@@ -293,15 +300,19 @@ tvf_ring_kernel(const RingParams q, const __grid_constant__ CUtensorMap vmap) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], kConsumerWarps);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kPRing; ++i) {
             mbar_init(&pfull[i], 1);
             mbar_init(&pempty[i], kConsumerWarps);
+        }
+        for (int i = 0; i < kColRing; ++i) {
+            mbar_init(&cfull[i], 32);              // one cp.async-completion arrival per copying lane
+            mbar_init(&cempty[i], kRingScanWarps);
         }
         mbar_fence_init();
         tma_prefetch_desc(&vmap);
     }
-    // Slab and prefix memory start finite: entries whose bootstrap is switched off still read them,
-    // and prefix row 0 (S_0 = 0) is never written again.
+    // Slab, prefix and column memory start finite / zero: entries whose bootstrap is switched off still read
+    // the slab, prefix row 0 (S_0 = 0) is never written again, and reward rows past N stay zero.
     for (uint32_t i = threadIdx.x * 16u; i < q.off_bar; i += blockDim.x * 16u)
         *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
     __syncthreads();
@@ -321,88 +332,103 @@ tvf_ring_kernel(const RingParams q, const __grid_constant__ CUtensorMap vmap) {
                     mbar_wait(&empty[slot], par ^ 1);
                     if (q.dbg & 2) {
                         mbar_arrive(&full[slot]);
-                        if (++slot == q.nslot) slot = 0, par ^= 1;
-                        continue;
+                    } else {
+                        // a box that reaches past row N is zero-filled by the TMA unit and still counts in full
+                        mbar_arrive_expect_tx(&full[slot], CHUNK);
+                        tma_load_3d(ring + static_cast<size_t>(slot) * CHUNK, &vmap, &full[slot], 0, env, c * kRC + 1);
                     }
-                    mbar_arrive_expect_tx(&full[slot], CHUNK);
-                    tma_load_3d(ring + static_cast<size_t>(slot) * CHUNK, &vmap, &full[slot], 0, env, c * kRC + 1);
                     if (++slot == q.nslot) slot = 0, par ^= 1;
                 }
             }
         }
     } else if (warp >= kConsumerWarps) {
         // ------------------------------------------------------------------ prefix-sum warps
-        const int s = warp - kConsumerWarps;
-        float* my_rs = rs + static_cast<size_t>(s) * 2 * q.npad;
+        const int w = warp - kConsumerWarps;
         const int dm_words = q.npad / 32;
-        uint32_t* my_dm = reinterpret_cast<uint32_t*>(ds) + static_cast<size_t>(s) * 2 * dm_words;  // bit r%32 of word r/32
-        float* myPT = PT + static_cast<size_t>(s) * (q.pt_buf_bytes / 4);
-        int* my_lim = lim_s + s * TC;
-        const int total = nenv * q.ncht;
-        int cur = 0;       // which private column buffer holds the current env
-        uint32_t use = 0;  // how many times this warp has filled its prefix buffer
+        uint32_t* my_dm = dm_s + static_cast<size_t>(w) * dm_words;  // bit r % 32 of word r / 32
+        const int total = nenv * q.nblk;
+        const int ncols = (N + 31) / 32;  // 32-row groups of a column
 
-        float cr[kColRegs];
-        uint32_t cd[kColRegs / 4];
-        auto load_cols = [&](int e_local) {
-            const int64_t env = env0 + e_local;
-#pragma unroll
-            for (int i = 0; i < kColRegs / 4; ++i) cd[i] = 0;
-#pragma unroll
-            for (int i = 0; i < kColRegs; ++i) {
+        // Stage the reward / done columns of local env `ec` (this warp's duty when ec % scan warps == w).
+        auto stage_cols = [&](int ec) {
+            const int cs = ec % kColRing;
+            mbar_wait(&cempty[cs], ((ec / kColRing) & 1) ^ 1);
+            const int64_t env = env0 + ec;
+            float* dr = col_r + static_cast<size_t>(cs) * q.npad;
+            uint32_t* dd = col_d + static_cast<size_t>(cs) * q.npad;
+            for (int i = 0; i < ncols; ++i) {
                 const int row = i * 32 + lane;
-                cr[i] = 0.f;
                 if (row < N) {
-                    cr[i] = __ldg(p.rewards + static_cast<int64_t>(row) * p.r_rs + env);
-                    const uint32_t dn = done_at(p.dones, p.done_kind, static_cast<int64_t>(row) * p.d_rs + env) ? 1u : 0u;
-                    cd[i / 4] |= dn << (8 * (i % 4));
+                    cp_async_4(dr + row, p.rewards + static_cast<int64_t>(row) * p.r_rs + env);
+                    if (p.done_kind == PPO_DONE_U8) {
+                        const uintptr_t a = reinterpret_cast<uintptr_t>(p.dones) + static_cast<uint64_t>(row) * p.d_rs + env;
+                        cp_async_4(dd + row, reinterpret_cast<const void*>(a & ~static_cast<uintptr_t>(3)));
+                    } else if (p.done_kind == PPO_DONE_F32) {
+                        cp_async_4(dd + row, static_cast<const float*>(p.dones) + static_cast<int64_t>(row) * p.d_rs + env);
+                    }
                 }
             }
+            cp_async_mbar_arrive(&cfull[cs]);
         };
-        auto store_cols = [&](int buf) {
-#pragma unroll
-            for (int i = 0; i < kColRegs; ++i) {
-                const int row = i * 32 + lane;
-                const uint32_t dn = (cd[i / 4] >> (8 * (i % 4))) & 0xffu;
-                const uint32_t word = __ballot_sync(0xffffffffu, dn != 0);
-                if (i * 32 < N) {  // rows >= N stay zero: the prefix rows continue as constants past the rollout
-                    if (row < N) my_rs[buf * q.npad + row] = cr[i];
-                    if (lane == 0) my_dm[buf * dm_words + i] = word;
+        for (int ec = 0; ec < 2 && ec < nenv; ++ec)
+            if (ec % kRingScanWarps == w) stage_cols(ec);
+
+        int e_cur = -1;
+        const float* r_env = col_r;
+        for (int g = w; g < total; g += kRingScanWarps) {
+            const int e = g / q.nblk, j = g - e * q.nblk;
+            // Every scan warp visits every env in order (even one in which it owns no block), so the column
+            // ring's full / empty phases advance in lock step for all four warps.
+            while (e_cur < e) {
+                if (e_cur >= 0 && lane == 0) mbar_arrive(&cempty[e_cur % kColRing]);
+                ++e_cur;
+                const int ec = e_cur + 2;  // staged two envs ahead
+                if (ec < nenv && ec % kRingScanWarps == w) stage_cols(ec);
+                mbar_wait(&cfull[e_cur % kColRing], (e_cur / kColRing) & 1);
+                if (e_cur == e) {
+                    // done bitmask of the env (private copy)
+                    const int cs = e % kColRing;
+                    const uint32_t* dd = col_d + static_cast<size_t>(cs) * q.npad;
+                    for (int i = 0; i < ncols; ++i) {
+                        const int row = i * 32 + lane;
+                        bool dn = false;
+                        if (row < N) {
+                            const uint32_t wd = dd[row];
+                            if (p.done_kind == PPO_DONE_U8) {
+                                const uint32_t a = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(p.dones) +
+                                                                         static_cast<uint64_t>(row) * p.d_rs + (env0 + e));
+                                dn = ((wd >> (8 * (a & 3u))) & 0xffu) != 0;
+                            } else if (p.done_kind == PPO_DONE_F32) {
+                                dn = __uint_as_float(wd) != 0.f;
+                            }
+                        }
+                        const uint32_t word = __ballot_sync(0xffffffffu, dn);
+                        if (lane == 0) my_dm[i] = word;
+                    }
+                    __syncwarp();
+                    r_env = col_r + static_cast<size_t>(cs) * q.npad;
                 }
             }
-            __syncwarp();
-        };
 
-        if (s < total) {
-            load_cols(s / q.ncht);
-            store_cols(cur);
-        }
-        for (int g = s; g < total; g += kRingScanWarps) {
-            const int e = g / q.ncht, j = g - e * q.ncht;
-            const int g_next = g + kRingScanWarps;
-            const int e_next = g_next < total ? g_next / q.ncht : e;
-            const bool switch_env = e_next != e;
-            if (switch_env) load_cols(e_next);  // in flight while this chunk is computed
-
-            mbar_wait(&pempty[s], (use & 1) ^ 1);
-#pragma unroll 1
-            for (int sp = 0; sp < TC / 32; ++sp) {
-                const int tl = sp * 32 + lane;
-                const int t = j * TC + tl;  // rows past the rollout read zero rewards
-                const float* r_col = my_rs + cur * q.npad + t;
-                float* col = myPT + tl;
+            const int ps = g % kPRing;
+            float* myPT = PT + static_cast<size_t>(ps) * (q.pt_buf_bytes / 4);
+            int* my_lim = lim_s + ps * kTB;
+            mbar_wait(&pempty[ps], ((g / kPRing) & 1) ^ 1);
+            {
+                const int t = j * kTB + lane;  // rows past the rollout read zero rewards
+                const float* r_col = r_env + t;
+                float* col = myPT + lane;
                 // distance to the first terminal at or after t (only terminals inside the n-step window matter)
                 int first_done = kNoDone;
                 {
-                    const int w0 = t >> 5;  // == j * TC / 32 + sp
-                    const uint32_t* dm = my_dm + cur * dm_words + w0;
+                    const uint32_t* dm = my_dm + j;
                     uint32_t m = dm[0] & (0xffffffffu << lane);
                     const int words = (nmax + 31 + 31) / 32;
                     int base = -lane;
-                    for (int w = 0; w < words; ++w) {
+                    for (int wi = 0; wi < words; ++wi) {
                         if (first_done == kNoDone && m != 0u) first_done = base + __ffs(m) - 1;
                         base += 32;
-                        m = (w0 + w + 1 < dm_words) ? dm[w + 1] : 0u;
+                        m = (j + wi + 1 < ncols) ? dm[wi + 1] : 0u;
                     }
                 }
                 // S_n(t) = sum_{i<n} float32(r[t+i] * D_i), D_i = gamma^i while no terminal lies in t..t+i-1, else 0:
@@ -425,16 +451,18 @@ tvf_ring_kernel(const RingParams q, const __grid_constant__ CUtensorMap vmap) {
                         }
                     }
                 }
-                my_lim[tl] = min(N - t, first_done) * (TCP * 4);  // bootstrap limit of the row, in prefix-row bytes
+                my_lim[lane] = min(N - t, first_done) * (TCP * 4);  // bootstrap limit of the row, in prefix-row bytes
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&pfull[s]);
-            ++use;
-
-            if (switch_env) {
-                cur ^= 1;
-                store_cols(cur);
-            }
+            if (lane == 0) mbar_arrive(&pfull[ps]);
+        }
+        // drain the column ring protocol for envs after this warp's last block (other warps may still wait on phases)
+        while (e_cur < nenv - 1) {
+            if (e_cur >= 0 && lane == 0) mbar_arrive(&cempty[e_cur % kColRing]);
+            ++e_cur;
+            const int ec = e_cur + 2;
+            if (ec < nenv && ec % kRingScanWarps == w) stage_cols(ec);
+            mbar_wait(&cfull[e_cur % kColRing], (e_cur / kColRing) & 1);
         }
     } else {
         // ------------------------------------------------------------------ consumers
@@ -453,49 +481,49 @@ tvf_ring_kernel(const RingParams q, const __grid_constant__ CUtensorMap vmap) {
         const int ecnt = __reduce_max_sync(0xffffffffu, mine);
         switch (ecnt) {
             case 0:
-            case 1: consume<V, TC, 1>(q, c); break;
-            case 2: consume<V, TC, 2>(q, c); break;
-            case 3: consume<V, TC, 3>(q, c); break;
-            case 4: consume<V, TC, 4>(q, c); break;
-            case 5: consume<V, TC, 5>(q, c); break;
-            case 6: consume<V, TC, 6>(q, c); break;
-            case 7: consume<V, TC, 7>(q, c); break;
-            default: consume<V, TC, 8>(q, c); break;
+            case 1: consume<V, 1>(q, c); break;
+            case 2: consume<V, 2>(q, c); break;
+            case 3: consume<V, 3>(q, c); break;
+            case 4: consume<V, 4>(q, c); break;
+            case 5: consume<V, 5>(q, c); break;
+            case 6: consume<V, 6>(q, c); break;
+            case 7: consume<V, 7>(q, c); break;
+            default: consume<V, 8>(q, c); break;
         }
     }
 }
 
 static uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
-template <int V, int TC>
+template <int V>
 static int launch_variant(RingParams& q, const CUtensorMap& vmap, int64_t grid, cudaStream_t stream) {
-    PPO_CUDA(cudaFuncSetAttribute(tvf_ring_kernel<V, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PPO_CUDA(cudaFuncSetAttribute(tvf_ring_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(q.smem_total)));
-    tvf_ring_kernel<V, TC><<<static_cast<unsigned>(grid), kRingThreads, q.smem_total, stream>>>(q, vmap);
+    tvf_ring_kernel<V><<<static_cast<unsigned>(grid), kRingThreads, q.smem_total, stream>>>(q, vmap);
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;
 }
 
-// Shared-memory plan for a time-chunk length; false when it does not fit.
-static bool plan_smem(RingParams& q, int N, int V, int nmax, int tc, int max_smem) {
+// Shared-memory plan; false when one env slab plus the tables do not fit.
+static bool plan_smem(RingParams& q, int N, int V, int nmax, int max_smem) {
     const uint32_t row_bytes = static_cast<uint32_t>(V) * 4;
     q.cpe = (N + kRC - 1) / kRC;
-    q.ncht = (N + tc - 1) / tc;
-    // reward rows are read as r_col[t + i], t < ncht * tc, i < nmax + 7, zero past N
-    q.npad = ((q.ncht * tc + nmax + 8 + 31) / 32 + 1) * 32;
+    q.nblk = (N + kTB - 1) / kTB;
+    // reward rows are read as r_col[t + i], t < nblk * kTB, i < nmax + 7, zero past N
+    q.npad = ((q.nblk * kTB + nmax + 8 + 31) / 32 + 1) * 32;
     const uint32_t chunk_bytes = kRC * row_bytes;
     q.slab_bytes = static_cast<uint32_t>(q.cpe) * chunk_bytes;
-    q.pt_buf_bytes = static_cast<uint32_t>(nmax + 1) * (tc + 4) * 4u;
-    const uint32_t p_bytes = 2u * q.pt_buf_bytes;
-    const uint32_t nd_bytes = 2u * tc * 4u;
-    const uint32_t rs_bytes = kRingScanWarps * 2u * q.npad * 4u;
-    const uint32_t ds_bytes = align_up(kRingScanWarps * 2u * (q.npad / 32) * 4u, 16);
+    q.pt_buf_bytes = static_cast<uint32_t>(nmax + 1) * (kTB + 4) * 4u;
+    const uint32_t p_bytes = kPRing * q.pt_buf_bytes;
+    const uint32_t lim_bytes = kPRing * kTB * 4u;
+    const uint32_t col_bytes = kColRing * static_cast<uint32_t>(q.npad) * 4u;  // each of rewards / done words
+    const uint32_t dm_bytes = align_up(kRingScanWarps * (q.npad / 32) * 4u, 16);
     const uint32_t gp_bytes = align_up((nmax + 8) * 4u, 16);
-    const uint32_t other = p_bytes + nd_bytes + rs_bytes + ds_bytes + gp_bytes + 256;
+    const uint32_t other = p_bytes + lim_bytes + 2 * col_bytes + dm_bytes + gp_bytes + 256;
     int menv = 0;
     while (menv < 4) {
         const uint64_t need = static_cast<uint64_t>(menv + 1) * q.slab_bytes + other +
-                              (2ull * (menv + 1) * q.cpe + 4) * 8;
+                              (2ull * (menv + 1) * q.cpe + 2 * kPRing + 2 * kColRing) * 8;
         if (need > static_cast<uint64_t>(max_smem)) break;
         ++menv;
     }
@@ -503,12 +531,13 @@ static bool plan_smem(RingParams& q, int N, int V, int nmax, int tc, int max_sme
     q.menv = menv;
     q.nslot = menv * q.cpe;
     q.off_p = align_up(static_cast<uint32_t>(menv) * q.slab_bytes, 128);
-    q.off_nd = q.off_p + p_bytes;
-    q.off_rs = q.off_nd + nd_bytes;
-    q.off_ds = q.off_rs + rs_bytes;
-    q.off_gpow = align_up(q.off_ds + ds_bytes, 16);
+    q.off_lim = q.off_p + p_bytes;
+    q.off_colr = q.off_lim + lim_bytes;
+    q.off_cold = q.off_colr + col_bytes;
+    q.off_dm = q.off_cold + col_bytes;
+    q.off_gpow = align_up(q.off_dm + dm_bytes, 16);
     q.off_bar = align_up(q.off_gpow + gp_bytes, 16);
-    q.smem_total = q.off_bar + (2 * q.nslot + 4) * 8;
+    q.smem_total = q.off_bar + (2 * q.nslot + 2 * kPRing + 2 * kColRing) * 8;
     return q.smem_total <= static_cast<uint32_t>(max_smem);
 }
 
@@ -543,12 +572,8 @@ int launch_tvf_ring(const TvfParams& p, const float* tail_wlo, const float* tail
     int kb = 1;
     while (kb * 32 < K) kb <<= 1;
     q.kb = kb;
-    int tc = 64;  // longer chunks halve the producer/consumer handshakes; fall back when the tables do not fit
-    if (!plan_smem(q, N, V, nmax, tc, max_smem)) {
-        tc = 32;
-        if (!plan_smem(q, N, V, nmax, tc, max_smem))
-            return unsupported("one env slab of value rows plus the prefix tables do not fit in shared memory");
-    }
+    if (!plan_smem(q, N, V, nmax, max_smem))
+        return unsupported("one env slab of value rows plus the prefix tables do not fit in shared memory");
     if (probe_only) return PPO_OK;
 
     CUtensorMap vmap;
@@ -563,13 +588,9 @@ int launch_tvf_ring(const TvfParams& p, const float* tail_wlo, const float* tail
     q.env_base = p.envs / grid;
     q.env_rem = p.envs % grid;
 
-#define PPO_RING_CASE(VV)                                                          \
-    if (V == VV) return tc == 64 ? launch_variant<VV, 64>(q, vmap, grid, stream)   \
-                                 : launch_variant<VV, 32>(q, vmap, grid, stream);
-    PPO_RING_CASE(128)
-    PPO_RING_CASE(64)
-    PPO_RING_CASE(32)
-#undef PPO_RING_CASE
+    if (V == 128) return launch_variant<128>(q, vmap, grid, stream);
+    if (V == 64) return launch_variant<64>(q, vmap, grid, stream);
+    if (V == 32) return launch_variant<32>(q, vmap, grid, stream);
     return unsupported("no kernel variant");
 }
 

@@ -71,6 +71,9 @@ def test_production_horizons_golden(golden):
     (256, 8, 128, 30000, 20, 8, 0.0),      # no terminals at all
     (64, 16, 128, 30000, 64, 1, 0.3),      # n-step == N, many terminals
     (33, 5, 16, 200, 7, 3, 0.1),           # ragged sizes
+    (100, 7, 128, 30000, 20, 8, 0.05),     # slab kernel with a partial last TMA box and a partial last block
+    (45, 3, 32, 1000, 30, 4, 0.1),         # slab kernel, V = 32
+    (70, 301, 64, 5000, 9, 5, 0.02),       # slab kernel, V = 64, more envs than SMs
     (1, 3, 8, 50, 2, 2, 0.0),              # a single step
 ])
 def test_vs_oracle(path, steps, envs, heads, max_h, n_step, samples, done_p):
