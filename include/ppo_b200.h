@@ -160,6 +160,33 @@ typedef struct {
     float inv_c;
 } ppo_tvf_tables;
 
+/* Offsets (in 32-bit words) of the twelve tables inside the packed blob written by ppo_tvf_tables_build, in the
+ * order of the pointer members of ppo_tvf_tables (ent_n ... gpow); every table starts 16-byte aligned. */
+typedef struct {
+    int32_t n_entries;
+    int32_t nmax;
+    int64_t total_words;
+    int64_t offset_words[12];
+    float inv_c;
+} ppo_tvf_table_layout;
+
+/*
+ * HOST-side construction of the index tables (no device work, no rollout data): resolves a [K, C] n-step sample
+ * table exactly like rl/returns_truncated.py:590-591 (clamp to the horizon), :142-174 (searchsorted slot and lerp
+ * weights, float64 arithmetic), :565,:573-574 (log-interpolation axis) and :669 (float32 discount powers).
+ * All pointers are HOST pointers; `blob` receives the packed tables (copy it to the device and add its device
+ * address to the offsets to fill ppo_tvf_tables).  ppo_tvf_tables_words gives a sufficient blob size.
+ * optimise_slots != 0 permutes the entry slots of each horizon to avoid shared-memory bank conflicts in the slab
+ * kernel (the set of entries per horizon is unchanged).  Returns PPO_ERR_BAD_ARG when a clamped n-step is outside
+ * 1..N (the reference's assert, :597) and PPO_ERR_UNSUPPORTED when a bootstrap horizon lies beyond the last value
+ * horizon (the reference's IndexError, :157).
+ */
+int64_t ppo_tvf_tables_words(int64_t n_req, int64_t n_samples, int64_t steps);
+int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* required_horizons, int64_t n_req,
+                         const int64_t* value_horizons, int64_t n_val, const int64_t* samples, int64_t n_samples,
+                         int use_log_interpolation, int optimise_slots, int32_t* blob, int64_t blob_words,
+                         ppo_tvf_table_layout* layout);
+
 /* which TVF kernel ppo_tvf_targets may use */
 typedef enum {
     PPO_TVF_AUTO = 0,    /* TMA ring kernel when the shape allows it, else the generic kernel */

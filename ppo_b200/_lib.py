@@ -38,6 +38,9 @@ _SIGNATURES = {
     "ppo_adv_normalize": (c_int, [c_ptr, c_i64, c_ptr, c_dbl, c_dbl, c_ptr, c_ptr]),
     "ppo_moments": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
     "ppo_tvf_workspace_bytes": (c_i64, [c_i64, c_i64]),
+    "ppo_tvf_tables_words": (c_i64, [c_i64, c_i64, c_i64]),
+    "ppo_tvf_tables_build": (c_int, [c_dbl, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_int, c_int,
+                                     c_ptr, c_i64, c_ptr]),
     "ppo_tvf_targets": (c_int, [c_ptr, c_i64, c_ptr, c_int, c_i64, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
                                 c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "ppo_tvf_last_horizon_stats": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),

@@ -1,0 +1,330 @@
+// Host-side builder of the TVF index tables (ppo_tvf_tables_build): integers and table arithmetic only,
+// no rollout data.  Same construction as ppo_b200/_tvf_tables.py (which stays as the documented
+// reference and is compared with this builder bit for bit in tests/test_tvf_tables_cpu.py):
+//   * per horizon h_k the distinct clamped n-steps n' = min(sample, h_k) with multiplicities
+//     (rl/returns_truncated.py:590-591, :616-618);
+//   * per entry, and per tail length m = N - t, the searchsorted slot and the lerp weights of
+//     rl/returns_truncated.py:142-174 (float64 arithmetic like NumPy, rounded to float32 once);
+//   * discount powers as the reference's float32 running product times a float64 gamma (:669).
+// In addition the builder may permute the entry slots of every horizon so that the consumer warps of
+// the slab kernel (lane <-> horizon, 32 consecutive horizons per warp) hit distinct shared-memory
+// banks: the order of the entries of one horizon is arbitrary (their terms are summed), so this only
+// changes the float32 summation order.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace ppo {
+namespace {
+
+struct Lerp {
+    int32_t lo, hi;
+    float wlo, whi;
+};
+
+// Vectorised `_interpolate` bookkeeping for one target (ppo_b200/_tvf_tables.py:_lerp_slots).
+// Returns false when a positive target lies beyond the last horizon (the reference raises IndexError).
+bool lerp_slot(const std::vector<double>& axis, double tg, bool positive, Lerp* out) {
+    const int n_val = static_cast<int>(axis.size());
+    int j = static_cast<int>(std::lower_bound(axis.begin(), axis.end(), tg) - axis.begin());
+    if (positive && j >= n_val) return false;
+    j = std::min(j, n_val - 1);
+    const bool exact = axis[j] == tg;
+    const int jm = std::max(j - 1, 0);
+    const double width = axis[j] - axis[jm];
+    const double safe = width == 0 ? 1.0 : width;
+    const double frac = (tg - axis[jm]) / safe;
+    const bool single = exact || j == 0;
+    const bool left = !single && width == 0;
+    int lo = single ? j : jm;
+    int hi = (single || left) ? lo : j;
+    double wlo = (single || left) ? 1.0 : 1.0 - frac;
+    double whi = (single || left) ? 0.0 : frac;
+    if (!positive) lo = 0, hi = 0, wlo = 0.0, whi = 0.0;
+    out->lo = lo, out->hi = hi;
+    out->wlo = static_cast<float>(wlo), out->whi = static_cast<float>(whi);
+    return true;
+}
+
+struct Entry {
+    int32_t n;
+    float cnt;
+    Lerp l;
+};
+
+// Minimum-cost assignment of r rows to 8 columns (r <= 8), O(n^3) Hungarian on a padded square matrix.
+void assign8(const double cost[8][8], int rows, int* col_of_row) {
+    const int n = 8;
+    double u[9] = {0}, v[9] = {0};
+    int p[9] = {0}, way[9] = {0};
+    for (int i = 1; i <= n; ++i) {
+        p[0] = i;
+        int j0 = 0;
+        double minv[9];
+        bool used[9] = {false};
+        for (int j = 0; j <= n; ++j) minv[j] = 1e300;
+        do {
+            used[j0] = true;
+            const int i0 = p[j0];
+            double delta = 1e300;
+            int j1 = 0;
+            for (int j = 1; j <= n; ++j) {
+                if (used[j]) continue;
+                const double c = (i0 <= rows ? cost[i0 - 1][j - 1] : 0.0) - u[i0] - v[j];
+                if (c < minv[j]) minv[j] = c, way[j] = j0;
+                if (minv[j] < delta) delta = minv[j], j1 = j;
+            }
+            for (int j = 0; j <= n; ++j) {
+                if (used[j]) u[p[j]] += delta, v[j] -= delta;
+                else minv[j] -= delta;
+            }
+            j0 = j1;
+        } while (p[j0] != 0);
+        do {
+            const int j1 = way[j0];
+            p[j0] = p[j1];
+            j0 = j1;
+        } while (j0);
+    }
+    for (int j = 1; j <= n; ++j)
+        if (p[j] >= 1 && p[j] <= rows) col_of_row[p[j] - 1] = j - 1;
+}
+
+// Slot permutation for one warp of up to 32 horizons.  ent[k] holds the live entries of horizon k.
+// Cost model of the slab kernel: per slot one 16-byte prefix read per lane (quarter-warps of 8 lanes
+// conflict when distinct n fall into the same 16-byte bank group) and eight 4-byte slab reads (lanes
+// conflict when distinct (row, column) addresses share a bank = column mod 32).
+void permute_warp(std::vector<std::vector<Entry>>& ent, int k0, int k1, int n_slots, int pt_pitch_words) {
+    const int lanes = k1 - k0;
+    std::vector<std::vector<int>> slot_of(lanes);
+    for (int i = 0; i < lanes; ++i) {
+        slot_of[i].resize(ent[k0 + i].size());
+        for (size_t e = 0; e < slot_of[i].size(); ++e) slot_of[i][e] = static_cast<int>(e);
+    }
+    auto quad_of = [&](int n) { return (n * pt_pitch_words / 4) & 7; };
+    auto boots = [](const Entry& x) { return x.l.wlo != 0.f || x.l.whi != 0.f; };
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int i = 0; i < lanes; ++i) {
+            const std::vector<Entry>& mine = ent[k0 + i];
+            const int r = static_cast<int>(mine.size());
+            if (r == 0) continue;
+            double cost[8][8];
+            for (int a = 0; a < r; ++a) {
+                for (int s = 0; s < 8; ++s) {
+                    if (s >= n_slots) {
+                        cost[a][s] = 1e9;
+                        continue;
+                    }
+                    int cv = 0, cs = 0;
+                    for (int o = 0; o < lanes; ++o) {
+                        if (o == i) continue;
+                        if (pass == 0 && o > i) break;  // first pass: only lanes already placed
+                        const std::vector<Entry>& other = ent[k0 + o];
+                        for (size_t e = 0; e < other.size(); ++e) {
+                            if (slot_of[o][e] != s) continue;
+                            const Entry& y = other[e];
+                            if (boots(mine[a]) && boots(y) && ((y.l.lo ^ mine[a].l.lo) & 31) == 0 &&
+                                !(y.n == mine[a].n && y.l.lo == mine[a].l.lo))
+                                ++cv;
+                            if ((o >> 3) == (i >> 3) && y.n != mine[a].n && quad_of(y.n) == quad_of(mine[a].n)) ++cs;
+                        }
+                    }
+                    cost[a][s] = 8.0 * (cv * cv + cv) + (cs * cs + cs);
+                }
+            }
+            int col[8];
+            assign8(cost, r, col);
+            for (int a = 0; a < r; ++a) slot_of[i][a] = col[a];
+        }
+    }
+    for (int i = 0; i < lanes; ++i) {
+        std::vector<Entry>& mine = ent[k0 + i];
+        std::vector<Entry> placed(n_slots, Entry{0, 0.f, Lerp{0, 0, 0.f, 0.f}});
+        for (size_t e = 0; e < mine.size(); ++e) placed[slot_of[i][e]] = mine[e];
+        mine.swap(placed);
+    }
+}
+
+// Sample-independent part of the tail tables, cached per horizon set (it depends on the horizons, the
+// interpolation axis and the number of steps only).
+struct TailCache {
+    std::vector<int64_t> req, vsh;
+    int64_t steps = -1;
+    int use_log = -1;
+    std::vector<Lerp> slots;  // [steps + 1][K], valid flag in lo >= 0
+    std::vector<unsigned char> ok;
+};
+std::mutex g_cache_mutex;
+TailCache g_cache;
+
+}  // namespace
+}  // namespace ppo
+
+using namespace ppo;
+
+extern "C" int64_t ppo_tvf_tables_words(int64_t n_req, int64_t n_samples, int64_t steps) {
+    if (n_req < 0 || n_samples < 1 || steps < 0) return -1;
+    const int64_t e = std::min<int64_t>(n_samples, std::max<int64_t>(steps, 1));
+    auto pad = [](int64_t w) { return (w + 3) / 4 * 4; };
+    return 6 * pad(e * n_req) + 5 * pad((steps + 1) * n_req) + pad(steps + 1) + 16;
+}
+
+extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* required_horizons, int64_t n_req,
+                                    const int64_t* value_horizons, int64_t n_val, const int64_t* samples,
+                                    int64_t n_samples, int use_log_interpolation, int optimise_slots,
+                                    int32_t* blob, int64_t blob_words, ppo_tvf_table_layout* layout) {
+    PPO_REQUIRE(required_horizons && value_horizons && samples && blob && layout, "ppo_tvf_tables_build: null pointer");
+    PPO_REQUIRE(n_req >= 1 && n_val >= 1 && n_samples >= 1 && steps >= 1, "ppo_tvf_tables_build: bad shape");
+    const int K = static_cast<int>(n_req), V = static_cast<int>(n_val), C = static_cast<int>(n_samples);
+
+    std::vector<double> axis(V);
+    for (int j = 0; j < V; ++j)
+        axis[j] = use_log_interpolation ? log10(10.0 + static_cast<double>(value_horizons[j])) - 1.0
+                                        : static_cast<double>(value_horizons[j]);
+    auto to_axis = [&](int64_t x) {
+        return use_log_interpolation ? log10(10.0 + static_cast<double>(std::max<int64_t>(x, -9))) - 1.0
+                                     : static_cast<double>(x);
+    };
+
+    // ---- entries: distinct clamped n-steps per horizon, ascending, with multiplicities
+    std::vector<std::vector<Entry>> ent(K);
+    int n_entries = 1, nmax = 1;
+    std::vector<int64_t> row(C);
+    for (int k = 0; k < K; ++k) {
+        const int64_t h = required_horizons[k];
+        if (h <= 0) continue;  // h == 0 -> zeros (rl/returns_truncated.py:580-583)
+        for (int c = 0; c < C; ++c) {
+            const int64_t n = std::min(samples[static_cast<int64_t>(k) * C + c], h);
+            if (n < 1 || n > steps) {
+                set_error("n-step samples must satisfy 1 <= min(sample, horizon) <= N (horizon %lld, sample %lld, N %lld)",
+                          (long long)h, (long long)samples[static_cast<int64_t>(k) * C + c], (long long)steps);
+                return PPO_ERR_BAD_ARG;  // rl/returns_truncated.py:597 assert
+            }
+            row[c] = n;
+        }
+        std::sort(row.begin(), row.end());
+        for (int c = 0; c < C; ++c) {
+            if (c > 0 && row[c] == row[c - 1]) {
+                ent[k].back().cnt += 1.f;
+                continue;
+            }
+            Entry x;
+            x.n = static_cast<int32_t>(row[c]), x.cnt = 1.f;
+            const int64_t left = h - row[c];
+            if (!lerp_slot(axis, to_axis(left), left > 0, &x.l)) {
+                set_error("index %d is out of bounds for axis 0 with size %d", V, V);
+                return PPO_ERR_UNSUPPORTED;  // the reference's IndexError (rl/returns_truncated.py:157)
+            }
+            ent[k].push_back(x);
+        }
+        n_entries = std::max(n_entries, static_cast<int>(ent[k].size()));
+        nmax = std::max(nmax, ent[k].back().n);
+    }
+    const int E = n_entries;
+
+    // ---- discount powers (float32 running product, float64 multiply)
+    std::vector<float> gpow(nmax + 1);
+    gpow[0] = 1.f;
+    for (int n = 1; n <= nmax; ++n) gpow[n] = static_cast<float>(static_cast<double>(gpow[n - 1]) * gamma);
+
+    // ---- tails: horizon h_k - m for m = N - t; used for m <= largest entry of the horizon
+    std::vector<int> k_nmax(K, 0);
+    for (int k = 0; k < K; ++k)
+        if (!ent[k].empty()) k_nmax[k] = ent[k].back().n;
+    std::vector<Lerp> tail(static_cast<size_t>(nmax + 1) * K, Lerp{0, 0, 0.f, 0.f});
+    {
+        std::lock_guard<std::mutex> guard(g_cache_mutex);
+        TailCache& tc = g_cache;
+        const bool hit = tc.steps == steps && tc.use_log == use_log_interpolation &&
+                         tc.req.size() == static_cast<size_t>(K) && tc.vsh.size() == static_cast<size_t>(V) &&
+                         std::equal(tc.req.begin(), tc.req.end(), required_horizons) &&
+                         std::equal(tc.vsh.begin(), tc.vsh.end(), value_horizons);
+        if (!hit) {
+            tc.req.assign(required_horizons, required_horizons + K);
+            tc.vsh.assign(value_horizons, value_horizons + V);
+            tc.steps = steps, tc.use_log = use_log_interpolation;
+            tc.slots.assign(static_cast<size_t>(steps + 1) * K, Lerp{0, 0, 0.f, 0.f});
+            tc.ok.assign(static_cast<size_t>(steps + 1) * K, 1);
+            for (int64_t m = 1; m <= steps; ++m)
+                for (int k = 0; k < K; ++k) {
+                    const int64_t left = required_horizons[k] - m;
+                    if (required_horizons[k] <= 0 || left <= 0) continue;
+                    if (!lerp_slot(axis, to_axis(left), true, &tc.slots[m * K + k])) tc.ok[m * K + k] = 0;
+                }
+        }
+        for (int m = 1; m <= nmax; ++m)
+            for (int k = 0; k < K; ++k) {
+                if (m > k_nmax[k]) continue;
+                if (!tc.ok[static_cast<size_t>(m) * K + k]) {
+                    set_error("index %d is out of bounds for axis 0 with size %d", V, V);
+                    return PPO_ERR_UNSUPPORTED;
+                }
+                tail[static_cast<size_t>(m) * K + k] = tc.slots[static_cast<size_t>(m) * K + k];
+            }
+    }
+
+    // ---- optional slot permutation for the slab kernel's bank behaviour
+    if (optimise_slots && E <= 8 && E >= 2) {
+        for (int k0 = 0; k0 < K; k0 += 32) permute_warp(ent, k0, std::min(K, k0 + 32), E, 36);
+    } else {
+        for (int k = 0; k < K; ++k) ent[k].resize(E, Entry{0, 0.f, Lerp{0, 0, 0.f, 0.f}});
+    }
+
+    // ---- pack
+    auto pad = [](int64_t w) { return (w + 3) / 4 * 4; };
+    const int64_t ek = static_cast<int64_t>(E) * K, tk = static_cast<int64_t>(nmax + 1) * K;
+    int64_t off = 0;
+    int64_t* offs = layout->offset_words;
+    for (int i = 0; i < 6; ++i) offs[i] = off, off += pad(ek);
+    for (int i = 6; i < 11; ++i) offs[i] = off, off += pad(tk);
+    offs[11] = off, off += pad(nmax + 1);
+    if (off > blob_words) {
+        set_error("ppo_tvf_tables_build: blob of %lld words required, got %lld", (long long)off, (long long)blob_words);
+        return PPO_ERR_WORKSPACE;
+    }
+    memset(blob, 0, static_cast<size_t>(off) * 4);
+    int32_t* ent_n = blob + offs[0];
+    float* ent_cnt = reinterpret_cast<float*>(blob + offs[1]);
+    int32_t* ent_idx = blob + offs[2];
+    float* ent_wlo = reinterpret_cast<float*>(blob + offs[3]);
+    float* ent_whi = reinterpret_cast<float*>(blob + offs[4]);
+    float* ent_g = reinterpret_cast<float*>(blob + offs[5]);
+    int32_t* tail_idx = blob + offs[6];
+    float* tail_wlo = reinterpret_cast<float*>(blob + offs[7]);
+    float* tail_whi = reinterpret_cast<float*>(blob + offs[8]);
+    float* tail_cwlo = reinterpret_cast<float*>(blob + offs[9]);
+    float* tail_cwhi = reinterpret_cast<float*>(blob + offs[10]);
+    float* gp = reinterpret_cast<float*>(blob + offs[11]);
+    for (int k = 0; k < K; ++k)
+        for (int e = 0; e < E; ++e) {
+            const Entry& x = ent[k][e];
+            const int64_t i = static_cast<int64_t>(e) * K + k;
+            ent_n[i] = x.n, ent_cnt[i] = x.cnt;
+            ent_idx[i] = x.l.lo | (x.l.hi << 16);
+            ent_wlo[i] = x.l.wlo, ent_whi[i] = x.l.whi;
+            ent_g[i] = gpow[x.n];  // gpow[0] = 1 for padding slots, like the NumPy builder
+        }
+    for (int m = 0; m <= nmax; ++m)
+        for (int k = 0; k < K; ++k) {
+            const int64_t i = static_cast<int64_t>(m) * K + k;
+            const Lerp& l = tail[i];
+            tail_idx[i] = l.lo | (l.hi << 16);
+            tail_wlo[i] = l.wlo, tail_whi[i] = l.whi;
+            double beyond = 0.0;  // multiplicity of the entries that run past m
+            for (int e = 0; e < E; ++e)
+                if (ent[k][e].n > m) beyond += ent[k][e].cnt;
+            const double scale = beyond * static_cast<double>(gpow[m]);
+            tail_cwlo[i] = static_cast<float>(static_cast<double>(l.wlo) * scale);
+            tail_cwhi[i] = static_cast<float>(static_cast<double>(l.whi) * scale);
+        }
+    for (int n = 0; n <= nmax; ++n) gp[n] = gpow[n];
+    layout->n_entries = E, layout->nmax = nmax;
+    layout->total_words = off;
+    layout->inv_c = static_cast<float>(1.0 / static_cast<double>(C));
+    return PPO_OK;
+}
