@@ -238,7 +238,7 @@ def run_ours(args):
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_begin.record()
@@ -307,7 +307,7 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "tvf_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "tvf slab kernel (ppo_tvf_targets)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": f"ppo_tvf_targets, {rp.tvf_kernel} kernel (targets + fused last-horizon statistics)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": tvf_avg_ms,
                 "kernel_share_of_step": tvf_avg_ms / ms_per_step,

@@ -141,6 +141,14 @@ int ppo_discounted_returns(const float* rewards, int64_t reward_row_stride,
  *            entries with n' > m (so the run-off-the-end bootstrap is one fused term per target)
  *   gpow     gamma^n, n = 0..nmax
  *   inv_c    float32(1 / C)
+ *   tailT_*  (optional) horizon-major copies [K, tail_pitch] of tail_idx / tail_cwlo / tail_cwhi
+ *   host_blob / dev_blob  (optional) when every table above lives in ONE packed device allocation starting at
+ *            dev_blob and host_blob is a HOST copy of the same bytes (both as written by
+ *            ppo_tvf_tables_build), ppo_tvf_targets may resolve per-horizon launch constants on the host
+ *            without a device round trip; required by the transposed slab kernel (PPO_TVF_TSLAB).  host_blob
+ *            only has to stay valid for the duration of the call.
+ *   gamma    (optional, 0 = absent) the float64 discount the tables were built for; the transposed slab kernel
+ *            carries the discounted reward-to-go in float64 with it
  */
 typedef struct {
     int32_t n_entries;
@@ -158,16 +166,26 @@ typedef struct {
     const float* tail_cwhi;
     const float* gpow;
     float inv_c;
+    int32_t tail_pitch;
+    const int32_t* tailT_idx;
+    const float* tailT_cwlo;
+    const float* tailT_cwhi;
+    const void* host_blob;
+    const void* dev_blob;
+    double gamma;
 } ppo_tvf_tables;
 
-/* Offsets (in 32-bit words) of the twelve tables inside the packed blob written by ppo_tvf_tables_build, in the
- * order of the pointer members of ppo_tvf_tables (ent_n ... gpow); every table starts 16-byte aligned. */
+/* Offsets (in 32-bit words) of the tables inside the packed blob written by ppo_tvf_tables_build: [0..11] in the
+ * order of the first twelve pointer members of ppo_tvf_tables (ent_n ... gpow), [12..14] tailT_idx / tailT_cwlo /
+ * tailT_cwhi, [15] = total_words; every table starts 16-byte aligned. */
 typedef struct {
     int32_t n_entries;
     int32_t nmax;
     int64_t total_words;
-    int64_t offset_words[12];
+    int64_t offset_words[16];
     float inv_c;
+    int32_t tail_pitch;
+    double gamma;
 } ppo_tvf_table_layout;
 
 /*
@@ -189,9 +207,11 @@ int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* required_ho
 
 /* which TVF kernel ppo_tvf_targets may use */
 typedef enum {
-    PPO_TVF_AUTO = 0,    /* TMA ring kernel when the shape allows it, else the generic kernel */
+    PPO_TVF_AUTO = 0,    /* transposed slab kernel for >= 3 n-steps per horizon, else the TMA ring kernel, when the
+                            shape allows them; else the generic kernel */
     PPO_TVF_GENERIC = 1, /* global-memory gather kernel, any shape                            */
-    PPO_TVF_RING = 2     /* TMA ring kernel or PPO_ERR_UNSUPPORTED                            */
+    PPO_TVF_RING = 2,    /* TMA ring kernel or PPO_ERR_UNSUPPORTED                            */
+    PPO_TVF_TSLAB = 3    /* transposed slab kernel or PPO_ERR_UNSUPPORTED                     */
 } ppo_tvf_path;
 
 /*
@@ -213,6 +233,10 @@ int ppo_tvf_targets(const float* rewards, int64_t reward_row_stride,
                     int64_t steps, int64_t envs, int64_t n_req, int64_t n_val,
                     const ppo_tvf_tables* tables, int path,
                     float* out, double* stats, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* The kernel the last successful ppo_tvf_targets call of this thread launched: a ppo_tvf_path value (never AUTO),
+ * plus 0x100 when the statistics of the longest horizon were fused into that launch (no second kernel). */
+int ppo_tvf_last_path(void);
 
 /* count / sum / sumsq / min / max of the longest horizon targets[:, K-1] of a [rows, K] target buffer into the
  * ADV_* slots of `stats` (rl/rollout.py:1270 `tvf_return_ext`); what ppo_tvf_targets runs when `stats` is given. */

@@ -43,6 +43,7 @@ _SIGNATURES = {
                                      c_ptr, c_i64, c_ptr]),
     "ppo_tvf_targets": (c_int, [c_ptr, c_i64, c_ptr, c_int, c_i64, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
                                 c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "ppo_tvf_last_path": (c_int, []),
     "ppo_tvf_last_horizon_stats": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
     "ppo_vtrace": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_i64, c_i64, c_i64,
                            c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr]),

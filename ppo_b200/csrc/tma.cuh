@@ -12,7 +12,8 @@ namespace ppo {
 // Encode a tiled tensor map of up to 3 dimensions (dims[0] is the contiguous one).  strides are in
 // BYTES for dims 1.. (dim 0 is packed).  Returns PPO_OK / PPO_ERR_CUDA / PPO_ERR_UNSUPPORTED.
 int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const void* base,
-                      const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+                      const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                      bool swizzle_128b = false);
 
 // ---- device: mbarrier ----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -91,6 +92,13 @@ __device__ __forceinline__ void cp_async_4(void* dst, const void* src) {
 // arrival is one of the barrier's expected arrivals (init count = number of copying threads).
 __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- device: TMA stores (shared -> global, bulk-group completion) ------------------------------
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
 }
 
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {

@@ -17,6 +17,8 @@
 
 namespace ppo {
 
+int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsigned int* ticket, int64_t max_partials,
+                     cudaStream_t stream, bool* stats_fused);
 int launch_tvf_ring(const TvfParams& p, const float* tail_cwlo, const float* tail_cwhi, cudaStream_t stream,
                     bool probe_only);  // tvf_ring.cu
 
@@ -215,6 +217,10 @@ constexpr int kStatsBlocks = 296;
 
 using namespace ppo;
 
+static thread_local int g_last_path = 0;
+
+extern "C" int ppo_tvf_last_path(void) { return g_last_path; }
+
 extern "C" int64_t ppo_tvf_workspace_bytes(int64_t steps, int64_t envs) {
     (void)steps;
     (void)envs;
@@ -230,7 +236,7 @@ extern "C" int ppo_tvf_targets(const float* rewards, int64_t reward_row_stride, 
     PPO_REQUIRE(steps < (1 << 24) && n_req < (1 << 20) && n_val < (1 << 16), "ppo_tvf_targets: shape too large");
     PPO_REQUIRE(done_kind == PPO_DONE_U8 || done_kind == PPO_DONE_F32 || done_kind == PPO_DONE_NONE,
                 "ppo_tvf_targets: unknown done_kind %d", done_kind);
-    PPO_REQUIRE(path == PPO_TVF_AUTO || path == PPO_TVF_GENERIC || path == PPO_TVF_RING,
+    PPO_REQUIRE(path == PPO_TVF_AUTO || path == PPO_TVF_GENERIC || path == PPO_TVF_RING || path == PPO_TVF_TSLAB,
                 "ppo_tvf_targets: unknown path %d", path);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (steps == 0 || envs == 0 || n_req == 0) {
@@ -255,15 +261,31 @@ extern "C" int ppo_tvf_targets(const float* rewards, int64_t reward_row_stride, 
     p.out = out;
 
     int rc = PPO_ERR_UNSUPPORTED;
-    if (path != PPO_TVF_GENERIC) {
-        rc = launch_tvf_ring(p, tables->tail_cwlo, tables->tail_cwhi, s, false);
-        if (rc == PPO_ERR_UNSUPPORTED && path == PPO_TVF_AUTO) rc = launch_generic(p, s);
-    } else {
-        rc = launch_generic(p, s);
+    bool stats_fused = false;
+    int taken = PPO_TVF_GENERIC;
+    // Several n-steps per horizon: gather-bound, transposed slab kernel.  One or two: HBM-bound, ring kernel.
+    if (path == PPO_TVF_TSLAB || (path == PPO_TVF_AUTO && tables->n_entries >= 3)) {
+        double* partials = nullptr;
+        unsigned int* ticket = nullptr;
+        if (stats && workspace && workspace_bytes >= ppo_tvf_workspace_bytes(0, 0)) {
+            ticket = static_cast<unsigned int*>(workspace);
+            partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
+        }
+        rc = launch_tvf_tslab(p, stats, partials, ticket, kStatsBlocks, s, &stats_fused);
+        if (path == PPO_TVF_TSLAB && rc != PPO_OK) return rc;
+        taken = PPO_TVF_TSLAB;
     }
+    if (rc == PPO_ERR_UNSUPPORTED && path != PPO_TVF_GENERIC) {
+        rc = launch_tvf_ring(p, tables->tail_cwlo, tables->tail_cwhi, s, false);
+        if (path == PPO_TVF_RING && rc != PPO_OK) return rc;
+        taken = PPO_TVF_RING;
+    }
+    if (rc == PPO_ERR_UNSUPPORTED) rc = launch_generic(p, s), taken = PPO_TVF_GENERIC;
     if (rc != PPO_OK) return rc;
+    g_last_path = taken | (stats_fused ? 0x100 : 0);
 
-    if (stats) return ppo_tvf_last_horizon_stats(out, steps * envs, n_req, stats, workspace, workspace_bytes, stream);
+    if (stats && !stats_fused)
+        return ppo_tvf_last_horizon_stats(out, steps * envs, n_req, stats, workspace, workspace_bytes, stream);
     return PPO_OK;
 }
 

@@ -171,7 +171,7 @@ extern "C" int64_t ppo_tvf_tables_words(int64_t n_req, int64_t n_samples, int64_
     if (n_req < 0 || n_samples < 1 || steps < 0) return -1;
     const int64_t e = std::min<int64_t>(n_samples, std::max<int64_t>(steps, 1));
     auto pad = [](int64_t w) { return (w + 3) / 4 * 4; };
-    return 6 * pad(e * n_req) + 5 * pad((steps + 1) * n_req) + pad(steps + 1) + 16;
+    return 6 * pad(e * n_req) + 5 * pad((steps + 1) * n_req) + pad(steps + 1) + 3 * pad(n_req * pad(steps + 1)) + 16;
 }
 
 extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* required_horizons, int64_t n_req,
@@ -283,6 +283,10 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
     for (int i = 0; i < 6; ++i) offs[i] = off, off += pad(ek);
     for (int i = 6; i < 11; ++i) offs[i] = off, off += pad(tk);
     offs[11] = off, off += pad(nmax + 1);
+    // horizon-major copies of the folded tail tables, [K][tail_pitch], for the transposed slab kernel
+    const int64_t tpitch = pad(nmax + 1);
+    for (int i = 12; i < 15; ++i) offs[i] = off, off += pad(static_cast<int64_t>(K) * tpitch);
+    offs[15] = off;
     if (off > blob_words) {
         set_error("ppo_tvf_tables_build: blob of %lld words required, got %lld", (long long)off, (long long)blob_words);
         return PPO_ERR_WORKSPACE;
@@ -323,6 +327,18 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
             tail_cwhi[i] = static_cast<float>(static_cast<double>(l.whi) * scale);
         }
     for (int n = 0; n <= nmax; ++n) gp[n] = gpow[n];
+    {
+        int32_t* t_idx = blob + offs[12];
+        float* t_wlo = reinterpret_cast<float*>(blob + offs[13]);
+        float* t_whi = reinterpret_cast<float*>(blob + offs[14]);
+        for (int k = 0; k < K; ++k)
+            for (int m = 0; m <= nmax; ++m) {
+                const int64_t src = static_cast<int64_t>(m) * K + k, dst = static_cast<int64_t>(k) * tpitch + m;
+                t_idx[dst] = tail_idx[src], t_wlo[dst] = tail_cwlo[src], t_whi[dst] = tail_cwhi[src];
+            }
+    }
+    layout->tail_pitch = static_cast<int32_t>(tpitch);
+    layout->gamma = gamma;
     layout->n_entries = E, layout->nmax = nmax;
     layout->total_words = off;
     layout->inv_c = static_cast<float>(1.0 / static_cast<double>(C));

@@ -1,0 +1,692 @@
+// TVF targets, transposed slab kernel (PPO_TVF_TSLAB): the path for several n-step samples per horizon.
+//
+// With E distinct n-steps per horizon every target needs 2 E gathered value samples, so the pass is bound by
+// shared-memory gather bandwidth (one 128-byte wavefront per clock per SM), not by HBM.  This kernel is built
+// around that limit: every gather is one conflict-free wavefront and nothing else is gathered.
+//
+//   * Return form.  With R(t) = sum_i r[t+i] * prod_{j<i} gamma * nt[t+j] (the discounted reward-to-go inside
+//     the rollout, zero from row N on),  S_n(t) = R(t) - gamma^n * R(t+n)  whenever no terminal lies in
+//     t..t+n-1, and S_n(t) = R(t) otherwise.  Hence
+//         out[t,k] = R(t) + 1/C * sum_e cnt_e * gamma^n_e * [n_e <= lim(t)] * lerp_e(W[t+n_e, :]),
+//         W[r, j] = V[r, j] - R(r),   lim(t) = min(N - t, steps to the first terminal at or after t),
+//     so the reward part rides on the value gathers: no prefix tables, no extra reads per entry.  Entries
+//     without a bootstrap (h_k - n <= 0) read an extra slab column that holds -R(r).  R is carried in float64
+//     and stored as float32; the error model is in DESIGN.md (a few ulp of max|R|).
+//   * Transposed slab.  Shared memory holds W^T[j][r] for ONE env: column j of the value curve along time,
+//     pitch P odd.  A consumer warp owns 32 consecutive time rows (lane <-> t) and walks horizons; n_e, the
+//     column and the lerp weights are warp-uniform (they come from the kernel parameter bank), so a gather is
+//     32 consecutive words W^T[lo][t0 + n - 1 + lane]: one wavefront whatever the sample table looks like.
+//   * Flow per SM (one persistent CTA, envs in order): TMA loads 32-row chunks of V[:, env, :] into a staging
+//     ring; transform warps subtract R(r) and write the chunk transposed into the slab (odd pitch: conflict
+//     free) as soon as the consumers of the PREVIOUS env have finished the same 32-row block (the slab is
+//     replaced in place, row by row); consumers evaluate blocks of 32 rows x K horizons; results go through a
+//     row-major staging tile (16-byte stores, pitch chosen conflict free) and leave with bulk async copies
+//     (cp.async.bulk shared -> global), so neither the output nor the input path uses gather bandwidth.
+//   * Rows that run off the rollout bootstrap from the final row with host-folded weights (horizon-major
+//     tables so that lanes read consecutive words).
+// Warp roles: 0-15 consumers, 16-19 transform, 20 scan (R and lim tables, float64), 21 store, 22 TMA producer.
+#include <math.h>
+#include <stdlib.h>
+
+#include "tma.cuh"
+#include "tvf_common.cuh"
+
+namespace ppo {
+
+constexpr int kTsConsumers = 16;
+constexpr int kTsXform = 4;
+constexpr int kTsThreads = (kTsConsumers + kTsXform + 3) * 32;
+constexpr int kTsMaxK = 128;
+constexpr int kTsMaxEntries = 1024;
+constexpr int kTsRows = 32;        // value rows per TMA chunk = time rows per lane group
+constexpr int kTsStep = 64;        // time rows per consumer step: a thread owns rows t and t + 32 of the step
+constexpr int kTsMaxChunks = 16;   // N <= 512
+constexpr int kTsMaxSteps = 8;
+
+struct __align__(16) TsEntry {
+    uint32_t off;    // byte offset of W^T[col][n - 1] in the slab
+    float wlo, whi;  // multiplicity * gamma^n * lerp weights
+    int32_t n;
+};
+struct __align__(16) TsHorizon {
+    int32_t beg, cnt;  // entries [beg, beg + cnt)
+    float rscale;      // 1 for a live horizon, 0 for h = 0 (all-zero targets)
+    int32_t maxn;      // largest n-step of the horizon (tail rows: N - t < maxn)
+};
+
+struct TsParams {
+    TvfParams p;
+    double gamma;
+    int nc, ns, pitch, nstage, kq, rt_words, tail_pitch, want_stats, n_ent;
+    int dbg;  // development switches (PPO_TVF_DEBUG): 1 no stores, 2 no TMA loads, 4 no transform, 8 no entry loop
+    int64_t env_base, env_rem;
+    uint32_t off_stage, off_ot, off_ent, off_hz, off_rtab, off_lim, off_fr, off_bar, smem_total;
+    double* partials;  // [grid][8] per-CTA statistics of the longest horizon (want_stats)
+    unsigned int* ticket;
+    double* stats;
+    TsHorizon hz[kTsMaxK];
+    TsEntry ent[kTsMaxEntries];
+};
+
+template <int IMM>
+__device__ __forceinline__ float ts_ldsi(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
+__device__ __forceinline__ float ts_lds(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int ts_lds_s32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 ts_lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void ts_sts(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void ts_sts_s32(uint32_t addr, int v) {
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void ts_sts128(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// acc += [n <= lim] * (lo * wlo + hi * whi): the per-lane predicate stays a predicate on the two FMAs.
+__device__ __forceinline__ void ts_fma_if(float& acc, float lo, float hi, float wlo, float whi, int n, int lim) {
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.le.s32 p, %5, %6;\n\t"
+        "@p fma.rn.f32 %0, %1, %3, %0;\n\t"
+        "@p fma.rn.f32 %0, %2, %4, %0;\n\t}"
+        : "+f"(acc)
+        : "f"(lo), "f"(hi), "f"(wlo), "f"(whi), "r"(n), "r"(lim));
+}
+
+// G entries of one horizon for the thread's two time rows (t, t + 32).  The entry constants are one broadcast
+// 16-byte shared-memory read each; all gathers are issued before the first use.  PITCH4 = slab pitch in bytes
+// when it is known at compile time (immediate offsets), 0 = runtime pitch in `p4`.
+template <int G, int PITCH4>
+__device__ __forceinline__ void ts_eval(uint32_t cent, uint32_t base, uint32_t p4, int lim0, int lim1, float& acc0,
+                                        float& acc1) {
+    uint4 c[G];
+    float lo0[G], hi0[G], lo1[G], hi1[G];
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+        c[i] = ts_lds128(cent + i * 16);
+        const uint32_t a = base + c[i].x;
+        if (PITCH4) {
+            lo0[i] = ts_ldsi<0>(a), hi0[i] = ts_ldsi<PITCH4>(a);
+            lo1[i] = ts_ldsi<kTsRows * 4>(a), hi1[i] = ts_ldsi<PITCH4 + kTsRows * 4>(a);
+        } else {
+            const uint32_t ah = a + p4;
+            lo0[i] = ts_ldsi<0>(a), hi0[i] = ts_ldsi<0>(ah);
+            lo1[i] = ts_ldsi<kTsRows * 4>(a), hi1[i] = ts_ldsi<kTsRows * 4>(ah);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+        const float wlo = __uint_as_float(c[i].y), whi = __uint_as_float(c[i].z);
+        ts_fma_if(acc0, lo0[i], hi0[i], wlo, whi, static_cast<int>(c[i].w), lim0);
+        ts_fma_if(acc1, lo1[i], hi1[i], wlo, whi, static_cast<int>(c[i].w), lim1);
+    }
+}
+
+template <int V, int PITCH>
+__global__ void __launch_bounds__(kTsThreads, 1)
+tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUtensorMap vmap,
+                 const __grid_constant__ CUtensorMap omap) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr uint32_t CHUNK = kTsRows * V * 4;  // bytes per TMA chunk
+    constexpr int PITCH4 = PITCH * 4;
+    const TvfParams& p = q.p;
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
+    const int N = p.steps, K = p.n_req, nmax = p.tab.nmax, NC = q.nc, NS = q.ns;
+    const int P = PITCH ? PITCH : q.pitch;
+
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + q.off_bar);
+    uint64_t* sfull = bars;                     // [4] TMA chunk landed
+    uint64_t* sempty = sfull + 4;               // [4] chunk transposed, slot reusable
+    uint64_t* wfull = sempty + 4;               // [NC] chunk c of the current env is in the slab
+    uint64_t* bdone = wfull + kTsMaxChunks;     // [NS] consumers finished step s (slab rows of its chunks reusable)
+    uint64_t* rfull = bdone + kTsMaxSteps;      // [2] R / lim tables of env parity ready
+    uint64_t* rempty = rfull + 2;               // [2]
+    uint64_t* ofull = rempty + 2;               // output tile written
+    uint64_t* oempty = ofull + 1;               // output tile copied out
+
+    const uint32_t wt_a = smem_u32(smem);
+    const uint32_t stage_a = smem_u32(smem + q.off_stage);
+    const uint32_t ot_a = smem_u32(smem + q.off_ot);
+    const uint32_t ent_a = smem_u32(smem + q.off_ent);
+    const uint32_t hz_a = smem_u32(smem + q.off_hz);
+    const uint32_t rt_a = smem_u32(smem + q.off_rtab);
+    const uint32_t lim_a = smem_u32(smem + q.off_lim);
+    const uint32_t fr_a = smem_u32(smem + q.off_fr);
+    const uint32_t rt_bytes = static_cast<uint32_t>(q.rt_words) * 4u;
+
+    const int64_t bidx = blockIdx.x;
+    const int nenv = static_cast<int>(q.env_base + (bidx < q.env_rem ? 1 : 0));
+    const int64_t env0 = bidx * q.env_base + (bidx < q.env_rem ? bidx : q.env_rem);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(&sfull[i], 1), mbar_init(&sempty[i], kTsXform);
+        for (int i = 0; i < kTsMaxChunks; ++i) mbar_init(&wfull[i], kTsXform);
+        for (int i = 0; i < kTsMaxSteps; ++i) mbar_init(&bdone[i], kTsConsumers);
+        for (int i = 0; i < 2; ++i) mbar_init(&rfull[i], 1), mbar_init(&rempty[i], kTsConsumers + kTsXform);
+        mbar_init(ofull, kTsConsumers), mbar_init(oempty, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&vmap);
+        tma_prefetch_desc(&omap);
+    }
+    // Everything starts zero: the zero column behind the -R column, the padding behind the slab, R(N) = 0.
+    for (uint32_t i = threadIdx.x * 16u; i < q.off_bar; i += blockDim.x * 16u)
+        *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    // per-horizon launch constants: parameter bank -> shared memory (read by the consumers as broadcasts)
+    for (int i = threadIdx.x; i < q.n_ent; i += blockDim.x)
+        *reinterpret_cast<uint4*>(smem + q.off_ent + i * 16) = *reinterpret_cast<const uint4*>(&q.ent[i]);
+    for (int i = threadIdx.x; i < K; i += blockDim.x)
+        *reinterpret_cast<uint4*>(smem + q.off_hz + i * 16) = *reinterpret_cast<const uint4*>(&q.hz[i]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    if (warp == kTsConsumers + kTsXform + 2) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int slot = 0;
+            uint32_t par = 0;
+            for (int e = 0; e < nenv; ++e) {
+                const int env = static_cast<int>(env0 + e);
+                for (int c = 0; c < NC; ++c) {
+                    mbar_wait_sleep(&sempty[slot], par ^ 1);
+                    if (q.dbg & 2) {
+                        mbar_arrive(&sfull[slot]);
+                    } else {
+                        // rows past N are zero-filled by the TMA unit and still count in the transaction bytes
+                        mbar_arrive_expect_tx(&sfull[slot], CHUNK);
+                        tma_load_3d(smem + q.off_stage + static_cast<size_t>(slot) * CHUNK, &vmap, &sfull[slot], 0, env,
+                                    c * kTsRows + 1);
+                    }
+                    if (++slot == q.nstage) slot = 0, par ^= 1;
+                }
+            }
+        }
+    } else if (warp == kTsConsumers + kTsXform + 1) {
+        // ------------------------------------------------------------------ store warp
+        uint32_t it = 0;
+        for (int e = 0; e < nenv; ++e) {
+            const int64_t env = env0 + e;
+            for (int s = 0; s < NS; ++s, ++it) {
+                mbar_wait_sleep(ofull, it & 1u);
+                // one tensor store per (32 rows x 32 horizons) sub-tile; rows past N are clipped by the TMA unit
+                const int nsub = 2 * (K / 32);
+                if (lane < nsub && !(q.dbg & 1)) {
+                    const int half = lane / (K / 32), kg = lane % (K / 32);
+                    const int row0 = s * kTsStep + half * kTsRows;
+                    if (row0 < N)
+                        tma_store_3d(&omap, smem + q.off_ot + static_cast<size_t>(lane) * 4096, kg * 32,
+                                     static_cast<int>(env), row0);
+                }
+                bulk_commit();
+                bulk_wait_read();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(oempty);
+            }
+        }
+        bulk_wait_all();
+    } else if (warp == kTsConsumers + kTsXform) {
+        // ------------------------------------------------------------------ scan warp: R(t) and lim(t) per env
+        const int RPL = NC;  // rows per lane, lane l owns rows [l * RPL, (l + 1) * RPL)
+        const double gamma = q.gamma;
+        for (int e = 0; e < nenv; ++e) {
+            const uint32_t par = static_cast<uint32_t>(e & 1);
+            const int64_t env = env0 + e;
+            float rr[kTsMaxChunks];
+            bool dn[kTsMaxChunks];
+#pragma unroll
+            for (int i = 0; i < kTsMaxChunks; ++i) {
+                const int row = lane * RPL + i;
+                rr[i] = 0.f, dn[i] = true;  // rows past the rollout: reward 0, "terminal" (R = 0, lim = 0)
+                if (i < RPL && row < N) {
+                    rr[i] = __ldg(p.rewards + static_cast<int64_t>(row) * p.r_rs + env);
+                    dn[i] = done_at(p.dones, p.done_kind, static_cast<int64_t>(row) * p.d_rs + env);
+                }
+            }
+            // segment maps: R_start = a + bc * R_next;  lim_start = hd ? c : c + lim_next
+            double a = 0.0, bc = 1.0;
+            int c = 0;
+            bool hd = false;
+#pragma unroll
+            for (int i = kTsMaxChunks - 1; i >= 0; --i) {
+                if (i < RPL) {
+                    const double g = dn[i] ? 0.0 : gamma;
+                    a = static_cast<double>(rr[i]) + g * a;
+                    bc = g * bc;
+                    c = dn[i] ? 0 : c + 1;
+                    hd = hd || dn[i];
+                }
+            }
+            // suffix scan over lanes (lane l composes with lanes l+1.. ; beyond lane 31 both are 0)
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double a2 = shfl_down_f64(a, d), b2 = shfl_down_f64(bc, d);
+                const int c2 = __shfl_down_sync(0xffffffffu, c, d);
+                const int hd2 = __shfl_down_sync(0xffffffffu, static_cast<int>(hd), d);
+                if (lane + d < 32) {
+                    a = a + bc * a2;
+                    bc = bc * b2;
+                    if (!hd) c += c2, hd = hd2 != 0;
+                }
+            }
+            double x = shfl_down_f64(a, 1);
+            int l = __shfl_down_sync(0xffffffffu, c, 1);
+            if (lane == 31) x = 0.0, l = 0;
+            mbar_wait_sleep(&rempty[par], ((static_cast<uint32_t>(e) >> 1) & 1u) ^ 1u);
+            const uint32_t rt = rt_a + par * rt_bytes, lt = lim_a + par * rt_bytes;
+#pragma unroll
+            for (int i = kTsMaxChunks - 1; i >= 0; --i) {
+                if (i < RPL) {
+                    const int row = lane * RPL + i;
+                    const double g = dn[i] ? 0.0 : gamma;
+                    x = static_cast<double>(rr[i]) + g * x;
+                    l = dn[i] ? 0 : l + 1;
+                    ts_sts(rt + static_cast<uint32_t>(row) * 4u, static_cast<float>(x));
+                    ts_sts_s32(lt + static_cast<uint32_t>(row) * 4u, l);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&rfull[par]);
+        }
+    } else if (warp >= kTsConsumers) {
+        // ------------------------------------------------------------------ transform warps
+        const int xw = warp - kTsConsumers;
+        int slot = 0;
+        uint32_t spar = 0;
+        for (int e = 0; e < nenv; ++e) {
+            const uint32_t par = static_cast<uint32_t>(e & 1);
+            mbar_wait_sleep(&rfull[par], (static_cast<uint32_t>(e) >> 1) & 1u);
+            const uint32_t rt = rt_a + par * rt_bytes;
+            for (int c = 0; c < NC; ++c) {
+                // slab rows of chunk c were last needed by step c / 2 of the previous env
+                if (e > 0) mbar_wait_sleep(&bdone[c >> 1], static_cast<uint32_t>(e - 1) & 1u);
+                mbar_wait(&sfull[slot], spar);
+                const uint32_t src = stage_a + static_cast<uint32_t>(slot) * CHUNK + static_cast<uint32_t>(lane) * 4u;
+                if (!(q.dbg & 4))
+#pragma unroll
+                for (int rl = 0; rl < kTsRows / kTsXform; ++rl) {
+                    const int lr = xw + rl * kTsXform;  // row inside the chunk
+                    const int i = c * kTsRows + lr;     // slab index: value row r = i + 1
+                    if (i < N) {
+                        const float Rr = ts_lds(rt + static_cast<uint32_t>(i + 1) * 4u);
+                        float v[V / 32];
+#pragma unroll
+                        for (int cg = 0; cg < V / 32; ++cg) v[cg] = ts_lds(src + static_cast<uint32_t>(lr * V + cg * 32) * 4u);
+#pragma unroll
+                        for (int cg = 0; cg < V / 32; ++cg) {
+                            ts_sts(wt_a + static_cast<uint32_t>((cg * 32 + lane) * P + i) * 4u, v[cg] - Rr);
+                            if (i == N - 1) ts_sts(fr_a + static_cast<uint32_t>(cg * 32 + lane) * 4u, v[cg]);
+                        }
+                    }
+                }
+                if (xw == 0) {  // the -R column (index V); column V + 1 stays zero
+                    const int i = c * kTsRows + lane;
+                    if (i < N) ts_sts(wt_a + static_cast<uint32_t>(V * P + i) * 4u, -ts_lds(rt + static_cast<uint32_t>(i + 1) * 4u));
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&sempty[slot]);
+                    mbar_arrive(&wfull[c]);
+                }
+                if (++slot == q.nstage) slot = 0, spar ^= 1;
+            }
+            if (lane == 0) mbar_arrive(&rempty[par]);
+        }
+    } else {
+        // ------------------------------------------------------------------ consumers
+        const int cw = warp;
+        const uint32_t P4 = static_cast<uint32_t>(P) * 4u;
+        const float inv_c = p.tab.inv_c;
+        // statistics of the longest horizon (want_stats): float64 partial sums of this thread
+        double st_n = 0.0, st_s = 0.0, st_q = 0.0;
+        float st_mn = INFINITY, st_mx = -INFINITY;
+        uint32_t it = 0;
+        for (int e = 0; e < nenv; ++e) {
+            const uint32_t par = static_cast<uint32_t>(e & 1);
+            mbar_wait(&rfull[par], (static_cast<uint32_t>(e) >> 1) & 1u);
+            const uint32_t rt = rt_a + par * rt_bytes, lt = lim_a + par * rt_bytes;
+            int waited = 0;
+            for (int s = 0; s < NS; ++s, ++it) {
+                const int t0 = s * kTsStep + lane, t1 = t0 + kTsRows;
+                const int last_i = min(N - 1, s * kTsStep + kTsStep - 1 + nmax - 1);  // last slab index a live gather may touch
+                const int cneed = last_i / kTsRows;
+                while (waited <= cneed) {
+                    mbar_wait(&wfull[waited], par);
+                    ++waited;
+                }
+                const int lim0 = ts_lds_s32(lt + static_cast<uint32_t>(t0) * 4u);
+                const int lim1 = ts_lds_s32(lt + static_cast<uint32_t>(t1) * 4u);
+                const float R0 = ts_lds(rt + static_cast<uint32_t>(t0) * 4u);
+                const float R1 = ts_lds(rt + static_cast<uint32_t>(t1) * 4u);
+                const int m0 = N - t0, m1 = N - t1;              // rows left
+                const int m_min = N - (s * kTsStep + kTsStep - 1);  // smallest m of the step (may be <= 0)
+                const bool end0 = m0 >= 1 && m0 <= nmax && lim0 == m0;  // alive until the rollout ends, window may run off
+                const bool end1 = m1 >= 1 && m1 <= nmax && lim1 == m1;
+                const uint32_t base = wt_a + static_cast<uint32_t>(t0) * 4u;
+                // output tile: [half][32-horizon group][32 rows][128 B], 16-byte chunks swizzled with the row (TMA 128B
+                // swizzle): the 8 lanes of a quarter-warp store to 8 different bank groups
+                const uint32_t orow = ot_a + static_cast<uint32_t>(lane) * 128u;
+                const uint32_t ohalf = static_cast<uint32_t>(K / 32) * 4096u;
+                bool tile_free = false;
+                for (int quad = (cw + s) % kTsConsumers; quad < q.kq; quad += kTsConsumers) {
+                    float o0[4], o1[4];
+                    uint4 hz[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) hz[u] = ts_lds128(hz_a + static_cast<uint32_t>(quad * 4 + u) * 16u);
+                    // rows whose n-step windows run off the rollout: one folded bootstrap from the final row, host
+                    // weights from the horizon-major tables (issued for the whole quad before the entry loops)
+                    float tacc0[4] = {0.f, 0.f, 0.f, 0.f}, tacc1[4] = {0.f, 0.f, 0.f, 0.f};
+                    const int maxn_q = max(max(static_cast<int>(hz[0].w), static_cast<int>(hz[1].w)),
+                                           max(static_cast<int>(hz[2].w), static_cast<int>(hz[3].w)));
+                    if (m_min < maxn_q) {
+                        int idx0[4], idx1[4];
+                        float w00[4], w01[4], w10[4], w11[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int64_t tb = static_cast<int64_t>(quad * 4 + u) * q.tail_pitch;
+                            idx0[u] = 0, idx1[u] = 0, w00[u] = 0.f, w01[u] = 0.f, w10[u] = 0.f, w11[u] = 0.f;
+                            if (end0) {
+                                idx0[u] = __ldg(p.tab.tailT_idx + tb + m0);
+                                w00[u] = __ldg(p.tab.tailT_cwlo + tb + m0), w01[u] = __ldg(p.tab.tailT_cwhi + tb + m0);
+                            }
+                            if (end1) {
+                                idx1[u] = __ldg(p.tab.tailT_idx + tb + m1);
+                                w10[u] = __ldg(p.tab.tailT_cwlo + tb + m1), w11[u] = __ldg(p.tab.tailT_cwhi + tb + m1);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (end0) {
+                                const float v0 = ts_lds(fr_a + static_cast<uint32_t>(idx0[u] & 0xffff) * 4u);
+                                const float v1 = ts_lds(fr_a + static_cast<uint32_t>(idx0[u] >> 16) * 4u);
+                                tacc0[u] = fmaf(v1, w01[u], v0 * w00[u]);
+                            }
+                            if (end1) {
+                                const float v0 = ts_lds(fr_a + static_cast<uint32_t>(idx1[u] & 0xffff) * 4u);
+                                const float v1 = ts_lds(fr_a + static_cast<uint32_t>(idx1[u] >> 16) * 4u);
+                                tacc1[u] = fmaf(v1, w11[u], v0 * w10[u]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float acc0 = tacc0[u], acc1 = tacc1[u];
+                        uint32_t ce = ent_a + hz[u].x * 16u;
+                        int left = (q.dbg & 8) ? 0 : static_cast<int>(hz[u].y);
+                        for (; left >= 4; left -= 4, ce += 64) ts_eval<4, PITCH4>(ce, base, P4, lim0, lim1, acc0, acc1);
+                        if (left >= 2) ts_eval<2, PITCH4>(ce, base, P4, lim0, lim1, acc0, acc1), ce += 32, left -= 2;
+                        if (left >= 1) ts_eval<1, PITCH4>(ce, base, P4, lim0, lim1, acc0, acc1);
+                        const float rs = __uint_as_float(hz[u].z);
+                        o0[u] = fmaf(rs, R0, acc0 * inv_c);
+                        o1[u] = fmaf(rs, R1, acc1 * inv_c);
+                    }
+                    if (!tile_free) {  // the previous step's tile has been copied out (single output tile)
+                        mbar_wait(oempty, (it & 1u) ^ 1u);
+                        tile_free = true;
+                    }
+                    const uint32_t oq = orow + static_cast<uint32_t>(quad >> 3) * 4096u +
+                                        (static_cast<uint32_t>((quad & 7) ^ (lane & 7)) << 4);
+                    ts_sts128(oq, o0[0], o0[1], o0[2], o0[3]);
+                    ts_sts128(oq + ohalf, o1[0], o1[1], o1[2], o1[3]);
+                    if (q.want_stats && quad == q.kq - 1) {
+                        if (t0 < N) {
+                            const float x = o0[3];
+                            st_n += 1.0, st_s += x, st_q += static_cast<double>(x) * x;
+                            st_mn = fminf(st_mn, x), st_mx = fmaxf(st_mx, x);
+                        }
+                        if (t1 < N) {
+                            const float x = o1[3];
+                            st_n += 1.0, st_s += x, st_q += static_cast<double>(x) * x;
+                            st_mn = fminf(st_mn, x), st_mx = fmaxf(st_mx, x);
+                        }
+                    }
+                }
+                if (!tile_free) mbar_wait(oempty, (it & 1u) ^ 1u);  // warps without a quad still keep the phases in step
+                fence_async_smem();  // tile writes -> visible to the bulk-copy (async) proxy
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(ofull);
+                    mbar_arrive(&bdone[s]);
+                }
+            }
+            if (lane == 0) mbar_arrive(&rempty[par]);
+        }
+        if (q.want_stats) {
+            // per-CTA record: the staging ring is idle by now (every chunk has been transposed and consumed)
+            asm volatile("bar.sync 1, %0;" ::"n"(kTsConsumers * 32) : "memory");
+            double* red = reinterpret_cast<double*>(smem + q.off_stage);
+            const double n = warp_sum_f64(st_n), sm = warp_sum_f64(st_s), sq = warp_sum_f64(st_q);
+            const float mn = warp_min_f32(st_mn), mx = warp_max_f32(st_mx);
+            if (lane == 0) {
+                red[cw * 8 + 0] = n, red[cw * 8 + 1] = sm, red[cw * 8 + 2] = sq;
+                red[cw * 8 + 3] = static_cast<double>(mn), red[cw * 8 + 4] = static_cast<double>(mx);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kTsConsumers * 32) : "memory");
+            if (cw == 0) {
+                double an = 0, as = 0, aq = 0, amn = INFINITY, amx = -INFINITY;
+                if (lane < kTsConsumers) {
+                    an = red[lane * 8 + 0], as = red[lane * 8 + 1], aq = red[lane * 8 + 2];
+                    amn = red[lane * 8 + 3], amx = red[lane * 8 + 4];
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    an += shfl_down_f64(an, d), as += shfl_down_f64(as, d), aq += shfl_down_f64(aq, d);
+                    amn = fmin(amn, shfl_down_f64(amn, d)), amx = fmax(amx, shfl_down_f64(amx, d));
+                }
+                int last = 0;
+                if (lane == 0) {
+                    double* rec = q.partials + static_cast<int64_t>(blockIdx.x) * 8;
+                    rec[0] = an, rec[1] = as, rec[2] = aq, rec[3] = amn, rec[4] = amx;
+                    __threadfence();
+                    last = atomicAdd(q.ticket, 1u) == gridDim.x - 1;
+                }
+                last = __shfl_sync(0xffffffffu, last, 0);
+                if (last) {
+                    // the last CTA folds all records in index order: deterministic, no float atomics
+                    __threadfence();
+                    an = 0, as = 0, aq = 0, amn = INFINITY, amx = -INFINITY;
+                    for (unsigned int g = lane; g < gridDim.x; g += 32) {
+                        const double* rec = q.partials + static_cast<int64_t>(g) * 8;
+                        an += __ldcg(rec), as += __ldcg(rec + 1), aq += __ldcg(rec + 2);
+                        amn = fmin(amn, __ldcg(rec + 3)), amx = fmax(amx, __ldcg(rec + 4));
+                    }
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) {
+                        an += shfl_down_f64(an, d), as += shfl_down_f64(as, d), aq += shfl_down_f64(aq, d);
+                        amn = fmin(amn, shfl_down_f64(amn, d)), amx = fmax(amx, shfl_down_f64(amx, d));
+                    }
+                    if (lane == 0) {
+                        for (int j = 0; j < PPO_STATS_LEN; ++j) q.stats[j] = 0.0;
+                        q.stats[PPO_STAT_COUNT] = an;
+                        q.stats[PPO_STAT_ADV_SUM] = as;
+                        q.stats[PPO_STAT_ADV_SUMSQ] = aq;
+                        q.stats[PPO_STAT_ADV_MIN] = amn;
+                        q.stats[PPO_STAT_ADV_MAX] = amx;
+                        *q.ticket = 0u;
+                    }
+                }
+            }
+        }
+    }
+}
+
+static uint32_t ts_align(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
+
+template <int V, int PITCH>
+static int ts_launch_variant(const TsParams& q, const CUtensorMap& vmap, const CUtensorMap& omap, int64_t grid,
+                             cudaStream_t stream) {
+    PPO_CUDA(cudaFuncSetAttribute(tvf_tslab_kernel<V, PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(q.smem_total)));
+    tvf_tslab_kernel<V, PITCH><<<static_cast<unsigned>(grid), kTsThreads, q.smem_total, stream>>>(q, vmap, omap);
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+// stats / partials / ticket: optional fused statistics of the longest horizon (workspace layout of tvf.cu).
+int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsigned int* ticket, int64_t max_partials,
+                     cudaStream_t stream, bool* stats_fused) {
+    *stats_fused = false;
+    const int N = p.steps, K = p.n_req, V = p.n_val, nmax = p.tab.nmax, E = p.tab.n_entries;
+    auto unsupported = [&](const char* why) {
+        set_error("ppo_tvf_targets: transposed slab kernel unavailable: %s", why);
+        return PPO_ERR_UNSUPPORTED;
+    };
+    if (V != 32 && V != 64 && V != 128) return unsupported("value horizons must be 32, 64 or 128");
+    if (K > kTsMaxK || K % 32 != 0) return unsupported("required horizons must be a multiple of 32, at most 128");
+    if (N > kTsMaxChunks * kTsRows) return unsupported("more than 512 steps");
+    if (!p.tab.host_blob || !p.tab.dev_blob) return unsupported("tables carry no host mirror (ppo_tvf_tables_build)");
+    if (!p.tab.tailT_idx || !p.tab.tailT_cwlo || !p.tab.tailT_cwhi || p.tab.tail_pitch <= nmax)
+        return unsupported("horizon-major tail tables missing");
+    if (!(p.tab.gamma > 0.0)) return unsupported("tables carry no gamma");
+    if ((reinterpret_cast<uintptr_t>(p.vs) & 15) || (p.vs_es * 4) % 16 || (p.vs_rs * 4) % 16 || p.vs_es < V)
+        return unsupported("value samples are not 16-byte aligned / strided");
+    if (reinterpret_cast<uintptr_t>(p.out) & 15) return unsupported("targets are not 16-byte aligned");
+    if (p.envs > INT32_MAX) return unsupported("too many envs");
+    if (static_cast<int64_t>(K) * E > kTsMaxEntries) return unsupported("more than 1024 (horizon, n-step) entries");
+
+    TsParams q{};
+    q.p = p;
+    q.gamma = p.tab.gamma;
+    q.nc = (N + kTsRows - 1) / kTsRows;
+    q.ns = (N + kTsStep - 1) / kTsStep;
+    q.pitch = N | 1;
+    q.kq = K / 4;
+    q.rt_words = q.ns * kTsStep + kTsStep;
+    q.tail_pitch = p.tab.tail_pitch;
+    {
+        const char* d = getenv("PPO_TVF_DEBUG");
+        q.dbg = d ? atoi(d) : 0;
+    }
+
+    // ---- per-horizon launch constants from the host mirror of the tables
+    auto host = [&](const void* dev_ptr) {
+        return static_cast<const char*>(p.tab.host_blob) +
+               (static_cast<const char*>(dev_ptr) - static_cast<const char*>(p.tab.dev_blob));
+    };
+    const int32_t* h_n = reinterpret_cast<const int32_t*>(host(p.tab.ent_n));
+    const float* h_cnt = reinterpret_cast<const float*>(host(p.tab.ent_cnt));
+    const int32_t* h_idx = reinterpret_cast<const int32_t*>(host(p.tab.ent_idx));
+    const float* h_wlo = reinterpret_cast<const float*>(host(p.tab.ent_wlo));
+    const float* h_whi = reinterpret_cast<const float*>(host(p.tab.ent_whi));
+    int total = 0;
+    for (int k = 0; k < K; ++k) {
+        TsHorizon& h = q.hz[k];
+        h.beg = total, h.cnt = 0, h.maxn = 0;
+        double csum = 0.0;
+        for (int e = 0; e < E; ++e) {
+            const int64_t i = static_cast<int64_t>(e) * K + k;
+            const float cc = h_cnt[i];
+            if (!(cc > 0.f)) continue;
+            const int n = h_n[i];
+            if (n < 1 || n > N) return unsupported("entry n-step outside 1..N");
+            int lo = h_idx[i] & 0xffff, hi = h_idx[i] >> 16;
+            double a = h_wlo[i], bw = h_whi[i];
+            if (lo >= V || hi >= V) return unsupported("interpolation slot outside the value horizons");
+            int col;
+            if (a == 0.0 && bw == 0.0) {
+                col = V, a = 1.0, bw = 0.0;  // no bootstrap: gamma^n * (-R(t + n)) from the -R column
+            } else if (hi == lo) {
+                col = lo, bw = 0.0;          // single slot: the neighbour column is read with weight zero
+            } else if (hi == lo + 1) {
+                col = lo;
+            } else {
+                return unsupported("interpolation slots are not adjacent");
+            }
+            const double cg = static_cast<double>(cc) * pow(q.gamma, static_cast<double>(n));
+            TsEntry& t = q.ent[total++];
+            t.off = static_cast<uint32_t>((static_cast<int64_t>(col) * q.pitch + n - 1) * 4);
+            t.wlo = static_cast<float>(a * cg), t.whi = static_cast<float>(bw * cg);
+            t.n = n;
+            ++h.cnt;
+            csum += cc;
+            h.maxn = n > h.maxn ? n : h.maxn;
+        }
+        h.rscale = static_cast<float>(csum * static_cast<double>(p.tab.inv_c));
+    }
+    q.n_ent = total;
+
+    int dev = 0, max_smem = 0;
+    PPO_CUDA(cudaGetDevice(&dev));
+    PPO_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const uint32_t chunk = kTsRows * static_cast<uint32_t>(V) * 4u;
+    const uint32_t wt_bytes = ts_align((static_cast<uint32_t>(V + 2) * q.pitch + nmax + 2 * kTsStep) * 4u, 1024);
+    const uint32_t ot_bytes = static_cast<uint32_t>(kTsStep) * K * 4u;  // dense swizzled sub-tiles of 4096 bytes
+    const uint32_t ent_bytes = ts_align(static_cast<uint32_t>(total > 0 ? total : 1) * 16u, 128);
+    const uint32_t hz_bytes = ts_align(static_cast<uint32_t>(K) * 16u, 128);
+    const uint32_t rt_bytes = ts_align(2u * q.rt_words * 4u, 128);
+    const uint32_t fr_bytes = ts_align(static_cast<uint32_t>(V) * 4u, 128);
+    const uint32_t bar_bytes = (8u + kTsMaxChunks + kTsMaxSteps + 4 + 2) * 8u;
+    const uint32_t fixed = wt_bytes + ot_bytes + ent_bytes + hz_bytes + 2 * rt_bytes + fr_bytes + bar_bytes;
+    int nstage = 0;
+    while (nstage < 4 && fixed + static_cast<uint32_t>(nstage + 1) * chunk <= static_cast<uint32_t>(max_smem)) ++nstage;
+    if (nstage < 2) return unsupported("the transposed env slab does not fit in shared memory");
+    q.nstage = nstage;
+    q.off_stage = wt_bytes;
+    q.off_ot = q.off_stage + static_cast<uint32_t>(nstage) * chunk;
+    q.off_ent = q.off_ot + ot_bytes;
+    q.off_hz = q.off_ent + ent_bytes;
+    q.off_rtab = q.off_hz + hz_bytes;
+    q.off_lim = q.off_rtab + rt_bytes;
+    q.off_fr = q.off_lim + rt_bytes;
+    q.off_bar = q.off_fr + fr_bytes;
+    q.smem_total = q.off_bar + bar_bytes;
+
+    CUtensorMap vmap;
+    const uint64_t dims[3] = {static_cast<uint64_t>(V), static_cast<uint64_t>(p.envs), static_cast<uint64_t>(N) + 1};
+    const uint64_t strides[2] = {static_cast<uint64_t>(p.vs_es) * 4, static_cast<uint64_t>(p.vs_rs) * 4};
+    const uint32_t box[3] = {static_cast<uint32_t>(V), 1u, static_cast<uint32_t>(kTsRows)};
+    int rc = encode_tensor_map(&vmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.vs, dims, strides, box);
+    if (rc != PPO_OK) return rc;
+
+    CUtensorMap omap;  // targets [N, A, K]: 32 rows x 32 horizons per store, 128-byte swizzle
+    {
+        const uint64_t odims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(p.envs), static_cast<uint64_t>(N)};
+        const uint64_t ostrides[2] = {static_cast<uint64_t>(K) * 4, static_cast<uint64_t>(p.envs) * K * 4};
+        const uint32_t obox[3] = {32u, 1u, static_cast<uint32_t>(kTsRows)};
+        rc = encode_tensor_map(&omap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.out, odims, ostrides, obox, true);
+        if (rc != PPO_OK) return rc;
+    }
+
+    int64_t grid = sm_count();
+    if (grid > p.envs) grid = p.envs;
+    q.env_base = p.envs / grid;
+    q.env_rem = p.envs % grid;
+    q.want_stats = (stats && partials && ticket && grid <= max_partials) ? 1 : 0;
+    q.stats = stats, q.partials = partials, q.ticket = ticket;
+
+    // the production shapes get the slab pitch as a compile-time constant (immediate gather offsets)
+    if (V == 128 && q.pitch == 257) rc = ts_launch_variant<128, 257>(q, vmap, omap, grid, stream);
+    else if (V == 128 && q.pitch == 129) rc = ts_launch_variant<128, 129>(q, vmap, omap, grid, stream);
+    else if (V == 128) rc = ts_launch_variant<128, 0>(q, vmap, omap, grid, stream);
+    else if (V == 64) rc = ts_launch_variant<64, 0>(q, vmap, omap, grid, stream);
+    else rc = ts_launch_variant<32, 0>(q, vmap, omap, grid, stream);
+    if (rc != PPO_OK) return rc;
+    *stats_fused = q.want_stats != 0;
+    return PPO_OK;
+}
+
+}  // namespace ppo

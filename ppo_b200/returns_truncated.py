@@ -14,20 +14,91 @@ from . import _device as dev
 from . import _lib
 from . import _tvf_tables
 
-PATH_AUTO, PATH_GENERIC, PATH_RING = 0, 1, 2
+PATH_AUTO, PATH_GENERIC, PATH_RING, PATH_TSLAB = 0, 1, 2, 3
 
 
 class _CTables(ctypes.Structure):
+    """``ppo_tvf_tables`` of include/ppo_b200.h."""
     _fields_ = [("n_entries", ctypes.c_int32), ("nmax", ctypes.c_int32),
                 ("ent_n", ctypes.c_void_p), ("ent_cnt", ctypes.c_void_p), ("ent_idx", ctypes.c_void_p),
                 ("ent_wlo", ctypes.c_void_p), ("ent_whi", ctypes.c_void_p), ("ent_g", ctypes.c_void_p),
                 ("tail_idx", ctypes.c_void_p), ("tail_wlo", ctypes.c_void_p), ("tail_whi", ctypes.c_void_p),
                 ("tail_cwlo", ctypes.c_void_p), ("tail_cwhi", ctypes.c_void_p),
-                ("gpow", ctypes.c_void_p), ("inv_c", ctypes.c_float)]
+                ("gpow", ctypes.c_void_p), ("inv_c", ctypes.c_float), ("tail_pitch", ctypes.c_int32),
+                ("tailT_idx", ctypes.c_void_p), ("tailT_cwlo", ctypes.c_void_p), ("tailT_cwhi", ctypes.c_void_p),
+                ("host_blob", ctypes.c_void_p), ("dev_blob", ctypes.c_void_p), ("gamma", ctypes.c_double)]
+
+
+class _CLayout(ctypes.Structure):
+    """``ppo_tvf_table_layout`` of include/ppo_b200.h."""
+    _fields_ = [("n_entries", ctypes.c_int32), ("nmax", ctypes.c_int32), ("total_words", ctypes.c_int64),
+                ("offset_words", ctypes.c_int64 * 16), ("inv_c", ctypes.c_float), ("tail_pitch", ctypes.c_int32),
+                ("gamma", ctypes.c_double)]
+
+
+_TABLE_NAMES = ["ent_n", "ent_cnt", "ent_idx", "ent_wlo", "ent_whi", "ent_g", "tail_idx", "tail_wlo", "tail_whi",
+                "tail_cwlo", "tail_cwhi", "gpow", "tailT_idx", "tailT_cwlo", "tailT_cwhi"]
+
+
+class NativeTables:
+    """Packed index tables built by ``ppo_tvf_tables_build`` (host integers and table arithmetic only):
+    ``host`` is the blob (a pinned CPU int32 tensor when CUDA is present), ``layout`` its table offsets."""
+    __slots__ = ("host", "layout", "n_entries", "nmax", "inv_c", "n_req", "steps")
+
+    def table(self, name):
+        """NumPy view of one table inside the host blob (for tests)."""
+        i = _TABLE_NAMES.index(name)
+        lo, hi = self.layout.offset_words[i], self.layout.offset_words[i + 1]
+        words = self.host.numpy()[lo:hi]
+        return words.view(np.float32) if name not in ("ent_n", "ent_idx", "tail_idx", "tailT_idx") else words
+
+
+def build_tables(gamma, steps, required_horizons, value_sample_horizons, n_step_samples,
+                 use_log_interpolation=False, optimise_slots=False):
+    """Resolve a ``[K, C]`` n-step sample table into the packed index tables (host side of ``ppo_tvf_targets``).
+    Raises like the reference: ``AssertionError`` for an n-step outside ``1..N`` (rl/returns_truncated.py:597),
+    ``IndexError`` for a bootstrap horizon beyond the last value horizon (:157)."""
+    lib = _lib.load()
+    req = np.ascontiguousarray(np.asarray(required_horizons).reshape(-1), dtype=np.int64)
+    vsh = np.ascontiguousarray(np.asarray(value_sample_horizons).reshape(-1), dtype=np.int64)
+    samples = np.asarray(n_step_samples)
+    assert samples.ndim == 2 and samples.shape[0] == len(req), \
+        f"n_step_samples must be [K, C] with K={len(req)}, got {samples.shape}"
+    assert samples.shape[1] >= 1, "at least one n-step sample per horizon is required"
+    samples = np.ascontiguousarray(samples, dtype=np.int64)
+    words = int(lib.ppo_tvf_tables_words(len(req), samples.shape[1], int(steps)))
+    host = torch.empty(max(words, 16), dtype=torch.int32, pin_memory=torch.cuda.is_available())
+    layout = _CLayout()
+    rc = lib.ppo_tvf_tables_build(float(gamma), int(steps), req.ctypes.data, len(req), vsh.ctypes.data, len(vsh),
+                                  samples.ctypes.data, samples.shape[1], int(bool(use_log_interpolation)),
+                                  int(bool(optimise_slots)), host.data_ptr(), host.numel(), ctypes.byref(layout))
+    if rc == _lib.PPO_ERR_BAD_ARG:
+        raise AssertionError(lib.ppo_last_error().decode("utf-8", "replace"))
+    if rc == _lib.PPO_ERR_UNSUPPORTED:
+        raise IndexError(lib.ppo_last_error().decode("utf-8", "replace"))
+    _lib.check(rc, "ppo_tvf_tables_build")
+    t = NativeTables()
+    t.host, t.layout = host, layout
+    t.n_entries, t.nmax, t.inv_c = layout.n_entries, layout.nmax, layout.inv_c
+    t.n_req, t.steps = len(req), int(steps)
+    return t
 
 
 def _upload_tables(tabs, device):
-    """One packed H2D copy of all tables; returns (ctypes struct, tensor keeping the memory alive)."""
+    """One packed H2D copy of all tables; returns (ctypes struct, tensors keeping the memory alive).
+    ``tabs``: :class:`NativeTables`, or the NumPy reference builder's ``TvfTables`` (tests; no host mirror, so
+    the transposed slab kernel is not available for it)."""
+    c = _CTables()
+    if isinstance(tabs, NativeTables):
+        n = int(tabs.layout.total_words)
+        blob = tabs.host[:n].to(device, non_blocking=True)
+        base = blob.data_ptr()
+        for i, name in enumerate(_TABLE_NAMES):
+            setattr(c, name, base + 4 * int(tabs.layout.offset_words[i]))
+        c.n_entries, c.nmax, c.inv_c = tabs.n_entries, tabs.nmax, float(tabs.inv_c)
+        c.tail_pitch, c.gamma = tabs.layout.tail_pitch, tabs.layout.gamma
+        c.host_blob, c.dev_blob = tabs.host.data_ptr(), base
+        return c, (blob, tabs.host)
     parts = [tabs.ent_n, tabs.ent_cnt, tabs.ent_idx, tabs.ent_wlo, tabs.ent_whi, tabs.ent_g,
              tabs.tail_idx, tabs.tail_wlo, tabs.tail_whi, tabs.tail_cwlo, tabs.tail_cwhi, tabs.gpow]
     words, offsets = 0, []
@@ -39,18 +110,15 @@ def _upload_tables(tabs, device):
         host[off:off + a.size] = np.ascontiguousarray(a).reshape(-1).view(np.int32)
     blob = torch.from_numpy(host).to(device, non_blocking=True)
     base = blob.data_ptr()
-    c = _CTables()
     c.n_entries, c.nmax = tabs.n_entries, tabs.nmax
-    names = ["ent_n", "ent_cnt", "ent_idx", "ent_wlo", "ent_whi", "ent_g", "tail_idx", "tail_wlo", "tail_whi",
-             "tail_cwlo", "tail_cwhi", "gpow"]
-    for name, off in zip(names, offsets):
+    for name, off in zip(_TABLE_NAMES[:12], offsets):
         setattr(c, name, base + 4 * off)
     c.inv_c = float(tabs.inv_c)
     return c, blob
 
 
 def _launch(gamma, rewards, dones, required_horizons, value_sample_horizons, value_samples, n_step_samples,
-            use_log_interpolation, path=PATH_AUTO, with_stats=False, keep_on_device=False):
+            use_log_interpolation, path=PATH_AUTO, with_stats=False, keep_on_device=False, numpy_tables=False):
     device = dev.require_cuda()
     lib = _lib.load()
     np_like = dev.is_numpy_like(rewards)
@@ -68,7 +136,10 @@ def _launch(gamma, rewards, dones, required_horizons, value_sample_horizons, val
     assert d is not None and tuple(d.shape) == (steps, envs), f"dones must be [N, A] = {(steps, envs)}"
     d = dev.env_contiguous(d)
 
-    tabs = _tvf_tables.build(gamma, steps, req, vsh, n_step_samples, use_log_interpolation)
+    if numpy_tables or steps == 0 or envs == 0 or n_req == 0:  # the documented NumPy builder (tests compare both builders through the kernels)
+        tabs = _tvf_tables.build(gamma, steps, req, vsh, n_step_samples, use_log_interpolation)
+    else:
+        tabs = build_tables(gamma, steps, req, vsh, n_step_samples, use_log_interpolation)
     ctab, blob = _upload_tables(tabs, device)
 
     out = torch.empty((steps, envs, n_req), dtype=torch.float32, device=device)

@@ -207,10 +207,11 @@ class ReturnPass:
                                   dtype=torch.uint8, device=self.device)
         self._ctab = self._blob = None
         self.kernel_launches_per_pass = 4
+        self.tvf_kernel = "?"
 
     def set_samples(self, n_step_samples):
-        tabs = _rt._tvf_tables.build(self.tvf_gamma, self.steps, self.horizons, self.horizons, n_step_samples,
-                                     self.use_log)
+        tabs = _rt.build_tables(self.tvf_gamma, self.steps, self.horizons, self.horizons, n_step_samples,
+                                self.use_log)
         self._ctab, self._blob = _rt._upload_tables(tabs, self.device)
         return tabs
 
@@ -232,20 +233,20 @@ class ReturnPass:
         rc = lib.ppo_adv_normalize(self.advantage.data_ptr(), n * a, self.stats.data_ptr(), self.eps, self.clip,
                                    self.advantages.data_ptr(), s)
         _lib.check(rc, "ppo_adv_normalize")
-        if tvf_events is not None:  # (start, mid, end): target kernel between start..mid, statistics mid..end
+        if tvf_events is not None:  # (start, end) around the target launch(es)
             tvf_events[0].record()
+        # targets + statistics of the longest horizon: one launch on the transposed slab kernel (statistics fused),
+        # two on the other paths
         rc = lib.ppo_tvf_targets(rewards.data_ptr(), rewards.stride(0), dones.data_ptr(), _lib.DONE_U8, dones.stride(0),
                                  value_samples.data_ptr(), value_samples.stride(0), value_samples.stride(1),
                                  n, a, k, k, ctypes.byref(self._ctab), self.tvf_path, self.tvf_returns.data_ptr(),
-                                 0, 0, 0, s)
+                                 self.tvf_stats.data_ptr(), self.ws_tvf.data_ptr(), self.ws_tvf.numel(), s)
         _lib.check(rc, "ppo_tvf_targets")
+        last = lib.ppo_tvf_last_path()
+        self.tvf_kernel = {1: "generic", 2: "ring", 3: "tslab"}.get(last & 0xff, "?")
+        self.kernel_launches_per_pass = 3 if last & 0x100 else 4
         if tvf_events is not None:
             tvf_events[1].record()
-        rc = lib.ppo_tvf_last_horizon_stats(self.tvf_returns.data_ptr(), n * a, k, self.tvf_stats.data_ptr(),
-                                            self.ws_tvf.data_ptr(), self.ws_tvf.numel(), s)
-        _lib.check(rc, "ppo_tvf_last_horizon_stats")
-        if tvf_events is not None:
-            tvf_events[2].record()
         return self
 
 

@@ -90,6 +90,72 @@ def test_vs_oracle(path, steps, envs, heads, max_h, n_step, samples, done_p):
     assert rel_err(got, ref) <= TOL
 
 
+@pytest.mark.parametrize("path", [rt.PATH_TSLAB, rt.PATH_RING])
+@pytest.mark.parametrize("steps,envs,heads,max_h,n_step,samples,done_p,use_log", [
+    (128, 64, 128, 30000, 20, 8, 0.03, False),   # c3 shape, fewer envs
+    (256, 24, 128, 30000, 20, 8, 0.03, False),   # c5 shape, fewer envs
+    (256, 8, 128, 30000, 20, 8, 0.0, False),     # no terminals at all: the reward-to-go spans the whole rollout
+    (256, 160, 128, 30000, 20, 8, 0.03, True),   # more envs than SMs (in-place slab replacement), log interpolation
+    (64, 16, 128, 30000, 64, 1, 0.3, False),     # n-step == N, many terminals
+    (100, 7, 128, 30000, 20, 8, 0.05, False),    # partial last TMA box and partial last block
+    (45, 3, 32, 1000, 30, 4, 0.1, False),        # V = 32
+    (70, 301, 64, 5000, 9, 5, 0.02, False),      # V = 64, more envs than SMs
+    (31, 2, 32, 1000, 31, 6, 0.0, False),        # a single (partial) block, windows as long as the rollout
+])
+def test_slab_kernels_vs_oracle(path, steps, envs, heads, max_h, n_step, samples, done_p, use_log):
+    """The two shared-memory slab kernels explicitly (PATH_RING / PATH_TSLAB fail instead of falling back)."""
+    hz = oracle.get_value_head_horizons(heads, max_h)
+    if len(hz) % 4:
+        pytest.skip("horizon count is not a multiple of 4")
+    r, d, _ = synthetic.rollout(steps, envs, seed=steps + envs, done_prob=done_p)
+    vs = synthetic.value_samples(steps, envs, len(hz), seed=steps)
+    for mode in ("advanced", "standard"):
+        table = oracle.draw_n_step_samples("exponential", mode, hz, steps, n_step, samples, seed=5)
+        ref = oracle.sampled_return_multi(0.99997, r, d, hz, hz, vs, n_step_samples=table,
+                                          use_log_interpolation=use_log)
+        got = rt._calculate_sampled_return_multi_fast(0.99997, r, d, hz, hz, vs, n_step_samples=table,
+                                                      use_log_interpolation=use_log, path=path)
+        assert rel_err(got, ref) <= TOL
+
+
+def test_tslab_fused_statistics_and_large_rewards():
+    """Statistics of the longest horizon fused into the transposed slab kernel; rewards of one sign and no
+    terminals make the reward-to-go as large as it gets relative to the targets."""
+    steps, envs = 256, 200
+    hz = oracle.get_value_head_horizons(128, 30000)
+    rng = np.random.RandomState(3)
+    r = (rng.rand(steps, envs) * 3 + 1).astype(np.float32)
+    d = np.zeros((steps, envs), dtype=bool)
+    vs = synthetic.value_samples(steps, envs, len(hz), seed=4)
+    table = oracle.draw_n_step_samples("exponential", "advanced", hz, steps, 20, 8, seed=2)
+    ref = oracle.sampled_return_multi(0.99997, r, d, hz, hz, vs, n_step_samples=table)
+    res, stats = rt._launch(0.99997, r, d, hz, hz, vs, table, False, path=rt.PATH_TSLAB, with_stats=True)
+    from ppo_b200 import _lib
+    assert _lib.load().ppo_tvf_last_path() == (rt.PATH_TSLAB | 0x100)  # one launch, statistics fused
+    assert rel_err(res, ref) <= TOL
+    # PATH_AUTO picks the same kernel for eight n-steps per horizon, and the ring kernel for a fixed n-step
+    rt._launch(0.99997, r, d, hz, hz, vs, table, False, with_stats=True)
+    assert _lib.load().ppo_tvf_last_path() == (rt.PATH_TSLAB | 0x100)
+    rt._launch(0.99997, r, d, hz, hz, vs, np.zeros([len(hz), 1], dtype=np.int32) + 20, False)
+    assert _lib.load().ppo_tvf_last_path() == rt.PATH_RING
+    s = stats.cpu().numpy()
+    last = res[:, :, -1].astype(np.float64)
+    assert s[0] == last.size and s[3] == last.min() and s[4] == last.max()
+    np.testing.assert_allclose(s[1], last.sum(), rtol=1e-12)
+    np.testing.assert_allclose(s[2], (last ** 2).sum(), rtol=1e-12)
+
+
+def test_numpy_and_native_tables_agree_through_the_kernels(golden):
+    a = _tvf_args(golden)
+    s = golden["tvf_in_samples"]
+    steps = a['rewards'].shape[0]
+    x = rt._launch(a['gamma'], a['rewards'], a['dones'], a['required_horizons'], a['value_sample_horizons'],
+                   a['value_samples'], s, False, path=rt.PATH_GENERIC, numpy_tables=True)
+    y = rt._launch(a['gamma'], a['rewards'], a['dones'], a['required_horizons'], a['value_sample_horizons'],
+                   a['value_samples'], s, False, path=rt.PATH_GENERIC, numpy_tables=False)
+    assert np.array_equal(x, y) and steps > 0
+
+
 def test_device_tensors_strided_values_and_stats():
     steps, envs = 48, 40
     hz = oracle.get_value_head_horizons(32, 1000)

@@ -63,3 +63,47 @@ def test_rejects_bad_tables():
         T.build(0.99, 10, hz, hz, np.zeros([16, 2], dtype=np.int32))       # n-step < 1
     with pytest.raises(IndexError):
         T.build(0.99, 10, np.asarray([500]), hz, np.ones([1, 1], dtype=np.int32))
+
+
+@pytest.mark.parametrize("use_log", [False, True])
+@pytest.mark.parametrize("case", ["geometric", "test_tvf", "production"])
+def test_native_builder_matches_numpy_builder(built_library, case, use_log):
+    """ppo_tvf_tables_build (C++, the product path) against the documented NumPy construction, bit for bit."""
+    from ppo_b200 import returns_truncated as rt
+    rng = np.random.RandomState(1)
+    if case == "geometric":
+        req = vsh = oracle.get_value_head_horizons(64, 3000)
+        steps, table = 96, rng.randint(1, 97, size=[64, 6])
+    elif case == "test_tvf":
+        req = np.geomspace(1, 1024, num=16).astype('int32')
+        vsh = np.geomspace(1, 1024, num=32).astype('int32') - 1
+        steps, table = 48, rng.randint(1, 49, size=[16, 5])
+    else:
+        req = vsh = oracle.get_value_head_horizons(128, 30000)
+        steps = 256
+        table = oracle.draw_n_step_samples("exponential", "advanced", req, steps, 20, 8, seed=1)
+    ref = T.build(0.99997, steps, req, vsh, table, use_log)
+    nat = rt.build_tables(0.99997, steps, req, vsh, table, use_log)
+    assert (nat.n_entries, nat.nmax) == (ref.n_entries, ref.nmax)
+    assert np.float32(nat.inv_c) == ref.inv_c and nat.layout.gamma == 0.99997
+    for name in ["ent_n", "ent_cnt", "ent_idx", "ent_wlo", "ent_whi", "ent_g", "tail_idx", "tail_wlo", "tail_whi",
+                 "tail_cwlo", "tail_cwhi", "gpow"]:
+        want = np.ascontiguousarray(getattr(ref, name)).reshape(-1)
+        got = nat.table(name)[:want.size]
+        assert np.array_equal(got.view(np.int32), want.view(np.int32)), name
+    # horizon-major tail tables are the transposes of the row-major ones
+    pitch, k = nat.layout.tail_pitch, len(req)
+    for name, src in [("tailT_idx", ref.tail_idx), ("tailT_cwlo", ref.tail_cwlo), ("tailT_cwhi", ref.tail_cwhi)]:
+        got = nat.table(name)[:k * pitch].reshape(k, pitch)[:, :ref.nmax + 1]
+        assert np.array_equal(got.view(np.int32), np.ascontiguousarray(src.T).view(np.int32)), name
+
+
+def test_native_builder_errors(built_library):
+    from ppo_b200 import returns_truncated as rt
+    hz = oracle.get_value_head_horizons(16, 100)
+    with pytest.raises(AssertionError):
+        rt.build_tables(0.99, 10, hz, hz, np.zeros([16, 2], dtype=np.int32) + 11)
+    with pytest.raises(AssertionError):
+        rt.build_tables(0.99, 10, hz, hz, np.zeros([16, 2], dtype=np.int32))
+    with pytest.raises(IndexError):
+        rt.build_tables(0.99, 10, np.asarray([500]), hz, np.ones([1, 1], dtype=np.int32))

@@ -34,10 +34,10 @@ def main():
                     table = oracle.draw_n_step_samples("exponential", "standard", hz, steps, 20, 8, seed=1)
                 else:
                     table = np.zeros([128, 1], dtype=np.int32) + 20
-                tabs = _tvf_tables.build(0.99997, steps, hz, hz, table)
+                tabs = rt.build_tables(0.99997, steps, hz, hz, table)
                 ctab, blob = rt._upload_tables(tabs, device)
-                for path, name in ((rt.PATH_RING, "ring"), (rt.PATH_GENERIC, "generic")):
-                    if name == "generic" and envs > 4096:
+                for path, name in ((rt.PATH_TSLAB, "tslab"), (rt.PATH_RING, "ring"), (rt.PATH_GENERIC, "generic")):
+                    if name == "generic" and (envs > 4096 or len(sys.argv) > 1):
                         continue
                     def fn():
                         rc = lib.ppo_tvf_targets(r.data_ptr(), envs, d.data_ptr(), 1, envs, vs.data_ptr(), envs * 128, 128,

@@ -9,6 +9,7 @@ from ppo_b200 import returns_truncated as rt, _lib, _tvf_tables
 def main():
     steps, envs = 256, int(sys.argv[1]) if len(sys.argv) > 1 else 1184
     mode = sys.argv[2] if len(sys.argv) > 2 else "advanced8"
+    path = {"ring": rt.PATH_RING, "tslab": rt.PATH_TSLAB}[sys.argv[3] if len(sys.argv) > 3 else "tslab"]
     lib = _lib.load()
     hz = oracle.get_value_head_horizons(128, 30000)
     device = torch.device("cuda")
@@ -21,11 +22,11 @@ def main():
         table = oracle.draw_n_step_samples("exponential", "advanced", hz, steps, 20, 8, seed=1)
     else:
         table = np.zeros([128, 1], dtype=np.int32) + 20
-    tabs = _tvf_tables.build(0.99997, steps, hz, hz, table)
+    tabs = rt.build_tables(0.99997, steps, hz, hz, table)
     ctab, blob = rt._upload_tables(tabs, device)
     for _ in range(3):
         rc = lib.ppo_tvf_targets(r.data_ptr(), envs, d.data_ptr(), 1, envs, vs.data_ptr(), envs * 128, 128,
-                                 steps, envs, 128, 128, ctypes.byref(ctab), rt.PATH_RING, out.data_ptr(), 0, 0, 0,
+                                 steps, envs, 128, 128, ctypes.byref(ctab), path, out.data_ptr(), 0, 0, 0,
                                  torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "tvf")
     torch.cuda.synchronize()
