@@ -262,6 +262,15 @@ int ppo_vtrace(const float* behaviour_log_policy, const float* target_log_policy
 int ppo_vtrace_trust_region(const float* behaviour_log_policy, const float* target_log_policy,
                             int64_t rows, int64_t n_actions, float* out, void* stream);
 
+/*
+ * Stream-ordered strided copy between host (pinned) and device memory: `rows` rows of `width_bytes`, any direction.
+ * Plumbing for calls whose rollout buffers live in host memory (the reference keeps them in NumPy arrays,
+ * rl/rollout.py:646-680): an env block of a [N, A, K] host buffer is `N` rows of `A_block * K * 4` bytes with the
+ * full row as pitch, so blocks can be uploaded / downloaded while other blocks are being computed.
+ */
+int ppo_memcpy_2d_async(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes,
+                        int64_t width_bytes, int64_t rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

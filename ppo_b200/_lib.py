@@ -45,6 +45,7 @@ _SIGNATURES = {
                                 c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "ppo_tvf_last_path": (c_int, []),
     "ppo_tvf_last_horizon_stats": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
+    "ppo_memcpy_2d_async": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64, c_ptr]),
     "ppo_vtrace": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_i64, c_i64, c_i64,
                            c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ppo_vtrace_trust_region": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),

@@ -45,3 +45,15 @@ extern "C" int ppo_device_count(void) {
     if (e != cudaSuccess) return ppo::cuda_fail(e, "cudaGetDeviceCount");
     return n;
 }
+
+extern "C" int ppo_memcpy_2d_async(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes,
+                                   int64_t width_bytes, int64_t rows, void* stream) {
+    PPO_REQUIRE(width_bytes >= 0 && rows >= 0 && dst_pitch_bytes >= width_bytes && src_pitch_bytes >= width_bytes,
+                "ppo_memcpy_2d_async: bad geometry");
+    if (width_bytes == 0 || rows == 0) return PPO_OK;
+    PPO_REQUIRE(dst && src, "ppo_memcpy_2d_async: null pointer");
+    PPO_CUDA(cudaMemcpy2DAsync(dst, static_cast<size_t>(dst_pitch_bytes), src, static_cast<size_t>(src_pitch_bytes),
+                               static_cast<size_t>(width_bytes), static_cast<size_t>(rows), cudaMemcpyDefault,
+                               static_cast<cudaStream_t>(stream)));
+    return PPO_OK;
+}

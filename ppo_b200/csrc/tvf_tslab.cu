@@ -386,6 +386,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                 const int m_min = N - (s * kTsStep + kTsStep - 1);  // smallest m of the step (may be <= 0)
                 const bool end0 = m0 >= 1 && m0 <= nmax && lim0 == m0;  // alive until the rollout ends, window may run off
                 const bool end1 = m1 >= 1 && m1 <= nmax && lim1 == m1;
+                const bool any_end = __any_sync(0xffffffffu, end0 || end1);  // usually false before the last rows
                 const uint32_t base = wt_a + static_cast<uint32_t>(t0) * 4u;
                 // output tile: [half][32-horizon group][32 rows][128 B], 16-byte chunks swizzled with the row (TMA 128B
                 // swizzle): the 8 lanes of a quarter-warp store to 8 different bank groups
@@ -402,7 +403,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                     float tacc0[4] = {0.f, 0.f, 0.f, 0.f}, tacc1[4] = {0.f, 0.f, 0.f, 0.f};
                     const int maxn_q = max(max(static_cast<int>(hz[0].w), static_cast<int>(hz[1].w)),
                                            max(static_cast<int>(hz[2].w), static_cast<int>(hz[3].w)));
-                    if (m_min < maxn_q) {
+                    if (any_end && m_min < maxn_q) {
                         int idx0[4], idx1[4];
                         float w00[4], w01[4], w10[4], w11[4];
 #pragma unroll

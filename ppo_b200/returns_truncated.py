@@ -6,6 +6,7 @@ distribution / mode (``rl/returns_truncated.py:78,139``); ``AssertionError`` for
 ``1..N`` (:597); ``IndexError`` when a bootstrap horizon lies beyond the last value horizon (:157).
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -156,6 +157,140 @@ def _launch(gamma, rewards, dones, required_horizons, value_sample_horizons, val
     del blob  # same-stream allocator reuse is ordered after the kernel
     res = out if keep_on_device else dev.like_input(out, np_like)
     return (res, stats) if with_stats else res
+
+
+_pipelines = {}
+
+
+def _pipeline_state(device, steps, block, n_val, n_req):
+    """Streams and double-buffered device scratch of the host-buffer path, cached per device and shape."""
+    key = (device.index, steps, block, n_val, n_req)
+    st = _pipelines.get(key)
+    if st is None:
+        st = {
+            "s_in": torch.cuda.Stream(device=device), "s_out": torch.cuda.Stream(device=device),
+            "s_comp": torch.cuda.Stream(device=device),
+            "ws": torch.zeros(max(int(_lib.load().ppo_tvf_workspace_bytes(steps, block)), 1 << 12), dtype=torch.uint8,
+                              device=device),
+            "vs": [torch.empty((steps + 1, block, n_val), dtype=torch.float32, device=device) for _ in range(2)],
+            "out": [torch.empty((steps, block, n_req), dtype=torch.float32, device=device) for _ in range(2)],
+        }
+        _pipelines.clear()  # one shape at a time: the scratch is ~2 x (value samples + targets) of one env block
+        _pipelines[key] = st
+    return st
+
+
+def host_pipeline_ok(value_samples, out):
+    """True when the env-blocked host path applies: pinned CPU float32 tensors with contiguous env blocks."""
+    return (isinstance(value_samples, torch.Tensor) and isinstance(out, torch.Tensor)
+            and value_samples.device.type == "cpu" and out.device.type == "cpu"
+            and value_samples.is_pinned() and out.is_pinned()
+            and value_samples.dtype == torch.float32 and out.dtype == torch.float32
+            and value_samples.dim() == 3 and value_samples.stride(2) == 1
+            and value_samples.stride(1) == value_samples.shape[2] and out.is_contiguous())
+
+
+def _launch_host_blocks(gamma, rewards, dones, required_horizons, value_sample_horizons, value_samples,
+                        n_step_samples, use_log_interpolation, out, path=PATH_AUTO, with_stats=True, block_envs=None,
+                        defer_join=False):
+    """Targets for rollout buffers that live in pinned HOST memory (``value_samples [N+1, A, V]`` in, ``out
+    [N, A, K]`` out): the env axis is cut into blocks, and the upload of block c + 1, the kernels of block c and
+    the download of block c - 1 run concurrently on three streams (envs are independent, ``rl/returns_truncated.py``
+    never mixes columns), so the call costs about max(upload, download) instead of their sum.  Returns the merged
+    statistics record of the longest horizon (device tensor) or None.  The results are complete once the current
+    stream has been synchronised.  ``defer_join=True`` returns a function instead that joins the side streams
+    into the current stream and returns the record, so the caller can enqueue other work (the GAE part of the
+    pass) on its own stream while the blocks are in flight."""
+    device = dev.require_cuda()
+    lib = _lib.load()
+    r = dev.env_contiguous(dev.to_device(rewards, torch.float32, device))
+    steps, envs = r.shape
+    req, vsh = np.asarray(required_horizons), np.asarray(value_sample_horizons)
+    n_req, n_val = len(req), len(vsh)
+    assert tuple(value_samples.shape) == (steps + 1, envs, n_val), \
+        f"value_samples must be [N+1, A, V] = {(steps + 1, envs, n_val)}, got {tuple(value_samples.shape)}"
+    assert tuple(out.shape) == (steps, envs, n_req), f"out must be [N, A, K] = {(steps, envs, n_req)}"
+    d, kind = dev.done_tensor(dones, device)
+    assert d is not None and tuple(d.shape) == (steps, envs), f"dones must be [N, A] = {(steps, envs)}"
+    d = dev.env_contiguous(d)
+    tabs = build_tables(gamma, steps, req, vsh, n_step_samples, use_log_interpolation)
+    ctab, blob = _upload_tables(tabs, device)
+
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    if block_envs is None:
+        # about `target` blocks of a whole number of envs per SM; the first and last blocks are smaller so that the
+        # pipeline fills (first upload) and drains (last download) quickly
+        target = int(os.environ.get("PPO_HOST_BLOCKS", "12"))
+        block_envs = int(min(envs, sms * max(1, -(-envs // (target * sms)))))
+        ramp = [b for b in (sms, 2 * sms) if b < block_envs]
+        sizes, left = [], envs
+        if envs >= 2 * sum(ramp) + block_envs:
+            left -= 2 * sum(ramp)
+            sizes = ramp + [block_envs] * (left // block_envs) + ([left % block_envs] if left % block_envs else []) + ramp[::-1]
+        else:
+            sizes = [block_envs] * (envs // block_envs) + ([envs % block_envs] if envs % block_envs else [])
+    else:
+        block_envs = int(min(block_envs, envs))
+        sizes = [block_envs] * (envs // block_envs) + ([envs % block_envs] if envs % block_envs else [])
+    st = _pipeline_state(device, steps, block_envs, n_val, n_req)
+    s_main, s_in, s_out, s_comp = torch.cuda.current_stream(), st["s_in"], st["s_out"], st["s_comp"]
+    for s_ in (s_in, s_out, s_comp):
+        s_.wait_stream(s_main)
+    n_blocks = len(sizes)
+    stats = torch.zeros((n_blocks, _lib.STATS_LEN), dtype=torch.float64, device=device) if with_stats else None
+    ws = st["ws"] if with_stats else None
+    ev_comp, ev_out = [], []
+    lo = 0
+    for c, ab in enumerate(sizes):
+        vs_d, out_d = st["vs"][c & 1], st["out"][c & 1]
+        # ---- upload (waits until the kernels of block c - 2 have released this scratch)
+        if c >= 2:
+            s_in.wait_event(ev_comp[c - 2])
+        rc = lib.ppo_memcpy_2d_async(vs_d.data_ptr(), ab * n_val * 4,
+                                     value_samples.data_ptr() + lo * n_val * 4, value_samples.stride(0) * 4,
+                                     ab * n_val * 4, steps + 1, s_in.cuda_stream)
+        _lib.check(rc, "ppo_memcpy_2d_async")
+        ev_in = torch.cuda.Event()
+        ev_in.record(s_in)
+        # ---- kernels (their own stream: the caller's stream stays free for the GAE part of the pass)
+        s_comp.wait_event(ev_in)
+        if c >= 2:
+            s_comp.wait_event(ev_out[c - 2])
+        rc = lib.ppo_tvf_targets(
+            r.data_ptr() + lo * 4, r.stride(0), d.data_ptr() + lo * d.element_size(), kind, d.stride(0),
+            vs_d.data_ptr(), ab * n_val, n_val, steps, ab, n_req, n_val, ctypes.byref(ctab), path,
+            out_d.data_ptr(), stats[c].data_ptr() if with_stats else 0,
+            dev.ptr(ws), ws.numel() if ws is not None else 0, s_comp.cuda_stream)
+        _lib.check(rc, "ppo_tvf_targets")
+        e = torch.cuda.Event()
+        e.record(s_comp)
+        ev_comp.append(e)
+        # ---- download
+        s_out.wait_event(e)
+        rc = lib.ppo_memcpy_2d_async(out.data_ptr() + lo * n_req * 4, envs * n_req * 4, out_d.data_ptr(),
+                                     ab * n_req * 4, ab * n_req * 4, steps, s_out.cuda_stream)
+        _lib.check(rc, "ppo_memcpy_2d_async")
+        e = torch.cuda.Event()
+        e.record(s_out)
+        ev_out.append(e)
+        lo += ab
+    # the inputs (r, d, tables) must outlive the kernels: tie their lifetime to the side stream
+    for t_ in (r, d, blob[0] if isinstance(blob, tuple) else blob):
+        t_.record_stream(s_comp)
+    if stats is not None:
+        stats.record_stream(s_comp)
+    del blob
+
+    def join():
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(s_comp)
+        cur.wait_stream(s_out)
+        if not with_stats:
+            return None
+        from . import rollout as _rollout  # merge of disjoint env blocks (sums add, min / max reduce)
+        return _rollout.merge_stats(stats)  # on the caller's stream, which now waits for the kernels above
+
+    return join if defer_join else join()
 
 
 def _calculate_sampled_return_multi_fast(gamma: float, rewards, dones, required_horizons, value_sample_horizons,

@@ -115,8 +115,30 @@ def calculate_returns(ext_rewards, ext_value_estimates, terminals, gamma, lambda
     """
     np_like = dev.is_numpy_like(ext_rewards)
     device = dev.require_cuda()
+    steps = ext_value_estimates.shape[0] - 1
+    tvf_join = tvf_launch = None
+    if tvf is not None:
+        kw = dict(tvf)
+        vs = kw.pop("value_samples")
+        hz = kw.pop("horizons")
+        g = kw.pop("gamma")
+        mode = kw.pop("mode", "advanced")
+        distribution = kw.pop("distribution", "exponential")
+        samples = _rt.draw_n_step_samples(distribution, mode, np.asarray(hz), steps, kw.pop("n_step", 40),
+                                          kw.pop("max_samples", 40), kw.pop("seed", None))
+        if distribution != "fixed" and mode == "full":
+            raise ValueError("calculate_returns: use returns_truncated.get_return_estimate for mode='full'")
+        use_log = kw.pop("use_log_interpolation", False)
+        to_host = out is not None and "tvf_returns" in out
+        if to_host and steps > 0 and _rt.host_pipeline_ok(vs, out["tvf_returns"]):
+            # rollout buffers in pinned host memory: env blocks are uploaded, computed and downloaded concurrently on
+            # side streams, started first so that the transfers overlap the GAE part below
+            tvf_join = _rt._launch_host_blocks(g, ext_rewards, terminals, hz, hz, vs, samples, use_log,
+                                               out["tvf_returns"], defer_join=True)
+        else:
+            tvf_launch = lambda: _rt._launch(g, ext_rewards, terminals, hz, hz, vs, samples, use_log,  # noqa: E731
+                                             with_stats=True, keep_on_device=to_host)
     values = dev.to_device(ext_value_estimates, torch.float32, device)
-    steps = values.shape[0] - 1
     adv, ret, stats = _returns._gae_launch(ext_rewards, values[:steps], values[steps], terminals, gamma,
                                            lambda_policy, lambda_value, True, True, True)
     local = stats.clone()
@@ -127,6 +149,7 @@ def calculate_returns(ext_rewards, ext_value_estimates, terminals, gamma, lambda
                                float(advantage_clipping) if advantage_clipping is not None else 0.0,
                                dev.ptr(norm), dev.stream_ptr())
     _lib.check(rc, "ppo_adv_normalize")
+
     def deliver(name, tensor):
         if out is not None and name in out:
             out[name].copy_(tensor.view(out[name].shape), non_blocking=True)
@@ -141,21 +164,13 @@ def calculate_returns(ext_rewards, ext_value_estimates, terminals, gamma, lambda
         "local_stats": local,
     }
     if tvf is not None:
-        kw = dict(tvf)
-        vs = kw.pop("value_samples")
-        hz = kw.pop("horizons")
-        g = kw.pop("gamma")
-        mode = kw.pop("mode", "advanced")
-        distribution = kw.pop("distribution", "exponential")
-        samples = _rt.draw_n_step_samples(distribution, mode, np.asarray(hz), steps, kw.pop("n_step", 40),
-                                          kw.pop("max_samples", 40), kw.pop("seed", None))
-        if distribution != "fixed" and mode == "full":
-            raise ValueError("calculate_returns: use returns_truncated.get_return_estimate for mode='full'")
-        targets, tstats = _rt._launch(g, ext_rewards, terminals, hz, hz, vs, samples,
-                                      kw.pop("use_log_interpolation", False), with_stats=True,
-                                      keep_on_device=out is not None and "tvf_returns" in out)
+        if tvf_join is not None:
+            tstats = tvf_join()
+            result["tvf_returns"] = out["tvf_returns"]
+        else:
+            targets, tstats = tvf_launch()
+            result["tvf_returns"] = deliver("tvf_returns", targets) if to_host else targets
         allreduce_stats(tstats, group)
-        result["tvf_returns"] = deliver("tvf_returns", targets) if out is not None and "tvf_returns" in out else targets
         result["tvf_stats"] = tstats
     if out is not None:
         torch.cuda.current_stream().synchronize()

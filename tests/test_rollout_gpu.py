@@ -107,3 +107,29 @@ def test_env_sharding_is_exact_on_one_gpu():
     norm = [rollout.normalize_advantages(p["advantage"], stats=merged) for p in parts]
     got = np.concatenate([n.reshape(steps, -1) for n in norm], axis=1).reshape(-1)
     assert rel_err(got, full["advantages"]) <= 1e-6
+
+
+@pytest.mark.parametrize("steps,envs,heads,block", [(96, 700, 64, 148), (64, 90, 32, 40), (40, 10, 32, None)])
+def test_host_blocks_pipeline_equals_one_launch(steps, envs, heads, block):
+    """Pinned host buffers: env blocks uploaded / computed / downloaded on three streams give exactly the targets
+    and statistics of one whole-buffer launch (ragged last block included)."""
+    hz = oracle.get_value_head_horizons(heads, 3000)
+    r, d, _ = synthetic.rollout(steps, envs, seed=5)
+    vs = torch.from_numpy(synthetic.value_samples(steps, envs, len(hz), seed=6)).pin_memory()
+    table = oracle.draw_n_step_samples("exponential", "advanced", hz, steps, 12, 6, seed=3)
+    out = torch.empty((steps, envs, len(hz)), dtype=torch.float32).pin_memory()
+    assert rt.host_pipeline_ok(vs, out)
+    stats = rt._launch_host_blocks(0.9999, r, d, hz, hz, vs, table, False, out, block_envs=block)
+    torch.cuda.current_stream().synchronize()
+    whole, wstats = rt._launch(0.9999, r, d, hz, hz, vs.numpy(), table, False, with_stats=True)
+    assert np.array_equal(out.numpy(), whole)
+    s, w = stats.cpu().numpy(), wstats.cpu().numpy()
+    assert s[0] == w[0] and s[3] == w[3] and s[4] == w[4]
+    np.testing.assert_allclose(s[1:3], w[1:3], rtol=1e-12)
+    ref = oracle.sampled_return_multi(0.9999, r, d, hz, hz, vs.numpy(), n_step_samples=table)
+    assert rel_err(out.numpy(), ref) <= TOL
+    # a second call re-uses the cached scratch while the first results are still being read: must stay correct
+    out2 = torch.empty_like(out).pin_memory()
+    rt._launch_host_blocks(0.9999, r, d, hz, hz, vs, table, False, out2, block_envs=block, with_stats=False)
+    torch.cuda.current_stream().synchronize()
+    assert torch.equal(out, out2)
