@@ -19,6 +19,8 @@
 // the reference's operation order and explicit (non-fused) roundings, so outputs differ from the
 // reference only through the re-associated carry-in of a chunk (a few float64 ulps before the
 // float32 rounding).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ppo {
@@ -54,6 +56,17 @@ struct GaeParams {
 struct ThreadStats {
     double n = 0, s_adv = 0, q_adv = 0, s_ret = 0, q_ret = 0;
     float mn_adv = INFINITY, mx_adv = -INFINITY, mn_ret = INFINITY, mx_ret = -INFINITY;
+    // sums, squares and extrema only: the caller sets `n` from the element count it owns
+    __device__ __forceinline__ void add_no_count(float a, float r) {
+        s_adv += a;
+        q_adv += static_cast<double>(a) * a;
+        s_ret += r;
+        q_ret += static_cast<double>(r) * r;
+        mn_adv = fminf(mn_adv, a);
+        mx_adv = fmaxf(mx_adv, a);
+        mn_ret = fminf(mn_ret, r);
+        mx_ret = fmaxf(mx_ret, r);
+    }
     __device__ __forceinline__ void add(float a, float r) {
         n += 1.0;
         s_adv += a;
@@ -113,27 +126,41 @@ __device__ void publish_stats(const ThreadStats& ts, const ScanStatsIo& io, doub
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    // Last CTA: fold all CTA records.  Warp j handles slot j; lanes stride over the CTAs and are
-    // combined by a fixed shuffle tree, so the result does not depend on scheduling.
-    if (w < PPO_STATS_LEN) {
-        const int j = w;
+    // Last CTA: fold all CTA records.  The records are [grid][16] doubles, so consecutive threads read consecutive
+    // words: thread t owns slot t % 16 of records t / 16, t / 16 + groups, ... (loads issued 32 at a time), and
+    // the per-group partials are combined in group order.  Fixed order everywhere: the result does not depend on
+    // scheduling.
+    {
+        const int j = threadIdx.x & (PPO_STATS_LEN - 1);
+        const int g = threadIdx.x / PPO_STATS_LEN, groups = blockDim.x / PPO_STATS_LEN;
         const bool is_min = (j == PPO_STAT_ADV_MIN || j == PPO_STAT_RET_MIN);
         const bool is_max = (j == PPO_STAT_ADV_MAX || j == PPO_STAT_RET_MAX);
         double acc = is_min ? INFINITY : is_max ? -INFINITY : 0.0;
-        if (j <= PPO_STAT_RET_MAX) {
-            for (unsigned int b = lane; b < gridDim.x; b += 32) {
-                const double x = __ldcg(io.partials + static_cast<int64_t>(b) * PPO_STATS_LEN + j);
-                acc = is_min ? fmin(acc, x) : is_max ? fmax(acc, x) : acc + x;
+        const unsigned int G = gridDim.x;
+        constexpr int kFoldBatch = 32;  // loads in flight per thread: the fold is a latency chain at the very end
+        for (unsigned int b0 = g; b0 < G; b0 += kFoldBatch * groups) {
+            double x[kFoldBatch];
+#pragma unroll
+            for (int u = 0; u < kFoldBatch; ++u) {
+                const unsigned int b = b0 + u * groups;
+                x[u] = b < G ? __ldcg(io.partials + static_cast<int64_t>(b) * PPO_STATS_LEN + j)
+                             : (is_min ? INFINITY : is_max ? -INFINITY : 0.0);
             }
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                const double x = shfl_down_f64(acc, d);
-                acc = is_min ? fmin(acc, x) : is_max ? fmax(acc, x) : acc + x;
-            }
-        } else {
-            acc = 0.0;
+            for (int u = 0; u < kFoldBatch; ++u) acc = is_min ? fmin(acc, x[u]) : is_max ? fmax(acc, x[u]) : acc + x[u];
         }
-        if (lane == 0) io.stats[j] = acc;
+        __syncthreads();  // every warp has passed its use of `red` above
+        double* fold = &red[0][0];  // [groups][16], groups <= nwarps * 2
+        fold[g * PPO_STATS_LEN + j] = acc;
+        __syncthreads();
+        if (threadIdx.x < PPO_STATS_LEN) {
+            double tot = fold[j];
+            for (int i = 1; i < groups; ++i) {
+                const double x = fold[i * PPO_STATS_LEN + j];
+                tot = is_min ? fmin(tot, x) : is_max ? fmax(tot, x) : tot + x;
+            }
+            io.stats[j] = j <= PPO_STAT_RET_MAX ? tot : 0.0;
+        }
     }
     if (threadIdx.x == 0) *io.ticket = 0u;
 }
@@ -142,7 +169,7 @@ template <int DONE, bool CACHED, bool STATS>
 __global__ void __launch_bounds__(kScanThreads) gae_kernel(const GaeParams p) {
     __shared__ double sB[2][kScanWarps][32];
     __shared__ double sC[2][kScanWarps][32];
-    __shared__ double red[kScanWarps][PPO_STATS_LEN];
+    __shared__ double red[2 * kScanWarps][PPO_STATS_LEN];  // per-warp records, re-used as [threads / 16][16] by the final fold
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t env = static_cast<int64_t>(blockIdx.x) * 32 + lane;
@@ -254,6 +281,185 @@ __global__ void __launch_bounds__(kScanThreads) gae_kernel(const GaeParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Tile form of the same scan for bandwidth: a CTA stages its whole [N, EW] tile of rewards, values
+// and terminals in shared memory with asynchronous copies (cp.async: no registers, nothing waits
+// until the tile is complete), so several CTAs per SM keep loads in flight while others compute,
+// and the per-thread state is a handful of registers instead of the cached chunk.  EW envs (16 or
+// 32) x kTileChunks time chunks per CTA; the arithmetic is the one of gae_kernel (float64 carries,
+// reference operation order), with the 0/1 terminal mask applied as a select instead of a multiply
+// and the two recurrences merged when lambda_policy == lambda_value.
+constexpr int kTileChunks = 8;
+
+struct GaeTileParams {
+    GaeParams g;
+    int chunk_len;      // rows per time chunk (odd when EW = 16: the two chunks of a warp then hit different banks)
+    int vec_r, vec_v, vec_d;  // bytes per asynchronous copy: 16 / 4, and 1 (synchronous byte loads) for the terminals
+    int same_lambda;
+};
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4b(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+
+template <int DONE, int EW, bool STATS>
+__global__ void __launch_bounds__(EW * kTileChunks) gae_tile_kernel(const GaeTileParams q) {
+    extern __shared__ __align__(16) unsigned char tile[];
+    const GaeParams& p = q.g;
+    constexpr int T = EW * kTileChunks;
+    constexpr int DB = DONE == PPO_DONE_U8 ? 1 : DONE == PPO_DONE_F32 ? 4 : 0;  // bytes per terminal
+    const int N = static_cast<int>(p.steps);
+    float* sr = reinterpret_cast<float*>(tile);                  // [N][EW]
+    float* sv = sr + static_cast<size_t>(N) * EW;                // [N + 1][EW], row N = final estimate
+    unsigned char* sd = reinterpret_cast<unsigned char*>(sv + static_cast<size_t>(N + 1) * EW);  // [N][EW] x DB
+    double* xB = reinterpret_cast<double*>(sd + ((static_cast<size_t>(N) * EW * DB + 15) / 16) * 16);  // [2][chunks][EW]
+    double* xC = xB + 2 * kTileChunks * EW;
+    double (*red)[PPO_STATS_LEN] = reinterpret_cast<double (*)[PPO_STATS_LEN]>(xC + 2 * kTileChunks * EW);
+
+    const int tid = threadIdx.x;
+    const int64_t env0 = static_cast<int64_t>(blockIdx.x) * EW;
+    const uint32_t sr_a = static_cast<uint32_t>(__cvta_generic_to_shared(sr));
+    const uint32_t sv_a = static_cast<uint32_t>(__cvta_generic_to_shared(sv));
+    const uint32_t sd_a = static_cast<uint32_t>(__cvta_generic_to_shared(sd));
+
+    // ---- stage the tile
+    if (q.vec_r == 16) {
+        for (int i = tid; i < N * (EW / 4); i += T) {
+            const int row = i / (EW / 4), seg = i % (EW / 4);
+            if (env0 + seg * 4 < p.envs) cp_async_16(sr_a + (row * EW + seg * 4) * 4, p.rewards + row * p.r_rs + env0 + seg * 4);
+        }
+    } else {
+        for (int i = tid; i < N * EW; i += T) {
+            const int row = i / EW, e = i % EW;
+            if (env0 + e < p.envs) cp_async_4b(sr_a + i * 4, p.rewards + row * p.r_rs + env0 + e);
+        }
+    }
+    if (q.vec_v == 16) {
+        for (int i = tid; i < N * (EW / 4); i += T) {
+            const int row = i / (EW / 4), seg = i % (EW / 4);
+            if (env0 + seg * 4 < p.envs) cp_async_16(sv_a + (row * EW + seg * 4) * 4, p.values + row * p.v_rs + env0 + seg * 4);
+        }
+    } else if (p.v_es == 1) {
+        for (int i = tid; i < N * EW; i += T) {
+            const int row = i / EW, e = i % EW;
+            if (env0 + e < p.envs) cp_async_4b(sv_a + i * 4, p.values + row * p.v_rs + env0 + e);
+        }
+    } else {
+        // strided value column (e.g. the last horizon of a [N+1, A, K] value buffer, rl/tvf.py:325-340): one sector
+        // per element, a latency-bound gather -> plain loads, sixteen in flight per thread
+        constexpr int U = 16;
+        for (int i0 = tid; i0 < N * EW; i0 += T * U) {
+            float x[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * T, row = i / EW, e = i % EW;
+                x[u] = (i < N * EW && env0 + e < p.envs) ? __ldg(p.values + row * p.v_rs + (env0 + e) * p.v_es) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * T;
+                if (i < N * EW) sv[i] = x[u];
+            }
+        }
+    }
+    if (tid < EW && env0 + tid < p.envs) cp_async_4b(sv_a + (N * EW + tid) * 4, p.final_value + (env0 + tid) * p.f_es);
+    if (DONE != PPO_DONE_NONE) {
+        const unsigned char* dn = static_cast<const unsigned char*>(p.dones);
+        constexpr int RB = EW * DB;  // bytes per tile row
+        if (q.vec_d == 16) {
+            for (int i = tid; i < N * (RB / 16); i += T) {
+                const int row = i / (RB / 16), seg = i % (RB / 16);
+                if (env0 * DB + seg * 16 < p.envs * DB)
+                    cp_async_16(sd_a + row * RB + seg * 16, dn + (row * p.d_rs + env0) * DB + seg * 16);
+            }
+        } else if (q.vec_d == 4) {
+            for (int i = tid; i < N * (RB / 4); i += T) {
+                const int row = i / (RB / 4), seg = i % (RB / 4);
+                if (env0 * DB + seg * 4 < p.envs * DB)
+                    cp_async_4b(sd_a + row * RB + seg * 4, dn + (row * p.d_rs + env0) * DB + seg * 4);
+            }
+        } else {
+            for (int i = tid; i < N * EW; i += T) {
+                const int row = i / EW, e = i % EW;
+                if (env0 + e < p.envs) sd[i] = dn[row * p.d_rs + env0 + e];
+            }
+        }
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    const int e = tid % EW, w = tid / EW;
+    const int64_t env = env0 + e;
+    const bool live = env < p.envs;
+    const int lo = w * q.chunk_len;
+    const int hi = min(N, lo + q.chunk_len);
+    const bool same = q.same_lambda != 0;
+
+    // terminal -> (boot, k_adv, k_ret): 0/1 masks are selects (bit-identical to the reference's multiply by 0.0 / 1.0)
+    auto coeffs = [&](int i, float vn, double& boot, double& ka, double& kr) {
+        const double gv = static_cast<double>(__fmul_rn(p.gamma32, vn));
+        if (DONE == PPO_DONE_U8) {
+            const bool d = sd[i * EW + e] != 0;
+            boot = d ? 0.0 : gv, ka = d ? 0.0 : p.gl_adv, kr = d ? 0.0 : p.gl_ret;
+        } else if (DONE == PPO_DONE_F32) {
+            const double nt = static_cast<double>(1.0f - reinterpret_cast<const float*>(sd)[i * EW + e]);
+            boot = gv * nt, ka = __dmul_rn(p.gl_adv, nt), kr = __dmul_rn(p.gl_ret, nt);
+        } else {
+            boot = gv, ka = p.gl_adv, kr = p.gl_ret;
+        }
+    };
+
+    // ---- phase 1: compose the chunk into x_lo = B + C * x_in
+    double b_adv = 0, c_adv = 1, b_ret = 0, c_ret = 1;
+    if (live) {
+        for (int i = hi - 1; i >= lo; --i) {
+            double boot, ka, kr;
+            coeffs(i, sv[(i + 1) * EW + e], boot, ka, kr);
+            const double delta = __dsub_rn(__dadd_rn(static_cast<double>(sr[i * EW + e]), boot),
+                                           static_cast<double>(sv[i * EW + e]));
+            b_adv = __dadd_rn(delta, __dmul_rn(ka, b_adv));
+            c_adv *= ka;
+            if (!same) {
+                b_ret = __dadd_rn(delta, __dmul_rn(kr, b_ret));
+                c_ret *= kr;
+            }
+        }
+    }
+    xB[w * EW + e] = b_adv, xC[w * EW + e] = c_adv;
+    if (!same) xB[(kTileChunks + w) * EW + e] = b_ret, xC[(kTileChunks + w) * EW + e] = c_ret;
+    __syncthreads();
+
+    // ---- phase 2: carry-in = later chunks applied to A_N = 0
+    double x_adv = 0, x_ret = 0;
+    for (int j = kTileChunks - 1; j > w; --j) {
+        x_adv = xB[j * EW + e] + xC[j * EW + e] * x_adv;
+        if (!same) x_ret = xB[(kTileChunks + j) * EW + e] + xC[(kTileChunks + j) * EW + e] * x_ret;
+    }
+
+    // ---- phase 3: replay and stream the outputs
+    ThreadStats ts;
+    if (live) {
+        for (int i = hi - 1; i >= lo; --i) {
+            double boot, ka, kr;
+            const float vv = sv[i * EW + e];
+            coeffs(i, sv[(i + 1) * EW + e], boot, ka, kr);
+            const double delta = __dsub_rn(__dadd_rn(static_cast<double>(sr[i * EW + e]), boot), static_cast<double>(vv));
+            x_adv = __dadd_rn(delta, __dmul_rn(ka, x_adv));
+            if (!same) x_ret = __dadd_rn(delta, __dmul_rn(kr, x_ret));
+            const float a = static_cast<float>(x_adv);
+            const float t = __fadd_rn(same ? a : static_cast<float>(x_ret), vv);  // rl/returns.py:66-67
+            if (p.adv) store_stream(p.adv + static_cast<int64_t>(i) * p.envs + env, a);
+            if (p.ret) store_stream(p.ret + static_cast<int64_t>(i) * p.envs + env, t);
+            if (STATS) ts.add_no_count(a, t);
+        }
+        ts.n = hi > lo ? static_cast<double>(hi - lo) : 0.0;
+    }
+    if (STATS) publish_stats(ts, p.io, red);
+}
+
+// ------------------------------------------------------------------------------------------
 // Bootstrapped discounted returns (rl/returns.py:32-55): R_t = r_t + (R_{t+1} * g_t) * (1 - done_t).
 struct ReturnsParams {
     const float* rewards;
@@ -337,7 +543,7 @@ struct MomentsParams {
 };
 
 __global__ void __launch_bounds__(512) moments_kernel(const MomentsParams p) {
-    __shared__ double red[16][PPO_STATS_LEN];
+    __shared__ double red[32][PPO_STATS_LEN];
     ThreadStats ts;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.count; i += stride) {
@@ -402,6 +608,78 @@ static int split_workspace(void* workspace, int64_t bytes, int64_t blocks, ScanS
 
 constexpr int kMomentsMaxBlocks = 1184;  // 8 CTAs of 512 threads per SM would not fit; 148 * 8 is the cap we size for
 
+template <int DONE, int EW>
+static int launch_gae_tile_variant(const GaeTileParams& q, bool stats, int64_t grid, size_t smem, cudaStream_t s) {
+    if (stats) {
+        PPO_CUDA(cudaFuncSetAttribute(gae_tile_kernel<DONE, EW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+        gae_tile_kernel<DONE, EW, true><<<static_cast<unsigned>(grid), EW * kTileChunks, smem, s>>>(q);
+    } else {
+        PPO_CUDA(cudaFuncSetAttribute(gae_tile_kernel<DONE, EW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+        gae_tile_kernel<DONE, EW, false><<<static_cast<unsigned>(grid), EW * kTileChunks, smem, s>>>(q);
+    }
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+// The tile kernel when a whole [N, EW] tile fits in shared memory; PPO_ERR_UNSUPPORTED otherwise (the caller then
+// launches gae_kernel).  `p.io.stats` must already be set when statistics are wanted.
+static int launch_gae_tile(GaeParams p, int done_kind, bool want_stats, void* workspace, int64_t workspace_bytes,
+                           cudaStream_t s) {
+    const int64_t N = p.steps, A = p.envs;
+    if (N > 4096) return PPO_ERR_UNSUPPORTED;
+    // A strided value column (one DRAM sector per element) is a latency-bound gather; the register-cached kernel
+    // keeps more of those loads in flight and measures faster (30 vs 37 us at 256 x 4096).
+    if (p.v_es != 1) return PPO_ERR_UNSUPPORTED;
+    {
+        const char* sw = getenv("PPO_GAE_TILE");  // development switch: 0 = always the register-cached kernel
+        if (sw && atoi(sw) == 0) return PPO_ERR_UNSUPPORTED;
+    }
+    // few envs: 16 per CTA so that the grid still covers the SMs
+    int ew = (A + 31) / 32 < 2 * static_cast<int64_t>(sm_count()) ? 16 : 32;
+    {
+        const char* sw = getenv("PPO_GAE_EW");  // development switch
+        if (sw && (atoi(sw) == 16 || atoi(sw) == 32)) ew = atoi(sw);
+    }
+    const int db = done_kind == PPO_DONE_U8 ? 1 : done_kind == PPO_DONE_F32 ? 4 : 0;
+    const size_t smem = static_cast<size_t>(N) * ew * 4 + static_cast<size_t>(N + 1) * ew * 4 +
+                        (static_cast<size_t>(N) * ew * db + 15) / 16 * 16 +
+                        static_cast<size_t>(4) * kTileChunks * ew * sizeof(double) +
+                        static_cast<size_t>(ew * kTileChunks / 16) * PPO_STATS_LEN * sizeof(double);
+    int dev = 0, max_smem = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+        return PPO_ERR_UNSUPPORTED;
+    if (smem > static_cast<size_t>(max_smem) / 2) return PPO_ERR_UNSUPPORTED;  // keep at least two CTAs per SM
+    const int64_t grid = (A + ew - 1) / ew;
+    if (want_stats) {
+        if (split_workspace(workspace, workspace_bytes, grid, &p.io) != PPO_OK) return PPO_ERR_UNSUPPORTED;
+    }
+    GaeTileParams q{};
+    q.g = p;
+    q.chunk_len = static_cast<int>((N + kTileChunks - 1) / kTileChunks);
+    if (ew == 16) q.chunk_len |= 1;
+    auto aligned16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
+    q.vec_r = (aligned16(p.rewards) && p.r_rs % 4 == 0 && A % 4 == 0) ? 16 : 4;
+    q.vec_v = (p.v_es == 1 && aligned16(p.values) && p.v_rs % 4 == 0 && A % 4 == 0) ? 16 : 4;
+    q.vec_d = 1;
+    if (db) {
+        const int64_t row_bytes = p.d_rs * db, a_bytes = A * db;
+        if (aligned16(p.dones) && row_bytes % 16 == 0 && a_bytes % 16 == 0) q.vec_d = 16;
+        else if ((reinterpret_cast<uintptr_t>(p.dones) & 3) == 0 && row_bytes % 4 == 0 && a_bytes % 4 == 0) q.vec_d = 4;
+        else if (db == 4) q.vec_d = 4;
+    }
+    q.same_lambda = p.gl_adv == p.gl_ret ? 1 : 0;
+#define PPO_TILE(D)                                                                    \
+    (ew == 16 ? launch_gae_tile_variant<D, 16>(q, want_stats, grid, smem, s)           \
+              : launch_gae_tile_variant<D, 32>(q, want_stats, grid, smem, s))
+    if (done_kind == PPO_DONE_U8) return PPO_TILE(PPO_DONE_U8);
+    if (done_kind == PPO_DONE_F32) return PPO_TILE(PPO_DONE_F32);
+    return PPO_TILE(PPO_DONE_NONE);
+#undef PPO_TILE
+}
+
 }  // namespace ppo
 
 using namespace ppo;
@@ -446,9 +724,10 @@ extern "C" int ppo_gae(const float* rewards, int64_t reward_row_stride, const fl
         if (rc != PPO_OK) return rc;
         p.io.stats = stats;
     }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (launch_gae_tile(p, done_kind, want_stats, workspace, workspace_bytes, s) == PPO_OK) return PPO_OK;
     const bool cached = p.chunk_len <= kCachedLen;
     dim3 grid(static_cast<unsigned>(blocks)), block(kScanThreads);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
 
 #define PPO_LAUNCH_GAE(D)                                                           \
     do {                                                                            \
