@@ -192,6 +192,110 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def other_configs(device, peak_gbs, iters=40):
+    """Kernel-level figures of the other BASELINE.json configurations (parity-test cases, not bench lines):
+    back-to-back launches through the C ABI on rotating buffer sets larger than L2, device time per launch from
+    CUDA events, algorithmic bytes as in DESIGN.md."""
+    import ctypes
+    import torch
+    from ppo_b200 import _lib
+    from ppo_b200 import returns_truncated as rt
+    from ppo_b200 import tvf as tvf_mod
+    lib = _lib.load()
+    stream = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device=device)
+    g.manual_seed(123)
+
+    def timed(launch, nbytes, units):
+        for i in range(6):
+            launch(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            launch(i)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / iters
+        return {"us_per_launch": us, "targets_per_s": units / (us * 1e-6), "achieved_gbs": nbytes / us / 1e3,
+                "frac_of_hbm_peak": nbytes / us / 1e3 / peak_gbs, "algorithmic_bytes": nbytes}
+
+    out = {}
+    # ---- c2: GAE + TD(lambda) + statistics, then advantage normalisation, 256 x 4096, contiguous values
+    n, a, sets = 256, 4096, 8
+    bufs = []
+    for _ in range(sets):
+        r = torch.randint(-1, 3, (n, a), device=device, generator=g).float()
+        d = (torch.rand((n, a), device=device, generator=g) < 3 / 101).view(torch.uint8)
+        v = torch.randn((n + 1, a), device=device, generator=g) * 0.4 + 0.1
+        bufs.append((r, d, v, torch.empty((n, a), device=device), torch.empty((n, a), device=device),
+                     torch.empty(n * a, device=device)))
+    st = torch.zeros(_lib.STATS_LEN, dtype=torch.float64, device=device)
+    ws = torch.zeros(int(lib.ppo_gae_workspace_bytes(a)), dtype=torch.uint8, device=device)
+
+    def c2(i):
+        r, d, v, adv, ret, norm = bufs[i % sets]
+        _lib.check(lib.ppo_gae(r.data_ptr(), a, v.data_ptr(), a, 1, v[n].data_ptr(), 1, d.data_ptr(), _lib.DONE_U8, a,
+                               n, a, GAMMA, LAMBDA_POLICY, LAMBDA_VALUE, adv.data_ptr(), ret.data_ptr(),
+                               st.data_ptr(), ws.data_ptr(), ws.numel(), stream), "ppo_gae")
+        _lib.check(lib.ppo_adv_normalize(adv.data_ptr(), n * a, st.data_ptr(), 1e-8, 0.0, norm.data_ptr(), stream),
+                   "ppo_adv_normalize")
+    out["c2_gae_tdlambda_stats_advnorm_256x4096"] = dict(
+        timed(c2, n * a * 21, n * a), note="two launches; 21 B per (t, env): r 4 + V 4 + done 1 in, raw adv 4 + "
+        "TD(lambda) return 4 + normalised adv 4 out; launch latency is a large part of the time at 22 MB")
+    del bufs
+
+    # ---- c3: TVF targets 128 steps x 1024 envs x 128 horizons, exponential / advanced 8 samples and fixed n-step
+    n, a, k = 128, 1024, HORIZONS
+    hz = tvf_mod.get_value_head_horizons(k, MAX_HORIZON)
+    sets = 6
+    bufs = []
+    for _ in range(sets):
+        r = torch.randint(-1, 3, (n, a), device=device, generator=g).float()
+        d = (torch.rand((n, a), device=device, generator=g) < 3 / 101).view(torch.uint8)
+        vs = torch.randn((n + 1, a, k), device=device, generator=g) * 0.4 + 0.1
+        bufs.append((r, d, vs, torch.empty((n, a, k), device=device)))
+    nbytes = 4 * (n + 1) * a * k + 4 * n * a * k + 5 * n * a
+    for name, table in (("exponential_advanced_8", rt.draw_n_step_samples("exponential", "advanced", hz, n, N_STEP,
+                                                                            SAMPLES, seed=SAMPLE_SEED)),
+                        ("fixed_n_step_20", rt.draw_n_step_samples("fixed", "advanced", hz, n, N_STEP, SAMPLES))):
+        ctab, keep = rt._upload_tables(rt.build_tables(TVF_GAMMA, n, hz, hz, table), device)
+
+        def c3(i):
+            r, d, vs, tg = bufs[i % sets]
+            _lib.check(lib.ppo_tvf_targets(r.data_ptr(), a, d.data_ptr(), _lib.DONE_U8, a, vs.data_ptr(), a * k, k,
+                                           n, a, k, k, ctypes.byref(ctab), rt.PATH_AUTO, tg.data_ptr(), 0, 0, 0,
+                                           stream), "ppo_tvf_targets")
+        res = timed(c3, nbytes, n * a * k)
+        res["kernel"] = {1: "generic", 2: "ring", 3: "tslab"}.get(lib.ppo_tvf_last_path() & 0xff)
+        out[f"c3_tvf_128x1024x128_{name}"] = res
+        del keep
+    del bufs
+
+    # ---- c4: V-trace 256 steps x 4096 envs x 18 actions (one GPU's worth of the 8-way sharded config is 512 envs)
+    n, b, act, sets = 256, 4096, 18, 4
+    bufs = []
+    for _ in range(sets):
+        beh = torch.log_softmax(torch.randn((n, b, act), device=device, generator=g), dim=-1)
+        tgt = torch.log_softmax(torch.randn((n, b, act), device=device, generator=g), dim=-1)
+        actions = torch.randint(0, act, (n, b), device=device, generator=g)
+        r = torch.randint(-1, 3, (n, b), device=device, generator=g).float()
+        d = (torch.rand((n, b), device=device, generator=g) < 3 / 101).view(torch.uint8)
+        v = torch.randn((n + 1, b), device=device, generator=g) * 0.4 + 0.1
+        bufs.append((beh, tgt, actions, r, d, v, [torch.empty((n, b), device=device) for _ in range(3)]))
+
+    def c4(i):
+        beh, tgt, actions, r, d, v, o = bufs[i % sets]
+        _lib.check(lib.ppo_vtrace(beh.data_ptr(), tgt.data_ptr(), actions.data_ptr(), 8, r.data_ptr(), d.data_ptr(),
+                                  _lib.DONE_U8, v.data_ptr(), v[n].data_ptr(), n, b, act, GAMMA, 1.0,
+                                  o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), stream), "ppo_vtrace")
+    out["c4_vtrace_256x4096x18"] = dict(
+        timed(c4, n * b * 37, n * b), note="37 useful B per (t, env); the action gather touches one 32-byte sector "
+        "per 4-byte log-probability, so DRAM traffic is about 93 B per (t, env)")
+    return out
+
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -270,9 +374,11 @@ def run_ours(args):
     tvf_kw = dict(value_samples=host_in["value_samples"], horizons=hz, gamma=TVF_GAMMA, mode="advanced",
                   distribution="exponential", n_step=N_STEP, max_samples=SAMPLES, seed=SAMPLE_SEED)
 
+    group = dist.group.WORLD if world > 1 else None  # sharded: the all-reduce of the advantage moments is inside
+
     def e2e_step():
         return rollout.calculate_returns(host_in["rewards"], host_in["values"], host_in["dones"], GAMMA,
-                                         LAMBDA_POLICY, LAMBDA_VALUE, tvf=tvf_kw, out=host_out)
+                                         LAMBDA_POLICY, LAMBDA_VALUE, tvf=tvf_kw, group=group, out=host_out)
 
     e2e_steps = max(3, min(args.steps, 20))
     for _ in range(2):
@@ -313,6 +419,7 @@ def run_ours(args):
                 "kernel_share_of_step": tvf_avg_ms / ms_per_step,
                 "units_per_launch": f"{steps} x {envs} x {n_h} targets at 8.06 B/target"}
 
+    other = other_configs(device, peak) if world == 1 and not args.no_other_configs else None
     if rank == 0:
         cpu = cpu_baseline_single() if world == 1 and not args.no_cpu_baseline else None
         line = {
@@ -326,6 +433,8 @@ def run_ours(args):
             "roofline": roofline,
             "tvf_tables": {"entries_per_horizon": int(tabs.n_entries), "nmax": int(tabs.nmax)},
         }
+        if other is not None:
+            line["other_configs"] = other
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -341,6 +450,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~15 s oracle timing (development)")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the kernel-level figures of the other BASELINE configs (clean launch lists under ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

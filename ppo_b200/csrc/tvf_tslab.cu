@@ -58,7 +58,7 @@ struct TsParams {
     TvfParams p;
     double gamma;
     int nc, ns, pitch, nstage, kq, rt_words, tail_pitch, want_stats, n_ent;
-    int dbg;  // development switches (PPO_TVF_DEBUG): 1 no stores, 2 no TMA loads, 4 no transform, 8 no entry loop
+    int dbg;  // development switches (PPO_TVF_DEBUG): 1 no stores, 2 no TMA loads, 4 no transform, 8 no entry loop, 16 no tail term
     int64_t env_base, env_rem;
     uint32_t off_stage, off_ot, off_ent, off_hz, off_rtab, off_lim, off_fr, off_bar, smem_total;
     double* partials;  // [grid][8] per-CTA statistics of the longest horizon (want_stats)
@@ -386,7 +386,9 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                 const int m_min = N - (s * kTsStep + kTsStep - 1);  // smallest m of the step (may be <= 0)
                 const bool end0 = m0 >= 1 && m0 <= nmax && lim0 == m0;  // alive until the rollout ends, window may run off
                 const bool end1 = m1 >= 1 && m1 <= nmax && lim1 == m1;
-                const bool any_end = __any_sync(0xffffffffu, end0 || end1);  // usually false before the last rows
+                // warp votes: the tail work of a 32-row half is skipped when none of its rows is alive to the end
+                const bool any_end0 = __any_sync(0xffffffffu, end0), any_end1 = __any_sync(0xffffffffu, end1);
+                const bool any_end = any_end0 || any_end1;
                 const uint32_t base = wt_a + static_cast<uint32_t>(t0) * 4u;
                 // output tile: [half][32-horizon group][32 rows][128 B], 16-byte chunks swizzled with the row (TMA 128B
                 // swizzle): the 8 lanes of a quarter-warp store to 8 different bank groups
@@ -403,30 +405,30 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                     float tacc0[4] = {0.f, 0.f, 0.f, 0.f}, tacc1[4] = {0.f, 0.f, 0.f, 0.f};
                     const int maxn_q = max(max(static_cast<int>(hz[0].w), static_cast<int>(hz[1].w)),
                                            max(static_cast<int>(hz[2].w), static_cast<int>(hz[3].w)));
-                    if (any_end && m_min < maxn_q) {
+                    if (any_end && m_min < maxn_q && !(q.dbg & 16)) {
                         int idx0[4], idx1[4];
                         float w00[4], w01[4], w10[4], w11[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const int64_t tb = static_cast<int64_t>(quad * 4 + u) * q.tail_pitch;
                             idx0[u] = 0, idx1[u] = 0, w00[u] = 0.f, w01[u] = 0.f, w10[u] = 0.f, w11[u] = 0.f;
-                            if (end0) {
+                            if (any_end0 && end0) {
                                 idx0[u] = __ldg(p.tab.tailT_idx + tb + m0);
                                 w00[u] = __ldg(p.tab.tailT_cwlo + tb + m0), w01[u] = __ldg(p.tab.tailT_cwhi + tb + m0);
                             }
-                            if (end1) {
+                            if (any_end1 && end1) {
                                 idx1[u] = __ldg(p.tab.tailT_idx + tb + m1);
                                 w10[u] = __ldg(p.tab.tailT_cwlo + tb + m1), w11[u] = __ldg(p.tab.tailT_cwhi + tb + m1);
                             }
                         }
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            if (end0) {
+                            if (any_end0 && end0) {
                                 const float v0 = ts_lds(fr_a + static_cast<uint32_t>(idx0[u] & 0xffff) * 4u);
                                 const float v1 = ts_lds(fr_a + static_cast<uint32_t>(idx0[u] >> 16) * 4u);
                                 tacc0[u] = fmaf(v1, w01[u], v0 * w00[u]);
                             }
-                            if (end1) {
+                            if (any_end1 && end1) {
                                 const float v0 = ts_lds(fr_a + static_cast<uint32_t>(idx1[u] & 0xffff) * 4u);
                                 const float v1 = ts_lds(fr_a + static_cast<uint32_t>(idx1[u] >> 16) * 4u);
                                 tacc1[u] = fmaf(v1, w11[u], v0 * w10[u]);
