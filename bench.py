@@ -5,12 +5,13 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-One "step" is one full pass of the return stage over one synthetic rollout of
-256 steps x 4096 envs x 128 horizons PER GPU (weak scaling; 8 GPUs = BASELINE config 5, 32768 envs):
-GAE advantages + TD(lambda) returns + their statistics -> all-reduce of {count, sum, sumsq} (N > 1) ->
-advantage normalisation -> 128-horizon TVF targets (exponential / advanced, 8 samples, n_step 20) + statistics
-of the longest horizon.  ``value`` counts steps x envs x horizons TVF targets per second over all ranks
-(the 2 x steps x envs GAE outputs of the same pass are not counted).
+One "step" is one full pass of the return stage (rl/rollout.py:1182-1285 + :1886-1897) over one synthetic rollout
+of 256 steps x 4096 envs x 128 horizons PER GPU (weak scaling; 8 GPUs = BASELINE config 5, 32768 envs), in the
+reference's own data flow: 128-horizon TVF targets (exponential / advanced, 8 samples, n_step 20) + statistics of
+the longest horizon + the value estimate GAE reads, rediscounted from the TVF gamma 0.99997 to gamma 0.999
+(rl/rollout.py:1196 -> rl/tvf.py:303-433) -> GAE advantages + TD(lambda) returns + their statistics -> all-reduce
+of {count, sum, sumsq} (N > 1) -> advantage normalisation.  ``value`` counts steps x envs x horizons TVF targets
+per second over all ranks (the 2 x steps x envs GAE outputs of the same pass are not counted).
 
 Prints ONE JSON line (rank 0).  ``--impl reference`` times the CPU arm: the NumPy oracle (a restatement of
 the reference, pinned to it by tests/golden) on the host cores; nothing else in this file executes ``oracle/``
@@ -40,7 +41,8 @@ UNIT = "targets/s"
 def config(n_gpus):
     return {
         "workload": f"full return pass, {STEPS} steps x {ENVS_PER_GPU} envs x {HORIZONS} horizons per GPU "
-                    f"(total {ENVS_PER_GPU * n_gpus} envs; 8 GPUs = BASELINE config 5)",
+                    f"(total {ENVS_PER_GPU * n_gpus} envs; 8 GPUs = BASELINE config 5): TVF targets + rediscounted "
+                    f"value estimate + GAE / TD(lambda) + advantage normalisation",
         "steps": STEPS, "envs_per_gpu": ENVS_PER_GPU, "envs_total": ENVS_PER_GPU * n_gpus, "horizons": HORIZONS,
         "max_horizon": MAX_HORIZON, "gae": {"gamma": GAMMA, "lambda_policy": LAMBDA_POLICY, "lambda_value": LAMBDA_VALUE},
         "tvf": {"gamma": TVF_GAMMA, "distribution": "exponential", "mode": "advanced", "n_step": N_STEP,
@@ -57,6 +59,9 @@ def config(n_gpus):
 def _oracle_pass(rewards, dones, values, value_samples, horizons):
     """One full pass with the NumPy oracle (reference algorithm)."""
     import oracle
+    n1, envs, k = value_samples.shape
+    values = oracle.get_rediscounted_value_estimate(value_samples.reshape(n1 * envs, k), TVF_GAMMA, GAMMA,
+                                                    horizons).reshape(n1, envs)
     adv = oracle.gae(rewards, values[:-1], values[-1], dones, GAMMA, LAMBDA_POLICY)
     ret = oracle.td_lambda(rewards, values[:-1], values[-1], dones, GAMMA, LAMBDA_VALUE)
     norm = oracle.normalize_advantages(adv)
@@ -325,7 +330,7 @@ def run_ours(args):
     dones = (torch.rand((steps, envs), device=device, generator=g) < 3 / 101).view(torch.uint8)
     value_samples = torch.randn((steps + 1, envs, n_h), device=device, generator=g) * 0.4 + 0.1
     value_samples[:, :, 0] = 0
-    values = value_samples[:, :, -1]  # rl/tvf.py:325-340: the value estimate GAE uses is the longest horizon
+    # the value estimate GAE uses comes off the value curves inside the pass (rl/rollout.py:1196, rl/tvf.py:303-433)
 
     samples = rt.draw_n_step_samples("exponential", "advanced", hz, steps, N_STEP, SAMPLES, seed=SAMPLE_SEED)
     rp = rollout.ReturnPass(steps, envs, hz, GAMMA, TVF_GAMMA, LAMBDA_POLICY, LAMBDA_VALUE)
@@ -338,7 +343,7 @@ def run_ours(args):
 
     # ---- device-resident timing
     for _ in range(args.warmup):
-        rp.run(rewards, values, dones, value_samples)
+        rp.run(rewards, None, dones, value_samples)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -347,7 +352,7 @@ def run_ours(args):
     barrier()
     t_begin.record()
     for i in range(args.steps):
-        rp.run(rewards, values, dones, value_samples, tvf_events=evs[i])
+        rp.run(rewards, None, dones, value_samples, tvf_events=evs[i])
     t_end.record()
     barrier()
     total_ms = t_begin.elapsed_time(t_end)
@@ -362,7 +367,7 @@ def run_ours(args):
 
     # ---- end to end through the public API with pinned host buffers
     host_in = {
-        "rewards": rewards.cpu().pin_memory(), "values": values.contiguous().cpu().pin_memory(),
+        "rewards": rewards.cpu().pin_memory(),
         "dones": dones.view(torch.bool).cpu().pin_memory(), "value_samples": value_samples.cpu().pin_memory(),
     }
     host_out = {
@@ -377,7 +382,7 @@ def run_ours(args):
     group = dist.group.WORLD if world > 1 else None  # sharded: the all-reduce of the advantage moments is inside
 
     def e2e_step():
-        return rollout.calculate_returns(host_in["rewards"], host_in["values"], host_in["dones"], GAMMA,
+        return rollout.calculate_returns(host_in["rewards"], None, host_in["dones"], GAMMA,
                                          LAMBDA_POLICY, LAMBDA_VALUE, tvf=tvf_kw, group=group, out=host_out)
 
     e2e_steps = max(3, min(args.steps, 20))
@@ -401,7 +406,7 @@ def run_ours(args):
     same = bool(torch.equal(host_out["tvf_returns"], rp.tvf_returns.cpu()))
 
     # ---- roofline of the dominant kernel (TVF targets), from CUDA events inside the timed region
-    alg_bytes = 4 * (steps + 1) * envs * n_h + 4 * steps * envs * n_h + 5 * steps * envs
+    alg_bytes = 4 * (steps + 1) * envs * n_h + 4 * steps * envs * n_h + 5 * steps * envs  # + 4 (N+1) A value estimate, not counted
     tvf_avg_ms = sum(tvf_ms) / len(tvf_ms)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -413,7 +418,8 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "tvf_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": f"ppo_tvf_targets, {rp.tvf_kernel} kernel (targets + fused last-horizon statistics)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": f"ppo_tvf_targets_ex, {rp.tvf_kernel} kernel (targets + fused last-horizon "
+                                          f"statistics + fused rediscounted value estimate)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": tvf_avg_ms,
                 "kernel_share_of_step": tvf_avg_ms / ms_per_step,

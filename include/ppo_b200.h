@@ -234,8 +234,41 @@ int ppo_tvf_targets(const float* rewards, int64_t reward_row_stride,
                     const ppo_tvf_tables* tables, int path,
                     float* out, double* stats, void* workspace, int64_t workspace_bytes, void* stream);
 
+/*
+ * ppo_tvf_targets plus the value estimate the GAE stage reads off the same value curves
+ * (rl/rollout.py:1196 -> rl/tvf.py:303-360 `get_tvf_ext_value_estimate`):
+ *     value_out[r, a] = sum_j value_weights[j] * value_samples[r, a, j],   r = 0..N
+ * value_weights is a HOST array of n_val floats: w_0 = -rho_1, w_j = rho_j - rho_{j+1}, w_{V-1} = rho_{V-1} with the
+ * clipped rediscount ratios rho of rl/tvf.py:424-431 gives `get_rediscounted_value_estimate` (rl/tvf.py:388-433);
+ * NULL selects the last value horizon (`tvf_value[:, :, -1]`, rl/tvf.py:325-340).  On the transposed slab kernel the
+ * estimate is produced by the same launch from the value rows it streams anyway; otherwise one more kernel runs.
+ * value_out is [N+1, A] with row stride value_out_row_stride (0 = envs).  extras == NULL: plain ppo_tvf_targets.
+ */
+typedef struct {
+    const float* value_weights;
+    float* value_out;
+    int64_t value_out_row_stride;
+} ppo_tvf_extras;
+
+int ppo_tvf_targets_ex(const float* rewards, int64_t reward_row_stride,
+                       const void* dones, int done_kind, int64_t done_row_stride,
+                       const float* value_samples, int64_t vs_row_stride, int64_t vs_env_stride,
+                       int64_t steps, int64_t envs, int64_t n_req, int64_t n_val,
+                       const ppo_tvf_tables* tables, int path,
+                       float* out, double* stats, void* workspace, int64_t workspace_bytes,
+                       const ppo_tvf_extras* extras, void* stream);
+
+/* Standalone forms.  ppo_value_estimate: out[b] = sum_j host_weights[j] * values[b * row_stride + j] (replaces
+ * rl/tvf.py:388-433 with the weights above).  ppo_rediscount_horizons: out[b, k] = sum_{i=1..k} (V[b,i] - V[b,i-1]) *
+ * host_ratios[i] (replaces rl/tvf.py:362-380 for old_gamma != new_gamma; host_ratios[0] is ignored). */
+int ppo_value_estimate(const float* values, int64_t rows, int64_t row_stride, int64_t n_val,
+                       const float* host_weights, float* out, void* stream);
+int ppo_rediscount_horizons(const float* values, int64_t rows, int64_t row_stride, int64_t n_val,
+                            const float* host_ratios, float* out, int64_t out_row_stride, void* stream);
+
 /* The kernel the last successful ppo_tvf_targets call of this thread launched: a ppo_tvf_path value (never AUTO),
- * plus 0x100 when the statistics of the longest horizon were fused into that launch (no second kernel). */
+ * plus 0x100 when the statistics of the longest horizon were fused into that launch (no second kernel) and 0x200
+ * when the value estimate of ppo_tvf_targets_ex was. */
 int ppo_tvf_last_path(void);
 
 /* count / sum / sumsq / min / max of the longest horizon targets[:, K-1] of a [rows, K] target buffer into the

@@ -18,7 +18,10 @@
 namespace ppo {
 
 int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsigned int* ticket, int64_t max_partials,
-                     cudaStream_t stream, bool* stats_fused);
+                     const float* host_value_weights, float* value_out, int64_t value_row_stride, cudaStream_t stream,
+                     bool* stats_fused);  // tvf_tslab.cu
+int launch_value_dot(const float* v, int64_t rows_t, int64_t envs, int64_t rs_t, int64_t rs_e, int k,
+                     const float* host_weights, float* out, int64_t os_t, cudaStream_t s);  // value_estimate.cu
 int launch_tvf_ring(const TvfParams& p, const float* tail_cwlo, const float* tail_cwhi, cudaStream_t stream,
                     bool probe_only);  // tvf_ring.cu
 
@@ -232,6 +235,20 @@ extern "C" int ppo_tvf_targets(const float* rewards, int64_t reward_row_stride, 
                                int64_t vs_env_stride, int64_t steps, int64_t envs, int64_t n_req, int64_t n_val,
                                const ppo_tvf_tables* tables, int path, float* out, double* stats,
                                void* workspace, int64_t workspace_bytes, void* stream) {
+    return ppo_tvf_targets_ex(rewards, reward_row_stride, dones, done_kind, done_row_stride, value_samples,
+                              vs_row_stride, vs_env_stride, steps, envs, n_req, n_val, tables, path, out, stats,
+                              workspace, workspace_bytes, nullptr, stream);
+}
+
+extern "C" int ppo_tvf_targets_ex(const float* rewards, int64_t reward_row_stride, const void* dones, int done_kind,
+                                  int64_t done_row_stride, const float* value_samples, int64_t vs_row_stride,
+                                  int64_t vs_env_stride, int64_t steps, int64_t envs, int64_t n_req, int64_t n_val,
+                                  const ppo_tvf_tables* tables, int path, float* out, double* stats,
+                                  void* workspace, int64_t workspace_bytes, const ppo_tvf_extras* extras,
+                                  void* stream) {
+    const float* vweights = extras ? extras->value_weights : nullptr;
+    float* vout = extras ? extras->value_out : nullptr;
+    const int64_t vout_rs = extras && extras->value_out_row_stride > 0 ? extras->value_out_row_stride : envs;
     PPO_REQUIRE(steps >= 0 && envs >= 0 && n_req >= 0 && n_val >= 1, "ppo_tvf_targets: bad shape");
     PPO_REQUIRE(steps < (1 << 24) && n_req < (1 << 20) && n_val < (1 << 16), "ppo_tvf_targets: shape too large");
     PPO_REQUIRE(done_kind == PPO_DONE_U8 || done_kind == PPO_DONE_F32 || done_kind == PPO_DONE_NONE,
@@ -271,9 +288,10 @@ extern "C" int ppo_tvf_targets(const float* rewards, int64_t reward_row_stride, 
             ticket = static_cast<unsigned int*>(workspace);
             partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
         }
-        rc = launch_tvf_tslab(p, stats, partials, ticket, kStatsBlocks, s, &stats_fused);
+        rc = launch_tvf_tslab(p, stats, partials, ticket, kStatsBlocks, vweights, vout, vout_rs, s, &stats_fused);
         if (path == PPO_TVF_TSLAB && rc != PPO_OK) return rc;
         taken = PPO_TVF_TSLAB;
+        if (rc == PPO_OK) vout = nullptr;  // the value estimate was written by the same launch
     }
     if (rc == PPO_ERR_UNSUPPORTED && path != PPO_TVF_GENERIC) {
         rc = launch_tvf_ring(p, tables->tail_cwlo, tables->tail_cwhi, s, false);
@@ -282,7 +300,12 @@ extern "C" int ppo_tvf_targets(const float* rewards, int64_t reward_row_stride, 
     }
     if (rc == PPO_ERR_UNSUPPORTED) rc = launch_generic(p, s), taken = PPO_TVF_GENERIC;
     if (rc != PPO_OK) return rc;
-    g_last_path = taken | (stats_fused ? 0x100 : 0);
+    if (vout) {  // not fused: one more pass over the value rows (weighted) or a strided column copy (last horizon)
+        rc = launch_value_dot(value_samples, steps + 1, envs, vs_row_stride, vs_env_stride, static_cast<int>(n_val),
+                              vweights, vout, vout_rs, s);
+        if (rc != PPO_OK) return rc;
+    }
+    g_last_path = taken | (stats_fused ? 0x100 : 0) | (extras && extras->value_out && !vout ? 0x200 : 0);
 
     if (stats && !stats_fused)
         return ppo_tvf_last_horizon_stats(out, steps * envs, n_req, stats, workspace, workspace_bytes, stream);

@@ -61,6 +61,10 @@ struct TsParams {
     int dbg;  // development switches (PPO_TVF_DEBUG): 1 no stores, 2 no TMA loads, 4 no transform, 8 no entry loop, 16 no tail term
     int64_t env_base, env_rem;
     uint32_t off_stage, off_ot, off_ent, off_hz, off_rtab, off_lim, off_fr, off_bar, smem_total;
+    float* value_out;   // [N + 1, A] value estimate sum_j vw[j] * V[r, a, j] (want_value), row stride vo_rs
+    int64_t vo_rs;
+    int want_value;     // 0 none, 1 the last value horizon (no arithmetic), 2 weighted with vw
+    float vw[kTsMaxK];
     double* partials;  // [grid][8] per-CTA statistics of the longest horizon (want_stats)
     unsigned int* ticket;
     double* stats;
@@ -317,8 +321,28 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
         const int xw = warp - kTsConsumers;
         int slot = 0;
         uint32_t spar = 0;
+        // value estimate for the GAE stage off the rows that pass through here anyway (rl/tvf.py:303-360: the last
+        // horizon, or the rediscounted sum over horizons as one dot product per row)
+        float vw[V / 32];
+#pragma unroll
+        for (int cg = 0; cg < V / 32; ++cg) vw[cg] = q.want_value == 2 ? q.vw[cg * 32 + lane] : 0.f;
         for (int e = 0; e < nenv; ++e) {
             const uint32_t par = static_cast<uint32_t>(e & 1);
+            if (q.want_value && xw == 0) {
+                // row 0 is not part of the slab (no target bootstraps from it): straight from global memory
+                const float* row0 = p.vs + (env0 + e) * p.vs_es;
+                float acc = 0.f;
+#pragma unroll
+                for (int cg = 0; cg < V / 32; ++cg) {
+                    const float v = __ldg(row0 + cg * 32 + lane);
+                    acc = q.want_value == 2 ? fmaf(v, vw[cg], acc) : (cg == V / 32 - 1 ? v : 0.f);
+                }
+                if (q.want_value == 2) {
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+                }
+                if (lane == 31) q.value_out[env0 + e] = acc;
+            }
             mbar_wait_sleep(&rfull[par], (static_cast<uint32_t>(e) >> 1) & 1u);
             const uint32_t rt = rt_a + par * rt_bytes;
             for (int c = 0; c < NC; ++c) {
@@ -326,6 +350,9 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                 if (e > 0) mbar_wait_sleep(&bdone[c >> 1], static_cast<uint32_t>(e - 1) & 1u);
                 mbar_wait(&sfull[slot], spar);
                 const uint32_t src = stage_a + static_cast<uint32_t>(slot) * CHUNK + static_cast<uint32_t>(lane) * 4u;
+                float part[kTsRows / kTsXform];  // value-estimate partial sums of this warp's eight rows
+#pragma unroll
+                for (int rl = 0; rl < kTsRows / kTsXform; ++rl) part[rl] = 0.f;
                 if (!(q.dbg & 4))
 #pragma unroll
                 for (int rl = 0; rl < kTsRows / kTsXform; ++rl) {
@@ -341,6 +368,40 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                             ts_sts(wt_a + static_cast<uint32_t>((cg * 32 + lane) * P + i) * 4u, v[cg] - Rr);
                             if (i == N - 1) ts_sts(fr_a + static_cast<uint32_t>(cg * 32 + lane) * 4u, v[cg]);
                         }
+                        if (q.want_value == 2) {
+#pragma unroll
+                            for (int cg = 0; cg < V / 32; ++cg) part[rl] = fmaf(v[cg], vw[cg], part[rl]);
+                        } else if (q.want_value == 1) {
+                            part[rl] = v[V / 32 - 1];  // lane 31 holds the last value horizon
+                        }
+                    }
+                }
+                if (q.want_value == 2) {
+                    // eight row sums at once: each exchange halves the rows a lane still carries (4 + 2 + 1 shuffles),
+                    // two more fold the remaining four lanes -- nine shuffles per chunk instead of forty
+                    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+                    float k4[4], k2[2];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float got = __shfl_xor_sync(0xffffffffu, b4 ? part[j] : part[j + 4], 16);
+                        k4[j] = (b4 ? part[j + 4] : part[j]) + got;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const float got = __shfl_xor_sync(0xffffffffu, b3 ? k4[j] : k4[j + 2], 8);
+                        k2[j] = (b3 ? k4[j + 2] : k4[j]) + got;
+                    }
+                    float k1 = (b2 ? k2[1] : k2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? k2[0] : k2[1], 4);
+                    k1 += __shfl_xor_sync(0xffffffffu, k1, 2);
+                    k1 += __shfl_xor_sync(0xffffffffu, k1, 1);
+                    const int rl = (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0);
+                    const int i = c * kTsRows + xw + rl * kTsXform;
+                    if ((lane & 3) == 0 && i < N) q.value_out[static_cast<int64_t>(i + 1) * q.vo_rs + env0 + e] = k1;
+                } else if (q.want_value == 1 && lane == 31) {
+#pragma unroll
+                    for (int rl = 0; rl < kTsRows / kTsXform; ++rl) {
+                        const int i = c * kTsRows + xw + rl * kTsXform;
+                        if (i < N) q.value_out[static_cast<int64_t>(i + 1) * q.vo_rs + env0 + e] = part[rl];
                     }
                 }
                 if (xw == 0) {  // the -R column (index V); column V + 1 stays zero
@@ -551,7 +612,8 @@ static int ts_launch_variant(const TsParams& q, const CUtensorMap& vmap, const C
 
 // stats / partials / ticket: optional fused statistics of the longest horizon (workspace layout of tvf.cu).
 int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsigned int* ticket, int64_t max_partials,
-                     cudaStream_t stream, bool* stats_fused) {
+                     const float* host_value_weights, float* value_out, int64_t value_row_stride, cudaStream_t stream,
+                     bool* stats_fused) {
     *stats_fused = false;
     const int N = p.steps, K = p.n_req, V = p.n_val, nmax = p.tab.nmax, E = p.tab.n_entries;
     auto unsupported = [&](const char* why) {
@@ -678,6 +740,10 @@ int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsign
     if (grid > p.envs) grid = p.envs;
     q.env_base = p.envs / grid;
     q.env_rem = p.envs % grid;
+    q.want_value = value_out ? (host_value_weights ? 2 : 1) : 0;
+    q.value_out = value_out, q.vo_rs = value_row_stride;
+    if (host_value_weights)
+        for (int j = 0; j < V; ++j) q.vw[j] = host_value_weights[j];
     q.want_stats = (stats && partials && ticket && grid <= max_partials) ? 1 : 0;
     q.stats = stats, q.partials = partials, q.ticket = ticket;
 

@@ -1,0 +1,138 @@
+// Value estimates read off the truncated value curves: rediscounting to another gamma.
+//
+// Replaces rl/tvf.py:388-433 `get_rediscounted_value_estimate` and rl/tvf.py:362-380 `rediscount_horizons`:
+//     est[b]    = sum_{i=1..K-1} (V[b,i] - V[b,i-1]) * rho_i,   rho_i = min((g_new / g_old)^mid_i, clip)
+//     pref[b,k] = sum_{i=1..k}   (V[b,i] - V[b,i-1]) * rho_i
+// The ratios are host floats (Python computes them exactly like the reference, float64 then float32).  `est` is
+// evaluated as one dot product per row with w_0 = -rho_1, w_i = rho_i - rho_{i+1}, w_{K-1} = rho_{K-1} (the same sum
+// re-associated; float32 accumulation like the reference's torch float32 tensors) so that it can also ride on the
+// value rows the TVF target kernel already streams (ppo_tvf_targets_ex); this file is the standalone form.
+// Both kernels are one warp per row, coalesced 128-byte row segments, HBM-bound: 4 K + 4 bytes per row.
+#include "common.cuh"
+
+namespace ppo {
+
+constexpr int kMaxValueHorizons = 1024;
+
+struct DotParams {
+    const float* v;   // element (r, a, j) at v[r * rs_t + a * rs_e + j]
+    int64_t rows_t, envs, rs_t, rs_e, os_t;
+    int k;
+    int last_only;    // 1: out = the last column (no arithmetic)
+    float* out;       // (r, a) at out[r * os_t + a]
+    float w[kMaxValueHorizons];
+};
+
+__global__ void __launch_bounds__(256) value_dot_kernel(const __grid_constant__ DotParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t total = p.rows_t * p.envs;
+    if (p.last_only) {
+        const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+        for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+            const int64_t r = i / p.envs, a = i - r * p.envs;
+            p.out[r * p.os_t + a] = __ldcs(p.v + r * p.rs_t + a * p.rs_e + (p.k - 1));
+        }
+        return;
+    }
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t row = warp; row < total; row += nwarps) {
+        const int64_t r = row / p.envs, a = row - r * p.envs;
+        const float* src = p.v + r * p.rs_t + a * p.rs_e;
+        float acc = 0.f;
+        for (int j = lane; j < p.k; j += 32) acc = fmaf(__ldcs(src + j), p.w[j], acc);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if (lane == 0) p.out[r * p.os_t + a] = acc;
+    }
+}
+
+struct PrefixParams {
+    const float* v;
+    int64_t rows, rs, os;
+    int k;
+    float* out;
+    float rho[kMaxValueHorizons];  // rho[0] unused
+};
+
+// lane l owns columns [l * seg, (l + 1) * seg): local running sum, exclusive warp scan of the segment totals
+__global__ void __launch_bounds__(256) value_prefix_kernel(const __grid_constant__ PrefixParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    const int seg = (p.k + 31) / 32;
+    for (int64_t row = warp; row < p.rows; row += nwarps) {
+        const float* src = p.v + row * p.rs;
+        float* dst = p.out + row * p.os;
+        const int lo = lane * seg, hi = min(p.k, lo + seg);
+        float total = 0.f;
+        for (int j = lo; j < hi; ++j)
+            if (j >= 1) total += __fmul_rn(__fsub_rn(src[j], src[j - 1]), p.rho[j]);
+        float incl = total;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        float run = incl - total;  // sum of the segments before this lane
+        for (int j = lo; j < hi; ++j) {
+            if (j >= 1) run += __fmul_rn(__fsub_rn(src[j], src[j - 1]), p.rho[j]);
+            dst[j] = run;
+        }
+    }
+}
+
+static int64_t warp_grid(int64_t rows) {
+    int64_t blocks = (rows + 7) / 8;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+    return blocks < 1 ? 1 : (blocks > cap ? cap : blocks);
+}
+
+// host_weights == nullptr: the last column
+int launch_value_dot(const float* v, int64_t rows_t, int64_t envs, int64_t rs_t, int64_t rs_e, int k,
+                     const float* host_weights, float* out, int64_t os_t, cudaStream_t s) {
+    if (k > kMaxValueHorizons) {
+        set_error("value estimate: more than %d value horizons", kMaxValueHorizons);
+        return PPO_ERR_UNSUPPORTED;
+    }
+    DotParams p{};
+    p.v = v, p.rows_t = rows_t, p.envs = envs, p.rs_t = rs_t, p.rs_e = rs_e, p.os_t = os_t, p.k = k, p.out = out;
+    p.last_only = host_weights ? 0 : 1;
+    if (host_weights)
+        for (int j = 0; j < k; ++j) p.w[j] = host_weights[j];
+    const int64_t units = p.last_only ? (rows_t * envs + 31) / 32 : rows_t * envs;
+    value_dot_kernel<<<static_cast<unsigned>(warp_grid(units)), 256, 0, s>>>(p);
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+}  // namespace ppo
+
+using namespace ppo;
+
+extern "C" int ppo_value_estimate(const float* values, int64_t rows, int64_t row_stride, int64_t n_val,
+                                  const float* host_weights, float* out, void* stream) {
+    PPO_REQUIRE(rows >= 0 && n_val >= 1 && row_stride >= n_val, "ppo_value_estimate: bad shape");
+    if (rows == 0) return PPO_OK;
+    PPO_REQUIRE(values && host_weights && out, "ppo_value_estimate: null pointer");
+    return launch_value_dot(values, 1, rows, 0, row_stride, static_cast<int>(n_val), host_weights, out, 0,
+                            static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ppo_rediscount_horizons(const float* values, int64_t rows, int64_t row_stride, int64_t n_val,
+                                       const float* host_ratios, float* out, int64_t out_row_stride, void* stream) {
+    PPO_REQUIRE(rows >= 0 && n_val >= 1 && row_stride >= n_val && out_row_stride >= n_val,
+                "ppo_rediscount_horizons: bad shape");
+    if (rows == 0) return PPO_OK;
+    PPO_REQUIRE(values && host_ratios && out, "ppo_rediscount_horizons: null pointer");
+    if (n_val > kMaxValueHorizons) {
+        set_error("ppo_rediscount_horizons: more than %d value horizons", kMaxValueHorizons);
+        return PPO_ERR_UNSUPPORTED;
+    }
+    PrefixParams p{};
+    p.v = values, p.rows = rows, p.rs = row_stride, p.os = out_row_stride, p.k = static_cast<int>(n_val), p.out = out;
+    for (int j = 0; j < p.k; ++j) p.rho[j] = host_ratios[j];
+    value_prefix_kernel<<<static_cast<unsigned>(warp_grid(rows)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}

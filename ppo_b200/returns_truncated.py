@@ -37,6 +37,28 @@ class _CLayout(ctypes.Structure):
                 ("gamma", ctypes.c_double)]
 
 
+class _CExtras(ctypes.Structure):
+    """``ppo_tvf_extras`` of include/ppo_b200.h."""
+    _fields_ = [("value_weights", ctypes.c_void_p), ("value_out", ctypes.c_void_p),
+                ("value_out_row_stride", ctypes.c_int64)]
+
+
+def _extras(value_out, value_weights, env_offset=0):
+    """ctypes extras for ``ppo_tvf_targets_ex`` (or None): ``value_out`` is a device ``[N+1, A]`` float32 tensor that
+    receives the value estimate of the env block starting at ``env_offset``; ``value_weights`` a float32 NumPy
+    vector ``[V]`` (rediscount weights, ``tvf.rediscount_weights``) or None for the last value horizon."""
+    if value_out is None:
+        return None, None
+    x = _CExtras()
+    keep = None
+    if value_weights is not None:
+        keep = np.ascontiguousarray(value_weights, dtype=np.float32)
+        x.value_weights = keep.ctypes.data
+    x.value_out = value_out.data_ptr() + 4 * env_offset
+    x.value_out_row_stride = value_out.stride(0)
+    return x, keep
+
+
 _TABLE_NAMES = ["ent_n", "ent_cnt", "ent_idx", "ent_wlo", "ent_whi", "ent_g", "tail_idx", "tail_wlo", "tail_whi",
                 "tail_cwlo", "tail_cwhi", "gpow", "tailT_idx", "tailT_cwlo", "tailT_cwhi"]
 
@@ -119,7 +141,8 @@ def _upload_tables(tabs, device):
 
 
 def _launch(gamma, rewards, dones, required_horizons, value_sample_horizons, value_samples, n_step_samples,
-            use_log_interpolation, path=PATH_AUTO, with_stats=False, keep_on_device=False, numpy_tables=False):
+            use_log_interpolation, path=PATH_AUTO, with_stats=False, keep_on_device=False, numpy_tables=False,
+            value_out=None, value_weights=None):
     device = dev.require_cuda()
     lib = _lib.load()
     np_like = dev.is_numpy_like(rewards)
@@ -148,13 +171,15 @@ def _launch(gamma, rewards, dones, required_horizons, value_sample_horizons, val
     if with_stats:
         stats = torch.empty(_lib.STATS_LEN, dtype=torch.float64, device=device)
         ws = dev.workspace(lib.ppo_tvf_workspace_bytes(steps, envs), device)
-    rc = lib.ppo_tvf_targets(
+    extras, keep = _extras(value_out, value_weights)
+    rc = lib.ppo_tvf_targets_ex(
         dev.ptr(r), r.stride(0) if steps else 0, dev.ptr(d), kind, d.stride(0) if steps else 0,
         dev.ptr(vs), vs.stride(0), vs.stride(1) if envs else 0, steps, envs, n_req, n_val,
         ctypes.byref(ctab), path, dev.ptr(out), dev.ptr(stats),
-        dev.ptr(ws), ws.numel() if ws is not None else 0, dev.stream_ptr())
+        dev.ptr(ws), ws.numel() if ws is not None else 0, ctypes.byref(extras) if extras is not None else None,
+        dev.stream_ptr())
     _lib.check(rc, "ppo_tvf_targets")
-    del blob  # same-stream allocator reuse is ordered after the kernel
+    del blob, keep  # same-stream allocator reuse is ordered after the kernel
     res = out if keep_on_device else dev.like_input(out, np_like)
     return (res, stats) if with_stats else res
 
@@ -192,7 +217,7 @@ def host_pipeline_ok(value_samples, out):
 
 def _launch_host_blocks(gamma, rewards, dones, required_horizons, value_sample_horizons, value_samples,
                         n_step_samples, use_log_interpolation, out, path=PATH_AUTO, with_stats=True, block_envs=None,
-                        defer_join=False):
+                        defer_join=False, value_out=None, value_weights=None):
     """Targets for rollout buffers that live in pinned HOST memory (``value_samples [N+1, A, V]`` in, ``out
     [N, A, K]`` out): the env axis is cut into blocks, and the upload of block c + 1, the kernels of block c and
     the download of block c - 1 run concurrently on three streams (envs are independent, ``rl/returns_truncated.py``
@@ -256,11 +281,13 @@ def _launch_host_blocks(gamma, rewards, dones, required_horizons, value_sample_h
         s_comp.wait_event(ev_in)
         if c >= 2:
             s_comp.wait_event(ev_out[c - 2])
-        rc = lib.ppo_tvf_targets(
+        extras, keep = _extras(value_out, value_weights, env_offset=lo)
+        rc = lib.ppo_tvf_targets_ex(
             r.data_ptr() + lo * 4, r.stride(0), d.data_ptr() + lo * d.element_size(), kind, d.stride(0),
             vs_d.data_ptr(), ab * n_val, n_val, steps, ab, n_req, n_val, ctypes.byref(ctab), path,
             out_d.data_ptr(), stats[c].data_ptr() if with_stats else 0,
-            dev.ptr(ws), ws.numel() if ws is not None else 0, s_comp.cuda_stream)
+            dev.ptr(ws), ws.numel() if ws is not None else 0,
+            ctypes.byref(extras) if extras is not None else None, s_comp.cuda_stream)
         _lib.check(rc, "ppo_tvf_targets")
         e = torch.cuda.Event()
         e.record(s_comp)
@@ -279,6 +306,8 @@ def _launch_host_blocks(gamma, rewards, dones, required_horizons, value_sample_h
         t_.record_stream(s_comp)
     if stats is not None:
         stats.record_stream(s_comp)
+    if value_out is not None:
+        value_out.record_stream(s_comp)
     del blob
 
     def join():

@@ -102,7 +102,9 @@ def calculate_returns(ext_rewards, ext_value_estimates, terminals, gamma, lambda
                       advantage_epsilon=1e-8, advantage_clipping=None, tvf=None, group=None, out=None):
     """One pass of the return stage (``rl/rollout.py:1182-1285`` + ``:1886-1897``) over this rank's envs.
 
-    ``ext_value_estimates`` is ``[N+1, A]`` (row N is the final estimate, ``rl/rollout.py:1207-1214``).
+    ``ext_value_estimates`` is ``[N+1, A]`` (row N is the final estimate, ``rl/rollout.py:1207-1214``); ``None`` takes
+    it off the value curves in ``tvf`` like ``rl/rollout.py:1196`` does (``get_tvf_ext_value_estimate``, rediscounted
+    when ``gamma`` differs from the TVF gamma), fused into the target launch.
     ``tvf`` (optional) is a dict with ``value_samples [N+1, A, K]``, ``horizons [K]``, ``gamma`` and the
     ``get_return_estimate`` keywords (``mode``, ``distribution``, ``n_step``, ``max_samples``,
     ``use_log_interpolation``, ``seed``), mirroring ``TVFRunnerModule.calculate_tvf_returns``.
@@ -115,8 +117,10 @@ def calculate_returns(ext_rewards, ext_value_estimates, terminals, gamma, lambda
     """
     np_like = dev.is_numpy_like(ext_rewards)
     device = dev.require_cuda()
-    steps = ext_value_estimates.shape[0] - 1
+    steps = ext_rewards.shape[0]
     tvf_join = tvf_launch = None
+    from_curves = ext_value_estimates is None
+    assert not from_curves or tvf is not None, "ext_value_estimates=None needs the value curves in `tvf`"
     if tvf is not None:
         kw = dict(tvf)
         vs = kw.pop("value_samples")
@@ -130,15 +134,31 @@ def calculate_returns(ext_rewards, ext_value_estimates, terminals, gamma, lambda
             raise ValueError("calculate_returns: use returns_truncated.get_return_estimate for mode='full'")
         use_log = kw.pop("use_log_interpolation", False)
         to_host = out is not None and "tvf_returns" in out
+        vkw = {}
+        if from_curves:
+            # rl/rollout.py:1196: the value estimate GAE reads comes off the value curves (rl/tvf.py:303-360): the last
+            # horizon for the TVF gamma, the rediscounted estimate otherwise -- produced by the target launch itself
+            from . import tvf as _tvf
+            values = torch.empty((steps + 1, ext_rewards.shape[1]), dtype=torch.float32, device=device)
+            weights = None if abs(gamma - g) < 1e-8 else _tvf.rediscount_weights(g, gamma, [int(h) for h in hz])
+            vkw = dict(value_out=values, value_weights=weights)
         if to_host and steps > 0 and _rt.host_pipeline_ok(vs, out["tvf_returns"]):
             # rollout buffers in pinned host memory: env blocks are uploaded, computed and downloaded concurrently on
             # side streams, started first so that the transfers overlap the GAE part below
             tvf_join = _rt._launch_host_blocks(g, ext_rewards, terminals, hz, hz, vs, samples, use_log,
-                                               out["tvf_returns"], defer_join=True)
+                                               out["tvf_returns"], defer_join=True, **vkw)
+            if from_curves:  # GAE needs every block's value estimate
+                tstats_early = tvf_join()
+                tvf_join = lambda: tstats_early  # noqa: E731
+        elif from_curves:
+            early = _rt._launch(g, ext_rewards, terminals, hz, hz, vs, samples, use_log, with_stats=True,
+                                keep_on_device=to_host, **vkw)
+            tvf_launch = lambda: early  # noqa: E731
         else:
             tvf_launch = lambda: _rt._launch(g, ext_rewards, terminals, hz, hz, vs, samples, use_log,  # noqa: E731
                                              with_stats=True, keep_on_device=to_host)
-    values = dev.to_device(ext_value_estimates, torch.float32, device)
+    if not from_curves:
+        values = dev.to_device(ext_value_estimates, torch.float32, device)
     adv, ret, stats = _returns._gae_launch(ext_rewards, values[:steps], values[steps], terminals, gamma,
                                            lambda_policy, lambda_value, True, True, True)
     local = stats.clone()
@@ -157,6 +177,7 @@ def calculate_returns(ext_rewards, ext_value_estimates, terminals, gamma, lambda
         return dev.like_input(tensor, np_like)
 
     result = {
+        "value_estimates": values,
         "advantage": deliver("advantage", adv),
         "ext_returns": deliver("ext_returns", ret),
         "advantages": deliver("advantages", norm),
@@ -185,7 +206,8 @@ class ReturnPass:
       1. ``ppo_gae``            advantages (lambda_policy) + TD(lambda) returns (lambda_value) + statistics
       2. all-reduce (sum) of {count, sum, sum of squares} of the raw advantages -- only when sharded
       3. ``ppo_adv_normalize``  normalised (optionally clipped) advantages
-      4. ``ppo_tvf_targets``    [N, A, K] truncated-return targets + statistics of the longest horizon
+      4. ``ppo_tvf_targets_ex`` [N, A, K] truncated-return targets + statistics of the longest horizon
+         (first, and also producing the value estimate GAE reads, when ``run(values=None)``)
 
     ``set_samples`` resolves an n-step sample table (host integers only) and uploads it; the reference
     draws a new table every rollout (``rl/returns_truncated.py:85-129``), so call it per pass when the
@@ -223,6 +245,7 @@ class ReturnPass:
         self._ctab = self._blob = None
         self.kernel_launches_per_pass = 4
         self.tvf_kernel = "?"
+        self.value_estimates = self._value_weights = None
 
     def set_samples(self, n_step_samples):
         tabs = _rt.build_tables(self.tvf_gamma, self.steps, self.horizons, self.horizons, n_step_samples,
@@ -232,11 +255,44 @@ class ReturnPass:
 
     def run(self, rewards, values, dones, value_samples, tvf_events=None):
         """``rewards [N, A] f32``, ``values [N+1, A] f32`` (row N = final estimate; any strides with a
-        unit-stride env axis or a strided view of the value-sample buffer), ``dones [N, A] uint8``,
-        ``value_samples [N+1, A, K] f32`` -- all CUDA tensors of this rank's env block."""
+        unit-stride env axis or a strided view of the value-sample buffer) or ``None``, ``dones [N, A] uint8``,
+        ``value_samples [N+1, A, K] f32`` -- all CUDA tensors of this rank's env block.
+
+        ``values=None`` is the reference's own data flow (``rl/rollout.py:1196``): the estimate GAE reads is taken
+        off the value curves (``rl/tvf.py:303-360``: last horizon for the TVF gamma, rediscounted otherwise).  The
+        target launch then runs first and writes ``self.value_estimates [N+1, A]`` as a by-product of the value rows
+        it streams, and GAE reads that contiguous buffer."""
         assert self._ctab is not None, "call set_samples() first"
         lib, s = self.lib, dev.stream_ptr()
         n, a, k = self.steps, self.envs, self.n_h
+
+        def targets(extras):
+            if tvf_events is not None:  # (start, end) around the target launch(es)
+                tvf_events[0].record()
+            # targets + statistics of the longest horizon (+ value estimate): one launch on the transposed slab
+            # kernel, up to three on the other paths
+            rc = lib.ppo_tvf_targets_ex(
+                rewards.data_ptr(), rewards.stride(0), dones.data_ptr(), _lib.DONE_U8, dones.stride(0),
+                value_samples.data_ptr(), value_samples.stride(0), value_samples.stride(1), n, a, k, k,
+                ctypes.byref(self._ctab), self.tvf_path, self.tvf_returns.data_ptr(), self.tvf_stats.data_ptr(),
+                self.ws_tvf.data_ptr(), self.ws_tvf.numel(), ctypes.byref(extras) if extras is not None else None, s)
+            _lib.check(rc, "ppo_tvf_targets")
+            last = lib.ppo_tvf_last_path()
+            self.tvf_kernel = {1: "generic", 2: "ring", 3: "tslab"}.get(last & 0xff, "?")
+            extra_launches = (0 if last & 0x100 else 1) + (1 if extras is not None and not last & 0x200 else 0)
+            self.kernel_launches_per_pass = 3 + extra_launches
+            if tvf_events is not None:
+                tvf_events[1].record()
+
+        if values is None:
+            if self.value_estimates is None:
+                from . import tvf as _tvf
+                self.value_estimates = torch.empty((n + 1, a), dtype=torch.float32, device=self.device)
+                self._value_weights = None if abs(self.gamma - self.tvf_gamma) < 1e-8 else \
+                    _tvf.rediscount_weights(self.tvf_gamma, self.gamma, [int(h) for h in self.horizons])
+            extras, _keep = _rt._extras(self.value_estimates, self._value_weights)
+            targets(extras)
+            values = self.value_estimates
         rc = lib.ppo_gae(rewards.data_ptr(), rewards.stride(0), values.data_ptr(), values.stride(0), values.stride(1),
                          values[n].data_ptr(), values.stride(1), dones.data_ptr(), _lib.DONE_U8, dones.stride(0),
                          n, a, self.gamma, self.lambda_policy, self.lambda_value,
@@ -248,20 +304,8 @@ class ReturnPass:
         rc = lib.ppo_adv_normalize(self.advantage.data_ptr(), n * a, self.stats.data_ptr(), self.eps, self.clip,
                                    self.advantages.data_ptr(), s)
         _lib.check(rc, "ppo_adv_normalize")
-        if tvf_events is not None:  # (start, end) around the target launch(es)
-            tvf_events[0].record()
-        # targets + statistics of the longest horizon: one launch on the transposed slab kernel (statistics fused),
-        # two on the other paths
-        rc = lib.ppo_tvf_targets(rewards.data_ptr(), rewards.stride(0), dones.data_ptr(), _lib.DONE_U8, dones.stride(0),
-                                 value_samples.data_ptr(), value_samples.stride(0), value_samples.stride(1),
-                                 n, a, k, k, ctypes.byref(self._ctab), self.tvf_path, self.tvf_returns.data_ptr(),
-                                 self.tvf_stats.data_ptr(), self.ws_tvf.data_ptr(), self.ws_tvf.numel(), s)
-        _lib.check(rc, "ppo_tvf_targets")
-        last = lib.ppo_tvf_last_path()
-        self.tvf_kernel = {1: "generic", 2: "ring", 3: "tslab"}.get(last & 0xff, "?")
-        self.kernel_launches_per_pass = 3 if last & 0x100 else 4
-        if tvf_events is not None:
-            tvf_events[1].record()
+        if values is not self.value_estimates:
+            targets(None)
         return self
 
 

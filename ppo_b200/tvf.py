@@ -8,7 +8,10 @@ import math
 import time as clock
 
 import numpy as np
+import torch
 
+from . import _device as dev
+from . import _lib
 from .returns_truncated import get_return_estimate
 
 
@@ -36,6 +39,71 @@ def get_value_head_horizons(n_heads: int, max_horizon: int, spacing: str = "geom
         weights = np.asarray(list(counts.values()), dtype=np.float32)
         return (result, weights) if include_weight else result
     raise ValueError(f"Invalid spacing value {spacing}")
+
+
+def rediscount_ratios(old_gamma, new_gamma, horizons, clipping=10):
+    """Clipped ratios ``rho_i = min((new_gamma / old_gamma)^mid_i, clipping)`` with
+    ``mid_i = (h_{i-1} + 1 + h_i) / 2 - 1`` for i = 1..K-1, as Python floats exactly like ``rl/tvf.py:420-429``;
+    ``rho_0 = 0`` (unused).  Host integers / floats only."""
+    rho = np.zeros(len(horizons), dtype=np.float64)
+    prev_h = 0
+    for i in range(1, len(horizons)):
+        h = horizons[i]
+        mid_h = ((prev_h + 1 + h) / 2) - 1
+        prev_h = h
+        rho[i] = min((new_gamma ** mid_h) / (old_gamma ** mid_h), clipping)
+    return rho
+
+
+def rediscount_weights(old_gamma, new_gamma, horizons, clipping=10):
+    """Per-horizon weights ``w`` with ``sum_i (V_i - V_{i-1}) rho_i == sum_j w_j V_j``: the rediscounted estimate as
+    one dot product per value curve (what ``ppo_value_estimate`` and ``ppo_tvf_targets_ex`` consume).  float32 [K]."""
+    rho = rediscount_ratios(old_gamma, new_gamma, horizons, clipping)
+    w = np.zeros(len(rho), dtype=np.float64)
+    if len(rho) > 1:
+        w[0] = -rho[1]
+        w[1:-1] = rho[1:-1] - rho[2:]
+        w[-1] = rho[-1]
+    return w.astype(np.float32)
+
+
+def get_rediscounted_value_estimate(values, old_gamma: float, new_gamma: float, horizons, clipping=10):
+    """Rediscounted return at the longest horizon, ``[B, K] -> [B]`` float32 (reference: ``rl/tvf.py:388-433``;
+    NumPy in -> NumPy out, tensor in -> tensor out, ``old_gamma == new_gamma`` -> ``values[:, -1]``)."""
+    n_rows, n_h = values.shape
+    if old_gamma == new_gamma:
+        return values[:, -1]
+    assert n_h == len(horizons), f"missmatch {n_h} {horizons}"
+    assert horizons[0] == 0, 'first horizon must be 0'
+    device = dev.require_cuda()
+    lib = _lib.load()
+    np_like = dev.is_numpy_like(values)
+    v = dev.env_contiguous(dev.to_device(values, torch.float32, device))
+    w = rediscount_weights(old_gamma, new_gamma, [int(h) for h in horizons], clipping)
+    out = torch.empty(n_rows, dtype=torch.float32, device=device)
+    rc = lib.ppo_value_estimate(dev.ptr(v), n_rows, v.stride(0) if n_rows else n_h, n_h, w.ctypes.data, dev.ptr(out),
+                                dev.stream_ptr())
+    _lib.check(rc, "ppo_value_estimate")
+    return dev.like_input(out, np_like)
+
+
+def rediscount_horizons(values, old_gamma: float, new_gamma: float, horizons, clipping=10):
+    """Every horizon rediscounted: ``out[:, k]`` is the estimate from the first ``k + 1`` horizons, ``[B, K] ->
+    [B, K]`` (reference: the loop of ``TVFRunnerModule.rediscount_horizons``, ``rl/tvf.py:362-380``)."""
+    if old_gamma == new_gamma:
+        return values
+    n_rows, n_h = values.shape
+    assert n_h == len(horizons) and horizons[0] == 0, 'first horizon must be 0'
+    device = dev.require_cuda()
+    lib = _lib.load()
+    np_like = dev.is_numpy_like(values)
+    v = dev.env_contiguous(dev.to_device(values, torch.float32, device))
+    rho = rediscount_ratios(old_gamma, new_gamma, [int(h) for h in horizons], clipping).astype(np.float32)
+    out = torch.empty((n_rows, n_h), dtype=torch.float32, device=device)
+    rc = lib.ppo_rediscount_horizons(dev.ptr(v), n_rows, v.stride(0) if n_rows else n_h, n_h, rho.ctypes.data,
+                                     dev.ptr(out), n_h, dev.stream_ptr())
+    _lib.check(rc, "ppo_rediscount_horizons")
+    return dev.like_input(out, np_like)
 
 
 class TVFRunnerModule:
@@ -94,9 +162,8 @@ class TVFRunnerModule:
         return returns
 
     def get_tvf_ext_value_estimate(self, new_gamma: float):
-        """``[N+1, A]`` value estimate fed to GAE (reference: ``rl/tvf.py:303-360``).  Same-gamma cases are
-        slices of the value buffers; rediscounting to a different gamma is a "next" row and
-        raises until that kernel lands."""
+        """``[N+1, A]`` value estimate fed to GAE (reference: ``rl/tvf.py:303-360``): slices of the value buffers for
+        the TVF gamma, the rediscounted estimate (``ppo_value_estimate``) for any other gamma."""
         args = self.args
         assert args.tvf.enabled
         head = self.runner.value_heads.index('ext')
@@ -112,7 +179,27 @@ class TVFRunnerModule:
             elif args.tvf.trim_advantages == "untrimmed":
                 return untrimmed[:, :, -1]
             raise ValueError(f"Invalid advantage trimming mode {args.tvf.trim_advantages}.")
-        raise NotImplementedError("rediscounting to a different gamma (rl/tvf.py:355-360) is not built yet")
+        assert args.tvf.trim_advantages != "average", "Average advantage trimming not supported with rediscounting."
+        if args.tvf.trim_advantages == "trimmed":
+            tvf_values = trimmed
+        elif args.tvf.trim_advantages == "untrimmed":
+            tvf_values = untrimmed
+        else:
+            raise ValueError()
+        n1, n_envs, n_h = tvf_values.shape
+        return get_rediscounted_value_estimate(
+            values=tvf_values.reshape([n1 * n_envs, -1]),
+            old_gamma=args.tvf.gamma,
+            new_gamma=new_gamma,
+            horizons=self.runner.tvf_horizons,
+        ).reshape([n1, n_envs])
+
+    def rediscount_horizons(self, old_value_estimates):
+        """``[B, K] -> [B, K]`` (reference: ``rl/tvf.py:362-380``)."""
+        args = self.args
+        if args.tvf.gamma == args.gamma:
+            return old_value_estimates
+        return rediscount_horizons(old_value_estimates, args.tvf.gamma, args.gamma, self.runner.tvf_horizons)
 
     def save(self):
         pass

@@ -1,0 +1,142 @@
+"""GPU parity of the value estimates read off the truncated value curves (rl/tvf.py:303-433): standalone
+rediscounting kernels against the golden vectors and the oracle, and the estimate fused into the target launch."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from ppo_b200 import _lib, rollout, synthetic
+from ppo_b200 import returns_truncated as rt
+from ppo_b200 import tvf
+from util import TOL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def test_rediscount_golden(golden):
+    hz, rv = golden["prod_in_horizons"], golden["redis_in_values"]
+    got = tvf.get_rediscounted_value_estimate(rv, 0.9999, 0.999, hz)
+    assert got.dtype == np.float32 and rel_err(got, golden["redis_down"]) <= TOL
+    assert rel_err(tvf.get_rediscounted_value_estimate(rv, 0.99, 0.9999, hz), golden["redis_up"]) <= TOL
+    assert np.array_equal(tvf.get_rediscounted_value_estimate(rv, 0.99, 0.99, hz), golden["redis_same"])
+    t = tvf.get_rediscounted_value_estimate(torch.from_numpy(rv).cuda(), 0.9999, 0.999, hz)
+    assert isinstance(t, torch.Tensor) and t.is_cuda and rel_err(t.cpu().numpy(), golden["redis_down"]) <= TOL
+    with pytest.raises(AssertionError):  # rl/tvf.py:409 `first horizon must be 0`
+        tvf.get_rediscounted_value_estimate(rv[:, 1:], 0.99, 0.999, hz[1:])
+
+
+@pytest.mark.parametrize("rows,heads,max_h", [(3000, 128, 30000), (17, 16, 200), (1, 8, 50), (0, 8, 50)])
+def test_rediscount_vs_oracle(rows, heads, max_h):
+    hz = oracle.get_value_head_horizons(heads, max_h)
+    rng = np.random.RandomState(rows + heads)
+    v = np.cumsum(np.abs(rng.normal(0, 1, [rows, len(hz)])), axis=1).astype(np.float32)
+    v[:, 0] = 0
+    for old, new in ((0.99997, 0.999), (0.99, 0.9999)):
+        ref = oracle.get_rediscounted_value_estimate(v, old, new, hz)
+        assert rel_err(tvf.get_rediscounted_value_estimate(v, old, new, hz), ref) <= TOL
+        ref = oracle.rediscount_horizons(v, old, new, hz)
+        got = tvf.rediscount_horizons(v, old, new, hz)
+        assert got.shape == ref.shape and rel_err(got, ref) <= TOL
+    assert tvf.rediscount_horizons(v, 0.99, 0.99, hz) is v
+
+
+def test_rediscount_weights_are_the_reference_sum():
+    """sum_i (V_i - V_{i-1}) rho_i == sum_j w_j V_j in exact arithmetic (float64 check of the re-association)."""
+    hz = oracle.get_value_head_horizons(128, 30000)
+    rho = tvf.rediscount_ratios(0.99997, 0.999, [int(h) for h in hz])
+    w = tvf.rediscount_weights(0.99997, 0.999, [int(h) for h in hz]).astype(np.float64)
+    v = np.random.RandomState(0).normal(size=[50, len(hz)])
+    ref = ((v[:, 1:] - v[:, :-1]) * rho[1:]).sum(axis=1)
+    assert np.abs(v @ w - ref).max() <= 1e-6 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("gamma,path", [(0.999, rt.PATH_TSLAB), (0.99997, rt.PATH_TSLAB), (0.999, rt.PATH_RING),
+                                        (0.99997, rt.PATH_GENERIC)])
+def test_value_estimate_fused_into_the_target_launch(gamma, path):
+    """ppo_tvf_targets_ex: targets unchanged, value estimate = rediscounted curve (gamma != tvf gamma) or the last
+    horizon (same gamma); on the transposed slab kernel it comes out of the same launch (flag 0x200)."""
+    steps, envs, tvf_gamma = 96, 210, 0.99997
+    hz = oracle.get_value_head_horizons(128, 30000)
+    r, d, _ = synthetic.rollout(steps, envs, seed=8)
+    vs = synthetic.value_samples(steps, envs, len(hz), seed=9)
+    table = oracle.draw_n_step_samples("exponential", "advanced", hz, steps, 20, 8, seed=2)
+    out = torch.empty((steps + 1, envs), dtype=torch.float32, device="cuda")
+    w = None if gamma == tvf_gamma else tvf.rediscount_weights(tvf_gamma, gamma, [int(h) for h in hz])
+    got = rt._launch(tvf_gamma, r, d, hz, hz, vs, table, False, path=path, value_out=out, value_weights=w)
+    last = _lib.load().ppo_tvf_last_path()
+    assert (last & 0xff) == path and bool(last & 0x200) == (path == rt.PATH_TSLAB)
+    assert rel_err(got, oracle.sampled_return_multi(tvf_gamma, r, d, hz, hz, vs, n_step_samples=table)) <= TOL
+    flat = vs.reshape(-1, len(hz))
+    ref = oracle.get_rediscounted_value_estimate(flat, tvf_gamma, gamma, hz).reshape(steps + 1, envs)
+    if gamma == tvf_gamma:
+        assert np.array_equal(out.cpu().numpy(), vs[:, :, -1])
+    else:
+        assert rel_err(out.cpu().numpy(), ref) <= TOL
+
+
+@pytest.mark.parametrize("gamma", [0.999, 0.99997])
+def test_return_pass_with_values_from_the_curves(gamma):
+    """rl/rollout.py:1196 data flow: GAE reads the (rediscounted) estimate taken off the value curves."""
+    steps, envs, tvf_gamma = 128, 300, 0.99997
+    hz = oracle.get_value_head_horizons(128, 30000)
+    r, d, _ = synthetic.rollout(steps, envs, seed=3)
+    vs = synthetic.value_samples(steps, envs, len(hz), seed=4)
+    table = oracle.draw_n_step_samples("exponential", "advanced", hz, steps, 20, 8, seed=1)
+    rp = rollout.ReturnPass(steps, envs, hz, gamma, tvf_gamma, 0.95, 0.9)
+    rp.set_samples(table)
+    rp.run(torch.from_numpy(r).cuda(), None, torch.from_numpy(d).cuda().view(torch.uint8), torch.from_numpy(vs).cuda())
+    torch.cuda.synchronize()
+    assert rp.tvf_kernel == "tslab" and rp.kernel_launches_per_pass == 3
+    values = oracle.get_rediscounted_value_estimate(vs.reshape(-1, len(hz)), tvf_gamma, gamma, hz).reshape(steps + 1, envs)
+    assert rel_err(rp.value_estimates.cpu().numpy(), values) <= TOL
+    got_v = rp.value_estimates.cpu().numpy()  # GAE parity on the estimate the device actually used
+    assert rel_err(rp.advantage.cpu().numpy(), oracle.gae(r, got_v[:-1], got_v[-1], d, gamma, 0.95)) <= TOL
+    assert rel_err(rp.ext_returns.cpu().numpy(), oracle.td_lambda(r, got_v[:-1], got_v[-1], d, gamma, 0.9)) <= TOL
+    ref = oracle.sampled_return_multi(tvf_gamma, r, d, hz, hz, vs, n_step_samples=table)
+    assert rel_err(rp.tvf_returns.cpu().numpy(), ref) <= TOL
+    # the same through calculate_returns, NumPy buffers and pinned host buffers (env-blocked pipeline)
+    kw = dict(value_samples=vs, horizons=hz, gamma=tvf_gamma, mode="advanced", distribution="exponential", n_step=20,
+              max_samples=8, seed=1)
+    res = rollout.calculate_returns(r, None, d, gamma, 0.95, 0.9, tvf=kw)
+    assert np.array_equal(res["advantage"], rp.advantage.cpu().numpy())
+    assert np.array_equal(res["tvf_returns"], rp.tvf_returns.cpu().numpy())
+    pinned = dict(kw, value_samples=torch.from_numpy(vs).pin_memory())
+    out = {"tvf_returns": torch.empty((steps, envs, len(hz))).pin_memory(), "advantage": torch.empty((steps, envs)).pin_memory()}
+    res2 = rollout.calculate_returns(torch.from_numpy(r).pin_memory(), None, torch.from_numpy(d).pin_memory(), gamma,
+                                     0.95, 0.9, tvf=pinned, out=out)
+    assert torch.equal(out["advantage"], rp.advantage.cpu()) and torch.equal(out["tvf_returns"], rp.tvf_returns.cpu())
+    assert torch.equal(res2["value_estimates"].cpu(), rp.value_estimates.cpu())
+
+
+def test_runner_module_value_estimate_and_returns():
+    """TVFRunnerModule with a stand-in runner: the rediscounted branch of get_tvf_ext_value_estimate
+    (rl/tvf.py:342-360) and calculate_tvf_returns (rl/tvf.py:210-271)."""
+    steps, envs = 24, 12
+    hz = oracle.get_value_head_horizons(32, 1000)
+    r, d, _ = synthetic.rollout(steps, envs, seed=12)
+    log = types.SimpleNamespace(watch_mean=lambda *a, **k: None)
+    runner = types.SimpleNamespace(ext_rewards=r, terminals=d, all_obs=np.zeros([steps + 1, envs, 2], np.float32),
+                                   tvf_horizons=list(hz), value_heads=["ext", "int"], N=steps, log=log)
+    args = types.SimpleNamespace(
+        gamma=0.999, tvf_return_n_step=8,
+        tvf=types.SimpleNamespace(enabled=True, gamma=0.9999, trimming_mode="off", trim_advantages="untrimmed",
+                                  return_mode="advanced", return_distribution="exponential", return_samples=4,
+                                  return_use_log_interpolation=False))
+    mod = tvf.TVFRunnerModule(runner, args)
+    vs = synthetic.value_samples(steps, envs, len(hz), seed=13)
+    mod.tvf_value[..., 0] = vs
+    mod.tvf_untrimmed_value[..., 0] = vs
+    same = mod.get_tvf_ext_value_estimate(0.9999)
+    assert np.array_equal(same, vs[:, :, -1])
+    got = mod.get_tvf_ext_value_estimate(0.999)
+    ref = oracle.get_rediscounted_value_estimate(vs.reshape(-1, len(hz)), 0.9999, 0.999, hz).reshape(steps + 1, envs)
+    assert got.shape == (steps + 1, envs) and rel_err(got, ref) <= TOL
+    np.random.seed(5)
+    targets = mod.calculate_tvf_returns()
+    np.random.seed(5)
+    ref = oracle.get_return_estimate("exponential", "advanced", 0.9999, r, d, hz, hz, vs, n_step=8, max_samples=4)
+    assert targets.shape == (steps, envs, len(hz)) and rel_err(targets, ref) <= TOL
+    assert rel_err(mod.rediscount_horizons(vs.reshape(-1, len(hz))),
+                   oracle.rediscount_horizons(vs.reshape(-1, len(hz)), 0.9999, 0.999, hz)) <= TOL
