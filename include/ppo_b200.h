@@ -194,15 +194,14 @@ typedef struct {
  * weights, float64 arithmetic), :565,:573-574 (log-interpolation axis) and :669 (float32 discount powers).
  * All pointers are HOST pointers; `blob` receives the packed tables (copy it to the device and add its device
  * address to the offsets to fill ppo_tvf_tables).  ppo_tvf_tables_words gives a sufficient blob size.
- * optimise_slots != 0 permutes the entry slots of each horizon to avoid shared-memory bank conflicts in the slab
- * kernel (the set of entries per horizon is unchanged).  Returns PPO_ERR_BAD_ARG when a clamped n-step is outside
+ * Returns PPO_ERR_BAD_ARG when a clamped n-step is outside
  * 1..N (the reference's assert, :597) and PPO_ERR_UNSUPPORTED when a bootstrap horizon lies beyond the last value
  * horizon (the reference's IndexError, :157).
  */
 int64_t ppo_tvf_tables_words(int64_t n_req, int64_t n_samples, int64_t steps);
 int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* required_horizons, int64_t n_req,
                          const int64_t* value_horizons, int64_t n_val, const int64_t* samples, int64_t n_samples,
-                         int use_log_interpolation, int optimise_slots, int32_t* blob, int64_t blob_words,
+                         int use_log_interpolation, int32_t* blob, int64_t blob_words,
                          ppo_tvf_table_layout* layout);
 
 /* which TVF kernel ppo_tvf_targets may use */
@@ -265,6 +264,13 @@ int ppo_value_estimate(const float* values, int64_t rows, int64_t row_stride, in
                        const float* host_weights, float* out, void* stream);
 int ppo_rediscount_horizons(const float* values, int64_t rows, int64_t row_stride, int64_t n_val,
                             const float* host_ratios, float* out, int64_t out_row_stride, void* stream);
+
+/* Per-row interpolation of value curves at per-row target horizons.  Replaces rl/tvf.py:527-573 `horizon_interpolate`
+ * (float64 result like the reference; targets are clipped to the axis, targets at or below the first horizon give 0).
+ * host_horizons: HOST [n_val] strictly ascending axis (any scale, e.g. the log scale of rl/tvf.py:143-152);
+ * values [rows, n_val] float32 and targets / out [rows] float64 are device arrays. */
+int ppo_horizon_interpolate(const double* host_horizons, int64_t n_val, const float* values, int64_t rows,
+                            int64_t row_stride, const double* targets, double* out, void* stream);
 
 /* The kernel the last successful ppo_tvf_targets call of this thread launched: a ppo_tvf_path value (never AUTO),
  * plus 0x100 when the statistics of the longest horizon were fused into that launch (no second kernel) and 0x200

@@ -39,7 +39,7 @@ _SIGNATURES = {
     "ppo_moments": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
     "ppo_tvf_workspace_bytes": (c_i64, [c_i64, c_i64]),
     "ppo_tvf_tables_words": (c_i64, [c_i64, c_i64, c_i64]),
-    "ppo_tvf_tables_build": (c_int, [c_dbl, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_int, c_int,
+    "ppo_tvf_tables_build": (c_int, [c_dbl, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_int,
                                      c_ptr, c_i64, c_ptr]),
     "ppo_tvf_targets": (c_int, [c_ptr, c_i64, c_ptr, c_int, c_i64, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
                                 c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
@@ -47,6 +47,7 @@ _SIGNATURES = {
                                    c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     "ppo_value_estimate": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr]),
     "ppo_rediscount_horizons": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
+    "ppo_horizon_interpolate": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr]),
     "ppo_tvf_last_path": (c_int, []),
     "ppo_tvf_last_horizon_stats": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
     "ppo_memcpy_2d_async": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64, c_ptr]),

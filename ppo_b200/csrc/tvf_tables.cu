@@ -6,10 +6,8 @@
 //   * per entry, and per tail length m = N - t, the searchsorted slot and the lerp weights of
 //     rl/returns_truncated.py:142-174 (float64 arithmetic like NumPy, rounded to float32 once);
 //   * discount powers as the reference's float32 running product times a float64 gamma (:669).
-// In addition the builder may permute the entry slots of every horizon so that the consumer warps of
-// the slab kernel (lane <-> horizon, 32 consecutive horizons per warp) hit distinct shared-memory
-// banks: the order of the entries of one horizon is arbitrary (their terms are summed), so this only
-// changes the float32 summation order.
+// It also writes horizon-major copies of the folded tail tables (what the transposed slab kernel reads with
+// lanes along time).
 #include <math.h>
 #include <string.h>
 
@@ -57,99 +55,6 @@ struct Entry {
     Lerp l;
 };
 
-// Minimum-cost assignment of r rows to 8 columns (r <= 8), O(n^3) Hungarian on a padded square matrix.
-void assign8(const double cost[8][8], int rows, int* col_of_row) {
-    const int n = 8;
-    double u[9] = {0}, v[9] = {0};
-    int p[9] = {0}, way[9] = {0};
-    for (int i = 1; i <= n; ++i) {
-        p[0] = i;
-        int j0 = 0;
-        double minv[9];
-        bool used[9] = {false};
-        for (int j = 0; j <= n; ++j) minv[j] = 1e300;
-        do {
-            used[j0] = true;
-            const int i0 = p[j0];
-            double delta = 1e300;
-            int j1 = 0;
-            for (int j = 1; j <= n; ++j) {
-                if (used[j]) continue;
-                const double c = (i0 <= rows ? cost[i0 - 1][j - 1] : 0.0) - u[i0] - v[j];
-                if (c < minv[j]) minv[j] = c, way[j] = j0;
-                if (minv[j] < delta) delta = minv[j], j1 = j;
-            }
-            for (int j = 0; j <= n; ++j) {
-                if (used[j]) u[p[j]] += delta, v[j] -= delta;
-                else minv[j] -= delta;
-            }
-            j0 = j1;
-        } while (p[j0] != 0);
-        do {
-            const int j1 = way[j0];
-            p[j0] = p[j1];
-            j0 = j1;
-        } while (j0);
-    }
-    for (int j = 1; j <= n; ++j)
-        if (p[j] >= 1 && p[j] <= rows) col_of_row[p[j] - 1] = j - 1;
-}
-
-// Slot permutation for one warp of up to 32 horizons.  ent[k] holds the live entries of horizon k.
-// Cost model of the slab kernel: per slot one 16-byte prefix read per lane (quarter-warps of 8 lanes
-// conflict when distinct n fall into the same 16-byte bank group) and eight 4-byte slab reads (lanes
-// conflict when distinct (row, column) addresses share a bank = column mod 32).
-void permute_warp(std::vector<std::vector<Entry>>& ent, int k0, int k1, int n_slots, int pt_pitch_words) {
-    const int lanes = k1 - k0;
-    std::vector<std::vector<int>> slot_of(lanes);
-    for (int i = 0; i < lanes; ++i) {
-        slot_of[i].resize(ent[k0 + i].size());
-        for (size_t e = 0; e < slot_of[i].size(); ++e) slot_of[i][e] = static_cast<int>(e);
-    }
-    auto quad_of = [&](int n) { return (n * pt_pitch_words / 4) & 7; };
-    auto boots = [](const Entry& x) { return x.l.wlo != 0.f || x.l.whi != 0.f; };
-    for (int pass = 0; pass < 2; ++pass) {
-        for (int i = 0; i < lanes; ++i) {
-            const std::vector<Entry>& mine = ent[k0 + i];
-            const int r = static_cast<int>(mine.size());
-            if (r == 0) continue;
-            double cost[8][8];
-            for (int a = 0; a < r; ++a) {
-                for (int s = 0; s < 8; ++s) {
-                    if (s >= n_slots) {
-                        cost[a][s] = 1e9;
-                        continue;
-                    }
-                    int cv = 0, cs = 0;
-                    for (int o = 0; o < lanes; ++o) {
-                        if (o == i) continue;
-                        if (pass == 0 && o > i) break;  // first pass: only lanes already placed
-                        const std::vector<Entry>& other = ent[k0 + o];
-                        for (size_t e = 0; e < other.size(); ++e) {
-                            if (slot_of[o][e] != s) continue;
-                            const Entry& y = other[e];
-                            if (boots(mine[a]) && boots(y) && ((y.l.lo ^ mine[a].l.lo) & 31) == 0 &&
-                                !(y.n == mine[a].n && y.l.lo == mine[a].l.lo))
-                                ++cv;
-                            if ((o >> 3) == (i >> 3) && y.n != mine[a].n && quad_of(y.n) == quad_of(mine[a].n)) ++cs;
-                        }
-                    }
-                    cost[a][s] = 8.0 * (cv * cv + cv) + (cs * cs + cs);
-                }
-            }
-            int col[8];
-            assign8(cost, r, col);
-            for (int a = 0; a < r; ++a) slot_of[i][a] = col[a];
-        }
-    }
-    for (int i = 0; i < lanes; ++i) {
-        std::vector<Entry>& mine = ent[k0 + i];
-        std::vector<Entry> placed(n_slots, Entry{0, 0.f, Lerp{0, 0, 0.f, 0.f}});
-        for (size_t e = 0; e < mine.size(); ++e) placed[slot_of[i][e]] = mine[e];
-        mine.swap(placed);
-    }
-}
-
 // Sample-independent part of the tail tables, cached per horizon set (it depends on the horizons, the
 // interpolation axis and the number of steps only).
 struct TailCache {
@@ -176,7 +81,7 @@ extern "C" int64_t ppo_tvf_tables_words(int64_t n_req, int64_t n_samples, int64_
 
 extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* required_horizons, int64_t n_req,
                                     const int64_t* value_horizons, int64_t n_val, const int64_t* samples,
-                                    int64_t n_samples, int use_log_interpolation, int optimise_slots,
+                                    int64_t n_samples, int use_log_interpolation,
                                     int32_t* blob, int64_t blob_words, ppo_tvf_table_layout* layout) {
     PPO_REQUIRE(required_horizons && value_horizons && samples && blob && layout, "ppo_tvf_tables_build: null pointer");
     PPO_REQUIRE(n_req >= 1 && n_val >= 1 && n_samples >= 1 && steps >= 1, "ppo_tvf_tables_build: bad shape");
@@ -268,12 +173,7 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
             }
     }
 
-    // ---- optional slot permutation for the slab kernel's bank behaviour
-    if (optimise_slots && E <= 8 && E >= 2) {
-        for (int k0 = 0; k0 < K; k0 += 32) permute_warp(ent, k0, std::min(K, k0 + 32), E, 36);
-    } else {
-        for (int k = 0; k < K; ++k) ent[k].resize(E, Entry{0, 0.f, Lerp{0, 0, 0.f, 0.f}});
-    }
+    for (int k = 0; k < K; ++k) ent[k].resize(E, Entry{0, 0.f, Lerp{0, 0, 0.f, 0.f}});
 
     // ---- pack
     auto pad = [](int64_t w) { return (w + 3) / 4 * 4; };

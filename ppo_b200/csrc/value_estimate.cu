@@ -82,6 +82,43 @@ __global__ void __launch_bounds__(256) value_prefix_kernel(const __grid_constant
     }
 }
 
+// Per-row linear interpolation of a value curve at a per-row target horizon (rl/tvf.py:527-573 `horizon_interpolate`):
+// clip the target to [h_0, h_{K-1}], post = searchsorted(h, x, left), pre = max(post - 1, 0),
+// f = (x - h_pre) / (h_post - h_pre) (1 where the width is 0), out = v_pre (1 - f) + v_post f in float64, 0 where
+// post == 0.  The horizon axis arrives as doubles (the reference also calls this on a log-scaled axis,
+// rl/tvf.py:143-152); one thread per row, the axis in shared memory, two value reads per row.
+struct InterpParams {
+    const float* v;
+    int64_t rows, rs;
+    int k;
+    const double* targets;
+    double* out;
+    double h[kMaxValueHorizons];
+};
+
+__global__ void __launch_bounds__(256) horizon_interpolate_kernel(const __grid_constant__ InterpParams p) {
+    __shared__ double sh[kMaxValueHorizons];
+    for (int j = threadIdx.x; j < p.k; j += blockDim.x) sh[j] = p.h[j];
+    __syncthreads();
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; row < p.rows; row += stride) {
+        double x = p.targets[row];
+        x = fmin(fmax(x, sh[0]), sh[p.k - 1]);
+        int lo = 0, hi = p.k;  // first index with h[index] >= x
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (sh[mid] < x) lo = mid + 1;
+            else hi = mid;
+        }
+        const int post = lo, pre = post > 0 ? post - 1 : 0;
+        double width = sh[post] - sh[pre];
+        if (width == 0.0) width = 1.0;
+        const double f = (x - sh[pre]) / width;
+        const double a = static_cast<double>(p.v[row * p.rs + pre]), b = static_cast<double>(p.v[row * p.rs + post]);
+        p.out[row] = post == 0 ? 0.0 : __dadd_rn(__dmul_rn(a, 1.0 - f), __dmul_rn(b, f));
+    }
+}
+
 static int64_t warp_grid(int64_t rows) {
     int64_t blocks = (rows + 7) / 8;
     const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
@@ -133,6 +170,26 @@ extern "C" int ppo_rediscount_horizons(const float* values, int64_t rows, int64_
     p.v = values, p.rows = rows, p.rs = row_stride, p.os = out_row_stride, p.k = static_cast<int>(n_val), p.out = out;
     for (int j = 0; j < p.k; ++j) p.rho[j] = host_ratios[j];
     value_prefix_kernel<<<static_cast<unsigned>(warp_grid(rows)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+extern "C" int ppo_horizon_interpolate(const double* host_horizons, int64_t n_val, const float* values, int64_t rows,
+                                       int64_t row_stride, const double* targets, double* out, void* stream) {
+    PPO_REQUIRE(rows >= 0 && n_val >= 1 && row_stride >= n_val, "ppo_horizon_interpolate: bad shape");
+    if (rows == 0) return PPO_OK;
+    PPO_REQUIRE(host_horizons && values && targets && out, "ppo_horizon_interpolate: null pointer");
+    if (n_val > kMaxValueHorizons) {
+        set_error("ppo_horizon_interpolate: more than %d value horizons", kMaxValueHorizons);
+        return PPO_ERR_UNSUPPORTED;
+    }
+    InterpParams p{};
+    p.v = values, p.rows = rows, p.rs = row_stride, p.k = static_cast<int>(n_val), p.targets = targets, p.out = out;
+    for (int j = 0; j < p.k; ++j) p.h[j] = host_horizons[j];
+    int64_t blocks = (rows + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+    if (blocks > cap) blocks = cap;
+    horizon_interpolate_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;
 }

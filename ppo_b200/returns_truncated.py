@@ -77,7 +77,7 @@ class NativeTables:
 
 
 def build_tables(gamma, steps, required_horizons, value_sample_horizons, n_step_samples,
-                 use_log_interpolation=False, optimise_slots=False):
+                 use_log_interpolation=False):
     """Resolve a ``[K, C]`` n-step sample table into the packed index tables (host side of ``ppo_tvf_targets``).
     Raises like the reference: ``AssertionError`` for an n-step outside ``1..N`` (rl/returns_truncated.py:597),
     ``IndexError`` for a bootstrap horizon beyond the last value horizon (:157)."""
@@ -94,7 +94,7 @@ def build_tables(gamma, steps, required_horizons, value_sample_horizons, n_step_
     layout = _CLayout()
     rc = lib.ppo_tvf_tables_build(float(gamma), int(steps), req.ctypes.data, len(req), vsh.ctypes.data, len(vsh),
                                   samples.ctypes.data, samples.shape[1], int(bool(use_log_interpolation)),
-                                  int(bool(optimise_slots)), host.data_ptr(), host.numel(), ctypes.byref(layout))
+                                  host.data_ptr(), host.numel(), ctypes.byref(layout))
     if rc == _lib.PPO_ERR_BAD_ARG:
         raise AssertionError(lib.ppo_last_error().decode("utf-8", "replace"))
     if rc == _lib.PPO_ERR_UNSUPPORTED:

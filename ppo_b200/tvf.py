@@ -106,6 +106,31 @@ def rediscount_horizons(values, old_gamma: float, new_gamma: float, horizons, cl
     return dev.like_input(out, np_like)
 
 
+def horizon_interpolate(horizons, values, target_horizons):
+    """Linearly interpolated value at a per-example target horizon: ``values [*shape, K]``, ``target_horizons
+    [*shape]`` -> ``[*shape]`` float64 (reference: ``rl/tvf.py:527-573``, same assertions)."""
+    horizons = np.asarray(horizons)
+    assert len(set(horizons.tolist())) == len(horizons), f"Horizons duplicates not supported {horizons}"
+    assert np.all(np.diff(horizons) > 0), \
+        f"Horizons must be sorted and unique horizons:{horizons}, targets:{target_horizons}"
+    assert horizons[0] == 0, "first horizon must be 0"
+    *shape, n_h = values.shape
+    shape = tuple(shape)
+    assert horizons.shape == (n_h,)
+    assert tuple(target_horizons.shape) == shape, f"{tuple(target_horizons.shape)} != {shape}"
+    device = dev.require_cuda()
+    lib = _lib.load()
+    np_like = dev.is_numpy_like(values)
+    v = dev.to_device(values, torch.float32, device).reshape(-1, n_h).contiguous()
+    t = dev.to_device(target_horizons, torch.float64, device).reshape(-1).contiguous()
+    out = torch.empty(v.shape[0], dtype=torch.float64, device=device)
+    axis = np.ascontiguousarray(horizons, dtype=np.float64)
+    rc = lib.ppo_horizon_interpolate(axis.ctypes.data, n_h, dev.ptr(v), v.shape[0], n_h, dev.ptr(t), dev.ptr(out),
+                                     dev.stream_ptr())
+    _lib.check(rc, "ppo_horizon_interpolate")
+    return dev.like_input(out.reshape(shape), np_like)
+
+
 class TVFRunnerModule:
     """Return-side mirror of ``rl.tvf.TVFRunnerModule``.
 

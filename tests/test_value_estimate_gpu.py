@@ -140,3 +140,21 @@ def test_runner_module_value_estimate_and_returns():
     assert targets.shape == (steps, envs, len(hz)) and rel_err(targets, ref) <= TOL
     assert rel_err(mod.rediscount_horizons(vs.reshape(-1, len(hz))),
                    oracle.rediscount_horizons(vs.reshape(-1, len(hz)), 0.9999, 0.999, hz)) <= TOL
+
+
+def test_horizon_interpolate_golden_and_oracle(golden):
+    hz = golden["prod_in_horizons"]
+    got = tvf.horizon_interpolate(hz, golden["hinterp_in_values"], golden["hinterp_in_targets"])
+    assert got.dtype == np.float64 and got.shape == golden["hinterp"].shape
+    assert np.abs(got - golden["hinterp"]).max() <= 1e-12 * max(np.abs(golden["hinterp"]).max(), 1.0)
+    # the log-scaled axis of trim_horizons (rl/tvf.py:143-152), targets beyond both ends of the axis, exact hits
+    rng = np.random.RandomState(2)
+    v = rng.normal(size=[5000, len(hz)]).astype(np.float32)
+    t = rng.uniform(-10, 40000, size=[5000])
+    t[:len(hz)] = hz
+    scale = lambda x: np.log10(10 + np.maximum(x, -9)) - 1  # noqa: E731
+    ref = oracle.horizon_interpolate(scale(hz.astype(np.float64)), v, scale(t))
+    got = tvf.horizon_interpolate(scale(hz.astype(np.float64)), v, scale(t))
+    assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+    with pytest.raises(AssertionError):
+        tvf.horizon_interpolate(hz[1:], v[:, 1:], t)  # first horizon must be 0
