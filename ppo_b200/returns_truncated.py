@@ -228,18 +228,12 @@ def _launch_host_blocks(gamma, rewards, dones, required_horizons, value_sample_h
     pass) on its own stream while the blocks are in flight."""
     device = dev.require_cuda()
     lib = _lib.load()
-    r = dev.env_contiguous(dev.to_device(rewards, torch.float32, device))
-    steps, envs = r.shape
+    steps, envs = rewards.shape
     req, vsh = np.asarray(required_horizons), np.asarray(value_sample_horizons)
     n_req, n_val = len(req), len(vsh)
     assert tuple(value_samples.shape) == (steps + 1, envs, n_val), \
         f"value_samples must be [N+1, A, V] = {(steps + 1, envs, n_val)}, got {tuple(value_samples.shape)}"
     assert tuple(out.shape) == (steps, envs, n_req), f"out must be [N, A, K] = {(steps, envs, n_req)}"
-    d, kind = dev.done_tensor(dones, device)
-    assert d is not None and tuple(d.shape) == (steps, envs), f"dones must be [N, A] = {(steps, envs)}"
-    d = dev.env_contiguous(d)
-    tabs = build_tables(gamma, steps, req, vsh, n_step_samples, use_log_interpolation)
-    ctab, blob = _upload_tables(tabs, device)
 
     sms = torch.cuda.get_device_properties(device).multi_processor_count
     if block_envs is None:
@@ -257,28 +251,46 @@ def _launch_host_blocks(gamma, rewards, dones, required_horizons, value_sample_h
     else:
         block_envs = int(min(block_envs, envs))
         sizes = [block_envs] * (envs // block_envs) + ([envs % block_envs] if envs % block_envs else [])
+    starts = [sum(sizes[:c]) for c in range(len(sizes))]
     st = _pipeline_state(device, steps, block_envs, n_val, n_req)
     s_main, s_in, s_out, s_comp = torch.cuda.current_stream(), st["s_in"], st["s_out"], st["s_comp"]
     for s_ in (s_in, s_out, s_comp):
         s_.wait_stream(s_main)
     n_blocks = len(sizes)
-    stats = torch.zeros((n_blocks, _lib.STATS_LEN), dtype=torch.float64, device=device) if with_stats else None
-    ws = st["ws"] if with_stats else None
-    ev_comp, ev_out = [], []
-    lo = 0
-    for c, ab in enumerate(sizes):
-        vs_d, out_d = st["vs"][c & 1], st["out"][c & 1]
-        # ---- upload (waits until the kernels of block c - 2 have released this scratch)
+    ev_in, ev_comp, ev_out = {}, [], []
+
+    def upload(c):
+        """value curves of block c -> scratch c & 1 (after the kernels of block c - 2 have released it)"""
+        lo, ab = starts[c], sizes[c]
         if c >= 2:
             s_in.wait_event(ev_comp[c - 2])
-        rc = lib.ppo_memcpy_2d_async(vs_d.data_ptr(), ab * n_val * 4,
+        rc = lib.ppo_memcpy_2d_async(st["vs"][c & 1].data_ptr(), ab * n_val * 4,
                                      value_samples.data_ptr() + lo * n_val * 4, value_samples.stride(0) * 4,
                                      ab * n_val * 4, steps + 1, s_in.cuda_stream)
         _lib.check(rc, "ppo_memcpy_2d_async")
-        ev_in = torch.cuda.Event()
-        ev_in.record(s_in)
+        ev_in[c] = torch.cuda.Event()
+        ev_in[c].record(s_in)
+
+    # the first two uploads do not depend on anything computed below: start them before the host-side table work
+    for c in range(min(2, n_blocks)):
+        upload(c)
+
+    r = dev.env_contiguous(dev.to_device(rewards, torch.float32, device))
+    d, kind = dev.done_tensor(dones, device)
+    assert d is not None and tuple(d.shape) == (steps, envs), f"dones must be [N, A] = {(steps, envs)}"
+    d = dev.env_contiguous(d)
+    tabs = build_tables(gamma, steps, req, vsh, n_step_samples, use_log_interpolation)
+    ctab, blob = _upload_tables(tabs, device)
+    stats = torch.zeros((n_blocks, _lib.STATS_LEN), dtype=torch.float64, device=device) if with_stats else None
+    ws = st["ws"] if with_stats else None
+    s_comp.wait_stream(s_main)  # rewards / terminals / tables / zeroed records were issued on the caller's stream
+    for c, ab in enumerate(sizes):
+        lo = starts[c]
+        vs_d, out_d = st["vs"][c & 1], st["out"][c & 1]
+        if c not in ev_in:
+            upload(c)
         # ---- kernels (their own stream: the caller's stream stays free for the GAE part of the pass)
-        s_comp.wait_event(ev_in)
+        s_comp.wait_event(ev_in[c])
         if c >= 2:
             s_comp.wait_event(ev_out[c - 2])
         extras, keep = _extras(value_out, value_weights, env_offset=lo)
@@ -300,7 +312,6 @@ def _launch_host_blocks(gamma, rewards, dones, required_horizons, value_sample_h
         e = torch.cuda.Event()
         e.record(s_out)
         ev_out.append(e)
-        lo += ab
     # the inputs (r, d, tables) must outlive the kernels: tie their lifetime to the side stream
     for t_ in (r, d, blob[0] if isinstance(blob, tuple) else blob):
         t_.record_stream(s_comp)
