@@ -149,6 +149,9 @@ int ppo_discounted_returns(const float* rewards, int64_t reward_row_stride,
  *            only has to stay valid for the duration of the call.
  *   gamma    (optional, 0 = absent) the float64 discount the tables were built for; the transposed slab kernel
  *            carries the discounted reward-to-go in float64 with it
+ *   tslab_offset_words  (optional, 0 = absent) offset inside the blob of the per-(horizon, n-step) launch
+ *            constants of the transposed slab kernel (ppo_tvf_table_layout.offset_words[15]); they are copied from
+ *            host_blob into the kernel parameters, so a launch does no table arithmetic
  */
 typedef struct {
     int32_t n_entries;
@@ -173,11 +176,12 @@ typedef struct {
     const void* host_blob;
     const void* dev_blob;
     double gamma;
+    int64_t tslab_offset_words;
 } ppo_tvf_tables;
 
 /* Offsets (in 32-bit words) of the tables inside the packed blob written by ppo_tvf_tables_build: [0..11] in the
  * order of the first twelve pointer members of ppo_tvf_tables (ent_n ... gpow), [12..14] tailT_idx / tailT_cwlo /
- * tailT_cwhi, [15] = total_words; every table starts 16-byte aligned. */
+ * tailT_cwhi, [15] launch constants of the transposed slab kernel; every table starts 16-byte aligned. */
 typedef struct {
     int32_t n_entries;
     int32_t nmax;

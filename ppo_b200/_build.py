@@ -57,13 +57,33 @@ def build(force=False, verbose=False):
     nvcc = nvcc_path()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build ppo_b200/csrc/libppo_b200.so")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + _sources()
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    log = proc.stdout + proc.stderr
+    # one translation unit per nvcc process, in parallel; objects live in csrc/build/ (git-ignored)
+    obj_dir = os.path.join(CSRC, "build")
+    os.makedirs(obj_dir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc] + compile_flags + ["-c", "-o", obj, src]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        return obj, " ".join(cmd) + "\n" + proc.stdout + proc.stderr, proc.returncode
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, _sources()))
+    log = "".join(text for _, text, _ in results)
+    failed = [text for _, text, rc in results if rc != 0]
+    if not failed:
+        cmd = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + \
+              [obj for obj, _, _ in results]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        log += " ".join(cmd) + "\n" + proc.stdout + proc.stderr
+        if proc.returncode != 0:
+            failed = [proc.stdout + proc.stderr]
     with open(os.path.join(CSRC, "build.log"), "w") as fh:
-        fh.write(" ".join(cmd) + "\n" + log)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + log[-8000:])
+        fh.write(log)
+    if failed:
+        raise RuntimeError("nvcc failed:\n" + "\n".join(failed)[-8000:])
     if verbose:
         print(log)
     with open(_STAMP, "w") as fh:

@@ -21,6 +21,22 @@ struct TvfParams {
     float* out;  // [N, A, K]
 };
 
+// Launch constants of the transposed slab kernel (tvf_tslab.cu), resolved on the host by ppo_tvf_tables_build.
+constexpr int kTsMaxK = 128;
+constexpr int kTsMaxEntries = 1024;
+constexpr int kTsConstMagic = 0x54534c42;  // header word of the constants section: magic, n_ent (-1 = none), pitch, V
+struct __align__(16) TsEntry {
+    uint32_t off;    // byte offset of W^T[col][n - 1] in the slab
+    float wlo, whi;  // multiplicity * gamma^n * lerp weights
+    int32_t n;
+};
+struct __align__(16) TsHorizon {
+    int32_t beg, cnt;  // entries [beg, beg + cnt)
+    float rscale;      // 1 for a live horizon, 0 for h = 0 (all-zero targets)
+    int32_t maxn;      // largest n-step of the horizon (tail rows: N - t < maxn)
+};
+
+
 __device__ __forceinline__ bool done_at(const void* dones, int kind, int64_t idx) {
     if (kind == PPO_DONE_U8) return static_cast<const unsigned char*>(dones)[idx] != 0;
     if (kind == PPO_DONE_F32) return static_cast<const float*>(dones)[idx] != 0.f;

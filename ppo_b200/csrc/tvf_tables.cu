@@ -15,7 +15,7 @@
 #include <mutex>
 #include <vector>
 
-#include "common.cuh"
+#include "tvf_common.cuh"
 
 namespace ppo {
 namespace {
@@ -76,7 +76,8 @@ extern "C" int64_t ppo_tvf_tables_words(int64_t n_req, int64_t n_samples, int64_
     if (n_req < 0 || n_samples < 1 || steps < 0) return -1;
     const int64_t e = std::min<int64_t>(n_samples, std::max<int64_t>(steps, 1));
     auto pad = [](int64_t w) { return (w + 3) / 4 * 4; };
-    return 6 * pad(e * n_req) + 5 * pad((steps + 1) * n_req) + pad(steps + 1) + 3 * pad(n_req * pad(steps + 1)) + 16;
+    return 6 * pad(e * n_req) + 5 * pad((steps + 1) * n_req) + pad(steps + 1) + 3 * pad(n_req * pad(steps + 1)) +
+           pad(4 + 4 * n_req + 4 * e * n_req) + 16;
 }
 
 extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* required_horizons, int64_t n_req,
@@ -186,7 +187,8 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
     // horizon-major copies of the folded tail tables, [K][tail_pitch], for the transposed slab kernel
     const int64_t tpitch = pad(nmax + 1);
     for (int i = 12; i < 15; ++i) offs[i] = off, off += pad(static_cast<int64_t>(K) * tpitch);
-    offs[15] = off;
+    // launch constants of the transposed slab kernel: header, K horizon records, the live entries
+    offs[15] = off, off += pad(4 + 4 * static_cast<int64_t>(K) + 4 * ek);
     if (off > blob_words) {
         set_error("ppo_tvf_tables_build: blob of %lld words required, got %lld", (long long)off, (long long)blob_words);
         return PPO_ERR_WORKSPACE;
@@ -236,6 +238,46 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
                 const int64_t src = static_cast<int64_t>(m) * K + k, dst = static_cast<int64_t>(k) * tpitch + m;
                 t_idx[dst] = tail_idx[src], t_wlo[dst] = tail_cwlo[src], t_whi[dst] = tail_cwhi[src];
             }
+    }
+    {
+        // Per (horizon, n-step) constants of the transposed slab kernel: byte offset of W^T[col][n - 1] in a slab of
+        // pitch N | 1, multiplicity * gamma^n * lerp weights (float64 product, rounded once), n.  Entries without a
+        // bootstrap read the -R column (index V) with weight multiplicity * gamma^n; single-slot values read their
+        // neighbour column with weight zero.
+        int32_t* hdr = blob + offs[15];
+        const int pitch = static_cast<int>(steps) | 1;
+        hdr[0] = kTsConstMagic, hdr[1] = -1, hdr[2] = pitch, hdr[3] = V;
+        bool ok = K <= kTsMaxK && ek <= kTsMaxEntries;
+        TsHorizon* hz = reinterpret_cast<TsHorizon*>(hdr + 4);
+        TsEntry* te = reinterpret_cast<TsEntry*>(hdr + 4 + 4 * K);
+        std::vector<double> gp64(nmax + 1, 1.0);
+        for (int n = 1; n <= nmax; ++n) gp64[n] = pow(gamma, static_cast<double>(n));
+        int total = 0;
+        for (int k = 0; k < K && ok; ++k) {
+            TsHorizon& h = hz[k];
+            h.beg = total, h.cnt = 0, h.maxn = 0;
+            double csum = 0.0;
+            for (int e = 0; e < E && ok; ++e) {
+                const Entry& x = ent[k][e];
+                if (!(x.cnt > 0.f)) continue;
+                double a = x.l.wlo, bw = x.l.whi;
+                int col;
+                if (a == 0.0 && bw == 0.0) col = V, a = 1.0;
+                else if (x.l.hi == x.l.lo) col = x.l.lo, bw = 0.0;
+                else if (x.l.hi == x.l.lo + 1) col = x.l.lo;
+                else { ok = false; break; }
+                const double cg = static_cast<double>(x.cnt) * gp64[x.n];
+                TsEntry& t = te[total++];
+                t.off = static_cast<uint32_t>((static_cast<int64_t>(col) * pitch + x.n - 1) * 4);
+                t.wlo = static_cast<float>(a * cg), t.whi = static_cast<float>(bw * cg);
+                t.n = x.n;
+                ++h.cnt;
+                csum += x.cnt;
+                h.maxn = std::max(h.maxn, x.n);
+            }
+            h.rscale = static_cast<float>(csum / static_cast<double>(C));
+        }
+        if (ok) hdr[1] = total;
     }
     layout->tail_pitch = static_cast<int32_t>(tpitch);
     layout->gamma = gamma;

@@ -27,6 +27,7 @@
 // Warp roles: 0-15 consumers, 16-19 transform, 20 scan (R and lim tables, float64), 21 store, 22 TMA producer.
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "tma.cuh"
 #include "tvf_common.cuh"
@@ -36,28 +37,17 @@ namespace ppo {
 constexpr int kTsConsumers = 16;
 constexpr int kTsXform = 4;
 constexpr int kTsThreads = (kTsConsumers + kTsXform + 3) * 32;
-constexpr int kTsMaxK = 128;
-constexpr int kTsMaxEntries = 1024;
 constexpr int kTsRows = 32;        // value rows per TMA chunk = time rows per lane group
 constexpr int kTsStep = 64;        // time rows per consumer step: a thread owns rows t and t + 32 of the step
 constexpr int kTsMaxChunks = 16;   // N <= 512
 constexpr int kTsMaxSteps = 8;
 
-struct __align__(16) TsEntry {
-    uint32_t off;    // byte offset of W^T[col][n - 1] in the slab
-    float wlo, whi;  // multiplicity * gamma^n * lerp weights
-    int32_t n;
-};
-struct __align__(16) TsHorizon {
-    int32_t beg, cnt;  // entries [beg, beg + cnt)
-    float rscale;      // 1 for a live horizon, 0 for h = 0 (all-zero targets)
-    int32_t maxn;      // largest n-step of the horizon (tail rows: N - t < maxn)
-};
-
 struct TsParams {
     TvfParams p;
     double gamma;
     int nc, ns, pitch, nstage, kq, rt_words, tail_pitch, want_stats, n_ent;
+    int nslab;            // env slabs in shared memory: 2 when they fit (the next env is staged while this one is evaluated)
+    uint32_t slab_bytes;  // bytes of one slab (value columns + -R column + zero column + padding)
     int dbg;  // development switches (PPO_TVF_DEBUG): 1 no stores, 2 no TMA loads, 4 no transform, 8 no entry loop, 16 no tail term
     int64_t env_base, env_rem;
     uint32_t off_stage, off_ot, off_ent, off_hz, off_rtab, off_lim, off_fr, off_bar, smem_total;
@@ -166,9 +156,9 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + q.off_bar);
     uint64_t* sfull = bars;                     // [4] TMA chunk landed
     uint64_t* sempty = sfull + 4;               // [4] chunk transposed, slot reusable
-    uint64_t* wfull = sempty + 4;               // [NC] chunk c of the current env is in the slab
-    uint64_t* bdone = wfull + kTsMaxChunks;     // [NS] consumers finished step s (slab rows of its chunks reusable)
-    uint64_t* rfull = bdone + kTsMaxSteps;      // [2] R / lim tables of env parity ready
+    uint64_t* wfull = sempty + 4;                   // [2][NC] chunk c of an env is in its slab
+    uint64_t* bdone = wfull + 2 * kTsMaxChunks;     // [2][NS] consumers finished step s (slab rows of its chunks reusable)
+    uint64_t* rfull = bdone + 2 * kTsMaxSteps;      // [2] R / lim tables of env parity ready
     uint64_t* rempty = rfull + 2;               // [2]
     uint64_t* ofull = rempty + 2;               // output tile written
     uint64_t* oempty = ofull + 1;               // output tile copied out
@@ -189,8 +179,8 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 4; ++i) mbar_init(&sfull[i], 1), mbar_init(&sempty[i], kTsXform);
-        for (int i = 0; i < kTsMaxChunks; ++i) mbar_init(&wfull[i], kTsXform);
-        for (int i = 0; i < kTsMaxSteps; ++i) mbar_init(&bdone[i], kTsConsumers);
+        for (int i = 0; i < 2 * kTsMaxChunks; ++i) mbar_init(&wfull[i], kTsXform);
+        for (int i = 0; i < 2 * kTsMaxSteps; ++i) mbar_init(&bdone[i], kTsConsumers);
         for (int i = 0; i < 2; ++i) mbar_init(&rfull[i], 1), mbar_init(&rempty[i], kTsConsumers + kTsXform);
         mbar_init(ofull, kTsConsumers), mbar_init(oempty, 1);
         mbar_fence_init();
@@ -345,9 +335,14 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
             }
             mbar_wait_sleep(&rfull[par], (static_cast<uint32_t>(e) >> 1) & 1u);
             const uint32_t rt = rt_a + par * rt_bytes;
+            // slab of this env; it was last used by env e - nslab (the j-th use of a slab waits for use j - 1)
+            const int sl = e % q.nslab;
+            const uint32_t use = static_cast<uint32_t>(e / q.nslab);
+            const uint32_t wt_e = wt_a + static_cast<uint32_t>(sl) * q.slab_bytes;
+            const uint32_t fr_e = fr_a + static_cast<uint32_t>(sl * V) * 4u;
             for (int c = 0; c < NC; ++c) {
-                // slab rows of chunk c were last needed by step c / 2 of the previous env
-                if (e > 0) mbar_wait_sleep(&bdone[c >> 1], static_cast<uint32_t>(e - 1) & 1u);
+                // slab rows of chunk c were last needed by step c / 2 of the previous env in this slab
+                if (use > 0) mbar_wait_sleep(&bdone[sl * kTsMaxSteps + (c >> 1)], (use - 1) & 1u);
                 mbar_wait(&sfull[slot], spar);
                 const uint32_t src = stage_a + static_cast<uint32_t>(slot) * CHUNK + static_cast<uint32_t>(lane) * 4u;
                 float part[kTsRows / kTsXform];  // value-estimate partial sums of this warp's eight rows
@@ -365,8 +360,8 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                         for (int cg = 0; cg < V / 32; ++cg) v[cg] = ts_lds(src + static_cast<uint32_t>(lr * V + cg * 32) * 4u);
 #pragma unroll
                         for (int cg = 0; cg < V / 32; ++cg) {
-                            ts_sts(wt_a + static_cast<uint32_t>((cg * 32 + lane) * P + i) * 4u, v[cg] - Rr);
-                            if (i == N - 1) ts_sts(fr_a + static_cast<uint32_t>(cg * 32 + lane) * 4u, v[cg]);
+                            ts_sts(wt_e + static_cast<uint32_t>((cg * 32 + lane) * P + i) * 4u, v[cg] - Rr);
+                            if (i == N - 1) ts_sts(fr_e + static_cast<uint32_t>(cg * 32 + lane) * 4u, v[cg]);
                         }
                         if (q.want_value == 2) {
 #pragma unroll
@@ -406,12 +401,12 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                 }
                 if (xw == 0) {  // the -R column (index V); column V + 1 stays zero
                     const int i = c * kTsRows + lane;
-                    if (i < N) ts_sts(wt_a + static_cast<uint32_t>(V * P + i) * 4u, -ts_lds(rt + static_cast<uint32_t>(i + 1) * 4u));
+                    if (i < N) ts_sts(wt_e + static_cast<uint32_t>(V * P + i) * 4u, -ts_lds(rt + static_cast<uint32_t>(i + 1) * 4u));
                 }
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(&sempty[slot]);
-                    mbar_arrive(&wfull[c]);
+                    mbar_arrive(&wfull[sl * kTsMaxChunks + c]);
                 }
                 if (++slot == q.nstage) slot = 0, spar ^= 1;
             }
@@ -431,12 +426,16 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
             mbar_wait(&rfull[par], (static_cast<uint32_t>(e) >> 1) & 1u);
             const uint32_t rt = rt_a + par * rt_bytes, lt = lim_a + par * rt_bytes;
             int waited = 0;
+            const int sl = e % q.nslab;
+            const uint32_t use_par = static_cast<uint32_t>(e / q.nslab) & 1u;
+            const uint32_t wt_e = wt_a + static_cast<uint32_t>(sl) * q.slab_bytes;
+            const uint32_t fr_e = fr_a + static_cast<uint32_t>(sl * V) * 4u;
             for (int s = 0; s < NS; ++s, ++it) {
                 const int t0 = s * kTsStep + lane, t1 = t0 + kTsRows;
                 const int last_i = min(N - 1, s * kTsStep + kTsStep - 1 + nmax - 1);  // last slab index a live gather may touch
                 const int cneed = last_i / kTsRows;
                 while (waited <= cneed) {
-                    mbar_wait(&wfull[waited], par);
+                    mbar_wait(&wfull[sl * kTsMaxChunks + waited], use_par);
                     ++waited;
                 }
                 const int lim0 = ts_lds_s32(lt + static_cast<uint32_t>(t0) * 4u);
@@ -450,7 +449,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                 // warp votes: the tail work of a 32-row half is skipped when none of its rows is alive to the end
                 const bool any_end0 = __any_sync(0xffffffffu, end0), any_end1 = __any_sync(0xffffffffu, end1);
                 const bool any_end = any_end0 || any_end1;
-                const uint32_t base = wt_a + static_cast<uint32_t>(t0) * 4u;
+                const uint32_t base = wt_e + static_cast<uint32_t>(t0) * 4u;
                 // output tile: [half][32-horizon group][32 rows][128 B], 16-byte chunks swizzled with the row (TMA 128B
                 // swizzle): the 8 lanes of a quarter-warp store to 8 different bank groups
                 const uint32_t orow = ot_a + static_cast<uint32_t>(lane) * 128u;
@@ -485,13 +484,13 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             if (any_end0 && end0) {
-                                const float v0 = ts_lds(fr_a + static_cast<uint32_t>(idx0[u] & 0xffff) * 4u);
-                                const float v1 = ts_lds(fr_a + static_cast<uint32_t>(idx0[u] >> 16) * 4u);
+                                const float v0 = ts_lds(fr_e + static_cast<uint32_t>(idx0[u] & 0xffff) * 4u);
+                                const float v1 = ts_lds(fr_e + static_cast<uint32_t>(idx0[u] >> 16) * 4u);
                                 tacc0[u] = fmaf(v1, w01[u], v0 * w00[u]);
                             }
                             if (any_end1 && end1) {
-                                const float v0 = ts_lds(fr_a + static_cast<uint32_t>(idx1[u] & 0xffff) * 4u);
-                                const float v1 = ts_lds(fr_a + static_cast<uint32_t>(idx1[u] >> 16) * 4u);
+                                const float v0 = ts_lds(fr_e + static_cast<uint32_t>(idx1[u] & 0xffff) * 4u);
+                                const float v1 = ts_lds(fr_e + static_cast<uint32_t>(idx1[u] >> 16) * 4u);
                                 tacc1[u] = fmaf(v1, w11[u], v0 * w10[u]);
                             }
                         }
@@ -534,7 +533,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(ofull);
-                    mbar_arrive(&bdone[s]);
+                    mbar_arrive(&bdone[sl * kTsMaxSteps + s]);
                 }
             }
             if (lane == 0) mbar_arrive(&rempty[par]);
@@ -647,51 +646,15 @@ int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsign
         q.dbg = d ? atoi(d) : 0;
     }
 
-    // ---- per-horizon launch constants from the host mirror of the tables
-    auto host = [&](const void* dev_ptr) {
-        return static_cast<const char*>(p.tab.host_blob) +
-               (static_cast<const char*>(dev_ptr) - static_cast<const char*>(p.tab.dev_blob));
-    };
-    const int32_t* h_n = reinterpret_cast<const int32_t*>(host(p.tab.ent_n));
-    const float* h_cnt = reinterpret_cast<const float*>(host(p.tab.ent_cnt));
-    const int32_t* h_idx = reinterpret_cast<const int32_t*>(host(p.tab.ent_idx));
-    const float* h_wlo = reinterpret_cast<const float*>(host(p.tab.ent_wlo));
-    const float* h_whi = reinterpret_cast<const float*>(host(p.tab.ent_whi));
-    int total = 0;
-    for (int k = 0; k < K; ++k) {
-        TsHorizon& h = q.hz[k];
-        h.beg = total, h.cnt = 0, h.maxn = 0;
-        double csum = 0.0;
-        for (int e = 0; e < E; ++e) {
-            const int64_t i = static_cast<int64_t>(e) * K + k;
-            const float cc = h_cnt[i];
-            if (!(cc > 0.f)) continue;
-            const int n = h_n[i];
-            if (n < 1 || n > N) return unsupported("entry n-step outside 1..N");
-            int lo = h_idx[i] & 0xffff, hi = h_idx[i] >> 16;
-            double a = h_wlo[i], bw = h_whi[i];
-            if (lo >= V || hi >= V) return unsupported("interpolation slot outside the value horizons");
-            int col;
-            if (a == 0.0 && bw == 0.0) {
-                col = V, a = 1.0, bw = 0.0;  // no bootstrap: gamma^n * (-R(t + n)) from the -R column
-            } else if (hi == lo) {
-                col = lo, bw = 0.0;          // single slot: the neighbour column is read with weight zero
-            } else if (hi == lo + 1) {
-                col = lo;
-            } else {
-                return unsupported("interpolation slots are not adjacent");
-            }
-            const double cg = static_cast<double>(cc) * pow(q.gamma, static_cast<double>(n));
-            TsEntry& t = q.ent[total++];
-            t.off = static_cast<uint32_t>((static_cast<int64_t>(col) * q.pitch + n - 1) * 4);
-            t.wlo = static_cast<float>(a * cg), t.whi = static_cast<float>(bw * cg);
-            t.n = n;
-            ++h.cnt;
-            csum += cc;
-            h.maxn = n > h.maxn ? n : h.maxn;
-        }
-        h.rscale = static_cast<float>(csum * static_cast<double>(p.tab.inv_c));
-    }
+    // ---- per-horizon launch constants: resolved once by ppo_tvf_tables_build, copied from the host mirror
+    if (p.tab.tslab_offset_words <= 0) return unsupported("tables carry no launch constants for this kernel");
+    const int32_t* hdr = static_cast<const int32_t*>(p.tab.host_blob) + p.tab.tslab_offset_words;
+    if (hdr[0] != kTsConstMagic || hdr[1] < 0)
+        return unsupported("more than 128 horizons / 1024 entries, or interpolation slots that are not adjacent");
+    if (hdr[2] != q.pitch || hdr[3] != V) return unsupported("launch constants were built for another shape");
+    const int total = hdr[1];
+    memcpy(q.hz, hdr + 4, static_cast<size_t>(K) * sizeof(TsHorizon));
+    memcpy(q.ent, hdr + 4 + 4 * K, static_cast<size_t>(total) * sizeof(TsEntry));
     q.n_ent = total;
 
     int dev = 0, max_smem = 0;
@@ -703,14 +666,19 @@ int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsign
     const uint32_t ent_bytes = ts_align(static_cast<uint32_t>(total > 0 ? total : 1) * 16u, 128);
     const uint32_t hz_bytes = ts_align(static_cast<uint32_t>(K) * 16u, 128);
     const uint32_t rt_bytes = ts_align(2u * q.rt_words * 4u, 128);
-    const uint32_t fr_bytes = ts_align(static_cast<uint32_t>(V) * 4u, 128);
-    const uint32_t bar_bytes = (8u + kTsMaxChunks + kTsMaxSteps + 4 + 2) * 8u;
-    const uint32_t fixed = wt_bytes + ot_bytes + ent_bytes + hz_bytes + 2 * rt_bytes + fr_bytes + bar_bytes;
+    const uint32_t fr_bytes = ts_align(2u * static_cast<uint32_t>(V) * 4u, 128);
+    const uint32_t bar_bytes = (8u + 2 * kTsMaxChunks + 2 * kTsMaxSteps + 4 + 2) * 8u;
+    const uint32_t rest = ot_bytes + ent_bytes + hz_bytes + 2 * rt_bytes + fr_bytes + bar_bytes;
+    // two slabs when they fit beside two staging chunks: the next env is transposed while this one is evaluated
+    // (with one slab the replacement is in place, which stalls when the n-step window is as long as the rollout)
+    q.nslab = (2 * wt_bytes + rest + 2 * chunk <= static_cast<uint32_t>(max_smem)) ? 2 : 1;
+    q.slab_bytes = wt_bytes;
+    const uint32_t fixed = q.nslab * wt_bytes + rest;
     int nstage = 0;
     while (nstage < 4 && fixed + static_cast<uint32_t>(nstage + 1) * chunk <= static_cast<uint32_t>(max_smem)) ++nstage;
     if (nstage < 2) return unsupported("the transposed env slab does not fit in shared memory");
     q.nstage = nstage;
-    q.off_stage = wt_bytes;
+    q.off_stage = q.nslab * wt_bytes;
     q.off_ot = q.off_stage + static_cast<uint32_t>(nstage) * chunk;
     q.off_ent = q.off_ot + ot_bytes;
     q.off_hz = q.off_ent + ent_bytes;

@@ -27,7 +27,8 @@ class _CTables(ctypes.Structure):
                 ("tail_cwlo", ctypes.c_void_p), ("tail_cwhi", ctypes.c_void_p),
                 ("gpow", ctypes.c_void_p), ("inv_c", ctypes.c_float), ("tail_pitch", ctypes.c_int32),
                 ("tailT_idx", ctypes.c_void_p), ("tailT_cwlo", ctypes.c_void_p), ("tailT_cwhi", ctypes.c_void_p),
-                ("host_blob", ctypes.c_void_p), ("dev_blob", ctypes.c_void_p), ("gamma", ctypes.c_double)]
+                ("host_blob", ctypes.c_void_p), ("dev_blob", ctypes.c_void_p), ("gamma", ctypes.c_double),
+                ("tslab_offset_words", ctypes.c_int64)]
 
 
 class _CLayout(ctypes.Structure):
@@ -121,6 +122,7 @@ def _upload_tables(tabs, device):
         c.n_entries, c.nmax, c.inv_c = tabs.n_entries, tabs.nmax, float(tabs.inv_c)
         c.tail_pitch, c.gamma = tabs.layout.tail_pitch, tabs.layout.gamma
         c.host_blob, c.dev_blob = tabs.host.data_ptr(), base
+        c.tslab_offset_words = int(tabs.layout.offset_words[15])
         return c, (blob, tabs.host)
     parts = [tabs.ent_n, tabs.ent_cnt, tabs.ent_idx, tabs.ent_wlo, tabs.ent_whi, tabs.ent_g,
              tabs.tail_idx, tabs.tail_wlo, tabs.tail_whi, tabs.tail_cwlo, tabs.tail_cwhi, tabs.gpow]
