@@ -276,6 +276,12 @@ int ppo_rediscount_horizons(const float* values, int64_t rows, int64_t row_strid
 int ppo_horizon_interpolate(const double* host_horizons, int64_t n_val, const float* values, int64_t rows,
                             int64_t row_stride, const double* targets, double* out, void* stream);
 
+/* Development aid: with the environment variable PPO_TVF_DEBUG bit 64 set, the transposed slab kernel records
+ * globaltimer stamps (ns) of its first CTA at ten hand-off points (start, shared memory initialised, first R / lim
+ * tables, first chunk / first env in the slab, first step starts, first env done, last step starts, consumers done,
+ * last store done); this call synchronises the device and copies the 16 slots of the last such launch. */
+int ppo_tvf_debug_times(unsigned long long* out16);
+
 /* The kernel the last successful ppo_tvf_targets call of this thread launched: a ppo_tvf_path value (never AUTO),
  * plus 0x100 when the statistics of the longest horizon were fused into that launch (no second kernel) and 0x200
  * when the value estimate of ppo_tvf_targets_ex was. */

@@ -58,9 +58,19 @@ struct TsParams {
     double* partials;  // [grid][8] per-CTA statistics of the longest horizon (want_stats)
     unsigned int* ticket;
     double* stats;
-    TsHorizon hz[kTsMaxK];
-    TsEntry ent[kTsMaxEntries];
+    const TsHorizon* hz;  // [K] device copies of the launch constants (inside the packed table blob)
+    const TsEntry* ent;   // [n_ent]
 };
+
+// development: globaltimer stamps of CTA 0 at a few hand-off points (PPO_TVF_DEBUG bit 64), read by ppo_tvf_debug_times
+__device__ unsigned long long g_ts_times[16];
+__device__ __forceinline__ void ts_stamp(const TsParams& q, int slot) {
+    if ((q.dbg & 64) && blockIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        g_ts_times[slot] = t;
+    }
+}
 
 template <int IMM>
 __device__ __forceinline__ float ts_ldsi(uint32_t addr) {
@@ -177,6 +187,27 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
     const int nenv = static_cast<int>(q.env_base + (bidx < q.env_rem ? 1 : 0));
     const int64_t env0 = bidx * q.env_base + (bidx < q.env_rem ? bidx : q.env_rem);
 
+    if (threadIdx.x == 0) ts_stamp(q, 0);  // kernel start
+    // The reward / terminal columns of the first env are requested before anything else: the first R / lim tables
+    // gate the whole pipeline fill, and these strided loads are pure latency.
+    float rr[kTsMaxChunks];
+    uint32_t dw[kTsMaxChunks];  // raw terminal words (nothing depends on the loads until the scan itself)
+    auto load_columns = [&](int e) {
+        const int64_t env = env0 + e;
+#pragma unroll
+        for (int i = 0; i < kTsMaxChunks; ++i) {
+            const int row = lane * NC + i;
+            rr[i] = 0.f, dw[i] = 1u;  // rows past the rollout: reward 0, "terminal" (R = 0, lim = 0)
+            if (i < NC && row < N) {
+                rr[i] = __ldg(p.rewards + static_cast<int64_t>(row) * p.r_rs + env);
+                const int64_t di = static_cast<int64_t>(row) * p.d_rs + env;
+                if (p.done_kind == PPO_DONE_U8) dw[i] = __ldg(static_cast<const unsigned char*>(p.dones) + di);
+                else if (p.done_kind == PPO_DONE_F32) dw[i] = __float_as_uint(__ldg(static_cast<const float*>(p.dones) + di));
+                else dw[i] = 0u;
+            }
+        }
+    };
+    if (warp == kTsConsumers + kTsXform && nenv > 0) load_columns(0);
     if (threadIdx.x == 0) {
         for (int i = 0; i < 4; ++i) mbar_init(&sfull[i], 1), mbar_init(&sempty[i], kTsXform);
         for (int i = 0; i < 2 * kTsMaxChunks; ++i) mbar_init(&wfull[i], kTsXform);
@@ -191,13 +222,14 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
     for (uint32_t i = threadIdx.x * 16u; i < q.off_bar; i += blockDim.x * 16u)
         *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    // per-horizon launch constants: parameter bank -> shared memory (read by the consumers as broadcasts)
+    // per-horizon launch constants: table blob -> shared memory (read by the consumers as broadcasts)
     for (int i = threadIdx.x; i < q.n_ent; i += blockDim.x)
-        *reinterpret_cast<uint4*>(smem + q.off_ent + i * 16) = *reinterpret_cast<const uint4*>(&q.ent[i]);
+        *reinterpret_cast<uint4*>(smem + q.off_ent + i * 16) = __ldg(reinterpret_cast<const uint4*>(q.ent) + i);
     for (int i = threadIdx.x; i < K; i += blockDim.x)
-        *reinterpret_cast<uint4*>(smem + q.off_hz + i * 16) = *reinterpret_cast<const uint4*>(&q.hz[i]);
+        *reinterpret_cast<uint4*>(smem + q.off_hz + i * 16) = __ldg(reinterpret_cast<const uint4*>(q.hz) + i);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0) ts_stamp(q, 1);  // shared memory initialised
 
     if (warp == kTsConsumers + kTsXform + 2) {
         // ------------------------------------------------------------------ TMA producer
@@ -243,24 +275,18 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
             }
         }
         bulk_wait_all();
+        if (lane == 0) ts_stamp(q, 9);  // last store complete
     } else if (warp == kTsConsumers + kTsXform) {
         // ------------------------------------------------------------------ scan warp: R(t) and lim(t) per env
         const int RPL = NC;  // rows per lane, lane l owns rows [l * RPL, (l + 1) * RPL)
         const double gamma = q.gamma;
         for (int e = 0; e < nenv; ++e) {
             const uint32_t par = static_cast<uint32_t>(e & 1);
-            const int64_t env = env0 + e;
-            float rr[kTsMaxChunks];
+            if (e > 0) load_columns(e);
             bool dn[kTsMaxChunks];
 #pragma unroll
-            for (int i = 0; i < kTsMaxChunks; ++i) {
-                const int row = lane * RPL + i;
-                rr[i] = 0.f, dn[i] = true;  // rows past the rollout: reward 0, "terminal" (R = 0, lim = 0)
-                if (i < RPL && row < N) {
-                    rr[i] = __ldg(p.rewards + static_cast<int64_t>(row) * p.r_rs + env);
-                    dn[i] = done_at(p.dones, p.done_kind, static_cast<int64_t>(row) * p.d_rs + env);
-                }
-            }
+            for (int i = 0; i < kTsMaxChunks; ++i)
+                dn[i] = p.done_kind == PPO_DONE_F32 ? (__uint_as_float(dw[i]) != 0.f) : (dw[i] != 0u);
             // segment maps: R_start = a + bc * R_next;  lim_start = hd ? c : c + lim_next
             double a = 0.0, bc = 1.0;
             int c = 0;
@@ -305,6 +331,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&rfull[par]);
+            if (lane == 0 && e == 0) ts_stamp(q, 2);  // first R / lim tables ready
         }
     } else if (warp >= kTsConsumers) {
         // ------------------------------------------------------------------ transform warps
@@ -408,6 +435,8 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                     mbar_arrive(&sempty[slot]);
                     mbar_arrive(&wfull[sl * kTsMaxChunks + c]);
                 }
+                if (lane == 0 && xw == 0 && e == 0 && c == 0) ts_stamp(q, 3);       // first chunk transposed
+                if (lane == 0 && xw == 0 && e == 0 && c == NC - 1) ts_stamp(q, 4);  // first env transposed
                 if (++slot == q.nstage) slot = 0, spar ^= 1;
             }
             if (lane == 0) mbar_arrive(&rempty[par]);
@@ -438,6 +467,8 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                     mbar_wait(&wfull[sl * kTsMaxChunks + waited], use_par);
                     ++waited;
                 }
+                if (lane == 0 && cw == 0 && e == 0 && s == 0) ts_stamp(q, 5);  // consumers start the first step
+                if (lane == 0 && cw == 0 && e == nenv - 1 && s == NS - 1) ts_stamp(q, 7);  // ... the last step
                 const int lim0 = ts_lds_s32(lt + static_cast<uint32_t>(t0) * 4u);
                 const int lim1 = ts_lds_s32(lt + static_cast<uint32_t>(t1) * 4u);
                 const float R0 = ts_lds(rt + static_cast<uint32_t>(t0) * 4u);
@@ -537,7 +568,9 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                 }
             }
             if (lane == 0) mbar_arrive(&rempty[par]);
+            if (lane == 0 && cw == 0 && e == 0) ts_stamp(q, 6);  // first env evaluated
         }
+        if (lane == 0 && cw == 0) ts_stamp(q, 8);  // consumers done
         if (q.want_stats) {
             // per-CTA record: the staging ring is idle by now (every chunk has been transposed and consumed)
             asm volatile("bar.sync 1, %0;" ::"n"(kTsConsumers * 32) : "memory");
@@ -646,15 +679,17 @@ int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsign
         q.dbg = d ? atoi(d) : 0;
     }
 
-    // ---- per-horizon launch constants: resolved once by ppo_tvf_tables_build, copied from the host mirror
+    // ---- per-horizon launch constants: resolved once by ppo_tvf_tables_build; the header is checked on the host
+    // mirror, the kernel reads the device copy
     if (p.tab.tslab_offset_words <= 0) return unsupported("tables carry no launch constants for this kernel");
     const int32_t* hdr = static_cast<const int32_t*>(p.tab.host_blob) + p.tab.tslab_offset_words;
     if (hdr[0] != kTsConstMagic || hdr[1] < 0)
         return unsupported("more than 128 horizons / 1024 entries, or interpolation slots that are not adjacent");
     if (hdr[2] != q.pitch || hdr[3] != V) return unsupported("launch constants were built for another shape");
     const int total = hdr[1];
-    memcpy(q.hz, hdr + 4, static_cast<size_t>(K) * sizeof(TsHorizon));
-    memcpy(q.ent, hdr + 4 + 4 * K, static_cast<size_t>(total) * sizeof(TsEntry));
+    const int32_t* dhdr = static_cast<const int32_t*>(p.tab.dev_blob) + p.tab.tslab_offset_words;
+    q.hz = reinterpret_cast<const TsHorizon*>(dhdr + 4);
+    q.ent = reinterpret_cast<const TsEntry*>(dhdr + 4 + 4 * K);
     q.n_ent = total;
 
     int dev = 0, max_smem = 0;
@@ -727,3 +762,10 @@ int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsign
 }
 
 }  // namespace ppo
+
+// development aid: the stamps of the last launch with PPO_TVF_DEBUG bit 64 (nanoseconds, CTA 0)
+extern "C" int ppo_tvf_debug_times(unsigned long long* out16) {
+    PPO_CUDA(cudaDeviceSynchronize());
+    PPO_CUDA(cudaMemcpyFromSymbol(out16, ppo::g_ts_times, sizeof(unsigned long long) * 16));
+    return PPO_OK;
+}
