@@ -14,3 +14,6 @@ python tools/prof_tvf.py 4096 advanced8 tslab > gpurun_out/plain_tslab.log 2>&1 
 ncu --set full --clock-control none --import-source on -k regex:tvf_tslab -s 2 -c 1 -o gpurun_out/tslab_4096_adv \
     python tools/prof_tvf.py 4096 advanced8 tslab > gpurun_out/ncu_tslab.log 2>&1
 tail -3 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/smoke.log; cat gpurun_out/bench.json; cat gpurun_out/bench_ref.json
+python tools/prof_gae.py 32768 > gpurun_out/plain_gae.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:gae_tile -s 2 -c 1 -o gpurun_out/gae_tile_32768 \
+    python tools/prof_gae.py 32768 > gpurun_out/ncu_gae.log 2>&1
