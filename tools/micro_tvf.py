@@ -4,11 +4,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from ppo_b200 import returns_truncated as rt, synthetic, _lib, _device as dev, _tvf_tables
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
 
 def heads():
-    import oracle
-    return oracle.get_value_head_horizons(128, 30000)
+    from ppo_b200 import tvf as _tvf_mod
+    return _tvf_mod.get_value_head_horizons(128, 30000)
 
 def main():
     lib = _lib.load()
@@ -27,11 +26,11 @@ def main():
             vs[:, :, 0] = 0
             out = torch.empty((steps, envs, 128), device=device)
             for mode in ("advanced8", "fixed20", "standard8"):
-                import oracle
+                pass
                 if mode == "advanced8":
-                    table = oracle.draw_n_step_samples("exponential", "advanced", hz, steps, 20, 8, seed=1)
+                    table = rt.draw_n_step_samples("exponential", "advanced", hz, steps, 20, 8, seed=1)
                 elif mode == "standard8":
-                    table = oracle.draw_n_step_samples("exponential", "standard", hz, steps, 20, 8, seed=1)
+                    table = rt.draw_n_step_samples("exponential", "standard", hz, steps, 20, 8, seed=1)
                 else:
                     table = np.zeros([128, 1], dtype=np.int32) + 20
                 tabs = rt.build_tables(0.99997, steps, hz, hz, table)

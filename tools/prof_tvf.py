@@ -3,7 +3,7 @@ import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
-import oracle
+from ppo_b200 import tvf as _tvf_mod
 from ppo_b200 import returns_truncated as rt, _lib, _tvf_tables
 
 def main():
@@ -11,7 +11,7 @@ def main():
     mode = sys.argv[2] if len(sys.argv) > 2 else "advanced8"
     path = {"ring": rt.PATH_RING, "tslab": rt.PATH_TSLAB}[sys.argv[3] if len(sys.argv) > 3 else "tslab"]
     lib = _lib.load()
-    hz = oracle.get_value_head_horizons(128, 30000)
+    hz = _tvf_mod.get_value_head_horizons(128, 30000)
     device = torch.device("cuda")
     g = torch.Generator(device="cuda"); g.manual_seed(0)
     r = torch.randint(-1, 3, (steps, envs), device=device, generator=g).float()
@@ -19,7 +19,7 @@ def main():
     vs = torch.randn((steps + 1, envs, 128), device=device, generator=g) * 0.4 + 0.1
     out = torch.empty((steps, envs, 128), device=device)
     if mode == "advanced8":
-        table = oracle.draw_n_step_samples("exponential", "advanced", hz, steps, 20, 8, seed=1)
+        table = rt.draw_n_step_samples("exponential", "advanced", hz, steps, 20, 8, seed=1)
     else:
         table = np.zeros([128, 1], dtype=np.int32) + 20
     tabs = rt.build_tables(0.99997, steps, hz, hz, table)

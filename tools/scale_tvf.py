@@ -3,16 +3,16 @@ import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
-import oracle
+from ppo_b200 import tvf as _tvf_mod
 from ppo_b200 import returns_truncated as rt, _lib
 
 def main():
     lib = _lib.load()
-    hz = oracle.get_value_head_horizons(128, 30000)
+    hz = _tvf_mod.get_value_head_horizons(128, 30000)
     device = torch.device("cuda")
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
     for steps in (128, 256):
-        table = oracle.draw_n_step_samples("exponential", "advanced", hz, steps, 20, 8, seed=1)
+        table = rt.draw_n_step_samples("exponential", "advanced", hz, steps, 20, 8, seed=1)
         tabs = rt.build_tables(0.99997, steps, hz, hz, table)
         ctab, blob = rt._upload_tables(tabs, device)
         for per_sm in (1, 2, 4, 8, 16):
@@ -46,13 +46,13 @@ def stamps():
     os.environ["PPO_TVF_DEBUG"] = "64"
     lib = _lib.load()
     import ctypes as C
-    hz = oracle.get_value_head_horizons(128, 30000)
+    hz = _tvf_mod.get_value_head_horizons(128, 30000)
     device = torch.device("cuda")
     names = ["start", "smem init", "R/lim ready", "chunk 0 in slab", "env 0 in slab", "consumers start", "env 0 done",
              "last step starts", "consumers done", "last store done"]
     for steps, per_sm in ((128, 1), (128, 8), (256, 1), (256, 8)):
         envs = 148 * per_sm
-        table = oracle.draw_n_step_samples("exponential", "advanced", hz, steps, 20, 8, seed=1)
+        table = rt.draw_n_step_samples("exponential", "advanced", hz, steps, 20, 8, seed=1)
         tabs = rt.build_tables(0.99997, steps, hz, hz, table)
         ctab, blob = rt._upload_tables(tabs, device)
         r = torch.randint(-1, 3, (steps, envs), device=device).float()
