@@ -13,3 +13,5 @@ All arithmetic on rollout data runs in hand-written sm_100a CUDA kernels behind 
 without a CUDA device every call raises.
 """
 __version__ = "0.1.0"
+
+from ._device import pin_numpy  # noqa: E402,F401  (page-lock persistent NumPy rollout buffers once)

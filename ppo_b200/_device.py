@@ -69,6 +69,56 @@ def workspace(nbytes, device):
     return ws
 
 
+_registered = {}
+
+
+def pin_numpy(array):
+    """Page-lock the memory of a NumPy rollout buffer in place (``cudaHostRegister``) and return it unchanged.
+
+    The reference keeps its rollout in persistent NumPy arrays (``rl/rollout.py:646-680``, ``rl/tvf.py:27-30``);
+    registering them once lets every later call move them with asynchronous, full-rate PCIe copies (and the
+    env-blocked pipeline of ``returns_truncated``) instead of pageable staging.  The registration is dropped
+    when the array's memory owner is garbage-collected.  Only C-contiguous arrays that own their memory (or
+    views whose base does) make sense here; call it on the base buffers at start-up."""
+    import weakref
+    require_cuda()
+    owner = array
+    while isinstance(getattr(owner, "base", None), np.ndarray):
+        owner = owner.base
+    ptr, nbytes = owner.ctypes.data, owner.nbytes
+    if nbytes == 0 or ptr in _registered:
+        return array
+    rt = torch.cuda.cudart()
+    err = rt.cudaHostRegister(ptr, nbytes, 0)
+    if int(err) != 0:
+        raise RuntimeError(f"cudaHostRegister failed with error {int(err)} for {nbytes} bytes at {ptr:#x}")
+    _registered[ptr] = nbytes
+
+    def release(p=ptr):
+        if _registered.pop(p, None) is not None:
+            try:
+                torch.cuda.cudart().cudaHostUnregister(p)
+            except Exception:
+                pass
+    weakref.finalize(owner, release)
+    return array
+
+
+def pinned_tensor_of(x):
+    """CPU tensor view of ``x`` when its memory is page-locked (a pinned tensor, or a NumPy array registered with
+    :func:`pin_numpy`), else None."""
+    if isinstance(x, torch.Tensor):
+        return x if x.device.type == "cpu" and x.is_pinned() else None
+    if isinstance(x, np.ndarray) and x.flags.writeable and torch.cuda.is_available():
+        owner = x
+        while isinstance(getattr(owner, "base", None), np.ndarray):
+            owner = owner.base
+        if owner.ctypes.data in _registered:
+            t = torch.from_numpy(x)
+            return t if t.is_pinned() else None
+    return None
+
+
 def like_input(result, wants_numpy):
     """Reference semantics: NumPy in -> NumPy out; CUDA tensor in -> CUDA tensor out."""
     if wants_numpy:

@@ -148,6 +148,24 @@ def _launch(gamma, rewards, dones, required_horizons, value_sample_horizons, val
     device = dev.require_cuda()
     lib = _lib.load()
     np_like = dev.is_numpy_like(rewards)
+    # Host buffers that are page-locked (pinned tensors, or NumPy arrays registered with ppo_b200.pin_numpy): the
+    # env-blocked pipeline moves them at the PCIe rate of both directions together.
+    pinned_vs = dev.pinned_tensor_of(value_samples)
+    if (pinned_vs is not None and not numpy_tables and value_out is None and rewards.shape[0] > 0
+            and len(required_horizons) > 0 and pinned_vs.dtype == torch.float32 and pinned_vs.dim() == 3
+            and pinned_vs.stride(2) == 1 and pinned_vs.stride(1) == pinned_vs.shape[2] and not keep_on_device):
+        out_host = torch.empty((rewards.shape[0], rewards.shape[1], len(required_horizons)), dtype=torch.float32,
+                               pin_memory=True)
+        stats = _launch_host_blocks(gamma, rewards, dones,
+                                    np.asarray(required_horizons.cpu() if isinstance(required_horizons, torch.Tensor)
+                                               else required_horizons),
+                                    np.asarray(value_sample_horizons.cpu() if isinstance(value_sample_horizons, torch.Tensor)
+                                               else value_sample_horizons),
+                                    pinned_vs, n_step_samples, use_log_interpolation, out_host, path=path,
+                                    with_stats=with_stats)
+        torch.cuda.current_stream().synchronize()
+        res = out_host.numpy() if np_like else out_host
+        return (res, stats) if with_stats else res
     r = dev.env_contiguous(dev.to_device(rewards, torch.float32, device))
     steps, envs = r.shape
     req = np.asarray(required_horizons.cpu() if isinstance(required_horizons, torch.Tensor) else required_horizons)

@@ -133,3 +133,23 @@ def test_host_blocks_pipeline_equals_one_launch(steps, envs, heads, block):
     rt._launch_host_blocks(0.9999, r, d, hz, hz, vs, table, False, out2, block_envs=block, with_stats=False)
     torch.cuda.current_stream().synchronize()
     assert torch.equal(out, out2)
+
+
+def test_registered_numpy_buffers_take_the_pipeline():
+    """ppo_b200.pin_numpy: a persistent NumPy value buffer is page-locked in place once; the drop-in call then runs
+    the env-blocked pipeline and still returns a plain NumPy array with the same bits."""
+    import ppo_b200
+    from ppo_b200 import _device as dev
+    steps, envs = 64, 400
+    hz = oracle.get_value_head_horizons(64, 3000)
+    r, d, _ = synthetic.rollout(steps, envs, seed=9)
+    vs = synthetic.value_samples(steps, envs, len(hz), seed=9)
+    kw = dict(n_step=12, max_samples=6, seed=3)
+    plain = rt.get_return_estimate("exponential", "advanced", 0.9999, r, d, hz, hz, vs, **kw)
+    assert dev.pinned_tensor_of(vs) is None
+    assert ppo_b200.pin_numpy(vs) is vs and dev.pinned_tensor_of(vs) is not None
+    piped = rt.get_return_estimate("exponential", "advanced", 0.9999, r, d, hz, hz, vs, **kw)
+    assert isinstance(piped, np.ndarray) and piped.dtype == np.float32 and np.array_equal(piped, plain)
+    view = vs[:, :200]  # a view that is not env-contiguous per row falls back to the plain path, same result
+    assert np.array_equal(rt.get_return_estimate("exponential", "advanced", 0.9999, r[:, :200], d[:, :200], hz, hz,
+                                                 view, **kw), plain[:, :200])
