@@ -190,3 +190,30 @@ def test_error_behaviour(golden):
     b['required_horizons'] = np.asarray([5000], dtype=np.int32)  # beyond the last value horizon: :157 IndexError
     with pytest.raises(IndexError):
         rt._calculate_sampled_return_multi_fast(n_step_list=[4], **b)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_slab_kernels_fuzz_against_the_generic_kernel(seed):
+    """Random shapes (steps, envs, horizon counts 32 / 64 / 96 / 128, sample counts, terminal rates, random horizon
+    sets): both slab kernels against the generic kernel, which the other tests hold to the oracle."""
+    rng = np.random.RandomState(500 + seed)
+    steps = int(rng.randint(2, 257))
+    envs = int(rng.choice([1, 3, 50, 149, 300, 700]))
+    n_val = int(rng.choice([32, 64, 128]))
+    n_req = int(rng.choice([32, 64, 96, 128]))
+    vsh = np.unique(np.concatenate([[0], rng.randint(1, int(rng.choice([200, 5000, 30000])), size=4 * n_val)]))[:n_val]
+    while len(vsh) < n_val:  # tiny ranges: pad with consecutive horizons
+        vsh = np.unique(np.concatenate([vsh, vsh[-1:] + 1 + np.arange(n_val - len(vsh))]))
+    req = np.sort(rng.randint(0, vsh[-1] + 1, size=n_req))
+    c = int(rng.randint(1, 9))
+    table = rng.randint(1, steps + 1, size=[n_req, c])
+    r = rng.randint(-1, 3, size=[steps, envs]).astype(np.float32)
+    d = rng.rand(steps, envs) < float(rng.choice([0.0, 0.03, 0.3]))
+    vs = rng.normal(0.1, 0.4, size=[steps + 1, envs, n_val]).astype(np.float32)
+    use_log = bool(seed % 2)
+    ref = rt._calculate_sampled_return_multi_fast(0.9997, r, d, req, vsh, vs, n_step_samples=table,
+                                                  use_log_interpolation=use_log, path=rt.PATH_GENERIC)
+    for path in (rt.PATH_TSLAB, rt.PATH_RING):
+        got = rt._calculate_sampled_return_multi_fast(0.9997, r, d, req, vsh, vs, n_step_samples=table,
+                                                      use_log_interpolation=use_log, path=path)
+        assert rel_err(got, ref) <= TOL, (path, steps, envs, n_val, n_req, c)

@@ -107,3 +107,31 @@ def test_native_builder_errors(built_library):
         rt.build_tables(0.99, 10, hz, hz, np.zeros([16, 2], dtype=np.int32))
     with pytest.raises(IndexError):
         rt.build_tables(0.99, 10, np.asarray([500]), hz, np.ones([1, 1], dtype=np.int32))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_native_builder_fuzz(built_library, seed):
+    """Random horizon sets (duplicates, zeros, dense and sparse), sample counts and rollout lengths: the C++ builder
+    and the NumPy construction agree bit for bit, and every horizon's multiplicities sum to the sample count."""
+    from ppo_b200 import returns_truncated as rt
+    rng = np.random.RandomState(100 + seed)
+    steps = int(rng.randint(1, 300))
+    n_val = int(rng.choice([4, 8, 32, 64, 128]))
+    vsh = np.sort(rng.randint(0, int(rng.choice([20, 300, 40000])), size=n_val))
+    vsh[0] = 0
+    if seed % 3 == 0:
+        vsh = np.unique(vsh)  # strictly ascending variant
+    n_req = int(rng.randint(1, 130))
+    req = np.sort(rng.randint(0, vsh[-1] + 1, size=n_req))
+    c = int(rng.randint(1, 12))
+    table = rng.randint(1, steps + 1, size=[n_req, c])
+    use_log = bool(seed % 2)
+    ref = T.build(0.9997, steps, req, vsh, table, use_log)
+    nat = rt.build_tables(0.9997, steps, req, vsh, table, use_log)
+    assert (nat.n_entries, nat.nmax) == (ref.n_entries, ref.nmax)
+    for name in ["ent_n", "ent_cnt", "ent_idx", "ent_wlo", "ent_whi", "ent_g", "tail_idx", "tail_wlo", "tail_whi",
+                 "tail_cwlo", "tail_cwhi", "gpow"]:
+        want = np.ascontiguousarray(getattr(ref, name)).reshape(-1)
+        assert np.array_equal(nat.table(name)[:want.size].view(np.int32), want.view(np.int32)), (name, seed)
+    cnt = nat.table("ent_cnt")[:ref.n_entries * n_req].reshape(ref.n_entries, n_req)
+    assert np.array_equal(cnt.sum(axis=0), np.where(req > 0, c, 0))
