@@ -238,16 +238,20 @@ def other_configs(device, peak_gbs, iters=40):
     st = torch.zeros(_lib.STATS_LEN, dtype=torch.float64, device=device)
     ws = torch.zeros(int(lib.ppo_gae_workspace_bytes(a)), dtype=torch.uint8, device=device)
 
+    fused = []
+
     def c2(i):
         r, d, v, adv, ret, norm = bufs[i % sets]
-        _lib.check(lib.ppo_gae(r.data_ptr(), a, v.data_ptr(), a, 1, v[n].data_ptr(), 1, d.data_ptr(), _lib.DONE_U8, a,
-                               n, a, GAMMA, LAMBDA_POLICY, LAMBDA_VALUE, adv.data_ptr(), ret.data_ptr(),
-                               st.data_ptr(), ws.data_ptr(), ws.numel(), stream), "ppo_gae")
-        _lib.check(lib.ppo_adv_normalize(adv.data_ptr(), n * a, st.data_ptr(), 1e-8, 0.0, norm.data_ptr(), stream),
-                   "ppo_adv_normalize")
+        rc = lib.ppo_gae_normalized(r.data_ptr(), a, v.data_ptr(), a, 1, v[n].data_ptr(), 1, d.data_ptr(), _lib.DONE_U8,
+                                    a, n, a, GAMMA, LAMBDA_POLICY, LAMBDA_VALUE, 1e-8, 0.0, adv.data_ptr(),
+                                    ret.data_ptr(), norm.data_ptr(), st.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+        _lib.check(rc, "ppo_gae_normalized")
+        fused.append(rc)
     out["c2_gae_tdlambda_stats_advnorm_256x4096"] = dict(
-        timed(c2, n * a * 21, n * a), note="two launches; 21 B per (t, env): r 4 + V 4 + done 1 in, raw adv 4 + "
-        "TD(lambda) return 4 + normalised adv 4 out; launch latency is a large part of the time at 22 MB")
+        timed(c2, n * a * 21, n * a), launches_per_pass=1 if fused and fused[-1] == 1 else 2,
+        note="GAE + TD(lambda) + statistics + advantage normalisation in one cooperative launch; 21 B per (t, env): "
+        "r 4 + V 4 + done 1 in, raw adv 4 + TD(lambda) return 4 + normalised adv 4 out; launch latency is a large "
+        "part of the time at 22 MB")
     del bufs
 
     # ---- c3: TVF targets 128 steps x 1024 envs x 128 horizons, exponential / advanced 8 samples and fixed n-step

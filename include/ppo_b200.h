@@ -102,6 +102,22 @@ int ppo_gae(const float* rewards, int64_t reward_row_stride,
             void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
+ * ppo_gae followed by ppo_adv_normalize on the raw advantages (single GPU: no moment exchange in between), as ONE
+ * cooperative launch when the whole grid of the tile kernel is resident: every CTA keeps its advantages in shared
+ * memory, waits for the folded statistics and writes the normalised values itself.  Returns 1 when fused, 0 when it
+ * fell back to the two launches, < 0 on error.  stats, adv_out and norm_out are required; workspace as for ppo_gae
+ * (zero-initialised, left zero).
+ */
+int ppo_gae_normalized(const float* rewards, int64_t reward_row_stride,
+                       const float* values, int64_t value_row_stride, int64_t value_env_stride,
+                       const float* final_value, int64_t final_env_stride,
+                       const void* dones, int done_kind, int64_t done_row_stride,
+                       int64_t steps, int64_t envs,
+                       double gamma, double lamb_adv, double lamb_ret, double eps, double clip,
+                       float* adv_out, float* ret_out, float* norm_out, double* stats,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
  * Batch advantage normalisation: out = clip((x - mean) / (std + eps), -clip, +clip), population std.
  * Replaces the inline NumPy at rl/rollout.py:1887-1897.  `stats` is a device record as written by
  * ppo_gae (after an optional cross-GPU sum of COUNT / ADV_SUM / ADV_SUMSQ).  clip <= 0 disables

@@ -35,6 +35,9 @@ _SIGNATURES = {
     "ppo_gae_workspace_bytes": (c_i64, [c_i64]),
     "ppo_gae": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_int, c_i64,
                         c_i64, c_i64, c_dbl, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "ppo_gae_normalized": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_int, c_i64,
+                                   c_i64, c_i64, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                   c_i64, c_ptr]),
     "ppo_adv_normalize": (c_int, [c_ptr, c_i64, c_ptr, c_dbl, c_dbl, c_ptr, c_ptr]),
     "ppo_moments": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
     "ppo_tvf_workspace_bytes": (c_i64, [c_i64, c_i64]),

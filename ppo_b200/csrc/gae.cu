@@ -82,7 +82,8 @@ struct ThreadStats {
 
 // Combine per-thread statistics into one record per CTA, then let the last CTA to finish fold all
 // CTA records in index order (deterministic, no float atomics) into io.stats.
-__device__ void publish_stats(const ThreadStats& ts, const ScanStatsIo& io, double (*red)[PPO_STATS_LEN]) {
+__device__ void publish_stats(const ThreadStats& ts, const ScanStatsIo& io, double (*red)[PPO_STATS_LEN],
+                              unsigned int* ready = nullptr) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
     double n = warp_sum_f64(ts.n);
@@ -160,6 +161,11 @@ __device__ void publish_stats(const ThreadStats& ts, const ScanStatsIo& io, doub
                 tot = is_min ? fmin(tot, x) : is_max ? fmax(tot, x) : tot + x;
             }
             io.stats[j] = j <= PPO_STAT_RET_MAX ? tot : 0.0;
+            __threadfence();
+        }
+        if (ready) {  // the folded record is visible: release the CTAs that wait for it
+            __syncthreads();
+            if (threadIdx.x == 0) atomicExch(ready, 1u);
         }
     }
     if (threadIdx.x == 0) *io.ticket = 0u;
@@ -290,11 +296,23 @@ __global__ void __launch_bounds__(kScanThreads) gae_kernel(const GaeParams p) {
 // and the two recurrences merged when lambda_policy == lambda_value.
 constexpr int kTileChunks = 8;
 
+__device__ __forceinline__ float norm_one(float x, float mean, float denom, float clip) {
+    float y = __fdiv_rn(__fsub_rn(x, mean), denom);  // rl/rollout.py:1891
+    if (clip > 0.f) y = fminf(fmaxf(y, -clip), clip);  // rl/rollout.py:1895-1896
+    return y;
+}
+
+
 struct GaeTileParams {
     GaeParams g;
     int chunk_len;      // rows per time chunk (odd when EW = 16: the two chunks of a warp then hit different banks)
     int vec_r, vec_v, vec_d;  // bytes per asynchronous copy: 16 / 4, and 1 (synchronous byte loads) for the terminals
     int same_lambda;
+    // fused advantage normalisation (cooperative launch, every CTA resident): the CTAs wait for the folded statistics
+    // and normalise their own tile of advantages out of shared memory
+    float* norm_out;           // [N * A] or nullptr
+    float norm_eps, norm_clip;
+    unsigned int* ready;       // two words: statistics-ready flag, exit counter (both zero between launches)
 };
 
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
@@ -304,7 +322,7 @@ __device__ __forceinline__ void cp_async_4b(uint32_t dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 
-template <int DONE, int EW, bool STATS>
+template <int DONE, int EW, bool STATS, bool NORM = false>
 __global__ void __launch_bounds__(EW * kTileChunks) gae_tile_kernel(const GaeTileParams q) {
     extern __shared__ __align__(16) unsigned char tile[];
     const GaeParams& p = q.g;
@@ -453,10 +471,39 @@ __global__ void __launch_bounds__(EW * kTileChunks) gae_tile_kernel(const GaeTil
             if (p.adv) store_stream(p.adv + static_cast<int64_t>(i) * p.envs + env, a);
             if (p.ret) store_stream(p.ret + static_cast<int64_t>(i) * p.envs + env, t);
             if (STATS) ts.add_no_count(a, t);
+            if (NORM) sr[i * EW + e] = a;  // the reward slot is dead: the raw advantage waits here for the statistics
         }
         ts.n = hi > lo ? static_cast<double>(hi - lo) : 0.0;
     }
-    if (STATS) publish_stats(ts, p.io, red);
+    if (STATS) publish_stats(ts, p.io, red, NORM ? q.ready : nullptr);
+    if (NORM) {
+        // Grid-wide hand-off: the CTA that folds the records raises the flag (publish_stats), everyone else spins on
+        // it -- legal because the launch is cooperative (all CTAs resident).  Then (x - mean) / (std + eps) exactly as
+        // normalize_kernel computes it (rl/rollout.py:1887-1897), from the tile in shared memory.
+        if (threadIdx.x == 0) {
+            while (*reinterpret_cast<volatile unsigned int*>(q.ready) == 0u) __nanosleep(32);
+            __threadfence();
+        }
+        __syncthreads();
+        const double n = __ldcg(p.io.stats + PPO_STAT_COUNT);
+        const double mean64 = __ldcg(p.io.stats + PPO_STAT_ADV_SUM) / n;
+        const double var64 = fmax(__ldcg(p.io.stats + PPO_STAT_ADV_SUMSQ) / n - mean64 * mean64, 0.0);
+        const float mean = static_cast<float>(mean64);
+        const float denom = __fadd_rn(static_cast<float>(sqrt(var64)), q.norm_eps);
+        if (live) {
+            for (int i = hi - 1; i >= lo; --i)
+                store_stream(q.norm_out + static_cast<int64_t>(i) * p.envs + env,
+                             norm_one(sr[i * EW + e], mean, denom, q.norm_clip));
+        }
+        // the last CTA to leave clears the flag and the counter for the next launch
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (atomicAdd(q.ready + 1, 1u) == gridDim.x - 1) {
+                q.ready[0] = 0u;
+                q.ready[1] = 0u;
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -561,12 +608,6 @@ struct NormParams {
     float clip;  // <= 0: no clipping
 };
 
-__device__ __forceinline__ float norm_one(float x, float mean, float denom, float clip) {
-    float y = __fdiv_rn(__fsub_rn(x, mean), denom);  // rl/rollout.py:1891
-    if (clip > 0.f) y = fminf(fmaxf(y, -clip), clip);  // rl/rollout.py:1895-1896
-    return y;
-}
-
 __global__ void __launch_bounds__(256) normalize_kernel(const NormParams p) {
     const double n = p.stats[PPO_STAT_COUNT];
     const double mean64 = p.stats[PPO_STAT_ADV_SUM] / n;
@@ -610,6 +651,20 @@ constexpr int kMomentsMaxBlocks = 1184;  // 8 CTAs of 512 threads per SM would n
 
 template <int DONE, int EW>
 static int launch_gae_tile_variant(const GaeTileParams& q, bool stats, int64_t grid, size_t smem, cudaStream_t s) {
+    if (q.norm_out) {
+        // fused normalisation: every CTA must be resident (they wait for the folded statistics), so the launch is
+        // cooperative and only made when the whole grid fits
+        auto kernel = gae_tile_kernel<DONE, EW, true, true>;
+        PPO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        int per_sm = 0;
+        PPO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, EW * kTileChunks, smem));
+        if (static_cast<int64_t>(per_sm) * sm_count() < grid) return PPO_ERR_UNSUPPORTED;
+        GaeTileParams copy = q;
+        void* args[] = {&copy};
+        PPO_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(static_cast<unsigned>(grid)),
+                                             dim3(EW * kTileChunks), args, smem, s));
+        return PPO_OK;
+    }
     if (stats) {
         PPO_CUDA(cudaFuncSetAttribute(gae_tile_kernel<DONE, EW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
@@ -626,7 +681,7 @@ static int launch_gae_tile_variant(const GaeTileParams& q, bool stats, int64_t g
 // The tile kernel when a whole [N, EW] tile fits in shared memory; PPO_ERR_UNSUPPORTED otherwise (the caller then
 // launches gae_kernel).  `p.io.stats` must already be set when statistics are wanted.
 static int launch_gae_tile(GaeParams p, int done_kind, bool want_stats, void* workspace, int64_t workspace_bytes,
-                           cudaStream_t s) {
+                           cudaStream_t s, float* norm_out = nullptr, float norm_eps = 0.f, float norm_clip = 0.f) {
     const int64_t N = p.steps, A = p.envs;
     if (N > 4096) return PPO_ERR_UNSUPPORTED;
     // A strided value column (one DRAM sector per element) is a latency-bound gather; the register-cached kernel
@@ -671,6 +726,11 @@ static int launch_gae_tile(GaeParams p, int done_kind, bool want_stats, void* wo
         else if (db == 4) q.vec_d = 4;
     }
     q.same_lambda = p.gl_adv == p.gl_ret ? 1 : 0;
+    if (norm_out) {
+        if (!want_stats) return PPO_ERR_UNSUPPORTED;
+        q.norm_out = norm_out, q.norm_eps = norm_eps, q.norm_clip = norm_clip;
+        q.ready = static_cast<unsigned int*>(workspace) + 32;  // bytes 128..135 of the reserved 256-byte header
+    }
 #define PPO_TILE(D)                                                                    \
     (ew == 16 ? launch_gae_tile_variant<D, 16>(q, want_stats, grid, smem, s)           \
               : launch_gae_tile_variant<D, 32>(q, want_stats, grid, smem, s))
@@ -742,6 +802,41 @@ extern "C" int ppo_gae(const float* rewards, int64_t reward_row_stride, const fl
 #undef PPO_LAUNCH_GAE
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;
+}
+
+extern "C" int ppo_gae_normalized(const float* rewards, int64_t reward_row_stride, const float* values,
+                                  int64_t value_row_stride, int64_t value_env_stride, const float* final_value,
+                                  int64_t final_env_stride, const void* dones, int done_kind,
+                                  int64_t done_row_stride, int64_t steps, int64_t envs, double gamma, double lamb_adv,
+                                  double lamb_ret, double eps, double clip, float* adv_out, float* ret_out,
+                                  float* norm_out, double* stats, void* workspace, int64_t workspace_bytes,
+                                  void* stream) {
+    PPO_REQUIRE(stats && norm_out && adv_out, "ppo_gae_normalized: stats, adv_out and norm_out are required");
+    PPO_REQUIRE(steps >= 0 && envs >= 0, "ppo_gae_normalized: negative shape");
+    PPO_REQUIRE(done_kind == PPO_DONE_NONE || done_kind == PPO_DONE_U8 || done_kind == PPO_DONE_F32,
+                "ppo_gae_normalized: unknown done_kind %d", done_kind);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (steps > 0 && envs > 0 && rewards && values && final_value && (done_kind == PPO_DONE_NONE || dones)) {
+        GaeParams p{};
+        p.rewards = rewards, p.r_rs = reward_row_stride;
+        p.values = values, p.v_rs = value_row_stride, p.v_es = value_env_stride;
+        p.final_value = final_value, p.f_es = final_env_stride;
+        p.dones = dones, p.d_rs = done_row_stride;
+        p.steps = steps, p.envs = envs;
+        p.gl_adv = gamma * lamb_adv, p.gl_ret = gamma * lamb_ret;
+        p.gamma32 = static_cast<float>(gamma);
+        p.adv = adv_out, p.ret = ret_out;
+        p.io.stats = stats;
+        // one cooperative launch when the whole grid is resident; PPO_ERR_UNSUPPORTED otherwise
+        if (launch_gae_tile(p, done_kind, true, workspace, workspace_bytes, s, norm_out, static_cast<float>(eps),
+                            clip > 0 ? static_cast<float>(clip) : 0.f) == PPO_OK)
+            return 1;  // fused: one launch
+    }
+    int rc = ppo_gae(rewards, reward_row_stride, values, value_row_stride, value_env_stride, final_value,
+                     final_env_stride, dones, done_kind, done_row_stride, steps, envs, gamma, lamb_adv, lamb_ret,
+                     adv_out, ret_out, stats, workspace, workspace_bytes, stream);
+    if (rc != PPO_OK) return rc;
+    return ppo_adv_normalize(adv_out, steps * envs, stats, eps, clip, norm_out, stream);
 }
 
 extern "C" int ppo_discounted_returns(const float* rewards, int64_t reward_row_stride, const void* dones,

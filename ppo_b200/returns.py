@@ -12,7 +12,9 @@ from . import _lib
 
 
 def _gae_launch(batch_rewards, batch_value, final_value_estimate, batch_terminal, gamma, lamb_adv, lamb_ret,
-                want_adv, want_ret, want_stats):
+                want_adv, want_ret, want_stats, normalize=None):
+    """``normalize=(eps, clip)``: also the batch-normalised advantages (``ppo_gae_normalized``, one launch when the
+    grid is resident); returns ``(adv, ret, norm, stats)`` then."""
     device = dev.require_cuda()
     lib = _lib.load()
     rewards = dev.env_contiguous(dev.to_device(batch_rewards, torch.float32, device))
@@ -36,6 +38,18 @@ def _gae_launch(batch_rewards, batch_value, final_value_estimate, batch_terminal
     ret = torch.empty((steps, envs), dtype=torch.float32, device=device) if want_ret else None
     stats = torch.empty(_lib.STATS_LEN, dtype=torch.float64, device=device) if want_stats else None
     ws = dev.workspace(lib.ppo_gae_workspace_bytes(envs), device) if want_stats else None
+    if normalize is not None:
+        norm = torch.empty(steps * envs, dtype=torch.float32, device=device)
+        rc = lib.ppo_gae_normalized(
+            dev.ptr(rewards), rewards.stride(0) if steps else 0,
+            dev.ptr(values), values.stride(0) if steps else 0, values.stride(1) if envs else 0,
+            dev.ptr(final), final.stride(0) if envs else 0,
+            dev.ptr(dones), kind, dones.stride(0) if dones is not None and steps else 0,
+            steps, envs, float(gamma), float(lamb_adv), float(lamb_ret), float(normalize[0]), float(normalize[1]),
+            dev.ptr(adv), dev.ptr(ret), dev.ptr(norm), dev.ptr(stats),
+            dev.ptr(ws), ws.numel() if ws is not None else 0, dev.stream_ptr())
+        _lib.check(rc, "ppo_gae_normalized")
+        return adv, ret, norm, stats
     rc = lib.ppo_gae(
         dev.ptr(rewards), rewards.stride(0) if steps else 0,
         dev.ptr(values), values.stride(0) if steps else 0, values.stride(1) if envs else 0,

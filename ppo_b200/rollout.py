@@ -159,16 +159,24 @@ def calculate_returns(ext_rewards, ext_value_estimates, terminals, gamma, lambda
                                              with_stats=True, keep_on_device=to_host)
     if not from_curves:
         values = dev.to_device(ext_value_estimates, torch.float32, device)
-    adv, ret, stats = _returns._gae_launch(ext_rewards, values[:steps], values[steps], terminals, gamma,
-                                           lambda_policy, lambda_value, True, True, True)
-    local = stats.clone()
-    allreduce_stats(stats, group)
-    norm = torch.empty(adv.numel(), dtype=torch.float32, device=device)
     lib = _lib.load()
-    rc = lib.ppo_adv_normalize(dev.ptr(adv), adv.numel(), dev.ptr(stats), float(advantage_epsilon),
-                               float(advantage_clipping) if advantage_clipping is not None else 0.0,
-                               dev.ptr(norm), dev.stream_ptr())
-    _lib.check(rc, "ppo_adv_normalize")
+    clip = float(advantage_clipping) if advantage_clipping is not None else 0.0
+    sharded = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if sharded:
+        adv, ret, stats = _returns._gae_launch(ext_rewards, values[:steps], values[steps], terminals, gamma,
+                                               lambda_policy, lambda_value, True, True, True)
+        local = stats.clone()
+        allreduce_stats(stats, group)
+        norm = torch.empty(adv.numel(), dtype=torch.float32, device=device)
+        rc = lib.ppo_adv_normalize(dev.ptr(adv), adv.numel(), dev.ptr(stats), float(advantage_epsilon), clip,
+                                   dev.ptr(norm), dev.stream_ptr())
+        _lib.check(rc, "ppo_adv_normalize")
+    else:
+        # one GPU: scan, statistics and normalisation in one launch (ppo_gae_normalized)
+        adv, ret, norm, stats = _returns._gae_launch(ext_rewards, values[:steps], values[steps], terminals, gamma,
+                                                     lambda_policy, lambda_value, True, True, True,
+                                                     normalize=(float(advantage_epsilon), clip))
+        local = stats.clone()
 
     def deliver(name, tensor):
         if out is not None and name in out:
@@ -244,6 +252,7 @@ class ReturnPass:
                                   dtype=torch.uint8, device=self.device)
         self._ctab = self._blob = None
         self.kernel_launches_per_pass = 4
+        self._tvf_launches = 2
         self.tvf_kernel = "?"
         self.value_estimates = self._value_weights = None
 
@@ -279,8 +288,7 @@ class ReturnPass:
             _lib.check(rc, "ppo_tvf_targets")
             last = lib.ppo_tvf_last_path()
             self.tvf_kernel = {1: "generic", 2: "ring", 3: "tslab"}.get(last & 0xff, "?")
-            extra_launches = (0 if last & 0x100 else 1) + (1 if extras is not None and not last & 0x200 else 0)
-            self.kernel_launches_per_pass = 3 + extra_launches
+            self._tvf_launches = 1 + (0 if last & 0x100 else 1) + (1 if extras is not None and not last & 0x200 else 0)
             if tvf_events is not None:
                 tvf_events[1].record()
 
@@ -293,19 +301,31 @@ class ReturnPass:
             extras, _keep = _rt._extras(self.value_estimates, self._value_weights)
             targets(extras)
             values = self.value_estimates
-        rc = lib.ppo_gae(rewards.data_ptr(), rewards.stride(0), values.data_ptr(), values.stride(0), values.stride(1),
-                         values[n].data_ptr(), values.stride(1), dones.data_ptr(), _lib.DONE_U8, dones.stride(0),
-                         n, a, self.gamma, self.lambda_policy, self.lambda_value,
-                         self.advantage.data_ptr(), self.ext_returns.data_ptr(), self.stats.data_ptr(),
-                         self.ws_gae.data_ptr(), self.ws_gae.numel(), s)
-        _lib.check(rc, "ppo_gae")
+        gae_launches = 2
         if self.sharded:
+            rc = lib.ppo_gae(rewards.data_ptr(), rewards.stride(0), values.data_ptr(), values.stride(0),
+                             values.stride(1), values[n].data_ptr(), values.stride(1), dones.data_ptr(), _lib.DONE_U8,
+                             dones.stride(0), n, a, self.gamma, self.lambda_policy, self.lambda_value,
+                             self.advantage.data_ptr(), self.ext_returns.data_ptr(), self.stats.data_ptr(),
+                             self.ws_gae.data_ptr(), self.ws_gae.numel(), s)
+            _lib.check(rc, "ppo_gae")
             dist.all_reduce(self._moments, op=dist.ReduceOp.SUM, group=self.group)
-        rc = lib.ppo_adv_normalize(self.advantage.data_ptr(), n * a, self.stats.data_ptr(), self.eps, self.clip,
-                                   self.advantages.data_ptr(), s)
-        _lib.check(rc, "ppo_adv_normalize")
+            rc = lib.ppo_adv_normalize(self.advantage.data_ptr(), n * a, self.stats.data_ptr(), self.eps, self.clip,
+                                       self.advantages.data_ptr(), s)
+            _lib.check(rc, "ppo_adv_normalize")
+        else:
+            # one GPU: no exchange between the scan and the normalisation -> one cooperative launch when the grid fits
+            rc = lib.ppo_gae_normalized(rewards.data_ptr(), rewards.stride(0), values.data_ptr(), values.stride(0),
+                                        values.stride(1), values[n].data_ptr(), values.stride(1), dones.data_ptr(),
+                                        _lib.DONE_U8, dones.stride(0), n, a, self.gamma, self.lambda_policy,
+                                        self.lambda_value, self.eps, self.clip, self.advantage.data_ptr(),
+                                        self.ext_returns.data_ptr(), self.advantages.data_ptr(), self.stats.data_ptr(),
+                                        self.ws_gae.data_ptr(), self.ws_gae.numel(), s)
+            _lib.check(rc, "ppo_gae_normalized")
+            gae_launches = 1 if rc == 1 else 2
         if values is not self.value_estimates:
             targets(None)
+        self.kernel_launches_per_pass = self._tvf_launches + gae_launches
         return self
 
 

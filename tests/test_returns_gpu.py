@@ -78,3 +78,33 @@ def test_gae_stats_and_empty():
     e = returns.gae(np.zeros([0, 4], np.float32), np.zeros([0, 4], np.float32), np.zeros([4], np.float32),
                     np.zeros([0, 4], bool), 0.99)
     assert e.shape == (0, 4)
+
+
+@pytest.mark.parametrize("steps,envs,clip,fused", [(256, 4096, None, True), (96, 200, 1.5, True), (33, 5, None, True),
+                                                    (256, 32768, None, False)])
+def test_gae_with_fused_normalisation(steps, envs, clip, fused):
+    """ppo_gae_normalized: one cooperative launch when the grid is resident (flagged by the return value), else the two
+    launches; either way the bits of ppo_gae followed by ppo_adv_normalize."""
+    from ppo_b200 import _lib, _device as dev
+    lib = _lib.load()
+    r, d, v = synthetic.rollout(steps, envs, seed=3)
+    r, d, v = (torch.from_numpy(x).cuda() for x in (r, d, v))
+    d = d.view(torch.uint8)
+    outs = [torch.empty((steps, envs), device="cuda") for _ in range(6)]
+    st = [torch.zeros(_lib.STATS_LEN, dtype=torch.float64, device="cuda") for _ in range(2)]
+    ws = torch.zeros(int(lib.ppo_gae_workspace_bytes(envs)), dtype=torch.uint8, device="cuda")
+    s = dev.stream_ptr()
+    args = (r.data_ptr(), envs, v.data_ptr(), envs, 1, v[steps].data_ptr(), 1, d.data_ptr(), _lib.DONE_U8, envs,
+            steps, envs, 0.999, 0.95, 0.9)
+    for _ in range(2):  # twice: the flags of the cooperative launch must be left clear
+        rc = lib.ppo_gae_normalized(*args, 1e-8, clip or 0.0, outs[0].data_ptr(), outs[1].data_ptr(),
+                                    outs[2].data_ptr(), st[0].data_ptr(), ws.data_ptr(), ws.numel(), s)
+        assert rc == (1 if fused else 0), lib.ppo_last_error()
+    _lib.check(lib.ppo_gae(*args, outs[3].data_ptr(), outs[4].data_ptr(), st[1].data_ptr(), ws.data_ptr(), ws.numel(), s),
+               "ppo_gae")
+    _lib.check(lib.ppo_adv_normalize(outs[3].data_ptr(), steps * envs, st[1].data_ptr(), 1e-8, clip or 0.0,
+                                     outs[5].data_ptr(), s), "ppo_adv_normalize")
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[3]) and torch.equal(outs[1], outs[4]) and torch.equal(st[0], st[1])
+    assert torch.equal(outs[2], outs[5])
+    assert not ws[:256].any()
