@@ -429,6 +429,18 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": tvf_avg_ms,
                 "kernel_share_of_step": tvf_avg_ms / ms_per_step,
                 "units_per_launch": f"{steps} x {envs} x {n_h} targets at 8.06 B/target"}
+    # informational: the same kernel against the shared-memory gather bound that actually limits it:
+    # every target gathers 2 x (distinct n-steps per horizon) float32 value samples, one 128-byte wavefront per clock per SM
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    ent = float(tabs.layout.offset_words[15] and tabs.host[int(tabs.layout.offset_words[15]) + 1].item())
+    gather_bytes = steps * envs * ent * 2 * 4 if ent > 0 else None
+    if gather_bytes:
+        smem_peak = sms * 128 * (clocks.get("sm_max_mhz") or 1965) * 1e6 / 1e9
+        roofline["shared_memory_gather_bound"] = {
+            "gather_bytes_per_launch": gather_bytes, "peak_gbs": smem_peak,
+            "floor_ms": gather_bytes / smem_peak / 1e6, "frac_of_floor": gather_bytes / smem_peak / 1e6 / tvf_avg_ms,
+            "note": "2 gathers x 4 B per (target, distinct n-step); HBM traffic is 8.06 B per target, so at 8 samples "
+                    "per horizon the gathers take longer than the HBM transfers on any shared-memory formulation"}
 
     other = other_configs(device, peak) if world == 1 and not args.no_other_configs else None
     if rank == 0:

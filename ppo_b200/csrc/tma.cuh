@@ -64,8 +64,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // for warps that are far ahead of their consumers (producer, scan): back off between polls
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+// (every poll is a shared-memory access: warps that wait for microseconds should poll rarely, or they take a
+// measurable share of the shared-memory pipe from the warps that do the work)
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns = 64) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
 }
 
 // ---- device: TMA loads (global -> shared, completion on an mbarrier) ------------------------

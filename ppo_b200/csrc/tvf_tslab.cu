@@ -41,6 +41,7 @@ constexpr int kTsRows = 32;        // value rows per TMA chunk = time rows per l
 constexpr int kTsStep = 64;        // time rows per consumer step: a thread owns rows t and t + 32 of the step
 constexpr int kTsMaxChunks = 16;   // N <= 512
 constexpr int kTsMaxSteps = 8;
+constexpr unsigned kTsPollNs = 400;  // poll period of the helper warps (producer, transform, store, scan)
 
 struct TsParams {
     TvfParams p;
@@ -239,7 +240,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
             for (int e = 0; e < nenv; ++e) {
                 const int env = static_cast<int>(env0 + e);
                 for (int c = 0; c < NC; ++c) {
-                    mbar_wait_sleep(&sempty[slot], par ^ 1);
+                    mbar_wait_sleep(&sempty[slot], par ^ 1, kTsPollNs);
                     if (q.dbg & 2) {
                         mbar_arrive(&sfull[slot]);
                     } else {
@@ -258,7 +259,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
         for (int e = 0; e < nenv; ++e) {
             const int64_t env = env0 + e;
             for (int s = 0; s < NS; ++s, ++it) {
-                mbar_wait_sleep(ofull, it & 1u);
+                mbar_wait_sleep(ofull, it & 1u, kTsPollNs);
                 // one tensor store per (32 rows x 32 horizons) sub-tile; rows past N are clipped by the TMA unit
                 const int nsub = 2 * (K / 32);
                 if (lane < nsub && !(q.dbg & 1)) {
@@ -316,7 +317,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
             double x = shfl_down_f64(a, 1);
             int l = __shfl_down_sync(0xffffffffu, c, 1);
             if (lane == 31) x = 0.0, l = 0;
-            mbar_wait_sleep(&rempty[par], ((static_cast<uint32_t>(e) >> 1) & 1u) ^ 1u);
+            mbar_wait_sleep(&rempty[par], ((static_cast<uint32_t>(e) >> 1) & 1u) ^ 1u, 4 * kTsPollNs);
             const uint32_t rt = rt_a + par * rt_bytes, lt = lim_a + par * rt_bytes;
 #pragma unroll
             for (int i = kTsMaxChunks - 1; i >= 0; --i) {
@@ -360,7 +361,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                 }
                 if (lane == 31) q.value_out[env0 + e] = acc;
             }
-            mbar_wait_sleep(&rfull[par], (static_cast<uint32_t>(e) >> 1) & 1u);
+            mbar_wait_sleep(&rfull[par], (static_cast<uint32_t>(e) >> 1) & 1u, kTsPollNs);
             const uint32_t rt = rt_a + par * rt_bytes;
             // slab of this env; it was last used by env e - nslab (the j-th use of a slab waits for use j - 1)
             const int sl = e % q.nslab;
@@ -369,7 +370,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
             const uint32_t fr_e = fr_a + static_cast<uint32_t>(sl * V) * 4u;
             for (int c = 0; c < NC; ++c) {
                 // slab rows of chunk c were last needed by step c / 2 of the previous env in this slab
-                if (use > 0) mbar_wait_sleep(&bdone[sl * kTsMaxSteps + (c >> 1)], (use - 1) & 1u);
+                if (use > 0) mbar_wait_sleep(&bdone[sl * kTsMaxSteps + (c >> 1)], (use - 1) & 1u, kTsPollNs);
                 mbar_wait(&sfull[slot], spar);
                 const uint32_t src = stage_a + static_cast<uint32_t>(slot) * CHUNK + static_cast<uint32_t>(lane) * 4u;
                 float part[kTsRows / kTsXform];  // value-estimate partial sums of this warp's eight rows
