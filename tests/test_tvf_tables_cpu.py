@@ -135,3 +135,19 @@ def test_native_builder_fuzz(built_library, seed):
         assert np.array_equal(nat.table(name)[:want.size].view(np.int32), want.view(np.int32)), (name, seed)
     cnt = nat.table("ent_cnt")[:ref.n_entries * n_req].reshape(ref.n_entries, n_req)
     assert np.array_equal(cnt.sum(axis=0), np.where(req > 0, c, 0))
+
+
+def test_rediscount_weights_host_arithmetic(golden):
+    """Host side of the rediscounted value estimate (no GPU): the per-horizon weights handed to the kernels give the
+    reference's sum (rl/tvf.py:388-433) on the golden inputs, and the ratios are the reference's clipped ratios."""
+    from ppo_b200 import tvf
+    hz, rv = golden["prod_in_horizons"], golden["redis_in_values"].astype(np.float64)
+    for old, new, key in ((0.9999, 0.999, "redis_down"), (0.99, 0.9999, "redis_up")):
+        w = tvf.rediscount_weights(old, new, [int(h) for h in hz]).astype(np.float64)
+        got = rv @ w
+        ref = golden[key].astype(np.float64)
+        assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+        rho = tvf.rediscount_ratios(old, new, [int(h) for h in hz])
+        assert rho[0] == 0 and rho.max() <= 10 and np.all(rho[1:] > 0)
+    # clipping engages when discounting up over long horizons (ratio capped at 10, rl/tvf.py:429)
+    assert tvf.rediscount_ratios(0.99, 0.9999, [int(h) for h in hz]).max() == 10
