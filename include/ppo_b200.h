@@ -52,7 +52,8 @@ typedef enum {
     PPO_DONE_F32 = 2   /* float32 0/1 mask (rl/unit_tests.py:205)                         */
 } ppo_done_kind;
 
-/* Layout of one statistics record (doubles).  Sums are over the float32-rounded outputs. */
+/* Layout of one statistics record (doubles).  Sums are over the float32-rounded outputs; the VAL_* slots are the
+ * moments of the value estimates the scan read, all N + 1 rows (rl/rollout.py:1205 `*ext_value_estimates`). */
 enum {
     PPO_STAT_COUNT = 0,
     PPO_STAT_ADV_SUM = 1,
@@ -63,6 +64,9 @@ enum {
     PPO_STAT_RET_SUMSQ = 6,
     PPO_STAT_RET_MIN = 7,
     PPO_STAT_RET_MAX = 8,
+    PPO_STAT_VAL_SUM = 9,
+    PPO_STAT_VAL_SUMSQ = 10,
+    PPO_STAT_VAL_COUNT = 11,
     PPO_STATS_LEN = 16
 };
 

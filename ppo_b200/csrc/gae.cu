@@ -55,6 +55,12 @@ struct GaeParams {
 
 struct ThreadStats {
     double n = 0, s_adv = 0, q_adv = 0, s_ret = 0, q_ret = 0;
+    double s_val = 0, q_val = 0, n_val = 0;  // value estimates read by the scan (rl/rollout.py:1205)
+    __device__ __forceinline__ void add_value(float v) {
+        s_val += v;
+        q_val += static_cast<double>(v) * v;
+        n_val += 1.0;
+    }
     float mn_adv = INFINITY, mx_adv = -INFINITY, mn_ret = INFINITY, mx_ret = -INFINITY;
     // sums, squares and extrema only: the caller sets `n` from the element count it owns
     __device__ __forceinline__ void add_no_count(float a, float r) {
@@ -91,7 +97,11 @@ __device__ void publish_stats(const ThreadStats& ts, const ScanStatsIo& io, doub
     double s_ret = warp_sum_f64(ts.s_ret), q_ret = warp_sum_f64(ts.q_ret);
     float mn_adv = warp_min_f32(ts.mn_adv), mx_adv = warp_max_f32(ts.mx_adv);
     float mn_ret = warp_min_f32(ts.mn_ret), mx_ret = warp_max_f32(ts.mx_ret);
+    double s_val = warp_sum_f64(ts.s_val), q_val = warp_sum_f64(ts.q_val), n_val = warp_sum_f64(ts.n_val);
     if (lane == 0) {
+        red[w][PPO_STAT_VAL_SUM] = s_val;
+        red[w][PPO_STAT_VAL_SUMSQ] = q_val;
+        red[w][PPO_STAT_VAL_COUNT] = n_val;
         red[w][PPO_STAT_COUNT] = n;
         red[w][PPO_STAT_ADV_SUM] = s_adv;
         red[w][PPO_STAT_ADV_SUMSQ] = q_adv;
@@ -109,7 +119,7 @@ __device__ void publish_stats(const ThreadStats& ts, const ScanStatsIo& io, doub
         const bool is_min = (j == PPO_STAT_ADV_MIN || j == PPO_STAT_RET_MIN);
         const bool is_max = (j == PPO_STAT_ADV_MAX || j == PPO_STAT_RET_MAX);
         double acc = 0;
-        if (j <= PPO_STAT_RET_MAX) {
+        if (j <= PPO_STAT_VAL_COUNT) {
             acc = red[0][j];
             for (int i = 1; i < nwarps; ++i) {
                 const double x = red[i][j];
@@ -160,7 +170,7 @@ __device__ void publish_stats(const ThreadStats& ts, const ScanStatsIo& io, doub
                 const double x = fold[i * PPO_STATS_LEN + j];
                 tot = is_min ? fmin(tot, x) : is_max ? fmax(tot, x) : tot + x;
             }
-            io.stats[j] = j <= PPO_STAT_RET_MAX ? tot : 0.0;
+            io.stats[j] = j <= PPO_STAT_VAL_COUNT ? tot : 0.0;
             __threadfence();
         }
         if (ready) {  // the folded record is visible: release the CTAs that wait for it
@@ -265,7 +275,7 @@ __global__ void __launch_bounds__(kScanThreads) gae_kernel(const GaeParams p) {
                     const float t = __fadd_rn(static_cast<float>(x_ret), v[i]);  // rl/returns.py:66-67
                     if (ap) store_stream(ap + i * p.envs, a);
                     if (tp) store_stream(tp + i * p.envs, t);
-                    if (STATS) ts.add(a, t);
+                    if (STATS) ts.add(a, t), ts.add_value(v[i]);
                 }
             }
         } else {
@@ -278,10 +288,11 @@ __global__ void __launch_bounds__(kScanThreads) gae_kernel(const GaeParams p) {
                 const float t = __fadd_rn(static_cast<float>(x_ret), vv);
                 if (ap) store_stream(ap + i * p.envs, a);
                 if (tp) store_stream(tp + i * p.envs, t);
-                if (STATS) ts.add(a, t);
+                if (STATS) ts.add(a, t), ts.add_value(vv);
                 vn = vv;
             }
         }
+        if (STATS && len > 0 && hi == p.steps) ts.add_value(vtop);  // the final estimate, row N
     }
     if (STATS) publish_stats(ts, p.io, red);
 }
@@ -470,10 +481,11 @@ __global__ void __launch_bounds__(EW * kTileChunks) gae_tile_kernel(const GaeTil
             const float t = __fadd_rn(same ? a : static_cast<float>(x_ret), vv);  // rl/returns.py:66-67
             if (p.adv) store_stream(p.adv + static_cast<int64_t>(i) * p.envs + env, a);
             if (p.ret) store_stream(p.ret + static_cast<int64_t>(i) * p.envs + env, t);
-            if (STATS) ts.add_no_count(a, t);
+            if (STATS) ts.add_no_count(a, t), ts.add_value(vv);
             if (NORM) sr[i * EW + e] = a;  // the reward slot is dead: the raw advantage waits here for the statistics
         }
         ts.n = hi > lo ? static_cast<double>(hi - lo) : 0.0;
+        if (STATS && hi > lo && hi == N) ts.add_value(sv[N * EW + e]);  // the final estimate, row N
     }
     if (STATS) publish_stats(ts, p.io, red, NORM ? q.ready : nullptr);
     if (NORM) {

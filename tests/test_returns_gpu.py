@@ -72,6 +72,10 @@ def test_gae_stats_and_empty():
     assert s[3] == adv.min() and s[4] == adv.max()
     np.testing.assert_allclose(s[5], ret.astype(np.float64).sum(), rtol=1e-12)
     assert s[7] == ret.min() and s[8] == ret.max()
+    # moments of the value estimates the scan read, all N + 1 rows (rl/rollout.py:1205)
+    assert s[11] == v.size
+    np.testing.assert_allclose(s[9], v.astype(np.float64).sum(), rtol=1e-12)
+    np.testing.assert_allclose(s[10], (v.astype(np.float64) ** 2).sum(), rtol=1e-12)
     # run twice: the ticket must have been reset
     _, _, stats2 = returns.gae_td_lambda(r, v[:-1], v[-1], d, 0.999, 0.95, 0.9, with_stats=True)
     assert np.array_equal(stats2.cpu().numpy(), s)

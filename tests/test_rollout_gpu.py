@@ -51,6 +51,8 @@ def test_calculate_returns_matches_oracle():
     assert summary["count"] == adv.size
     np.testing.assert_allclose(summary["adv_mean"], adv.astype(np.float64).mean(), rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(summary["adv_std"], adv.astype(np.float64).std(), rtol=1e-9)
+    np.testing.assert_allclose(summary["value_mean"], v.astype(np.float64).mean(), rtol=1e-9)
+    np.testing.assert_allclose(summary["value_std"], v.astype(np.float64).std(), rtol=1e-9)
     t = rollout.stats_summary(res["tvf_stats"])
     last = np.asarray(res["tvf_returns"])[:, :, -1].astype(np.float64)
     assert t["adv_min"] == last.min() and t["adv_max"] == last.max()
