@@ -261,7 +261,7 @@ def _launch_host_blocks(gamma, rewards, dones, required_horizons, value_sample_h
         # pipeline fills (first upload) and drains (last download) quickly
         target = int(os.environ.get("PPO_HOST_BLOCKS", "12"))
         block_envs = int(min(envs, sms * max(1, -(-envs // (target * sms)))))
-        ramp = [b for b in (sms, 2 * sms) if b < block_envs]
+        ramp = [b for b in (sms // 2, sms, 2 * sms) if 0 < b < block_envs]
         sizes, left = [], envs
         if envs >= 2 * sum(ramp) + block_envs:
             left -= 2 * sum(ramp)
@@ -341,10 +341,15 @@ def _launch_host_blocks(gamma, rewards, dones, required_horizons, value_sample_h
         value_out.record_stream(s_comp)
     del blob
 
-    def join():
+    def join(kernels_only=False):
+        """Make the caller's stream wait for the kernels (value estimate, statistics) and, unless ``kernels_only``,
+        for the downloads; returns the merged statistics record.  A caller that passes ``kernels_only=True`` (to
+        enqueue work that only needs the kernels' results while the last downloads are still running) must call
+        ``join()`` again before it synchronises its stream."""
         cur = torch.cuda.current_stream()
         cur.wait_stream(s_comp)
-        cur.wait_stream(s_out)
+        if not kernels_only:
+            cur.wait_stream(s_out)
         if not with_stats:
             return None
         from . import rollout as _rollout  # merge of disjoint env blocks (sums add, min / max reduce)

@@ -148,9 +148,12 @@ def calculate_returns(ext_rewards, ext_value_estimates, terminals, gamma, lambda
             # side streams, started first so that the transfers overlap the GAE part below
             tvf_join = _rt._launch_host_blocks(g, ext_rewards, terminals, hz, hz, vs, samples, use_log,
                                                out["tvf_returns"], defer_join=True, **vkw)
-            if from_curves:  # GAE needs every block's value estimate
-                tstats_early = tvf_join()
-                tvf_join = lambda: tstats_early  # noqa: E731
+            if from_curves:  # GAE needs every block's value estimate (not the downloads: those are joined at the end)
+                tstats_early, join_all = tvf_join(kernels_only=True), tvf_join
+
+                def tvf_join():
+                    join_all()
+                    return tstats_early
         elif from_curves:
             early = _rt._launch(g, ext_rewards, terminals, hz, hz, vs, samples, use_log, with_stats=True,
                                 keep_on_device=to_host, **vkw)
