@@ -296,6 +296,20 @@ int ppo_rediscount_horizons(const float* values, int64_t rows, int64_t row_strid
 int ppo_horizon_interpolate(const double* host_horizons, int64_t n_val, const float* values, int64_t rows,
                             int64_t row_stride, const double* targets, double* out, void* stream);
 
+/*
+ * Horizon trimming of one rollout step.  Replaces the arithmetic of rl/tvf.py:91-208 `TVFRunnerModule.trim_horizons`
+ * (modes 0 interpolate, 1 average, 2 substitute, 3 random).  values [A, K, VH] float32 (device, contiguous).  The host
+ * resolves every index with the reference's own NumPy calls: trim_index [A] = searchsorted(horizons, time left)
+ * (:137); for mode 0 the slot (pre, post, frac) of `horizon_interpolate` on the log-scaled axis (:143-152); for mode 3
+ * picks [A, K], the source horizon drawn for every horizon (:179-189).  out is [A, K, VH] ([A, K, 1] for mode 2,
+ * :172-178); final_value [A] is the mean of the valid untrimmed ext estimates (:193-196); clip < 0 disables the
+ * clipping of the change (:199-201).
+ */
+int ppo_tvf_trim_horizons(const float* values, int64_t envs, int64_t n_val, int64_t n_heads, int mode,
+                          const int32_t* trim_index, const int32_t* interp_pre, const int32_t* interp_post,
+                          const double* interp_frac, const int32_t* picks, double clip, float* out,
+                          float* final_value, void* stream);
+
 /* Development aid: with the environment variable PPO_TVF_DEBUG bit 64 set, the transposed slab kernel records
  * globaltimer stamps (ns) of its first CTA at ten hand-off points (start, shared memory initialised, first R / lim
  * tables, first chunk / first env in the slab, first step starts, first env done, last step starts, consumers done,

@@ -26,5 +26,6 @@ from .tvf_np import (  # noqa: F401
     get_rediscounted_value_estimate,
     rediscount_horizons,
     get_value_head_horizons,
+    trim_horizons,
 )
 from .vtrace_np import importance_sampling_v_trace, v_trace_trust_region  # noqa: F401

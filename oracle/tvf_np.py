@@ -328,3 +328,68 @@ def get_value_head_horizons(n_heads, max_horizon, spacing="geometric", include_w
     res = np.asarray(order, dtype=np.int32)
     counts = np.asarray([multiplicity[h] for h in order], dtype=np.float32)
     return (res, counts) if include_weight else res
+
+
+def trim_horizons(horizons, tvf_value_estimates, time, method="timelimit", mode="interpolate", timeout=27000,
+                  trim_clip=-1, episode_length_buffer=(), eta_percentile=90, eta_buffer=32, eta_minh=128,
+                  randint=None):
+    """Pull value estimates of horizons that extend past the time limit back to the limit; follows
+    ``TVFRunnerModule.trim_horizons`` (``rl/tvf.py:91-208``) with the module state passed in explicitly.
+
+    ``tvf_value_estimates [A, K, VH]``, ``time [A]`` -> ``(trimmed [A, K, VH] (``[A, K, 1]`` in substitute mode),
+    final value estimate [A] float32 or 0, time till termination [A] or None)``.  ``randint(lo, hi)`` stands in for
+    ``np.random.randint`` in the ``random`` mode.
+    """
+    horizons = np.asarray(horizons)
+    old = tvf_value_estimates.copy()  # :106-107 two private copies
+    new = tvf_value_estimates.copy()
+    assert horizons[0] == 0, "First horizon must be zero"  # :110
+    new[:, 0, :] = 0  # :111-112
+    old[:, 0, :] = 0
+    if method == "off":  # :116-117
+        return new, 0, None
+    elif method == "timelimit":  # :118-119
+        ttt = np.maximum(timeout - time, 0)
+    elif method == "est_term":  # :120-127
+        est_len = np.percentile(list(episode_length_buffer) + list(time), eta_percentile).astype(int) + eta_buffer
+        est_len += eta_minh / 4
+        ttt = np.maximum(timeout - time, 0)
+        est_ttt = np.maximum(est_len - time, eta_minh)
+        ttt = np.minimum(ttt, est_ttt)
+    else:
+        raise ValueError(f"Invalid trimming method {method}")
+    n_envs, n_h, n_vh = new.shape
+    trimmed_ks = np.searchsorted(horizons, ttt)  # :137
+    if mode == "interpolate":  # :140-155, interpolation on the log scale
+        def log_scale(x):
+            return np.log10(10 + x) - 1
+        value = horizon_interpolate(log_scale(horizons), old[..., 0], log_scale(ttt))
+        for a in range(n_envs):
+            new[a, trimmed_ks[a]:, 0] = value[a]
+    elif mode == "average":  # :156-171 running mean of the untrimmed estimates from the trimming point on
+        for a, tk in enumerate(trimmed_ks):
+            if tk >= n_h - 1:
+                continue
+            acc, cnt = 0, 0
+            for k in range(tk, n_h):
+                acc = acc + old[a, k, :]
+                cnt += 1
+                new[a, k, :] = acc / cnt
+    elif mode == "substitute":  # :172-178 shortest admissible horizon, ext head only
+        ks = np.minimum(trimmed_ks[:, None].copy(), np.arange(n_h)[None, :])
+        new = np.take_along_axis(new[:, :, 0], ks, axis=1)[:, :, None]
+    elif mode == "random":  # :179-189
+        randint = randint or np.random.randint
+        for a, tk in zip(range(n_envs), trimmed_ks):
+            ks = np.arange(n_h)
+            for k in range(tk, n_h):
+                ks[k] = randint(tk, k + 1)
+            new[a, range(n_h)] = old[a, ks]
+    else:
+        raise ValueError(f"Invalid trimming mode {mode}")
+    final = np.zeros([n_envs], dtype=np.float32)  # :193-196 mean of the valid untrimmed ext estimates
+    for a, tk in enumerate(trimmed_ks):
+        final[a] = old[a, min(tk, n_h - 1):, 0].mean()
+    if trim_clip >= 0:  # :199-201
+        new = old + np.clip(new - old, -trim_clip, +trim_clip)
+    return new, final, ttt

@@ -52,6 +52,8 @@ _SIGNATURES = {
     "ppo_value_estimate": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr]),
     "ppo_rediscount_horizons": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
     "ppo_horizon_interpolate": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr]),
+    "ppo_tvf_trim_horizons": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr,
+                                      c_ptr, c_ptr]),
     "ppo_tvf_debug_times": (c_int, [c_ptr]),
     "ppo_tvf_last_path": (c_int, []),
     "ppo_tvf_last_horizon_stats": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),

@@ -119,6 +119,90 @@ __global__ void __launch_bounds__(256) horizon_interpolate_kernel(const __grid_c
     }
 }
 
+// Horizon trimming of one rollout step (rl/tvf.py:91-208): value estimates of horizons beyond the time left are pulled
+// back to the horizon that is still reachable.  Everything that is an index (the trimming point `searchsorted(h, ttt)`,
+// the interpolation slot on the log-scaled axis, the random horizon picks) is resolved on the host; this kernel does
+// the arithmetic on the value estimates.  One CTA per env, one thread per (horizon, head) where that parallelises and
+// one thread per head for the sequential running mean of the `average` mode (float32 accumulation in the
+// reference's order).
+struct TrimParams {
+    const float* v;        // [A, K, VH]
+    int64_t envs;
+    int k, vh, mode;       // mode: 0 interpolate, 1 average, 2 substitute, 3 random
+    const int32_t* tk;     // [A] trimming point
+    const int32_t* pre;    // [A] interpolate: lower slot, upper slot, factor
+    const int32_t* post;
+    const double* frac;
+    const int32_t* picks;  // [A, K] random: source horizon of every horizon
+    float clip;            // < 0: off
+    float* out;            // [A, K, VH] ([A, K, 1] for substitute)
+    float* final_value;    // [A]
+};
+
+__global__ void __launch_bounds__(256) trim_horizons_kernel(const TrimParams p) {
+    const int64_t a = blockIdx.x;
+    const float* src = p.v + a * p.k * p.vh;
+    const int K = p.k, VH = p.vh, tk = p.tk[a];
+    const int ovh = p.mode == 2 ? 1 : VH;
+    float* dst = p.out + a * K * ovh;
+    auto old_at = [&](int k, int h) { return k == 0 ? 0.f : src[k * VH + h]; };  // h = 0 is zero by definition (:111-112)
+    auto clipped = [&](float nv, float ov) {
+        return p.clip >= 0.f ? __fadd_rn(ov, fminf(fmaxf(__fsub_rn(nv, ov), -p.clip), p.clip)) : nv;  // :199-201
+    };
+    if (p.mode == 1) {
+        // running mean from the trimming point on, every head (:156-171)
+        for (int h = threadIdx.x; h < VH; h += blockDim.x) {
+            float acc = 0.f;
+            int cnt = 0;
+            for (int k = 0; k < K; ++k) {
+                const float ov = old_at(k, h);
+                float nv = ov;
+                if (tk < K - 1 && k >= tk) {
+                    acc = __fadd_rn(acc, ov);
+                    ++cnt;
+                    nv = __fdiv_rn(acc, static_cast<float>(cnt));
+                }
+                dst[k * VH + h] = clipped(nv, ov);
+            }
+        }
+    } else {
+        float iv = 0.f;
+        if (p.mode == 0) {  // horizon_interpolate on the log axis, float64 like the reference, rounded on assignment
+            const int lo = p.pre[a], hi = p.post[a];
+            const double f = p.frac[a];
+            const double x = __dadd_rn(__dmul_rn(static_cast<double>(old_at(lo, 0)), 1.0 - f),
+                                       __dmul_rn(static_cast<double>(old_at(hi, 0)), f));
+            iv = hi == 0 ? 0.f : static_cast<float>(x);
+        }
+        for (int i = threadIdx.x; i < K * ovh; i += blockDim.x) {
+            const int k = i / ovh, h = i % ovh;
+            const float ov = old_at(k, h);
+            float nv = ov;
+            if (p.mode == 0) {
+                if (h == 0 && k >= tk) nv = iv;                                    // :151-155
+            } else if (p.mode == 2) {
+                nv = old_at(min(tk, k), 0);                                        // :172-178
+            } else {
+                nv = old_at(p.picks[a * K + k], h);                                // :179-189
+            }
+            dst[i] = clipped(nv, ov);
+        }
+    }
+    // estimate used for the advantages: mean of the untrimmed ext estimates that are still valid (:193-196)
+    __shared__ double part[8];
+    const int k0 = min(tk, K - 1);
+    double s = 0.0;
+    for (int k = k0 + threadIdx.x; k < K; k += blockDim.x) s += static_cast<double>(old_at(k, 0));
+    s = warp_sum_f64(s);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < (blockDim.x + 31) / 32; ++w) tot += part[w];
+        p.final_value[a] = static_cast<float>(tot / static_cast<double>(K - k0));
+    }
+}
+
 static int64_t warp_grid(int64_t rows) {
     int64_t blocks = (rows + 7) / 8;
     const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
@@ -190,6 +274,25 @@ extern "C" int ppo_horizon_interpolate(const double* host_horizons, int64_t n_va
     const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
     if (blocks > cap) blocks = cap;
     horizon_interpolate_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+extern "C" int ppo_tvf_trim_horizons(const float* values, int64_t envs, int64_t n_val, int64_t n_heads, int mode,
+                                     const int32_t* trim_index, const int32_t* interp_pre, const int32_t* interp_post,
+                                     const double* interp_frac, const int32_t* picks, double clip, float* out,
+                                     float* final_value, void* stream) {
+    PPO_REQUIRE(envs >= 0 && n_val >= 1 && n_heads >= 1 && mode >= 0 && mode <= 3, "ppo_tvf_trim_horizons: bad arguments");
+    if (envs == 0) return PPO_OK;
+    PPO_REQUIRE(values && trim_index && out && final_value, "ppo_tvf_trim_horizons: null pointer");
+    PPO_REQUIRE(mode != 0 || (interp_pre && interp_post && interp_frac), "ppo_tvf_trim_horizons: interpolation slots missing");
+    PPO_REQUIRE(mode != 3 || picks, "ppo_tvf_trim_horizons: random picks missing");
+    TrimParams p{};
+    p.v = values, p.envs = envs, p.k = static_cast<int>(n_val), p.vh = static_cast<int>(n_heads), p.mode = mode;
+    p.tk = trim_index, p.pre = interp_pre, p.post = interp_post, p.frac = interp_frac, p.picks = picks;
+    p.clip = clip >= 0 ? static_cast<float>(clip) : -1.f;
+    p.out = out, p.final_value = final_value;
+    trim_horizons_kernel<<<static_cast<unsigned>(envs), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;
 }

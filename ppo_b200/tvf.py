@@ -151,6 +151,79 @@ class TVFRunnerModule:
         self.tvf_final_value = np.zeros([n_steps + 1, n_envs], dtype=np.float32)
         self.tvf_returns = np.zeros([n_steps, n_envs, n_h, n_vh], dtype=np.float32)
 
+    def trim_horizons(self, tvf_value_estimates, time, method: str = "timelimit", mode: str = "interpolate"):
+        """Pull horizons that extend over the time limit back to the limit (reference: ``rl/tvf.py:91-208``, same
+        arguments and return values: trimmed estimates ``[A, K, VH]`` (``[A, K, 1]`` in substitute mode), the value
+        estimate used for advantages ``[A]`` and the time till termination ``[A]``; ``(copy, 0, None)`` for
+        ``method="off"``).  Indices (trimming point, interpolation slot, random picks) are resolved on the host
+        with the reference's NumPy calls, the arithmetic on the estimates runs in ``ppo_tvf_trim_horizons``."""
+        args = self.args
+        horizons = np.asarray(self.runner.tvf_horizons)
+        assert horizons[0] == 0, "First horizon must be zero"
+        if method == "off":
+            out = np.array(tvf_value_estimates, copy=True) if dev.is_numpy_like(tvf_value_estimates) \
+                else tvf_value_estimates.clone()
+            out[:, 0, :] = 0
+            return out, 0, None
+        time = np.asarray(time.cpu() if isinstance(time, torch.Tensor) else time)
+        if method == "timelimit":
+            time_till_termination = np.maximum(args.env.timeout - time, 0)
+        elif method == "est_term":
+            est_ep_length = np.percentile(list(self.runner.episode_length_buffer) + list(time),
+                                          args.tvf.eta_percentile).astype(int) + args.tvf.eta_buffer
+            est_ep_length += args.tvf.eta_minh / 4
+            time_till_termination = np.maximum(args.env.timeout - time, 0)
+            est_time_till_termination = np.maximum(est_ep_length - time, args.tvf.eta_minh)
+            time_till_termination = np.minimum(time_till_termination, est_time_till_termination)
+            self.runner.log.watch_mean("*ttt_ep_length", np.percentile(self.runner.episode_length_buffer,
+                                                                     args.tvf.eta_percentile).astype(int))
+            self.runner.log.watch_mean("*ttt_ep_std", np.std(self.runner.episode_length_buffer))
+        else:
+            raise ValueError(f"Invalid trimming method {method}")
+        self.runner.log.watch_stats("ttt", time_till_termination, display_width=0, history_length=4)
+
+        n_envs, n_h, n_vh = tvf_value_estimates.shape
+        modes = {"interpolate": 0, "average": 1, "substitute": 2, "random": 3}
+        if mode not in modes:
+            raise ValueError(f"Invalid trimming mode {mode}")
+        trimmed_ks = np.searchsorted(horizons, time_till_termination).astype(np.int32)
+        pre = post = frac = picks = None
+        if mode == "interpolate":
+            # the slot of horizon_interpolate (rl/tvf.py:527-573) on the log-scaled axis (:143-152)
+            axis = np.log10(10 + horizons) - 1
+            target = np.clip(np.log10(10 + time_till_termination) - 1, axis[0], axis[-1])
+            post_i = np.searchsorted(axis, target, side='left')
+            pre_i = np.maximum(post_i - 1, 0)
+            dx = axis[post_i] - axis[pre_i]
+            dx[dx == 0] = 1.0
+            frac = np.ascontiguousarray((target - axis[pre_i]) / dx, dtype=np.float64)
+            pre, post = pre_i.astype(np.int32), post_i.astype(np.int32)
+        elif mode == "random":
+            # same np.random.randint calls in the same order as the reference (:182-188)
+            picks = np.tile(np.arange(n_h, dtype=np.int32), (n_envs, 1))
+            for a, trimmed_k in zip(range(n_envs), trimmed_ks):
+                for k in range(trimmed_k, n_h):
+                    picks[a, k] = np.random.randint(trimmed_k, k + 1)
+
+        device = dev.require_cuda()
+        lib = _lib.load()
+        np_like = dev.is_numpy_like(tvf_value_estimates)
+        v = dev.to_device(tvf_value_estimates, torch.float32, device).contiguous()
+        up = lambda x: None if x is None else torch.from_numpy(np.ascontiguousarray(x)).to(device)  # noqa: E731
+        d_tk, d_pre, d_post, d_frac, d_picks = up(trimmed_ks), up(pre), up(post), up(frac), up(picks)
+        out = torch.empty((n_envs, n_h, 1 if mode == "substitute" else n_vh), dtype=torch.float32, device=device)
+        final = torch.empty(n_envs, dtype=torch.float32, device=device)
+        rc = lib.ppo_tvf_trim_horizons(dev.ptr(v), n_envs, n_h, n_vh, modes[mode], dev.ptr(d_tk), dev.ptr(d_pre),
+                                       dev.ptr(d_post), dev.ptr(d_frac), dev.ptr(d_picks), float(args.tvf.trim_clip),
+                                       dev.ptr(out), dev.ptr(final), dev.stream_ptr())
+        _lib.check(rc, "ppo_tvf_trim_horizons")
+        new, fin = dev.like_input(out, np_like), dev.like_input(final, np_like)
+        if np_like:
+            delta = np.abs(new - np.where(np.arange(n_h)[None, :, None] == 0, 0, np.asarray(tvf_value_estimates))
+                           [:, :, :new.shape[2]])
+            self.runner.log.watch_stats("ved", delta.ravel(), display_width=0, history_length=4)
+        return new, fin, time_till_termination
+
     def calculate_tvf_returns(self, value_head: str = "ext", obs=None, rewards=None, dones=None,
                               tvf_return_mode=None, tvf_return_distribution=None, tvf_n_step=None):
         """(tvf_gamma discounted) return estimates ``[N, A, K]`` for the rollout (reference: ``rl/tvf.py:210-271``)."""

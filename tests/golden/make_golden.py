@@ -159,6 +159,41 @@ def main():
     out["redis_up"] = ref.tvf.get_rediscounted_value_estimate(rv, 0.99, 0.9999, hz)
     out["redis_same"] = np.asarray(ref.tvf.get_rediscounted_value_estimate(rv, 0.99, 0.99, hz))
 
+    # ---- TVFRunnerModule.trim_horizons (rl/tvf.py:91-208) with a stand-in runner and config
+    import types as _types
+    import rl.config as _cfg
+    hz_t = ref.tvf.get_value_head_horizons(32, 1000)
+    _cfg.args.env = _types.SimpleNamespace(timeout=900)
+    _cfg.args.tvf = _types.SimpleNamespace(eta_percentile=90, eta_buffer=32, eta_minh=128, trim_clip=-1)
+    ref.tvf.args = _cfg.args
+    log = _types.SimpleNamespace(watch_stats=lambda *a, **k: None, watch_mean=lambda *a, **k: None)
+    n_envs_t = 37
+    runner = _types.SimpleNamespace(ext_rewards=np.zeros([4, n_envs_t], np.float32), value_heads=["ext", "int"],
+                                    tvf_horizons=list(hz_t), K=len(hz_t), log=log,
+                                    episode_length_buffer=[300, 420, 510, 640, 880, 200])
+    mod = ref.tvf.TVFRunnerModule(runner)
+    rng = np.random.RandomState(77)
+    tv = np.cumsum(np.abs(rng.normal(0, 1, [n_envs_t, len(hz_t), 2])), axis=1).astype(np.float32)
+    tt = rng.randint(0, 1000, size=[n_envs_t])
+    tt[:4] = [0, 899, 900, 950]  # nothing trimmed, one step left, at the limit, past the limit
+    out["trim_in_horizons"], out["trim_in_values"], out["trim_in_time"] = hz_t, tv, tt
+    out["trim_in_ep_lengths"] = np.asarray(runner.episode_length_buffer)
+    for method in ("timelimit", "est_term"):
+        for mode in ("interpolate", "average", "substitute"):
+            new, fin, ttt = mod.trim_horizons(tv, tt, method=method, mode=mode)
+            out[f"trim_{method}_{mode}_values"], out[f"trim_{method}_{mode}_final"] = new, fin
+            out[f"trim_{method}_{mode}_ttt"] = np.asarray(ttt)
+    _cfg.args.tvf.trim_clip = 0.25
+    new, fin, _ = mod.trim_horizons(tv, tt, method="timelimit", mode="average")
+    out["trim_clip_values"], out["trim_clip_final"] = new, fin
+    _cfg.args.tvf.trim_clip = -1
+    np.random.seed(123)
+    new, fin, _ = mod.trim_horizons(tv, tt, method="timelimit", mode="random")
+    out["trim_random_values"], out["trim_random_final"] = new, fin
+    new, fin, ttt = mod.trim_horizons(tv, tt, method="off", mode="average")
+    out["trim_off_values"] = new
+    assert fin == 0 and ttt is None
+
     # ---- V-trace (rl/vtrace.py)
     beh, tgt, act = synthetic.policies(14, 6, n_actions=5, seed=41)
     r3, d3, v3 = synthetic.rollout(14, 6, seed=41)

@@ -126,6 +126,24 @@ def test_rediscount(golden):
     assert same(oracle.get_rediscounted_value_estimate(rv, 0.99, 0.99, hz), golden["redis_same"])
 
 
+def test_trim_horizons(golden):
+    """rl/tvf.py:91-208 through a stand-in runner (tests/golden/make_golden.py), every method / mode, bit for bit."""
+    g = golden
+    hz, tv, tt, ep = g["trim_in_horizons"], g["trim_in_values"], g["trim_in_time"], list(g["trim_in_ep_lengths"])
+    for method in ("timelimit", "est_term"):
+        for mode in ("interpolate", "average", "substitute"):
+            new, fin, ttt = oracle.trim_horizons(hz, tv, tt, method, mode, timeout=900, episode_length_buffer=ep)
+            assert same(new, g[f"trim_{method}_{mode}_values"]) and same(fin, g[f"trim_{method}_{mode}_final"])
+            assert same(np.asarray(ttt), g[f"trim_{method}_{mode}_ttt"])
+    new, fin, _ = oracle.trim_horizons(hz, tv, tt, "timelimit", "average", timeout=900, trim_clip=0.25)
+    assert same(new, g["trim_clip_values"]) and same(fin, g["trim_clip_final"])
+    np.random.seed(123)
+    new, fin, _ = oracle.trim_horizons(hz, tv, tt, "timelimit", "random", timeout=900)
+    assert same(new, g["trim_random_values"]) and same(fin, g["trim_random_final"])
+    new, fin, ttt = oracle.trim_horizons(hz, tv, tt, "off", "average")
+    assert same(new, g["trim_off_values"]) and fin == 0 and ttt is None
+
+
 def test_vtrace(golden):
     g = golden
     beh, tgt, act = g["vt_in_beh"], g["vt_in_tgt"], g["vt_in_act"]

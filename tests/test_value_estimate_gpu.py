@@ -158,3 +158,57 @@ def test_horizon_interpolate_golden_and_oracle(golden):
     assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
     with pytest.raises(AssertionError):
         tvf.horizon_interpolate(hz[1:], v[:, 1:], t)  # first horizon must be 0
+
+
+def _trim_module(golden, clip=-1):
+    hz = golden["trim_in_horizons"]
+    log = types.SimpleNamespace(watch_stats=lambda *a, **k: None, watch_mean=lambda *a, **k: None)
+    runner = types.SimpleNamespace(ext_rewards=np.zeros([4, 37], np.float32), terminals=None, all_obs=None,
+                                   tvf_horizons=list(hz), value_heads=["ext", "int"], N=4, K=len(hz), log=log,
+                                   episode_length_buffer=list(golden["trim_in_ep_lengths"]))
+    args = types.SimpleNamespace(env=types.SimpleNamespace(timeout=900),
+                                 tvf=types.SimpleNamespace(eta_percentile=90, eta_buffer=32, eta_minh=128, trim_clip=clip))
+    return tvf.TVFRunnerModule(runner, args)
+
+
+def test_trim_horizons_golden(golden):
+    """TVFRunnerModule.trim_horizons (rl/tvf.py:91-208) against outputs of the real reference, every method / mode."""
+    g = golden
+    tv, tt = g["trim_in_values"], g["trim_in_time"]
+    mod = _trim_module(g)
+    for method in ("timelimit", "est_term"):
+        for mode in ("interpolate", "average", "substitute"):
+            new, fin, ttt = mod.trim_horizons(tv, tt, method=method, mode=mode)
+            ref = g[f"trim_{method}_{mode}_values"]
+            assert new.dtype == np.float32 and new.shape == ref.shape
+            assert rel_err(new, ref) <= TOL and rel_err(fin, g[f"trim_{method}_{mode}_final"]) <= TOL
+            assert np.array_equal(np.asarray(ttt), g[f"trim_{method}_{mode}_ttt"])  # integer work: exact
+    new, fin, _ = _trim_module(g, clip=0.25).trim_horizons(tv, tt, method="timelimit", mode="average")
+    assert rel_err(new, g["trim_clip_values"]) <= TOL and rel_err(fin, g["trim_clip_final"]) <= TOL
+    np.random.seed(123)
+    new, fin, _ = mod.trim_horizons(tv, tt, method="timelimit", mode="random")
+    assert np.array_equal(new, g["trim_random_values"])  # pure gathers with the reference's random picks: exact
+    new, fin, ttt = mod.trim_horizons(tv, tt, method="off", mode="average")
+    assert np.array_equal(new, g["trim_off_values"]) and fin == 0 and ttt is None
+    with pytest.raises(ValueError):
+        mod.trim_horizons(tv, tt, method="nope")
+    with pytest.raises(ValueError):
+        mod.trim_horizons(tv, tt, method="timelimit", mode="nope")
+
+
+def test_trim_horizons_production_shape_vs_oracle():
+    hz = oracle.get_value_head_horizons(128, 30000)
+    rng = np.random.RandomState(5)
+    n_envs = 512
+    tv = np.cumsum(np.abs(rng.normal(0, 1, [n_envs, len(hz), 1])), axis=1).astype(np.float32)
+    tt = rng.randint(0, 30000, size=[n_envs])
+    log = types.SimpleNamespace(watch_stats=lambda *a, **k: None, watch_mean=lambda *a, **k: None)
+    runner = types.SimpleNamespace(ext_rewards=np.zeros([2, n_envs], np.float32), tvf_horizons=list(hz),
+                                   value_heads=["ext"], N=2, K=len(hz), log=log, episode_length_buffer=[5000, 9000])
+    args = types.SimpleNamespace(env=types.SimpleNamespace(timeout=27000),
+                                 tvf=types.SimpleNamespace(eta_percentile=90, eta_buffer=32, eta_minh=128, trim_clip=-1))
+    mod = tvf.TVFRunnerModule(runner, args)
+    for mode in ("interpolate", "average", "substitute"):
+        new, fin, ttt = mod.trim_horizons(tv, tt, method="timelimit", mode=mode)
+        ref_new, ref_fin, ref_ttt = oracle.trim_horizons(hz, tv, tt, "timelimit", mode, timeout=27000)
+        assert rel_err(new, ref_new) <= TOL and rel_err(fin, ref_fin) <= TOL and np.array_equal(ttt, ref_ttt)
