@@ -67,6 +67,8 @@ enum {
     PPO_STAT_VAL_SUM = 9,
     PPO_STAT_VAL_SUMSQ = 10,
     PPO_STAT_VAL_COUNT = 11,
+    PPO_STAT_ADV_ZEROS = 12, /* number of exact zeros: the "sparsity" of rl/logger.py:201-229 is zeros / count */
+    PPO_STAT_RET_ZEROS = 13,
     PPO_STATS_LEN = 16
 };
 

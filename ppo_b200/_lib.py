@@ -27,6 +27,7 @@ STATS_LEN = 16
 STAT_COUNT, STAT_ADV_SUM, STAT_ADV_SUMSQ, STAT_ADV_MIN, STAT_ADV_MAX = 0, 1, 2, 3, 4
 STAT_RET_SUM, STAT_RET_SUMSQ, STAT_RET_MIN, STAT_RET_MAX = 5, 6, 7, 8
 STAT_VAL_SUM, STAT_VAL_SUMSQ, STAT_VAL_COUNT = 9, 10, 11
+STAT_ADV_ZEROS, STAT_RET_ZEROS = 12, 13
 
 # name -> (restype, argtypes); must match include/ppo_b200.h
 _SIGNATURES = {

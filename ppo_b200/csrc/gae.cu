@@ -56,6 +56,7 @@ struct GaeParams {
 struct ThreadStats {
     double n = 0, s_adv = 0, q_adv = 0, s_ret = 0, q_ret = 0;
     double s_val = 0, q_val = 0, n_val = 0;  // value estimates read by the scan (rl/rollout.py:1205)
+    double z_adv = 0, z_ret = 0;             // exact zeros (rl/logger.py:201-229 `sparsity`)
     __device__ __forceinline__ void add_value(float v) {
         s_val += v;
         q_val += static_cast<double>(v) * v;
@@ -64,6 +65,8 @@ struct ThreadStats {
     float mn_adv = INFINITY, mx_adv = -INFINITY, mn_ret = INFINITY, mx_ret = -INFINITY;
     // sums, squares and extrema only: the caller sets `n` from the element count it owns
     __device__ __forceinline__ void add_no_count(float a, float r) {
+        z_adv += a == 0.f ? 1.0 : 0.0;
+        z_ret += r == 0.f ? 1.0 : 0.0;
         s_adv += a;
         q_adv += static_cast<double>(a) * a;
         s_ret += r;
@@ -75,6 +78,8 @@ struct ThreadStats {
     }
     __device__ __forceinline__ void add(float a, float r) {
         n += 1.0;
+        z_adv += a == 0.f ? 1.0 : 0.0;
+        z_ret += r == 0.f ? 1.0 : 0.0;
         s_adv += a;
         q_adv += static_cast<double>(a) * a;
         s_ret += r;
@@ -98,7 +103,10 @@ __device__ void publish_stats(const ThreadStats& ts, const ScanStatsIo& io, doub
     float mn_adv = warp_min_f32(ts.mn_adv), mx_adv = warp_max_f32(ts.mx_adv);
     float mn_ret = warp_min_f32(ts.mn_ret), mx_ret = warp_max_f32(ts.mx_ret);
     double s_val = warp_sum_f64(ts.s_val), q_val = warp_sum_f64(ts.q_val), n_val = warp_sum_f64(ts.n_val);
+    double z_adv = warp_sum_f64(ts.z_adv), z_ret = warp_sum_f64(ts.z_ret);
     if (lane == 0) {
+        red[w][PPO_STAT_ADV_ZEROS] = z_adv;
+        red[w][PPO_STAT_RET_ZEROS] = z_ret;
         red[w][PPO_STAT_VAL_SUM] = s_val;
         red[w][PPO_STAT_VAL_SUMSQ] = q_val;
         red[w][PPO_STAT_VAL_COUNT] = n_val;
@@ -119,7 +127,7 @@ __device__ void publish_stats(const ThreadStats& ts, const ScanStatsIo& io, doub
         const bool is_min = (j == PPO_STAT_ADV_MIN || j == PPO_STAT_RET_MIN);
         const bool is_max = (j == PPO_STAT_ADV_MAX || j == PPO_STAT_RET_MAX);
         double acc = 0;
-        if (j <= PPO_STAT_VAL_COUNT) {
+        if (j <= PPO_STAT_RET_ZEROS) {
             acc = red[0][j];
             for (int i = 1; i < nwarps; ++i) {
                 const double x = red[i][j];
@@ -170,7 +178,7 @@ __device__ void publish_stats(const ThreadStats& ts, const ScanStatsIo& io, doub
                 const double x = fold[i * PPO_STATS_LEN + j];
                 tot = is_min ? fmin(tot, x) : is_max ? fmax(tot, x) : tot + x;
             }
-            io.stats[j] = j <= PPO_STAT_VAL_COUNT ? tot : 0.0;
+            io.stats[j] = j <= PPO_STAT_RET_ZEROS ? tot : 0.0;
             __threadfence();
         }
         if (ready) {  // the folded record is visible: release the CTAs that wait for it

@@ -161,29 +161,29 @@ struct LastHorizonParams {
 };
 
 __global__ void __launch_bounds__(512) tvf_last_horizon_stats_kernel(const LastHorizonParams p) {
-    __shared__ double red[16][4];
+    __shared__ double red[16][4];  // n, sum, sumsq, zeros
     __shared__ bool is_last;
-    double n = 0, s = 0, q = 0;
+    double n = 0, s = 0, q = 0, z = 0;
     float mn = INFINITY, mx = -INFINITY;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.rows; i += stride) {
         const float x = __ldg(p.out + i * p.K + (p.K - 1));
-        n += 1.0, s += x, q += static_cast<double>(x) * x;
+        n += 1.0, s += x, q += static_cast<double>(x) * x, z += x == 0.f ? 1.0 : 0.0;
         mn = fminf(mn, x), mx = fmaxf(mx, x);
     }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    n = warp_sum_f64(n), s = warp_sum_f64(s), q = warp_sum_f64(q);
+    n = warp_sum_f64(n), s = warp_sum_f64(s), q = warp_sum_f64(q), z = warp_sum_f64(z);
     mn = warp_min_f32(mn), mx = warp_max_f32(mx);
     __shared__ float redm[16][2];
-    if (lane == 0) red[w][0] = n, red[w][1] = s, red[w][2] = q, redm[w][0] = mn, redm[w][1] = mx;
+    if (lane == 0) red[w][0] = n, red[w][1] = s, red[w][2] = q, red[w][3] = z, redm[w][0] = mn, redm[w][1] = mx;
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int i = 1; i < 16; ++i) {
-            n += red[i][0], s += red[i][1], q += red[i][2];
+            n += red[i][0], s += red[i][1], q += red[i][2], z += red[i][3];
             mn = fminf(mn, redm[i][0]), mx = fmaxf(mx, redm[i][1]);
         }
         double* rec = p.partials + static_cast<int64_t>(blockIdx.x) * 8;
-        rec[0] = n, rec[1] = s, rec[2] = q, rec[3] = mn, rec[4] = mx;
+        rec[0] = n, rec[1] = s, rec[2] = q, rec[3] = mn, rec[4] = mx, rec[5] = z;
         __threadfence();
         is_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
     }
@@ -191,15 +191,16 @@ __global__ void __launch_bounds__(512) tvf_last_horizon_stats_kernel(const LastH
     if (!is_last) return;
     __threadfence();
     if (w == 0) {
-        double an = 0, as = 0, aq = 0, amn = INFINITY, amx = -INFINITY;
+        double an = 0, as = 0, aq = 0, az = 0, amn = INFINITY, amx = -INFINITY;
         for (unsigned int b = lane; b < gridDim.x; b += 32) {
             const double* rec = p.partials + static_cast<int64_t>(b) * 8;
-            an += __ldcg(rec), as += __ldcg(rec + 1), aq += __ldcg(rec + 2);
+            an += __ldcg(rec), as += __ldcg(rec + 1), aq += __ldcg(rec + 2), az += __ldcg(rec + 5);
             amn = fmin(amn, __ldcg(rec + 3)), amx = fmax(amx, __ldcg(rec + 4));
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             an += shfl_down_f64(an, d), as += shfl_down_f64(as, d), aq += shfl_down_f64(aq, d);
+            az += shfl_down_f64(az, d);
             amn = fmin(amn, shfl_down_f64(amn, d)), amx = fmax(amx, shfl_down_f64(amx, d));
         }
         if (lane == 0) {
@@ -209,6 +210,7 @@ __global__ void __launch_bounds__(512) tvf_last_horizon_stats_kernel(const LastH
             p.stats[PPO_STAT_ADV_SUMSQ] = aq;
             p.stats[PPO_STAT_ADV_MIN] = amn;
             p.stats[PPO_STAT_ADV_MAX] = amx;
+            p.stats[PPO_STAT_ADV_ZEROS] = az;
             *p.ticket = 0u;
         }
     }

@@ -448,7 +448,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
         const uint32_t P4 = static_cast<uint32_t>(P) * 4u;
         const float inv_c = p.tab.inv_c;
         // statistics of the longest horizon (want_stats): float64 partial sums of this thread
-        double st_n = 0.0, st_s = 0.0, st_q = 0.0;
+        double st_n = 0.0, st_s = 0.0, st_q = 0.0, st_z = 0.0;
         float st_mn = INFINITY, st_mx = -INFINITY;
         uint32_t it = 0;
         for (int e = 0; e < nenv; ++e) {
@@ -550,12 +550,12 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                     if (q.want_stats && quad == q.kq - 1) {
                         if (t0 < N) {
                             const float x = o0[3];
-                            st_n += 1.0, st_s += x, st_q += static_cast<double>(x) * x;
+                            st_n += 1.0, st_s += x, st_q += static_cast<double>(x) * x, st_z += x == 0.f ? 1.0 : 0.0;
                             st_mn = fminf(st_mn, x), st_mx = fmaxf(st_mx, x);
                         }
                         if (t1 < N) {
                             const float x = o1[3];
-                            st_n += 1.0, st_s += x, st_q += static_cast<double>(x) * x;
+                            st_n += 1.0, st_s += x, st_q += static_cast<double>(x) * x, st_z += x == 0.f ? 1.0 : 0.0;
                             st_mn = fminf(st_mn, x), st_mx = fmaxf(st_mx, x);
                         }
                     }
@@ -576,28 +576,30 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
             // per-CTA record: the staging ring is idle by now (every chunk has been transposed and consumed)
             asm volatile("bar.sync 1, %0;" ::"n"(kTsConsumers * 32) : "memory");
             double* red = reinterpret_cast<double*>(smem + q.off_stage);
-            const double n = warp_sum_f64(st_n), sm = warp_sum_f64(st_s), sq = warp_sum_f64(st_q);
+            const double n = warp_sum_f64(st_n), sm = warp_sum_f64(st_s), sq = warp_sum_f64(st_q), sz = warp_sum_f64(st_z);
             const float mn = warp_min_f32(st_mn), mx = warp_max_f32(st_mx);
             if (lane == 0) {
                 red[cw * 8 + 0] = n, red[cw * 8 + 1] = sm, red[cw * 8 + 2] = sq;
                 red[cw * 8 + 3] = static_cast<double>(mn), red[cw * 8 + 4] = static_cast<double>(mx);
+                red[cw * 8 + 5] = sz;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kTsConsumers * 32) : "memory");
             if (cw == 0) {
-                double an = 0, as = 0, aq = 0, amn = INFINITY, amx = -INFINITY;
+                double an = 0, as = 0, aq = 0, az = 0, amn = INFINITY, amx = -INFINITY;
                 if (lane < kTsConsumers) {
-                    an = red[lane * 8 + 0], as = red[lane * 8 + 1], aq = red[lane * 8 + 2];
+                    an = red[lane * 8 + 0], as = red[lane * 8 + 1], aq = red[lane * 8 + 2], az = red[lane * 8 + 5];
                     amn = red[lane * 8 + 3], amx = red[lane * 8 + 4];
                 }
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) {
                     an += shfl_down_f64(an, d), as += shfl_down_f64(as, d), aq += shfl_down_f64(aq, d);
+                    az += shfl_down_f64(az, d);
                     amn = fmin(amn, shfl_down_f64(amn, d)), amx = fmax(amx, shfl_down_f64(amx, d));
                 }
                 int last = 0;
                 if (lane == 0) {
                     double* rec = q.partials + static_cast<int64_t>(blockIdx.x) * 8;
-                    rec[0] = an, rec[1] = as, rec[2] = aq, rec[3] = amn, rec[4] = amx;
+                    rec[0] = an, rec[1] = as, rec[2] = aq, rec[3] = amn, rec[4] = amx, rec[5] = az;
                     __threadfence();
                     last = atomicAdd(q.ticket, 1u) == gridDim.x - 1;
                 }
@@ -605,15 +607,16 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                 if (last) {
                     // the last CTA folds all records in index order: deterministic, no float atomics
                     __threadfence();
-                    an = 0, as = 0, aq = 0, amn = INFINITY, amx = -INFINITY;
+                    an = 0, as = 0, aq = 0, az = 0, amn = INFINITY, amx = -INFINITY;
                     for (unsigned int g = lane; g < gridDim.x; g += 32) {
                         const double* rec = q.partials + static_cast<int64_t>(g) * 8;
-                        an += __ldcg(rec), as += __ldcg(rec + 1), aq += __ldcg(rec + 2);
+                        an += __ldcg(rec), as += __ldcg(rec + 1), aq += __ldcg(rec + 2), az += __ldcg(rec + 5);
                         amn = fmin(amn, __ldcg(rec + 3)), amx = fmax(amx, __ldcg(rec + 4));
                     }
 #pragma unroll
                     for (int d = 16; d > 0; d >>= 1) {
                         an += shfl_down_f64(an, d), as += shfl_down_f64(as, d), aq += shfl_down_f64(aq, d);
+                        az += shfl_down_f64(az, d);
                         amn = fmin(amn, shfl_down_f64(amn, d)), amx = fmax(amx, shfl_down_f64(amx, d));
                     }
                     if (lane == 0) {
@@ -623,6 +626,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                         q.stats[PPO_STAT_ADV_SUMSQ] = aq;
                         q.stats[PPO_STAT_ADV_MIN] = amn;
                         q.stats[PPO_STAT_ADV_MAX] = amx;
+                        q.stats[PPO_STAT_ADV_ZEROS] = az;
                         *q.ticket = 0u;
                     }
                 }

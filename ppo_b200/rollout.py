@@ -31,7 +31,7 @@ def shard_envs(array, rank, world, axis=1):
 
 
 _SUM_SLOTS = [_lib.STAT_COUNT, _lib.STAT_ADV_SUM, _lib.STAT_ADV_SUMSQ, _lib.STAT_RET_SUM, _lib.STAT_RET_SUMSQ,
-              _lib.STAT_VAL_SUM, _lib.STAT_VAL_SUMSQ, _lib.STAT_VAL_COUNT]
+              _lib.STAT_VAL_SUM, _lib.STAT_VAL_SUMSQ, _lib.STAT_VAL_COUNT, _lib.STAT_ADV_ZEROS, _lib.STAT_RET_ZEROS]
 _MIN_SLOTS = [_lib.STAT_ADV_MIN, _lib.STAT_RET_MIN]
 _MAX_SLOTS = [_lib.STAT_ADV_MAX, _lib.STAT_RET_MAX]
 
@@ -349,5 +349,6 @@ def stats_summary(stats):
     val_mean = s[_lib.STAT_VAL_SUM] / nv
     val_std = float(np.sqrt(max(s[_lib.STAT_VAL_SUMSQ] / nv - val_mean * val_mean, 0.0)))
     return {"count": int(s[_lib.STAT_COUNT]), "value_mean": val_mean, "value_std": val_std,
+            "adv_sparsity": s[_lib.STAT_ADV_ZEROS] / n, "ret_sparsity": s[_lib.STAT_RET_ZEROS] / n,
             "adv_mean": adv_mean, "adv_std": adv_std, "adv_min": s[_lib.STAT_ADV_MIN], "adv_max": s[_lib.STAT_ADV_MAX],
             "ret_mean": ret_mean, "ret_std": ret_std, "ret_min": s[_lib.STAT_RET_MIN], "ret_max": s[_lib.STAT_RET_MAX]}

@@ -57,6 +57,8 @@ def test_statistics_and_normalisation_are_consistent(full):
     assert s[_lib.STAT_COUNT] == STEPS * ENVS
     np.testing.assert_allclose(s[_lib.STAT_ADV_SUM], adv.sum().item(), rtol=1e-9, atol=1e-6)
     np.testing.assert_allclose(s[_lib.STAT_ADV_SUMSQ], (adv * adv).sum().item(), rtol=1e-9)
+    assert s[_lib.STAT_ADV_ZEROS] == (rp.advantage == 0).sum().item()
+    assert s[_lib.STAT_RET_ZEROS] == (rp.ext_returns == 0).sum().item()
     norm = rp.advantages.double()
     assert abs(norm.mean().item()) <= 1e-5 and abs(norm.std(unbiased=False).item() - 1.0) <= 1e-5
     last = rp.tvf_returns[:, :, -1].double()
@@ -64,6 +66,7 @@ def test_statistics_and_normalisation_are_consistent(full):
     assert t[_lib.STAT_COUNT] == STEPS * ENVS
     np.testing.assert_allclose(t[_lib.STAT_ADV_SUM], last.sum().item(), rtol=1e-9)
     assert t[_lib.STAT_ADV_MIN] == last.min().item() and t[_lib.STAT_ADV_MAX] == last.max().item()
+    assert t[_lib.STAT_ADV_ZEROS] == (last == 0).sum().item()
 
 
 def test_linearity_is_exact_for_powers_of_two(full):

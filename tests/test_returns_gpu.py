@@ -64,9 +64,13 @@ def test_gae_strided_and_device_inputs():
 
 def test_gae_stats_and_empty():
     r, d, v = synthetic.rollout(96, 200, seed=5)
+    r[:, 7:40:3], v[:, 7:40:3] = 0.0, 0.0  # silent envs: exact zeros for the sparsity the logger reports (rl/logger.py:201-229)
+    r[50:, 100] = 0.0
+    v[50:, 100] = 0.0
     adv, ret, stats = returns.gae_td_lambda(r, v[:-1], v[-1], d, 0.999, 0.95, 0.9, with_stats=True)
     s = stats.cpu().numpy()
     assert s[0] == adv.size
+    assert s[12] == np.count_nonzero(adv == 0) > 0 and s[13] == np.count_nonzero(ret == 0) > 0
     np.testing.assert_allclose(s[1], adv.astype(np.float64).sum(), rtol=1e-12)
     np.testing.assert_allclose(s[2], (adv.astype(np.float64) ** 2).sum(), rtol=1e-12)
     assert s[3] == adv.min() and s[4] == adv.max()

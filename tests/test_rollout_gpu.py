@@ -53,6 +53,7 @@ def test_calculate_returns_matches_oracle():
     np.testing.assert_allclose(summary["adv_std"], adv.astype(np.float64).std(), rtol=1e-9)
     np.testing.assert_allclose(summary["value_mean"], v.astype(np.float64).mean(), rtol=1e-9)
     np.testing.assert_allclose(summary["value_std"], v.astype(np.float64).std(), rtol=1e-9)
+    assert summary["adv_sparsity"] == np.mean(adv == 0) and summary["ret_sparsity"] == np.mean(res["ext_returns"] == 0)
     t = rollout.stats_summary(res["tvf_stats"])
     last = np.asarray(res["tvf_returns"])[:, :, -1].astype(np.float64)
     assert t["adv_min"] == last.min() and t["adv_max"] == last.max()

@@ -127,6 +127,7 @@ def test_tslab_fused_statistics_and_large_rewards():
     r = (rng.rand(steps, envs) * 3 + 1).astype(np.float32)
     d = np.zeros((steps, envs), dtype=bool)
     vs = synthetic.value_samples(steps, envs, len(hz), seed=4)
+    r[:, 5:11], vs[:, 5:11] = 0.0, 0.0  # silent envs: exact zeros, counted for the logger's sparsity (rl/logger.py:201-229)
     table = oracle.draw_n_step_samples("exponential", "advanced", hz, steps, 20, 8, seed=2)
     ref = oracle.sampled_return_multi(0.99997, r, d, hz, hz, vs, n_step_samples=table)
     res, stats = rt._launch(0.99997, r, d, hz, hz, vs, table, False, path=rt.PATH_TSLAB, with_stats=True)
@@ -141,6 +142,7 @@ def test_tslab_fused_statistics_and_large_rewards():
     s = stats.cpu().numpy()
     last = res[:, :, -1].astype(np.float64)
     assert s[0] == last.size and s[3] == last.min() and s[4] == last.max()
+    assert s[12] == np.count_nonzero(last == 0) == 6 * steps
     np.testing.assert_allclose(s[1], last.sum(), rtol=1e-12)
     np.testing.assert_allclose(s[2], (last ** 2).sum(), rtol=1e-12)
 
@@ -163,6 +165,7 @@ def test_device_tensors_strided_values_and_stats():
     full = np.stack([synthetic.value_samples(steps, envs, len(hz), seed=2),
                      synthetic.value_samples(steps, envs, len(hz), seed=3)], axis=-1)  # [N+1, A, K, VH]
     vs = full[..., 1]  # rl/tvf.py:248 strided view
+    r[:, 3:9], full[:, 3:9] = 0.0, 0.0
     table = oracle.draw_n_step_samples("exponential", "advanced", hz, steps, 10, 4, seed=1)
     ref = oracle.sampled_return_multi(0.999, r, d, hz, hz, vs, n_step_samples=table)
     got = rt._calculate_sampled_return_multi_fast(
@@ -174,6 +177,7 @@ def test_device_tensors_strided_values_and_stats():
     s = stats.cpu().numpy()
     last = res[:, :, -1].astype(np.float64)
     assert s[0] == last.size and s[3] == last.min() and s[4] == last.max()
+    assert s[12] == np.count_nonzero(last == 0) >= 6 * steps  # also zero reward on a terminal step
     np.testing.assert_allclose(s[1], last.sum(), rtol=1e-12)
     np.testing.assert_allclose(s[2], (last ** 2).sum(), rtol=1e-12)
 
