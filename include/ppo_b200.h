@@ -348,6 +348,40 @@ int ppo_vtrace_trust_region(const float* behaviour_log_policy, const float* targ
                             int64_t rows, int64_t n_actions, float* out, void* stream);
 
 /*
+ * Forward return trackers and running moments: intrinsic-return normalisation (rl/rollout.py:1147-1165,
+ * Runner.calculate_intrinsic_returns) and reward normalisation (rl/wrappers.py:795-885, VecNormalizeRewardWrapper.step)
+ * over a whole [N, A] rollout.  Both run  x_t = r_t + gamma * (1 - done_t) * x_{t-1}  forwards in time with a float64
+ * carry per env that survives between rollouts (`ems_norm`, rl/rollout.py:280; `current_returns`, rl/wrappers.py:826),
+ * and after every step merge the batch mean / variance of x_t over the envs into a running (mean, var, count)
+ * (rl/utils.py:379-443 RunningMeanStd.update).
+ *
+ * ppo_return_tracker_scan: carry [A] float64 in/out; tracker_out [N, A] float64 (row t = x_t).  done_kind NONE is
+ *   `ir.propagation` (rl/rollout.py:1151: terminals are ignored).
+ * ppo_row_sums: out[t] = sum_a x[t, a]  (row_sums == NULL)  or  sum_a (x[t, a] - row_sums[t] / total_envs)^2, the two
+ *   passes of np.mean / np.var; env-sharded callers all-reduce `out` (sum) between the two calls.
+ * ppo_rms_fold: the N merges in step order.  rms = {mean, var, count} in/out (device); row_var [N] (optional) receives
+ *   the running variance after each step.
+ * ppo_scale_rewards: out[t, a] = clip((r[t, a] - shift) / s, +-clip) * scale with
+ *   PPO_SCALE_INTRINSIC  s = eps + sqrt(var)   (rl/rollout.py:1164-1165, eps = 1e-5), var = var[0] or var[t] (per_row)
+ *   PPO_SCALE_WRAPPER    s = sqrt(var + eps)   (rl/wrappers.py:893-895, eps = 1e-2)
+ *   clip < 0 disables clipping (rl/wrappers.py:873); center_stats != NULL: shift = mean of the raw rewards from a
+ *   ppo_moments record (`ir.center`, rl/rollout.py:1167-1168), else 0; clips (optional) is incremented by the number of
+ *   clipped elements (rl/wrappers.py:876).
+ */
+typedef enum { PPO_SCALE_INTRINSIC = 0, PPO_SCALE_WRAPPER = 1 } ppo_scale_mode;
+
+int ppo_return_tracker_scan(const float* rewards, int64_t reward_row_stride, const void* dones, int done_kind,
+                            int64_t done_row_stride, int64_t steps, int64_t envs, double gamma, double* carry,
+                            double* tracker_out, void* stream);
+int ppo_row_sums(const double* x, int64_t steps, int64_t envs, const double* row_sums, double total_envs, double* out,
+                 void* stream);
+int ppo_rms_fold(const double* row_sums, const double* row_sq, int64_t steps, double total_envs, double* rms,
+                 double* row_var, void* stream);
+int ppo_scale_rewards(const float* rewards, int64_t reward_row_stride, int64_t steps, int64_t envs, const double* var,
+                      int per_row, int mode, double eps, double clip, double scale, const double* center_stats,
+                      float* out, unsigned long long* clips, void* stream);
+
+/*
  * Stream-ordered strided copy between host (pinned) and device memory: `rows` rows of `width_bytes`, any direction.
  * Plumbing for calls whose rollout buffers live in host memory (the reference keeps them in NumPy arrays,
  * rl/rollout.py:646-680): an env block of a [N, A, K] host buffer is `N` rows of `A_block * K * 4` bytes with the

@@ -29,3 +29,4 @@ from .tvf_np import (  # noqa: F401
     trim_horizons,
 )
 from .vtrace_np import importance_sampling_v_trace, v_trace_trust_region  # noqa: F401
+from .normalization_np import RunningMeanStd, intrinsic_returns, vec_normalize_rewards  # noqa: F401

@@ -1,0 +1,82 @@
+"""CPU oracle (NumPy): return trackers and running moments around the hot path.  TEST INFRASTRUCTURE ONLY.
+
+Restates, in the reference's own order of operations:
+
+* ``RunningMeanStd`` / ``update_mean_var_count_from_moments``  (``rl/utils.py:379-396, 414-443``)
+* ``Runner.calculate_intrinsic_returns``                      (``rl/rollout.py:1140-1180``)
+* ``VecNormalizeRewardWrapper.step`` run over a whole rollout  (``rl/wrappers.py:795-895``), mode "rms", no episodic
+  discounting (``ed_type=None``), identity ``returns_transform``
+
+Pinned against outputs of the reference's own source for these pieces, executed by ``tests/golden/make_golden.py``
+(``tests/golden/normalization_vectors.npz``; ``tests/test_oracle_golden.py``).
+"""
+import math
+
+import numpy as np
+
+from .returns_np import gae
+
+
+class RunningMeanStd:
+    """rl/utils.py:414-443 (scalar shape)."""
+
+    def __init__(self, epsilon=1e-4):
+        self.mean = np.float64(0.0)
+        self.var = np.float64(1.0)
+        self.count = epsilon
+
+    def update(self, x):  # rl/utils.py:425-435
+        x = np.asarray(x)
+        self.update_from_moments(np.mean(x, axis=0), np.var(x, axis=0), x.shape[0])
+
+    def update_from_moments(self, batch_mean, batch_var, batch_count):  # rl/utils.py:379-396
+        delta = batch_mean - self.mean
+        tot_count = self.count + batch_count
+        new_mean = self.mean + delta * batch_count / tot_count
+        m_a = self.var * self.count
+        m_b = batch_var * batch_count
+        m2 = m_a + m_b + np.square(delta) * self.count * batch_count / tot_count
+        self.mean, self.var, self.count = new_mean, m2 / tot_count, tot_count
+
+    def state(self):
+        return np.asarray([self.mean, self.var, self.count], dtype=np.float64)
+
+
+def intrinsic_returns(int_rewards, int_value, terminals, gamma_int, lambda_policy, ems_norm, rms,
+                      normalize=True, center=False, propagation=False):
+    """rl/rollout.py:1140-1180.  ``ems_norm`` [A] float64 and ``rms`` are updated in place like the runner's state.
+    Returns (int_advantage, int_returns, normalised int_rewards, scale)."""
+    int_rewards = np.asarray(int_rewards)
+    steps = int_rewards.shape[0]
+    scale = 1.0
+    if normalize:
+        for t in range(steps):  # :1150-1153
+            term = (not propagation) * terminals[t, :]
+            ems_norm[:] = (1 - term) * gamma_int * ems_norm + int_rewards[t, :]
+            rms.update(ems_norm.reshape(-1))
+        scale = 1e-5 + rms.var ** 0.5  # :1164
+        int_rewards = int_rewards / scale  # :1165
+    if center:
+        int_rewards = int_rewards - int_rewards.mean()  # :1167-1168
+    adv = gae(int_rewards, int_value[:steps], int_value[steps], (not propagation) * terminals,
+              gamma=gamma_int, lamb=lambda_policy)  # :1170-1177
+    return adv, adv + int_value[:steps], int_rewards, scale
+
+
+def vec_normalize_rewards(rewards, dones, gamma, current_returns, rms, clip=10.0, scale=1.0, epsilon=1e-2):
+    """rl/wrappers.py:825-885 applied to each row of a [N, A] rollout in order.  ``current_returns`` [A] and ``rms``
+    are updated in place.  Returns (scaled rewards [N, A], number of clipped elements)."""
+    rewards = np.asarray(rewards)
+    out = np.zeros(rewards.shape, dtype=np.float64)
+    clips = 0
+    for t in range(rewards.shape[0]):
+        current_returns[:] = rewards[t] + gamma * current_returns * (1 - dones[t])  # :847
+        rms.update(current_returns)  # :856 (norms = 1, identity transform)
+        std = math.sqrt(rms.var + epsilon)  # :893-895
+        scaled = rewards[t] / std  # :863
+        if clip is not None and clip >= 0:  # :866-873
+            clipped = np.clip(scaled, -clip, +clip)
+            clips += int(np.sum(clipped != scaled))
+            scaled = clipped
+        out[t] = scaled * scale  # :875
+    return out, clips

@@ -7,6 +7,8 @@ Drop-in modules (same function names and signatures as the reference's ``rl`` pa
 * :mod:`ppo_b200.tvf`                <- ``rl/tvf.py``                (``get_value_head_horizons``, ``TVFRunnerModule`` return-side methods)
 * :mod:`ppo_b200.vtrace`             <- ``rl/vtrace.py``             (``importance_sampling_v_trace``, ``v_trace_trust_region``)
 * :mod:`ppo_b200.rollout`            <- the return stage of ``rl/rollout.py`` (``calculate_returns``, ``normalize_advantages``)
+* :mod:`ppo_b200.normalization`      <- ``Runner.calculate_intrinsic_returns`` (``rl/rollout.py:1140-1180``), ``VecNormalizeRewardWrapper``
+  (``rl/wrappers.py:795-919``) and ``RunningMeanStd`` (``rl/utils.py:414-443``) over whole rollouts
 
 All arithmetic on rollout data runs in hand-written sm_100a CUDA kernels behind the C ABI of
 ``include/ppo_b200.h`` (``ppo_b200/csrc``).  There is no CPU fallback: without the built library or

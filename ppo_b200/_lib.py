@@ -28,6 +28,7 @@ STAT_COUNT, STAT_ADV_SUM, STAT_ADV_SUMSQ, STAT_ADV_MIN, STAT_ADV_MAX = 0, 1, 2, 
 STAT_RET_SUM, STAT_RET_SUMSQ, STAT_RET_MIN, STAT_RET_MAX = 5, 6, 7, 8
 STAT_VAL_SUM, STAT_VAL_SUMSQ, STAT_VAL_COUNT = 9, 10, 11
 STAT_ADV_ZEROS, STAT_RET_ZEROS = 12, 13
+SCALE_INTRINSIC, SCALE_WRAPPER = 0, 1
 
 # name -> (restype, argtypes); must match include/ppo_b200.h
 _SIGNATURES = {
@@ -64,6 +65,11 @@ _SIGNATURES = {
     "ppo_vtrace_trust_region": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "ppo_discounted_returns": (c_int, [c_ptr, c_i64, c_ptr, c_int, c_i64, c_ptr, c_i64, c_dbl, c_ptr, c_i64,
                                        c_i64, c_i64, c_ptr, c_ptr]),
+    "ppo_return_tracker_scan": (c_int, [c_ptr, c_i64, c_ptr, c_int, c_i64, c_i64, c_i64, c_dbl, c_ptr, c_ptr, c_ptr]),
+    "ppo_row_sums": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_dbl, c_ptr, c_ptr]),
+    "ppo_rms_fold": (c_int, [c_ptr, c_ptr, c_i64, c_dbl, c_ptr, c_ptr, c_ptr]),
+    "ppo_scale_rewards": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_int, c_int, c_dbl, c_dbl, c_dbl, c_ptr, c_ptr,
+                                  c_ptr, c_ptr]),
 }
 
 _lock = threading.Lock()

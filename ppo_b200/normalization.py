@@ -1,0 +1,212 @@
+"""Return trackers and running moments around the hot path, on the device (``ppo_b200/csrc/return_tracker.cu``).
+
+Mirrors, with the reference's names and state:
+
+* ``RunningMeanStd``                       ``rl/utils.py:414-443`` (scalar shape); state {mean, var, count} lives on the GPU
+* ``IntrinsicReturns.calculate_intrinsic_returns``   ``Runner.calculate_intrinsic_returns``, ``rl/rollout.py:1140-1180``
+  (state ``ems_norm`` [A] float64 and ``intrinsic_returns_rms``, ``rl/rollout.py:279-280``)
+* ``VecNormalizeRewards.normalize_rollout``          ``VecNormalizeRewardWrapper.step`` (``rl/wrappers.py:795-895``, mode
+  "rms") applied to the N rows of a rollout in order (state ``current_returns`` [A] and ``ret_rms``)
+
+Both are the forward recurrence ``x_t = r_t + gamma * (1 - done_t) * x_{t-1}`` followed, step by step, by a merge of the
+batch moments of ``x_t`` over the envs into the running moments.  The reference does N NumPy passes; here one scan
+launch, two row-reduction launches and one fold.  With envs sharded over ranks (``group``) the only exchange is the
+all-reduce of the two [N] row vectors.  No CPU fallback.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _device as dev
+from . import _lib
+from . import returns as _returns
+from . import rollout as _rollout
+
+
+def _world(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group)
+    return 1
+
+
+class RunningMeanStd:
+    """Running mean / variance book-keeping (``rl/utils.py:414-443``), scalar shape, state on the device."""
+
+    def __init__(self, epsilon=1e-4, shape=(), device=None):
+        if tuple(shape) != ():
+            raise ValueError("only the scalar RunningMeanStd (shape=()) of the return trackers is provided")
+        self.device = device or dev.require_cuda()
+        self.state = torch.tensor([0.0, 1.0, float(epsilon)], dtype=torch.float64, device=self.device)
+
+    mean = property(lambda self: float(self.state[0].item()))
+    var = property(lambda self: float(self.state[1].item()))
+    count = property(lambda self: float(self.state[2].item()))
+
+    def update(self, x, group=None):
+        """One merge of the batch ``x`` (1-D; a float / int counts as a batch of one, ``rl/utils.py:427-430``)."""
+        if type(x) in (float, int):
+            self.update_from_moments(x, 0.0, 1)
+            return
+        t = dev.to_device(x, torch.float64, self.device).reshape(1, -1).contiguous()
+        _fold_rows(t, self.state, group, None)
+
+    def update_from_moments(self, batch_mean, batch_var, batch_count):
+        lib = _lib.load()
+        n = float(batch_count)
+        sums = torch.tensor([float(batch_mean) * n], dtype=torch.float64, device=self.device)
+        sq = torch.tensor([float(batch_var) * n], dtype=torch.float64, device=self.device)
+        _lib.check(lib.ppo_rms_fold(dev.ptr(sums), dev.ptr(sq), 1, n, dev.ptr(self.state), 0, dev.stream_ptr()),
+                   "ppo_rms_fold")
+
+    def save_state(self):
+        s = self.state.cpu().numpy()
+        return tuple([s[0], s[1], s[2]])
+
+    def restore_state(self, state):
+        self.state.copy_(torch.as_tensor([float(v) for v in state], dtype=torch.float64))
+
+
+def _fold_rows(x, rms_state, group, row_var):
+    """Merge every row of the float64 [N, A] tracker ``x`` into ``rms_state`` in row order."""
+    lib = _lib.load()
+    steps, envs = x.shape
+    s = dev.stream_ptr()
+    sums = torch.empty(steps, dtype=torch.float64, device=x.device)
+    sq = torch.empty(steps, dtype=torch.float64, device=x.device)
+    total = float(envs * _world(group))
+    _lib.check(lib.ppo_row_sums(dev.ptr(x), steps, envs, 0, total, dev.ptr(sums), s), "ppo_row_sums")
+    if _world(group) > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    _lib.check(lib.ppo_row_sums(dev.ptr(x), steps, envs, dev.ptr(sums), total, dev.ptr(sq), s), "ppo_row_sums")
+    if _world(group) > 1:
+        dist.all_reduce(sq, op=dist.ReduceOp.SUM, group=group)
+    _lib.check(lib.ppo_rms_fold(dev.ptr(sums), dev.ptr(sq), steps, total, dev.ptr(rms_state), dev.ptr(row_var), s),
+               "ppo_rms_fold")
+
+
+def track_returns(rewards, dones, gamma, carry, rms, group=None, want_row_var=False):
+    """The tracker scan + the N moment merges.  ``carry`` (float64 device tensor [A]) and ``rms`` are updated in
+    place; returns (rewards on the device, running variance after each step [N] or None)."""
+    device = dev.require_cuda()
+    lib = _lib.load()
+    r = dev.env_contiguous(dev.to_device(rewards, torch.float32, device))
+    if r.dim() != 2:
+        raise ValueError(f"rewards must be [N, A], got {tuple(r.shape)}")
+    steps, envs = r.shape
+    if tuple(carry.shape) != (envs,) or carry.dtype != torch.float64 or not carry.is_cuda:
+        raise ValueError(f"carry must be a float64 CUDA tensor of shape {(envs,)}")
+    d, kind = dev.done_tensor(dones, device)
+    if d is not None:
+        if tuple(d.shape) != (steps, envs):
+            raise ValueError(f"operands could not be broadcast together: dones {tuple(d.shape)} vs {(steps, envs)}")
+        d = dev.env_contiguous(d)
+    x = torch.empty((steps, envs), dtype=torch.float64, device=device)
+    rc = lib.ppo_return_tracker_scan(dev.ptr(r), r.stride(0) if steps else 0, dev.ptr(d), kind,
+                                     d.stride(0) if d is not None and steps else 0, steps, envs, float(gamma),
+                                     dev.ptr(carry), dev.ptr(x), dev.stream_ptr())
+    _lib.check(rc, "ppo_return_tracker_scan")
+    row_var = torch.empty(steps, dtype=torch.float64, device=device) if want_row_var else None
+    if steps and envs:
+        _fold_rows(x, rms.state, group, row_var)
+    return r, row_var
+
+
+def _scale(r, var, per_row, mode, eps, clip, scale, center_stats, clips):
+    lib = _lib.load()
+    steps, envs = r.shape
+    out = torch.empty((steps, envs), dtype=torch.float32, device=r.device)
+    rc = lib.ppo_scale_rewards(dev.ptr(r), r.stride(0) if steps else 0, steps, envs, dev.ptr(var), int(per_row), mode,
+                               float(eps), float(clip), float(scale), dev.ptr(center_stats), dev.ptr(out),
+                               dev.ptr(clips), dev.stream_ptr())
+    _lib.check(rc, "ppo_scale_rewards")
+    return out
+
+
+class IntrinsicReturns:
+    """The runner state and method of ``rl/rollout.py:279-280, 1140-1180``."""
+
+    def __init__(self, envs, device=None):
+        self.device = device or dev.require_cuda()
+        self.ems_norm = torch.zeros(envs, dtype=torch.float64, device=self.device)
+        self.intrinsic_returns_rms = RunningMeanStd(shape=(), device=self.device)
+        self.intrinsic_reward_norm_scale = 1.0
+
+    def calculate_intrinsic_returns(self, int_rewards, int_value, terminals, gamma_int, lambda_policy=0.95,
+                                    normalize=True, center=False, propagation=False, group=None):
+        """``args.ir.normalize / center / propagation`` are the keyword arguments.  Returns a dict with
+        ``int_advantage`` [N, A] (the reference's return value), ``int_returns`` [N, A] (``self.int_returns``),
+        ``int_rewards`` (the normalised rewards the reference writes back to ``self.int_rewards``) and ``scale``
+        (a device float64 scalar; ``self.intrinsic_reward_norm_scale`` reads it)."""
+        np_like = dev.is_numpy_like(int_rewards)
+        device = self.device
+        r = dev.env_contiguous(dev.to_device(int_rewards, torch.float32, device))
+        steps, envs = r.shape
+        value = dev.to_device(int_value, torch.float32, device)
+        if tuple(value.shape) != (steps + 1, envs):
+            raise ValueError(f"int_value must be [N + 1, A] = {(steps + 1, envs)}, got {tuple(value.shape)}")
+        dones = None if propagation else terminals  # rl/rollout.py:1151,1174: `(not propagation) * terminals`
+        scale = torch.ones((), dtype=torch.float64, device=device)
+        if normalize:
+            track_returns(r, dones, gamma_int, self.ems_norm, self.intrinsic_returns_rms, group=group)
+            var = self.intrinsic_returns_rms.state[1:2]
+            scale = 1e-5 + var[0].sqrt()  # rl/rollout.py:1164 (device scalar, no synchronisation)
+        else:
+            var = torch.zeros(1, dtype=torch.float64, device=device)
+        if normalize or center:
+            stats = None
+            if center:  # rl/rollout.py:1167-1168: the mean over every env of every rank
+                stats = _rollout.allreduce_moments(_rollout.moments(r), group)
+            # eps 1e-5 (rl/rollout.py:1164); without normalisation the divisor is exactly 1
+            r = _scale(r, var if normalize else torch.ones_like(var), False, _lib.SCALE_INTRINSIC,
+                       1e-5 if normalize else 0.0, -1.0, 1.0, stats, None)
+        adv, ret, _ = _returns._gae_launch(r, value[:steps], value[steps], dones, gamma_int, lambda_policy,
+                                           lambda_policy, True, True, False)
+        self.intrinsic_reward_norm_scale = scale
+        return {"int_advantage": dev.like_input(adv, np_like), "int_returns": dev.like_input(ret, np_like),
+                "int_rewards": dev.like_input(r, np_like), "scale": scale}
+
+
+class VecNormalizeRewards:
+    """``VecNormalizeRewardWrapper`` (``rl/wrappers.py:795-919``, mode "rms", ``ed_type=None``) over whole rollouts:
+    rewards are divided by the running return std AS OF THEIR OWN STEP, clipped and scaled."""
+
+    def __init__(self, num_envs, initial_state=None, gamma=1.0, clip=10.0, scale=1.0, mode="rms", device=None):
+        if mode != "rms":
+            raise ValueError(f"Invalid mode {mode}: only 'rms' is provided")
+        self.device = device or dev.require_cuda()
+        self.clip, self.epsilon, self.gamma, self.scale = clip, 1e-2, gamma, scale
+        self.current_returns = torch.zeros(num_envs, dtype=torch.float64, device=self.device)
+        self.ret_rms = RunningMeanStd(shape=(), device=self.device)
+        if initial_state is not None:
+            self.ret_rms.restore_state(initial_state)
+
+    def reset(self):
+        self.current_returns.zero_()
+
+    @property
+    def mean(self):
+        return self.ret_rms.mean
+
+    @property
+    def std(self):
+        return float(np.sqrt(self.ret_rms.var + self.epsilon))
+
+    def normalize_rollout(self, rewards, dones, group=None):
+        """[N, A] raw rewards and dones -> (scaled rewards [N, A] float32, number of clipped elements as a device
+        counter)."""
+        np_like = dev.is_numpy_like(rewards)
+        r, row_var = track_returns(rewards, dones, self.gamma, self.current_returns, self.ret_rms, group=group,
+                                   want_row_var=True)
+        clips = torch.zeros(1, dtype=torch.int64, device=self.device)
+        clip = -1.0 if self.clip is None else float(self.clip)
+        out = _scale(r, row_var, True, _lib.SCALE_WRAPPER, self.epsilon, clip, self.scale, None, clips)
+        return dev.like_input(out, np_like), clips
+
+    def save_state(self, buffer):
+        buffer["ret_rms"] = self.ret_rms.save_state()
+        buffer["ret_var"] = 0.0
+        buffer["current_returns"] = self.current_returns.cpu().numpy()
+
+    def restore_state(self, buffer):
+        self.ret_rms.restore_state(buffer["ret_rms"])
+        self.current_returns.copy_(torch.as_tensor(np.asarray(buffer["current_returns"], dtype=np.float64)))

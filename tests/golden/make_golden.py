@@ -74,6 +74,117 @@ def _zero_h0(vs):
     return vs
 
 
+def reference_source(root, rel, name, method=None):
+    """Source text of a top-level function / class (or one method of a class) of a reference file that cannot be
+    imported as a module (``rl/utils.py``, ``rl/wrappers.py`` and ``rl/rollout.py`` pull in gym, cv2 and removed
+    NumPy aliases).  The text is executed as is, never stored."""
+    import ast
+    import textwrap
+    text = open(os.path.join(root, rel)).read()
+    for node in ast.parse(text).body:
+        if getattr(node, "name", None) != name:
+            continue
+        if method is None:
+            return ast.get_source_segment(text, node)
+        for sub in node.body:
+            if getattr(sub, "name", None) == method:
+                lines = text.splitlines()[sub.lineno - 1:sub.end_lineno]
+                return textwrap.dedent("\n".join(lines))
+    raise KeyError(f"{name}.{method} not found in {rel}")
+
+
+def normalization_vectors(root, ref):
+    """Return trackers + running moments: RunningMeanStd (rl/utils.py:379-443), Runner.calculate_intrinsic_returns
+    (rl/rollout.py:1140-1180) and VecNormalizeRewardWrapper (rl/wrappers.py:795-919), run from the reference's own
+    source text with stand-in runner / env objects."""
+    import math
+    import typing
+    out = {}
+    ns = {"np": np}
+    exec(reference_source(root, "rl/utils.py", "update_mean_var_count_from_moments"), ns)
+    exec(reference_source(root, "rl/utils.py", "RunningMeanStd"), ns)
+    rms_cls = ns["RunningMeanStd"]
+
+    # ---- RunningMeanStd on its own
+    rng = np.random.RandomState(5)
+    rms = rms_cls(shape=())
+    batches = [rng.normal(3.0, 2.0, size=n) for n in (1, 7, 64, 5)]
+    states = []
+    for b in batches:
+        rms.update(b)
+        states.append([rms.mean, rms.var, rms.count])
+    out["rms_in_batches"] = np.concatenate(batches)
+    out["rms_in_sizes"] = np.asarray([len(b) for b in batches])
+    out["rms_states"] = np.asarray(states, dtype=np.float64)
+
+    # ---- Runner.calculate_intrinsic_returns over two consecutive rollouts (the carry and the moments persist)
+    steps, envs = 40, 24
+    src = reference_source(root, "rl/rollout.py", "Runner", "calculate_intrinsic_returns")
+    for tag, normalize, center, propagation in [("norm", True, False, False), ("center", True, True, False),
+                                                ("prop", True, False, True), ("raw", False, True, False)]:
+        args = types.SimpleNamespace(use_intrinsic_rewards=True, gamma_int=0.99, lambda_policy=0.95,
+                                     ir=types.SimpleNamespace(normalize=normalize, center=center,
+                                                              propagation=propagation))
+        fns = {"np": np, "args": args, "gae": ref.returns.gae}
+        exec(src, fns)
+        runner = types.SimpleNamespace(N=steps, intrinsic_returns_rms=rms_cls(shape=()), ems_norm=np.zeros([envs]),
+                                       intrinsic_reward_norm_scale=1, int_returns=np.zeros([steps, envs], np.float32),
+                                       prev_obs=np.zeros([steps, envs, 1]))
+        for roll in range(2):
+            rng = np.random.RandomState(100 + roll)
+            runner.int_rewards = np.abs(rng.normal(0.2, 0.3, [steps, envs])).astype(np.float32)
+            runner.terminals = rng.random_sample([steps, envs]) < 0.05
+            runner.int_value = rng.normal(0.5, 0.4, [steps + 1, envs]).astype(np.float32)
+            if tag == "norm":
+                out[f"ir_in_rewards_{roll}"], out[f"ir_in_terminals_{roll}"] = runner.int_rewards, runner.terminals
+                out[f"ir_in_value_{roll}"] = runner.int_value
+            adv = fns["calculate_intrinsic_returns"](runner)
+            out[f"ir_{tag}_adv_{roll}"] = np.asarray(adv)
+            out[f"ir_{tag}_returns_{roll}"] = runner.int_returns.copy()
+            out[f"ir_{tag}_rewards_{roll}"] = np.asarray(runner.int_rewards)
+            out[f"ir_{tag}_scale_{roll}"] = np.asarray(runner.intrinsic_reward_norm_scale, dtype=np.float64)
+            out[f"ir_{tag}_ems_{roll}"] = runner.ems_norm.copy()
+            r = runner.intrinsic_returns_rms
+            out[f"ir_{tag}_rms_{roll}"] = np.asarray([r.mean, r.var, r.count], dtype=np.float64)
+
+    # ---- VecNormalizeRewardWrapper.step over a rollout, fed by a stand-in vector env
+    gym = types.SimpleNamespace(Wrapper=type("Wrapper", (), {"__init__": lambda self, env: setattr(self, "env", env)}))
+    wns = {"np": np, "math": math, "gym": gym, "utils": types.SimpleNamespace(RunningMeanStd=rms_cls),
+           "VectorEnv": object, "Optional": typing.Optional, "EpisodicDiscounting": None}
+    exec(reference_source(root, "rl/wrappers.py", "VecNormalizeRewardWrapper"), wns)
+    rng = np.random.RandomState(9)
+    steps, envs = 50, 16
+    rewards = (rng.randint(-1, 3, size=[steps, envs]) * rng.choice([1.0, 30.0], size=[steps, envs], p=[0.9, 0.1]))
+    rewards = rewards.astype(np.float32)
+    dones = rng.random_sample([steps, envs]) < 0.04
+    out["vn_in_rewards"], out["vn_in_dones"] = rewards, dones
+
+    class Env:
+        num_envs = envs
+
+        def __init__(self):
+            self.t = 0
+
+        def step(self, actions):
+            t = self.t
+            self.t += 1
+            return None, rewards[t], dones[t], [{} for _ in range(envs)]
+
+    for tag, kwargs in [("default", dict(gamma=0.99)), ("noclip", dict(gamma=0.999, clip=-1, scale=0.5)),
+                        ("tight", dict(gamma=0.9, clip=1.0))]:
+        w = wns["VecNormalizeRewardWrapper"](Env(), **kwargs)
+        rows, clips = [], 0
+        for t in range(steps):
+            _, scaled, _, infos = w.step(None)
+            rows.append(np.asarray(scaled, dtype=np.float64))
+            clips += int(infos[0].get("reward_clips", 0))
+        out[f"vn_{tag}_scaled"] = np.stack(rows)
+        out[f"vn_{tag}_clips"] = np.asarray(clips)
+        out[f"vn_{tag}_returns"] = np.asarray(w.current_returns, dtype=np.float64)
+        out[f"vn_{tag}_rms"] = np.asarray([w.ret_rms.mean, w.ret_rms.var, w.ret_rms.count], dtype=np.float64)
+    return out
+
+
 def main():
     root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     ref = load_reference(root)
@@ -208,6 +319,11 @@ def main():
     path = os.path.join(HERE, "reference_vectors.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.1f} KiB")
+
+    norm = normalization_vectors(root, ref)
+    path = os.path.join(HERE, "normalization_vectors.npz")
+    np.savez_compressed(path, **norm)
+    print(f"wrote {path}: {len(norm)} arrays, {os.path.getsize(path) / 1024:.1f} KiB")
 
 
 if __name__ == "__main__":

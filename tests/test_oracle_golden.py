@@ -158,3 +158,43 @@ def test_vtrace(golden):
     gae = oracle.gae(r, v[:-1], v[-1], d, 0.99, 1.0)
     assert np.abs(vs - ret).max() <= 1e-5 * np.abs(ret).max()
     assert np.abs(adv - gae).max() <= 1e-5 * np.abs(gae).max()
+
+
+def test_running_mean_std(golden_norm):
+    """rl/utils.py:379-443, bit for bit."""
+    g = golden_norm
+    rms, at, states = oracle.RunningMeanStd(), 0, []
+    for n in g["rms_in_sizes"]:
+        rms.update(g["rms_in_batches"][at:at + n])
+        at += n
+        states.append(rms.state())
+    assert same(np.asarray(states), g["rms_states"])
+
+
+def test_intrinsic_returns(golden_norm):
+    """Runner.calculate_intrinsic_returns (rl/rollout.py:1140-1180) over two consecutive rollouts, bit for bit."""
+    g = golden_norm
+    for tag, normalize, center, propagation in [("norm", True, False, False), ("center", True, True, False),
+                                                ("prop", True, False, True), ("raw", False, True, False)]:
+        ems, rms = np.zeros(g["ir_in_rewards_0"].shape[1]), oracle.RunningMeanStd()
+        for roll in range(2):
+            adv, ret, rew, scale = oracle.intrinsic_returns(
+                g[f"ir_in_rewards_{roll}"], g[f"ir_in_value_{roll}"], g[f"ir_in_terminals_{roll}"], 0.99, 0.95, ems,
+                rms, normalize=normalize, center=center, propagation=propagation)
+            assert same(adv, g[f"ir_{tag}_adv_{roll}"]) and same(rew, g[f"ir_{tag}_rewards_{roll}"]), tag
+            assert same(ret.astype(np.float32), g[f"ir_{tag}_returns_{roll}"]), tag
+            assert same(np.asarray(scale, dtype=np.float64), g[f"ir_{tag}_scale_{roll}"])
+            assert same(ems, g[f"ir_{tag}_ems_{roll}"]) and same(rms.state(), g[f"ir_{tag}_rms_{roll}"])
+
+
+def test_vec_normalize_rewards(golden_norm):
+    """VecNormalizeRewardWrapper.step (rl/wrappers.py:795-895) over a rollout, bit for bit."""
+    g = golden_norm
+    for tag, kwargs in [("default", dict(gamma=0.99)), ("noclip", dict(gamma=0.999, clip=-1, scale=0.5)),
+                        ("tight", dict(gamma=0.9, clip=1.0))]:
+        cur, rms = np.zeros(g["vn_in_rewards"].shape[1], dtype=np.float32), oracle.RunningMeanStd()
+        cur = cur.astype(np.float64)  # the reference's float32 carry becomes float64 after the first step (:847)
+        scaled, clips = oracle.vec_normalize_rewards(g["vn_in_rewards"], g["vn_in_dones"], kwargs["gamma"], cur, rms,
+                                                     clip=kwargs.get("clip", 10.0), scale=kwargs.get("scale", 1.0))
+        assert same(scaled, g[f"vn_{tag}_scaled"]) and clips == int(g[f"vn_{tag}_clips"]), tag
+        assert same(cur, g[f"vn_{tag}_returns"]) and same(rms.state(), g[f"vn_{tag}_rms"])
