@@ -302,6 +302,23 @@ def other_configs(device, peak_gbs, iters=40):
         timed(c4, n * b * 37, n * b), note="37 useful B per (t, env); each gathered 4-byte log-probability costs a 64-byte "
         "DRAM burst: ncu measures 169 MB of DRAM reads per launch (161 B per (t, env), profiles/r01c_vtrace_*), i.e. "
         "about 4.1 TB/s = 63 % of the measured HBM peak in traffic terms")
+    del bufs
+
+    # ---- intrinsic-return normalisation + GAE (rl/rollout.py:1140-1180), 256 x 4096, device tensors
+    from ppo_b200 import normalization as nz
+    n, a = 256, 4096
+    ir = nz.IntrinsicReturns(a, device=device)
+    r = torch.rand((n, a), device=device, generator=g) * 0.5
+    d = torch.rand((n, a), device=device, generator=g) < 3 / 101
+    v = torch.randn((n + 1, a), device=device, generator=g) * 0.4 + 0.5
+
+    def f3(i):
+        ir.calculate_intrinsic_returns(r, v, d, 0.99, LAMBDA_POLICY, normalize=True, center=False)
+    # r 4 + done 1 in, tracker rows 8 out + 8 + 8 re-read (two row passes), r 4 in + scaled r 4 out, GAE 13 in + 8 out
+    res = timed(f3, n * a * 58, n * a)
+    res["note"] = ("tracker scan + 2 row-moment passes + fold + scale + GAE (6 launches) through the Python API; "
+                   "58 B per (t, env) incl. the float64 tracker rows; the working set (60 MB) stays in L2")
+    out["f3_intrinsic_returns_256x4096"] = res
     return out
 
 
