@@ -10,8 +10,9 @@ Mirrors, with the reference's names and state:
 
 Both are the forward recurrence ``x_t = r_t + gamma * (1 - done_t) * x_{t-1}`` followed, step by step, by a merge of the
 batch moments of ``x_t`` over the envs into the running moments.  The reference does N NumPy passes; here one scan
-launch, two row-reduction launches and one fold.  With envs sharded over ranks (``group``) the only exchange is the
-all-reduce of the two [N] row vectors.  No CPU fallback.
+launch, two row-reduction launches and one fold.  With envs sharded evenly over ranks (``group``) the only exchange is
+the all-reduce of the two [N] row vectors (``tools/dist_check.py`` checks the sharded result against the unsharded one
+on real GPUs).  No CPU fallback.
 """
 import numpy as np
 import torch
