@@ -382,6 +382,30 @@ int ppo_scale_rewards(const float* rewards, int64_t reward_row_stride, int64_t s
                       float* out, unsigned long long* clips, void* stream);
 
 /*
+ * Consumers of device-resident targets.
+ *
+ * ppo_gather_rows: out[i, :] = src[index[i], :] for byte rows (the minibatch selection `var_value[sample]` of
+ *   rl/rollout.py:2349-2372 on buffers that never left the device).  index is int64 [n_index], negative values count
+ *   from the end like NumPy; an index outside [-n_src_rows, n_src_rows) zero-fills the row and sets *out_of_range = 1
+ *   (the caller raises IndexError).  Pitches are in bytes.
+ * ppo_tvf_value_loss: TVFRunnerModule.on_train_value_minibatch (rl/tvf.py:32-77), forward and gradient in one pass:
+ *     loss[b]    = sqrt(K) * mean_k( coef * 0.5 * (targets[b, head_index[k]] - pred[b, k])^2 * head_weights[k] * mask[b, k] )
+ *     grad[b, k] = d loss[b] / d pred[b, k]
+ *   head_index (optional, int32 [K]) is `required_tvf_heads` (:45-46); head_weights [K] carries the duplicate-head
+ *   weights and the h-weighting (:52-62) folded on the host; mask (optional, [rows, K], contiguous) is the horizon
+ *   dropout mask (:64-69, drawn by the caller).  predictions are strided: [rows, K, VH] with VH heads -> pred_head_stride.
+ */
+int ppo_gather_rows(const void* src, int64_t src_pitch_bytes, int64_t row_bytes, int64_t n_src_rows,
+                    const int64_t* index, int64_t n_index, void* out, int64_t out_pitch_bytes, int* out_of_range,
+                    void* stream);
+int ppo_tvf_value_loss(const float* targets, int64_t target_row_stride, const int32_t* head_index,
+                       const float* predictions, int64_t pred_row_stride, int64_t pred_head_stride,
+                       const float* head_weights, const float* mask, int64_t rows, int64_t heads, double coef,
+                       float* loss_out, float* grad_out, void* stream);
+/* out[b, k] = grad[b, k] * row_scale[b] (contiguous [rows, width]): the backward step of the loss above. */
+int ppo_scale_rows(const float* grad, const float* row_scale, int64_t rows, int64_t width, float* out, void* stream);
+
+/*
  * Stream-ordered strided copy between host (pinned) and device memory: `rows` rows of `width_bytes`, any direction.
  * Plumbing for calls whose rollout buffers live in host memory (the reference keeps them in NumPy arrays,
  * rl/rollout.py:646-680): an env block of a [N, A, K] host buffer is `N` rows of `A_block * K * 4` bytes with the

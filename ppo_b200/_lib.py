@@ -68,6 +68,10 @@ _SIGNATURES = {
     "ppo_return_tracker_scan": (c_int, [c_ptr, c_i64, c_ptr, c_int, c_i64, c_i64, c_i64, c_dbl, c_ptr, c_ptr, c_ptr]),
     "ppo_row_sums": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_dbl, c_ptr, c_ptr]),
     "ppo_rms_fold": (c_int, [c_ptr, c_ptr, c_i64, c_dbl, c_ptr, c_ptr, c_ptr]),
+    "ppo_gather_rows": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr]),
+    "ppo_tvf_value_loss": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_i64, c_dbl, c_ptr,
+                                   c_ptr, c_ptr]),
+    "ppo_scale_rows": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "ppo_scale_rewards": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_int, c_int, c_dbl, c_dbl, c_dbl, c_ptr, c_ptr,
                                   c_ptr, c_ptr]),
 }

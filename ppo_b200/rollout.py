@@ -30,6 +30,31 @@ def shard_envs(array, rank, world, axis=1):
     return array[tuple(index)]
 
 
+def gather_rows(buffer, sample, check=True):
+    """``buffer[sample]`` for a device-resident ``[M, ...]`` buffer and an int64 index vector: the minibatch selection
+    of ``rl/rollout.py:2349-2372`` without the host round trip.  Rows are gathered as bytes (any dtype, any trailing
+    shape; the row axis may be strided).  ``check`` raises ``IndexError`` for an out-of-range index like NumPy (one
+    synchronisation); with ``check=False`` such rows are zero-filled."""
+    device = dev.require_cuda()
+    lib = _lib.load()
+    if not (isinstance(buffer, torch.Tensor) and buffer.is_cuda):
+        raise ValueError("gather_rows: buffer must be a CUDA tensor (device-resident rollout buffer)")
+    rows = buffer.shape[0]
+    if buffer.dim() > 1 and not buffer[0].is_contiguous():
+        buffer = buffer.contiguous()
+    index = dev.to_device(sample, torch.int64, device).reshape(-1).contiguous()
+    row_bytes = (buffer[0].numel() if rows else 0) * buffer.element_size()
+    out = torch.empty((index.numel(),) + tuple(buffer.shape[1:]), dtype=buffer.dtype, device=device)
+    bad = torch.zeros(1, dtype=torch.int32, device=device)
+    pitch = buffer.stride(0) * buffer.element_size() if rows > 1 else row_bytes
+    rc = lib.ppo_gather_rows(dev.ptr(buffer), pitch, row_bytes, rows, dev.ptr(index), index.numel(), dev.ptr(out),
+                             row_bytes, dev.ptr(bad), dev.stream_ptr())
+    _lib.check(rc, "ppo_gather_rows")
+    if check and int(bad.item()):
+        raise IndexError(f"index out of bounds for axis 0 with size {rows}")
+    return out
+
+
 _SUM_SLOTS = [_lib.STAT_COUNT, _lib.STAT_ADV_SUM, _lib.STAT_ADV_SUMSQ, _lib.STAT_RET_SUM, _lib.STAT_RET_SUMSQ,
               _lib.STAT_VAL_SUM, _lib.STAT_VAL_SUMSQ, _lib.STAT_VAL_COUNT, _lib.STAT_ADV_ZEROS, _lib.STAT_RET_ZEROS]
 _MIN_SLOTS = [_lib.STAT_ADV_MIN, _lib.STAT_RET_MIN]

@@ -1,7 +1,7 @@
 """Drop-in for the return-side pieces of the reference's ``rl/tvf.py``: the horizon table generator and the
 ``TVFRunnerModule`` methods that feed / call the hot path (``calculate_tvf_returns`` :210-271,
-``get_tvf_ext_value_estimate`` :303-360).  The loss, trimming and logging parts of the module are not on
-the return path and are out of scope.
+``get_tvf_ext_value_estimate`` :303-360), trimming (:91-208) and the value loss that consumes the targets
+(``on_train_value_minibatch`` :32-77, forward and gradient in one CUDA pass behind ``torch.autograd``).
 """
 import collections
 import math
@@ -129,6 +129,93 @@ def horizon_interpolate(horizons, values, target_horizons):
                                      dev.stream_ptr())
     _lib.check(rc, "ppo_horizon_interpolate")
     return dev.like_input(out.reshape(shape), np_like)
+
+
+def tvf_head_loss_weights(tvf_weights, horizons=None, required_tvf_heads=None, single_value_head=None,
+                          head_weighting="off", max_horizon=None, n_step=None):
+    """Per-head loss weights of ``rl/tvf.py:51-62`` folded into one float32 vector on the host: the duplicate-head
+    weights (``runner.tvf_weights[head_filter]``) times, for ``head_weighting == "h_weighted"`` with every head trained,
+    ``(1 + (max_horizon - h) / n_step) * 2 / (min + max)``."""
+    head_filter = required_tvf_heads if required_tvf_heads is not None else slice(None, None)
+    weights = np.asarray(tvf_weights, dtype=np.float32)[head_filter]
+    if head_weighting == "h_weighted" and single_value_head is None:
+        weighting = np.asarray([1 + ((max_horizon - h) / n_step) for h in horizons], dtype=np.float32)
+        adjustment = 2 / (np.min(weighting) + np.max(weighting))
+        weights = (weights * weighting) * np.float32(adjustment)
+    return np.ascontiguousarray(weights, dtype=np.float32)
+
+
+class _TVFValueLoss(torch.autograd.Function):
+    """``ppo_tvf_value_loss``: the per-sample loss and d loss / d prediction from one pass; backward is the chain rule
+    step ``ppo_scale_rows``."""
+
+    @staticmethod
+    def forward(ctx, predictions, targets, head_weights, head_index, mask, coef):
+        lib = _lib.load()
+        rows, heads = predictions.shape
+        loss = torch.empty(rows, dtype=torch.float32, device=predictions.device)
+        grad = torch.empty((rows, heads), dtype=torch.float32, device=predictions.device) \
+            if predictions.requires_grad else None
+        rc = lib.ppo_tvf_value_loss(dev.ptr(targets), targets.stride(0) if rows else 0, dev.ptr(head_index),
+                                    dev.ptr(predictions), predictions.stride(0) if rows else 0, predictions.stride(1),
+                                    dev.ptr(head_weights), dev.ptr(mask), rows, heads, float(coef), dev.ptr(loss),
+                                    dev.ptr(grad), dev.stream_ptr())
+        _lib.check(rc, "ppo_tvf_value_loss")
+        ctx.grad = grad
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        grad = ctx.grad
+        if grad is None:
+            return None, None, None, None, None, None
+        lib = _lib.load()
+        rows, heads = grad.shape
+        out = torch.empty_like(grad)
+        g = grad_loss.to(torch.float32).contiguous()
+        _lib.check(lib.ppo_scale_rows(dev.ptr(grad), dev.ptr(g), rows, heads, dev.ptr(out), dev.stream_ptr()),
+                   "ppo_scale_rows")
+        return out, None, None, None, None, None
+
+
+def tvf_value_loss(targets, predictions, head_weights, coef=1.0, required_tvf_heads=None, mask=None):
+    """Per-sample TVF value loss ``[B]`` of ``rl/tvf.py:44-73``:
+    ``sqrt(K) * mean_k(coef * 0.5 * (targets[:, heads] - predictions)^2 * head_weights * mask)``.
+
+    ``targets`` ``[B, K_all]`` and ``predictions`` ``[B, K]`` (any strides, e.g. ``model_out["tvf_value"][:, :, 0]``)
+    are CUDA tensors; ``head_weights`` ``[K]`` comes from :func:`tvf_head_loss_weights`; ``mask`` is the optional
+    horizon-dropout mask ``[B, K]`` (already divided by the keep probability, ``rl/tvf.py:67-69``).  Differentiable
+    with respect to ``predictions``."""
+    device = dev.require_cuda()
+    if not (isinstance(predictions, torch.Tensor) and predictions.is_cuda):
+        raise ValueError("tvf_value_loss: predictions must be a CUDA tensor (the model output)")
+    if predictions.dim() != 2:
+        raise ValueError(f"tvf_value_loss: predictions must be [B, K], got {tuple(predictions.shape)}")
+    rows, heads = predictions.shape
+    t = dev.to_device(targets, torch.float32, device)
+    if t.dim() != 2 or t.shape[0] != rows:
+        raise ValueError(f"tvf_value_loss: targets must be [B, K], got {tuple(t.shape)} for B={rows}")
+    if t.stride(1) != 1:
+        t = t.contiguous()
+    index = None
+    if required_tvf_heads is not None:
+        idx = np.asarray(required_tvf_heads, dtype=np.int64).reshape(-1)
+        idx = np.where(idx < 0, idx + t.shape[1], idx)
+        if idx.size != heads or np.any((idx < 0) | (idx >= t.shape[1])):
+            raise IndexError(f"required_tvf_heads {list(required_tvf_heads)} do not select {heads} of {t.shape[1]} heads")
+        index = torch.from_numpy(idx.astype(np.int32)).to(device)
+    elif t.shape[1] != heads:
+        raise ValueError(f"tvf_value_loss: {t.shape[1]} target heads vs {heads} predicted heads")
+    w = dev.to_device(head_weights, torch.float32, device).contiguous()
+    if tuple(w.shape) != (heads,):
+        raise ValueError(f"tvf_value_loss: head_weights must be [{heads}], got {tuple(w.shape)}")
+    m = None
+    if mask is not None:
+        m = dev.to_device(mask, torch.float32, device).contiguous()
+        if tuple(m.shape) != (rows, heads):
+            raise ValueError(f"tvf_value_loss: mask must be {(rows, heads)}, got {tuple(m.shape)}")
+    p = predictions if predictions.dtype == torch.float32 else predictions.float()
+    return _TVFValueLoss.apply(p, t, w, index, m, coef)
 
 
 class TVFRunnerModule:
@@ -298,6 +385,27 @@ class TVFRunnerModule:
         if args.tvf.gamma == args.gamma:
             return old_value_estimates
         return rediscount_horizons(old_value_estimates, args.tvf.gamma, args.gamma, self.runner.tvf_horizons)
+
+    def on_train_value_minibatch(self, model_out, data, **kwargs):
+        """Per-sample TVF value loss ``[B]`` of one minibatch (reference: ``rl/tvf.py:32-77``, same arguments).
+        ``data["tvf_returns"]`` ``[B, K]`` and ``model_out["tvf_value"]`` ``[B, K, VH]`` are CUDA tensors (the
+        targets never left the device, see :func:`ppo_b200.rollout.gather_rows`)."""
+        args = self.args
+        assert "tvf_returns" in data, "TVF returns were not uploaded with batch."
+        required_tvf_heads = kwargs['required_tvf_heads']
+        single_value_head = kwargs['single_value_head']
+        predictions = model_out["tvf_value"][:, :, 0]
+        weights = tvf_head_loss_weights(self.runner.tvf_weights, self.runner.tvf_horizons, required_tvf_heads,
+                                        single_value_head, args.tvf.head_weighting,
+                                        getattr(args.tvf, "max_horizon", None), getattr(args, "tvf_return_n_step", None))
+        mask = None
+        if args.tvf.horizon_dropout > 0:
+            keep_prob = (1 - args.tvf.horizon_dropout)
+            mask = torch.bernoulli(torch.ones_like(predictions) * keep_prob) / keep_prob
+        tvf_loss = tvf_value_loss(data["tvf_returns"], predictions, weights, args.tvf.coef, required_tvf_heads, mask)
+        self.runner.log.watch_mean("loss_tvf", tvf_loss.mean(), history_length=64 * args.value_opt.epochs,
+                                   display_name="ls_tvf", display_width=8)
+        return tvf_loss
 
     def save(self):
         pass

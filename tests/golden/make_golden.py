@@ -182,6 +182,35 @@ def normalization_vectors(root, ref):
         out[f"vn_{tag}_clips"] = np.asarray(clips)
         out[f"vn_{tag}_returns"] = np.asarray(w.current_returns, dtype=np.float64)
         out[f"vn_{tag}_rms"] = np.asarray([w.ret_rms.mean, w.ret_rms.var, w.ret_rms.count], dtype=np.float64)
+
+    # ---- TVFRunnerModule.on_train_value_minibatch (rl/tvf.py:32-77): per-sample loss and its gradient (autograd)
+    import torch
+    import rl.config as cfg
+    hz, hw = ref.tvf.get_value_head_horizons(24, 1000, include_weight=True)
+    rng = np.random.RandomState(13)
+    batch = 19
+    targets = rng.normal(1.0, 2.0, [batch, len(hz)]).astype(np.float32)
+    preds = rng.normal(1.0, 2.0, [batch, len(hz), 2]).astype(np.float32)
+    out["loss_in_horizons"], out["loss_in_weights"] = hz, hw
+    out["loss_in_targets"], out["loss_in_predictions"] = targets, preds
+    log = types.SimpleNamespace(watch_mean=lambda *a, **k: None)
+    runner = types.SimpleNamespace(ext_rewards=np.zeros([2, 3], np.float32), value_heads=["ext", "int"],
+                                   tvf_horizons=list(hz), tvf_weights=hw, log=log,
+                                   model=types.SimpleNamespace(device="cpu"))
+    mod = ref.tvf.TVFRunnerModule(runner)
+    for tag, weighting, required, single in [("all", "off", None, None), ("hweighted", "h_weighted", None, None),
+                                             ("single", "h_weighted", [5], 5), ("prefix", "off", list(range(8)), -7)]:
+        cfg.args.tvf = types.SimpleNamespace(coef=0.7, head_weighting=weighting, max_horizon=1000, horizon_dropout=0.0)
+        cfg.args.tvf_return_n_step = 20
+        cfg.args.value_opt = types.SimpleNamespace(epochs=2)
+        ref.tvf.args = cfg.args
+        sel = slice(None) if required is None else required
+        p = torch.tensor(preds[:, sel, :], requires_grad=True)
+        loss = mod.on_train_value_minibatch({"tvf_value": p}, {"tvf_returns": torch.from_numpy(targets)},
+                                            required_tvf_heads=required, single_value_head=single)
+        (loss * 0.25).mean().backward()  # rl/rollout.py:1553-1555 with loss_scale = 0.25
+        out[f"loss_{tag}"] = loss.detach().numpy()
+        out[f"loss_{tag}_grad"] = p.grad.numpy()
     return out
 
 

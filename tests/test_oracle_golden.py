@@ -198,3 +198,23 @@ def test_vec_normalize_rewards(golden_norm):
                                                      clip=kwargs.get("clip", 10.0), scale=kwargs.get("scale", 1.0))
         assert same(scaled, g[f"vn_{tag}_scaled"]) and clips == int(g[f"vn_{tag}_clips"]), tag
         assert same(cur, g[f"vn_{tag}_returns"]) and same(rms.state(), g[f"vn_{tag}_rms"])
+
+
+LOSS_CASES = [("all", "off", None, None), ("hweighted", "h_weighted", None, None), ("single", "h_weighted", [5], 5),
+              ("prefix", "off", list(range(8)), -7)]
+
+
+def test_tvf_value_loss(golden_norm):
+    """TVFRunnerModule.on_train_value_minibatch (rl/tvf.py:32-77) and its autograd gradient.  Tolerance: 2 float32
+    ulp on the loss (torch and NumPy sum the horizon axis in different orders) and on the gradient (autograd
+    chains float32 products, the oracle rounds once)."""
+    from util import ulp_diff
+    g = golden_norm
+    for tag, weighting, required, single in LOSS_CASES:
+        sel = slice(None) if required is None else required
+        loss, grad = oracle.tvf_value_loss(g["loss_in_targets"], g["loss_in_predictions"][:, sel, 0], g["loss_in_weights"],
+                                           g["loss_in_horizons"], 0.7, required, single, weighting, 1000, 20,
+                                           loss_scale=0.25)
+        assert ulp_diff(loss, g[f"loss_{tag}"]) <= 2, tag
+        assert ulp_diff(grad, g[f"loss_{tag}_grad"][:, :, 0]) <= 2, tag
+        assert not g[f"loss_{tag}_grad"][:, :, 1].any()  # only the "ext" value head is trained (:43)
