@@ -132,6 +132,11 @@ int ppo_gae_normalized(const float* rewards, int64_t reward_row_stride,
 int ppo_adv_normalize(const float* adv, int64_t count, const double* stats,
                       double eps, double clip, float* out, void* stream);
 
+/* Statistics records [n_records][PPO_STATS_LEN] of disjoint env blocks or ranks -> one record: sums are added in
+ * record order, min / max are reduced (out may alias records[0]).  Used for the env-blocked host pipeline and, after an
+ * all-gather of the per-rank records, for the cross-GPU return statistics. */
+int ppo_merge_stats(const double* records, int64_t n_records, double* out, void* stream);
+
 /* count / sum / sumsq / min / max of a float32 vector into the ADV_* slots of `stats`
  * (for advantages that were combined on the device, e.g. ext + int, rl/rollout.py:1225-1228). */
 int ppo_moments(const float* x, int64_t count, double* stats,

@@ -71,6 +71,7 @@ _SIGNATURES = {
     "ppo_gather_rows": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr]),
     "ppo_tvf_value_loss": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_i64, c_dbl, c_ptr,
                                    c_ptr, c_ptr]),
+    "ppo_merge_stats": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
     "ppo_scale_rows": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "ppo_scale_rewards": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_int, c_int, c_dbl, c_dbl, c_dbl, c_ptr, c_ptr,
                                   c_ptr, c_ptr]),

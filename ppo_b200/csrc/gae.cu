@@ -887,6 +887,27 @@ extern "C" int ppo_discounted_returns(const float* rewards, int64_t reward_row_s
     return PPO_OK;
 }
 
+// Records of disjoint env blocks (or ranks) -> one record: sums add in record order, min / max reduce.
+__global__ void merge_stats_kernel(const double* __restrict__ records, int64_t n, double* __restrict__ out) {
+    const int j = threadIdx.x;
+    if (j >= PPO_STATS_LEN) return;
+    const bool is_min = (j == PPO_STAT_ADV_MIN || j == PPO_STAT_RET_MIN);
+    const bool is_max = (j == PPO_STAT_ADV_MAX || j == PPO_STAT_RET_MAX);
+    double acc = is_min ? INFINITY : is_max ? -INFINITY : 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+        const double x = records[i * PPO_STATS_LEN + j];
+        acc = is_min ? fmin(acc, x) : is_max ? fmax(acc, x) : acc + x;
+    }
+    out[j] = j <= PPO_STAT_RET_ZEROS ? acc : 0.0;
+}
+
+extern "C" int ppo_merge_stats(const double* records, int64_t n_records, double* out, void* stream) {
+    PPO_REQUIRE(n_records >= 1 && records && out, "ppo_merge_stats: bad arguments");
+    merge_stats_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(records, n_records, out);
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
 extern "C" int ppo_moments(const float* x, int64_t count, double* stats, void* workspace,
                            int64_t workspace_bytes, void* stream) {
     PPO_REQUIRE(count >= 0 && stats != nullptr, "ppo_moments: bad arguments");

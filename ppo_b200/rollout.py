@@ -62,9 +62,15 @@ _MAX_SLOTS = [_lib.STAT_ADV_MAX, _lib.STAT_RET_MAX]
 
 
 def merge_stats(records):
-    """Combine statistics records of disjoint env blocks: sums are added, min / max are reduced."""
-    stack = torch.stack(list(records))
+    """Combine statistics records of disjoint env blocks: sums are added, min / max are reduced (``ppo_merge_stats``;
+    CPU tensors -- the gloo tests of the sharding logic -- take the same reduction in torch)."""
+    stack = records if isinstance(records, torch.Tensor) and records.dim() == 2 else torch.stack(list(records))
+    stack = stack.contiguous()
     merged = torch.zeros_like(stack[0])
+    if stack.is_cuda:
+        rc = _lib.load().ppo_merge_stats(dev.ptr(stack), stack.shape[0], dev.ptr(merged), dev.stream_ptr())
+        _lib.check(rc, "ppo_merge_stats")
+        return merged
     merged[_SUM_SLOTS] = stack[:, _SUM_SLOTS].sum(dim=0)
     merged[_MIN_SLOTS] = stack[:, _MIN_SLOTS].min(dim=0).values
     merged[_MAX_SLOTS] = stack[:, _MAX_SLOTS].max(dim=0).values
@@ -72,14 +78,14 @@ def merge_stats(records):
 
 
 def allreduce_stats(stats, group=None):
-    """Combine per-rank statistics records in place across ``group`` (same result as :func:`merge_stats`)."""
+    """Combine per-rank statistics records in place across ``group`` (same result as :func:`merge_stats`): one
+    all-gather of the 16-double records, then the merge on every rank in rank order (identical bits everywhere)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return stats
-    sums, mins, maxs = stats[_SUM_SLOTS], stats[_MIN_SLOTS], stats[_MAX_SLOTS]
-    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(mins, op=dist.ReduceOp.MIN, group=group)
-    dist.all_reduce(maxs, op=dist.ReduceOp.MAX, group=group)
-    stats[_SUM_SLOTS], stats[_MIN_SLOTS], stats[_MAX_SLOTS] = sums, mins, maxs
+    world = dist.get_world_size(group)
+    gathered = torch.empty((world, stats.numel()), dtype=stats.dtype, device=stats.device)
+    dist.all_gather(list(gathered.unbind(0)), stats.contiguous(), group=group)  # rows of one buffer (NCCL and gloo)
+    stats.copy_(merge_stats(gathered))
     return stats
 
 
