@@ -122,18 +122,50 @@ __device__ __forceinline__ void ts_fma_if(float& acc, float lo, float hi, float 
         : "f"(lo), "f"(hi), "f"(wlo), "f"(whi), "r"(n), "r"(lim));
 }
 
-// G entries of one horizon for the thread's two time rows (t, t + 32).  The entry constants are one broadcast
-// 16-byte shared-memory read each; all gathers are issued before the first use.  PITCH4 = slab pitch in bytes
-// when it is known at compile time (immediate offsets), 0 = runtime pitch in `p4`.
+// Shared-memory form of the launch constants: an entry is 12 bytes {off | n << 18, wlo, whi} and every horizon's list
+// starts at a multiple of four entries (48 bytes), so four entries are three 16-byte broadcast reads -- 1.5 wavefronts
+// per entry instead of the 2 of a 16-byte entry (a broadcast LDS.128 costs two wavefronts, tools/micro_lsu.cu); a
+// horizon record is 8 bytes {beg | cnt << 12 | maxn << 20, rscale}.
+constexpr uint32_t kTsOffMask = 0x3ffffu;  // byte offset of W^T[col][n - 1] in the slab (< 256 KB)
+constexpr int kTsOffBits = 18;
+constexpr int kTsEntBytes = 12;
+
+__device__ __forceinline__ uint2 ts_lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t ts_lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// G entries of one horizon for the thread's two time rows (t, t + 32); `cent` is 16-byte aligned for G = 4 and G = 2
+// and 8-byte aligned for G = 1.  All gathers are issued before the first use.  PITCH4 = slab pitch in bytes when it is
+// known at compile time (immediate offsets), 0 = runtime pitch in `p4`.
 template <int G, int PITCH4>
 __device__ __forceinline__ void ts_eval(uint32_t cent, uint32_t base, uint32_t p4, int lim0, int lim1, float& acc0,
                                         float& acc1) {
-    uint4 c[G];
+    uint32_t w[3 * G];
+    if (G == 4) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const uint4 v = ts_lds128(cent + i * 16);
+            w[4 * i] = v.x, w[4 * i + 1] = v.y, w[4 * i + 2] = v.z, w[4 * i + 3] = v.w;
+        }
+    } else if (G == 2) {
+        const uint4 v = ts_lds128(cent);
+        const uint2 u = ts_lds64(cent + 16);
+        w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w, w[4] = u.x, w[5] = u.y;
+    } else {
+        const uint2 u = ts_lds64(cent);
+        w[0] = u.x, w[1] = u.y, w[2] = ts_lds_u32(cent + 8);
+    }
     float lo0[G], hi0[G], lo1[G], hi1[G];
 #pragma unroll
     for (int i = 0; i < G; ++i) {
-        c[i] = ts_lds128(cent + i * 16);
-        const uint32_t a = base + c[i].x;
+        const uint32_t a = base + (w[3 * i] & kTsOffMask);
         if (PITCH4) {
             lo0[i] = ts_ldsi<0>(a), hi0[i] = ts_ldsi<PITCH4>(a);
             lo1[i] = ts_ldsi<kTsRows * 4>(a), hi1[i] = ts_ldsi<PITCH4 + kTsRows * 4>(a);
@@ -145,9 +177,10 @@ __device__ __forceinline__ void ts_eval(uint32_t cent, uint32_t base, uint32_t p
     }
 #pragma unroll
     for (int i = 0; i < G; ++i) {
-        const float wlo = __uint_as_float(c[i].y), whi = __uint_as_float(c[i].z);
-        ts_fma_if(acc0, lo0[i], hi0[i], wlo, whi, static_cast<int>(c[i].w), lim0);
-        ts_fma_if(acc1, lo1[i], hi1[i], wlo, whi, static_cast<int>(c[i].w), lim1);
+        const float wlo = __uint_as_float(w[3 * i + 1]), whi = __uint_as_float(w[3 * i + 2]);
+        const int n = static_cast<int>(w[3 * i] >> kTsOffBits);
+        ts_fma_if(acc0, lo0[i], hi0[i], wlo, whi, n, lim0);
+        ts_fma_if(acc1, lo1[i], hi1[i], wlo, whi, n, lim1);
     }
 }
 
@@ -223,11 +256,33 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
     for (uint32_t i = threadIdx.x * 16u; i < q.off_bar; i += blockDim.x * 16u)
         *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    // per-horizon launch constants: table blob -> shared memory (read by the consumers as broadcasts)
-    for (int i = threadIdx.x; i < q.n_ent; i += blockDim.x)
-        *reinterpret_cast<uint4*>(smem + q.off_ent + i * 16) = __ldg(reinterpret_cast<const uint4*>(q.ent) + i);
-    for (int i = threadIdx.x; i < K; i += blockDim.x)
-        *reinterpret_cast<uint4*>(smem + q.off_hz + i * 16) = __ldg(reinterpret_cast<const uint4*>(q.hz) + i);
+    // per-horizon launch constants: table blob -> shared memory in the packed form above (read by the consumers as
+    // broadcasts).  Thread k owns horizon k: its list starts at the padded prefix sum of the earlier counts.
+    {
+        __shared__ uint32_t warp_total[kTsMaxK / 32];
+        const int k = threadIdx.x;  // K <= 128 < blockDim.x
+        uint4 h = make_uint4(0, 0, 0, 0);
+        if (k < K) h = __ldg(reinterpret_cast<const uint4*>(q.hz) + k);  // beg, cnt, rscale, maxn
+        const uint32_t padded = (h.y + 3u) & ~3u;
+        uint32_t incl = padded;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31 && warp < kTsMaxK / 32) warp_total[warp] = incl;
+        __syncthreads();
+        if (k < K) {
+            uint32_t pbeg = incl - padded;
+            for (int j = 0; j < warp; ++j) pbeg += warp_total[j];
+            *reinterpret_cast<uint2*>(smem + q.off_hz + k * 8) = make_uint2(pbeg | (h.y << 12) | (h.w << 20), h.z);
+            for (uint32_t e = 0; e < h.y; ++e) {
+                const uint4 t = __ldg(reinterpret_cast<const uint4*>(q.ent) + h.x + e);  // off, wlo, whi, n
+                uint32_t* dst = reinterpret_cast<uint32_t*>(smem + q.off_ent + (pbeg + e) * kTsEntBytes);
+                dst[0] = t.x | (t.w << kTsOffBits), dst[1] = t.y, dst[2] = t.z;
+            }
+        }
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (threadIdx.x == 0) ts_stamp(q, 1);  // shared memory initialised
@@ -489,14 +544,17 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                 bool tile_free = false;
                 for (int quad = (cw + s) % kTsConsumers; quad < q.kq; quad += kTsConsumers) {
                     float o0[4], o1[4];
-                    uint4 hz[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) hz[u] = ts_lds128(hz_a + static_cast<uint32_t>(quad * 4 + u) * 16u);
+                    uint2 hz[4];  // {beg | cnt << 12 | maxn << 20, rscale} of the quad's four horizons: two 16-byte reads
+                    {
+                        const uint4 a = ts_lds128(hz_a + static_cast<uint32_t>(quad) * 32u);
+                        const uint4 b = ts_lds128(hz_a + static_cast<uint32_t>(quad) * 32u + 16u);
+                        hz[0] = make_uint2(a.x, a.y), hz[1] = make_uint2(a.z, a.w);
+                        hz[2] = make_uint2(b.x, b.y), hz[3] = make_uint2(b.z, b.w);
+                    }
                     // rows whose n-step windows run off the rollout: one folded bootstrap from the final row, host
                     // weights from the horizon-major tables (issued for the whole quad before the entry loops)
                     float tacc0[4] = {0.f, 0.f, 0.f, 0.f}, tacc1[4] = {0.f, 0.f, 0.f, 0.f};
-                    const int maxn_q = max(max(static_cast<int>(hz[0].w), static_cast<int>(hz[1].w)),
-                                           max(static_cast<int>(hz[2].w), static_cast<int>(hz[3].w)));
+                    const int maxn_q = static_cast<int>(max(max(hz[0].x >> 20, hz[1].x >> 20), max(hz[2].x >> 20, hz[3].x >> 20)));
                     if (any_end && m_min < maxn_q && !(q.dbg & 16)) {
                         int idx0[4], idx1[4];
                         float w00[4], w01[4], w10[4], w11[4];
@@ -530,12 +588,12 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         float acc0 = tacc0[u], acc1 = tacc1[u];
-                        uint32_t ce = ent_a + hz[u].x * 16u;
-                        int left = (q.dbg & 8) ? 0 : static_cast<int>(hz[u].y);
-                        for (; left >= 4; left -= 4, ce += 64) ts_eval<4, PITCH4>(ce, base, P4, lim0, lim1, acc0, acc1);
-                        if (left >= 2) ts_eval<2, PITCH4>(ce, base, P4, lim0, lim1, acc0, acc1), ce += 32, left -= 2;
+                        uint32_t ce = ent_a + (hz[u].x & 0xfffu) * kTsEntBytes;
+                        int left = (q.dbg & 8) ? 0 : static_cast<int>((hz[u].x >> 12) & 0xffu);
+                        for (; left >= 4; left -= 4, ce += 4 * kTsEntBytes) ts_eval<4, PITCH4>(ce, base, P4, lim0, lim1, acc0, acc1);
+                        if (left >= 2) ts_eval<2, PITCH4>(ce, base, P4, lim0, lim1, acc0, acc1), ce += 2 * kTsEntBytes, left -= 2;
                         if (left >= 1) ts_eval<1, PITCH4>(ce, base, P4, lim0, lim1, acc0, acc1);
-                        const float rs = __uint_as_float(hz[u].z);
+                        const float rs = __uint_as_float(hz[u].y);
                         o0[u] = fmaf(rs, R0, acc0 * inv_c);
                         o1[u] = fmaf(rs, R1, acc1 * inv_c);
                     }
@@ -669,6 +727,7 @@ int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsign
     if (reinterpret_cast<uintptr_t>(p.out) & 15) return unsupported("targets are not 16-byte aligned");
     if (p.envs > INT32_MAX) return unsupported("too many envs");
     if (static_cast<int64_t>(K) * E > kTsMaxEntries) return unsupported("more than 1024 (horizon, n-step) entries");
+    if (E > 255 || nmax > 1023) return unsupported("more than 255 n-steps per horizon or an n-step above 1023");
 
     TsParams q{};
     q.p = p;
@@ -703,8 +762,9 @@ int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsign
     const uint32_t chunk = kTsRows * static_cast<uint32_t>(V) * 4u;
     const uint32_t wt_bytes = ts_align((static_cast<uint32_t>(V + 2) * q.pitch + nmax + 2 * kTsStep) * 4u, 1024);
     const uint32_t ot_bytes = static_cast<uint32_t>(kTsStep) * K * 4u;  // dense swizzled sub-tiles of 4096 bytes
-    const uint32_t ent_bytes = ts_align(static_cast<uint32_t>(total > 0 ? total : 1) * 16u, 128);
-    const uint32_t hz_bytes = ts_align(static_cast<uint32_t>(K) * 16u, 128);
+    // packed entries, every horizon's list padded to a multiple of four
+    const uint32_t ent_bytes = ts_align(static_cast<uint32_t>(total + 3 * K + 4) * kTsEntBytes, 128);
+    const uint32_t hz_bytes = ts_align(static_cast<uint32_t>(K) * 8u, 128);
     const uint32_t rt_bytes = ts_align(2u * q.rt_words * 4u, 128);
     const uint32_t fr_bytes = ts_align(2u * static_cast<uint32_t>(V) * 4u, 128);
     const uint32_t bar_bytes = (8u + 2 * kTsMaxChunks + 2 * kTsMaxSteps + 4 + 2) * 8u;
