@@ -445,7 +445,11 @@ def run_ours(args):
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": tvf_avg_ms,
                 "kernel_share_of_step": tvf_avg_ms / ms_per_step,
-                "units_per_launch": f"{steps} x {envs} x {n_h} targets at 8.06 B/target"}
+                "units_per_launch": f"{steps} x {envs} x {n_h} targets at 8.06 B/target",
+                # SURVEY 8(d) asks for both denominators: the measured copy bandwidth above and the 8 TB/s spec figure
+                "frac_of_8tbs_spec": achieved / 8000.0,
+                # the whole step (target launch + GAE / TD(lambda) / normalisation at 21 B per (t, env)) against the same peak
+                "whole_step_frac": (alg_bytes + 21 * steps * envs) / (ms_per_step * 1e-3) / 1e9 / peak}
     # informational: the same kernel against the shared-memory gather bound that actually limits it:
     # every target gathers 2 x (distinct n-steps per horizon) float32 value samples, one 128-byte wavefront per clock per SM
     sms = torch.cuda.get_device_properties(device).multi_processor_count
