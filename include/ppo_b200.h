@@ -107,6 +107,8 @@ int ppo_gae(const float* rewards, int64_t reward_row_stride,
             float* adv_out, float* ret_out, double* stats,
             void* workspace, int64_t workspace_bytes, void* stream);
 
+#define PPO_MAX_PEERS 8
+
 /*
  * ppo_gae followed by ppo_adv_normalize on the raw advantages (single GPU: no moment exchange in between), as ONE
  * cooperative launch when the whole grid of the tile kernel is resident: every CTA keeps its advantages in shared
@@ -122,6 +124,35 @@ int ppo_gae_normalized(const float* rewards, int64_t reward_row_stride,
                        double gamma, double lamb_adv, double lamb_ret, double eps, double clip,
                        float* adv_out, float* ret_out, float* norm_out, double* stats,
                        void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * Env-sharded form of ppo_gae_normalized (one process per GPU, envs split over `world` GPUs of one NVLink domain): the
+ * exchange of the advantage moments -- the only cross-GPU step of the path, SURVEY 8e -- happens INSIDE the launch
+ * over peer memory instead of an NCCL all-reduce between two launches.  Every rank owns a mailbox [world][PPO_STATS_LEN]
+ * doubles and `world` 64-bit flag words, mapped into all peers (CUDA IPC); peer_mail[r] / peer_flags[r] are rank r's
+ * buffers as seen from this process (host arrays of `world` device pointers).  The CTA that folds the local statistics
+ * stores the record into slot `rank` of every mailbox and release-stores `epoch` into flag `rank` there; all CTAs then
+ * wait until their own `world` flags have reached `epoch`, add the moments in rank order (identical bits on every
+ * rank) and normalise their tile.  epoch must increase with every launch on every rank (flags are never reset; zero
+ * them once at start-up).  stats receives the local record, global_stats (optional) the merged one.
+ * Returns 1 when launched, 0 when the shard shape does not fit the resident tile kernel (nothing launched: every rank
+ * decides alike; use ppo_gae + all-reduce + ppo_adv_normalize), < 0 on error.  A peer that never arrives makes the
+ * kernel give up after 4 s and write NaN advantages rather than hang.
+ */
+/* 1 when ppo_gae_normalized / ppo_gae_normalized_peers would take the single cooperative launch for this shard shape
+ * on the current device (nothing is launched): ranks agree on it (all-reduce MIN) before relying on the peer exchange. */
+int ppo_gae_normalized_fits(int64_t steps, int64_t envs, int done_kind, int64_t value_env_stride);
+
+int ppo_gae_normalized_peers(const float* rewards, int64_t reward_row_stride,
+                             const float* values, int64_t value_row_stride, int64_t value_env_stride,
+                             const float* final_value, int64_t final_env_stride,
+                             const void* dones, int done_kind, int64_t done_row_stride,
+                             int64_t steps, int64_t envs,
+                             double gamma, double lamb_adv, double lamb_ret, double eps, double clip,
+                             float* adv_out, float* ret_out, float* norm_out, double* stats, double* global_stats,
+                             void* workspace, int64_t workspace_bytes, int rank, int world,
+                             double* const* peer_mail, unsigned long long* const* peer_flags,
+                             unsigned long long epoch, void* stream);
 
 /*
  * Batch advantage normalisation: out = clip((x - mean) / (std + eps), -clip, +clip), population std.
@@ -418,6 +449,14 @@ int ppo_scale_rows(const float* grad, const float* row_scale, int64_t rows, int6
  */
 int ppo_memcpy_2d_async(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes,
                         int64_t width_bytes, int64_t rows, void* stream);
+
+/* Mailbox memory for ppo_gae_normalized_peers.  ppo_peer_alloc: zeroed cudaMalloc allocation on the current device and
+ * its 64-byte CUDA IPC handle (exchange it between the processes of the node any way you like); ppo_peer_open: map a
+ * peer's allocation for access from the CURRENT device (over NVLink); ppo_peer_close / ppo_peer_free undo them. */
+int ppo_peer_alloc(int64_t bytes, void** ptr, unsigned char* handle64);
+int ppo_peer_open(const unsigned char* handle64, void** ptr);
+int ppo_peer_close(void* ptr);
+int ppo_peer_free(void* ptr);
 
 #ifdef __cplusplus
 }

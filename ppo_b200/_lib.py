@@ -29,6 +29,7 @@ STAT_RET_SUM, STAT_RET_SUMSQ, STAT_RET_MIN, STAT_RET_MAX = 5, 6, 7, 8
 STAT_VAL_SUM, STAT_VAL_SUMSQ, STAT_VAL_COUNT = 9, 10, 11
 STAT_ADV_ZEROS, STAT_RET_ZEROS = 12, 13
 SCALE_INTRINSIC, SCALE_WRAPPER = 0, 1
+MAX_PEERS = 8
 
 # name -> (restype, argtypes); must match include/ppo_b200.h
 _SIGNATURES = {
@@ -71,6 +72,14 @@ _SIGNATURES = {
     "ppo_gather_rows": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr]),
     "ppo_tvf_value_loss": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_i64, c_dbl, c_ptr,
                                    c_ptr, c_ptr]),
+    "ppo_gae_normalized_peers": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_int, c_i64, c_i64, c_i64,
+                                         c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                         c_i64, c_int, c_int, c_ptr, c_ptr, ctypes.c_uint64, c_ptr]),
+    "ppo_gae_normalized_fits": (c_int, [c_i64, c_i64, c_int, c_i64]),
+    "ppo_peer_alloc": (c_int, [c_i64, c_ptr, c_ptr]),
+    "ppo_peer_open": (c_int, [c_ptr, c_ptr]),
+    "ppo_peer_close": (c_int, [c_ptr]),
+    "ppo_peer_free": (c_int, [c_ptr]),
     "ppo_merge_stats": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
     "ppo_scale_rows": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "ppo_scale_rewards": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_int, c_int, c_dbl, c_dbl, c_dbl, c_ptr, c_ptr,

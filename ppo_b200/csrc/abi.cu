@@ -1,5 +1,6 @@
 // Library-wide pieces of the C ABI: version, per-thread error text, device queries.
 #include <stdarg.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -55,5 +56,38 @@ extern "C" int ppo_memcpy_2d_async(void* dst, int64_t dst_pitch_bytes, const voi
     PPO_CUDA(cudaMemcpy2DAsync(dst, static_cast<size_t>(dst_pitch_bytes), src, static_cast<size_t>(src_pitch_bytes),
                                static_cast<size_t>(width_bytes), static_cast<size_t>(rows), cudaMemcpyDefault,
                                static_cast<cudaStream_t>(stream)));
+    return PPO_OK;
+}
+
+// Peer-visible device memory for the mailboxes of ppo_gae_normalized_peers: a plain cudaMalloc allocation (zeroed) with
+// its CUDA IPC handle; other processes of the node open the handle while THEIR device is current, which maps the memory
+// for access from that device over NVLink (cudaIpcMemLazyEnablePeerAccess).
+extern "C" int ppo_peer_alloc(int64_t bytes, void** ptr, unsigned char* handle64) {
+    PPO_REQUIRE(bytes > 0 && ptr && handle64, "ppo_peer_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    PPO_CUDA(cudaMalloc(ptr, static_cast<size_t>(bytes)));
+    PPO_CUDA(cudaMemset(*ptr, 0, static_cast<size_t>(bytes)));
+    PPO_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    PPO_CUDA(cudaIpcGetMemHandle(&h, *ptr));
+    memcpy(handle64, &h, 64);
+    return PPO_OK;
+}
+
+extern "C" int ppo_peer_open(const unsigned char* handle64, void** ptr) {
+    PPO_REQUIRE(handle64 && ptr, "ppo_peer_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    PPO_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PPO_OK;
+}
+
+extern "C" int ppo_peer_close(void* ptr) {
+    if (ptr) PPO_CUDA(cudaIpcCloseMemHandle(ptr));
+    return PPO_OK;
+}
+
+extern "C" int ppo_peer_free(void* ptr) {
+    if (ptr) PPO_CUDA(cudaFree(ptr));
     return PPO_OK;
 }

@@ -91,10 +91,30 @@ struct ThreadStats {
     }
 };
 
+// Exchange of the per-GPU statistics records over NVLink peer memory (env-sharded runs): every rank owns a mailbox
+// [world][16] doubles and a flag word per sender, mapped into its peers; the CTA that folds the local record stores it
+// into slot `rank` of every mailbox (its own included) and then raises flag `rank` there to the launch's epoch.
+struct PeerExchange {
+    int world, rank;               // world <= kMaxPeers; world == 0: no exchange
+    unsigned long long epoch;      // strictly increasing per launch: flags never need a reset
+    double* mail[PPO_MAX_PEERS];              // mail[p]: rank p's mailbox, [world][PPO_STATS_LEN]
+    unsigned long long* flags[PPO_MAX_PEERS];  // flags[p]: rank p's flag words, [world]
+    double* global_stats;          // merged record of all ranks (optional), written by CTA 0
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // Combine per-thread statistics into one record per CTA, then let the last CTA to finish fold all
 // CTA records in index order (deterministic, no float atomics) into io.stats.
 __device__ void publish_stats(const ThreadStats& ts, const ScanStatsIo& io, double (*red)[PPO_STATS_LEN],
-                              unsigned int* ready = nullptr) {
+                              unsigned int* ready = nullptr, const PeerExchange* px = nullptr) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
     double n = warp_sum_f64(ts.n);
@@ -180,6 +200,15 @@ __device__ void publish_stats(const ThreadStats& ts, const ScanStatsIo& io, doub
             }
             io.stats[j] = j <= PPO_STAT_RET_ZEROS ? tot : 0.0;
             __threadfence();
+            if (px) {  // the local record goes to slot `rank` of every mailbox (remote stores over NVLink)
+                for (int r = 0; r < px->world; ++r)
+                    px->mail[r][px->rank * PPO_STATS_LEN + j] = j <= PPO_STAT_RET_ZEROS ? tot : 0.0;
+                __threadfence_system();
+            }
+        }
+        if (px) {
+            __syncthreads();  // all sixteen slots are on their way; the release stores order them before the flags
+            if (threadIdx.x < px->world) st_release_sys(px->flags[threadIdx.x] + px->rank, px->epoch);
         }
         if (ready) {  // the folded record is visible: release the CTAs that wait for it
             __syncthreads();
@@ -332,6 +361,7 @@ struct GaeTileParams {
     float* norm_out;           // [N * A] or nullptr
     float norm_eps, norm_clip;
     unsigned int* ready;       // two words: statistics-ready flag, exit counter (both zero between launches)
+    PeerExchange px;           // world > 1: the moments come from every rank's record (ppo_gae_normalized_peers)
 };
 
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
@@ -495,19 +525,64 @@ __global__ void __launch_bounds__(EW * kTileChunks) gae_tile_kernel(const GaeTil
         ts.n = hi > lo ? static_cast<double>(hi - lo) : 0.0;
         if (STATS && hi > lo && hi == N) ts.add_value(sv[N * EW + e]);  // the final estimate, row N
     }
-    if (STATS) publish_stats(ts, p.io, red, NORM ? q.ready : nullptr);
+    const bool peers = NORM && q.px.world > 1;
+    if (STATS) publish_stats(ts, p.io, red, NORM && !peers ? q.ready : nullptr, peers ? &q.px : nullptr);
     if (NORM) {
         // Grid-wide hand-off: the CTA that folds the records raises the flag (publish_stats), everyone else spins on
         // it -- legal because the launch is cooperative (all CTAs resident).  Then (x - mean) / (std + eps) exactly as
         // normalize_kernel computes it (rl/rollout.py:1887-1897), from the tile in shared memory.
+        // Env-sharded (peers): the flags are the ones the folding CTAs of ALL ranks raise in this rank's mailbox; the
+        // moments are summed in rank order, so every rank normalises with the same bits.
+        __shared__ double s_mom[3];
         if (threadIdx.x == 0) {
-            while (*reinterpret_cast<volatile unsigned int*>(q.ready) == 0u) __nanosleep(32);
-            __threadfence();
+            if (!peers) {
+                while (*reinterpret_cast<volatile unsigned int*>(q.ready) == 0u) __nanosleep(32);
+                __threadfence();
+                s_mom[0] = __ldcg(p.io.stats + PPO_STAT_COUNT);
+                s_mom[1] = __ldcg(p.io.stats + PPO_STAT_ADV_SUM);
+                s_mom[2] = __ldcg(p.io.stats + PPO_STAT_ADV_SUMSQ);
+            } else {
+                const unsigned long long* mine = q.px.flags[q.px.rank];
+                unsigned long long t0, t1;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+                bool ok = true;
+                for (int r = 0; r < q.px.world && ok; ++r) {
+                    while (ld_acquire_sys(mine + r) < q.px.epoch) {
+                        __nanosleep(64);
+                        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+                        if (t1 - t0 > 4000000000ull) {  // a peer never arrived (4 s): fail loudly instead of hanging
+                            ok = false;
+                            break;
+                        }
+                    }
+                }
+                const volatile double* mail = q.px.mail[q.px.rank];
+                double n = 0.0, sm = 0.0, sq = 0.0;
+                for (int r = 0; r < q.px.world; ++r) {
+                    n += mail[r * PPO_STATS_LEN + PPO_STAT_COUNT];
+                    sm += mail[r * PPO_STATS_LEN + PPO_STAT_ADV_SUM];
+                    sq += mail[r * PPO_STATS_LEN + PPO_STAT_ADV_SUMSQ];
+                }
+                s_mom[0] = ok ? n : NAN, s_mom[1] = sm, s_mom[2] = sq;
+            }
         }
         __syncthreads();
-        const double n = __ldcg(p.io.stats + PPO_STAT_COUNT);
-        const double mean64 = __ldcg(p.io.stats + PPO_STAT_ADV_SUM) / n;
-        const double var64 = fmax(__ldcg(p.io.stats + PPO_STAT_ADV_SUMSQ) / n - mean64 * mean64, 0.0);
+        if (peers && blockIdx.x == 0 && threadIdx.x < PPO_STATS_LEN && q.px.global_stats) {
+            // merged record of all ranks, in rank order (same reduction as ppo_merge_stats)
+            const int j = threadIdx.x;
+            const bool is_min = (j == PPO_STAT_ADV_MIN || j == PPO_STAT_RET_MIN);
+            const bool is_max = (j == PPO_STAT_ADV_MAX || j == PPO_STAT_RET_MAX);
+            const volatile double* mail = q.px.mail[q.px.rank];
+            double acc = is_min ? INFINITY : is_max ? -INFINITY : 0.0;
+            for (int r = 0; r < q.px.world; ++r) {
+                const double x = mail[r * PPO_STATS_LEN + j];
+                acc = is_min ? fmin(acc, x) : is_max ? fmax(acc, x) : acc + x;
+            }
+            q.px.global_stats[j] = j <= PPO_STAT_RET_ZEROS ? acc : 0.0;
+        }
+        const double n = s_mom[0];
+        const double mean64 = s_mom[1] / n;
+        const double var64 = fmax(s_mom[2] / n - mean64 * mean64, 0.0);
         const float mean = static_cast<float>(mean64);
         const float denom = __fadd_rn(static_cast<float>(sqrt(var64)), q.norm_eps);
         if (live) {
@@ -517,7 +592,7 @@ __global__ void __launch_bounds__(EW * kTileChunks) gae_tile_kernel(const GaeTil
         }
         // the last CTA to leave clears the flag and the counter for the next launch
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0 && !peers) {
             if (atomicAdd(q.ready + 1, 1u) == gridDim.x - 1) {
                 q.ready[0] = 0u;
                 q.ready[1] = 0u;
@@ -669,6 +744,8 @@ static int split_workspace(void* workspace, int64_t bytes, int64_t blocks, ScanS
 
 constexpr int kMomentsMaxBlocks = 1184;  // 8 CTAs of 512 threads per SM would not fit; 148 * 8 is the cap we size for
 
+static thread_local bool t_tile_dry_run = false;  // ppo_gae_normalized_fits: decide, do not launch
+
 template <int DONE, int EW>
 static int launch_gae_tile_variant(const GaeTileParams& q, bool stats, int64_t grid, size_t smem, cudaStream_t s) {
     if (q.norm_out) {
@@ -679,6 +756,7 @@ static int launch_gae_tile_variant(const GaeTileParams& q, bool stats, int64_t g
         int per_sm = 0;
         PPO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, EW * kTileChunks, smem));
         if (static_cast<int64_t>(per_sm) * sm_count() < grid) return PPO_ERR_UNSUPPORTED;
+        if (t_tile_dry_run) return PPO_OK;
         GaeTileParams copy = q;
         void* args[] = {&copy};
         PPO_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(static_cast<unsigned>(grid)),
@@ -701,7 +779,8 @@ static int launch_gae_tile_variant(const GaeTileParams& q, bool stats, int64_t g
 // The tile kernel when a whole [N, EW] tile fits in shared memory; PPO_ERR_UNSUPPORTED otherwise (the caller then
 // launches gae_kernel).  `p.io.stats` must already be set when statistics are wanted.
 static int launch_gae_tile(GaeParams p, int done_kind, bool want_stats, void* workspace, int64_t workspace_bytes,
-                           cudaStream_t s, float* norm_out = nullptr, float norm_eps = 0.f, float norm_clip = 0.f) {
+                           cudaStream_t s, float* norm_out = nullptr, float norm_eps = 0.f, float norm_clip = 0.f,
+                           const PeerExchange* px = nullptr) {
     const int64_t N = p.steps, A = p.envs;
     if (N > 4096) return PPO_ERR_UNSUPPORTED;
     // A strided value column (one DRAM sector per element) is a latency-bound gather; the register-cached kernel
@@ -750,6 +829,7 @@ static int launch_gae_tile(GaeParams p, int done_kind, bool want_stats, void* wo
         if (!want_stats) return PPO_ERR_UNSUPPORTED;
         q.norm_out = norm_out, q.norm_eps = norm_eps, q.norm_clip = norm_clip;
         q.ready = static_cast<unsigned int*>(workspace) + 32;  // bytes 128..135 of the reserved 256-byte header
+        if (px) q.px = *px;
     }
 #define PPO_TILE(D)                                                                    \
     (ew == 16 ? launch_gae_tile_variant<D, 16>(q, want_stats, grid, smem, s)           \
@@ -857,6 +937,61 @@ extern "C" int ppo_gae_normalized(const float* rewards, int64_t reward_row_strid
                      adv_out, ret_out, stats, workspace, workspace_bytes, stream);
     if (rc != PPO_OK) return rc;
     return ppo_adv_normalize(adv_out, steps * envs, stats, eps, clip, norm_out, stream);
+}
+
+extern "C" int ppo_gae_normalized_fits(int64_t steps, int64_t envs, int done_kind, int64_t value_env_stride) {
+    if (steps <= 0 || envs <= 0) return 0;
+    GaeParams p{};
+    alignas(16) static float dummy[4];
+    p.rewards = p.values = p.final_value = dummy, p.dones = dummy;  // never dereferenced: nothing is launched
+    p.r_rs = p.v_rs = p.d_rs = envs, p.v_es = value_env_stride, p.f_es = 1;
+    p.steps = steps, p.envs = envs, p.gl_adv = p.gl_ret = 0.5, p.gamma32 = 0.5f;
+    p.adv = p.ret = dummy;
+    double stats_dummy[PPO_STATS_LEN];
+    p.io.stats = stats_dummy;
+    t_tile_dry_run = true;
+    const int rc = launch_gae_tile(p, done_kind, true, dummy, ppo_gae_workspace_bytes(envs), nullptr, dummy, 1e-8f, 0.f);
+    t_tile_dry_run = false;
+    return rc == PPO_OK ? 1 : 0;
+}
+
+extern "C" int ppo_gae_normalized_peers(const float* rewards, int64_t reward_row_stride, const float* values,
+                                        int64_t value_row_stride, int64_t value_env_stride, const float* final_value,
+                                        int64_t final_env_stride, const void* dones, int done_kind,
+                                        int64_t done_row_stride, int64_t steps, int64_t envs, double gamma,
+                                        double lamb_adv, double lamb_ret, double eps, double clip, float* adv_out,
+                                        float* ret_out, float* norm_out, double* stats, double* global_stats,
+                                        void* workspace, int64_t workspace_bytes, int rank, int world,
+                                        double* const* peer_mail, unsigned long long* const* peer_flags,
+                                        unsigned long long epoch, void* stream) {
+    PPO_REQUIRE(stats && norm_out && adv_out, "ppo_gae_normalized_peers: stats, adv_out and norm_out are required");
+    PPO_REQUIRE(world >= 2 && world <= PPO_MAX_PEERS && rank >= 0 && rank < world,
+                "ppo_gae_normalized_peers: rank %d of %d (at most %d peers)", rank, world, PPO_MAX_PEERS);
+    PPO_REQUIRE(peer_mail && peer_flags && epoch > 0, "ppo_gae_normalized_peers: mailboxes and a positive epoch are required");
+    PPO_REQUIRE(steps > 0 && envs > 0 && rewards && values && final_value, "ppo_gae_normalized_peers: empty shard");
+    PPO_REQUIRE(done_kind == PPO_DONE_NONE || ((done_kind == PPO_DONE_U8 || done_kind == PPO_DONE_F32) && dones),
+                "ppo_gae_normalized_peers: bad done_kind %d", done_kind);
+    GaeParams p{};
+    p.rewards = rewards, p.r_rs = reward_row_stride;
+    p.values = values, p.v_rs = value_row_stride, p.v_es = value_env_stride;
+    p.final_value = final_value, p.f_es = final_env_stride;
+    p.dones = dones, p.d_rs = done_row_stride;
+    p.steps = steps, p.envs = envs;
+    p.gl_adv = gamma * lamb_adv, p.gl_ret = gamma * lamb_ret;
+    p.gamma32 = static_cast<float>(gamma);
+    p.adv = adv_out, p.ret = ret_out;
+    p.io.stats = stats;
+    PeerExchange px{};
+    px.world = world, px.rank = rank, px.epoch = epoch, px.global_stats = global_stats;
+    for (int r = 0; r < world; ++r) {
+        PPO_REQUIRE(peer_mail[r] && peer_flags[r], "ppo_gae_normalized_peers: null mailbox of rank %d", r);
+        px.mail[r] = peer_mail[r], px.flags[r] = peer_flags[r];
+    }
+    // Every rank must take the same decision (a rank that does not launch never raises its flags): the fused launch
+    // needs the tile kernel with its whole grid resident, which depends on the shard shape only.
+    const int rc = launch_gae_tile(p, done_kind, true, workspace, workspace_bytes, static_cast<cudaStream_t>(stream),
+                                   norm_out, static_cast<float>(eps), clip > 0 ? static_cast<float>(clip) : 0.f, &px);
+    return rc == PPO_OK ? 1 : 0;  // 0: not launched (shape does not fit), use ppo_gae + all-reduce + ppo_adv_normalize
 }
 
 extern "C" int ppo_discounted_returns(const float* rewards, int64_t reward_row_stride, const void* dones,

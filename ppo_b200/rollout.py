@@ -8,6 +8,7 @@ of the raw advantages (three float64, plus min / max for the logged statistics) 
 normalisation: one NCCL all-reduce over NVLink.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -241,6 +242,59 @@ def calculate_returns(ext_rewards, ext_value_estimates, terminals, gamma, lambda
     return result
 
 
+class PeerMailbox:
+    """Statistics mailboxes of every rank of ``group`` mapped into this process over NVLink peer memory (CUDA IPC,
+    ``ppo_peer_alloc`` / ``ppo_peer_open``), for ``ppo_gae_normalized_peers``: rank r owns ``[world, 16]`` float64
+    records followed by ``world`` 64-bit flag words; ``mail_ptrs[r]`` / ``flag_ptrs[r]`` are rank r's buffers as seen
+    from here.  Construction is collective.  ``ok`` is False when some rank cannot map a peer: callers then keep the
+    all-reduce."""
+
+    def __init__(self, device, group=None):
+        lib = _lib.load()
+        self.lib = lib
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.global_stats = torch.zeros(_lib.STATS_LEN, dtype=torch.float64, device=device)
+        self.epoch = 0
+        mail_bytes = self.world * _lib.STATS_LEN * 8
+        self._own, self._opened = ctypes.c_void_p(), []
+        handle = (ctypes.c_ubyte * 64)()
+        ok = self.world <= _lib.MAX_PEERS
+        with torch.cuda.device(device):
+            ok = ok and lib.ppo_peer_alloc(mail_bytes + self.world * 8, ctypes.byref(self._own), handle) == 0
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle) if ok else None, group=group)
+            bases = []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    bases.append(self._own.value or 0)
+                    continue
+                ptr = ctypes.c_void_p()
+                if h is None or lib.ppo_peer_open((ctypes.c_ubyte * 64).from_buffer_copy(h), ctypes.byref(ptr)) != 0:
+                    ok = False
+                    bases.append(0)
+                else:
+                    self._opened.append(ptr)
+                    bases.append(ptr.value)
+        flag = torch.tensor([1 if ok else 0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        self.ok = bool(flag.item())
+        self.mail_ptrs = (ctypes.c_void_p * self.world)(*bases)
+        self.flag_ptrs = (ctypes.c_void_p * self.world)(*[b + mail_bytes if b else 0 for b in bases])
+
+    def next_epoch(self):
+        self.epoch += 1
+        return self.epoch
+
+    def close(self):
+        """Unmap the peers and free the own mailbox (collective in spirit: no rank may still be launching)."""
+        for ptr in self._opened:
+            self.lib.ppo_peer_close(ptr)
+        self._opened = []
+        if self._own:
+            self.lib.ppo_peer_free(self._own)
+            self._own = ctypes.c_void_p()
+
+
 class ReturnPass:
     """Device-resident form of the return stage for one rank's env block: buffers stay in HBM, outputs
     and workspaces are allocated once, and ``run()`` is exactly the launches of one pass
@@ -285,6 +339,16 @@ class ReturnPass:
                                   dtype=torch.uint8, device=self.device)
         self.ws_tvf = torch.zeros(max(int(self.lib.ppo_tvf_workspace_bytes(self.steps, self.envs)), 1 << 12),
                                   dtype=torch.uint8, device=self.device)
+        # env-sharded: the moment exchange inside the GAE launch over NVLink peer memory when every rank can take the
+        # single cooperative launch for its shard and map its peers (PPO_PEER_EXCHANGE=0 keeps the NCCL all-reduce)
+        self.peers = None
+        if self.sharded and os.environ.get("PPO_PEER_EXCHANGE", "1") != "0":
+            fits = torch.tensor([int(self.lib.ppo_gae_normalized_fits(self.steps, self.envs, _lib.DONE_U8, 1))],
+                                device=self.device)
+            dist.all_reduce(fits, op=dist.ReduceOp.MIN, group=group)
+            if fits.item() == 1 and dist.get_world_size(group) <= _lib.MAX_PEERS:
+                box = PeerMailbox(self.device, group)
+                self.peers = box if box.ok else None
         self._ctab = self._blob = None
         self.kernel_launches_per_pass = 4
         self._tvf_launches = 2
@@ -337,7 +401,24 @@ class ReturnPass:
             targets(extras)
             values = self.value_estimates
         gae_launches = 2
-        if self.sharded:
+        peer_rc = 0
+        if self.sharded and self.peers is not None and values.stride(1) == 1:
+            # moments exchanged inside the launch (NVLink peer mailboxes): GAE, TD(lambda), statistics, the cross-GPU
+            # sum and the normalisation in ONE cooperative launch per rank
+            box = self.peers
+            peer_rc = lib.ppo_gae_normalized_peers(
+                rewards.data_ptr(), rewards.stride(0), values.data_ptr(), values.stride(0), values.stride(1),
+                values[n].data_ptr(), values.stride(1), dones.data_ptr(), _lib.DONE_U8, dones.stride(0), n, a,
+                self.gamma, self.lambda_policy, self.lambda_value, self.eps, self.clip, self.advantage.data_ptr(),
+                self.ext_returns.data_ptr(), self.advantages.data_ptr(), self.stats.data_ptr(),
+                box.global_stats.data_ptr(), self.ws_gae.data_ptr(), self.ws_gae.numel(), box.rank, box.world,
+                box.mail_ptrs, box.flag_ptrs, box.next_epoch(), s)
+            _lib.check(peer_rc, "ppo_gae_normalized_peers")
+            assert peer_rc == 1, "ppo_gae_normalized_peers declined a shard shape ppo_gae_normalized_fits accepted"
+            gae_launches = 1
+        if peer_rc == 1:
+            pass
+        elif self.sharded:
             rc = lib.ppo_gae(rewards.data_ptr(), rewards.stride(0), values.data_ptr(), values.stride(0),
                              values.stride(1), values[n].data_ptr(), values.stride(1), dones.data_ptr(), _lib.DONE_U8,
                              dones.stride(0), n, a, self.gamma, self.lambda_policy, self.lambda_value,

@@ -74,6 +74,40 @@ def main():
     dist.all_reduce(total)
     check("clip count", total.item(), fc.item(), 0.0)
 
+    # ---- device-resident pass: the moment exchange inside the GAE launch over NVLink peer mailboxes must give the
+    # same bits as the NCCL all-reduce between two launches, and both the unsharded normalisation
+    from ppo_b200 import returns_truncated as rt
+    table = rt.draw_n_step_samples("exponential", "advanced", hz, steps, 12, 6, seed=4)
+    dev_t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()  # noqa: E731
+    sr, sv, sd, svs = dev_t(shard(r)), dev_t(shard(v)), dev_t(shard(d)).view(torch.uint8), dev_t(shard(vs))
+    passes = {}
+    for name, env in (("peers", "1"), ("nccl", "0")):
+        os.environ["PPO_PEER_EXCHANGE"] = env
+        rp = rollout.ReturnPass(steps, envs // world, hz, 0.999, 0.9999, 0.95, 0.9, advantage_clipping=2.0)
+        rp.set_samples(table)
+        for _ in range(3):  # several epochs through the same mailboxes
+            rp.run(sr, sv, sd, svs)
+        torch.cuda.synchronize()
+        passes[name] = (rp.advantages.clone(), rp.kernel_launches_per_pass, rp.peers is not None,
+                        None if rp.peers is None else rp.peers.global_stats.clone(), rp.stats.clone())
+        dist.barrier()
+        if rp.peers is not None:
+            rp.peers.close()
+    adv_p, launches_p, used_p, gstats, _ = passes["peers"]
+    adv_n, launches_n, _, _, nstats = passes["nccl"]
+    if rank == 0:
+        print(f"dist_check: peer exchange {'active' if used_p else 'UNAVAILABLE'}: {launches_p} launches per pass "
+              f"against {launches_n} with the all-reduce", flush=True)
+    check("peers vs nccl normalised advantages", adv_p.cpu().numpy(), adv_n.cpu().numpy(), 0.0 if used_p else 1e-6)
+    check("peers normalised advantages vs unsharded", adv_p.cpu().numpy().reshape(steps, -1),
+          shard(np.asarray(full["advantages"]).reshape(steps, envs)))
+    if used_p:
+        a, b = rollout.stats_summary(gstats), rollout.stats_summary(full["stats"])
+        for key in ("count", "adv_mean", "adv_std", "adv_min", "adv_max", "ret_mean", "ret_min", "ret_max"):
+            check("peer global stats." + key, a[key], b[key], 1e-9)
+        if launches_p != launches_n - 1:
+            failures.append(f"rank {rank}: expected one launch fewer with the peer exchange ({launches_p} vs {launches_n})")
+
     flags = torch.tensor([len(failures)], device="cuda")
     dist.all_reduce(flags)
     for line in failures:
