@@ -47,7 +47,8 @@ def config(n_gpus):
         "max_horizon": MAX_HORIZON, "gae": {"gamma": GAMMA, "lambda_policy": LAMBDA_POLICY, "lambda_value": LAMBDA_VALUE},
         "tvf": {"gamma": TVF_GAMMA, "distribution": "exponential", "mode": "advanced", "n_step": N_STEP,
                 "samples": SAMPLES, "seed": SAMPLE_SEED},
-        "sharding": f"env axis over {n_gpus} rank(s), all-reduce of 3 float64 advantage moments" if n_gpus > 1
+        "sharding": f"env axis over {n_gpus} rank(s); the 3 float64 advantage moments are exchanged inside the GAE launch "
+                    f"over NVLink peer mailboxes (NCCL all-reduce with PPO_PEER_EXCHANGE=0)" if n_gpus > 1
                     else "single GPU, no collective",
         "l2": "per-step working set 1.1 GB per GPU exceeds the 126 MB L2, no explicit flush",
         "sample_table": "drawn on the host with the reference's NumPy RNG calls; resolved index tables uploaded "

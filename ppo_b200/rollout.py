@@ -5,7 +5,8 @@ functions over rollout buffers, with the env axis optionally sharded over ``torc
 Envs are independent, so each rank owns a contiguous block of envs of every ``[N, A, ...]`` buffer and
 runs the same kernels on its block.  The only exchange is the sum of ``{count, sum, sum of squares}``
 of the raw advantages (three float64, plus min / max for the logged statistics) before the
-normalisation: one NCCL all-reduce over NVLink.
+normalisation: inside the GAE launch over NVLink peer mailboxes for the resident pass (``ReturnPass``,
+``PeerMailbox``), one NCCL all-reduce otherwise.
 """
 import ctypes
 import os
