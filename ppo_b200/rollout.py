@@ -356,6 +356,13 @@ class ReturnPass:
         self.tvf_kernel = "?"
         self.value_estimates = self._value_weights = None
 
+    def close(self):
+        """Release the peer mailboxes (env-sharded passes).  Collective in spirit: call it on every rank once no rank
+        launches this pass any more (e.g. after a barrier)."""
+        if self.peers is not None:
+            self.peers.close()
+            self.peers = None
+
     def set_samples(self, n_step_samples):
         tabs = _rt.build_tables(self.tvf_gamma, self.steps, self.horizons, self.horizons, n_step_samples,
                                 self.use_log)

@@ -104,6 +104,8 @@ def test_gae_with_fused_normalisation(steps, envs, clip, fused):
     s = dev.stream_ptr()
     args = (r.data_ptr(), envs, v.data_ptr(), envs, 1, v[steps].data_ptr(), 1, d.data_ptr(), _lib.DONE_U8, envs,
             steps, envs, 0.999, 0.95, 0.9)
+    # the shape query that env-sharded ranks agree on before relying on the in-launch exchange says the same
+    assert lib.ppo_gae_normalized_fits(steps, envs, _lib.DONE_U8, 1) == (1 if fused else 0)
     for _ in range(2):  # twice: the flags of the cooperative launch must be left clear
         rc = lib.ppo_gae_normalized(*args, 1e-8, clip or 0.0, outs[0].data_ptr(), outs[1].data_ptr(),
                                     outs[2].data_ptr(), st[0].data_ptr(), ws.data_ptr(), ws.numel(), s)
