@@ -112,16 +112,6 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// acc += [n <= lim] * (lo * wlo + hi * whi): the per-lane predicate stays a predicate on the two FMAs.
-__device__ __forceinline__ void ts_fma_if(float& acc, float lo, float hi, float wlo, float whi, int n, int lim) {
-    asm("{\n\t.reg .pred p;\n\t"
-        "setp.le.s32 p, %5, %6;\n\t"
-        "@p fma.rn.f32 %0, %1, %3, %0;\n\t"
-        "@p fma.rn.f32 %0, %2, %4, %0;\n\t}"
-        : "+f"(acc)
-        : "f"(lo), "f"(hi), "f"(wlo), "f"(whi), "r"(n), "r"(lim));
-}
-
 // Shared-memory form of the launch constants: an entry is 12 bytes {off | n << 18, wlo, whi} and every horizon's list
 // starts at a multiple of four entries (48 bytes), so four entries are three 16-byte broadcast reads -- 1.5 wavefronts
 // per entry instead of the 2 of a 16-byte entry (a broadcast LDS.128 costs two wavefronts, tools/micro_lsu.cu); a
@@ -141,12 +131,23 @@ __device__ __forceinline__ uint32_t ts_lds_u32(uint32_t addr) {
     return v;
 }
 
+// acc += [n <= lim] * (lo * wlo + hi * whi) with the predicate taken on the packed word: w = n << 18 | off and
+// lim_key = (lim + 1) << 18, so n <= lim  <=>  w < lim_key (no shift per entry).
+__device__ __forceinline__ void ts_fma_ifw(float& acc, float lo, float hi, float wlo, float whi, uint32_t w, uint32_t lim_key) {
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.lt.u32 p, %5, %6;\n\t"
+        "@p fma.rn.f32 %0, %1, %3, %0;\n\t"
+        "@p fma.rn.f32 %0, %2, %4, %0;\n\t}"
+        : "+f"(acc)
+        : "f"(lo), "f"(hi), "f"(wlo), "f"(whi), "r"(w), "r"(lim_key));
+}
+
 // G entries of one horizon for the thread's two time rows (t, t + 32); `cent` is 16-byte aligned for G = 4 and G = 2
 // and 8-byte aligned for G = 1.  All gathers are issued before the first use.  PITCH4 = slab pitch in bytes when it is
 // known at compile time (immediate offsets), 0 = runtime pitch in `p4`.
 template <int G, int PITCH4>
-__device__ __forceinline__ void ts_eval(uint32_t cent, uint32_t base, uint32_t p4, int lim0, int lim1, float& acc0,
-                                        float& acc1) {
+__device__ __forceinline__ void ts_eval(uint32_t cent, uint32_t base, uint32_t p4, uint32_t lim0, uint32_t lim1,
+                                        float& acc0, float& acc1) {
     uint32_t w[3 * G];
     if (G == 4) {
 #pragma unroll
@@ -178,9 +179,8 @@ __device__ __forceinline__ void ts_eval(uint32_t cent, uint32_t base, uint32_t p
 #pragma unroll
     for (int i = 0; i < G; ++i) {
         const float wlo = __uint_as_float(w[3 * i + 1]), whi = __uint_as_float(w[3 * i + 2]);
-        const int n = static_cast<int>(w[3 * i] >> kTsOffBits);
-        ts_fma_if(acc0, lo0[i], hi0[i], wlo, whi, n, lim0);
-        ts_fma_if(acc1, lo1[i], hi1[i], wlo, whi, n, lim1);
+        ts_fma_ifw(acc0, lo0[i], hi0[i], wlo, whi, w[3 * i], lim0);
+        ts_fma_ifw(acc1, lo1[i], hi1[i], wlo, whi, w[3 * i], lim1);
     }
 }
 
@@ -529,6 +529,8 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                 const int lim1 = ts_lds_s32(lt + static_cast<uint32_t>(t1) * 4u);
                 const float R0 = ts_lds(rt + static_cast<uint32_t>(t0) * 4u);
                 const float R1 = ts_lds(rt + static_cast<uint32_t>(t1) * 4u);
+                // n <= lim as one unsigned compare on the packed entry word (ts_fma_ifw)
+                const uint32_t key0 = static_cast<uint32_t>(lim0 + 1) << kTsOffBits, key1 = static_cast<uint32_t>(lim1 + 1) << kTsOffBits;
                 const int m0 = N - t0, m1 = N - t1;              // rows left
                 const int m_min = N - (s * kTsStep + kTsStep - 1);  // smallest m of the step (may be <= 0)
                 const bool end0 = m0 >= 1 && m0 <= nmax && lim0 == m0;  // alive until the rollout ends, window may run off
@@ -590,9 +592,9 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                         float acc0 = tacc0[u], acc1 = tacc1[u];
                         uint32_t ce = ent_a + (hz[u].x & 0xfffu) * kTsEntBytes;
                         int left = (q.dbg & 8) ? 0 : static_cast<int>((hz[u].x >> 12) & 0xffu);
-                        for (; left >= 4; left -= 4, ce += 4 * kTsEntBytes) ts_eval<4, PITCH4>(ce, base, P4, lim0, lim1, acc0, acc1);
-                        if (left >= 2) ts_eval<2, PITCH4>(ce, base, P4, lim0, lim1, acc0, acc1), ce += 2 * kTsEntBytes, left -= 2;
-                        if (left >= 1) ts_eval<1, PITCH4>(ce, base, P4, lim0, lim1, acc0, acc1);
+                        for (; left >= 4; left -= 4, ce += 4 * kTsEntBytes) ts_eval<4, PITCH4>(ce, base, P4, key0, key1, acc0, acc1);
+                        if (left >= 2) ts_eval<2, PITCH4>(ce, base, P4, key0, key1, acc0, acc1), ce += 2 * kTsEntBytes, left -= 2;
+                        if (left >= 1) ts_eval<1, PITCH4>(ce, base, P4, key0, key1, acc0, acc1);
                         const float rs = __uint_as_float(hz[u].y);
                         o0[u] = fmaf(rs, R0, acc0 * inv_c);
                         o1[u] = fmaf(rs, R1, acc1 * inv_c);
