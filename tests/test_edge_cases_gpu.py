@@ -3,7 +3,6 @@ of the kernels' fast paths: empty and single-element rollouts, every step termin
 horizon counts that no slab kernel takes, repeated horizons."""
 import numpy as np
 import pytest
-import torch
 
 import oracle
 from ppo_b200 import _lib, normalization as nz, returns, returns_truncated as rt, rollout, synthetic, vtrace
