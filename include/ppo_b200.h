@@ -239,7 +239,8 @@ typedef struct {
 
 /* Offsets (in 32-bit words) of the tables inside the packed blob written by ppo_tvf_tables_build: [0..11] in the
  * order of the first twelve pointer members of ppo_tvf_tables (ent_n ... gpow), [12..14] tailT_idx / tailT_cwlo /
- * tailT_cwhi, [15] launch constants of the transposed slab kernel; every table starts 16-byte aligned. */
+ * tailT_cwhi, [15] launch constants of the transposed slab kernel (header, horizon records, entries, then the tail
+ * tables once more as interleaved 16-byte records); every table starts 16-byte aligned. */
 typedef struct {
     int32_t n_entries;
     int32_t nmax;

@@ -77,7 +77,7 @@ extern "C" int64_t ppo_tvf_tables_words(int64_t n_req, int64_t n_samples, int64_
     const int64_t e = std::min<int64_t>(n_samples, std::max<int64_t>(steps, 1));
     auto pad = [](int64_t w) { return (w + 3) / 4 * 4; };
     return 6 * pad(e * n_req) + 5 * pad((steps + 1) * n_req) + pad(steps + 1) + 3 * pad(n_req * pad(steps + 1)) +
-           pad(4 + 4 * n_req + 4 * e * n_req) + 16;
+           pad(4 + 4 * n_req + 4 * e * n_req) + 4 * n_req * pad(steps + 1) + 16;
 }
 
 extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* required_horizons, int64_t n_req,
@@ -188,7 +188,9 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
     const int64_t tpitch = pad(nmax + 1);
     for (int i = 12; i < 15; ++i) offs[i] = off, off += pad(static_cast<int64_t>(K) * tpitch);
     // launch constants of the transposed slab kernel: header, K horizon records, the live entries
-    offs[15] = off, off += pad(4 + 4 * static_cast<int64_t>(K) + 4 * ek);
+    // (+ the folded tail tables once more, interleaved {idx, cwlo, cwhi, 0} per (horizon, tail length): one 16-byte
+    // load per row instead of three 4-byte loads)
+    offs[15] = off, off += pad(4 + 4 * static_cast<int64_t>(K) + 4 * ek) + 4 * static_cast<int64_t>(K) * tpitch;
     if (off > blob_words) {
         set_error("ppo_tvf_tables_build: blob of %lld words required, got %lld", (long long)off, (long long)blob_words);
         return PPO_ERR_WORKSPACE;
@@ -278,6 +280,13 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
             h.rscale = static_cast<float>(csum / static_cast<double>(C));
         }
         if (ok) hdr[1] = total;
+        // interleaved tail records behind the entry capacity: [K][tail_pitch] x {idx, cwlo, cwhi, 0}
+        int32_t* t4 = hdr + pad(4 + 4 * static_cast<int64_t>(K) + 4 * ek);
+        const int32_t* t_idx = blob + offs[12];
+        const int32_t* t_wlo = blob + offs[13];  // float bits
+        const int32_t* t_whi = blob + offs[14];
+        for (int64_t i = 0; i < static_cast<int64_t>(K) * tpitch; ++i)
+            t4[4 * i] = t_idx[i], t4[4 * i + 1] = t_wlo[i], t4[4 * i + 2] = t_whi[i], t4[4 * i + 3] = 0;
     }
     layout->tail_pitch = static_cast<int32_t>(tpitch);
     layout->gamma = gamma;

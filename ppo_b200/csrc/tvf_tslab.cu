@@ -61,6 +61,7 @@ struct TsParams {
     double* stats;
     const TsHorizon* hz;  // [K] device copies of the launch constants (inside the packed table blob)
     const TsEntry* ent;   // [n_ent]
+    const uint4* tail4;   // [K][tail_pitch] folded tail records {idx lo | hi << 16, cwlo, cwhi, 0}
 };
 
 // development: globaltimer stamps of CTA 0 at a few hand-off points (PPO_TVF_DEBUG bit 64), read by ppo_tvf_debug_times
@@ -558,32 +559,25 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                     float tacc0[4] = {0.f, 0.f, 0.f, 0.f}, tacc1[4] = {0.f, 0.f, 0.f, 0.f};
                     const int maxn_q = static_cast<int>(max(max(hz[0].x >> 20, hz[1].x >> 20), max(hz[2].x >> 20, hz[3].x >> 20)));
                     if (any_end && m_min < maxn_q && !(q.dbg & 16)) {
-                        int idx0[4], idx1[4];
-                        float w00[4], w01[4], w10[4], w11[4];
+                        uint4 r0[4], r1[4];  // one 16-byte record per (horizon, row): slots, folded weights
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const int64_t tb = static_cast<int64_t>(quad * 4 + u) * q.tail_pitch;
-                            idx0[u] = 0, idx1[u] = 0, w00[u] = 0.f, w01[u] = 0.f, w10[u] = 0.f, w11[u] = 0.f;
-                            if (any_end0 && end0) {
-                                idx0[u] = __ldg(p.tab.tailT_idx + tb + m0);
-                                w00[u] = __ldg(p.tab.tailT_cwlo + tb + m0), w01[u] = __ldg(p.tab.tailT_cwhi + tb + m0);
-                            }
-                            if (any_end1 && end1) {
-                                idx1[u] = __ldg(p.tab.tailT_idx + tb + m1);
-                                w10[u] = __ldg(p.tab.tailT_cwlo + tb + m1), w11[u] = __ldg(p.tab.tailT_cwhi + tb + m1);
-                            }
+                            const uint4* tb = q.tail4 + (quad * 4 + u) * q.tail_pitch;
+                            r0[u] = make_uint4(0u, 0u, 0u, 0u), r1[u] = r0[u];
+                            if (any_end0 && end0) r0[u] = __ldg(tb + m0);
+                            if (any_end1 && end1) r1[u] = __ldg(tb + m1);
                         }
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             if (any_end0 && end0) {
-                                const float v0 = ts_lds(fr_e + static_cast<uint32_t>(idx0[u] & 0xffff) * 4u);
-                                const float v1 = ts_lds(fr_e + static_cast<uint32_t>(idx0[u] >> 16) * 4u);
-                                tacc0[u] = fmaf(v1, w01[u], v0 * w00[u]);
+                                const float v0 = ts_lds(fr_e + (r0[u].x & 0xffffu) * 4u);
+                                const float v1 = ts_lds(fr_e + (r0[u].x >> 16) * 4u);
+                                tacc0[u] = fmaf(v1, __uint_as_float(r0[u].z), v0 * __uint_as_float(r0[u].y));
                             }
                             if (any_end1 && end1) {
-                                const float v0 = ts_lds(fr_e + static_cast<uint32_t>(idx1[u] & 0xffff) * 4u);
-                                const float v1 = ts_lds(fr_e + static_cast<uint32_t>(idx1[u] >> 16) * 4u);
-                                tacc1[u] = fmaf(v1, w11[u], v0 * w10[u]);
+                                const float v0 = ts_lds(fr_e + (r1[u].x & 0xffffu) * 4u);
+                                const float v1 = ts_lds(fr_e + (r1[u].x >> 16) * 4u);
+                                tacc1[u] = fmaf(v1, __uint_as_float(r1[u].z), v0 * __uint_as_float(r1[u].y));
                             }
                         }
                     }
@@ -756,6 +750,7 @@ int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsign
     const int32_t* dhdr = static_cast<const int32_t*>(p.tab.dev_blob) + p.tab.tslab_offset_words;
     q.hz = reinterpret_cast<const TsHorizon*>(dhdr + 4);
     q.ent = reinterpret_cast<const TsEntry*>(dhdr + 4 + 4 * K);
+    q.tail4 = reinterpret_cast<const uint4*>(dhdr + (4 + 4 * K + 4 * static_cast<int64_t>(E) * K + 3) / 4 * 4);
     q.n_ent = total;
 
     int dev = 0, max_smem = 0;
