@@ -524,8 +524,10 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                     mbar_wait(&wfull[sl * kTsMaxChunks + waited], use_par);
                     ++waited;
                 }
-                if (lane == 0 && cw == 0 && e == 0 && s == 0) ts_stamp(q, 5);  // consumers start the first step
-                if (lane == 0 && cw == 0 && e == nenv - 1 && s == NS - 1) ts_stamp(q, 7);  // ... the last step
+                if (q.dbg & 64) {  // (the switch first: one uniform branch per step when it is off)
+                    if (lane == 0 && cw == 0 && e == 0 && s == 0) ts_stamp(q, 5);  // consumers start the first step
+                    if (lane == 0 && cw == 0 && e == nenv - 1 && s == NS - 1) ts_stamp(q, 7);  // ... the last step
+                }
                 const int lim0 = ts_lds_s32(lt + static_cast<uint32_t>(t0) * 4u);
                 const int lim1 = ts_lds_s32(lt + static_cast<uint32_t>(t1) * 4u);
                 const float R0 = ts_lds(rt + static_cast<uint32_t>(t0) * 4u);
@@ -539,6 +541,9 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                 // warp votes: the tail work of a 32-row half is skipped when none of its rows is alive to the end
                 const bool any_end0 = __any_sync(0xffffffffu, end0), any_end1 = __any_sync(0xffffffffu, end1);
                 const bool any_end = any_end0 || any_end1;
+                // this thread's two columns of the folded tail records (only dereferenced for rows alive to the end)
+                const uint4* tail0 = q.tail4 + (end0 ? m0 : 0);
+                const uint4* tail1 = q.tail4 + (end1 ? m1 : 0);
                 const uint32_t base = wt_e + static_cast<uint32_t>(t0) * 4u;
                 // output tile: [half][32-horizon group][32 rows][128 B], 16-byte chunks swizzled with the row (TMA 128B
                 // swizzle): the 8 lanes of a quarter-warp store to 8 different bank groups
@@ -562,10 +567,10 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                         uint4 r0[4], r1[4];  // one 16-byte record per (horizon, row): slots, folded weights
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const uint4* tb = q.tail4 + (quad * 4 + u) * q.tail_pitch;
+                            const int tb = (quad * 4 + u) * q.tail_pitch;  // one 32 x 32 + 64 multiply-add per load
                             r0[u] = make_uint4(0u, 0u, 0u, 0u), r1[u] = r0[u];
-                            if (any_end0 && end0) r0[u] = __ldg(tb + m0);
-                            if (any_end1 && end1) r1[u] = __ldg(tb + m1);
+                            if (any_end0 && end0) r0[u] = __ldg(tail0 + tb);
+                            if (any_end1 && end1) r1[u] = __ldg(tail1 + tb);
                         }
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
