@@ -27,7 +27,7 @@ constexpr int kTsMaxEntries = 1024;
 constexpr int kTsConstMagic = 0x54534c42;  // header word of the constants section: magic, n_ent (-1 = none), pitch, V
 struct __align__(16) TsEntry {
     uint32_t off;    // byte offset of W^T[col][n - 1] in the slab
-    float wlo, whi;  // multiplicity * gamma^n * lerp weights
+    float wlo, whi;  // multiplicity * gamma^n * lerp weights / samples per horizon
     int32_t n;
 };
 struct __align__(16) TsHorizon {

@@ -268,7 +268,9 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
                 else if (x.l.hi == x.l.lo) col = x.l.lo, bw = 0.0;
                 else if (x.l.hi == x.l.lo + 1) col = x.l.lo;
                 else { ok = false; break; }
-                const double cg = static_cast<double>(x.cnt) * gp64[x.n];
+                // the 1 / C of the sample average is folded in here (and into the tail records below), so the kernel
+                // finishes a target with one multiply-add
+                const double cg = static_cast<double>(x.cnt) * gp64[x.n] / static_cast<double>(C);
                 TsEntry& t = te[total++];
                 t.off = static_cast<uint32_t>((static_cast<int64_t>(col) * pitch + x.n - 1) * 4);
                 t.wlo = static_cast<float>(a * cg), t.whi = static_cast<float>(bw * cg);
@@ -285,8 +287,14 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
         const int32_t* t_idx = blob + offs[12];
         const int32_t* t_wlo = blob + offs[13];  // float bits
         const int32_t* t_whi = blob + offs[14];
-        for (int64_t i = 0; i < static_cast<int64_t>(K) * tpitch; ++i)
-            t4[4 * i] = t_idx[i], t4[4 * i + 1] = t_wlo[i], t4[4 * i + 2] = t_whi[i], t4[4 * i + 3] = 0;
+        const double inv_c = 1.0 / static_cast<double>(C);
+        for (int64_t i = 0; i < static_cast<int64_t>(K) * tpitch; ++i) {
+            float wl, wh;
+            memcpy(&wl, t_wlo + i, 4), memcpy(&wh, t_whi + i, 4);
+            wl = static_cast<float>(static_cast<double>(wl) * inv_c), wh = static_cast<float>(static_cast<double>(wh) * inv_c);
+            t4[4 * i] = t_idx[i], t4[4 * i + 3] = 0;
+            memcpy(t4 + 4 * i + 1, &wl, 4), memcpy(t4 + 4 * i + 2, &wh, 4);
+        }
     }
     layout->tail_pitch = static_cast<int32_t>(tpitch);
     layout->gamma = gamma;

@@ -502,7 +502,6 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
         // ------------------------------------------------------------------ consumers
         const int cw = warp;
         const uint32_t P4 = static_cast<uint32_t>(P) * 4u;
-        const float inv_c = p.tab.inv_c;
         // statistics of the longest horizon (want_stats): float64 partial sums of this thread
         double st_n = 0.0, st_s = 0.0, st_q = 0.0, st_z = 0.0;
         float st_mn = INFINITY, st_mx = -INFINITY;
@@ -562,8 +561,8 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                     // rows whose n-step windows run off the rollout: one folded bootstrap from the final row, host
                     // weights from the horizon-major tables (issued for the whole quad before the entry loops)
                     float tacc0[4] = {0.f, 0.f, 0.f, 0.f}, tacc1[4] = {0.f, 0.f, 0.f, 0.f};
-                    const int maxn_q = static_cast<int>(max(max(hz[0].x >> 20, hz[1].x >> 20), max(hz[2].x >> 20, hz[3].x >> 20)));
-                    if (any_end && m_min < maxn_q && !(q.dbg & 16)) {
+                    if (any_end && !(q.dbg & 16) &&
+                        m_min < static_cast<int>(max(max(hz[0].x >> 20, hz[1].x >> 20), max(hz[2].x >> 20, hz[3].x >> 20)))) {
                         uint4 r0[4], r1[4];  // one 16-byte record per (horizon, row): slots, folded weights
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
@@ -595,8 +594,8 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                         if (left >= 2) ts_eval<2, PITCH4>(ce, base, P4, key0, key1, acc0, acc1), ce += 2 * kTsEntBytes, left -= 2;
                         if (left >= 1) ts_eval<1, PITCH4>(ce, base, P4, key0, key1, acc0, acc1);
                         const float rs = __uint_as_float(hz[u].y);
-                        o0[u] = fmaf(rs, R0, acc0 * inv_c);
-                        o1[u] = fmaf(rs, R1, acc1 * inv_c);
+                        o0[u] = fmaf(rs, R0, acc0);  // the entry and tail weights carry the 1 / C of the average
+                        o1[u] = fmaf(rs, R1, acc1);
                     }
                     if (!tile_free) {  // the previous step's tile has been copied out (single output tile)
                         mbar_wait(oempty, (it & 1u) ^ 1u);
