@@ -235,6 +235,8 @@ typedef struct {
     const void* dev_blob;
     double gamma;
     int64_t tslab_offset_words;
+    int64_t cslab_offset_words; /* (optional, 0 = absent) the same for the column slab kernel
+                                   (ppo_tvf_table_layout.cslab_offset_words) */
 } ppo_tvf_tables;
 
 /* Offsets (in 32-bit words) of the tables inside the packed blob written by ppo_tvf_tables_build: [0..11] in the
@@ -249,6 +251,8 @@ typedef struct {
     float inv_c;
     int32_t tail_pitch;
     double gamma;
+    int64_t cslab_offset_words; /* launch constants of the column slab kernel (header, horizon words, job words,
+                                   entries in ascending n-step order with their aligned row groups) */
 } ppo_tvf_table_layout;
 
 /*
@@ -269,11 +273,13 @@ int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* required_ho
 
 /* which TVF kernel ppo_tvf_targets may use */
 typedef enum {
-    PPO_TVF_AUTO = 0,    /* transposed slab kernel for >= 3 n-steps per horizon, else the TMA ring kernel, when the
-                            shape allows them; else the generic kernel */
+    PPO_TVF_AUTO = 0,    /* column slab kernel (else the transposed slab kernel) for >= 3 n-steps per horizon, else
+                            the TMA ring kernel, when the shape allows them; else the generic kernel */
     PPO_TVF_GENERIC = 1, /* global-memory gather kernel, any shape                            */
     PPO_TVF_RING = 2,    /* TMA ring kernel or PPO_ERR_UNSUPPORTED                            */
-    PPO_TVF_TSLAB = 3    /* transposed slab kernel or PPO_ERR_UNSUPPORTED                     */
+    PPO_TVF_TSLAB = 3,   /* transposed slab kernel or PPO_ERR_UNSUPPORTED                     */
+    PPO_TVF_CSLAB = 4    /* column slab kernel (128 or 256 steps, <= 128 value horizons in multiples of 32, horizon
+                            count a multiple of 4) or PPO_ERR_UNSUPPORTED */
 } ppo_tvf_path;
 
 /*

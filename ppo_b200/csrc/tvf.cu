@@ -20,6 +20,9 @@ namespace ppo {
 int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsigned int* ticket, int64_t max_partials,
                      const float* host_value_weights, float* value_out, int64_t value_row_stride, cudaStream_t stream,
                      bool* stats_fused);  // tvf_tslab.cu
+int launch_tvf_cslab(const TvfParams& p, double* stats, double* partials, unsigned int* ticket, int64_t max_partials,
+                     const float* host_value_weights, float* value_out, int64_t value_row_stride, cudaStream_t stream,
+                     bool* stats_fused);
 int launch_value_dot(const float* v, int64_t rows_t, int64_t envs, int64_t rs_t, int64_t rs_e, int k,
                      const float* host_weights, float* out, int64_t os_t, cudaStream_t s);  // value_estimate.cu
 int launch_tvf_ring(const TvfParams& p, const float* tail_cwlo, const float* tail_cwhi, cudaStream_t stream,
@@ -255,7 +258,8 @@ extern "C" int ppo_tvf_targets_ex(const float* rewards, int64_t reward_row_strid
     PPO_REQUIRE(steps < (1 << 24) && n_req < (1 << 20) && n_val < (1 << 16), "ppo_tvf_targets: shape too large");
     PPO_REQUIRE(done_kind == PPO_DONE_U8 || done_kind == PPO_DONE_F32 || done_kind == PPO_DONE_NONE,
                 "ppo_tvf_targets: unknown done_kind %d", done_kind);
-    PPO_REQUIRE(path == PPO_TVF_AUTO || path == PPO_TVF_GENERIC || path == PPO_TVF_RING || path == PPO_TVF_TSLAB,
+    PPO_REQUIRE(path == PPO_TVF_AUTO || path == PPO_TVF_GENERIC || path == PPO_TVF_RING || path == PPO_TVF_TSLAB ||
+                    path == PPO_TVF_CSLAB,
                 "ppo_tvf_targets: unknown path %d", path);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (steps == 0 || envs == 0 || n_req == 0) {
@@ -282,14 +286,21 @@ extern "C" int ppo_tvf_targets_ex(const float* rewards, int64_t reward_row_strid
     int rc = PPO_ERR_UNSUPPORTED;
     bool stats_fused = false;
     int taken = PPO_TVF_GENERIC;
-    // Several n-steps per horizon: gather-bound, transposed slab kernel.  One or two: HBM-bound, ring kernel.
-    if (path == PPO_TVF_TSLAB || (path == PPO_TVF_AUTO && tables->n_entries >= 3)) {
-        double* partials = nullptr;
-        unsigned int* ticket = nullptr;
-        if (stats && workspace && workspace_bytes >= ppo_tvf_workspace_bytes(0, 0)) {
-            ticket = static_cast<unsigned int*>(workspace);
-            partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
-        }
+    // Several n-steps per horizon: gather-bound, column slab kernel (128 / 256 steps) or transposed slab kernel.
+    // One or two: HBM-bound, ring kernel.
+    double* partials = nullptr;
+    unsigned int* ticket = nullptr;
+    if (stats && workspace && workspace_bytes >= ppo_tvf_workspace_bytes(0, 0)) {
+        ticket = static_cast<unsigned int*>(workspace);
+        partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
+    }
+    if (path == PPO_TVF_CSLAB || (path == PPO_TVF_AUTO && tables->n_entries >= 3)) {
+        rc = launch_tvf_cslab(p, stats, partials, ticket, kStatsBlocks, vweights, vout, vout_rs, s, &stats_fused);
+        if (path == PPO_TVF_CSLAB && rc != PPO_OK) return rc;
+        taken = PPO_TVF_CSLAB;
+        if (rc == PPO_OK) vout = nullptr;  // the value estimate was written by the same launch
+    }
+    if (path == PPO_TVF_TSLAB || (path == PPO_TVF_AUTO && tables->n_entries >= 3 && rc == PPO_ERR_UNSUPPORTED)) {
         rc = launch_tvf_tslab(p, stats, partials, ticket, kStatsBlocks, vweights, vout, vout_rs, s, &stats_fused);
         if (path == PPO_TVF_TSLAB && rc != PPO_OK) return rc;
         taken = PPO_TVF_TSLAB;

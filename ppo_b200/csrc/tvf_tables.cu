@@ -77,7 +77,8 @@ extern "C" int64_t ppo_tvf_tables_words(int64_t n_req, int64_t n_samples, int64_
     const int64_t e = std::min<int64_t>(n_samples, std::max<int64_t>(steps, 1));
     auto pad = [](int64_t w) { return (w + 3) / 4 * 4; };
     return 6 * pad(e * n_req) + 5 * pad((steps + 1) * n_req) + pad(steps + 1) + 3 * pad(n_req * pad(steps + 1)) +
-           pad(4 + 4 * n_req + 4 * e * n_req) + 4 * n_req * pad(steps + 1) + 16;
+           pad(4 + 4 * n_req + 4 * e * n_req) + 4 * n_req * pad(steps + 1) + 16 +
+           kCsHeaderWords + pad(n_req) + pad((n_req + 3) / 4) + 4 * (e * n_req + 1);
 }
 
 extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* required_horizons, int64_t n_req,
@@ -191,6 +192,9 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
     // (+ the folded tail tables once more, interleaved {idx, cwlo, cwhi, 0} per (horizon, tail length): one 16-byte
     // load per row instead of three 4-byte loads)
     offs[15] = off, off += pad(4 + 4 * static_cast<int64_t>(K) + 4 * ek) + 4 * static_cast<int64_t>(K) * tpitch;
+    // launch constants of the column slab kernel: header, K horizon words, K / 4 job words, the live entries + 1
+    const int64_t cs_off = off;
+    off += kCsHeaderWords + pad(K) + pad((K + 3) / 4) + 4 * (ek + 1);
     if (off > blob_words) {
         set_error("ppo_tvf_tables_build: blob of %lld words required, got %lld", (long long)off, (long long)blob_words);
         return PPO_ERR_WORKSPACE;
@@ -296,7 +300,79 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
             memcpy(t4 + 4 * i + 1, &wl, 4), memcpy(t4 + 4 * i + 2, &wh, 4);
         }
     }
+
+    {
+        // Column slab kernel (tvf_cslab.cu): per horizon the entries in ascending n with the aligned row group
+        // ("bin") they gather, their shift against the thread's own rows and a flag that says whether the group
+        // differs from the previous entry's; per job (four consecutive horizons) the column groups its gathers and
+        // its tail bootstraps touch, and per column group the number of jobs that touch it (the kernel refills a
+        // column group of the slab with the next env as soon as that many jobs have finished).
+        int32_t* hdr = blob + cs_off;
+        hdr[0] = kCsConstMagic, hdr[1] = -1, hdr[2] = static_cast<int32_t>(steps), hdr[3] = V;
+        const int jobs = (K + 3) / 4;
+        hdr[4] = jobs;
+        bool ok = K <= kCsMaxK && K % 4 == 0 && ek <= kCsMaxEntries && V % 32 == 0 && V <= 128 && steps % 128 == 0 &&
+                  steps <= 256;
+        uint32_t* hzw = reinterpret_cast<uint32_t*>(hdr + kCsHeaderWords);
+        uint32_t* jobw = hzw + pad(K);
+        CsEntry* ce = reinterpret_cast<CsEntry*>(jobw + pad(jobs));
+        std::vector<double> gp64(nmax + 1, 1.0);
+        for (int n = 1; n <= nmax; ++n) gp64[n] = pow(gamma, static_cast<double>(n));
+        auto group_of = [&](int col) { return col < V ? col / 32 : (col == V ? kCsSpecial : -1); };
+        int total = 0;
+        int arrivals[kCsGroups] = {0, 0, 0, 0, 0};
+        const int32_t* t_idx = blob + offs[12];
+        const int32_t* t_wlo = blob + offs[13];  // float bits of the folded tail weights
+        const int32_t* t_whi = blob + offs[14];
+        for (int k = 0; k < K && ok; ++k) {
+            int cnt = 0, maxn = 0, prev_bin = -1, prev_col = -1;
+            const int beg = total;
+            uint32_t mask = 0;
+            for (int e = 0; e < E && ok; ++e) {
+                const Entry& x = ent[k][e];
+                if (!(x.cnt > 0.f)) continue;
+                double a = x.l.wlo, bw = x.l.whi;
+                int col;
+                if (a == 0.0 && bw == 0.0) col = V, a = 1.0;
+                else if (x.l.hi == x.l.lo) col = x.l.lo, bw = 0.0;
+                else if (x.l.hi == x.l.lo + 1) col = x.l.lo;
+                else { ok = false; break; }
+                if (x.n > 1023) { ok = false; break; }
+                const double cg = static_cast<double>(x.cnt) * gp64[x.n] / static_cast<double>(C);
+                const int bin = (x.n - 1) / 4, shift = (x.n - 1) % 4;
+                CsEntry& t = ce[total++];
+                const uint32_t offb = static_cast<uint32_t>((static_cast<int64_t>(col) * steps + 4 * bin) * 4);
+                const bool fresh = bin != prev_bin || col != prev_col;
+                t.w = offb | (static_cast<uint32_t>(x.n) << 18) | (static_cast<uint32_t>(shift) << 1) | (fresh ? 1u : 0u);
+                t.wlo = static_cast<float>(a * cg), t.whi = static_cast<float>(bw * cg), t.pad = 0;
+                prev_bin = bin, prev_col = col;
+                ++cnt, maxn = std::max(maxn, x.n);
+                if (t.wlo != 0.f && group_of(col) >= 0) mask |= 1u << group_of(col);
+                if (t.whi != 0.f && group_of(col + 1) >= 0) mask |= 1u << group_of(col + 1);
+            }
+            if (cnt > 255) ok = false;
+            // value columns of the final row the tail bootstraps of this horizon read (rows with N - t < maxn)
+            for (int m = 1; m <= maxn && ok; ++m) {
+                const int64_t i = static_cast<int64_t>(k) * tpitch + m;
+                const int lo = t_idx[i] & 0xffff, hi = (t_idx[i] >> 16) & 0xffff;
+                if (t_wlo[i] != 0 && lo < V) mask |= 1u << (lo / 32);
+                if (t_whi[i] != 0 && hi < V) mask |= 1u << (hi / 32);
+            }
+            hzw[k] = static_cast<uint32_t>(beg) | (static_cast<uint32_t>(cnt) << 12) | (static_cast<uint32_t>(maxn) << 20) |
+                     (required_horizons[k] > 0 ? 1u << 30 : 0u);
+            jobw[k / 4] |= mask;
+        }
+        if (ok) {
+            for (int j = 0; j < jobs; ++j)
+                for (int g = 0; g < kCsGroups; ++g)
+                    if (jobw[j] >> g & 1u) ++arrivals[g];
+            for (int g = 0; g < kCsGroups; ++g) hdr[5 + g] = arrivals[g];
+            ce[total] = CsEntry{0u, 0.f, 0.f, 0u};  // the kernel fetches one entry ahead
+            hdr[1] = total;
+        }
+    }
     layout->tail_pitch = static_cast<int32_t>(tpitch);
+    layout->cslab_offset_words = cs_off;
     layout->gamma = gamma;
     layout->n_entries = E, layout->nmax = nmax;
     layout->total_words = off;

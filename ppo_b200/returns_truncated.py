@@ -15,7 +15,7 @@ from . import _device as dev
 from . import _lib
 from . import _tvf_tables
 
-PATH_AUTO, PATH_GENERIC, PATH_RING, PATH_TSLAB = 0, 1, 2, 3
+PATH_AUTO, PATH_GENERIC, PATH_RING, PATH_TSLAB, PATH_CSLAB = 0, 1, 2, 3, 4
 
 
 class _CTables(ctypes.Structure):
@@ -28,14 +28,14 @@ class _CTables(ctypes.Structure):
                 ("gpow", ctypes.c_void_p), ("inv_c", ctypes.c_float), ("tail_pitch", ctypes.c_int32),
                 ("tailT_idx", ctypes.c_void_p), ("tailT_cwlo", ctypes.c_void_p), ("tailT_cwhi", ctypes.c_void_p),
                 ("host_blob", ctypes.c_void_p), ("dev_blob", ctypes.c_void_p), ("gamma", ctypes.c_double),
-                ("tslab_offset_words", ctypes.c_int64)]
+                ("tslab_offset_words", ctypes.c_int64), ("cslab_offset_words", ctypes.c_int64)]
 
 
 class _CLayout(ctypes.Structure):
     """``ppo_tvf_table_layout`` of include/ppo_b200.h."""
     _fields_ = [("n_entries", ctypes.c_int32), ("nmax", ctypes.c_int32), ("total_words", ctypes.c_int64),
                 ("offset_words", ctypes.c_int64 * 16), ("inv_c", ctypes.c_float), ("tail_pitch", ctypes.c_int32),
-                ("gamma", ctypes.c_double)]
+                ("gamma", ctypes.c_double), ("cslab_offset_words", ctypes.c_int64)]
 
 
 class _CExtras(ctypes.Structure):
@@ -123,6 +123,7 @@ def _upload_tables(tabs, device):
         c.tail_pitch, c.gamma = tabs.layout.tail_pitch, tabs.layout.gamma
         c.host_blob, c.dev_blob = tabs.host.data_ptr(), base
         c.tslab_offset_words = int(tabs.layout.offset_words[15])
+        c.cslab_offset_words = int(tabs.layout.cslab_offset_words)
         return c, (blob, tabs.host)
     parts = [tabs.ent_n, tabs.ent_cnt, tabs.ent_idx, tabs.ent_wlo, tabs.ent_whi, tabs.ent_g,
              tabs.tail_idx, tabs.tail_wlo, tabs.tail_whi, tabs.tail_cwlo, tabs.tail_cwhi, tabs.gpow]
