@@ -214,7 +214,7 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
     if (warp >= kCsConsumers) {
         // helper warpgroups: 56 registers for the transform warps, 40 for scan / producer (the scan warp spills a few
         // values to local memory; it runs an env ahead and is latency tolerant)
-        if (warp >= kCsConsumers + kCsXform) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");  // second helper warpgroup
+        if (warp >= kCsConsumers + kCsXform) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");  // second helper warpgroup
         if (warp > kCsConsumers + kCsXform + 1) {
             // idle warps of the second helper warpgroup
         } else if (warp == kCsConsumers + kCsXform + 1) {
@@ -226,7 +226,7 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
                     const int env = static_cast<int>(env0 + e);
                     for (int g = 0; g < NG; ++g)
                         for (int c = 0; c < NCH; ++c) {
-                            mbar_wait_sleep(&sempty[slot], par ^ 1, poll_ns);
+                            mbar_wait_sleep(&sempty[slot], par ^ 1, 2 * poll_ns);
                             if (q.dbg & 2) {
                                 mbar_arrive(&sfull[slot]);
                             } else {
@@ -291,7 +291,7 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
             }
         } else {
             // ------------------------------------------------------------------ transform warps
-            asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
             // lane <-> value row of the 128-row chunk (32 rows per warp): 16-byte reads of the swizzled chunk, 4-byte
             // writes along the slab columns (32 consecutive rows: conflict free), and the value estimate for the GAE
             // stage (rl/tvf.py:303-360) as a thread-local dot product over the columns that pass through anyway
@@ -325,29 +325,25 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
                     if (e + 1 < nenv) load_row0(e + 1);
                 }
                 if (tw == 0 && lane == 0 && e < 4) cs_stamp(q.dbg, 64 * e + 0);
-                if (lane == 0) mbar_wait(&rfull[par], (static_cast<uint32_t>(e) >> 1) & 1u);
-                __syncwarp();
+                mbar_wait(&rfull[par], (static_cast<uint32_t>(e) >> 1) & 1u);
                 if (tw == 0 && lane == 0 && e < 4) cs_stamp(q.dbg, 64 * e + 1);
                 const uint32_t rt = rt_a + par * RT_BYTES;
                 float Rr[NCH], dot[NCH];
 #pragma unroll
                 for (int c = 0; c < NCH; ++c)
                     Rr[c] = cs_lds(rt + static_cast<uint32_t>(c * kCsChunkRows + rloc + 1) * 4u), dot[c] = 0.f;
-                if (e > 0 && q.arrivals[kCsSpecial] > 0 && lane == 0) mbar_wait(&gfree[kCsSpecial], (e - 1) & 1u);
-                __syncwarp();
+                if (e > 0 && q.arrivals[kCsSpecial] > 0) mbar_wait_sleep(&gfree[kCsSpecial], (e - 1) & 1u, poll_ns);
 #pragma unroll
                 for (int c = 0; c < NCH; ++c)  // the -R column (index V); column V + 1 stays zero
                     cs_sts(slab_a + static_cast<uint32_t>(V * N + c * kCsChunkRows + rloc) * 4u, -Rr[c]);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&gfull[kCsSpecial]);
                 for (int g = 0; g < NG; ++g) {
-                    if (e > 0 && q.arrivals[g] > 0 && (lane == 0 || (q.dbg & 2048))) mbar_wait(&gfree[g], (e - 1) & 1u);
-                    __syncwarp();
+                    if (e > 0 && q.arrivals[g] > 0) mbar_wait_sleep(&gfree[g], (e - 1) & 1u, poll_ns);
                     if (tw == 0 && lane == 0 && e < 4) cs_stamp(q.dbg, 64 * e + 2 + 2 * g);
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) {
-                        if (lane == 0 || (q.dbg & 2048)) mbar_wait(&sfull[slot], spar);
-                        __syncwarp();
+                        mbar_wait(&sfull[slot], spar);
                         const int i = c * kCsChunkRows + rloc;  // slab index: value row r = i + 1
                         const uint32_t src = stage_a + static_cast<uint32_t>(slot) * kCsChunkBytes + static_cast<uint32_t>(rloc) * 128u;
                         const uint32_t dst = slab_a + static_cast<uint32_t>(g * 32 * N + i) * 4u;
@@ -414,13 +410,16 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
         // one team job per env only one team works.
         const int total_jobs = team < NH ? nenv * NH : 0;
         for (int it = 0; total_jobs > 0; ++it) {
-            // one lane of the team takes the job and waits for its inputs (the R / lim tables of the env and the
-            // column groups any of the eight quads reads); the team barrier hands both to the other warps
-            if (w8 == 0 && lane == 0) {
-                const int jj = atomicAdd(jobctr, 1);
-                if (jj < total_jobs && !(q.dbg & 1024)) {
+            // The first warp of the team takes the job and waits for its inputs (the R / lim tables of the env and the
+            // column groups any of the eight quads reads); the team barrier hands both to the other warps.  (All 32
+            // lanes wait together: a single waiting lane is woken late by the mbarrier unit.)
+            if (w8 == 0) {
+                int jj = 0;
+                if (lane == 0) jj = atomicAdd(jobctr, 1);
+                jj = __shfl_sync(0xffffffffu, jj, 0);
+                if (jj < total_jobs) {
                     const int ee = jj / NH, hh = jj - ee * NH;
-                    if (ee < 4 && hh < 4) cs_stamp(q.dbg, 64 * ee + 12 + 12 * hh + 0);
+                    if (lane == 0 && ee < 4 && hh < 4) cs_stamp(q.dbg, 64 * ee + 12 + 12 * hh + 0);
                     uint32_t um = 0;
 #pragma unroll
                     for (int w = 0; w < 8; ++w) um |= q.jobmask[hh * 8 + w];
@@ -429,7 +428,7 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
                     for (int g = 0; g < kCsGroups; ++g)
                         if (um >> g & 1u) mbar_wait(&gfull[g], static_cast<uint32_t>(ee & 1));
                 }
-                slot[it & 1] = jj;
+                if (lane == 0) slot[it & 1] = jj;
             }
             asm volatile("bar.sync %0, 256;" ::"r"(1 + team) : "memory");
             const int j = slot[it & 1];
@@ -438,12 +437,6 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
             const bool stamp = w8 == 0 && lane == 0 && e < 4 && hg < 4;
             const uint32_t par = static_cast<uint32_t>(e & 1);
             const uint32_t mask = q.jobmask[qd];
-            if (q.dbg & 1024) {
-                mbar_wait(&rfull[par], (static_cast<uint32_t>(e) >> 1) & 1u);
-#pragma unroll
-                for (int g = 0; g < kCsGroups; ++g)
-                    if (mask >> g & 1u) mbar_wait(&gfull[g], par);
-            }
             if (stamp) cs_stamp(q.dbg, 64 * e + 12 + 12 * hg + 1);
             const uint32_t rt = rt_a + par * RT_BYTES, lt = lim_a + par * LIM_BYTES;
             // row limits of rows 4 i - 3 .. 4 i + 3 per group (the first three are the previous lane's last rows; the
@@ -479,10 +472,6 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
                 for (int g = 0; g < G; ++g)
 #pragma unroll
                     for (int i = 0; i < 7; ++i) acc[g][i] = 0.f;
-                // the folded tail records of this horizon are needed after the entry loop: 16 bytes per row that may run
-                // off the rollout, fetched into L1 now (one 128-byte line per lane) so that their L2 latency is hidden
-                if (!(q.dbg & (16 | 512)) && lane * 8 <= static_cast<int>((ha >> 20) & 0x3ffu))
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(q.tail4 + static_cast<int64_t>(k) * q.tail_pitch + lane * 8));
                 int i = static_cast<int>(ha & 0xfffu);
                 const int end = (q.dbg & 8) ? i : i + static_cast<int>((ha >> 12) & 0xffu);
                 if (i < end) {
