@@ -41,21 +41,29 @@ struct __align__(16) TsHorizon {
 // so an entry (horizon, n-step) is described by the aligned row group it reads ("bin" m = (n - 1) / 4: slab rows
 // 4 (i + m) .. 4 (i + m) + 3 for the thread that owns rows 4 i .. 4 i + 3) and by how far the group is shifted against
 // the thread's own rows (shift s = (n - 1) % 4: the values belong to rows 4 i - s .. 4 i - s + 3).  Entries of one
-// horizon are sorted by n, so entries that share a bin (and a column) are neighbours and the kernel loads the group
-// once for all of them.
+// horizon are sorted by shift (then n): the kernel runs one loop per shift, each with its accumulators fixed at
+// compile time.
 constexpr int kCsMaxK = 128;
 constexpr int kCsMaxEntries = 1024;
 constexpr int kCsGroups = 5;                // column groups of 32 value columns (at most four) + the -R column
 constexpr int kCsSpecial = kCsGroups - 1;   // group index of the -R column
-constexpr int kCsConstMagic = 0x43534c32;   // header: magic, n_ent (-1 = none), steps, V, jobs, arrivals[5], reserved
+constexpr int kCsConstMagic = 0x43534c33;   // header: magic, n_ent (-1 = none), steps, V, jobs, arrivals[5], reserved
 constexpr int kCsHeaderWords = 16;
 constexpr uint32_t kCsOffMask = 0x3fff0u;   // byte offset (multiple of 16) of the first gathered group in the slab
 struct __align__(16) CsEntry {
-    uint32_t w;      // off | n << 18 | shift << 1 | (1 = load a new row group)
+    uint32_t w;      // off | n << 18
     float wlo, whi;  // multiplicity * gamma^n * lerp weights / samples per horizon
     uint32_t pad;
 };
-// horizon word: first entry | entries << 12 | largest n-step << 20 | live << 30
+struct __align__(16) CsHorizon {
+    uint32_t w0;   // first entry | largest n-step << 11 | tail mode << 21 | live << 23
+    uint32_t w1;   // entries with shift 0 | shift 1 << 8 | shift 2 << 16 | shift 3 << 24
+    uint32_t w2;   // tail: first nibble of the horizon in the multiplicity table
+    int32_t w3;    // tail mode 1: h_k - N (table index of row t is w3 + t); mode 2: value column s | (h_k - vh[s-1]) << 8
+    float w4;      // tail mode 2: 1 / (vh[s] - vh[s-1])
+    uint32_t w5, w6, w7;
+};
+constexpr int kCsTailNone = 0, kCsTailTable = 1, kCsTailLinear = 2, kCsTailGeneric = 3;
 
 __device__ __forceinline__ bool done_at(const void* dones, int kind, int64_t idx) {
     if (kind == PPO_DONE_U8) return static_cast<const unsigned char*>(dones)[idx] != 0;

@@ -53,7 +53,9 @@ struct CsParams {
     int dbg;  // development switches (PPO_TVF_DEBUG): 1 no stores, 2 no TMA loads, 8 no entry loop, 16 no tail term
     int arrivals[kCsGroups];
     int64_t env_base, env_rem;
-    uint32_t off_stage, off_tile, off_rtab, off_lim, off_fr, off_misc, off_bar, smem_total;
+    uint32_t off_stage, off_tile, off_rtab, off_lim, off_fr, off_ftab, off_nib, off_gpc, off_misc, off_bar, smem_total;
+    int xmax, nib_words;      // table horizons 0..xmax of the final value curve; words of the multiplicity table
+    const uint32_t* nib_dev;  // multiplicity table (device copy inside the table blob)
     float* value_out;  // [N + 1, A] value estimate sum_j vw[j] * V[r, a, j] (want_value), row stride vo_rs
     int64_t vo_rs;
     double* partials;  // [grid][8] per-CTA statistics of the longest horizon (want_stats)
@@ -61,7 +63,8 @@ struct CsParams {
     double* stats;
     const uint4* tail4;  // [K][tail_pitch] folded tail records {idx lo | hi << 16, cwlo, cwhi, 0}
     float vw[kCsMaxK];
-    uint32_t hz[kCsMaxK];
+    int vh[kCsMaxK];  // value horizons
+    CsHorizon hz[kCsMaxK];
     uint32_t jobmask[kCsMaxK / 4];
     CsEntry ent[kCsMaxEntries + 1];
 };
@@ -122,6 +125,12 @@ __device__ __forceinline__ void cs_fma_if(float& acc, float lo, float hi, float 
         : "f"(lo), "f"(hi), "f"(wlo), "f"(whi), "r"(w), "r"(key));
 }
 
+__device__ __forceinline__ uint32_t cs_lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 // One entry on the loaded row groups: value q of a group belongs to row 4 i - S + q, accumulator 3 - S + q
 // (accumulators 0..2: rows 4 i - 3 .. 4 i - 1 of the previous lane, 3..6: the thread's own rows).
 template <int S, int G>
@@ -134,6 +143,28 @@ __device__ __forceinline__ void cs_tap(const float4 (&lo)[G], const float4 (&hi)
         cs_fma_if(acc[g][3 - S + 2], lo[g].z, hi[g].z, wlo, whi, w, key[g][3 - S + 2]);
         cs_fma_if(acc[g][3 - S + 3], lo[g].w, hi[g].w, wlo, whi, w, key[g][3 - S + 3]);
     }
+}
+
+// The entries of one horizon with shift S: constants from the parameter bank one entry ahead (their latency hides behind
+// the gathers), two 16-byte gathers per row group, accumulators fixed at compile time.
+template <int S, int G>
+__device__ __forceinline__ int cs_run(const CsParams& q, int i, int cnt, uint32_t base, float (&acc)[G][7],
+                                      const uint32_t (&key)[G][7]) {
+    constexpr int COLB = 512 * G;
+    if (cnt > 0) {
+        const int end = i + cnt;
+        CsEntry cur = q.ent[i];
+        for (; i < end; ++i) {
+            const CsEntry nxt = q.ent[i + 1];
+            const uint32_t a = base + (cur.w & kCsOffMask);
+            float4 lo[G], hi[G];
+            lo[0] = cs_lds128<0>(a), hi[0] = cs_lds128<COLB>(a);
+            if (G > 1) lo[G - 1] = cs_lds128<512>(a), hi[G - 1] = cs_lds128<COLB + 512>(a);
+            cs_tap<S, G>(lo, hi, cur.wlo, cur.whi, cur.w, acc, key);
+            cur = nxt;
+        }
+    }
+    return i;
 }
 
 template <int G>
@@ -163,6 +194,9 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
     const uint32_t rt_a = smem_u32(smem + q.off_rtab);
     const uint32_t lim_a = smem_u32(smem + q.off_lim);
     const uint32_t fr_a = smem_u32(smem + q.off_fr);
+    const uint32_t ftab_a = smem_u32(smem + q.off_ftab);
+    const uint32_t nib_a = smem_u32(smem + q.off_nib);
+    const uint32_t gpc_a = smem_u32(smem + q.off_gpc);
     constexpr uint32_t RT_BYTES = (N + 16) * 4, LIM_BYTES = (N + 16) * 2;
     double* st_sm = reinterpret_cast<double*>(smem + q.off_misc);         // [8] statistics of the longest horizon
     int* jobctr = reinterpret_cast<int*>(smem + q.off_misc + 64);
@@ -207,6 +241,13 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
     for (uint32_t i = threadIdx.x * 16u; i < q.off_bar; i += blockDim.x * 16u)
         *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
     __syncthreads();
+    // the multiplicity table of the tail bootstraps and gamma^m / C for the last 128 rows (m = 128 - index)
+    for (int i = threadIdx.x; i < q.nib_words; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(smem + q.off_nib)[i] = __ldg(q.nib_dev + i);
+    if (threadIdx.x < 128) {
+        const int m = 128 - static_cast<int>(threadIdx.x);
+        reinterpret_cast<float*>(smem + q.off_gpc)[threadIdx.x] = m <= p.tab.nmax ? __ldg(p.tab.gpow + m) * p.tab.inv_c : 0.f;
+    }
     if (threadIdx.x == 0) st_sm[3] = INFINITY, st_sm[4] = -INFINITY;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
@@ -384,6 +425,22 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
                         if (lane == 0) mbar_arrive(&sempty[slot]);
                         if (++slot == q.nstage) slot = 0, spar ^= 1;
                     }
+                    if (q.xmax > 0 && q.vh[g * 32 > 0 ? g * 32 - 1 : 0] < q.xmax) {
+                        // the final value curve on the integer horizons of this column group's slots: x in
+                        // (vh[s-1], vh[s]] is a line between the final-row values s - 1 and s (rl/returns_truncated.py:
+                        // 142-174); the consumers' tail bootstraps read it instead of gathering per target
+                        asm volatile("bar.sync 4, %0;" ::"n"(kCsXform * 32) : "memory");  // the final row of the group is in `fr`
+                        for (int sl = g * 32 + tw; sl < g * 32 + 32 && sl < V; sl += kCsXform) {
+                            const int xl = sl > 0 ? q.vh[sl - 1] : 0, xr = min(q.vh[sl], q.xmax);
+                            if (xl >= q.xmax) break;
+                            const float fb = cs_lds(fr_a + static_cast<uint32_t>(sl) * 4u);
+                            const float fa = sl > 0 ? cs_lds(fr_a + static_cast<uint32_t>(sl - 1) * 4u) : fb;
+                            const float slope = (fb - fa) / static_cast<float>(q.vh[sl] - xl);
+                            for (int x = xl + 1 + lane; x <= xr; x += 32)
+                                cs_sts(ftab_a + static_cast<uint32_t>(x) * 4u, fmaf(static_cast<float>(x - xl), slope, fa));
+                        }
+                        __syncwarp();
+                    }
                     if (lane == 0) mbar_arrive(&gfull[g]);
                     if (tw == 0 && lane == 0 && e < 4) cs_stamp(q.dbg, 64 * e + 3 + 2 * g);
                 }
@@ -465,36 +522,19 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int k = qd * 4 + u;
-                const uint32_t ha = q.hz[k];
-                live |= ((ha >> 30) & 1u) << u;
+                const CsHorizon hz = q.hz[k];
+                live |= ((hz.w0 >> 23) & 1u) << u;
                 float acc[G][7];
 #pragma unroll
                 for (int g = 0; g < G; ++g)
 #pragma unroll
                     for (int i = 0; i < 7; ++i) acc[g][i] = 0.f;
-                int i = static_cast<int>(ha & 0xfffu);
-                const int end = (q.dbg & 8) ? i : i + static_cast<int>((ha >> 12) & 0xffu);
-                if (i < end) {
-                    float4 lo[G], hi[G];
-#pragma unroll
-                    for (int g = 0; g < G; ++g) lo[g] = make_float4(0.f, 0.f, 0.f, 0.f), hi[g] = lo[g];
-                    CsEntry cur = q.ent[i];
-                    for (; i < end; ++i) {
-                        const CsEntry nxt = q.ent[i + 1];  // one entry ahead: the constant-bank latency hides here
-                        if (cur.w & 1u) {
-                            const uint32_t a = base + (cur.w & kCsOffMask);
-                            lo[0] = cs_lds128<0>(a), hi[0] = cs_lds128<COLB>(a);
-                            if (G > 1) lo[G - 1] = cs_lds128<512>(a), hi[G - 1] = cs_lds128<COLB + 512>(a);
-                        }
-                        const float wlo = cur.wlo, whi = cur.whi;
-                        switch ((cur.w >> 1) & 3u) {
-                            case 0: cs_tap<0, G>(lo, hi, wlo, whi, cur.w, acc, key); break;
-                            case 1: cs_tap<1, G>(lo, hi, wlo, whi, cur.w, acc, key); break;
-                            case 2: cs_tap<2, G>(lo, hi, wlo, whi, cur.w, acc, key); break;
-                            default: cs_tap<3, G>(lo, hi, wlo, whi, cur.w, acc, key); break;
-                        }
-                        cur = nxt;
-                    }
+                if (!(q.dbg & 8)) {
+                    int i = static_cast<int>(hz.w0 & 0x7ffu);
+                    i = cs_run<0, G>(q, i, static_cast<int>(hz.w1 & 0xffu), base, acc, key);
+                    i = cs_run<1, G>(q, i, static_cast<int>((hz.w1 >> 8) & 0xffu), base, acc, key);
+                    i = cs_run<2, G>(q, i, static_cast<int>((hz.w1 >> 16) & 0xffu), base, acc, key);
+                    i = cs_run<3, G>(q, i, static_cast<int>(hz.w1 >> 24), base, acc, key);
                 }
                 // carries: accumulators 0 .. 2 belong to the last three rows of the previous lane (lane 0 of a group
                 // hands over to lane 31 of the group before; lane 0 of the first group drops them)
@@ -506,10 +546,12 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
 #pragma unroll
                     for (int g = 0; g < G; ++g) acc[g][4 + c] += lane == 31 ? (g + 1 < G ? r[g + 1 < G ? g + 1 : 0] : 0.f) : r[g];
                 }
-                // rows whose n-step windows run off the rollout: one folded bootstrap from the final row, host
-                // weights from the horizon-major tables
-                const int maxn = static_cast<int>((ha >> 20) & 0x3ffu);
-                if (!(q.dbg & 16)) {
+                // rows whose n-step windows run off the rollout bootstrap from the final row:
+                //   tail[t, k] = cnt_k(m) / C * gamma^m * F(h_k - m),  m = N - t,  for rows alive until the rollout ends
+                const int maxn = static_cast<int>((hz.w0 >> 11) & 0x3ffu);
+                const int mode = static_cast<int>((hz.w0 >> 21) & 3u);
+                if (!(q.dbg & 16) && mode == kCsTailGeneric) {
+                    // folded records from the horizon-major tables in global memory (log interpolation, long windows)
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
                         if (N - (128 * g + 127) <= maxn && __any_sync(0xffffffffu, (endm >> (4 * g)) & 0xfu)) {
@@ -524,6 +566,37 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
                                     acc[g][3 + c] += fmaf(v1, __uint_as_float(rec.z), v0 * __uint_as_float(rec.y));
                                 }
                             }
+                        }
+                    }
+                } else if (!(q.dbg & 16) && mode != kCsTailNone) {
+                    // shared-memory form (n-steps up to 128: only the last row group has such rows): multiplicities from
+                    // the 4-bit table, gamma^m / C per row, F from the per-env table of the final value curve (mode 1)
+                    // or as a line in m when every h_k - m lies in one interpolation slot (mode 2)
+                    const uint32_t em = (endm >> (4 * (G - 1))) & 0xfu;
+                    const int m0 = 128 - 4 * lane;  // row c of the group has m = m0 - c
+                    if (__any_sync(0xffffffffu, em != 0u && m0 - 3 <= maxn)) {
+                        const uint32_t il = hz.w2 + static_cast<uint32_t>(m0 - 4);  // nibble of m = m0 - 3 (row c = 3)
+                        const uint32_t wa = cs_lds_u32(nib_a + (il >> 3) * 4u), wb = cs_lds_u32(nib_a + (il >> 3) * 4u + 4u);
+                        const uint32_t bits = __funnelshift_r(wa, wb, (il & 7u) * 4u);
+                        const float4 gp = cs_lds128<0>(gpc_a + static_cast<uint32_t>(lane) * 16u);
+                        float F[4];
+                        if (mode == kCsTailLinear) {
+                            const uint32_t sc = static_cast<uint32_t>(hz.w3) & 0xffu;
+                            const float c0 = static_cast<float>(hz.w3 >> 8);
+                            const float fa = cs_lds(fr_a + (sc - 1u) * 4u), fb = cs_lds(fr_a + sc * 4u);
+                            const float slope = (fb - fa) * hz.w4;
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) F[c] = fmaf(c0 - static_cast<float>(m0 - c), slope, fa);
+                        } else {
+                            const int x0 = hz.w3 + (N - 128) + 4 * lane;  // table horizon h_k - m of row c = 0
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) F[c] = cs_lds(ftab_a + static_cast<uint32_t>(max(x0 + c, 0)) * 4u);
+                        }
+                        const float gpv[4] = {gp.x, gp.y, gp.z, gp.w};
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float cntf = static_cast<float>((bits >> (4 * (3 - c))) & 15u);
+                            if ((em >> c & 1u) && m0 - c <= maxn) acc[G - 1][3 + c] = fmaf(cntf * gpv[c], F[c], acc[G - 1][3 + c]);
                         }
                     }
                 }
@@ -663,7 +736,7 @@ int launch_tvf_cslab(const TvfParams& p, double* stats, double* partials, unsign
     if (N != 128 && N != 256) return unsupported("steps must be 128 or 256");
     if (V % 32 != 0 || V > 128) return unsupported("value horizons must be 32, 64, 96 or 128");
     if (K > kCsMaxK || K % 32 != 0) return unsupported("required horizons must be a multiple of 32, at most 128");
-    if (!p.tab.host_blob || !p.tab.dev_blob) return unsupported("tables carry no host mirror (ppo_tvf_tables_build)");
+    if (!p.tab.host_blob || !p.tab.dev_blob || !p.tab.gpow) return unsupported("tables carry no host mirror (ppo_tvf_tables_build)");
     if (p.tab.cslab_offset_words <= 0 || p.tab.tslab_offset_words <= 0)
         return unsupported("tables carry no launch constants for this kernel");
     if (!(p.tab.gamma > 0.0)) return unsupported("tables carry no gamma");
@@ -687,13 +760,19 @@ int launch_tvf_cslab(const TvfParams& p, double* stats, double* partials, unsign
         q.dbg = d ? atoi(d) : 0;
     }
     auto pad4 = [](int64_t w) { return (w + 3) / 4 * 4; };
-    const uint32_t* hzw = reinterpret_cast<const uint32_t*>(hdr + kCsHeaderWords);
-    const uint32_t* jobw = hzw + pad4(K);
-    const CsEntry* ce = reinterpret_cast<const CsEntry*>(jobw + pad4(K / 4));
+    const CsHorizon* hzw = reinterpret_cast<const CsHorizon*>(hdr + kCsHeaderWords);
+    const uint32_t* jobw = reinterpret_cast<const uint32_t*>(hzw + K);
+    const int32_t* vhw = reinterpret_cast<const int32_t*>(jobw + pad4(K / 4));
+    const CsEntry* ce = reinterpret_cast<const CsEntry*>(vhw + 128);
+    const int64_t ek = static_cast<int64_t>(p.tab.n_entries) * K;
     for (int g = 0; g < kCsGroups; ++g) q.arrivals[g] = hdr[5 + g];
-    memcpy(q.hz, hzw, sizeof(uint32_t) * K);
+    memcpy(q.hz, hzw, sizeof(CsHorizon) * K);
     memcpy(q.jobmask, jobw, sizeof(uint32_t) * (K / 4));
+    memcpy(q.vh, vhw, sizeof(int32_t) * 128);
     memcpy(q.ent, ce, sizeof(CsEntry) * (q.n_ent + 1));
+    q.xmax = hdr[10], q.nib_words = hdr[11];
+    q.nib_dev = reinterpret_cast<const uint32_t*>(static_cast<const int32_t*>(p.tab.dev_blob) + p.tab.cslab_offset_words +
+                                                 (reinterpret_cast<const int32_t*>(ce + ek + 1) - hdr));
     // the interleaved tail records of the transposed slab section (device copy)
     {
         const int64_t E = p.tab.n_entries;
@@ -706,8 +785,11 @@ int launch_tvf_cslab(const TvfParams& p, double* stats, double* partials, unsign
     PPO_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     // slab: V value columns, the -R column, a zero column; gathers may run past the last column by the largest bin
     const uint32_t slab_bytes = cs_align((static_cast<uint32_t>(V + 2) * N + nmax + 16) * 4u, 1024);
+    const uint32_t ftab_bytes = cs_align(static_cast<uint32_t>(q.xmax + 8) * 4u, 128);
+    const uint32_t nib_bytes = cs_align(static_cast<uint32_t>(q.nib_words + 24) * 4u, 128);
     const uint32_t rest = 2u * 16384u + cs_align(2u * (N + 16) * 4u, 128) + cs_align(2u * (N + 16) * 2u, 128) +
-                          cs_align(static_cast<uint32_t>(V) * 4u, 128) + 128u + (2 * kCsMaxStages + 2 * kCsGroups + 4) * 8u;
+                          cs_align(static_cast<uint32_t>(V) * 4u, 128) + ftab_bytes + nib_bytes + 512u + 128u +
+                          (2 * kCsMaxStages + 2 * kCsGroups + 4) * 8u;
     int nstage = 0;  // staging ring: as deep as shared memory allows (the TMA loads are latency bound)
     while (nstage < kCsMaxStages && slab_bytes + rest + static_cast<uint32_t>(nstage + 1) * kCsChunkBytes <= static_cast<uint32_t>(max_smem))
         ++nstage;
@@ -719,7 +801,10 @@ int launch_tvf_cslab(const TvfParams& p, double* stats, double* partials, unsign
     q.off_rtab = q.off_tile + 2u * 16384u;
     q.off_lim = q.off_rtab + cs_align(2u * (N + 16) * 4u, 128);
     q.off_fr = q.off_lim + cs_align(2u * (N + 16) * 2u, 128);
-    q.off_misc = q.off_fr + cs_align(static_cast<uint32_t>(V) * 4u, 128);
+    q.off_ftab = q.off_fr + cs_align(static_cast<uint32_t>(V) * 4u, 128);
+    q.off_nib = q.off_ftab + ftab_bytes;
+    q.off_gpc = q.off_nib + nib_bytes;
+    q.off_misc = q.off_gpc + 512u;
     q.off_bar = q.off_misc + 128;
     q.smem_total = q.off_bar + (2 * kCsMaxStages + 2 * kCsGroups + 4) * 8u;
     if (q.smem_total > static_cast<uint32_t>(max_smem)) return unsupported("the env slab does not fit in shared memory");

@@ -11,6 +11,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <limits.h>
+
 #include <algorithm>
 #include <mutex>
 #include <vector>
@@ -78,7 +80,7 @@ extern "C" int64_t ppo_tvf_tables_words(int64_t n_req, int64_t n_samples, int64_
     auto pad = [](int64_t w) { return (w + 3) / 4 * 4; };
     return 6 * pad(e * n_req) + 5 * pad((steps + 1) * n_req) + pad(steps + 1) + 3 * pad(n_req * pad(steps + 1)) +
            pad(4 + 4 * n_req + 4 * e * n_req) + 4 * n_req * pad(steps + 1) + 16 +
-           kCsHeaderWords + pad(n_req) + pad((n_req + 3) / 4) + 4 * (e * n_req + 1);
+           kCsHeaderWords + 8 * n_req + pad((n_req + 3) / 4) + 128 + 4 * (e * n_req + 1) + pad(n_req * (steps + 8) / 8 + 8) + 16;
 }
 
 extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* required_horizons, int64_t n_req,
@@ -194,7 +196,8 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
     offs[15] = off, off += pad(4 + 4 * static_cast<int64_t>(K) + 4 * ek) + 4 * static_cast<int64_t>(K) * tpitch;
     // launch constants of the column slab kernel: header, K horizon words, K / 4 job words, the live entries + 1
     const int64_t cs_off = off;
-    off += kCsHeaderWords + pad(K) + pad((K + 3) / 4) + 4 * (ek + 1);
+    off += kCsHeaderWords + 8 * static_cast<int64_t>(K) + pad((K + 3) / 4) + 128 + 4 * (ek + 1) +
+           pad(static_cast<int64_t>(K) * (steps + 8) / 8 + 8);
     if (off > blob_words) {
         set_error("ppo_tvf_tables_build: blob of %lld words required, got %lld", (long long)off, (long long)blob_words);
         return PPO_ERR_WORKSPACE;
@@ -313,9 +316,13 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
         hdr[4] = jobs;
         bool ok = K <= kCsMaxK && K % 4 == 0 && ek <= kCsMaxEntries && V % 32 == 0 && V <= 128 && steps % 128 == 0 &&
                   steps <= 256;
-        uint32_t* hzw = reinterpret_cast<uint32_t*>(hdr + kCsHeaderWords);
-        uint32_t* jobw = hzw + pad(K);
-        CsEntry* ce = reinterpret_cast<CsEntry*>(jobw + pad(jobs));
+        CsHorizon* hzw = reinterpret_cast<CsHorizon*>(hdr + kCsHeaderWords);
+        uint32_t* jobw = reinterpret_cast<uint32_t*>(hzw + K);
+        int32_t* vhw = reinterpret_cast<int32_t*>(jobw + pad(jobs));  // [128] value horizons (the kernel interpolates with them)
+        CsEntry* ce = reinterpret_cast<CsEntry*>(vhw + 128);
+        uint32_t* nib = reinterpret_cast<uint32_t*>(ce + ek + 1);  // multiplicities of the n-steps beyond m, 4 bits each
+        for (int j = 0; j < V && j < 128; ++j)
+            vhw[j] = static_cast<int32_t>(std::min<int64_t>(std::max<int64_t>(value_horizons[j], 0), INT32_MAX));
         std::vector<double> gp64(nmax + 1, 1.0);
         for (int n = 1; n <= nmax; ++n) gp64[n] = pow(gamma, static_cast<double>(n));
         auto group_of = [&](int col) { return col < V ? col / 32 : (col == V ? kCsSpecial : -1); };
@@ -324,33 +331,43 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
         const int32_t* t_idx = blob + offs[12];
         const int32_t* t_wlo = blob + offs[13];  // float bits of the folded tail weights
         const int32_t* t_whi = blob + offs[14];
+        // Tail bootstraps (rows whose n-step window runs off the rollout) without table reads from global memory:
+        //   tail[t, k] = cnt_k(m) / C * gamma^m * F(h_k - m),  m = N - t,  F = the final value curve interpolated
+        // cnt_k(m) (samples of the horizon with n > m) comes from a 4-bit table; F either from a table over integer
+        // horizons 1..xmax that the kernel interpolates once per env (mode 1), or, when every h_k - m of the horizon
+        // lies in one interpolation slot, as a line in m (mode 2).  Anything else keeps the record tables (mode 3).
+        const bool plain_axis = !use_log_interpolation && C <= 15 && nmax <= 128 && V <= 128;
+        bool strictly_up = true;
+        for (int j = 1; j < V; ++j) strictly_up = strictly_up && value_horizons[j] > value_horizons[j - 1];
+        const int64_t xcap = 1535;  // table horizons the kernel has shared memory for
+        int64_t xmax = 0, nibbles = 0;
         for (int k = 0; k < K && ok; ++k) {
-            int cnt = 0, maxn = 0, prev_bin = -1, prev_col = -1;
+            int cnt[4] = {0, 0, 0, 0}, maxn = 0;
             const int beg = total;
             uint32_t mask = 0;
-            for (int e = 0; e < E && ok; ++e) {
-                const Entry& x = ent[k][e];
-                if (!(x.cnt > 0.f)) continue;
-                double a = x.l.wlo, bw = x.l.whi;
-                int col;
-                if (a == 0.0 && bw == 0.0) col = V, a = 1.0;
-                else if (x.l.hi == x.l.lo) col = x.l.lo, bw = 0.0;
-                else if (x.l.hi == x.l.lo + 1) col = x.l.lo;
-                else { ok = false; break; }
-                if (x.n > 1023) { ok = false; break; }
-                const double cg = static_cast<double>(x.cnt) * gp64[x.n] / static_cast<double>(C);
-                const int bin = (x.n - 1) / 4, shift = (x.n - 1) % 4;
-                CsEntry& t = ce[total++];
-                const uint32_t offb = static_cast<uint32_t>((static_cast<int64_t>(col) * steps + 4 * bin) * 4);
-                const bool fresh = bin != prev_bin || col != prev_col;
-                t.w = offb | (static_cast<uint32_t>(x.n) << 18) | (static_cast<uint32_t>(shift) << 1) | (fresh ? 1u : 0u);
-                t.wlo = static_cast<float>(a * cg), t.whi = static_cast<float>(bw * cg), t.pad = 0;
-                prev_bin = bin, prev_col = col;
-                ++cnt, maxn = std::max(maxn, x.n);
-                if (t.wlo != 0.f && group_of(col) >= 0) mask |= 1u << group_of(col);
-                if (t.whi != 0.f && group_of(col + 1) >= 0) mask |= 1u << group_of(col + 1);
-            }
-            if (cnt > 255) ok = false;
+            for (int shift = 0; shift < 4 && ok; ++shift)
+                for (int e = 0; e < E && ok; ++e) {
+                    const Entry& x = ent[k][e];
+                    if (!(x.cnt > 0.f) || (x.n - 1) % 4 != shift) continue;
+                    double a = x.l.wlo, bw = x.l.whi;
+                    int col;
+                    if (a == 0.0 && bw == 0.0) col = V, a = 1.0;
+                    else if (x.l.hi == x.l.lo) col = x.l.lo, bw = 0.0;
+                    else if (x.l.hi == x.l.lo + 1) col = x.l.lo;
+                    else { ok = false; break; }
+                    if (x.n > 1023) { ok = false; break; }
+                    const double cg = static_cast<double>(x.cnt) * gp64[x.n] / static_cast<double>(C);
+                    const int bin = (x.n - 1) / 4;
+                    CsEntry& t = ce[total++];
+                    const uint32_t offb = static_cast<uint32_t>((static_cast<int64_t>(col) * steps + 4 * bin) * 4);
+                    t.w = offb | (static_cast<uint32_t>(x.n) << 18);
+                    t.wlo = static_cast<float>(a * cg), t.whi = static_cast<float>(bw * cg), t.pad = 0;
+                    ++cnt[shift], maxn = std::max(maxn, x.n);
+                    if (t.wlo != 0.f && group_of(col) >= 0) mask |= 1u << group_of(col);
+                    if (t.whi != 0.f && group_of(col + 1) >= 0) mask |= 1u << group_of(col + 1);
+                }
+            for (int shift = 0; shift < 4; ++shift)
+                if (cnt[shift] > 255) ok = false;
             // value columns of the final row the tail bootstraps of this horizon read (rows with N - t < maxn)
             for (int m = 1; m <= maxn && ok; ++m) {
                 const int64_t i = static_cast<int64_t>(k) * tpitch + m;
@@ -358,10 +375,44 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
                 if (t_wlo[i] != 0 && lo < V) mask |= 1u << (lo / 32);
                 if (t_whi[i] != 0 && hi < V) mask |= 1u << (hi / 32);
             }
-            hzw[k] = static_cast<uint32_t>(beg) | (static_cast<uint32_t>(cnt) << 12) | (static_cast<uint32_t>(maxn) << 20) |
-                     (required_horizons[k] > 0 ? 1u << 30 : 0u);
+            // tail mode of the horizon
+            const int64_t h = required_horizons[k];
+            int mode = maxn > 0 ? kCsTailGeneric : kCsTailNone;
+            int32_t w3 = 0;
+            float w4 = 0.f;
+            if (maxn > 0 && plain_axis && strictly_up) {
+                // one slot for all m: vh[s-1] <= h - maxn and h - 1 <= vh[s]
+                const int s_hi = static_cast<int>(std::lower_bound(value_horizons, value_horizons + V, h - 1) - value_horizons);
+                if (s_hi >= 1 && s_hi < V && value_horizons[s_hi - 1] <= h - maxn && h - value_horizons[s_hi - 1] < (1 << 22)) {
+                    mode = kCsTailLinear;
+                    w3 = s_hi | static_cast<int32_t>((h - value_horizons[s_hi - 1]) << 8);
+                    w4 = static_cast<float>(1.0 / static_cast<double>(value_horizons[s_hi] - value_horizons[s_hi - 1]));
+                } else if (h - 1 <= xcap && h - 1 <= value_horizons[V - 1] && value_horizons[0] <= 1) {
+                    mode = kCsTailTable;
+                    w3 = static_cast<int32_t>(h - steps);
+                    xmax = std::max<int64_t>(xmax, h - 1);
+                }
+            }
+            CsHorizon& hz = hzw[k];
+            hz.w0 = static_cast<uint32_t>(beg) | (static_cast<uint32_t>(maxn) << 11) | (static_cast<uint32_t>(mode) << 21) |
+                    (h > 0 ? 1u << 23 : 0u);
+            hz.w1 = static_cast<uint32_t>(cnt[0]) | (static_cast<uint32_t>(cnt[1]) << 8) | (static_cast<uint32_t>(cnt[2]) << 16) |
+                    (static_cast<uint32_t>(cnt[3]) << 24);
+            hz.w2 = static_cast<uint32_t>(nibbles), hz.w3 = w3, hz.w4 = w4;
+            if (mode == kCsTailTable || mode == kCsTailLinear) {
+                for (int m = 1; m <= maxn; ++m) {
+                    int beyond = 0;
+                    for (int e = 0; e < E; ++e)
+                        if (ent[k][e].cnt > 0.f && ent[k][e].n > m) beyond += static_cast<int>(ent[k][e].cnt);
+                    const int64_t ni = nibbles + (m - 1);
+                    nib[ni >> 3] |= static_cast<uint32_t>(beyond & 15) << ((ni & 7) * 4);
+                }
+                nibbles += maxn;
+            }
             jobw[k / 4] |= mask;
         }
+        hdr[10] = static_cast<int32_t>(xmax);
+        hdr[11] = static_cast<int32_t>((nibbles + 7) / 8 + 2);  // words of the multiplicity table the kernel copies
         if (ok) {
             for (int j = 0; j < jobs; ++j)
                 for (int g = 0; g < kCsGroups; ++g)

@@ -95,8 +95,12 @@ def check():
                   torch.nonzero(m.any(1).any(1)).flatten().tolist()[:12])
         if not ok and nan == 0:
             diff = (got - ref).abs()
-            idx = torch.nonzero(diff > 1e-5 * ref.abs().max())[:8]
-            print("   first bad (t, env, k):", idx.tolist())
+            badm = diff > 1e-5 * ref.abs().max()
+            idx = torch.nonzero(badm)[:8]
+            print("   first bad (t, env, k):", idx.tolist(), " count", int(badm.sum()))
+            print("   bad t:", torch.nonzero(badm.any(1).any(1)).flatten().tolist()[:40])
+            print("   bad k:", torch.nonzero(badm.any(0).any(0)).flatten().tolist()[:40])
+            print("   bad env:", torch.nonzero(badm.any(0).any(1)).flatten().tolist()[:40])
     print("check:", "all ok" if bad == 0 else f"{bad} BAD")
     return bad
 
