@@ -145,24 +145,22 @@ __device__ __forceinline__ void cs_tap(const float4 (&lo)[G], const float4 (&hi)
     }
 }
 
-// The entries of one horizon with shift S: constants from the parameter bank one entry ahead (their latency hides behind
-// the gathers), two 16-byte gathers per row group, accumulators fixed at compile time.
+// The entries of one horizon with shift S: constants from the parameter bank one entry ahead (`cur` always holds entry i:
+// the stream continues across shifts, horizons and quads, so its latency hides behind the gathers), two 16-byte gathers
+// per row group, accumulators fixed at compile time.
 template <int S, int G>
-__device__ __forceinline__ int cs_run(const CsParams& q, int i, int cnt, uint32_t base, float (&acc)[G][7],
+__device__ __forceinline__ int cs_run(const CsParams& q, int i, int cnt, CsEntry& cur, uint32_t base, float (&acc)[G][7],
                                       const uint32_t (&key)[G][7]) {
     constexpr int COLB = 512 * G;
-    if (cnt > 0) {
-        const int end = i + cnt;
-        CsEntry cur = q.ent[i];
-        for (; i < end; ++i) {
-            const CsEntry nxt = q.ent[i + 1];
-            const uint32_t a = base + (cur.w & kCsOffMask);
-            float4 lo[G], hi[G];
-            lo[0] = cs_lds128<0>(a), hi[0] = cs_lds128<COLB>(a);
-            if (G > 1) lo[G - 1] = cs_lds128<512>(a), hi[G - 1] = cs_lds128<COLB + 512>(a);
-            cs_tap<S, G>(lo, hi, cur.wlo, cur.whi, cur.w, acc, key);
-            cur = nxt;
-        }
+    const int end = i + cnt;
+    for (; i < end; ++i) {
+        const CsEntry nxt = q.ent[i + 1];
+        const uint32_t a = base + (cur.w & kCsOffMask);
+        float4 lo[G], hi[G];
+        lo[0] = cs_lds128<0>(a), hi[0] = cs_lds128<COLB>(a);
+        if (G > 1) lo[G - 1] = cs_lds128<512>(a), hi[G - 1] = cs_lds128<COLB + 512>(a);
+        cs_tap<S, G>(lo, hi, cur.wlo, cur.whi, cur.w, acc, key);
+        cur = nxt;
     }
     return i;
 }
@@ -197,6 +195,7 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
     const uint32_t ftab_a = smem_u32(smem + q.off_ftab);
     const uint32_t nib_a = smem_u32(smem + q.off_nib);
     const uint32_t gpc_a = smem_u32(smem + q.off_gpc);
+    const uint32_t vh_a = gpc_a + 512u;  // value horizons (128 words behind the gamma^m / C table)
     constexpr uint32_t RT_BYTES = (N + 16) * 4, LIM_BYTES = (N + 16) * 2;
     double* st_sm = reinterpret_cast<double*>(smem + q.off_misc);         // [8] statistics of the longest horizon
     int* jobctr = reinterpret_cast<int*>(smem + q.off_misc + 64);
@@ -247,6 +246,7 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
     if (threadIdx.x < 128) {
         const int m = 128 - static_cast<int>(threadIdx.x);
         reinterpret_cast<float*>(smem + q.off_gpc)[threadIdx.x] = m <= p.tab.nmax ? __ldg(p.tab.gpow + m) * p.tab.inv_c : 0.f;
+        reinterpret_cast<int*>(smem + q.off_gpc)[128 + threadIdx.x] = q.vh[threadIdx.x];
     }
     if (threadIdx.x == 0) st_sm[3] = INFINITY, st_sm[4] = -INFINITY;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -428,17 +428,22 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
                     if (q.xmax > 0 && q.vh[g * 32 > 0 ? g * 32 - 1 : 0] < q.xmax) {
                         // the final value curve on the integer horizons of this column group's slots: x in
                         // (vh[s-1], vh[s]] is a line between the final-row values s - 1 and s (rl/returns_truncated.py:
-                        // 142-174); the consumers' tail bootstraps read it instead of gathering per target
+                        // 142-174); the consumers' tail bootstraps read it instead of gathering per target.
+                        // lane <-> slot, the four warps interleave the horizons of a slot
                         asm volatile("bar.sync 4, %0;" ::"n"(kCsXform * 32) : "memory");  // the final row of the group is in `fr`
-                        for (int sl = g * 32 + tw; sl < g * 32 + 32 && sl < V; sl += kCsXform) {
-                            const int xl = sl > 0 ? q.vh[sl - 1] : 0, xr = min(q.vh[sl], q.xmax);
-                            if (xl >= q.xmax) break;
+                        const int sl = g * 32 + lane;
+                        int xl = 0, dx = 0;
+                        float fa = 0.f, slope = 0.f;
+                        if (sl < V) {
+                            const int xr = static_cast<int>(cs_lds_u32(vh_a + static_cast<uint32_t>(sl) * 4u));
+                            xl = sl > 0 ? static_cast<int>(cs_lds_u32(vh_a + static_cast<uint32_t>(sl - 1) * 4u)) : 0;
                             const float fb = cs_lds(fr_a + static_cast<uint32_t>(sl) * 4u);
-                            const float fa = sl > 0 ? cs_lds(fr_a + static_cast<uint32_t>(sl - 1) * 4u) : fb;
-                            const float slope = (fb - fa) / static_cast<float>(q.vh[sl] - xl);
-                            for (int x = xl + 1 + lane; x <= xr; x += 32)
-                                cs_sts(ftab_a + static_cast<uint32_t>(x) * 4u, fmaf(static_cast<float>(x - xl), slope, fa));
+                            fa = sl > 0 ? cs_lds(fr_a + static_cast<uint32_t>(sl - 1) * 4u) : fb;
+                            slope = __fdividef(fb - fa, static_cast<float>(max(xr - xl, 1)));
+                            dx = max(min(xr, q.xmax) - xl, 0);
                         }
+                        for (int jx = tw; __any_sync(0xffffffffu, jx < dx); jx += kCsXform)
+                            if (jx < dx) cs_sts(ftab_a + static_cast<uint32_t>(xl + 1 + jx) * 4u, fmaf(static_cast<float>(jx + 1), slope, fa));
                         __syncwarp();
                     }
                     if (lane == 0) mbar_arrive(&gfull[g]);
@@ -513,6 +518,7 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
             }
             float o[G][4][4];
             uint32_t live = 0;
+            CsEntry cur = q.ent[q.hz[qd * 4].w0 & 0x7ffu];  // first entry of the quad (fetched before the row limits)
             if (q.dbg & 32) {
 #pragma unroll
                 for (int g = 0; g < G; ++g)
@@ -530,11 +536,11 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
 #pragma unroll
                     for (int i = 0; i < 7; ++i) acc[g][i] = 0.f;
                 if (!(q.dbg & 8)) {
-                    int i = static_cast<int>(hz.w0 & 0x7ffu);
-                    i = cs_run<0, G>(q, i, static_cast<int>(hz.w1 & 0xffu), base, acc, key);
-                    i = cs_run<1, G>(q, i, static_cast<int>((hz.w1 >> 8) & 0xffu), base, acc, key);
-                    i = cs_run<2, G>(q, i, static_cast<int>((hz.w1 >> 16) & 0xffu), base, acc, key);
-                    i = cs_run<3, G>(q, i, static_cast<int>(hz.w1 >> 24), base, acc, key);
+                    int i = static_cast<int>(hz.w0 & 0x7ffu);  // == ei: the lists of consecutive horizons are contiguous
+                    i = cs_run<0, G>(q, i, static_cast<int>(hz.w1 & 0xffu), cur, base, acc, key);
+                    i = cs_run<1, G>(q, i, static_cast<int>((hz.w1 >> 8) & 0xffu), cur, base, acc, key);
+                    i = cs_run<2, G>(q, i, static_cast<int>((hz.w1 >> 16) & 0xffu), cur, base, acc, key);
+                    i = cs_run<3, G>(q, i, static_cast<int>(hz.w1 >> 24), cur, base, acc, key);
                 }
                 // carries: accumulators 0 .. 2 belong to the last three rows of the previous lane (lane 0 of a group
                 // hands over to lane 31 of the group before; lane 0 of the first group drops them)
@@ -788,7 +794,7 @@ int launch_tvf_cslab(const TvfParams& p, double* stats, double* partials, unsign
     const uint32_t ftab_bytes = cs_align(static_cast<uint32_t>(q.xmax + 8) * 4u, 128);
     const uint32_t nib_bytes = cs_align(static_cast<uint32_t>(q.nib_words + 24) * 4u, 128);
     const uint32_t rest = 2u * 16384u + cs_align(2u * (N + 16) * 4u, 128) + cs_align(2u * (N + 16) * 2u, 128) +
-                          cs_align(static_cast<uint32_t>(V) * 4u, 128) + ftab_bytes + nib_bytes + 512u + 128u +
+                          cs_align(static_cast<uint32_t>(V) * 4u, 128) + ftab_bytes + nib_bytes + 1024u + 128u +
                           (2 * kCsMaxStages + 2 * kCsGroups + 4) * 8u;
     int nstage = 0;  // staging ring: as deep as shared memory allows (the TMA loads are latency bound)
     while (nstage < kCsMaxStages && slab_bytes + rest + static_cast<uint32_t>(nstage + 1) * kCsChunkBytes <= static_cast<uint32_t>(max_smem))
@@ -804,7 +810,7 @@ int launch_tvf_cslab(const TvfParams& p, double* stats, double* partials, unsign
     q.off_ftab = q.off_fr + cs_align(static_cast<uint32_t>(V) * 4u, 128);
     q.off_nib = q.off_ftab + ftab_bytes;
     q.off_gpc = q.off_nib + nib_bytes;
-    q.off_misc = q.off_gpc + 512u;
+    q.off_misc = q.off_gpc + 1024u;
     q.off_bar = q.off_misc + 128;
     q.smem_total = q.off_bar + (2 * kCsMaxStages + 2 * kCsGroups + 4) * 8u;
     if (q.smem_total > static_cast<uint32_t>(max_smem)) return unsupported("the env slab does not fit in shared memory");
