@@ -13,6 +13,7 @@
 //  * per (t,a,k) the (up to C) distinct clamped n-steps n' = min(sample, h_k) come from the host
 //    entry table with their slots / weights; entries with n' > min(N - t, nd) collapse into a single
 //    shared term (the episode ended: no bootstrap; or the rollout ended: bootstrap from row N).
+#include <stdlib.h>
 #include "tvf_common.cuh"
 
 namespace ppo {
@@ -294,7 +295,11 @@ extern "C" int ppo_tvf_targets_ex(const float* rewards, int64_t reward_row_strid
         ticket = static_cast<unsigned int*>(workspace);
         partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
     }
-    if (path == PPO_TVF_CSLAB || (path == PPO_TVF_AUTO && tables->n_entries >= 3)) {
+    static const bool prefer_cslab = [] {
+        const char* e = getenv("PPO_TVF_PREFER_CSLAB");
+        return e != nullptr && atoi(e) != 0;
+    }();
+    if (path == PPO_TVF_CSLAB || (path == PPO_TVF_AUTO && tables->n_entries >= 3 && prefer_cslab)) {
         rc = launch_tvf_cslab(p, stats, partials, ticket, kStatsBlocks, vweights, vout, vout_rs, s, &stats_fused);
         if (path == PPO_TVF_CSLAB && rc != PPO_OK) return rc;
         taken = PPO_TVF_CSLAB;
