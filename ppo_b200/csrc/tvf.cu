@@ -232,8 +232,9 @@ extern "C" int ppo_tvf_last_path(void) { return g_last_path; }
 
 extern "C" int64_t ppo_tvf_workspace_bytes(int64_t steps, int64_t envs) {
     (void)steps;
-    (void)envs;
-    return 256 + static_cast<int64_t>(kStatsBlocks) * 8 * sizeof(double);
+    // ticket + per-block records of the statistics kernels, or one record per env (column slab kernel)
+    const int64_t records = envs > kStatsBlocks ? envs : kStatsBlocks;
+    return 256 + records * 8 * static_cast<int64_t>(sizeof(double));
 }
 
 extern "C" int ppo_tvf_targets(const float* rewards, int64_t reward_row_stride, const void* dones, int done_kind,
@@ -300,7 +301,8 @@ extern "C" int ppo_tvf_targets_ex(const float* rewards, int64_t reward_row_strid
         return e != nullptr && atoi(e) != 0;
     }();
     if (path == PPO_TVF_CSLAB || (path == PPO_TVF_AUTO && tables->n_entries >= 3 && prefer_cslab)) {
-        rc = launch_tvf_cslab(p, stats, partials, ticket, kStatsBlocks, vweights, vout, vout_rs, s, &stats_fused);
+        rc = launch_tvf_cslab(p, stats, partials, ticket, partials ? (workspace_bytes - 256) / 8 : 0, vweights, vout, vout_rs, s,
+                              &stats_fused);
         if (path == PPO_TVF_CSLAB && rc != PPO_OK) return rc;
         taken = PPO_TVF_CSLAB;
         if (rc == PPO_OK) vout = nullptr;  // the value estimate was written by the same launch

@@ -32,6 +32,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "tma.cuh"
 #include "tvf_common.cuh"
 
@@ -52,13 +54,13 @@ struct CsParams {
     int ng, njobs, n_ent, tail_pitch, want_stats, want_value, nstage;
     int dbg;  // development switches (PPO_TVF_DEBUG): 1 no stores, 2 no TMA loads, 8 no entry loop, 16 no tail term
     int arrivals[kCsGroups];
-    int64_t env_base, env_rem;
+    unsigned int* sched;  // {next env, finished CTAs}: envs are drawn from a global counter (CTAs differ in speed)
+    double* env_stats;    // [envs][8] statistics of the longest horizon per env (want_stats), folded in env order at the end
     uint32_t off_stage, off_tile, off_rtab, off_lim, off_fr, off_ftab, off_nib, off_gpc, off_misc, off_bar, smem_total;
     int xmax, nib_words;      // table horizons 0..xmax of the final value curve; words of the multiplicity table
     const uint32_t* nib_dev;  // multiplicity table (device copy inside the table blob)
     float* value_out;  // [N + 1, A] value estimate sum_j vw[j] * V[r, a, j] (want_value), row stride vo_rs
     int64_t vo_rs;
-    double* partials;  // [grid][8] per-CTA statistics of the longest horizon (want_stats)
     unsigned int* ticket;
     double* stats;
     const uint4* tail4;  // [K][tail_pitch] folded tail records {idx lo | hi << 16, cwlo, cwhi, 0}
@@ -70,7 +72,8 @@ struct CsParams {
 };
 
 // development: globaltimer stamps of CTA 0 (PPO_TVF_DEBUG bit 256), read by ppo_tvf_cslab_debug_times
-__device__ unsigned long long g_cs_times[512];
+__device__ unsigned int g_cs_sched[2 * 64];  // 64 launches in flight at most; the last CTA of a launch zeroes its pair
+__device__ unsigned long long g_cs_times[512 + 2 * 160];  // [512 ..): start / end of every CTA
 __device__ __forceinline__ void cs_stamp(int dbg, int slot) {
     if ((dbg & 256) && blockIdx.x == 0 && slot < 512) {
         unsigned long long t;
@@ -185,6 +188,9 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
     uint64_t* gfree = gfull + kCsGroups;    // [5] every job of the env that reads the column group has finished
     uint64_t* rfull = gfree + kCsGroups;    // [2] R / lim tables of env parity ready
     uint64_t* rempty = rfull + 2;           // [2]
+    uint64_t* jobready = rempty + 2;        // [team][2] the coordinator has published the team's next job
+    uint64_t* tilefull = jobready + 4;      // [team] the eight warps of the team have written their columns of the job tile
+    uint64_t* tgrant = tilefull + 2;        // [2] the job tile belongs to job j (parity j & 1): every earlier job has left it
 
     const uint32_t slab_a = smem_u32(smem);
     const uint32_t stage_a = smem_u32(smem + q.off_stage);
@@ -197,20 +203,22 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
     const uint32_t gpc_a = smem_u32(smem + q.off_gpc);
     const uint32_t vh_a = gpc_a + 512u;  // value horizons (128 words behind the gamma^m / C table)
     constexpr uint32_t RT_BYTES = (N + 16) * 4, LIM_BYTES = (N + 16) * 2;
-    double* st_sm = reinterpret_cast<double*>(smem + q.off_misc);         // [8] statistics of the longest horizon
-    int* jobctr = reinterpret_cast<int*>(smem + q.off_misc + 64);
 
-    const int64_t bidx = blockIdx.x;
-    const int nenv = static_cast<int>(q.env_base + (bidx < q.env_rem ? 1 : 0));
-    const int64_t env0 = bidx * q.env_base + (bidx < q.env_rem ? bidx : q.env_rem);
+    // Envs are drawn one at a time from a global counter by the scan warp (SMs differ in speed by 20 % on this pass);
+    // local env e of this CTA is global env envq[e & 7], -1 after the last one.
+    volatile int* envq_n = reinterpret_cast<volatile int*>(smem + q.off_misc + 92);
+    volatile int* envq = reinterpret_cast<volatile int*>(smem + q.off_misc + 96);
+    auto env_of = [&](int e) {
+        while (*envq_n <= e) __nanosleep(40);
+        return envq[e & 7];
+    };
 
     // The reward / terminal columns of the first env are requested before anything else: the first R / lim tables
     // gate the pipeline fill, and these strided loads are pure latency.  Lane l owns rows [l * RPL, (l + 1) * RPL).
     constexpr int RPL = N / 32;
     float rr[RPL];
     uint32_t dw[RPL];
-    auto load_columns = [&](int e) {
-        const int64_t env = env0 + e;
+    auto load_columns = [&](int64_t env) {
 #pragma unroll
         for (int i = 0; i < RPL; ++i) {
             const int row = lane * RPL + i;
@@ -221,7 +229,11 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
             else dw[i] = 0u;
         }
     };
-    if (warp == kCsConsumers + kCsXform && nenv > 0) load_columns(0);
+    if ((q.dbg & 256) && threadIdx.x == 0 && blockIdx.x < 160) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        g_cs_times[512 + blockIdx.x] = t;
+    }
     int poll_ns = kCsPollNs;
     if (q.dbg >> 16) poll_ns = q.dbg >> 16;
     if (threadIdx.x == 0) {
@@ -231,6 +243,8 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
             mbar_init(&gfree[g], q.arrivals[g] > 0 ? q.arrivals[g] : 1);
         }
         for (int i = 0; i < 2; ++i) mbar_init(&rfull[i], 1), mbar_init(&rempty[i], NJ + kCsXform);
+        for (int i = 0; i < 4; ++i) mbar_init(&jobready[i], 1);
+        for (int i = 0; i < 2; ++i) mbar_init(&tilefull[i], 8), mbar_init(&tgrant[i], 1);
         mbar_fence_init();
         tma_prefetch_desc(&vmap);
         tma_prefetch_desc(&omap);
@@ -248,7 +262,9 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
         reinterpret_cast<float*>(smem + q.off_gpc)[threadIdx.x] = m <= p.tab.nmax ? __ldg(p.tab.gpow + m) * p.tab.inv_c : 0.f;
         reinterpret_cast<int*>(smem + q.off_gpc)[128 + threadIdx.x] = q.vh[threadIdx.x];
     }
-    if (threadIdx.x == 0) st_sm[3] = INFINITY, st_sm[4] = -INFINITY;
+    if (threadIdx.x == 0) {
+        mbar_arrive(&tgrant[0]);  // job 0 owns the tile from the start
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
@@ -257,14 +273,79 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
         // values to local memory; it runs an env ahead and is latency tolerant)
         if (warp >= kCsConsumers + kCsXform) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");  // second helper warpgroup
         if (warp > kCsConsumers + kCsXform + 1) {
-            // idle warps of the second helper warpgroup
+            // ------------------------------------------------------------------ team coordinators (one per team)
+            // Hands the team its jobs (32 consecutive horizons of one env; teams alternate within an env and swap
+            // roles every env, so both see every horizon group) once their inputs are in shared memory, and sends the
+            // team's finished job tile to global memory -- the consumer warps never wait for each other at a barrier.
+            const int T = warp - (kCsConsumers + kCsXform + 2);
+            const int NH = NJ >> 3;
+            auto team_of = [&](int j) { return NH == 1 ? 0 : ((j % NH) + (j / NH)) & 1; };
+            auto next_job = [&](int j) {
+                while (team_of(j) != T) ++j;
+                return j;
+            };
+            volatile int* slot = reinterpret_cast<volatile int*>(smem + q.off_misc + 72) + T * 2;
+            int jpub = next_job(0), jst = jpub;  // next job to publish / to store
+            int npub = 0, nst = 0;
+            bool done_pub = false;
+            while (!done_pub || nst < npub) {
+                bool progress = false;
+                if (!done_pub && npub - nst < 2 && *envq_n > jpub / NH) {
+                    if (envq[(jpub / NH) & 7] < 0) {
+                        if (lane == 0) slot[npub & 1] = -1, mbar_arrive(&jobready[T * 2 + (npub & 1)]);
+                        done_pub = true, progress = true;
+                    } else {
+                        const int ee = jpub / NH, hh = jpub - ee * NH;
+                        uint32_t um = 0;
+#pragma unroll
+                        for (int w = 0; w < 8; ++w) um |= q.jobmask[hh * 8 + w];
+                        bool ready = mbar_try_wait(&rfull[ee & 1], (static_cast<uint32_t>(ee) >> 1) & 1u);
+#pragma unroll
+                        for (int g = 0; g < kCsGroups; ++g)
+                            if (um >> g & 1u) ready = ready && mbar_try_wait(&gfull[g], static_cast<uint32_t>(ee & 1));
+                        if (ready) {
+                            if (lane == 0) {
+                                if (ee < 4 && hh < 4) cs_stamp(q.dbg, 64 * ee + 12 + 12 * hh + 0);
+                                slot[npub & 1] = jpub;
+                                mbar_arrive(&jobready[T * 2 + (npub & 1)]);
+                            }
+                            ++npub, jpub = next_job(jpub + 1), progress = true;
+                        }
+                    }
+                }
+                if (nst < npub) {
+                    if (mbar_try_wait(&tilefull[T], static_cast<uint32_t>(nst & 1))) {
+                        const int ee = jst / NH, hh = jst - ee * NH;
+                        if (lane == 0) {
+                            if (!(q.dbg & 1)) {
+#pragma unroll
+                                for (int g = 0; g < G; ++g)
+#pragma unroll
+                                    for (int c = 0; c < 4; ++c)
+                                        cs_store_4d(&omap, tile_a + static_cast<uint32_t>(g * 4 + c) * 4096u, hh * 32,
+                                                    envq[ee & 7], c, 32 * g);
+                                cs_bulk_commit();
+                                cs_bulk_wait_read();
+                            }
+                            mbar_arrive(&tgrant[(jst + 1) & 1]);  // the tile goes to the next job
+                            if (ee < 4 && hh < 4) cs_stamp(q.dbg, 64 * ee + 12 + 12 * hh + 4);
+                        }
+                        __syncwarp();
+                        ++nst, jst = next_job(jst + 1), progress = true;
+                    }
+                }
+                if (!progress) __nanosleep(100);
+            }
+            if (lane == 0) cs_bulk_wait_all();
+            if (lane == 0) cs_stamp(q.dbg, 500 + T);
         } else if (warp == kCsConsumers + kCsXform + 1) {
             // ------------------------------------------------------------------ TMA producer
             if (lane == 0) {
                 int slot = 0;
                 uint32_t par = 0;
-                for (int e = 0; e < nenv; ++e) {
-                    const int env = static_cast<int>(env0 + e);
+                for (int e = 0;; ++e) {
+                    const int env = env_of(e);
+                    if (env < 0) break;
                     for (int g = 0; g < NG; ++g)
                         for (int c = 0; c < NCH; ++c) {
                             mbar_wait_sleep(&sempty[slot], par ^ 1, 2 * poll_ns);
@@ -282,9 +363,26 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
         } else if (warp == kCsConsumers + kCsXform) {
             // ------------------------------------------------------------------ scan warp: R(t) and lim(t) per env
             const double gamma = q.gamma;
-            for (int e = 0; e < nenv; ++e) {
+            for (int e = 0;; ++e) {
                 const uint32_t par = static_cast<uint32_t>(e & 1);
-                if (e > 0 && !(q.dbg & 64)) load_columns(e);
+                // the tables of env e - 2 must have been consumed before this env is even drawn: drawing late keeps the
+                // envs a CTA holds in its pipeline (and with them the imbalance at the end of the launch) small
+                mbar_wait_sleep(&rempty[par], ((static_cast<uint32_t>(e) >> 1) & 1u) ^ 1u, 4 * poll_ns);
+                int env = -1;
+                if (lane == 0) {
+                    const unsigned int v = atomicAdd(q.sched, 1u);
+                    env = v < static_cast<unsigned int>(p.envs) ? static_cast<int>(v) : -1;
+                    envq[e & 7] = env;
+                    __threadfence_block();
+                    *envq_n = e + 1;
+                }
+                env = __shfl_sync(0xffffffffu, env, 0);
+                if (env < 0) {
+                    // no CTA draws after its last draw: the last CTA to get here resets the pair for the next launch
+                    if (lane == 0 && atomicAdd(q.sched + 1, 1u) == gridDim.x - 1) q.sched[0] = 0u, q.sched[1] = 0u;
+                    break;
+                }
+                load_columns(env);
                 bool dn[RPL];
 #pragma unroll
                 for (int i = 0; i < RPL; ++i)
@@ -316,7 +414,6 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
                 double x = shfl_down_f64(a, 1);
                 int l = __shfl_down_sync(0xffffffffu, c, 1);
                 if (lane == 31) x = 0.0, l = 0;
-                mbar_wait_sleep(&rempty[par], ((static_cast<uint32_t>(e) >> 1) & 1u) ^ 1u, 4 * poll_ns);
                 const uint32_t rt = rt_a + par * RT_BYTES, lt = lim_a + par * LIM_BYTES;
 #pragma unroll
                 for (int i = RPL - 1; i >= 0; --i) {
@@ -342,29 +439,19 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
             // row 0 is not part of the slab (no target bootstraps from it): straight from global memory, fetched one env
             // ahead so that its latency is off the critical path
             float row0v[4] = {0.f, 0.f, 0.f, 0.f};
-            auto load_row0 = [&](int e) {
-                const float* row0 = p.vs + (env0 + e) * p.vs_es;
+            auto load_row0 = [&](int64_t env) {
+                const float* row0 = p.vs + env * p.vs_es;
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj)
                     if (jj * 32 + lane < V) row0v[jj] = __ldg(row0 + jj * 32 + lane);
             };
             const int wv = q.want_value;
-            if (wv && tw == 0 && nenv > 0) load_row0(0);
             const int rloc = 32 * tw + lane;
-            for (int e = 0; e < nenv; ++e) {
+            for (int e = 0;; ++e) {
                 const uint32_t par = static_cast<uint32_t>(e & 1);
-                if (wv && tw == 0) {
-                    float acc = 0.f;
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int j = jj * 32 + lane;
-                        if (j < V) acc = wv == 2 ? fmaf(row0v[jj], q.vw[j], acc) : (j == V - 1 ? row0v[jj] : acc);
-                    }
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-                    if (lane == 0) q.value_out[env0 + e] = acc;
-                    if (e + 1 < nenv) load_row0(e + 1);
-                }
+                const int env = env_of(e);
+                if (env < 0) break;
+                if (wv && tw == 0) load_row0(env);  // used after the column groups: the latency hides behind them
                 if (tw == 0 && lane == 0 && e < 4) cs_stamp(q.dbg, 64 * e + 0);
                 mbar_wait(&rfull[par], (static_cast<uint32_t>(e) >> 1) & 1u);
                 if (tw == 0 && lane == 0 && e < 4) cs_stamp(q.dbg, 64 * e + 1);
@@ -452,7 +539,18 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
                 if (wv) {
 #pragma unroll
                     for (int c = 0; c < NCH; ++c)
-                        q.value_out[static_cast<int64_t>(c * kCsChunkRows + rloc + 1) * q.vo_rs + env0 + e] = dot[c];
+                        q.value_out[static_cast<int64_t>(c * kCsChunkRows + rloc + 1) * q.vo_rs + env] = dot[c];
+                    if (tw == 0) {
+                        float acc = 0.f;
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int j = jj * 32 + lane;
+                            if (j < V) acc = wv == 2 ? fmaf(row0v[jj], q.vw[j], acc) : (j == V - 1 ? row0v[jj] : acc);
+                        }
+#pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+                        if (lane == 0) q.value_out[env] = acc;
+                    }
                 }
                 if (lane == 0) mbar_arrive(&rempty[par]);
             }
@@ -461,41 +559,18 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
         // ---------------------------------------------------------------------- consumers
         asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
         const uint32_t base = slab_a + static_cast<uint32_t>(lane) * 16u;
-        // Two teams of eight warps: a team takes 32 consecutive horizons of one env (a "team job", handed out by an
-        // atomic counter in env / horizon order), warp w of the team the quad 8 hg + w for all rows; the team's
-        // results leave as 128-byte rows (a 16-byte row costs the TMA unit as much as a 128-byte one).
+        // Two teams of eight warps: a team takes 32 consecutive horizons of one env (a "team job", published by the
+        // team's coordinator warp), each warp one quad of them for all rows (the quads rotate over the warps from job
+        // to job: their costs differ); the team's results leave as 128-byte rows (a 16-byte row costs the TMA unit
+        // as much as a 128-byte one) from a job tile that the teams use in job order.
         const int team = warp >> 3, w8 = warp & 7;
-        const uint32_t tile = tile_a + static_cast<uint32_t>(team) * 16384u;  // [t % 4][t / 4 % 32][32 horizons], 128 B swizzle
         volatile int* slot = reinterpret_cast<volatile int*>(smem + q.off_misc + 72) + team * 2;
         const int NH = NJ >> 3;  // team jobs per env
-        // Jobs in flight must not span more than one env boundary (the hand-off barriers carry one parity bit): with
-        // one team job per env only one team works.
-        const int total_jobs = team < NH ? nenv * NH : 0;
-        for (int it = 0; total_jobs > 0; ++it) {
-            // The first warp of the team takes the job and waits for its inputs (the R / lim tables of the env and the
-            // column groups any of the eight quads reads); the team barrier hands both to the other warps.  (All 32
-            // lanes wait together: a single waiting lane is woken late by the mbarrier unit.)
-            if (w8 == 0) {
-                int jj = 0;
-                if (lane == 0) jj = atomicAdd(jobctr, 1);
-                jj = __shfl_sync(0xffffffffu, jj, 0);
-                if (jj < total_jobs) {
-                    const int ee = jj / NH, hh = jj - ee * NH;
-                    if (lane == 0 && ee < 4 && hh < 4) cs_stamp(q.dbg, 64 * ee + 12 + 12 * hh + 0);
-                    uint32_t um = 0;
-#pragma unroll
-                    for (int w = 0; w < 8; ++w) um |= q.jobmask[hh * 8 + w];
-                    mbar_wait(&rfull[ee & 1], (static_cast<uint32_t>(ee) >> 1) & 1u);
-#pragma unroll
-                    for (int g = 0; g < kCsGroups; ++g)
-                        if (um >> g & 1u) mbar_wait(&gfull[g], static_cast<uint32_t>(ee & 1));
-                }
-                if (lane == 0) slot[it & 1] = jj;
-            }
-            asm volatile("bar.sync %0, 256;" ::"r"(1 + team) : "memory");
+        for (int it = 0;; ++it) {
+            mbar_wait(&jobready[team * 2 + (it & 1)], (static_cast<uint32_t>(it) >> 1) & 1u);
             const int j = slot[it & 1];
-            if (j >= total_jobs) break;
-            const int e = j / NH, hg = j - e * NH, qd = hg * 8 + w8;
+            if (j < 0) break;
+            const int e = j / NH, hg = j - e * NH, qpos = (w8 + it) & 7, qd = hg * 8 + qpos;
             const bool stamp = w8 == 0 && lane == 0 && e < 4 && hg < 4;
             const uint32_t par = static_cast<uint32_t>(e & 1);
             const uint32_t mask = q.jobmask[qd];
@@ -630,9 +705,9 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
                 mbar_arrive(&rempty[par]);
             }
             if (q.want_stats && qd == NJ - 1) {
-                // statistics of the longest horizon: jobs of the same quad run in env order (job (e + 1, q) cannot
-                // start before job (e, q) has released its column groups), so the running sums are deterministic
-                double s = 0.0, sq = 0.0;
+                // statistics of the longest horizon: one record per env (folded in env order at the end of the launch,
+                // so the sums do not depend on which CTA took which env)
+                double sm = 0.0, sq = 0.0;
                 float mn = INFINITY, mx = -INFINITY;
                 int z = 0;
 #pragma unroll
@@ -640,77 +715,81 @@ tvf_cslab_kernel(const __grid_constant__ CsParams q, const __grid_constant__ CUt
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const float x = o[g][c][3];
-                        s += x, sq += static_cast<double>(x) * x, z += x == 0.f ? 1 : 0;
+                        sm += x, sq += static_cast<double>(x) * x, z += x == 0.f ? 1 : 0;
                         mn = fminf(mn, x), mx = fmaxf(mx, x);
                     }
-                s = warp_sum_f64(s), sq = warp_sum_f64(sq);
+                sm = warp_sum_f64(sm), sq = warp_sum_f64(sq);
                 mn = warp_min_f32(mn), mx = warp_max_f32(mx);
                 z = __reduce_add_sync(0xffffffffu, z);
                 if (lane == 0) {
-                    st_sm[0] += static_cast<double>(N), st_sm[1] += s, st_sm[2] += sq;
-                    st_sm[3] = fmin(st_sm[3], static_cast<double>(mn)), st_sm[4] = fmax(st_sm[4], static_cast<double>(mx));
-                    st_sm[5] += static_cast<double>(z);
+                    double* rec = q.env_stats + static_cast<int64_t>(envq[e & 7]) * 8;
+                    rec[0] = static_cast<double>(N), rec[1] = sm, rec[2] = sq, rec[3] = static_cast<double>(mn);
+                    rec[4] = static_cast<double>(mx), rec[5] = static_cast<double>(z);
                 }
             }
-            // results: tile [t % 4][t / 4][32 horizons] per 128-row group (128-byte rows in TMA's 128-byte swizzle:
-            // the eight lanes of a quarter-warp store to eight different bank groups), four tensor stores each
-            const int env = static_cast<int>(env0 + e);
+            // results: job tile [128-row group][t % 4][t / 4][32 horizons] (128-byte rows in TMA's 128-byte swizzle: the
+            // eight lanes of a quarter-warp store to eight different bank groups); the coordinator sends it off once
+            // all eight warps have written their quads
+            mbar_wait(&tgrant[j & 1], (static_cast<uint32_t>(j) >> 1) & 1u);
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                if (w8 == 0 && lane == 0) cs_bulk_wait_read();  // the previous stores of this team have read the tile
-                asm volatile("bar.sync %0, 256;" ::"r"(1 + team) : "memory");
+            for (int g = 0; g < G; ++g)
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
-                    cs_sts128(tile + static_cast<uint32_t>(c) * 4096u + static_cast<uint32_t>(lane) * 128u +
-                                  (static_cast<uint32_t>(w8 ^ (lane & 7)) << 4),
+                    cs_sts128(tile_a + static_cast<uint32_t>(g * 4 + c) * 4096u + static_cast<uint32_t>(lane) * 128u +
+                                  (static_cast<uint32_t>(qpos ^ (lane & 7)) << 4),
                               o[g][c][0], o[g][c][1], o[g][c][2], o[g][c][3]);
-                cs_fence_async();  // tile writes -> visible to the bulk-copy (async) proxy
-                asm volatile("bar.sync %0, 256;" ::"r"(1 + team) : "memory");
-                if (w8 == 0 && lane == 0 && !(q.dbg & 1)) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) cs_store_4d(&omap, tile + static_cast<uint32_t>(c) * 4096u, hg * 32, env, c, 32 * g);
-                    cs_bulk_commit();
-                }
-                if (stamp) cs_stamp(q.dbg, 64 * e + 12 + 12 * hg + 3 + g);
-            }
+            cs_fence_async();  // tile writes -> visible to the bulk-copy (async) proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tilefull[team]);
+            if (stamp) cs_stamp(q.dbg, 64 * e + 12 + 12 * hg + 3);
         }
-        if (lane == 0) cs_bulk_wait_all();
+        if (lane == 0 && (warp & 7) == 0) cs_stamp(q.dbg, 502 + (warp >> 3));
+        if ((q.dbg & 256) && threadIdx.x == 0 && blockIdx.x < 160) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            g_cs_times[512 + 160 + blockIdx.x] = t;
+        }
         if (q.want_stats) {
+            // the last CTA folds the env records: thread t takes envs t, t + 512, ... in order, then a fixed tree
+            __threadfence();
             asm volatile("bar.sync 3, %0;" ::"n"(kCsConsumers * 32) : "memory");
-            if (warp == 0) {
-                int last = 0;
-                if (lane == 0) {
-                    double* rec = q.partials + static_cast<int64_t>(blockIdx.x) * 8;
-                    rec[0] = st_sm[0], rec[1] = st_sm[1], rec[2] = st_sm[2], rec[3] = st_sm[3], rec[4] = st_sm[4], rec[5] = st_sm[5];
-                    __threadfence();
-                    last = atomicAdd(q.ticket, 1u) == gridDim.x - 1;
+            int* flag = reinterpret_cast<int*>(smem + q.off_misc + 64);
+            if (threadIdx.x == 0) *flag = atomicAdd(q.ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+            asm volatile("bar.sync 3, %0;" ::"n"(kCsConsumers * 32) : "memory");
+            if (*flag) {
+                __threadfence();
+                double an = 0, as = 0, aq = 0, az = 0, amn = INFINITY, amx = -INFINITY;
+                for (int64_t g = threadIdx.x; g < p.envs; g += kCsConsumers * 32) {
+                    const double* rec = q.env_stats + g * 8;
+                    an += __ldcg(rec), as += __ldcg(rec + 1), aq += __ldcg(rec + 2), az += __ldcg(rec + 5);
+                    amn = fmin(amn, __ldcg(rec + 3)), amx = fmax(amx, __ldcg(rec + 4));
                 }
-                last = __shfl_sync(0xffffffffu, last, 0);
-                if (last) {
-                    // the last CTA folds all records in index order: deterministic, no float atomics
-                    __threadfence();
-                    double an = 0, as = 0, aq = 0, az = 0, amn = INFINITY, amx = -INFINITY;
-                    for (unsigned int g = lane; g < gridDim.x; g += 32) {
-                        const double* rec = q.partials + static_cast<int64_t>(g) * 8;
-                        an += __ldcg(rec), as += __ldcg(rec + 1), aq += __ldcg(rec + 2), az += __ldcg(rec + 5);
-                        amn = fmin(amn, __ldcg(rec + 3)), amx = fmax(amx, __ldcg(rec + 4));
-                    }
 #pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) {
-                        an += shfl_down_f64(an, d), as += shfl_down_f64(as, d), aq += shfl_down_f64(aq, d);
-                        az += shfl_down_f64(az, d);
-                        amn = fmin(amn, shfl_down_f64(amn, d)), amx = fmax(amx, shfl_down_f64(amx, d));
+                for (int d = 16; d > 0; d >>= 1) {
+                    an += shfl_down_f64(an, d), as += shfl_down_f64(as, d), aq += shfl_down_f64(aq, d);
+                    az += shfl_down_f64(az, d);
+                    amn = fmin(amn, shfl_down_f64(amn, d)), amx = fmax(amx, shfl_down_f64(amx, d));
+                }
+                double* red = reinterpret_cast<double*>(smem + q.off_tile);  // the job tile is idle by now
+                if (lane == 0) {
+                    red[warp * 8 + 0] = an, red[warp * 8 + 1] = as, red[warp * 8 + 2] = aq, red[warp * 8 + 3] = amn;
+                    red[warp * 8 + 4] = amx, red[warp * 8 + 5] = az;
+                }
+                asm volatile("bar.sync 3, %0;" ::"n"(kCsConsumers * 32) : "memory");
+                if (threadIdx.x == 0) {
+                    an = 0, as = 0, aq = 0, az = 0, amn = INFINITY, amx = -INFINITY;
+                    for (int w = 0; w < kCsConsumers; ++w) {
+                        an += red[w * 8 + 0], as += red[w * 8 + 1], aq += red[w * 8 + 2], az += red[w * 8 + 5];
+                        amn = fmin(amn, red[w * 8 + 3]), amx = fmax(amx, red[w * 8 + 4]);
                     }
-                    if (lane == 0) {
-                        for (int j = 0; j < PPO_STATS_LEN; ++j) q.stats[j] = 0.0;
-                        q.stats[PPO_STAT_COUNT] = an;
-                        q.stats[PPO_STAT_ADV_SUM] = as;
-                        q.stats[PPO_STAT_ADV_SUMSQ] = aq;
-                        q.stats[PPO_STAT_ADV_MIN] = amn;
-                        q.stats[PPO_STAT_ADV_MAX] = amx;
-                        q.stats[PPO_STAT_ADV_ZEROS] = az;
-                        *q.ticket = 0u;
-                    }
+                    for (int j = 0; j < PPO_STATS_LEN; ++j) q.stats[j] = 0.0;
+                    q.stats[PPO_STAT_COUNT] = an;
+                    q.stats[PPO_STAT_ADV_SUM] = as;
+                    q.stats[PPO_STAT_ADV_SUMSQ] = aq;
+                    q.stats[PPO_STAT_ADV_MIN] = amn;
+                    q.stats[PPO_STAT_ADV_MAX] = amx;
+                    q.stats[PPO_STAT_ADV_ZEROS] = az;
+                    *q.ticket = 0u;
                 }
             }
         }
@@ -722,15 +801,20 @@ static uint32_t cs_align(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 template <int G>
 static int cs_launch_variant(const CsParams& q, const CUtensorMap& vmap, const CUtensorMap& omap, int64_t grid,
                              cudaStream_t stream) {
-    PPO_CUDA(cudaFuncSetAttribute(tvf_cslab_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(q.smem_total)));
+    static std::atomic<uint32_t> configured{0};  // largest dynamic shared-memory size set so far (per instantiation)
+    if (configured.load() < q.smem_total) {
+        PPO_CUDA(cudaFuncSetAttribute(tvf_cslab_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(q.smem_total)));
+        configured.store(q.smem_total);
+    }
     tvf_cslab_kernel<G><<<static_cast<unsigned>(grid), kCsThreads, q.smem_total, stream>>>(q, vmap, omap);
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;
 }
 
 // stats / partials / ticket: optional fused statistics of the longest horizon (workspace layout of tvf.cu).
-int launch_tvf_cslab(const TvfParams& p, double* stats, double* partials, unsigned int* ticket, int64_t max_partials,
+// partials: workspace for the per-env records of the fused statistics, `partial_doubles` doubles (>= 8 * envs)
+int launch_tvf_cslab(const TvfParams& p, double* stats, double* partials, unsigned int* ticket, int64_t partial_doubles,
                      const float* host_value_weights, float* value_out, int64_t value_row_stride, cudaStream_t stream,
                      bool* stats_fused) {
     *stats_fused = false;
@@ -795,7 +879,7 @@ int launch_tvf_cslab(const TvfParams& p, double* stats, double* partials, unsign
     const uint32_t nib_bytes = cs_align(static_cast<uint32_t>(q.nib_words + 24) * 4u, 128);
     const uint32_t rest = 2u * 16384u + cs_align(2u * (N + 16) * 4u, 128) + cs_align(2u * (N + 16) * 2u, 128) +
                           cs_align(static_cast<uint32_t>(V) * 4u, 128) + ftab_bytes + nib_bytes + 1024u + 128u +
-                          (2 * kCsMaxStages + 2 * kCsGroups + 4) * 8u;
+                          (2 * kCsMaxStages + 2 * kCsGroups + 4 + 8) * 8u;
     int nstage = 0;  // staging ring: as deep as shared memory allows (the TMA loads are latency bound)
     while (nstage < kCsMaxStages && slab_bytes + rest + static_cast<uint32_t>(nstage + 1) * kCsChunkBytes <= static_cast<uint32_t>(max_smem))
         ++nstage;
@@ -812,7 +896,7 @@ int launch_tvf_cslab(const TvfParams& p, double* stats, double* partials, unsign
     q.off_gpc = q.off_nib + nib_bytes;
     q.off_misc = q.off_gpc + 1024u;
     q.off_bar = q.off_misc + 128;
-    q.smem_total = q.off_bar + (2 * kCsMaxStages + 2 * kCsGroups + 4) * 8u;
+    q.smem_total = q.off_bar + (2 * kCsMaxStages + 2 * kCsGroups + 4 + 8) * 8u;
     if (q.smem_total > static_cast<uint32_t>(max_smem)) return unsupported("the env slab does not fit in shared memory");
 
     CUtensorMap vmap;  // value samples [N + 1, A, V]: 64 rows x 32 columns per load, 128-byte swizzle
@@ -835,15 +919,20 @@ int launch_tvf_cslab(const TvfParams& p, double* stats, double* partials, unsign
 
     int64_t grid = sm_count();
     if (grid > p.envs) grid = p.envs;
-    q.env_base = p.envs / grid;
-    q.env_rem = p.envs % grid;
+    {
+        // scheduler pair of this launch (zero before the first launch, zeroed again by the last CTA of every launch)
+        static std::atomic<unsigned int> launches{0};
+        unsigned int* base = nullptr;
+        PPO_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_cs_sched));
+        q.sched = base + 2 * (launches.fetch_add(1) % 64);
+    }
     q.want_value = value_out ? (host_value_weights ? 2 : 1) : 0;
     q.value_out = value_out, q.vo_rs = value_row_stride;
     memset(q.vw, 0, sizeof(q.vw));
     if (host_value_weights)
         for (int j = 0; j < V; ++j) q.vw[j] = host_value_weights[j];
-    q.want_stats = (stats && partials && ticket && grid <= max_partials) ? 1 : 0;
-    q.stats = stats, q.partials = partials, q.ticket = ticket;
+    q.want_stats = (stats && partials && ticket && partial_doubles >= 8 * p.envs) ? 1 : 0;
+    q.stats = stats, q.env_stats = partials, q.ticket = ticket;
 
     const int rc = N == 256 ? cs_launch_variant<2>(q, vmap, omap, grid, stream) : cs_launch_variant<1>(q, vmap, omap, grid, stream);
     if (rc != PPO_OK) return rc;
@@ -854,8 +943,8 @@ int launch_tvf_cslab(const TvfParams& p, double* stats, double* partials, unsign
 }  // namespace ppo
 
 // development aid: the stamps of the last launch with PPO_TVF_DEBUG bit 256 (nanoseconds, CTA 0)
-extern "C" int ppo_tvf_cslab_debug_times(unsigned long long* out512) {
+extern "C" int ppo_tvf_cslab_debug_times(unsigned long long* out832) {
     PPO_CUDA(cudaDeviceSynchronize());
-    PPO_CUDA(cudaMemcpyFromSymbol(out512, ppo::g_cs_times, sizeof(unsigned long long) * 512));
+    PPO_CUDA(cudaMemcpyFromSymbol(out832, ppo::g_cs_times, sizeof(unsigned long long) * 832));
     return PPO_OK;
 }

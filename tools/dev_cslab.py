@@ -131,7 +131,7 @@ def timing(full):
             for _ in range(3):
                 launch(lib, path, r, d, vs, ctab, out, stats, ws, ex)
             torch.cuda.synchronize()
-            ts = []
+            ts, ts3 = [], []
             for _ in range(10):
                 flush.zero_()
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -140,10 +140,19 @@ def timing(full):
                 e.record()
                 torch.cuda.synchronize()
                 ts.append(s.elapsed_time(e) * 1e3)
-            ts.sort()
+            for _ in range(5):  # back to back: the launch overhead of all but the first hides behind the previous kernel
+                flush.zero_()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                for _ in range(4):
+                    launch(lib, path, r, d, vs, ctab, out, stats, ws, ex)
+                e.record()
+                torch.cuda.synchronize()
+                ts3.append(s.elapsed_time(e) * 1e3 / 4)
+            ts.sort(), ts3.sort()
             med = ts[len(ts) // 2]
             print(f"tvf {steps}x{envs}x128 adv8 {name:6s} dbg={os.environ.get('PPO_TVF_DEBUG', '0'):3s}: med {med:8.1f} us best {ts[0]:8.1f} us "
-                  f"{nbytes / med / 1e3:6.0f} GB/s  frac {nbytes / med / 1e3 / 6548.8:.3f}", flush=True)
+                  f"{nbytes / med / 1e3:6.0f} GB/s  frac {nbytes / med / 1e3 / 6548.8:.3f} | 4 back to back: {ts3[len(ts3) // 2]:8.1f} us each", flush=True)
 
 
 def stamps():
@@ -163,12 +172,20 @@ def stamps():
     ctab, blob = rt._upload_tables(tabs, dev)
     for _ in range(2):
         launch(lib, rt.PATH_CSLAB, r, d, vs, ctab, out)
-    buf = (ctypes.c_ulonglong * 512)()
+    buf = (ctypes.c_ulonglong * 832)()
     lib.ppo_tvf_cslab_debug_times.argtypes = [ctypes.c_void_p]
     lib.ppo_tvf_cslab_debug_times(buf)
     t = np.array(buf[:], dtype=np.float64)
-    t0 = t[t > 0].min()
+    t0 = t[:512][t[:512] > 0].min()
     us = lambda i: (t[i] - t0) / 1e3 if t[i] > 0 else float("nan")
+    print("coordinators done", us(500), us(501), " consumers done", us(502), us(503))
+    st, en = t[512:512 + 148], t[672:672 + 148]
+    print("CTA start (us): min %.1f max %.1f | CTA end: min %.1f median %.1f max %.1f | duration: min %.1f median %.1f max %.1f" % (
+        (st.min() - t0) / 1e3, (st.max() - t0) / 1e3, (en.min() - t0) / 1e3, (np.median(en) - t0) / 1e3, (en.max() - t0) / 1e3,
+        (en - st).min() / 1e3, np.median(en - st) / 1e3, (en - st).max() / 1e3))
+    dur = (en - st) / 1e3
+    print("slowest CTAs:", np.argsort(-dur)[:12].tolist(), np.sort(-dur)[:12].round(1).tolist())
+    print("fastest CTAs:", np.argsort(dur)[:12].tolist(), np.sort(dur)[:12].round(1).tolist())
     for e in range(4):
         b = 64 * e
         print(f"env {e}: transform start {us(b):7.2f} rfull {us(b + 1):7.2f} | " +
