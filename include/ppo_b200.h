@@ -316,6 +316,19 @@ typedef struct {
     const float* value_weights;
     float* value_out;
     int64_t value_out_row_stride;
+    /* Optional: GAE + TD(lambda) over that value estimate in the SAME launch (rl/rollout.py:1207-1223 ->
+     * rl/returns.py:7-29 `gae`, :58-67 `td_lambda`), transposed slab kernel only.  gae_adv_out / gae_ret_out are
+     * contiguous [N, A]; gae_stats receives the PPO_STATS_LEN record of ppo_gae; gae_workspace is sized by
+     * ppo_gae_workspace_bytes(envs).  On return gae_done is 1 when the launch produced them and 0 when the caller has
+     * to run ppo_gae itself (another kernel was taken, or value_out is missing).  gae_enable == 0: ignored. */
+    int32_t gae_enable;
+    int32_t gae_done;
+    double gae_gamma, gae_lambda_adv, gae_lambda_ret;
+    float* gae_adv_out;
+    float* gae_ret_out;
+    double* gae_stats;
+    void* gae_workspace;
+    int64_t gae_workspace_bytes;
 } ppo_tvf_extras;
 
 int ppo_tvf_targets_ex(const float* rewards, int64_t reward_row_stride,
@@ -324,7 +337,7 @@ int ppo_tvf_targets_ex(const float* rewards, int64_t reward_row_stride,
                        int64_t steps, int64_t envs, int64_t n_req, int64_t n_val,
                        const ppo_tvf_tables* tables, int path,
                        float* out, double* stats, void* workspace, int64_t workspace_bytes,
-                       const ppo_tvf_extras* extras, void* stream);
+                       ppo_tvf_extras* extras, void* stream);
 
 /* Standalone forms.  ppo_value_estimate: out[b] = sum_j host_weights[j] * values[b * row_stride + j] (replaces
  * rl/tvf.py:388-433 with the weights above).  ppo_rediscount_horizons: out[b, k] = sum_{i=1..k} (V[b,i] - V[b,i-1]) *

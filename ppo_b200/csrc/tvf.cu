@@ -20,7 +20,7 @@ namespace ppo {
 
 int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsigned int* ticket, int64_t max_partials,
                      const float* host_value_weights, float* value_out, int64_t value_row_stride, cudaStream_t stream,
-                     bool* stats_fused);  // tvf_tslab.cu
+                     bool* stats_fused, const TsGae* gae, bool* gae_fused);  // tvf_tslab.cu
 int launch_tvf_cslab(const TvfParams& p, double* stats, double* partials, unsigned int* ticket, int64_t max_partials,
                      const float* host_value_weights, float* value_out, int64_t value_row_stride, cudaStream_t stream,
                      bool* stats_fused);
@@ -251,8 +251,8 @@ extern "C" int ppo_tvf_targets_ex(const float* rewards, int64_t reward_row_strid
                                   int64_t done_row_stride, const float* value_samples, int64_t vs_row_stride,
                                   int64_t vs_env_stride, int64_t steps, int64_t envs, int64_t n_req, int64_t n_val,
                                   const ppo_tvf_tables* tables, int path, float* out, double* stats,
-                                  void* workspace, int64_t workspace_bytes, const ppo_tvf_extras* extras,
-                                  void* stream) {
+                                  void* workspace, int64_t workspace_bytes, ppo_tvf_extras* extras, void* stream) {
+    if (extras) extras->gae_done = 0;
     const float* vweights = extras ? extras->value_weights : nullptr;
     float* vout = extras ? extras->value_out : nullptr;
     const int64_t vout_rs = extras && extras->value_out_row_stride > 0 ? extras->value_out_row_stride : envs;
@@ -308,7 +308,20 @@ extern "C" int ppo_tvf_targets_ex(const float* rewards, int64_t reward_row_strid
         if (rc == PPO_OK) vout = nullptr;  // the value estimate was written by the same launch
     }
     if (path == PPO_TVF_TSLAB || (path == PPO_TVF_AUTO && tables->n_entries >= 3 && rc == PPO_ERR_UNSUPPORTED)) {
-        rc = launch_tvf_tslab(p, stats, partials, ticket, kStatsBlocks, vweights, vout, vout_rs, s, &stats_fused);
+        TsGae gae{};
+        const bool ask_gae = extras && extras->gae_enable && extras->gae_adv_out && extras->gae_ret_out && extras->gae_stats &&
+                             extras->gae_workspace && extras->gae_workspace_bytes >= 256 + kStatsBlocks * PPO_STATS_LEN * 8;
+        if (ask_gae) {
+            gae.gamma = extras->gae_gamma, gae.lambda_adv = extras->gae_lambda_adv, gae.lambda_ret = extras->gae_lambda_ret;
+            gae.adv = extras->gae_adv_out, gae.ret = extras->gae_ret_out, gae.stats = extras->gae_stats;
+            gae.ticket = static_cast<unsigned int*>(extras->gae_workspace);
+            gae.partials = reinterpret_cast<double*>(static_cast<char*>(extras->gae_workspace) + 256);
+            gae.max_partials = kStatsBlocks;
+        }
+        bool gae_fused = false;
+        rc = launch_tvf_tslab(p, stats, partials, ticket, kStatsBlocks, vweights, vout, vout_rs, s, &stats_fused,
+                              ask_gae ? &gae : nullptr, &gae_fused);
+        if (rc == PPO_OK && gae_fused) extras->gae_done = 1;
         if (path == PPO_TVF_TSLAB && rc != PPO_OK) return rc;
         taken = PPO_TVF_TSLAB;
         if (rc == PPO_OK) vout = nullptr;  // the value estimate was written by the same launch

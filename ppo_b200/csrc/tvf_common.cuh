@@ -36,6 +36,17 @@ struct __align__(16) TsHorizon {
     int32_t maxn;      // largest n-step of the horizon (tail rows: N - t < maxn)
 };
 
+// Optional GAE + TD(lambda) stage fused into the transposed slab launch (host-side description).
+struct TsGae {
+    double gamma, lambda_adv, lambda_ret;
+    float* adv;            // [N, A] contiguous
+    float* ret;
+    double* stats;         // PPO_STATS_LEN doubles
+    double* partials;      // [max_partials][PPO_STATS_LEN]
+    unsigned int* ticket;  // zero on entry, zero again on exit
+    int64_t max_partials;
+};
+
 // Launch constants of the column slab kernel (tvf_cslab.cu), resolved on the host by ppo_tvf_tables_build.
 // A consumer thread of that kernel owns aligned groups of four consecutive time rows and gathers with 16-byte loads,
 // so an entry (horizon, n-step) is described by the aligned row group it reads ("bin" m = (n - 1) / 4: slab rows

@@ -59,6 +59,17 @@ struct TsParams {
     double* partials;  // [grid][8] per-CTA statistics of the longest horizon (want_stats)
     unsigned int* ticket;
     double* stats;
+    // fused GAE + TD(lambda) over the value estimate of the same launch (rl/rollout.py:1207-1223, rl/returns.py:7-29,
+    // 58-67): the scan warp runs the two float64 recurrences of an env once its value column is complete
+    int want_gae, gae_same_lambda;
+    float gae_gamma32;       // gamma as the float32 scalar of `gamma * value_next_t` (rl/returns.py:26)
+    double gae_gl_adv, gae_gl_ret;  // gamma * lambda (float64 products, rl/returns.py:27)
+    float* gae_adv;          // [N, A] contiguous
+    float* gae_ret;
+    double* gae_partials;    // [grid][PPO_STATS_LEN]
+    unsigned int* gae_ticket;
+    double* gae_stats;       // PPO_STATS_LEN doubles
+    uint32_t off_val;        // three value columns [N + 1] in shared memory (env e uses slot e % 3)
     const TsHorizon* hz;  // [K] device copies of the launch constants (inside the packed table blob)
     const TsEntry* ent;   // [n_ent]
     const uint4* tail4;   // [K][tail_pitch] folded tail records {idx lo | hi << 16, cwlo, cwhi, 0}
@@ -217,6 +228,8 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
     const uint32_t lim_a = smem_u32(smem + q.off_lim);
     const uint32_t fr_a = smem_u32(smem + q.off_fr);
     const uint32_t rt_bytes = static_cast<uint32_t>(q.rt_words) * 4u;
+    const uint32_t val_a = smem_u32(smem + q.off_val);
+    const int val_pitch = q.rt_words;  // >= N + 1
 
     const int64_t bidx = blockIdx.x;
     const int nenv = static_cast<int>(q.env_base + (bidx < q.env_rem ? 1 : 0));
@@ -337,6 +350,65 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
         // ------------------------------------------------------------------ scan warp: R(t) and lim(t) per env
         const int RPL = NC;  // rows per lane, lane l owns rows [l * RPL, (l + 1) * RPL)
         const double gamma = q.gamma;
+        // statistics of the fused GAE stage (this warp sees every env of the CTA)
+        double gs_n = 0, gs_sa = 0, gs_qa = 0, gs_sr = 0, gs_qr = 0, gs_sv = 0, gs_qv = 0, gs_nv = 0, gs_za = 0, gs_zr = 0;
+        float gs_mna = INFINITY, gs_mxa = -INFINITY, gs_mnr = INFINITY, gs_mxr = -INFINITY;
+        // GAE + TD(lambda) of one env: x_t = delta_t + gamma * lambda * nt_t * x_{t+1} with float64 carries and the
+        // reference's operation order (rl/returns.py:26-28); lane l owns rows [l * RPL, (l + 1) * RPL), the carries
+        // cross the lanes as a suffix scan of affine maps.  Rewards / terminals are read again (they left the
+        // registers two envs ago; the lines are still in L2).
+        auto gae_env = [&](int e2) {
+            load_columns(e2);
+            const uint32_t va = val_a + static_cast<uint32_t>((e2 % 3) * val_pitch) * 4u;
+            const int64_t env = env0 + e2;
+            auto step = [&](float rw, float vv, float vn, bool dn_, double& xa, double& xr) {
+                const double boot = dn_ ? 0.0 : static_cast<double>(__fmul_rn(q.gae_gamma32, vn));
+                const double delta = __dsub_rn(__dadd_rn(static_cast<double>(rw), boot), static_cast<double>(vv));
+                xa = __dadd_rn(delta, __dmul_rn(dn_ ? 0.0 : q.gae_gl_adv, xa));
+                xr = __dadd_rn(delta, __dmul_rn(dn_ ? 0.0 : q.gae_gl_ret, xr));
+            };
+            double ba = 0, ca = 1, br = 0, cr = 1;
+#pragma unroll
+            for (int i = kTsMaxChunks - 1; i >= 0; --i) {
+                const int row = lane * RPL + i;
+                if (i < RPL && row < N) {
+                    const bool dn_ = p.done_kind == PPO_DONE_F32 ? (__uint_as_float(dw[i]) != 0.f) : (dw[i] != 0u);
+                    const float vv = ts_lds(va + static_cast<uint32_t>(row) * 4u), vn = ts_lds(va + static_cast<uint32_t>(row + 1) * 4u);
+                    step(rr[i], vv, vn, dn_, ba, br);
+                    ca *= dn_ ? 0.0 : q.gae_gl_adv;
+                    cr *= dn_ ? 0.0 : q.gae_gl_ret;
+                }
+            }
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double ba2 = shfl_down_f64(ba, d), ca2 = shfl_down_f64(ca, d);
+                const double br2 = shfl_down_f64(br, d), cr2 = shfl_down_f64(cr, d);
+                if (lane + d < 32) {
+                    ba = ba + ca * ba2, ca = ca * ca2;
+                    br = br + cr * br2, cr = cr * cr2;
+                }
+            }
+            double xa = shfl_down_f64(ba, 1), xr = shfl_down_f64(br, 1);  // carry into this lane's last row
+            if (lane == 31) xa = 0.0, xr = 0.0;
+#pragma unroll
+            for (int i = kTsMaxChunks - 1; i >= 0; --i) {
+                const int row = lane * RPL + i;
+                if (i < RPL && row < N) {
+                    const bool dn_ = p.done_kind == PPO_DONE_F32 ? (__uint_as_float(dw[i]) != 0.f) : (dw[i] != 0u);
+                    const float vv = ts_lds(va + static_cast<uint32_t>(row) * 4u), vn = ts_lds(va + static_cast<uint32_t>(row + 1) * 4u);
+                    step(rr[i], vv, vn, dn_, xa, xr);
+                    const float a = static_cast<float>(xa);
+                    const float t = __fadd_rn(static_cast<float>(xr), vv);  // rl/returns.py:66-67
+                    q.gae_adv[static_cast<int64_t>(row) * p.envs + env] = a;
+                    q.gae_ret[static_cast<int64_t>(row) * p.envs + env] = t;
+                    gs_n += 1.0, gs_sa += a, gs_qa += static_cast<double>(a) * a, gs_sr += t, gs_qr += static_cast<double>(t) * t;
+                    gs_za += a == 0.f ? 1.0 : 0.0, gs_zr += t == 0.f ? 1.0 : 0.0;
+                    gs_mna = fminf(gs_mna, a), gs_mxa = fmaxf(gs_mxa, a), gs_mnr = fminf(gs_mnr, t), gs_mxr = fmaxf(gs_mxr, t);
+                    gs_sv += vv, gs_qv += static_cast<double>(vv) * vv, gs_nv += 1.0;
+                    if (row == N - 1) gs_sv += vn, gs_qv += static_cast<double>(vn) * vn, gs_nv += 1.0;  // the final estimate, row N
+                }
+            }
+        };
         for (int e = 0; e < nenv; ++e) {
             const uint32_t par = static_cast<uint32_t>(e & 1);
             if (e > 0) load_columns(e);
@@ -389,6 +461,50 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
             __syncwarp();
             if (lane == 0) mbar_arrive(&rfull[par]);
             if (lane == 0 && e == 0) ts_stamp(q, 2);  // first R / lim tables ready
+            // env e - 2 has left the pipeline (its tables were released above): its value column is complete
+            if (q.want_gae && e >= 2) gae_env(e - 2);
+        }
+        if (q.want_gae) {
+            for (int e2 = nenv > 2 ? nenv - 2 : 0; e2 < nenv; ++e2) {
+                mbar_wait_sleep(&rempty[e2 & 1], (static_cast<uint32_t>(e2) >> 1) & 1u, 4 * kTsPollNs);
+                gae_env(e2);
+            }
+            // per-CTA record, then the last CTA folds all records in index order (deterministic, no float atomics)
+            double rec[PPO_STATS_LEN];
+#pragma unroll
+            for (int j = 0; j < PPO_STATS_LEN; ++j) rec[j] = 0.0;
+            rec[PPO_STAT_COUNT] = warp_sum_f64(gs_n), rec[PPO_STAT_ADV_SUM] = warp_sum_f64(gs_sa);
+            rec[PPO_STAT_ADV_SUMSQ] = warp_sum_f64(gs_qa), rec[PPO_STAT_RET_SUM] = warp_sum_f64(gs_sr);
+            rec[PPO_STAT_RET_SUMSQ] = warp_sum_f64(gs_qr), rec[PPO_STAT_VAL_SUM] = warp_sum_f64(gs_sv);
+            rec[PPO_STAT_VAL_SUMSQ] = warp_sum_f64(gs_qv), rec[PPO_STAT_VAL_COUNT] = warp_sum_f64(gs_nv);
+            rec[PPO_STAT_ADV_ZEROS] = warp_sum_f64(gs_za), rec[PPO_STAT_RET_ZEROS] = warp_sum_f64(gs_zr);
+            rec[PPO_STAT_ADV_MIN] = warp_min_f32(gs_mna), rec[PPO_STAT_ADV_MAX] = warp_max_f32(gs_mxa);
+            rec[PPO_STAT_RET_MIN] = warp_min_f32(gs_mnr), rec[PPO_STAT_RET_MAX] = warp_max_f32(gs_mxr);
+            int last = 0;
+            if (lane == 0) {
+                double* out = q.gae_partials + static_cast<int64_t>(blockIdx.x) * PPO_STATS_LEN;
+#pragma unroll
+                for (int j = 0; j < PPO_STATS_LEN; ++j) out[j] = rec[j];
+                __threadfence();
+                last = atomicAdd(q.gae_ticket, 1u) == gridDim.x - 1;
+            }
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
+                __threadfence();
+                if (lane < PPO_STATS_LEN) {
+                    const int j = lane;
+                    const bool is_min = j == PPO_STAT_ADV_MIN || j == PPO_STAT_RET_MIN;
+                    const bool is_max = j == PPO_STAT_ADV_MAX || j == PPO_STAT_RET_MAX;
+                    double acc = is_min ? INFINITY : is_max ? -INFINITY : 0.0;
+                    for (unsigned int b = 0; b < gridDim.x; ++b) {
+                        const double x = __ldcg(q.gae_partials + static_cast<int64_t>(b) * PPO_STATS_LEN + j);
+                        acc = is_min ? fmin(acc, x) : is_max ? fmax(acc, x) : acc + x;
+                    }
+                    q.gae_stats[j] = j <= PPO_STAT_RET_ZEROS ? acc : 0.0;
+                }
+                __syncwarp();
+                if (lane == 0) *q.gae_ticket = 0u;
+            }
         }
     } else if (warp >= kTsConsumers) {
         // ------------------------------------------------------------------ transform warps
@@ -402,6 +518,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
         for (int cg = 0; cg < V / 32; ++cg) vw[cg] = q.want_value == 2 ? q.vw[cg * 32 + lane] : 0.f;
         for (int e = 0; e < nenv; ++e) {
             const uint32_t par = static_cast<uint32_t>(e & 1);
+            float row0_val = 0.f;
             if (q.want_value && xw == 0) {
                 // row 0 is not part of the slab (no target bootstraps from it): straight from global memory
                 const float* row0 = p.vs + (env0 + e) * p.vs_es;
@@ -416,8 +533,11 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                     for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
                 }
                 if (lane == 31) q.value_out[env0 + e] = acc;
+                row0_val = acc;
             }
             mbar_wait_sleep(&rfull[par], (static_cast<uint32_t>(e) >> 1) & 1u, kTsPollNs);
+            // (the value column slot e % 3 was read by the GAE stage of env e - 3, which ran before these tables were released)
+            if (q.want_gae && xw == 0 && lane == 31) ts_sts(val_a + static_cast<uint32_t>((e % 3) * val_pitch) * 4u, row0_val);
             const uint32_t rt = rt_a + par * rt_bytes;
             // slab of this env; it was last used by env e - nslab (the j-th use of a slab waits for use j - 1)
             const int sl = e % q.nslab;
@@ -475,12 +595,18 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                     k1 += __shfl_xor_sync(0xffffffffu, k1, 1);
                     const int rl = (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0);
                     const int i = c * kTsRows + xw + rl * kTsXform;
-                    if ((lane & 3) == 0 && i < N) q.value_out[static_cast<int64_t>(i + 1) * q.vo_rs + env0 + e] = k1;
+                    if ((lane & 3) == 0 && i < N) {
+                        q.value_out[static_cast<int64_t>(i + 1) * q.vo_rs + env0 + e] = k1;
+                        if (q.want_gae) ts_sts(val_a + static_cast<uint32_t>((e % 3) * val_pitch + i + 1) * 4u, k1);
+                    }
                 } else if (q.want_value == 1 && lane == 31) {
 #pragma unroll
                     for (int rl = 0; rl < kTsRows / kTsXform; ++rl) {
                         const int i = c * kTsRows + xw + rl * kTsXform;
-                        if (i < N) q.value_out[static_cast<int64_t>(i + 1) * q.vo_rs + env0 + e] = part[rl];
+                        if (i < N) {
+                            q.value_out[static_cast<int64_t>(i + 1) * q.vo_rs + env0 + e] = part[rl];
+                            if (q.want_gae) ts_sts(val_a + static_cast<uint32_t>((e % 3) * val_pitch + i + 1) * 4u, part[rl]);
+                        }
                     }
                 }
                 if (xw == 0) {  // the -R column (index V); column V + 1 stays zero
@@ -708,8 +834,9 @@ static int ts_launch_variant(const TsParams& q, const CUtensorMap& vmap, const C
 // stats / partials / ticket: optional fused statistics of the longest horizon (workspace layout of tvf.cu).
 int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsigned int* ticket, int64_t max_partials,
                      const float* host_value_weights, float* value_out, int64_t value_row_stride, cudaStream_t stream,
-                     bool* stats_fused) {
+                     bool* stats_fused, const TsGae* gae, bool* gae_fused) {
     *stats_fused = false;
+    if (gae_fused) *gae_fused = false;
     const int N = p.steps, K = p.n_req, V = p.n_val, nmax = p.tab.nmax, E = p.tab.n_entries;
     auto unsupported = [&](const char* why) {
         set_error("ppo_tvf_targets: transposed slab kernel unavailable: %s", why);
@@ -769,7 +896,10 @@ int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsign
     const uint32_t rt_bytes = ts_align(2u * q.rt_words * 4u, 128);
     const uint32_t fr_bytes = ts_align(2u * static_cast<uint32_t>(V) * 4u, 128);
     const uint32_t bar_bytes = (8u + 2 * kTsMaxChunks + 2 * kTsMaxSteps + 4 + 2) * 8u;
-    const uint32_t rest = ot_bytes + ent_bytes + hz_bytes + 2 * rt_bytes + fr_bytes + bar_bytes;
+    const bool with_gae = gae && gae->adv && gae->ret && gae->stats && gae->partials && gae->ticket && value_out &&
+                          sm_count() <= gae->max_partials;
+    const uint32_t val_bytes = with_gae ? ts_align(3u * q.rt_words * 4u, 128) : 0u;
+    const uint32_t rest = ot_bytes + ent_bytes + hz_bytes + 2 * rt_bytes + fr_bytes + val_bytes + bar_bytes;
     // two slabs when they fit beside two staging chunks: the next env is transposed while this one is evaluated
     // (with one slab the replacement is in place, which stalls when the n-step window is as long as the rollout)
     q.nslab = (2 * wt_bytes + rest + 2 * chunk <= static_cast<uint32_t>(max_smem)) ? 2 : 1;
@@ -786,8 +916,17 @@ int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsign
     q.off_rtab = q.off_hz + hz_bytes;
     q.off_lim = q.off_rtab + rt_bytes;
     q.off_fr = q.off_lim + rt_bytes;
-    q.off_bar = q.off_fr + fr_bytes;
+    q.off_val = q.off_fr + fr_bytes;
+    q.off_bar = q.off_val + val_bytes;
     q.smem_total = q.off_bar + bar_bytes;
+    q.want_gae = with_gae ? 1 : 0;
+    if (with_gae) {
+        q.gae_gamma32 = static_cast<float>(gae->gamma);
+        q.gae_gl_adv = gae->gamma * gae->lambda_adv, q.gae_gl_ret = gae->gamma * gae->lambda_ret;
+        q.gae_same_lambda = q.gae_gl_adv == q.gae_gl_ret;
+        q.gae_adv = gae->adv, q.gae_ret = gae->ret, q.gae_stats = gae->stats;
+        q.gae_partials = gae->partials, q.gae_ticket = gae->ticket;
+    }
 
     CUtensorMap vmap;
     const uint64_t dims[3] = {static_cast<uint64_t>(V), static_cast<uint64_t>(p.envs), static_cast<uint64_t>(N) + 1};
@@ -824,6 +963,7 @@ int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsign
     else rc = ts_launch_variant<32, 0>(q, vmap, omap, grid, stream);
     if (rc != PPO_OK) return rc;
     *stats_fused = q.want_stats != 0;
+    if (gae_fused) *gae_fused = q.want_gae != 0;
     return PPO_OK;
 }
 

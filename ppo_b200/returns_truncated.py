@@ -41,16 +41,28 @@ class _CLayout(ctypes.Structure):
 class _CExtras(ctypes.Structure):
     """``ppo_tvf_extras`` of include/ppo_b200.h."""
     _fields_ = [("value_weights", ctypes.c_void_p), ("value_out", ctypes.c_void_p),
-                ("value_out_row_stride", ctypes.c_int64)]
+                ("value_out_row_stride", ctypes.c_int64),
+                ("gae_enable", ctypes.c_int32), ("gae_done", ctypes.c_int32),
+                ("gae_gamma", ctypes.c_double), ("gae_lambda_adv", ctypes.c_double), ("gae_lambda_ret", ctypes.c_double),
+                ("gae_adv_out", ctypes.c_void_p), ("gae_ret_out", ctypes.c_void_p), ("gae_stats", ctypes.c_void_p),
+                ("gae_workspace", ctypes.c_void_p), ("gae_workspace_bytes", ctypes.c_int64)]
 
 
-def _extras(value_out, value_weights, env_offset=0):
+def _extras(value_out, value_weights, env_offset=0, gae=None):
     """ctypes extras for ``ppo_tvf_targets_ex`` (or None): ``value_out`` is a device ``[N+1, A]`` float32 tensor that
     receives the value estimate of the env block starting at ``env_offset``; ``value_weights`` a float32 NumPy
-    vector ``[V]`` (rediscount weights, ``tvf.rediscount_weights``) or None for the last value horizon."""
+    vector ``[V]`` (rediscount weights, ``tvf.rediscount_weights``) or None for the last value horizon.
+    ``gae``: optional dict(gamma, lambda_adv, lambda_ret, adv, ret, stats, workspace) of device tensors -- GAE and
+    TD(lambda) over the value estimate in the same launch (check ``extras.gae_done`` after the call)."""
     if value_out is None:
         return None, None
     x = _CExtras()
+    if gae is not None:
+        x.gae_enable = 1
+        x.gae_gamma, x.gae_lambda_adv, x.gae_lambda_ret = float(gae["gamma"]), float(gae["lambda_adv"]), float(gae["lambda_ret"])
+        x.gae_adv_out, x.gae_ret_out = gae["adv"].data_ptr(), gae["ret"].data_ptr()
+        x.gae_stats, x.gae_workspace = gae["stats"].data_ptr(), gae["workspace"].data_ptr()
+        x.gae_workspace_bytes = gae["workspace"].numel()
     keep = None
     if value_weights is not None:
         keep = np.ascontiguousarray(value_weights, dtype=np.float32)

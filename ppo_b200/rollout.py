@@ -351,6 +351,8 @@ class ReturnPass:
                 box = PeerMailbox(self.device, group)
                 self.peers = box if box.ok else None
         self._ctab = self._blob = None
+        self.fuse_gae = os.environ.get("PPO_FUSE_GAE", "1") != "0"
+        self.gae_fused = False
         self.kernel_launches_per_pass = 4
         self._tvf_launches = 2
         self.tvf_kernel = "?"
@@ -394,7 +396,7 @@ class ReturnPass:
                 self.ws_tvf.data_ptr(), self.ws_tvf.numel(), ctypes.byref(extras) if extras is not None else None, s)
             _lib.check(rc, "ppo_tvf_targets")
             last = lib.ppo_tvf_last_path()
-            self.tvf_kernel = {1: "generic", 2: "ring", 3: "tslab"}.get(last & 0xff, "?")
+            self.tvf_kernel = {1: "generic", 2: "ring", 3: "tslab", 4: "cslab"}.get(last & 0xff, "?")
             self._tvf_launches = 1 + (0 if last & 0x100 else 1) + (1 if extras is not None and not last & 0x200 else 0)
             if tvf_events is not None:
                 tvf_events[1].record()
@@ -405,9 +407,24 @@ class ReturnPass:
                 self.value_estimates = torch.empty((n + 1, a), dtype=torch.float32, device=self.device)
                 self._value_weights = None if abs(self.gamma - self.tvf_gamma) < 1e-8 else \
                     _tvf.rediscount_weights(self.tvf_gamma, self.gamma, [int(h) for h in self.horizons])
-            extras, _keep = _rt._extras(self.value_estimates, self._value_weights)
+            # GAE + TD(lambda) + their statistics ride on the same launch (the kernel's scan warp runs the two
+            # recurrences of an env as soon as its value column is complete): what is left is the normalisation
+            gae_req = dict(gamma=self.gamma, lambda_adv=self.lambda_policy, lambda_ret=self.lambda_value,
+                           adv=self.advantage, ret=self.ext_returns, stats=self.stats, workspace=self.ws_gae) \
+                if self.fuse_gae else None
+            extras, _keep = _rt._extras(self.value_estimates, self._value_weights, gae=gae_req)
             targets(extras)
             values = self.value_estimates
+            if extras.gae_done:
+                if self.sharded:
+                    dist.all_reduce(self._moments, op=dist.ReduceOp.SUM, group=self.group)
+                rc = lib.ppo_adv_normalize(self.advantage.data_ptr(), n * a, self.stats.data_ptr(), self.eps, self.clip,
+                                           self.advantages.data_ptr(), s)
+                _lib.check(rc, "ppo_adv_normalize")
+                self.gae_fused = True
+                self.kernel_launches_per_pass = self._tvf_launches + 1
+                return self
+        self.gae_fused = False
         gae_launches = 2
         peer_rc = 0
         if self.sharded and self.peers is not None and values.stride(1) == 1:

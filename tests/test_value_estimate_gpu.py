@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import oracle
-from ppo_b200 import _lib, rollout, synthetic
+from ppo_b200 import _lib, returns, rollout, synthetic
 from ppo_b200 import returns_truncated as rt
 from ppo_b200 import tvf
 from util import TOL, rel_err
@@ -88,7 +88,8 @@ def test_return_pass_with_values_from_the_curves(gamma):
     rp.set_samples(table)
     rp.run(torch.from_numpy(r).cuda(), None, torch.from_numpy(d).cuda().view(torch.uint8), torch.from_numpy(vs).cuda())
     torch.cuda.synchronize()
-    assert rp.tvf_kernel == "tslab" and rp.kernel_launches_per_pass == 2  # targets (+ by-products), GAE + normalisation
+    # targets (+ value estimate, GAE, TD(lambda) and both statistics records as by-products), normalisation
+    assert rp.tvf_kernel == "tslab" and rp.kernel_launches_per_pass == 2 and rp.gae_fused
     values = oracle.get_rediscounted_value_estimate(vs.reshape(-1, len(hz)), tvf_gamma, gamma, hz).reshape(steps + 1, envs)
     assert rel_err(rp.value_estimates.cpu().numpy(), values) <= TOL
     got_v = rp.value_estimates.cpu().numpy()  # GAE parity on the estimate the device actually used
@@ -96,17 +97,38 @@ def test_return_pass_with_values_from_the_curves(gamma):
     assert rel_err(rp.ext_returns.cpu().numpy(), oracle.td_lambda(r, got_v[:-1], got_v[-1], d, gamma, 0.9)) <= TOL
     ref = oracle.sampled_return_multi(tvf_gamma, r, d, hz, hz, vs, n_step_samples=table)
     assert rel_err(rp.tvf_returns.cpu().numpy(), ref) <= TOL
+    # the fused GAE stage against the stand-alone kernels on the same estimate: outputs within one float32 ulp (the
+    # float64 carries are composed in a different order), statistics of exactly these outputs
+    adv, ret = rp.advantage.cpu().numpy(), rp.ext_returns.cpu().numpy()
+    ref_adv = returns.gae(r, got_v[:-1], got_v[-1], d, gamma, 0.95)
+    ref_ret = returns.td_lambda(r, got_v[:-1], got_v[-1], d, gamma, 0.9)
+    assert np.abs(adv - ref_adv).max() <= np.spacing(np.abs(ref_adv).max()) and np.abs(ret - ref_ret).max() <= np.spacing(np.abs(ref_ret).max())
+    st = rp.stats.cpu().numpy()
+    a64, r64, v64 = adv.astype(np.float64), ret.astype(np.float64), got_v.astype(np.float64)
+    assert st[0] == adv.size and st[3] == adv.min() and st[4] == adv.max() and st[7] == ret.min() and st[8] == ret.max()
+    assert st[11] == got_v.size and st[12] == np.count_nonzero(adv == 0) and st[13] == np.count_nonzero(ret == 0)
+    np.testing.assert_allclose([st[1], st[2], st[5], st[6], st[9], st[10]],
+                               [a64.sum(), (a64 ** 2).sum(), r64.sum(), (r64 ** 2).sum(), v64.sum(), (v64 ** 2).sum()], rtol=1e-11)
+    assert rel_err(rp.advantages.cpu().numpy(), oracle.normalize_advantages(adv)) <= TOL
+    # ... and with the fusion switched off (separate GAE launch) the pass gives the same results within that ulp
+    rp2 = rollout.ReturnPass(steps, envs, hz, gamma, tvf_gamma, 0.95, 0.9)
+    rp2.fuse_gae = False
+    rp2.set_samples(table)
+    rp2.run(torch.from_numpy(r).cuda(), None, torch.from_numpy(d).cuda().view(torch.uint8), torch.from_numpy(vs).cuda())
+    torch.cuda.synchronize()
+    assert not rp2.gae_fused and torch.equal(rp2.tvf_returns, rp.tvf_returns)
+    assert np.abs(rp2.advantage.cpu().numpy() - adv).max() <= np.spacing(np.abs(adv).max())
     # the same through calculate_returns, NumPy buffers and pinned host buffers (env-blocked pipeline)
     kw = dict(value_samples=vs, horizons=hz, gamma=tvf_gamma, mode="advanced", distribution="exponential", n_step=20,
               max_samples=8, seed=1)
     res = rollout.calculate_returns(r, None, d, gamma, 0.95, 0.9, tvf=kw)
-    assert np.array_equal(res["advantage"], rp.advantage.cpu().numpy())
+    assert np.abs(res["advantage"] - adv).max() <= np.spacing(np.abs(adv).max())
     assert np.array_equal(res["tvf_returns"], rp.tvf_returns.cpu().numpy())
     pinned = dict(kw, value_samples=torch.from_numpy(vs).pin_memory())
     out = {"tvf_returns": torch.empty((steps, envs, len(hz))).pin_memory(), "advantage": torch.empty((steps, envs)).pin_memory()}
     res2 = rollout.calculate_returns(torch.from_numpy(r).pin_memory(), None, torch.from_numpy(d).pin_memory(), gamma,
                                      0.95, 0.9, tvf=pinned, out=out)
-    assert torch.equal(out["advantage"], rp.advantage.cpu()) and torch.equal(out["tvf_returns"], rp.tvf_returns.cpu())
+    assert torch.equal(out["advantage"], torch.from_numpy(res["advantage"])) and torch.equal(out["tvf_returns"], rp.tvf_returns.cpu())
     assert torch.equal(res2["value_estimates"].cpu(), rp.value_estimates.cpu())
 
 
