@@ -69,7 +69,8 @@ struct TsParams {
     double* gae_partials;    // [grid][PPO_STATS_LEN]
     unsigned int* gae_ticket;
     double* gae_stats;       // PPO_STATS_LEN doubles
-    uint32_t off_val;        // three value columns [N + 1] in shared memory (env e uses slot e % 3)
+    uint32_t off_val;        // three slots of {value column, rewards + alive bits} in shared memory (env e uses slot e % 3)
+    int val_pitch;           // words per array
     const TsHorizon* hz;  // [K] device copies of the launch constants (inside the packed table blob)
     const TsEntry* ent;   // [n_ent]
     const uint4* tail4;   // [K][tail_pitch] folded tail records {idx lo | hi << 16, cwlo, cwhi, 0}
@@ -228,8 +229,14 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
     const uint32_t lim_a = smem_u32(smem + q.off_lim);
     const uint32_t fr_a = smem_u32(smem + q.off_fr);
     const uint32_t rt_bytes = static_cast<uint32_t>(q.rt_words) * 4u;
+    // fused GAE stage: three slots (env e uses slot e % 3) of {value column [N + 1], rewards [N], alive mask [N]}; row r
+    // lives at word r + (r >> gsh), which spreads the rows of a lane (stride rows-per-lane) over the banks
     const uint32_t val_a = smem_u32(smem + q.off_val);
-    const int val_pitch = q.rt_words;  // >= N + 1
+    const int val_pitch = q.val_pitch;  // words per array: N + 1 rows, padded, + the alive bits (one word per 32 rows)
+    const int gsh = (NC & (NC - 1)) == 0 && NC > 1 ? 31 - __clz(NC) : 31;
+    auto gpad = [&](int r) { return static_cast<uint32_t>(r + (r >> gsh)) * 4u; };
+    auto gslot = [&](int e, int which) { return val_a + static_cast<uint32_t>(((e % 3) * 2 + which) * val_pitch) * 4u; };
+    const uint32_t gbits = gpad(N + 2);  // byte offset of the terminal bits inside array 1
 
     const int64_t bidx = blockIdx.x;
     const int nenv = static_cast<int>(q.env_base + (bidx < q.env_rem ? 1 : 0));
@@ -358,8 +365,14 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
         // cross the lanes as a suffix scan of affine maps.  Rewards / terminals are read again (they left the
         // registers two envs ago; the lines are still in L2).
         auto gae_env = [&](int e2) {
-            load_columns(e2);
-            const uint32_t va = val_a + static_cast<uint32_t>((e2 % 3) * val_pitch) * 4u;
+            if (q.dbg & 1024) return;
+            const uint32_t va = gslot(e2, 0), ra = gslot(e2, 1);
+            // terminal bits of this lane's rows, bit i = row lane * RPL + i
+            uint32_t dbits;
+            if (RPL <= 32 && (RPL & (RPL - 1)) == 0)
+                dbits = static_cast<uint32_t>(ts_lds_s32(ra + gbits + static_cast<uint32_t>((lane * RPL) >> 5) * 4u)) >> ((lane * RPL) & 31);
+            else
+                dbits = static_cast<uint32_t>(ts_lds_s32(ra + gbits + static_cast<uint32_t>(lane) * 4u));
             const int64_t env = env0 + e2;
             auto step = [&](float rw, float vv, float vn, bool dn_, double& xa, double& xr) {
                 const double boot = dn_ ? 0.0 : static_cast<double>(__fmul_rn(q.gae_gamma32, vn));
@@ -367,19 +380,16 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                 xa = __dadd_rn(delta, __dmul_rn(dn_ ? 0.0 : q.gae_gl_adv, xa));
                 xr = __dadd_rn(delta, __dmul_rn(dn_ ? 0.0 : q.gae_gl_ret, xr));
             };
+            const int r0 = lane * RPL, r1 = min(r0 + RPL, N);  // this lane's rows [r0, r1)
             double ba = 0, ca = 1, br = 0, cr = 1;
-#pragma unroll
-            for (int i = kTsMaxChunks - 1; i >= 0; --i) {
-                const int row = lane * RPL + i;
-                if (i < RPL && row < N) {
-                    const bool dn_ = p.done_kind == PPO_DONE_F32 ? (__uint_as_float(dw[i]) != 0.f) : (dw[i] != 0u);
-                    const float vv = ts_lds(va + static_cast<uint32_t>(row) * 4u), vn = ts_lds(va + static_cast<uint32_t>(row + 1) * 4u);
-                    step(rr[i], vv, vn, dn_, ba, br);
-                    ca *= dn_ ? 0.0 : q.gae_gl_adv;
-                    cr *= dn_ ? 0.0 : q.gae_gl_ret;
-                }
+#pragma unroll 1  // compact code: this runs once per env beside the consumers' hot loop (instruction cache)
+            for (int row = r1 - 1; row >= r0; --row) {
+                const bool dn_ = (dbits >> (row - r0)) & 1u;
+                step(ts_lds(ra + gpad(row)), ts_lds(va + gpad(row)), ts_lds(va + gpad(row + 1)), dn_, ba, br);
+                ca *= dn_ ? 0.0 : q.gae_gl_adv;
+                cr *= dn_ ? 0.0 : q.gae_gl_ret;
             }
-#pragma unroll
+#pragma unroll 1
             for (int d = 1; d < 32; d <<= 1) {
                 const double ba2 = shfl_down_f64(ba, d), ca2 = shfl_down_f64(ca, d);
                 const double br2 = shfl_down_f64(br, d), cr2 = shfl_down_f64(cr, d);
@@ -390,27 +400,30 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
             }
             double xa = shfl_down_f64(ba, 1), xr = shfl_down_f64(br, 1);  // carry into this lane's last row
             if (lane == 31) xa = 0.0, xr = 0.0;
-#pragma unroll
-            for (int i = kTsMaxChunks - 1; i >= 0; --i) {
-                const int row = lane * RPL + i;
-                if (i < RPL && row < N) {
-                    const bool dn_ = p.done_kind == PPO_DONE_F32 ? (__uint_as_float(dw[i]) != 0.f) : (dw[i] != 0u);
-                    const float vv = ts_lds(va + static_cast<uint32_t>(row) * 4u), vn = ts_lds(va + static_cast<uint32_t>(row + 1) * 4u);
-                    step(rr[i], vv, vn, dn_, xa, xr);
-                    const float a = static_cast<float>(xa);
-                    const float t = __fadd_rn(static_cast<float>(xr), vv);  // rl/returns.py:66-67
-                    q.gae_adv[static_cast<int64_t>(row) * p.envs + env] = a;
-                    q.gae_ret[static_cast<int64_t>(row) * p.envs + env] = t;
-                    gs_n += 1.0, gs_sa += a, gs_qa += static_cast<double>(a) * a, gs_sr += t, gs_qr += static_cast<double>(t) * t;
-                    gs_za += a == 0.f ? 1.0 : 0.0, gs_zr += t == 0.f ? 1.0 : 0.0;
-                    gs_mna = fminf(gs_mna, a), gs_mxa = fmaxf(gs_mxa, a), gs_mnr = fminf(gs_mnr, t), gs_mxr = fmaxf(gs_mxr, t);
-                    gs_sv += vv, gs_qv += static_cast<double>(vv) * vv, gs_nv += 1.0;
-                    if (row == N - 1) gs_sv += vn, gs_qv += static_cast<double>(vn) * vn, gs_nv += 1.0;  // the final estimate, row N
-                }
+#pragma unroll 1
+            for (int row = r1 - 1; row >= r0; --row) {
+                const bool dn_ = (dbits >> (row - r0)) & 1u;
+                const float vv = ts_lds(va + gpad(row)), vn = ts_lds(va + gpad(row + 1));
+                step(ts_lds(ra + gpad(row)), vv, vn, dn_, xa, xr);
+                const float a = static_cast<float>(xa);
+                const float t = __fadd_rn(static_cast<float>(xr), vv);  // rl/returns.py:66-67
+                q.gae_adv[static_cast<int64_t>(row) * p.envs + env] = a;
+                q.gae_ret[static_cast<int64_t>(row) * p.envs + env] = t;
+                gs_n += 1.0, gs_sa += a, gs_qa += static_cast<double>(a) * a, gs_sr += t, gs_qr += static_cast<double>(t) * t;
+                gs_za += a == 0.f ? 1.0 : 0.0, gs_zr += t == 0.f ? 1.0 : 0.0;
+                gs_mna = fminf(gs_mna, a), gs_mxa = fmaxf(gs_mxa, a), gs_mnr = fminf(gs_mnr, t), gs_mxr = fmaxf(gs_mxr, t);
+                gs_sv += vv, gs_qv += static_cast<double>(vv) * vv, gs_nv += 1.0;
+                if (row == N - 1) gs_sv += vn, gs_qv += static_cast<double>(vn) * vn, gs_nv += 1.0;  // the final estimate, row N
             }
         };
-        for (int e = 0; e < nenv; ++e) {
+        for (int e = 0; e < (q.want_gae ? nenv + 2 : nenv); ++e) {
             const uint32_t par = static_cast<uint32_t>(e & 1);
+            if (e >= nenv) {
+                // the GAE stage of the last two envs: wait until they have left the pipeline
+                mbar_wait_sleep(&rempty[par], ((static_cast<uint32_t>(e) >> 1) & 1u) ^ 1u, 4 * kTsPollNs);
+                gae_env(e - 2);
+                continue;
+            }
             if (e > 0) load_columns(e);
             bool dn[kTsMaxChunks];
 #pragma unroll
@@ -456,6 +469,28 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                     l = dn[i] ? 0 : l + 1;
                     ts_sts(rt + static_cast<uint32_t>(row) * 4u, static_cast<float>(x));
                     ts_sts_s32(lt + static_cast<uint32_t>(row) * 4u, l);
+                    if (q.want_gae && row < N) ts_sts(gslot(e, 1) + gpad(row), rr[i]);  // for the GAE stage, two envs later
+                }
+            }
+            if (q.want_gae) {
+                // terminal bits of the env, one word per 32 rows (lane l owns rows [l * RPL, (l + 1) * RPL))
+                uint32_t mine = 0;
+#pragma unroll
+                for (int i = 0; i < kTsMaxChunks; ++i)
+                    if (i < RPL && dn[i]) mine |= 1u << ((lane * RPL + i) & 31);
+                const int per_word = 32 / RPL > 0 ? 32 / RPL : 1;  // lanes that share a word (RPL divides 32 when it is a power of two)
+                uint32_t word = mine;
+                if (RPL < 32 && (RPL & (RPL - 1)) == 0)
+                    for (int d = 1; d < per_word; d <<= 1) word |= __shfl_xor_sync(0xffffffffu, word, d);
+                if (RPL <= 32 && (RPL & (RPL - 1)) == 0) {
+                    if (lane % per_word == 0) ts_sts_s32(gslot(e, 1) + gbits + static_cast<uint32_t>((lane * RPL) >> 5) * 4u, static_cast<int>(word));
+                } else {
+                    // rows per lane that do not divide 32: one word per lane (bit i = row lane * RPL + i)
+                    uint32_t w2 = 0;
+#pragma unroll
+                    for (int i = 0; i < kTsMaxChunks; ++i)
+                        if (i < RPL && dn[i]) w2 |= 1u << i;
+                    ts_sts_s32(gslot(e, 1) + gbits + static_cast<uint32_t>(lane) * 4u, static_cast<int>(w2));
                 }
             }
             __syncwarp();
@@ -465,10 +500,6 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
             if (q.want_gae && e >= 2) gae_env(e - 2);
         }
         if (q.want_gae) {
-            for (int e2 = nenv > 2 ? nenv - 2 : 0; e2 < nenv; ++e2) {
-                mbar_wait_sleep(&rempty[e2 & 1], (static_cast<uint32_t>(e2) >> 1) & 1u, 4 * kTsPollNs);
-                gae_env(e2);
-            }
             // per-CTA record, then the last CTA folds all records in index order (deterministic, no float atomics)
             double rec[PPO_STATS_LEN];
 #pragma unroll
@@ -537,7 +568,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
             }
             mbar_wait_sleep(&rfull[par], (static_cast<uint32_t>(e) >> 1) & 1u, kTsPollNs);
             // (the value column slot e % 3 was read by the GAE stage of env e - 3, which ran before these tables were released)
-            if (q.want_gae && xw == 0 && lane == 31) ts_sts(val_a + static_cast<uint32_t>((e % 3) * val_pitch) * 4u, row0_val);
+            if (q.want_gae && xw == 0 && lane == 31) ts_sts(gslot(e, 0) + gpad(0), row0_val);
             const uint32_t rt = rt_a + par * rt_bytes;
             // slab of this env; it was last used by env e - nslab (the j-th use of a slab waits for use j - 1)
             const int sl = e % q.nslab;
@@ -597,7 +628,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                     const int i = c * kTsRows + xw + rl * kTsXform;
                     if ((lane & 3) == 0 && i < N) {
                         q.value_out[static_cast<int64_t>(i + 1) * q.vo_rs + env0 + e] = k1;
-                        if (q.want_gae) ts_sts(val_a + static_cast<uint32_t>((e % 3) * val_pitch + i + 1) * 4u, k1);
+                        if (q.want_gae) ts_sts(gslot(e, 0) + gpad(i + 1), k1);
                     }
                 } else if (q.want_value == 1 && lane == 31) {
 #pragma unroll
@@ -605,7 +636,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                         const int i = c * kTsRows + xw + rl * kTsXform;
                         if (i < N) {
                             q.value_out[static_cast<int64_t>(i + 1) * q.vo_rs + env0 + e] = part[rl];
-                            if (q.want_gae) ts_sts(val_a + static_cast<uint32_t>((e % 3) * val_pitch + i + 1) * 4u, part[rl]);
+                            if (q.want_gae) ts_sts(gslot(e, 0) + gpad(i + 1), part[rl]);
                         }
                     }
                 }
@@ -887,6 +918,7 @@ int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsign
     int dev = 0, max_smem = 0;
     PPO_CUDA(cudaGetDevice(&dev));
     PPO_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    max_smem -= 1024;  // the kernel's static shared memory
     const uint32_t chunk = kTsRows * static_cast<uint32_t>(V) * 4u;
     const uint32_t wt_bytes = ts_align((static_cast<uint32_t>(V + 2) * q.pitch + nmax + 2 * kTsStep) * 4u, 1024);
     const uint32_t ot_bytes = static_cast<uint32_t>(kTsStep) * K * 4u;  // dense swizzled sub-tiles of 4096 bytes
@@ -898,7 +930,11 @@ int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsign
     const uint32_t bar_bytes = (8u + 2 * kTsMaxChunks + 2 * kTsMaxSteps + 4 + 2) * 8u;
     const bool with_gae = gae && gae->adv && gae->ret && gae->stats && gae->partials && gae->ticket && value_out &&
                           sm_count() <= gae->max_partials;
-    const uint32_t val_bytes = with_gae ? ts_align(3u * q.rt_words * 4u, 128) : 0u;
+    {
+        const int ncl = q.nc, sh = (ncl & (ncl - 1)) == 0 && ncl > 1 ? 31 - __builtin_clz(ncl) : 31;
+        q.val_pitch = N + 2 + ((N + 2) >> sh) + 34;  // rows (padded index) + up to 32 words of terminal bits
+    }
+    const uint32_t val_bytes = with_gae ? ts_align(6u * q.val_pitch * 4u, 128) : 0u;
     const uint32_t rest = ot_bytes + ent_bytes + hz_bytes + 2 * rt_bytes + fr_bytes + val_bytes + bar_bytes;
     // two slabs when they fit beside two staging chunks: the next env is transposed while this one is evaluated
     // (with one slab the replacement is in place, which stalls when the n-step window is as long as the rollout)

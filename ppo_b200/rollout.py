@@ -351,7 +351,10 @@ class ReturnPass:
                 box = PeerMailbox(self.device, group)
                 self.peers = box if box.ok else None
         self._ctab = self._blob = None
-        self.fuse_gae = os.environ.get("PPO_FUSE_GAE", "1") != "0"
+        # GAE inside the target launch (the transposed slab kernel's scan warp): measured slower than the separate
+        # cooperative GAE launch on B200 (0.536 vs 0.506 ms per pass at 256 x 4096 x 128: the target kernel is issue
+        # bound and every consumer waits for the scheduler that also carries the scan warp), so it is opt-in
+        self.fuse_gae = os.environ.get("PPO_FUSE_GAE", "0") != "0"
         self.gae_fused = False
         self.kernel_launches_per_pass = 4
         self._tvf_launches = 2

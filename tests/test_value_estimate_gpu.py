@@ -85,6 +85,7 @@ def test_return_pass_with_values_from_the_curves(gamma):
     vs = synthetic.value_samples(steps, envs, len(hz), seed=4)
     table = oracle.draw_n_step_samples("exponential", "advanced", hz, steps, 20, 8, seed=1)
     rp = rollout.ReturnPass(steps, envs, hz, gamma, tvf_gamma, 0.95, 0.9)
+    rp.fuse_gae = True  # (opt-in: GAE, TD(lambda) and their statistics inside the target launch)
     rp.set_samples(table)
     rp.run(torch.from_numpy(r).cuda(), None, torch.from_numpy(d).cuda().view(torch.uint8), torch.from_numpy(vs).cuda())
     torch.cuda.synchronize()
@@ -116,7 +117,7 @@ def test_return_pass_with_values_from_the_curves(gamma):
     rp2.set_samples(table)
     rp2.run(torch.from_numpy(r).cuda(), None, torch.from_numpy(d).cuda().view(torch.uint8), torch.from_numpy(vs).cuda())
     torch.cuda.synchronize()
-    assert not rp2.gae_fused and torch.equal(rp2.tvf_returns, rp.tvf_returns)
+    assert not rp2.gae_fused and rp2.kernel_launches_per_pass == 2 and torch.equal(rp2.tvf_returns, rp.tvf_returns)
     assert np.abs(rp2.advantage.cpu().numpy() - adv).max() <= np.spacing(np.abs(adv).max())
     # the same through calculate_returns, NumPy buffers and pinned host buffers (env-blocked pipeline)
     kw = dict(value_samples=vs, horizons=hz, gamma=tvf_gamma, mode="advanced", distribution="exponential", n_step=20,
