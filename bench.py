@@ -364,27 +364,41 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing
-    for _ in range(args.warmup):
-        rp.run(rewards, None, dones, value_samples)
+    # ---- device-resident timing.  Like the reference (rl/returns_truncated.py:85-129 draws a new n-step table in every
+    # call) each timed pass draws a fresh sample table, resolves it on the host and uploads it: that host work runs
+    # ahead of the GPU (all launches are asynchronous), so it costs GPU time only if it is slower than the pass itself.
+    def timed_passes(redraw):
+        for _ in range(args.warmup):
+            if redraw:
+                rp.set_samples(rt.draw_n_step_samples("exponential", "advanced", hz, steps, N_STEP, SAMPLES))
+            rp.run(rewards, None, dones, value_samples)
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+        t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        host_s = 0.0
+        t_begin.record()
+        for i in range(args.steps):
+            if redraw:
+                h0 = time.perf_counter()
+                rp.set_samples(rt.draw_n_step_samples("exponential", "advanced", hz, steps, N_STEP, SAMPLES))
+                host_s += time.perf_counter() - h0
+            rp.run(rewards, None, dones, value_samples, tvf_events=evs[i])
+        t_end.record()
+        barrier()
+        total = t_begin.elapsed_time(t_end)
+        if world > 1:
+            t = torch.tensor([total], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total = float(t.item())
+        return total / args.steps, [e[0].elapsed_time(e[1]) for e in evs], host_s / args.steps * 1e3
+
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
-    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_begin.record()
-    for i in range(args.steps):
-        rp.run(rewards, None, dones, value_samples, tvf_events=evs[i])
-    t_end.record()
-    barrier()
-    total_ms = t_begin.elapsed_time(t_end)
-    tvf_ms = [e[0].elapsed_time(e[1]) for e in evs]
-    if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
+    np.random.seed(SAMPLE_SEED + 1 + rank)
+    ms_per_step, tvf_ms, redraw_host_ms = timed_passes(redraw=True)
+    tabs = rp.set_samples(samples)  # back to the seeded table: the end-to-end leg below must reproduce these targets
+    fixed_ms_per_step, fixed_tvf_ms, _ = timed_passes(redraw=False)
     targets_per_step = steps * envs * n_h * world
     value = targets_per_step / (ms_per_step * 1e-3)
 
@@ -477,6 +491,13 @@ def run_ours(args):
             "gpu_launches": rp.kernel_launches_per_pass * args.steps,
             "roofline": roofline,
             "tvf_tables": {"entries_per_horizon": int(tabs.n_entries), "nmax": int(tabs.nmax)},
+            # `value` / `ms_per_step` include a fresh n-step table per pass (draw + ppo_tvf_tables_build + upload, like
+            # the reference's per-call draw); the same passes on one fixed table beside it
+            "table_redraw": {"per_pass": True, "host_ms_per_pass": redraw_host_ms,
+                             "fixed_table_ms_per_step": fixed_ms_per_step,
+                             "fixed_table_value": targets_per_step / (fixed_ms_per_step * 1e-3),
+                             "fixed_table_kernel_ms": sum(fixed_tvf_ms) / len(fixed_tvf_ms),
+                             "redraw_over_fixed": ms_per_step / fixed_ms_per_step},
         }
         if other is not None:
             line["other_configs"] = other

@@ -128,16 +128,21 @@ int ppo_gae_normalized(const float* rewards, int64_t reward_row_stride,
 /*
  * Env-sharded form of ppo_gae_normalized (one process per GPU, envs split over `world` GPUs of one NVLink domain): the
  * exchange of the advantage moments -- the only cross-GPU step of the path, SURVEY 8e -- happens INSIDE the launch
- * over peer memory instead of an NCCL all-reduce between two launches.  Every rank owns a mailbox [world][PPO_STATS_LEN]
- * doubles and `world` 64-bit flag words, mapped into all peers (CUDA IPC); peer_mail[r] / peer_flags[r] are rank r's
- * buffers as seen from this process (host arrays of `world` device pointers).  The CTA that folds the local statistics
- * stores the record into slot `rank` of every mailbox and release-stores `epoch` into flag `rank` there; all CTAs then
- * wait until their own `world` flags have reached `epoch`, add the moments in rank order (identical bits on every
- * rank) and normalise their tile.  epoch must increase with every launch on every rank (flags are never reset; zero
- * them once at start-up).  stats receives the local record, global_stats (optional) the merged one.
+ * over peer memory instead of an NCCL all-reduce between two launches.  Every rank owns a mailbox
+ * [2][world][PPO_STATS_LEN] doubles and 2 x `world` 64-bit flag words (two halves, used alternately by the parity of
+ * the epoch so that a rank one launch ahead never overwrites a record a slower rank still reads), mapped into all
+ * peers (CUDA IPC); peer_mail[r] / peer_flags[r] are rank r's buffers as seen from this process (host arrays of `world`
+ * device pointers).  The CTA that folds the local statistics stores the record into slot `rank` of every mailbox and
+ * release-stores `epoch` into flag `rank` there; all CTAs then wait until their own `world` flags have reached `epoch`,
+ * add the moments in rank order (identical bits on every rank) and normalise their tile.  epoch must increase by one
+ * with every launch on every rank (flags are never reset; zero them once at start-up).  stats receives the local
+ * record, global_stats (optional) the merged one.
  * Returns 1 when launched, 0 when the shard shape does not fit the resident tile kernel (nothing launched: every rank
- * decides alike; use ppo_gae + all-reduce + ppo_adv_normalize), < 0 on error.  A peer that never arrives makes the
- * kernel give up after 4 s and write NaN advantages rather than hang.
+ * decides alike; use ppo_gae + all-reduce + ppo_adv_normalize), < 0 on error.
+ * A peer that does not arrive within timeout_ms (<= 0: 4000) makes the kernel give up instead of hanging: it stores
+ * `epoch` into *status (optional; device memory or mapped pinned host memory, zero it at start-up and read it after
+ * the stream has drained -- non-zero means the normalised advantages of that launch are NaN and the pass must be
+ * repeated, e.g. with the all-reduce path, after the ranks have met at a host barrier).
  */
 /* 1 when ppo_gae_normalized / ppo_gae_normalized_peers would take the single cooperative launch for this shard shape
  * on the current device (nothing is launched): ranks agree on it (all-reduce MIN) before relying on the peer exchange. */
@@ -152,7 +157,7 @@ int ppo_gae_normalized_peers(const float* rewards, int64_t reward_row_stride,
                              float* adv_out, float* ret_out, float* norm_out, double* stats, double* global_stats,
                              void* workspace, int64_t workspace_bytes, int rank, int world,
                              double* const* peer_mail, unsigned long long* const* peer_flags,
-                             unsigned long long epoch, void* stream);
+                             unsigned long long epoch, unsigned long long* status, double timeout_ms, void* stream);
 
 /*
  * Batch advantage normalisation: out = clip((x - mean) / (std + eps), -clip, +clip), population std.

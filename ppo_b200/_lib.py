@@ -74,7 +74,7 @@ _SIGNATURES = {
                                    c_ptr, c_ptr]),
     "ppo_gae_normalized_peers": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_int, c_i64, c_i64, c_i64,
                                          c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
-                                         c_i64, c_int, c_int, c_ptr, c_ptr, ctypes.c_uint64, c_ptr]),
+                                         c_i64, c_int, c_int, c_ptr, c_ptr, ctypes.c_uint64, c_ptr, c_dbl, c_ptr]),
     "ppo_gae_normalized_fits": (c_int, [c_i64, c_i64, c_int, c_i64]),
     "ppo_peer_alloc": (c_int, [c_i64, c_ptr, c_ptr]),
     "ppo_peer_open": (c_int, [c_ptr, c_ptr]),

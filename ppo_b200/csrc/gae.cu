@@ -92,14 +92,20 @@ struct ThreadStats {
 };
 
 // Exchange of the per-GPU statistics records over NVLink peer memory (env-sharded runs): every rank owns a mailbox
-// [world][16] doubles and a flag word per sender, mapped into its peers; the CTA that folds the local record stores it
-// into slot `rank` of every mailbox (its own included) and then raises flag `rank` there to the launch's epoch.
+// [2][world][16] doubles and a flag word per (parity, sender), mapped into its peers; the CTA that folds the local record
+// stores it into slot `rank` of every mailbox (its own included) and then raises flag `rank` there to the launch's
+// epoch.  Records and flags are double-buffered by the parity of the epoch: a rank that is one launch ahead writes the
+// other half, so it cannot overwrite a record a slower rank's CTAs are still reading (it cannot be two launches ahead:
+// its launch k + 1 completes only after every rank has raised flag k + 1, i.e. has finished launch k).
 struct PeerExchange {
     int world, rank;               // world <= kMaxPeers; world == 0: no exchange
     unsigned long long epoch;      // strictly increasing per launch: flags never need a reset
-    double* mail[PPO_MAX_PEERS];              // mail[p]: rank p's mailbox, [world][PPO_STATS_LEN]
-    unsigned long long* flags[PPO_MAX_PEERS];  // flags[p]: rank p's flag words, [world]
+    double* mail[PPO_MAX_PEERS];              // mail[p]: rank p's mailbox, [2][world][PPO_STATS_LEN]
+    unsigned long long* flags[PPO_MAX_PEERS];  // flags[p]: rank p's flag words, [2][world]
     double* global_stats;          // merged record of all ranks (optional), written by CTA 0
+    unsigned long long* status;    // optional error word (device or mapped host memory): epoch of a timed-out wait
+    unsigned long long timeout_ns;
+    __device__ __forceinline__ int half() const { return static_cast<int>(epoch & 1ull) * world; }
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -202,13 +208,13 @@ __device__ void publish_stats(const ThreadStats& ts, const ScanStatsIo& io, doub
             __threadfence();
             if (px) {  // the local record goes to slot `rank` of every mailbox (remote stores over NVLink)
                 for (int r = 0; r < px->world; ++r)
-                    px->mail[r][px->rank * PPO_STATS_LEN + j] = j <= PPO_STAT_RET_ZEROS ? tot : 0.0;
+                    px->mail[r][(px->half() + px->rank) * PPO_STATS_LEN + j] = j <= PPO_STAT_RET_ZEROS ? tot : 0.0;
                 __threadfence_system();
             }
         }
         if (px) {
             __syncthreads();  // all sixteen slots are on their way; the release stores order them before the flags
-            if (threadIdx.x < px->world) st_release_sys(px->flags[threadIdx.x] + px->rank, px->epoch);
+            if (threadIdx.x < px->world) st_release_sys(px->flags[threadIdx.x] + px->half() + px->rank, px->epoch);
         }
         if (ready) {  // the folded record is visible: release the CTAs that wait for it
             __syncthreads();
@@ -542,7 +548,7 @@ __global__ void __launch_bounds__(EW * kTileChunks) gae_tile_kernel(const GaeTil
                 s_mom[1] = __ldcg(p.io.stats + PPO_STAT_ADV_SUM);
                 s_mom[2] = __ldcg(p.io.stats + PPO_STAT_ADV_SUMSQ);
             } else {
-                const unsigned long long* mine = q.px.flags[q.px.rank];
+                const unsigned long long* mine = q.px.flags[q.px.rank] + q.px.half();
                 unsigned long long t0, t1;
                 asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
                 bool ok = true;
@@ -550,13 +556,17 @@ __global__ void __launch_bounds__(EW * kTileChunks) gae_tile_kernel(const GaeTil
                     while (ld_acquire_sys(mine + r) < q.px.epoch) {
                         __nanosleep(64);
                         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-                        if (t1 - t0 > 4000000000ull) {  // a peer never arrived (4 s): fail loudly instead of hanging
+                        if (t1 - t0 > q.px.timeout_ns) {  // a peer never arrived: fail loudly instead of hanging
                             ok = false;
                             break;
                         }
                     }
                 }
-                const volatile double* mail = q.px.mail[q.px.rank];
+                if (!ok && q.px.status) {  // the host checks this word (ReturnPass.check_peers); NaN advantages besides
+                    *reinterpret_cast<volatile unsigned long long*>(q.px.status) = q.px.epoch;
+                    __threadfence_system();
+                }
+                const volatile double* mail = q.px.mail[q.px.rank] + q.px.half() * PPO_STATS_LEN;
                 double n = 0.0, sm = 0.0, sq = 0.0;
                 for (int r = 0; r < q.px.world; ++r) {
                     n += mail[r * PPO_STATS_LEN + PPO_STAT_COUNT];
@@ -572,7 +582,7 @@ __global__ void __launch_bounds__(EW * kTileChunks) gae_tile_kernel(const GaeTil
             const int j = threadIdx.x;
             const bool is_min = (j == PPO_STAT_ADV_MIN || j == PPO_STAT_RET_MIN);
             const bool is_max = (j == PPO_STAT_ADV_MAX || j == PPO_STAT_RET_MAX);
-            const volatile double* mail = q.px.mail[q.px.rank];
+            const volatile double* mail = q.px.mail[q.px.rank] + q.px.half() * PPO_STATS_LEN;
             double acc = is_min ? INFINITY : is_max ? -INFINITY : 0.0;
             for (int r = 0; r < q.px.world; ++r) {
                 const double x = mail[r * PPO_STATS_LEN + j];
@@ -963,7 +973,8 @@ extern "C" int ppo_gae_normalized_peers(const float* rewards, int64_t reward_row
                                         float* ret_out, float* norm_out, double* stats, double* global_stats,
                                         void* workspace, int64_t workspace_bytes, int rank, int world,
                                         double* const* peer_mail, unsigned long long* const* peer_flags,
-                                        unsigned long long epoch, void* stream) {
+                                        unsigned long long epoch, unsigned long long* status, double timeout_ms,
+                                        void* stream) {
     PPO_REQUIRE(stats && norm_out && adv_out, "ppo_gae_normalized_peers: stats, adv_out and norm_out are required");
     PPO_REQUIRE(world >= 2 && world <= PPO_MAX_PEERS && rank >= 0 && rank < world,
                 "ppo_gae_normalized_peers: rank %d of %d (at most %d peers)", rank, world, PPO_MAX_PEERS);
@@ -983,6 +994,8 @@ extern "C" int ppo_gae_normalized_peers(const float* rewards, int64_t reward_row
     p.io.stats = stats;
     PeerExchange px{};
     px.world = world, px.rank = rank, px.epoch = epoch, px.global_stats = global_stats;
+    px.status = status;
+    px.timeout_ns = static_cast<unsigned long long>((timeout_ms > 0 ? timeout_ms : 4000.0) * 1e6);
     for (int r = 0; r < world; ++r) {
         PPO_REQUIRE(peer_mail[r] && peer_flags[r], "ppo_gae_normalized_peers: null mailbox of rank %d", r);
         px.mail[r] = peer_mail[r], px.flags[r] = peer_flags[r];

@@ -63,11 +63,22 @@ struct TailCache {
     std::vector<int64_t> req, vsh;
     int64_t steps = -1;
     int use_log = -1;
-    std::vector<Lerp> slots;  // [steps + 1][K], valid flag in lo >= 0
+    std::vector<Lerp> slots;  // [K][steps + 1]: slot and weights of horizon h_k - m
     std::vector<unsigned char> ok;
 };
 std::mutex g_cache_mutex;
 TailCache g_cache;
+
+// Scratch of one build (per thread, reused: a build per rollout must not pay for allocations).
+struct Scratch {
+    std::vector<double> axis, gp64;
+    std::vector<Entry> ent;          // [K][C], ent_count[k] live entries in ascending n
+    std::vector<int> ent_count, k_nmax;
+    std::vector<float> gpow;
+    std::vector<unsigned char> beyond;  // [K][nmax + 1] samples of the horizon with n > m (valid for C <= 255)
+    std::vector<uint32_t> tail_mask;    // [K] column groups the tail bootstraps of the horizon read
+    std::vector<float> park;
+};
 
 }  // namespace
 }  // namespace ppo
@@ -91,7 +102,9 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
     PPO_REQUIRE(n_req >= 1 && n_val >= 1 && n_samples >= 1 && steps >= 1, "ppo_tvf_tables_build: bad shape");
     const int K = static_cast<int>(n_req), V = static_cast<int>(n_val), C = static_cast<int>(n_samples);
 
-    std::vector<double> axis(V);
+    static thread_local Scratch sc;
+    std::vector<double>& axis = sc.axis;
+    axis.resize(V);
     for (int j = 0; j < V; ++j)
         axis[j] = use_log_interpolation ? log10(10.0 + static_cast<double>(value_horizons[j])) - 1.0
                                         : static_cast<double>(value_horizons[j]);
@@ -100,55 +113,12 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
                                      : static_cast<double>(x);
     };
 
-    // ---- entries: distinct clamped n-steps per horizon, ascending, with multiplicities
-    std::vector<std::vector<Entry>> ent(K);
-    int n_entries = 1, nmax = 1;
-    std::vector<int64_t> row(C);
-    for (int k = 0; k < K; ++k) {
-        const int64_t h = required_horizons[k];
-        if (h <= 0) continue;  // h == 0 -> zeros (rl/returns_truncated.py:580-583)
-        for (int c = 0; c < C; ++c) {
-            const int64_t n = std::min(samples[static_cast<int64_t>(k) * C + c], h);
-            if (n < 1 || n > steps) {
-                set_error("n-step samples must satisfy 1 <= min(sample, horizon) <= N (horizon %lld, sample %lld, N %lld)",
-                          (long long)h, (long long)samples[static_cast<int64_t>(k) * C + c], (long long)steps);
-                return PPO_ERR_BAD_ARG;  // rl/returns_truncated.py:597 assert
-            }
-            row[c] = n;
-        }
-        std::sort(row.begin(), row.end());
-        for (int c = 0; c < C; ++c) {
-            if (c > 0 && row[c] == row[c - 1]) {
-                ent[k].back().cnt += 1.f;
-                continue;
-            }
-            Entry x;
-            x.n = static_cast<int32_t>(row[c]), x.cnt = 1.f;
-            const int64_t left = h - row[c];
-            if (!lerp_slot(axis, to_axis(left), left > 0, &x.l)) {
-                set_error("index %d is out of bounds for axis 0 with size %d", V, V);
-                return PPO_ERR_UNSUPPORTED;  // the reference's IndexError (rl/returns_truncated.py:157)
-            }
-            ent[k].push_back(x);
-        }
-        n_entries = std::max(n_entries, static_cast<int>(ent[k].size()));
-        nmax = std::max(nmax, ent[k].back().n);
-    }
-    const int E = n_entries;
-
-    // ---- discount powers (float32 running product, float64 multiply)
-    std::vector<float> gpow(nmax + 1);
-    gpow[0] = 1.f;
-    for (int n = 1; n <= nmax; ++n) gpow[n] = static_cast<float>(static_cast<double>(gpow[n - 1]) * gamma);
-
-    // ---- tails: horizon h_k - m for m = N - t; used for m <= largest entry of the horizon
-    std::vector<int> k_nmax(K, 0);
-    for (int k = 0; k < K; ++k)
-        if (!ent[k].empty()) k_nmax[k] = ent[k].back().n;
-    std::vector<Lerp> tail(static_cast<size_t>(nmax + 1) * K, Lerp{0, 0, 0.f, 0.f});
+    // ---- bootstrap slots of every (horizon, distance m): horizon h_k - m on the value axis.  They serve the entries
+    // (m = n-step) and the tails (m = N - t) alike and depend on the horizon set only, so they are cached.
+    std::lock_guard<std::mutex> guard(g_cache_mutex);
+    TailCache& tc = g_cache;
+    const size_t cpitch = static_cast<size_t>(steps) + 1;
     {
-        std::lock_guard<std::mutex> guard(g_cache_mutex);
-        TailCache& tc = g_cache;
         const bool hit = tc.steps == steps && tc.use_log == use_log_interpolation &&
                          tc.req.size() == static_cast<size_t>(K) && tc.vsh.size() == static_cast<size_t>(V) &&
                          std::equal(tc.req.begin(), tc.req.end(), required_horizons) &&
@@ -157,27 +127,69 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
             tc.req.assign(required_horizons, required_horizons + K);
             tc.vsh.assign(value_horizons, value_horizons + V);
             tc.steps = steps, tc.use_log = use_log_interpolation;
-            tc.slots.assign(static_cast<size_t>(steps + 1) * K, Lerp{0, 0, 0.f, 0.f});
-            tc.ok.assign(static_cast<size_t>(steps + 1) * K, 1);
-            for (int64_t m = 1; m <= steps; ++m)
-                for (int k = 0; k < K; ++k) {
+            tc.slots.assign(cpitch * K, Lerp{0, 0, 0.f, 0.f});
+            tc.ok.assign(cpitch * K, 1);
+            for (int k = 0; k < K; ++k)
+                for (int64_t m = 1; m <= steps; ++m) {
                     const int64_t left = required_horizons[k] - m;
-                    if (required_horizons[k] <= 0 || left <= 0) continue;
-                    if (!lerp_slot(axis, to_axis(left), true, &tc.slots[m * K + k])) tc.ok[m * K + k] = 0;
+                    if (required_horizons[k] <= 0 || left <= 0) continue;  // no bootstrap: zero weights
+                    if (!lerp_slot(axis, to_axis(left), true, &tc.slots[k * cpitch + m])) tc.ok[k * cpitch + m] = 0;
                 }
         }
-        for (int m = 1; m <= nmax; ++m)
-            for (int k = 0; k < K; ++k) {
-                if (m > k_nmax[k]) continue;
-                if (!tc.ok[static_cast<size_t>(m) * K + k]) {
-                    set_error("index %d is out of bounds for axis 0 with size %d", V, V);
-                    return PPO_ERR_UNSUPPORTED;
-                }
-                tail[static_cast<size_t>(m) * K + k] = tc.slots[static_cast<size_t>(m) * K + k];
-            }
     }
 
-    for (int k = 0; k < K; ++k) ent[k].resize(E, Entry{0, 0.f, Lerp{0, 0, 0.f, 0.f}});
+    // ---- entries: distinct clamped n-steps per horizon, ascending, with multiplicities
+    std::vector<Entry>& ent = sc.ent;
+    std::vector<int>& ent_count = sc.ent_count;
+    std::vector<int>& k_nmax = sc.k_nmax;
+    ent.resize(static_cast<size_t>(K) * C);
+    ent_count.assign(K, 0), k_nmax.assign(K, 0);
+    int n_entries = 1, nmax = 1;
+    for (int k = 0; k < K; ++k) {
+        const int64_t h = required_horizons[k];
+        if (h <= 0) continue;  // h == 0 -> zeros (rl/returns_truncated.py:580-583)
+        Entry* row = ent.data() + static_cast<size_t>(k) * C;
+        // insertion sort of the clamped samples into (n, multiplicity) pairs
+        int cnt = 0;
+        for (int c = 0; c < C; ++c) {
+            const int64_t n = std::min(samples[static_cast<int64_t>(k) * C + c], h);
+            if (n < 1 || n > steps) {
+                set_error("n-step samples must satisfy 1 <= min(sample, horizon) <= N (horizon %lld, sample %lld, N %lld)",
+                          (long long)h, (long long)samples[static_cast<int64_t>(k) * C + c], (long long)steps);
+                return PPO_ERR_BAD_ARG;  // rl/returns_truncated.py:597 assert
+            }
+            int pos = cnt;
+            while (pos > 0 && row[pos - 1].n > n) --pos;
+            if (pos > 0 && row[pos - 1].n == n) {
+                row[pos - 1].cnt += 1.f;
+                continue;
+            }
+            for (int i = cnt; i > pos; --i) row[i] = row[i - 1];
+            row[pos].n = static_cast<int32_t>(n), row[pos].cnt = 1.f;
+            ++cnt;
+        }
+        for (int e = 0; e < cnt; ++e) {
+            if (!tc.ok[k * cpitch + row[e].n]) {
+                set_error("index %d is out of bounds for axis 0 with size %d", V, V);
+                return PPO_ERR_UNSUPPORTED;  // the reference's IndexError (rl/returns_truncated.py:157)
+            }
+            row[e].l = tc.slots[k * cpitch + row[e].n];
+        }
+        ent_count[k] = cnt, k_nmax[k] = row[cnt - 1].n;
+        n_entries = std::max(n_entries, cnt);
+        nmax = std::max(nmax, k_nmax[k]);
+    }
+    const int E = n_entries;
+
+    // ---- discount powers (float32 running product, float64 multiply); float64 powers for the slab kernels
+    std::vector<float>& gpow = sc.gpow;
+    std::vector<double>& gp64 = sc.gp64;
+    gpow.resize(nmax + 1), gp64.resize(nmax + 1);
+    gpow[0] = 1.f, gp64[0] = 1.0;
+    for (int n = 1; n <= nmax; ++n) {
+        gpow[n] = static_cast<float>(static_cast<double>(gpow[n - 1]) * gamma);
+        gp64[n] = pow(gamma, static_cast<double>(n));
+    }
 
     // ---- pack
     auto pad = [](int64_t w) { return (w + 3) / 4 * 4; };
@@ -215,67 +227,121 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
     float* tail_cwlo = reinterpret_cast<float*>(blob + offs[9]);
     float* tail_cwhi = reinterpret_cast<float*>(blob + offs[10]);
     float* gp = reinterpret_cast<float*>(blob + offs[11]);
-    for (int k = 0; k < K; ++k)
+    int32_t* tT_idx = blob + offs[12];
+    float* tT_wlo = reinterpret_cast<float*>(blob + offs[13]);
+    float* tT_whi = reinterpret_cast<float*>(blob + offs[14]);
+    int32_t* ts_hdr = blob + offs[15];
+    int32_t* t4 = ts_hdr + pad(4 + 4 * static_cast<int64_t>(K) + 4 * ek);  // [K][tail_pitch] x {idx, cwlo / C, cwhi / C, 0}
+    for (int k = 0; k < K; ++k) {
+        const Entry* row = ent.data() + static_cast<size_t>(k) * C;
         for (int e = 0; e < E; ++e) {
-            const Entry& x = ent[k][e];
             const int64_t i = static_cast<int64_t>(e) * K + k;
-            ent_n[i] = x.n, ent_cnt[i] = x.cnt;
-            ent_idx[i] = x.l.lo | (x.l.hi << 16);
-            ent_wlo[i] = x.l.wlo, ent_whi[i] = x.l.whi;
-            ent_g[i] = gpow[x.n];  // gpow[0] = 1 for padding slots, like the NumPy builder
-        }
-    for (int m = 0; m <= nmax; ++m)
-        for (int k = 0; k < K; ++k) {
-            const int64_t i = static_cast<int64_t>(m) * K + k;
-            const Lerp& l = tail[i];
-            tail_idx[i] = l.lo | (l.hi << 16);
-            tail_wlo[i] = l.wlo, tail_whi[i] = l.whi;
-            double beyond = 0.0;  // multiplicity of the entries that run past m
-            for (int e = 0; e < E; ++e)
-                if (ent[k][e].n > m) beyond += ent[k][e].cnt;
-            const double scale = beyond * static_cast<double>(gpow[m]);
-            tail_cwlo[i] = static_cast<float>(static_cast<double>(l.wlo) * scale);
-            tail_cwhi[i] = static_cast<float>(static_cast<double>(l.whi) * scale);
-        }
-    for (int n = 0; n <= nmax; ++n) gp[n] = gpow[n];
-    {
-        int32_t* t_idx = blob + offs[12];
-        float* t_wlo = reinterpret_cast<float*>(blob + offs[13]);
-        float* t_whi = reinterpret_cast<float*>(blob + offs[14]);
-        for (int k = 0; k < K; ++k)
-            for (int m = 0; m <= nmax; ++m) {
-                const int64_t src = static_cast<int64_t>(m) * K + k, dst = static_cast<int64_t>(k) * tpitch + m;
-                t_idx[dst] = tail_idx[src], t_wlo[dst] = tail_cwlo[src], t_whi[dst] = tail_cwhi[src];
+            if (e < ent_count[k]) {
+                const Entry& x = row[e];
+                ent_n[i] = x.n, ent_cnt[i] = x.cnt;
+                ent_idx[i] = x.l.lo | (x.l.hi << 16);
+                ent_wlo[i] = x.l.wlo, ent_whi[i] = x.l.whi;
+                ent_g[i] = gpow[x.n];
+            } else {
+                ent_g[i] = gpow[0];  // padding slots: n = 0, weight 0, gamma^0 like the NumPy builder
             }
+        }
     }
+    for (int n = 0; n <= nmax; ++n) gp[n] = gpow[n];
+
+    // ---- tails: horizon h_k - m for m = N - t; used for m <= largest entry of the horizon.  One pass per horizon
+    // writes the length-major tables (generic kernel), the horizon-major folded copies and the interleaved records.
+    std::vector<unsigned char>& beyond_tab = sc.beyond;
+    std::vector<uint32_t>& tail_mask = sc.tail_mask;
+    beyond_tab.assign(static_cast<size_t>(K) * (nmax + 1), 0);
+    tail_mask.assign(K, 0);
+    {
+        const double inv_c = 1.0 / static_cast<double>(C);
+        // pass 1, horizon-major (every stream sequential): multiplicities beyond m, folded weights, the horizon-major
+        // tables and the interleaved records; the plain lerp weights are parked for pass 2
+        std::vector<float>& park = sc.park;  // [K][tail_pitch] x {wlo, whi}
+        park.resize(static_cast<size_t>(K) * tpitch * 2);
+        for (int k = 0; k < K; ++k) {
+            const Entry* row = ent.data() + static_cast<size_t>(k) * C;
+            const int ne = ent_count[k], maxn = k_nmax[k];
+            double beyond = 0.0;  // multiplicity of the entries that run past m
+            for (int i = 0; i < ne; ++i) beyond += row[i].cnt;
+            int e = 0;
+            uint32_t mask = 0;
+            unsigned char* bt = beyond_tab.data() + static_cast<size_t>(k) * (nmax + 1);
+            const Lerp* slots = tc.slots.data() + k * cpitch;
+            const unsigned char* oks = tc.ok.data() + k * cpitch;
+            const int64_t dst0 = static_cast<int64_t>(k) * tpitch;
+            unsigned bad = 0;
+            for (int m = 1; m <= maxn; ++m) {
+                while (e < ne && row[e].n <= m) beyond -= row[e++].cnt;
+                bt[m] = static_cast<unsigned char>(std::min(beyond, 255.0));
+                bad |= oks[m] ^ 1u;
+                const Lerp l = slots[m];
+                const int64_t dst = dst0 + m;
+                const int32_t idx = l.lo | (l.hi << 16);
+                const double scale = beyond * static_cast<double>(gpow[m]);
+                const float cwlo = static_cast<float>(static_cast<double>(l.wlo) * scale);
+                const float cwhi = static_cast<float>(static_cast<double>(l.whi) * scale);
+                tT_idx[dst] = idx, tT_wlo[dst] = cwlo, tT_whi[dst] = cwhi;
+                park[2 * dst] = l.wlo, park[2 * dst + 1] = l.whi;
+                const float wl = static_cast<float>(static_cast<double>(cwlo) * inv_c);
+                const float wh = static_cast<float>(static_cast<double>(cwhi) * inv_c);
+                t4[4 * dst] = idx;
+                memcpy(t4 + 4 * dst + 1, &wl, 4), memcpy(t4 + 4 * dst + 2, &wh, 4);
+                // value columns of the final row this tail bootstrap reads (column slab kernel: job masks)
+                mask |= (cwlo != 0.f && l.lo < V) ? 1u << (l.lo / 32 & 31) : 0u;
+                mask |= (cwhi != 0.f && l.hi < V) ? 1u << (l.hi / 32 & 31) : 0u;
+            }
+            if (bad) {
+                set_error("index %d is out of bounds for axis 0 with size %d", V, V);
+                return PPO_ERR_UNSUPPORTED;
+            }
+            tail_mask[k] = mask;
+        }
+        // pass 2: the length-major tables of the generic kernel, transposed in blocks of 16 horizons (one cache line
+        // per table and tail length)
+        for (int kb = 0; kb < K; kb += 16) {
+            const int ke = std::min(kb + 16, K);
+            int bmax = 0;
+            for (int k = kb; k < ke; ++k) bmax = std::max(bmax, k_nmax[k]);
+            for (int m = 1; m <= bmax; ++m)
+                for (int k = kb; k < ke; ++k) {
+                    // (rows beyond the horizon's largest n-step hold zeros in both layouts)
+                    const int64_t i = static_cast<int64_t>(m) * K + k, src = static_cast<int64_t>(k) * tpitch + m;
+                    tail_idx[i] = tT_idx[src], tail_cwlo[i] = tT_wlo[src], tail_cwhi[i] = tT_whi[src];
+                    tail_wlo[i] = m <= k_nmax[k] ? park[2 * src] : 0.f;
+                    tail_whi[i] = m <= k_nmax[k] ? park[2 * src + 1] : 0.f;
+                }
+        }
+    }
+
     {
         // Per (horizon, n-step) constants of the transposed slab kernel: byte offset of W^T[col][n - 1] in a slab of
         // pitch N | 1, multiplicity * gamma^n * lerp weights (float64 product, rounded once), n.  Entries without a
         // bootstrap read the -R column (index V) with weight multiplicity * gamma^n; single-slot values read their
         // neighbour column with weight zero.
-        int32_t* hdr = blob + offs[15];
+        int32_t* hdr = ts_hdr;
         const int pitch = static_cast<int>(steps) | 1;
         hdr[0] = kTsConstMagic, hdr[1] = -1, hdr[2] = pitch, hdr[3] = V;
         bool ok = K <= kTsMaxK && ek <= kTsMaxEntries;
         TsHorizon* hz = reinterpret_cast<TsHorizon*>(hdr + 4);
         TsEntry* te = reinterpret_cast<TsEntry*>(hdr + 4 + 4 * K);
-        std::vector<double> gp64(nmax + 1, 1.0);
-        for (int n = 1; n <= nmax; ++n) gp64[n] = pow(gamma, static_cast<double>(n));
         int total = 0;
         for (int k = 0; k < K && ok; ++k) {
+            const Entry* row = ent.data() + static_cast<size_t>(k) * C;
             TsHorizon& h = hz[k];
             h.beg = total, h.cnt = 0, h.maxn = 0;
             double csum = 0.0;
-            for (int e = 0; e < E && ok; ++e) {
-                const Entry& x = ent[k][e];
-                if (!(x.cnt > 0.f)) continue;
+            for (int e = 0; e < ent_count[k] && ok; ++e) {
+                const Entry& x = row[e];
                 double a = x.l.wlo, bw = x.l.whi;
                 int col;
                 if (a == 0.0 && bw == 0.0) col = V, a = 1.0;
                 else if (x.l.hi == x.l.lo) col = x.l.lo, bw = 0.0;
                 else if (x.l.hi == x.l.lo + 1) col = x.l.lo;
                 else { ok = false; break; }
-                // the 1 / C of the sample average is folded in here (and into the tail records below), so the kernel
+                // the 1 / C of the sample average is folded in here (and into the tail records above), so the kernel
                 // finishes a target with one multiply-add
                 const double cg = static_cast<double>(x.cnt) * gp64[x.n] / static_cast<double>(C);
                 TsEntry& t = te[total++];
@@ -289,27 +355,14 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
             h.rscale = static_cast<float>(csum / static_cast<double>(C));
         }
         if (ok) hdr[1] = total;
-        // interleaved tail records behind the entry capacity: [K][tail_pitch] x {idx, cwlo, cwhi, 0}
-        int32_t* t4 = hdr + pad(4 + 4 * static_cast<int64_t>(K) + 4 * ek);
-        const int32_t* t_idx = blob + offs[12];
-        const int32_t* t_wlo = blob + offs[13];  // float bits
-        const int32_t* t_whi = blob + offs[14];
-        const double inv_c = 1.0 / static_cast<double>(C);
-        for (int64_t i = 0; i < static_cast<int64_t>(K) * tpitch; ++i) {
-            float wl, wh;
-            memcpy(&wl, t_wlo + i, 4), memcpy(&wh, t_whi + i, 4);
-            wl = static_cast<float>(static_cast<double>(wl) * inv_c), wh = static_cast<float>(static_cast<double>(wh) * inv_c);
-            t4[4 * i] = t_idx[i], t4[4 * i + 3] = 0;
-            memcpy(t4 + 4 * i + 1, &wl, 4), memcpy(t4 + 4 * i + 2, &wh, 4);
-        }
     }
 
     {
-        // Column slab kernel (tvf_cslab.cu): per horizon the entries in ascending n with the aligned row group
-        // ("bin") they gather, their shift against the thread's own rows and a flag that says whether the group
-        // differs from the previous entry's; per job (four consecutive horizons) the column groups its gathers and
-        // its tail bootstraps touch, and per column group the number of jobs that touch it (the kernel refills a
-        // column group of the slab with the next env as soon as that many jobs have finished).
+        // Column slab kernel (tvf_cslab.cu): per horizon the entries sorted by their shift against the thread's own
+        // rows (then ascending n) with the aligned row group ("bin") they gather; per job (four consecutive horizons)
+        // the column groups its gathers and its tail bootstraps touch, and per column group the number of jobs that
+        // touch it (the kernel refills a column group of the slab with the next env as soon as that many jobs have
+        // finished).
         int32_t* hdr = blob + cs_off;
         hdr[0] = kCsConstMagic, hdr[1] = -1, hdr[2] = static_cast<int32_t>(steps), hdr[3] = V;
         const int jobs = (K + 3) / 4;
@@ -323,14 +376,9 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
         uint32_t* nib = reinterpret_cast<uint32_t*>(ce + ek + 1);  // multiplicities of the n-steps beyond m, 4 bits each
         for (int j = 0; j < V && j < 128; ++j)
             vhw[j] = static_cast<int32_t>(std::min<int64_t>(std::max<int64_t>(value_horizons[j], 0), INT32_MAX));
-        std::vector<double> gp64(nmax + 1, 1.0);
-        for (int n = 1; n <= nmax; ++n) gp64[n] = pow(gamma, static_cast<double>(n));
         auto group_of = [&](int col) { return col < V ? col / 32 : (col == V ? kCsSpecial : -1); };
         int total = 0;
         int arrivals[kCsGroups] = {0, 0, 0, 0, 0};
-        const int32_t* t_idx = blob + offs[12];
-        const int32_t* t_wlo = blob + offs[13];  // float bits of the folded tail weights
-        const int32_t* t_whi = blob + offs[14];
         // Tail bootstraps (rows whose n-step window runs off the rollout) without table reads from global memory:
         //   tail[t, k] = cnt_k(m) / C * gamma^m * F(h_k - m),  m = N - t,  F = the final value curve interpolated
         // cnt_k(m) (samples of the horizon with n > m) comes from a 4-bit table; F either from a table over integer
@@ -342,13 +390,14 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
         const int64_t xcap = 1535;  // table horizons the kernel has shared memory for
         int64_t xmax = 0, nibbles = 0;
         for (int k = 0; k < K && ok; ++k) {
+            const Entry* row = ent.data() + static_cast<size_t>(k) * C;
             int cnt[4] = {0, 0, 0, 0}, maxn = 0;
             const int beg = total;
             uint32_t mask = 0;
             for (int shift = 0; shift < 4 && ok; ++shift)
-                for (int e = 0; e < E && ok; ++e) {
-                    const Entry& x = ent[k][e];
-                    if (!(x.cnt > 0.f) || (x.n - 1) % 4 != shift) continue;
+                for (int e = 0; e < ent_count[k] && ok; ++e) {
+                    const Entry& x = row[e];
+                    if ((x.n - 1) % 4 != shift) continue;
                     double a = x.l.wlo, bw = x.l.whi;
                     int col;
                     if (a == 0.0 && bw == 0.0) col = V, a = 1.0;
@@ -369,12 +418,7 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
             for (int shift = 0; shift < 4; ++shift)
                 if (cnt[shift] > 255) ok = false;
             // value columns of the final row the tail bootstraps of this horizon read (rows with N - t < maxn)
-            for (int m = 1; m <= maxn && ok; ++m) {
-                const int64_t i = static_cast<int64_t>(k) * tpitch + m;
-                const int lo = t_idx[i] & 0xffff, hi = (t_idx[i] >> 16) & 0xffff;
-                if (t_wlo[i] != 0 && lo < V) mask |= 1u << (lo / 32);
-                if (t_whi[i] != 0 && hi < V) mask |= 1u << (hi / 32);
-            }
+            mask |= tail_mask[k] & ((1u << kCsSpecial) - 1);
             // tail mode of the horizon
             const int64_t h = required_horizons[k];
             int mode = maxn > 0 ? kCsTailGeneric : kCsTailNone;
@@ -400,12 +444,10 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
                     (static_cast<uint32_t>(cnt[3]) << 24);
             hz.w2 = static_cast<uint32_t>(nibbles), hz.w3 = w3, hz.w4 = w4;
             if (mode == kCsTailTable || mode == kCsTailLinear) {
+                const unsigned char* bt = beyond_tab.data() + static_cast<size_t>(k) * (nmax + 1);
                 for (int m = 1; m <= maxn; ++m) {
-                    int beyond = 0;
-                    for (int e = 0; e < E; ++e)
-                        if (ent[k][e].cnt > 0.f && ent[k][e].n > m) beyond += static_cast<int>(ent[k][e].cnt);
                     const int64_t ni = nibbles + (m - 1);
-                    nib[ni >> 3] |= static_cast<uint32_t>(beyond & 15) << ((ni & 7) * 4);
+                    nib[ni >> 3] |= static_cast<uint32_t>(bt[m] & 15) << ((ni & 7) * 4);
                 }
                 nibbles += maxn;
             }

@@ -73,6 +73,11 @@ struct TsParams {
     int val_pitch;           // words per array
     const TsHorizon* hz;  // [K] device copies of the launch constants (inside the packed table blob)
     const TsEntry* ent;   // [n_ent]
+    // the same constants in the kernel-parameter (constant) bank: the consumers read them with warp-uniform LDC loads,
+    // which cost no shared-memory wavefront (31.5 M of the 105 M wavefronts of a launch were broadcast constant reads)
+    int cbank;                        // 1: consumers read pe / ph below; 0: the packed copies in shared memory
+    uint2 ph[kTsMaxK];                // {beg | cnt << 12 | maxn << 20, rscale}
+    uint4 pe[kTsMaxEntries + 4];      // {off | n << 18, wlo, whi, 0}
     const uint4* tail4;   // [K][tail_pitch] folded tail records {idx lo | hi << 16, cwlo, cwhi, 0}
 };
 
@@ -197,6 +202,34 @@ __device__ __forceinline__ void ts_eval(uint32_t cent, uint32_t base, uint32_t p
     }
 }
 
+// The same with the entry constants taken from the kernel-parameter bank (`e` points at the first of G entries).
+template <int G, int PITCH4>
+__device__ __forceinline__ void ts_eval_c(const uint4* e, uint32_t base, uint32_t p4, uint32_t lim0, uint32_t lim1,
+                                          float& acc0, float& acc1) {
+    uint4 c[G];
+#pragma unroll
+    for (int i = 0; i < G; ++i) c[i] = e[i];
+    float lo0[G], hi0[G], lo1[G], hi1[G];
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+        const uint32_t a = base + (c[i].x & kTsOffMask);
+        if (PITCH4) {
+            lo0[i] = ts_ldsi<0>(a), hi0[i] = ts_ldsi<PITCH4>(a);
+            lo1[i] = ts_ldsi<kTsRows * 4>(a), hi1[i] = ts_ldsi<PITCH4 + kTsRows * 4>(a);
+        } else {
+            const uint32_t ah = a + p4;
+            lo0[i] = ts_ldsi<0>(a), hi0[i] = ts_ldsi<0>(ah);
+            lo1[i] = ts_ldsi<kTsRows * 4>(a), hi1[i] = ts_ldsi<kTsRows * 4>(ah);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+        const float wlo = __uint_as_float(c[i].y), whi = __uint_as_float(c[i].z);
+        ts_fma_ifw(acc0, lo0[i], hi0[i], wlo, whi, c[i].x, lim0);
+        ts_fma_ifw(acc1, lo1[i], hi1[i], wlo, whi, c[i].x, lim1);
+    }
+}
+
 template <int V, int PITCH>
 __global__ void __launch_bounds__(kTsThreads, 1)
 tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUtensorMap vmap,
@@ -283,7 +316,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
         __shared__ uint32_t warp_total[kTsMaxK / 32];
         const int k = threadIdx.x;  // K <= 128 < blockDim.x
         uint4 h = make_uint4(0, 0, 0, 0);
-        if (k < K) h = __ldg(reinterpret_cast<const uint4*>(q.hz) + k);  // beg, cnt, rscale, maxn
+        if (k < K && !q.cbank) h = __ldg(reinterpret_cast<const uint4*>(q.hz) + k);  // beg, cnt, rscale, maxn
         const uint32_t padded = (h.y + 3u) & ~3u;
         uint32_t incl = padded;
 #pragma unroll
@@ -293,7 +326,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
         }
         if (lane == 31 && warp < kTsMaxK / 32) warp_total[warp] = incl;
         __syncthreads();
-        if (k < K) {
+        if (k < K && !q.cbank) {
             uint32_t pbeg = incl - padded;
             for (int j = 0; j < warp; ++j) pbeg += warp_total[j];
             *reinterpret_cast<uint2*>(smem + q.off_hz + k * 8) = make_uint2(pbeg | (h.y << 12) | (h.w << 20), h.z);
@@ -709,7 +742,10 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                 for (int quad = (cw + s) % kTsConsumers; quad < q.kq; quad += kTsConsumers) {
                     float o0[4], o1[4];
                     uint2 hz[4];  // {beg | cnt << 12 | maxn << 20, rscale} of the quad's four horizons: two 16-byte reads
-                    {
+                    if (q.cbank) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) hz[u] = q.ph[quad * 4 + u];
+                    } else {
                         const uint4 a = ts_lds128(hz_a + static_cast<uint32_t>(quad) * 32u);
                         const uint4 b = ts_lds128(hz_a + static_cast<uint32_t>(quad) * 32u + 16u);
                         hz[0] = make_uint2(a.x, a.y), hz[1] = make_uint2(a.z, a.w);
@@ -745,11 +781,18 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         float acc0 = tacc0[u], acc1 = tacc1[u];
-                        uint32_t ce = ent_a + (hz[u].x & 0xfffu) * kTsEntBytes;
                         int left = (q.dbg & 8) ? 0 : static_cast<int>((hz[u].x >> 12) & 0xffu);
-                        for (; left >= 4; left -= 4, ce += 4 * kTsEntBytes) ts_eval<4, PITCH4>(ce, base, P4, key0, key1, acc0, acc1);
-                        if (left >= 2) ts_eval<2, PITCH4>(ce, base, P4, key0, key1, acc0, acc1), ce += 2 * kTsEntBytes, left -= 2;
-                        if (left >= 1) ts_eval<1, PITCH4>(ce, base, P4, key0, key1, acc0, acc1);
+                        if (q.cbank) {
+                            const uint4* pe = q.pe + (hz[u].x & 0xfffu);
+                            for (; left >= 4; left -= 4, pe += 4) ts_eval_c<4, PITCH4>(pe, base, P4, key0, key1, acc0, acc1);
+                            if (left >= 2) ts_eval_c<2, PITCH4>(pe, base, P4, key0, key1, acc0, acc1), pe += 2, left -= 2;
+                            if (left >= 1) ts_eval_c<1, PITCH4>(pe, base, P4, key0, key1, acc0, acc1);
+                        } else {
+                            uint32_t ce = ent_a + (hz[u].x & 0xfffu) * kTsEntBytes;
+                            for (; left >= 4; left -= 4, ce += 4 * kTsEntBytes) ts_eval<4, PITCH4>(ce, base, P4, key0, key1, acc0, acc1);
+                            if (left >= 2) ts_eval<2, PITCH4>(ce, base, P4, key0, key1, acc0, acc1), ce += 2 * kTsEntBytes, left -= 2;
+                            if (left >= 1) ts_eval<1, PITCH4>(ce, base, P4, key0, key1, acc0, acc1);
+                        }
                         const float rs = __uint_as_float(hz[u].y);
                         o0[u] = fmaf(rs, R0, acc0);  // the entry and tail weights carry the 1 / C of the average
                         o1[u] = fmaf(rs, R1, acc1);
@@ -887,7 +930,8 @@ int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsign
     if (static_cast<int64_t>(K) * E > kTsMaxEntries) return unsupported("more than 1024 (horizon, n-step) entries");
     if (E > 255 || nmax > 1023) return unsupported("more than 255 n-steps per horizon or an n-step above 1023");
 
-    TsParams q{};
+    static thread_local TsParams q;  // 20 KB with the constant-bank copies: not on the stack
+    q = TsParams{};
     q.p = p;
     q.gamma = p.tab.gamma;
     q.nc = (N + kTsRows - 1) / kTsRows;
@@ -914,6 +958,24 @@ int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsign
     q.ent = reinterpret_cast<const TsEntry*>(dhdr + 4 + 4 * K);
     q.tail4 = reinterpret_cast<const uint4*>(dhdr + (4 + 4 * K + 4 * static_cast<int64_t>(E) * K + 3) / 4 * 4);
     q.n_ent = total;
+    {
+        const char* cb = getenv("PPO_TSLAB_CBANK");
+        q.cbank = cb ? atoi(cb) : 0;  // (opt-in until measured on the GPU)
+        const TsHorizon* hh = reinterpret_cast<const TsHorizon*>(hdr + 4);
+        const TsEntry* he = reinterpret_cast<const TsEntry*>(hdr + 4 + 4 * K);
+        for (int k = 0; k < K; ++k) {
+            uint32_t rs;
+            memcpy(&rs, &hh[k].rscale, 4);
+            q.ph[k] = make_uint2(static_cast<uint32_t>(hh[k].beg) | (static_cast<uint32_t>(hh[k].cnt) << 12) |
+                                     (static_cast<uint32_t>(hh[k].maxn) << 20), rs);
+        }
+        for (int i = 0; i < total; ++i) {
+            uint32_t a, b;
+            memcpy(&a, &he[i].wlo, 4), memcpy(&b, &he[i].whi, 4);
+            q.pe[i] = make_uint4(he[i].off | (static_cast<uint32_t>(he[i].n) << kTsOffBits), a, b, 0u);
+        }
+        for (int i = total; i < total + 4; ++i) q.pe[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
 
     int dev = 0, max_smem = 0;
     PPO_CUDA(cudaGetDevice(&dev));

@@ -10,7 +10,7 @@ Mirrors, with the reference's names and state:
 
 Both are the forward recurrence ``x_t = r_t + gamma * (1 - done_t) * x_{t-1}`` followed, step by step, by a merge of the
 batch moments of ``x_t`` over the envs into the running moments.  The reference does N NumPy passes; here one scan
-launch, two row-reduction launches and one fold.  With envs sharded evenly over ranks (``group``) the only exchange is
+launch, two row-reduction launches and one fold.  With envs sharded over ranks (``group``; uneven shards allowed) the only exchange is
 the all-reduce of the two [N] row vectors (``tools/dist_check.py`` checks the sharded result against the unsharded one
 on real GPUs).  No CPU fallback.
 """
@@ -28,6 +28,25 @@ def _world(group):
     if dist.is_available() and dist.is_initialized():
         return dist.get_world_size(group)
     return 1
+
+
+_env_totals = {}
+
+
+def global_env_count(envs, group=None, device=None):
+    """Envs over all ranks of ``group``.  Shards may be uneven (``rollout.shard_envs`` gives the remainder to the low
+    ranks), so the count is summed over the ranks -- one tiny all-reduce the first time a (group, local count) pair is
+    seen, cached afterwards: every rank must keep its shard size between calls (collective on first use)."""
+    if _world(group) == 1:
+        return int(envs)
+    key = (id(group) if group is not None else 0, int(envs))
+    total = _env_totals.get(key)
+    if total is None:
+        on_gpu = dist.get_backend(group) == "nccl"
+        t = torch.tensor([int(envs)], dtype=torch.int64, device=(device or dev.require_cuda()) if on_gpu else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        total = _env_totals[key] = int(t.item())
+    return total
 
 
 class RunningMeanStd:
@@ -74,7 +93,7 @@ def _fold_rows(x, rms_state, group, row_var):
     s = dev.stream_ptr()
     sums = torch.empty(steps, dtype=torch.float64, device=x.device)
     sq = torch.empty(steps, dtype=torch.float64, device=x.device)
-    total = float(envs * _world(group))
+    total = float(global_env_count(envs, group, x.device))  # the true count: shards need not be equal
     _lib.check(lib.ppo_row_sums(dev.ptr(x), steps, envs, 0, total, dev.ptr(sums), s), "ppo_row_sums")
     if _world(group) > 1:
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)

@@ -90,20 +90,24 @@ class NativeTables:
 
 
 def build_tables(gamma, steps, required_horizons, value_sample_horizons, n_step_samples,
-                 use_log_interpolation=False):
+                 use_log_interpolation=False, host=None):
     """Resolve a ``[K, C]`` n-step sample table into the packed index tables (host side of ``ppo_tvf_targets``).
     Raises like the reference: ``AssertionError`` for an n-step outside ``1..N`` (rl/returns_truncated.py:597),
-    ``IndexError`` for a bootstrap horizon beyond the last value horizon (:157)."""
+    ``IndexError`` for a bootstrap horizon beyond the last value horizon (:157).
+    ``host``: an int32 CPU tensor to build into (reused when large enough; see :class:`TableRing`)."""
     lib = _lib.load()
-    req = np.ascontiguousarray(np.asarray(required_horizons).reshape(-1), dtype=np.int64)
-    vsh = np.ascontiguousarray(np.asarray(value_sample_horizons).reshape(-1), dtype=np.int64)
+    req = required_horizons if _is_i64_vector(required_horizons) else \
+        np.ascontiguousarray(np.asarray(required_horizons).reshape(-1), dtype=np.int64)
+    vsh = value_sample_horizons if _is_i64_vector(value_sample_horizons) else \
+        np.ascontiguousarray(np.asarray(value_sample_horizons).reshape(-1), dtype=np.int64)
     samples = np.asarray(n_step_samples)
     assert samples.ndim == 2 and samples.shape[0] == len(req), \
         f"n_step_samples must be [K, C] with K={len(req)}, got {samples.shape}"
     assert samples.shape[1] >= 1, "at least one n-step sample per horizon is required"
     samples = np.ascontiguousarray(samples, dtype=np.int64)
     words = int(lib.ppo_tvf_tables_words(len(req), samples.shape[1], int(steps)))
-    host = torch.empty(max(words, 16), dtype=torch.int32, pin_memory=torch.cuda.is_available())
+    if host is None or host.numel() < words:
+        host = torch.empty(max(words, 16), dtype=torch.int32, pin_memory=torch.cuda.is_available())
     layout = _CLayout()
     rc = lib.ppo_tvf_tables_build(float(gamma), int(steps), req.ctypes.data, len(req), vsh.ctypes.data, len(vsh),
                                   samples.ctypes.data, samples.shape[1], int(bool(use_log_interpolation)),
@@ -120,14 +124,49 @@ def build_tables(gamma, steps, required_horizons, value_sample_horizons, n_step_
     return t
 
 
-def _upload_tables(tabs, device):
+def _is_i64_vector(a):
+    return isinstance(a, np.ndarray) and a.dtype == np.int64 and a.ndim == 1 and a.flags.c_contiguous
+
+
+class TableRing:
+    """Rotating (pinned host blob, device blob) pairs for a pass that rebuilds its tables every rollout
+    (``rl/returns_truncated.py:85-129`` draws a new sample table per call): no allocation per rebuild, the upload is
+    one asynchronous copy on the current stream, and a host blob is rewritten only after the copy that read it has
+    finished (an event per slot; with three slots the wait is over long before the slot comes round again)."""
+
+    def __init__(self, device, slots=3):
+        self.device = device
+        self.slots = [dict(host=None, dev=None, event=None) for _ in range(slots)]
+        self.i = 0
+
+    def build(self, gamma, steps, req, vsh, n_step_samples, use_log):
+        slot = self.slots[self.i]
+        self.i = (self.i + 1) % len(self.slots)
+        if slot["event"] is not None:
+            slot["event"].synchronize()
+        tabs = build_tables(gamma, steps, req, vsh, n_step_samples, use_log, host=slot["host"])
+        slot["host"] = tabs.host
+        if slot["dev"] is None or slot["dev"].numel() < tabs.host.numel():
+            slot["dev"] = torch.empty(tabs.host.numel(), dtype=torch.int32, device=self.device)
+        ctab, keep = _upload_tables(tabs, self.device, dev_blob=slot["dev"])
+        if slot["event"] is None:
+            slot["event"] = torch.cuda.Event()
+        slot["event"].record()
+        return tabs, ctab, keep
+
+
+def _upload_tables(tabs, device, dev_blob=None):
     """One packed H2D copy of all tables; returns (ctypes struct, tensors keeping the memory alive).
     ``tabs``: :class:`NativeTables`, or the NumPy reference builder's ``TvfTables`` (tests; no host mirror, so
     the transposed slab kernel is not available for it)."""
     c = _CTables()
     if isinstance(tabs, NativeTables):
         n = int(tabs.layout.total_words)
-        blob = tabs.host[:n].to(device, non_blocking=True)
+        if dev_blob is not None:
+            blob = dev_blob[:n]
+            blob.copy_(tabs.host[:n], non_blocking=True)
+        else:
+            blob = tabs.host[:n].to(device, non_blocking=True)
         base = blob.data_ptr()
         for i, name in enumerate(_TABLE_NAMES):
             setattr(c, name, base + 4 * int(tabs.layout.offset_words[i]))
@@ -386,37 +425,67 @@ def _calculate_sampled_return_multi_fast(gamma: float, rewards, dones, required_
                    n_step_samples, use_log_interpolation, path)
 
 
+_weight_cache = {}
+
+
+def _sample_weights(distribution, steps, n_step):
+    """Normalised float32 n-step weights of ``rl/returns_truncated.py:60-80`` (computed with the reference's own
+    Python-float expressions, then cached: they depend on the three arguments only)."""
+    key = (distribution, int(steps), n_step)
+    w = _weight_cache.get(key)
+    if w is None:
+        lamb = 1 - (1 / n_step)
+
+        def get_weights(f):
+            return np.asarray([f(n) for n in range(1, steps + 1)], dtype=np.float32)
+
+        if distribution == "exponential":
+            w = get_weights(lambda x: lamb ** x)
+        elif distribution == "uniform":
+            w = get_weights(lambda x: 1)
+        elif distribution == "hyperbolic":
+            w = get_weights(lambda x: 1 / x)
+        elif distribution == "quadratic":
+            w = get_weights(lambda x: 1 / (steps + (x * x)))
+        else:
+            raise ValueError(f"Invalid distribution {distribution}")
+        w /= np.sum(w)
+        w.setflags(write=False)
+        if len(_weight_cache) > 64:
+            _weight_cache.clear()
+        _weight_cache[key] = w
+    return w
+
+
+def _choice_1_to_n(weights, size):
+    """``np.random.choice(range(1, len(weights) + 1), size=size, replace=True, p=weights)`` of the legacy global
+    generator without its per-call argument checks (0.4 ms for 256 weights): the same inverse-CDF draw on the same
+    ``random_sample`` stream (numpy/random/mtrand.pyx, ``RandomState.choice``), so the values and the generator
+    state afterwards are identical (tests/test_tvf_tables_cpu.py)."""
+    cdf = np.asarray(weights, dtype=np.float64).cumsum()
+    cdf /= cdf[-1]
+    idx = cdf.searchsorted(np.random.random_sample(size), side="right")
+    return np.asarray(idx, dtype=np.int64) + 1
+
+
 def draw_n_step_samples(distribution, mode, required_horizons, steps, n_step, max_samples, seed=None):
     """The reference's host-side draw of the n-step table (``rl/returns_truncated.py:60-129``), with the same
-    global ``np.random`` calls in the same order so that a seed reproduces the reference's table.
+    global ``np.random`` draws in the same order so that a seed reproduces the reference's table.
     Returns a ``[K, C]`` int table, or for ``mode == "full"`` the normalised float32 weights ``[N]``."""
     n_req = len(required_horizons)
-    lamb = 1 - (1 / n_step)
-
-    def get_weights(f):
-        return np.asarray([f(n) for n in range(1, steps + 1)], dtype=np.float32)
-
     if distribution == "fixed":
         return np.zeros([n_req, 1], dtype=np.int32) + n_step
-    elif distribution == "exponential":
-        weights = get_weights(lambda x: lamb ** x)
-    elif distribution == "uniform":
-        weights = get_weights(lambda x: 1)
-    elif distribution == "hyperbolic":
-        weights = get_weights(lambda x: 1 / x)
-    elif distribution == "quadratic":
-        weights = get_weights(lambda x: 1 / (steps + (x * x)))
-    else:
-        raise ValueError(f"Invalid distribution {distribution}")
-    weights /= np.sum(weights)
+    weights = _sample_weights(distribution, steps, n_step)
+    if mode == "full":
+        return weights.copy()
     if seed is not None:
         np.random.seed(seed)
     choices = range(1, len(weights) + 1)
     if mode == "standard":
-        samples = np.random.choice(choices, size=(1, max_samples), replace=True, p=weights)
+        samples = _choice_1_to_n(weights, (1, max_samples))
         return np.repeat(samples, n_req, axis=0)
     elif mode == "advanced":
-        return np.random.choice(choices, size=(n_req, max_samples), replace=True, p=weights)
+        return _choice_1_to_n(weights, (n_req, max_samples))
     elif mode in ("clipped", "adaptive"):
         samples = np.zeros([n_req, max_samples], dtype=np.int32)
         for k in range(n_req):

@@ -245,10 +245,15 @@ def calculate_returns(ext_rewards, ext_value_estimates, terminals, gamma, lambda
 
 class PeerMailbox:
     """Statistics mailboxes of every rank of ``group`` mapped into this process over NVLink peer memory (CUDA IPC,
-    ``ppo_peer_alloc`` / ``ppo_peer_open``), for ``ppo_gae_normalized_peers``: rank r owns ``[world, 16]`` float64
-    records followed by ``world`` 64-bit flag words; ``mail_ptrs[r]`` / ``flag_ptrs[r]`` are rank r's buffers as seen
-    from here.  Construction is collective.  ``ok`` is False when some rank cannot map a peer: callers then keep the
-    all-reduce."""
+    ``ppo_peer_alloc`` / ``ppo_peer_open``), for ``ppo_gae_normalized_peers``: rank r owns ``[2, world, 16]`` float64
+    records followed by ``2 x world`` 64-bit flag words (two halves used alternately by epoch parity);
+    ``mail_ptrs[r]`` / ``flag_ptrs[r]`` are rank r's buffers as seen from here.  Construction is collective.  ``ok``
+    is False when some rank cannot map a peer: callers then keep the all-reduce (and the mappings are released).
+
+    A rank whose peers do not launch within ``timeout_ms`` (env ``PPO_PEER_TIMEOUT_MS``, default 4000: ranks that
+    step their envs at different speeds should meet at a host barrier before the pass) gives up instead of hanging the
+    GPU: the kernel stores the epoch into ``status`` (mapped pinned host memory) and writes NaN advantages;
+    :meth:`check` raises ``TimeoutError`` for it."""
 
     def __init__(self, device, group=None):
         lib = _lib.load()
@@ -256,12 +261,14 @@ class PeerMailbox:
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.global_stats = torch.zeros(_lib.STATS_LEN, dtype=torch.float64, device=device)
         self.epoch = 0
-        mail_bytes = self.world * _lib.STATS_LEN * 8
+        self.timeout_ms = float(os.environ.get("PPO_PEER_TIMEOUT_MS", "4000"))
+        self.status = torch.zeros(1, dtype=torch.int64, pin_memory=True)  # written by the kernel on a timed-out wait
+        mail_bytes = 2 * self.world * _lib.STATS_LEN * 8
         self._own, self._opened = ctypes.c_void_p(), []
         handle = (ctypes.c_ubyte * 64)()
         ok = self.world <= _lib.MAX_PEERS
         with torch.cuda.device(device):
-            ok = ok and lib.ppo_peer_alloc(mail_bytes + self.world * 8, ctypes.byref(self._own), handle) == 0
+            ok = ok and lib.ppo_peer_alloc(mail_bytes + 2 * self.world * 8, ctypes.byref(self._own), handle) == 0
             handles = [None] * self.world
             dist.all_gather_object(handles, bytes(handle) if ok else None, group=group)
             bases = []
@@ -281,10 +288,23 @@ class PeerMailbox:
         self.ok = bool(flag.item())
         self.mail_ptrs = (ctypes.c_void_p * self.world)(*bases)
         self.flag_ptrs = (ctypes.c_void_p * self.world)(*[b + mail_bytes if b else 0 for b in bases])
+        if not self.ok:
+            self.close()
 
     def next_epoch(self):
         self.epoch += 1
         return self.epoch
+
+    def check(self):
+        """Raise ``TimeoutError`` if a launch gave up waiting for a peer.  Reads a host word: call it once the stream
+        has drained (``ReturnPass.run`` also looks at it on entry, which reports the failure of an earlier pass)."""
+        epoch = int(self.status[0])
+        if epoch:
+            raise TimeoutError(
+                f"ppo_gae_normalized_peers: rank {self.rank} waited more than {self.timeout_ms:.0f} ms for the statistics "
+                f"record of a peer in pass {epoch} (of {self.epoch}); its normalised advantages are NaN.  Some rank did "
+                f"not launch the pass: meet at a barrier before ReturnPass.run(), raise PPO_PEER_TIMEOUT_MS, or set "
+                f"PPO_PEER_EXCHANGE=0 for the NCCL all-reduce")
 
     def close(self):
         """Unmap the peers and free the own mailbox (collective in spirit: no rank may still be launching)."""
@@ -335,7 +355,10 @@ class ReturnPass:
         self.tvf_returns = torch.empty((self.steps, self.envs, self.n_h), **f32)
         self.stats = torch.zeros(_lib.STATS_LEN, dtype=torch.float64, device=self.device)
         self.tvf_stats = torch.zeros(_lib.STATS_LEN, dtype=torch.float64, device=self.device)
-        self._moments = self.stats[_lib.STAT_COUNT:_lib.STAT_ADV_SUMSQ + 1]
+        # `stats` is always THIS rank's record; `global_stats` the record merged over the ranks of the group (the same
+        # tensor on one GPU, the peer exchange's merged record, or an all-gather + ppo_merge_stats with NCCL)
+        self._gstats = torch.zeros(_lib.STATS_LEN, dtype=torch.float64, device=self.device) if self.sharded else None
+        self.global_stats = self._gstats if self.sharded else self.stats
         self.ws_gae = torch.zeros(max(int(self.lib.ppo_gae_workspace_bytes(self.envs)), 1 << 12),
                                   dtype=torch.uint8, device=self.device)
         self.ws_tvf = torch.zeros(max(int(self.lib.ppo_tvf_workspace_bytes(self.steps, self.envs)), 1 << 12),
@@ -350,7 +373,11 @@ class ReturnPass:
             if fits.item() == 1 and dist.get_world_size(group) <= _lib.MAX_PEERS:
                 box = PeerMailbox(self.device, group)
                 self.peers = box if box.ok else None
+                if self.peers is not None:
+                    self.global_stats = box.global_stats
         self._ctab = self._blob = None
+        self._ring = _rt.TableRing(self.device)
+        self._hz64 = np.ascontiguousarray(self.horizons.reshape(-1), dtype=np.int64)
         # GAE inside the target launch (the transposed slab kernel's scan warp): measured slower than the separate
         # cooperative GAE launch on B200 (0.536 vs 0.506 ms per pass at 256 x 4096 x 128: the target kernel is issue
         # bound and every consumer waits for the scheduler that also carries the scan warp), so it is opt-in
@@ -368,10 +395,27 @@ class ReturnPass:
             self.peers.close()
             self.peers = None
 
+    def _merge_global(self):
+        """NCCL form of the exchange: all-gather of the per-rank records + ``ppo_merge_stats`` in rank order (identical
+        bits on every rank), into ``global_stats``; ``stats`` stays local."""
+        if not self.sharded:
+            return self.stats
+        self.global_stats = self._gstats
+        self._gstats.copy_(self.stats)
+        allreduce_stats(self._gstats, self.group)
+        return self._gstats
+
+    def check_peers(self):
+        """Raise ``TimeoutError`` if the in-kernel peer exchange of an earlier pass gave up on a rank that never launched
+        (call after the stream has drained; see :class:`PeerMailbox`)."""
+        if self.peers is not None:
+            self.peers.check()
+
     def set_samples(self, n_step_samples):
-        tabs = _rt.build_tables(self.tvf_gamma, self.steps, self.horizons, self.horizons, n_step_samples,
-                                self.use_log)
-        self._ctab, self._blob = _rt._upload_tables(tabs, self.device)
+        """Resolve and upload a new ``[K, C]`` sample table: host integers only (about 0.3 ms for 128 horizons x 8
+        samples), into rotating pinned/device blobs, one asynchronous copy on the current stream -- call it per pass."""
+        tabs, self._ctab, self._blob = self._ring.build(self.tvf_gamma, self.steps, self._hz64, self._hz64,
+                                                        n_step_samples, self.use_log)
         return tabs
 
     def run(self, rewards, values, dones, value_samples, tvf_events=None):
@@ -384,6 +428,8 @@ class ReturnPass:
         target launch then runs first and writes ``self.value_estimates [N+1, A]`` as a by-product of the value rows
         it streams, and GAE reads that contiguous buffer."""
         assert self._ctab is not None, "call set_samples() first"
+        if self.peers is not None:
+            self.peers.check()  # an earlier pass that gave up on a peer (host word, no synchronisation)
         lib, s = self.lib, dev.stream_ptr()
         n, a, k = self.steps, self.envs, self.n_h
 
@@ -419,10 +465,8 @@ class ReturnPass:
             targets(extras)
             values = self.value_estimates
             if extras.gae_done:
-                if self.sharded:
-                    dist.all_reduce(self._moments, op=dist.ReduceOp.SUM, group=self.group)
-                rc = lib.ppo_adv_normalize(self.advantage.data_ptr(), n * a, self.stats.data_ptr(), self.eps, self.clip,
-                                           self.advantages.data_ptr(), s)
+                rc = lib.ppo_adv_normalize(self.advantage.data_ptr(), n * a, self._merge_global().data_ptr(), self.eps,
+                                           self.clip, self.advantages.data_ptr(), s)
                 _lib.check(rc, "ppo_adv_normalize")
                 self.gae_fused = True
                 self.kernel_launches_per_pass = self._tvf_launches + 1
@@ -440,9 +484,10 @@ class ReturnPass:
                 self.gamma, self.lambda_policy, self.lambda_value, self.eps, self.clip, self.advantage.data_ptr(),
                 self.ext_returns.data_ptr(), self.advantages.data_ptr(), self.stats.data_ptr(),
                 box.global_stats.data_ptr(), self.ws_gae.data_ptr(), self.ws_gae.numel(), box.rank, box.world,
-                box.mail_ptrs, box.flag_ptrs, box.next_epoch(), s)
+                box.mail_ptrs, box.flag_ptrs, box.next_epoch(), box.status.data_ptr(), box.timeout_ms, s)
             _lib.check(peer_rc, "ppo_gae_normalized_peers")
             assert peer_rc == 1, "ppo_gae_normalized_peers declined a shard shape ppo_gae_normalized_fits accepted"
+            self.global_stats = box.global_stats
             gae_launches = 1
         if peer_rc == 1:
             pass
@@ -453,10 +498,10 @@ class ReturnPass:
                              self.advantage.data_ptr(), self.ext_returns.data_ptr(), self.stats.data_ptr(),
                              self.ws_gae.data_ptr(), self.ws_gae.numel(), s)
             _lib.check(rc, "ppo_gae")
-            dist.all_reduce(self._moments, op=dist.ReduceOp.SUM, group=self.group)
-            rc = lib.ppo_adv_normalize(self.advantage.data_ptr(), n * a, self.stats.data_ptr(), self.eps, self.clip,
-                                       self.advantages.data_ptr(), s)
+            rc = lib.ppo_adv_normalize(self.advantage.data_ptr(), n * a, self._merge_global().data_ptr(), self.eps,
+                                       self.clip, self.advantages.data_ptr(), s)
             _lib.check(rc, "ppo_adv_normalize")
+            gae_launches = 3  # scan, merge of the gathered records, normalisation
         else:
             # one GPU: no exchange between the scan and the normalisation -> one cooperative launch when the grid fits
             rc = lib.ppo_gae_normalized(rewards.data_ptr(), rewards.stride(0), values.data_ptr(), values.stride(0),

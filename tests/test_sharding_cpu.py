@@ -61,6 +61,11 @@ def _worker(rank, world, port, result_dir):
         np.save(os.path.join(result_dir, f"full{rank}.npy"), full.numpy())
         np.save(os.path.join(result_dir, f"moments{rank}.npy"), only.numpy())
         np.save(os.path.join(result_dir, f"local{rank}.npy"), mine.numpy())
+        # uneven shards (51 envs over 2 ranks = 26 + 25): the row folds divide by the true env count
+        from ppo_b200 import normalization
+        mine_envs = rollout.shard_envs(np.zeros([1, 51]), rank, world).shape[1]
+        counts = [normalization.global_env_count(mine_envs), normalization.global_env_count(mine_envs)]  # 2nd: cached
+        np.save(os.path.join(result_dir, f"envs{rank}.npy"), np.asarray([mine_envs] + counts))
     finally:
         dist.destroy_process_group()
 
@@ -81,3 +86,5 @@ def test_allreduce_stats_world_size_2(tmp_path):
         np.testing.assert_allclose(mom[:3], whole[:3], rtol=1e-13)   # the three moments are global ...
         assert np.array_equal(mom[3:], local[3:])                      # ... everything else stays local
     assert np.array_equal(np.load(tmp_path / "full0.npy"), np.load(tmp_path / "full1.npy"))
+    assert np.load(tmp_path / "envs0.npy").tolist() == [26, 51, 51]
+    assert np.load(tmp_path / "envs1.npy").tolist() == [25, 51, 51]

@@ -151,3 +151,52 @@ def test_rediscount_weights_host_arithmetic(golden):
         assert rho[0] == 0 and rho.max() <= 10 and np.all(rho[1:] > 0)
     # clipping engages when discounting up over long horizons (ratio capped at 10, rl/tvf.py:429)
     assert tvf.rediscount_ratios(0.99, 0.9999, [int(h) for h in hz]).max() == 10
+
+
+@pytest.mark.parametrize("distribution", ["exponential", "uniform", "hyperbolic", "quadratic"])
+@pytest.mark.parametrize("mode", ["standard", "advanced"])
+def test_sample_draw_is_numpy_choice_on_the_same_stream(distribution, mode):
+    """draw_n_step_samples skips np.random.choice's argument checks but must draw the very same table and leave the
+    global generator in the very same state (the reference calls np.random.choice, rl/returns_truncated.py:85-129)."""
+    from ppo_b200 import returns_truncated as rt
+    hz = oracle.get_value_head_horizons(32, 3000)
+    steps, n_step, c = 96, 12, 5
+    lamb = 1 - 1 / n_step
+    f = {"exponential": lambda x: lamb ** x, "uniform": lambda x: 1, "hyperbolic": lambda x: 1 / x,
+         "quadratic": lambda x: 1 / (steps + x * x)}[distribution]
+    w = np.asarray([f(n) for n in range(1, steps + 1)], dtype=np.float32)
+    w /= np.sum(w)
+    for seed in (0, 3, 12345):
+        got = rt.draw_n_step_samples(distribution, mode, hz, steps, n_step, c, seed=seed)
+        after = np.random.random_sample(4)
+        np.random.seed(seed)
+        if mode == "standard":
+            want = np.repeat(np.random.choice(range(1, steps + 1), size=(1, c), replace=True, p=w), len(hz), axis=0)
+        else:
+            want = np.random.choice(range(1, steps + 1), size=(len(hz), c), replace=True, p=w)
+        assert got.dtype == want.dtype and np.array_equal(got, want)
+        assert np.array_equal(after, np.random.random_sample(4))
+        # an unseeded draw continues the stream like the reference's call would
+        np.random.seed(seed)
+        a = rt.draw_n_step_samples(distribution, mode, hz, steps, n_step, c)
+        b = rt.draw_n_step_samples(distribution, mode, hz, steps, n_step, c)
+        np.random.seed(seed)
+        shape = (1, c) if mode == "standard" else (len(hz), c)
+        a2 = np.random.choice(range(1, steps + 1), size=shape, replace=True, p=w)
+        b2 = np.random.choice(range(1, steps + 1), size=shape, replace=True, p=w)
+        assert np.array_equal(a[:shape[0]], a2) and np.array_equal(b[:shape[0]], b2)
+
+
+def test_native_builder_reuses_a_host_blob(built_library):
+    """TableRing's reuse: building into a blob that held another table gives the same words as a fresh build."""
+    from ppo_b200 import returns_truncated as rt
+    hz = oracle.get_value_head_horizons(32, 3000)
+    rng = np.random.RandomState(5)
+    t1 = rt.build_tables(0.999, 64, hz, hz, rng.randint(1, 65, size=[32, 6]), False)
+    table = rng.randint(1, 30, size=[32, 4])
+    fresh = rt.build_tables(0.999, 64, hz, hz, table, False)
+    again = rt.build_tables(0.999, 64, hz, hz, table, False, host=t1.host)
+    assert again.host.data_ptr() == t1.host.data_ptr()
+    n = int(fresh.layout.total_words)
+    assert int(again.layout.total_words) == n
+    assert np.array_equal(fresh.host.numpy()[:n], again.host.numpy()[:n])
