@@ -38,12 +38,21 @@ METRIC = "return targets (steps x envs x horizons) per second, full pass: GAE + 
 UNIT = "targets/s"
 
 
-def config(n_gpus):
+STRONG_TOTAL_ENVS = 32768  # BASELINE config 5 as stated: 256 x 32768 x 128 over the whole job
+
+
+def envs_per_gpu(n_gpus, scaling):
+    return ENVS_PER_GPU if scaling == "weak" else STRONG_TOTAL_ENVS // n_gpus
+
+
+def config(n_gpus, scaling="weak"):
+    per_gpu = envs_per_gpu(n_gpus, scaling)
     return {
-        "workload": f"full return pass, {STEPS} steps x {ENVS_PER_GPU} envs x {HORIZONS} horizons per GPU "
-                    f"(total {ENVS_PER_GPU * n_gpus} envs; 8 GPUs = BASELINE config 5): TVF targets + rediscounted "
-                    f"value estimate + GAE / TD(lambda) + advantage normalisation",
-        "steps": STEPS, "envs_per_gpu": ENVS_PER_GPU, "envs_total": ENVS_PER_GPU * n_gpus, "horizons": HORIZONS,
+        "workload": f"full return pass, {STEPS} steps x {per_gpu} envs x {HORIZONS} horizons per GPU "
+                    f"(total {per_gpu * n_gpus} envs; " +
+                    ("8 GPUs = BASELINE config 5" if scaling == "weak" else "BASELINE config 5 at every N, --scaling strong") +
+                    "): TVF targets + rediscounted value estimate + GAE / TD(lambda) + advantage normalisation",
+        "steps": STEPS, "envs_per_gpu": per_gpu, "envs_total": per_gpu * n_gpus, "horizons": HORIZONS,
         "max_horizon": MAX_HORIZON, "gae": {"gamma": GAMMA, "lambda_policy": LAMBDA_POLICY, "lambda_value": LAMBDA_VALUE},
         "tvf": {"gamma": TVF_GAMMA, "distribution": "exponential", "mode": "advanced", "n_step": N_STEP,
                 "samples": SAMPLES, "seed": SAMPLE_SEED},
@@ -51,8 +60,8 @@ def config(n_gpus):
                     f"over NVLink peer mailboxes (NCCL all-reduce with PPO_PEER_EXCHANGE=0)" if n_gpus > 1
                     else "single GPU, no collective",
         "l2": "per-step working set 1.1 GB per GPU exceeds the 126 MB L2, no explicit flush",
-        "sample_table": "drawn on the host with the reference's NumPy RNG calls; resolved index tables uploaded "
-                        "before the device-timed region, rebuilt and uploaded every step inside the e2e region",
+        "sample_table": "a fresh table per pass, drawn on the host with the reference's NumPy RNG calls, resolved "
+                        "(ppo_tvf_tables_build) and uploaded inside both timed regions (device-resident and e2e)",
     }
 
 
@@ -102,7 +111,18 @@ def cpu_baseline_single(envs=1024):
     t0 = time.perf_counter()
     _oracle_pass(r, d, v, vs, hz)
     dt = time.perf_counter() - t0
+    # BASELINE config 1: the reference's own CPU case, GAE over 128 steps x 128 envs (rl/returns.py:58-67)
+    import oracle
+    from ppo_b200 import synthetic
+    r1, d1, v1 = synthetic.rollout(128, 128, seed=0)
+    oracle.gae(r1, v1[:-1], v1[-1], d1, GAMMA, LAMBDA_POLICY)
+    c0 = time.perf_counter()
+    for _ in range(50):
+        oracle.gae(r1, v1[:-1], v1[-1], d1, GAMMA, LAMBDA_POLICY)
+    c1_us = (time.perf_counter() - c0) / 50 * 1e6
     return {"value": STEPS * envs * HORIZONS / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "c1_gae_128x128": {"us_per_call": c1_us, "step_env_per_s": 128 * 128 / (c1_us * 1e-6),
+                               "what": "oracle.gae (NumPy restatement of rl/returns.py:58-67), one core"},
             "sample": f"one full pass of the NumPy oracle over {STEPS} steps x {envs} envs x {HORIZONS} horizons "
                       f"({envs}/{ENVS_PER_GPU} of the per-GPU workload), {dt:.2f} s, single-threaded like the reference; "
                       f"host has {os.cpu_count()} logical cores"}
@@ -118,7 +138,7 @@ def run_reference(args):
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     workers = max(1, min(cores, 16))
-    warmup = min(args.warmup, 1)
+    warmup = args.warmup  # honoured as given: the sample below is sized for steps + warm-up together
     # bounded sample: ~3.4 M targets/s per core -> 256 steps x e envs x 128 horizons take ~e / 104 s; keep the whole
     # run near two minutes, never more than the reference's default 256 agents per call (rl/config.py:791)
     envs_per_worker = int(104 * 120 / (args.steps + warmup))
@@ -136,11 +156,12 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config(args.gpus),
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config(args.gpus, args.scaling),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
                          "sample": f"each step = one full oracle pass over {STEPS} steps x {sample_envs} envs x {HORIZONS} "
                                    f"horizons ({workers} processes x {envs_per_worker} envs), host has {cores} usable cores; "
-                                   f"warm-up capped at {warmup} step(s)"},
+                                   f"{warmup} warm-up step(s) as requested"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -277,10 +298,51 @@ def other_configs(device, peak_gbs, iters=40):
                                            n, a, k, k, ctypes.byref(ctab), rt.PATH_AUTO, tg.data_ptr(), 0, 0, 0,
                                            stream), "ppo_tvf_targets")
         res = timed(c3, nbytes, n * a * k)
-        res["kernel"] = {1: "generic", 2: "ring", 3: "tslab"}.get(lib.ppo_tvf_last_path() & 0xff)
+        res["kernel"] = {1: "generic", 2: "ring", 3: "tslab", 4: "cslab"}.get(lib.ppo_tvf_last_path() & 0xff)
         out[f"c3_tvf_128x1024x128_{name}"] = res
         del keep
     del bufs
+
+    # ---- c5 shape (256 x 4096 x 128) with a FIXED n-step table ("fixed" distribution: one n-step per horizon): one
+    # gather pair per target instead of eight, so the HBM transfers dominate -- through AUTO and on the ring kernel
+    n, a, k = 256, 4096, HORIZONS
+    r = torch.randint(-1, 3, (n, a), device=device, generator=g).float()
+    d = (torch.rand((n, a), device=device, generator=g) < 3 / 101).view(torch.uint8)
+    vs = torch.randn((n + 1, a, k), device=device, generator=g) * 0.4 + 0.1
+    tg = torch.empty((n, a, k), device=device)
+    nbytes = 4 * (n + 1) * a * k + 4 * n * a * k + 5 * n * a
+    table = rt.draw_n_step_samples("fixed", "advanced", hz, n, N_STEP, SAMPLES)
+    ctab, keep = rt._upload_tables(rt.build_tables(TVF_GAMMA, n, hz, hz, table), device)
+    for name, path in (("auto", rt.PATH_AUTO), ("ring", rt.PATH_RING)):
+        def c5(i):
+            _lib.check(lib.ppo_tvf_targets(r.data_ptr(), a, d.data_ptr(), _lib.DONE_U8, a, vs.data_ptr(), a * k, k,
+                                           n, a, k, k, ctypes.byref(ctab), path, tg.data_ptr(), 0, 0, 0, stream),
+                       "ppo_tvf_targets")
+        try:
+            res = timed(c5, nbytes, n * a * k)
+            res["kernel"] = {1: "generic", 2: "ring", 3: "tslab", 4: "cslab"}.get(lib.ppo_tvf_last_path() & 0xff)
+        except Exception as e:  # a path that declines this shape is reported, not hidden
+            res = {"error": repr(e)}
+        res["note"] = "1.07 GB per launch (> L2), targets only (no statistics, no value estimate)"
+        out[f"c5_tvf_256x4096x128_fixed_n_step_20_{name}"] = res
+    del r, d, vs, tg, keep
+
+    # ---- c1: GAE over 128 steps x 128 envs (the reference's own CPU-sized case): one launch, latency bound
+    n, a = 128, 128
+    r = torch.randint(-1, 3, (n, a), device=device, generator=g).float()
+    d = (torch.rand((n, a), device=device, generator=g) < 3 / 101).view(torch.uint8)
+    v = torch.randn((n + 1, a), device=device, generator=g) * 0.4 + 0.1
+    adv = torch.empty((n, a), device=device)
+    ws1 = torch.zeros(max(int(lib.ppo_gae_workspace_bytes(a)), 4096), dtype=torch.uint8, device=device)
+
+    def c1(i):
+        _lib.check(lib.ppo_gae(r.data_ptr(), a, v.data_ptr(), a, 1, v[n].data_ptr(), 1, d.data_ptr(), _lib.DONE_U8, a, n, a,
+                               GAMMA, LAMBDA_POLICY, LAMBDA_POLICY, adv.data_ptr(), 0, 0, ws1.data_ptr(), ws1.numel(),
+                               stream), "ppo_gae")
+    res = timed(c1, n * a * 13, n * a)
+    res["note"] = ("GAE advantages only (rl/returns.py:58-67), 13 B per (t, env), 213 KB in all: pure launch latency; "
+                   "the CPU time of the same call is in cpu_baseline.c1_gae_128x128")
+    out["c1_gae_128x128"] = res
 
     # ---- c4: V-trace 256 steps x 4096 envs x 18 actions (one GPU's worth of the 8-way sharded config is 512 envs)
     n, b, act, sets = 256, 4096, 18, 4
@@ -298,7 +360,7 @@ def other_configs(device, peak_gbs, iters=40):
         beh, tgt, actions, r, d, v, o = bufs[i % sets]
         _lib.check(lib.ppo_vtrace(beh.data_ptr(), tgt.data_ptr(), actions.data_ptr(), 8, r.data_ptr(), d.data_ptr(),
                                   _lib.DONE_U8, v.data_ptr(), v[n].data_ptr(), n, b, act, GAMMA, 1.0,
-                                  o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), stream), "ppo_vtrace")
+                                  o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), None, stream), "ppo_vtrace")
     out["c4_vtrace_256x4096x18"] = dict(
         timed(c4, n * b * 37, n * b), note="37 useful B per (t, env); each gathered 4-byte log-probability costs a 64-byte "
         "DRAM burst: ncu measures 169 MB of DRAM reads per launch (161 B per (t, env), profiles/r01c_vtrace_*), i.e. "
@@ -323,6 +385,161 @@ def other_configs(device, peak_gbs, iters=40):
     return out
 
 
+def sharded_check(rollout, samples, make_pass, rewards, dones, value_samples, device, world, rank):
+    """N > 1, before timing: one pass with the in-kernel peer exchange and one with PPO_PEER_EXCHANGE=0 (NCCL
+    all-gather + merge between two launches) must give the same bits, and the merged moments must be the moments of the
+    all-gathered raw advantages."""
+    import torch
+    import torch.distributed as dist
+    from ppo_b200 import _lib
+    res, outs = {}, {}
+    saved = os.environ.get("PPO_PEER_EXCHANGE")
+    for name, env in (("peers", "1"), ("nccl", "0")):
+        os.environ["PPO_PEER_EXCHANGE"] = env
+        rp = make_pass()
+        rp.set_samples(samples)
+        rp.run(rewards, None, dones, value_samples)
+        torch.cuda.synchronize()
+        status = 0
+        try:
+            rp.check_peers()
+        except TimeoutError:
+            status = 1
+        outs[name] = dict(norm=rp.advantages.clone(), merged=rp.global_stats.clone(), raw=rp.advantage.clone(),
+                          active=rp.peers is not None, status=status, launches=rp.kernel_launches_per_pass)
+        dist.barrier()
+        rp.close()
+    if saved is None:
+        os.environ.pop("PPO_PEER_EXCHANGE", None)
+    else:
+        os.environ["PPO_PEER_EXCHANGE"] = saved
+    pe, nc = outs["peers"], outs["nccl"]
+    flags = torch.tensor([int(torch.equal(pe["norm"], nc["norm"])), int(torch.equal(pe["merged"], nc["merged"])),
+                          int(pe["active"]), int(pe["status"] == 0 and nc["status"] == 0)], device=device)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    # the merged record holds the same bits on every rank (sums are added in rank order everywhere)
+    records = torch.empty((world, _lib.STATS_LEN), dtype=torch.float64, device=device)
+    dist.all_gather(list(records.unbind(0)), pe["merged"].contiguous())
+    identical = all(torch.equal(records[0].view(torch.int64), records[r].view(torch.int64)) for r in range(world))
+    # checksums of the normalised advantages of every rank, both paths
+    sums = torch.empty((world, 2), dtype=torch.int64, device=device)
+    mine = torch.stack([pe["norm"].view(torch.int32).to(torch.int64).sum(), nc["norm"].view(torch.int32).to(torch.int64).sum()])
+    dist.all_gather(list(sums.unbind(0)), mine)
+    # moments of the all-gathered raw advantages against the merged record
+    raw = torch.empty((world,) + tuple(pe["raw"].shape), dtype=torch.float32, device=device)
+    dist.all_gather(list(raw.unbind(0)), pe["raw"].contiguous())
+    x = raw.double()
+    want = [float(x.numel()), float(x.sum().item()), float((x * x).sum().item())]
+    got = [float(records[0][i].item()) for i in (_lib.STAT_COUNT, _lib.STAT_ADV_SUM, _lib.STAT_ADV_SUMSQ)]
+    rel = max(abs(g - w) / max(abs(w), 1e-30) for g, w in zip(got[1:], want[1:]))
+    mean = want[1] / want[0]
+    std = max(want[2] / want[0] - mean * mean, 0.0) ** 0.5
+    renorm = ((pe["raw"].reshape(-1).double() - mean) / (std + 1e-8)).float()
+    norm_err = float((renorm - pe["norm"]).abs().max().item())
+    res = {"peers_active": bool(flags[2].item()), "peers_vs_nccl_advantages_bit_equal": bool(flags[0].item()),
+           "merged_stats_bit_equal_across_paths": bool(flags[1].item()), "merged_stats_identical_on_all_ranks": identical,
+           "advantage_checksums_equal_on_all_ranks": bool((sums[:, 0] == sums[:, 1]).all().item()),
+           "count_exact": got[0] == want[0], "moments_vs_allgathered_raw_rel_err": rel,
+           "normalised_vs_recomputed_max_abs_err": norm_err, "no_peer_timeout": bool(flags[3].item()),
+           "launches_per_pass": {"peers": pe["launches"], "nccl": nc["launches"]}}
+    res["ok"] = bool(res["peers_vs_nccl_advantages_bit_equal"] and res["merged_stats_bit_equal_across_paths"]
+                     and identical and res["advantage_checksums_equal_on_all_ranks"] and res["count_exact"]
+                     and rel < 1e-11 and norm_err < 1e-5 and res["no_peer_timeout"])
+    return res
+
+
+def link_floor(h2d_bytes, d2h_bytes, device, world, iters=5):
+    """What the host link alone allows for one e2e step: every rank at once copies as many bytes host -> device and
+    device -> host as its e2e step moves (pinned buffers, two streams, both directions together), nothing else."""
+    import torch
+    import torch.distributed as dist
+    chunk = 256 << 20
+    hin = torch.empty(min(h2d_bytes, chunk), dtype=torch.uint8).pin_memory()
+    hout = torch.empty(min(d2h_bytes, chunk), dtype=torch.uint8).pin_memory()
+    din, dout = torch.empty(hin.numel(), dtype=torch.uint8, device=device), torch.empty(hout.numel(), dtype=torch.uint8, device=device)
+    s_in, s_out = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+
+    def one():
+        with torch.cuda.stream(s_in):
+            left = h2d_bytes
+            while left > 0:
+                n = min(left, hin.numel())
+                din[:n].copy_(hin[:n], non_blocking=True)
+                left -= n
+        with torch.cuda.stream(s_out):
+            left = d2h_bytes
+            while left > 0:
+                n = min(left, hout.numel())
+                hout[:n].copy_(dout[:n], non_blocking=True)
+                left -= n
+        s_in.synchronize()
+        s_out.synchronize()
+
+    one()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        one()
+    if world > 1:
+        dist.barrier()
+    dt = (time.perf_counter() - t0) / iters
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return dt * 1e3
+
+
+def vtrace_sharded(device, world, total_envs=4096, iters=40):
+    """BASELINE config 4 (V-trace 256 x 4096 x 18) with the env axis over the ranks: no exchange at all, every rank
+    launches its block; device time per launch, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from ppo_b200 import _lib
+    lib = _lib.load()
+    n, act = 256, 18
+    b = total_envs // world
+    g = torch.Generator(device=device)
+    g.manual_seed(77 + (dist.get_rank() if world > 1 else 0))
+    sets = max(2, min(8, (400 << 20) // (n * b * act * 8)))  # rotate through more than L2's worth of log-policies
+    bufs = []
+    for _ in range(sets):
+        beh = torch.log_softmax(torch.randn((n, b, act), device=device, generator=g), dim=-1)
+        tgt = torch.log_softmax(torch.randn((n, b, act), device=device, generator=g), dim=-1)
+        bufs.append((beh, tgt, torch.randint(0, act, (n, b), device=device, generator=g),
+                     torch.randint(-1, 3, (n, b), device=device, generator=g).float(),
+                     (torch.rand((n, b), device=device, generator=g) < 3 / 101).view(torch.uint8),
+                     torch.randn((n + 1, b), device=device, generator=g) * 0.4 + 0.1,
+                     [torch.empty((n, b), device=device) for _ in range(3)]))
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def launch(i):
+        beh, tgt, a, r, d, v, o = bufs[i % sets]
+        _lib.check(lib.ppo_vtrace(beh.data_ptr(), tgt.data_ptr(), a.data_ptr(), 8, r.data_ptr(), d.data_ptr(), _lib.DONE_U8,
+                                  v.data_ptr(), v[n].data_ptr(), n, b, act, GAMMA, 1.0, o[0].data_ptr(), o[1].data_ptr(),
+                                  o[2].data_ptr(), None, stream), "ppo_vtrace")
+    for i in range(6):
+        launch(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        launch(i)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / iters
+    if world > 1:
+        t = torch.tensor([us], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        us = float(t.item())
+    return {"workload": f"V-trace {n} steps x {total_envs} envs x {act} actions, {b} envs per GPU, no exchange",
+            "us_per_launch_max_over_ranks": us, "step_env_per_s": n * total_envs / (us * 1e-6),
+            "useful_gbs_per_gpu": n * b * 37 / us / 1e3}
+
 
 def run_ours(args):
     import torch
@@ -342,7 +559,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     _lib.load()
 
-    steps, envs, n_h = STEPS, ENVS_PER_GPU, HORIZONS
+    steps, envs, n_h = STEPS, envs_per_gpu(world, args.scaling), HORIZONS
     hz = tvf_mod.get_value_head_horizons(n_h, MAX_HORIZON)
     assert len(hz) == n_h
 
@@ -392,6 +609,11 @@ def run_ours(args):
             total = float(t.item())
         return total / args.steps, [e[0].elapsed_time(e[1]) for e in evs], host_s / args.steps * 1e3
 
+    check = None
+    if world > 1:
+        check = sharded_check(rollout, samples,
+                              lambda: rollout.ReturnPass(steps, envs, hz, GAMMA, TVF_GAMMA, LAMBDA_POLICY, LAMBDA_VALUE),
+                              rewards, dones, value_samples, device, world, rank)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -438,6 +660,8 @@ def run_ours(args):
     clocks = sampler.stop()
     h2d = sum(t.numel() * t.element_size() for t in host_in.values()) * world
     d2h = sum(t.numel() * t.element_size() for t in host_out.values()) * world
+    floor_ms = link_floor(h2d // world, d2h // world, device, world)
+    vt_leg = vtrace_sharded(device, world) if world > 1 else None
     e2e_value = targets_per_step * e2e_steps / e2e_s
     # the e2e results must equal the device-resident ones (same inputs, same sample table)
     same = bool(torch.equal(host_out["tvf_returns"], rp.tvf_returns.cpu()))
@@ -483,10 +707,13 @@ def run_ours(args):
         cpu = cpu_baseline_single() if world == 1 and not args.no_cpu_baseline else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config(world), "clocks": clocks,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config(world, args.scaling), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "matches_resident": same,
+                    # the host link alone: all ranks at once copy one step's bytes in both directions, nothing else
+                    "link_floor_ms": floor_ms, "frac_of_link_floor": floor_ms / (e2e_s / e2e_steps * 1e3),
+                    "link_gbs_at_floor": (h2d + d2h) / floor_ms / 1e6,
                     "api": "ppo_b200.rollout.calculate_returns(pinned host tensors, out=pinned host tensors)"},
             "gpu_launches": rp.kernel_launches_per_pass * args.steps,
             "roofline": roofline,
@@ -499,6 +726,10 @@ def run_ours(args):
                              "fixed_table_kernel_ms": sum(fixed_tvf_ms) / len(fixed_tvf_ms),
                              "redraw_over_fixed": ms_per_step / fixed_ms_per_step},
         }
+        if check is not None:
+            line["sharded_check"] = check
+        if vt_leg is not None:
+            line["c4_vtrace_sharded"] = vt_leg
         if other is not None:
             line["other_configs"] = other
         if cpu is not None:
@@ -515,6 +746,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 4096 envs per GPU (default); strong: 32768 envs over the whole job (BASELINE config 5)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~15 s oracle timing (development)")
     ap.add_argument("--no-other-configs", action="store_true",
                     help="skip the kernel-level figures of the other BASELINE configs (clean launch lists under ncu)")

@@ -258,7 +258,18 @@ typedef struct {
     double gamma;
     int64_t cslab_offset_words; /* launch constants of the column slab kernel (header, horizon words, job words,
                                    entries in ascending n-step order with their aligned row groups) */
+    int32_t sections;           /* PPO_TVF_TABLES_* bits of what was actually written (see ppo_tvf_tables_build_ex) */
+    int32_t reserved;
 } ppo_tvf_table_layout;
+
+/* Sections of the blob.  GENERIC: tables [0..14] (entry / tail tables of the generic and ring kernels); TSLAB /
+ * CSLAB: launch constants of the transposed / column slab kernels. */
+enum {
+    PPO_TVF_TABLES_GENERIC = 1,
+    PPO_TVF_TABLES_TSLAB = 2,
+    PPO_TVF_TABLES_CSLAB = 4,
+    PPO_TVF_TABLES_ALL = 7
+};
 
 /*
  * HOST-side construction of the index tables (no device work, no rollout data): resolves a [K, C] n-step sample
@@ -275,6 +286,17 @@ int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* required_ho
                          const int64_t* value_horizons, int64_t n_val, const int64_t* samples, int64_t n_samples,
                          int use_log_interpolation, int32_t* blob, int64_t blob_words,
                          ppo_tvf_table_layout* layout);
+/* The same with a choice of sections, for a caller that rebuilds the tables every rollout and knows which kernel
+ * runs (the build time is proportional to what is written).  A request without PPO_TVF_TABLES_GENERIC is honoured only
+ * if the transposed slab kernel can serve the table (>= 3 distinct n-steps per horizon, <= 1024 entries, adjacent
+ * interpolation slots, 32 / 64 / 128 value horizons, K % 32 == 0, N <= 512): otherwise the generic tables are written
+ * as well, so that some kernel can always run.  layout->sections reports what was written; leave the ppo_tvf_tables
+ * pointers of an unwritten section NULL (ppo_tvf_targets then refuses the kernels that need them instead of reading
+ * stale memory).  Blob offsets and size do not depend on the sections. */
+int ppo_tvf_tables_build_ex(double gamma, int64_t steps, const int64_t* required_horizons, int64_t n_req,
+                            const int64_t* value_horizons, int64_t n_val, const int64_t* samples, int64_t n_samples,
+                            int use_log_interpolation, int sections, int32_t* blob, int64_t blob_words,
+                            ppo_tvf_table_layout* layout);
 
 /* which TVF kernel ppo_tvf_targets may use */
 typedef enum {
@@ -396,12 +418,15 @@ int ppo_tvf_last_horizon_stats(const float* targets, int64_t rows, int64_t n_req
  *   acc_t = rho_t (r_t + g_t V_{t+1} - V_t) + g_t c_t acc_{t+1};  vs = acc + V;  adv_t = rho_t (r_t + g_t vs_{t+1} - V_t)
  * log-policies are contiguous [N, B, ACT]; actions [N, B] are int32 (action_bytes 4) or int64 (8) and may be
  * negative with NumPy semantics; every other array is contiguous [N, B] / [B].  cs_out may be NULL.
+ * bad_action (optional device word, zero it before the launch): set to 1 when some action lies outside
+ * [-ACT, ACT) -- the reference raises IndexError there (rl/vtrace.py:90).  Such an index is clamped to the nearest
+ * valid action, so the launch never reads outside the log-policy rows whether or not the word is given.
  */
 int ppo_vtrace(const float* behaviour_log_policy, const float* target_log_policy,
                const void* actions, int action_bytes, const float* rewards,
                const void* dones, int done_kind, const float* values, const float* final_value,
                int64_t steps, int64_t batch, int64_t n_actions, double gamma, double lamb,
-               float* vs_out, float* adv_out, float* cs_out, void* stream);
+               float* vs_out, float* adv_out, float* cs_out, int* bad_action, void* stream);
 
 /* Trust-region weight 1 / (1 + KL(pi || pi_hat)) per row, pi_hat = min(mu, pi) renormalised over the
  * actions.  Replaces rl/vtrace.py:3-39 `v_trace_trust_region`; rows = N * B, contiguous [rows, ACT]. */

@@ -48,6 +48,8 @@ _SIGNATURES = {
     "ppo_tvf_tables_words": (c_i64, [c_i64, c_i64, c_i64]),
     "ppo_tvf_tables_build": (c_int, [c_dbl, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_int,
                                      c_ptr, c_i64, c_ptr]),
+    "ppo_tvf_tables_build_ex": (c_int, [c_dbl, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_int, c_int,
+                                        c_ptr, c_i64, c_ptr]),
     "ppo_tvf_targets": (c_int, [c_ptr, c_i64, c_ptr, c_int, c_i64, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
                                 c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "ppo_tvf_targets_ex": (c_int, [c_ptr, c_i64, c_ptr, c_int, c_i64, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
@@ -62,7 +64,7 @@ _SIGNATURES = {
     "ppo_tvf_last_horizon_stats": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
     "ppo_memcpy_2d_async": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64, c_ptr]),
     "ppo_vtrace": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_i64, c_i64, c_i64,
-                           c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr]),
+                           c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ppo_vtrace_trust_region": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "ppo_discounted_returns": (c_int, [c_ptr, c_i64, c_ptr, c_int, c_i64, c_ptr, c_i64, c_dbl, c_ptr, c_i64,
                                        c_i64, c_i64, c_ptr, c_ptr]),

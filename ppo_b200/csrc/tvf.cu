@@ -272,8 +272,10 @@ extern "C" int ppo_tvf_targets_ex(const float* rewards, int64_t reward_row_strid
     PPO_REQUIRE(done_kind == PPO_DONE_NONE || dones, "ppo_tvf_targets: dones is null");
     PPO_REQUIRE(tables->n_entries >= 1 && tables->nmax >= 1 && tables->nmax <= steps,
                 "ppo_tvf_targets: tables describe n-steps up to %d for %lld steps", tables->nmax, (long long)steps);
-    PPO_REQUIRE(tables->ent_n && tables->ent_cnt && tables->ent_idx && tables->ent_wlo && tables->ent_whi &&
-                    tables->ent_g && tables->tail_idx && tables->tail_wlo && tables->tail_whi && tables->gpow,
+    // the generic section is all there or all absent (absent: tables built for the slab kernel only)
+    const bool generic_tables = tables->ent_n && tables->ent_cnt && tables->ent_idx && tables->ent_wlo && tables->ent_whi &&
+                                tables->ent_g && tables->tail_idx && tables->tail_wlo && tables->tail_whi && tables->gpow;
+    PPO_REQUIRE(generic_tables || (!tables->ent_n && tables->host_blob && tables->dev_blob && tables->tslab_offset_words > 0),
                 "ppo_tvf_targets: null table pointer");
 
     TvfParams p{};
@@ -325,6 +327,12 @@ extern "C" int ppo_tvf_targets_ex(const float* rewards, int64_t reward_row_strid
         if (path == PPO_TVF_TSLAB && rc != PPO_OK) return rc;
         taken = PPO_TVF_TSLAB;
         if (rc == PPO_OK) vout = nullptr;  // the value estimate was written by the same launch
+    }
+    if (rc == PPO_ERR_UNSUPPORTED && !generic_tables) {
+        // (tables built with ppo_tvf_tables_build_ex for the slab kernel only, and the slab kernel declined)
+        set_error("ppo_tvf_targets: the tables carry no generic section (ppo_tvf_tables_build_ex sections) and the slab "
+                  "kernel cannot take this call; rebuild them with PPO_TVF_TABLES_ALL");
+        return PPO_ERR_UNSUPPORTED;
     }
     if (rc == PPO_ERR_UNSUPPORTED && path != PPO_TVF_GENERIC) {
         rc = launch_tvf_ring(p, tables->tail_cwlo, tables->tail_cwhi, s, false);

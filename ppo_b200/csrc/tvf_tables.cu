@@ -98,7 +98,16 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
                                     const int64_t* value_horizons, int64_t n_val, const int64_t* samples,
                                     int64_t n_samples, int use_log_interpolation,
                                     int32_t* blob, int64_t blob_words, ppo_tvf_table_layout* layout) {
+    return ppo_tvf_tables_build_ex(gamma, steps, required_horizons, n_req, value_horizons, n_val, samples, n_samples,
+                                   use_log_interpolation, PPO_TVF_TABLES_ALL, blob, blob_words, layout);
+}
+
+extern "C" int ppo_tvf_tables_build_ex(double gamma, int64_t steps, const int64_t* required_horizons, int64_t n_req,
+                                       const int64_t* value_horizons, int64_t n_val, const int64_t* samples,
+                                       int64_t n_samples, int use_log_interpolation, int sections,
+                                       int32_t* blob, int64_t blob_words, ppo_tvf_table_layout* layout) {
     PPO_REQUIRE(required_horizons && value_horizons && samples && blob && layout, "ppo_tvf_tables_build: null pointer");
+    PPO_REQUIRE(sections > 0 && (sections & ~PPO_TVF_TABLES_ALL) == 0, "ppo_tvf_tables_build: unknown sections %d", sections);
     PPO_REQUIRE(n_req >= 1 && n_val >= 1 && n_samples >= 1 && steps >= 1, "ppo_tvf_tables_build: bad shape");
     const int K = static_cast<int>(n_req), V = static_cast<int>(n_val), C = static_cast<int>(n_samples);
 
@@ -214,108 +223,14 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
         set_error("ppo_tvf_tables_build: blob of %lld words required, got %lld", (long long)off, (long long)blob_words);
         return PPO_ERR_WORKSPACE;
     }
-    memset(blob, 0, static_cast<size_t>(off) * 4);
-    int32_t* ent_n = blob + offs[0];
-    float* ent_cnt = reinterpret_cast<float*>(blob + offs[1]);
-    int32_t* ent_idx = blob + offs[2];
-    float* ent_wlo = reinterpret_cast<float*>(blob + offs[3]);
-    float* ent_whi = reinterpret_cast<float*>(blob + offs[4]);
-    float* ent_g = reinterpret_cast<float*>(blob + offs[5]);
-    int32_t* tail_idx = blob + offs[6];
-    float* tail_wlo = reinterpret_cast<float*>(blob + offs[7]);
-    float* tail_whi = reinterpret_cast<float*>(blob + offs[8]);
-    float* tail_cwlo = reinterpret_cast<float*>(blob + offs[9]);
-    float* tail_cwhi = reinterpret_cast<float*>(blob + offs[10]);
-    float* gp = reinterpret_cast<float*>(blob + offs[11]);
-    int32_t* tT_idx = blob + offs[12];
-    float* tT_wlo = reinterpret_cast<float*>(blob + offs[13]);
-    float* tT_whi = reinterpret_cast<float*>(blob + offs[14]);
+    // ---- which sections: the transposed slab constants first (cheap), because whether the generic tables can be
+    // skipped depends on whether the slab kernel can serve this table at all
+    bool want_generic = (sections & PPO_TVF_TABLES_GENERIC) != 0;
+    const bool want_tslab = (sections & PPO_TVF_TABLES_TSLAB) != 0, want_cslab = (sections & PPO_TVF_TABLES_CSLAB) != 0;
     int32_t* ts_hdr = blob + offs[15];
     int32_t* t4 = ts_hdr + pad(4 + 4 * static_cast<int64_t>(K) + 4 * ek);  // [K][tail_pitch] x {idx, cwlo / C, cwhi / C, 0}
-    for (int k = 0; k < K; ++k) {
-        const Entry* row = ent.data() + static_cast<size_t>(k) * C;
-        for (int e = 0; e < E; ++e) {
-            const int64_t i = static_cast<int64_t>(e) * K + k;
-            if (e < ent_count[k]) {
-                const Entry& x = row[e];
-                ent_n[i] = x.n, ent_cnt[i] = x.cnt;
-                ent_idx[i] = x.l.lo | (x.l.hi << 16);
-                ent_wlo[i] = x.l.wlo, ent_whi[i] = x.l.whi;
-                ent_g[i] = gpow[x.n];
-            } else {
-                ent_g[i] = gpow[0];  // padding slots: n = 0, weight 0, gamma^0 like the NumPy builder
-            }
-        }
-    }
-    for (int n = 0; n <= nmax; ++n) gp[n] = gpow[n];
-
-    // ---- tails: horizon h_k - m for m = N - t; used for m <= largest entry of the horizon.  One pass per horizon
-    // writes the length-major tables (generic kernel), the horizon-major folded copies and the interleaved records.
-    std::vector<unsigned char>& beyond_tab = sc.beyond;
-    std::vector<uint32_t>& tail_mask = sc.tail_mask;
-    beyond_tab.assign(static_cast<size_t>(K) * (nmax + 1), 0);
-    tail_mask.assign(K, 0);
-    {
-        const double inv_c = 1.0 / static_cast<double>(C);
-        // pass 1, horizon-major (every stream sequential): multiplicities beyond m, folded weights, the horizon-major
-        // tables and the interleaved records; the plain lerp weights are parked for pass 2
-        std::vector<float>& park = sc.park;  // [K][tail_pitch] x {wlo, whi}
-        park.resize(static_cast<size_t>(K) * tpitch * 2);
-        for (int k = 0; k < K; ++k) {
-            const Entry* row = ent.data() + static_cast<size_t>(k) * C;
-            const int ne = ent_count[k], maxn = k_nmax[k];
-            double beyond = 0.0;  // multiplicity of the entries that run past m
-            for (int i = 0; i < ne; ++i) beyond += row[i].cnt;
-            int e = 0;
-            uint32_t mask = 0;
-            unsigned char* bt = beyond_tab.data() + static_cast<size_t>(k) * (nmax + 1);
-            const Lerp* slots = tc.slots.data() + k * cpitch;
-            const unsigned char* oks = tc.ok.data() + k * cpitch;
-            const int64_t dst0 = static_cast<int64_t>(k) * tpitch;
-            unsigned bad = 0;
-            for (int m = 1; m <= maxn; ++m) {
-                while (e < ne && row[e].n <= m) beyond -= row[e++].cnt;
-                bt[m] = static_cast<unsigned char>(std::min(beyond, 255.0));
-                bad |= oks[m] ^ 1u;
-                const Lerp l = slots[m];
-                const int64_t dst = dst0 + m;
-                const int32_t idx = l.lo | (l.hi << 16);
-                const double scale = beyond * static_cast<double>(gpow[m]);
-                const float cwlo = static_cast<float>(static_cast<double>(l.wlo) * scale);
-                const float cwhi = static_cast<float>(static_cast<double>(l.whi) * scale);
-                tT_idx[dst] = idx, tT_wlo[dst] = cwlo, tT_whi[dst] = cwhi;
-                park[2 * dst] = l.wlo, park[2 * dst + 1] = l.whi;
-                const float wl = static_cast<float>(static_cast<double>(cwlo) * inv_c);
-                const float wh = static_cast<float>(static_cast<double>(cwhi) * inv_c);
-                t4[4 * dst] = idx;
-                memcpy(t4 + 4 * dst + 1, &wl, 4), memcpy(t4 + 4 * dst + 2, &wh, 4);
-                // value columns of the final row this tail bootstrap reads (column slab kernel: job masks)
-                mask |= (cwlo != 0.f && l.lo < V) ? 1u << (l.lo / 32 & 31) : 0u;
-                mask |= (cwhi != 0.f && l.hi < V) ? 1u << (l.hi / 32 & 31) : 0u;
-            }
-            if (bad) {
-                set_error("index %d is out of bounds for axis 0 with size %d", V, V);
-                return PPO_ERR_UNSUPPORTED;
-            }
-            tail_mask[k] = mask;
-        }
-        // pass 2: the length-major tables of the generic kernel, transposed in blocks of 16 horizons (one cache line
-        // per table and tail length)
-        for (int kb = 0; kb < K; kb += 16) {
-            const int ke = std::min(kb + 16, K);
-            int bmax = 0;
-            for (int k = kb; k < ke; ++k) bmax = std::max(bmax, k_nmax[k]);
-            for (int m = 1; m <= bmax; ++m)
-                for (int k = kb; k < ke; ++k) {
-                    // (rows beyond the horizon's largest n-step hold zeros in both layouts)
-                    const int64_t i = static_cast<int64_t>(m) * K + k, src = static_cast<int64_t>(k) * tpitch + m;
-                    tail_idx[i] = tT_idx[src], tail_cwlo[i] = tT_wlo[src], tail_cwhi[i] = tT_whi[src];
-                    tail_wlo[i] = m <= k_nmax[k] ? park[2 * src] : 0.f;
-                    tail_whi[i] = m <= k_nmax[k] ? park[2 * src + 1] : 0.f;
-                }
-        }
-    }
-
+    bool tslab_ok = false;
+    memset(ts_hdr, 0, static_cast<size_t>(cs_off - offs[15]) * 4);
     {
         // Per (horizon, n-step) constants of the transposed slab kernel: byte offset of W^T[col][n - 1] in a slab of
         // pitch N | 1, multiplicity * gamma^n * lerp weights (float64 product, rounded once), n.  Entries without a
@@ -324,7 +239,7 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
         int32_t* hdr = ts_hdr;
         const int pitch = static_cast<int>(steps) | 1;
         hdr[0] = kTsConstMagic, hdr[1] = -1, hdr[2] = pitch, hdr[3] = V;
-        bool ok = K <= kTsMaxK && ek <= kTsMaxEntries;
+        bool ok = want_tslab && K <= kTsMaxK && ek <= kTsMaxEntries;
         TsHorizon* hz = reinterpret_cast<TsHorizon*>(hdr + 4);
         TsEntry* te = reinterpret_cast<TsEntry*>(hdr + 4 + 4 * K);
         int total = 0;
@@ -341,7 +256,7 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
                 else if (x.l.hi == x.l.lo) col = x.l.lo, bw = 0.0;
                 else if (x.l.hi == x.l.lo + 1) col = x.l.lo;
                 else { ok = false; break; }
-                // the 1 / C of the sample average is folded in here (and into the tail records above), so the kernel
+                // the 1 / C of the sample average is folded in here (and into the tail records below), so the kernel
                 // finishes a target with one multiply-add
                 const double cg = static_cast<double>(x.cnt) * gp64[x.n] / static_cast<double>(C);
                 TsEntry& t = te[total++];
@@ -355,6 +270,118 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
             h.rscale = static_cast<float>(csum / static_cast<double>(C));
         }
         if (ok) hdr[1] = total;
+        // would ppo_tvf_targets (PPO_TVF_AUTO) take the slab kernel for these tables?  (shape conditions of
+        // launch_tvf_tslab; buffer alignment is the caller's business)
+        tslab_ok = ok && E >= 3 && E <= 255 && nmax <= 1023 && (V == 32 || V == 64 || V == 128) && K % 32 == 0 &&
+                   steps <= 512;
+    }
+    if (!tslab_ok) want_generic = true;  // some kernel must be able to run: never hand out tables nothing can use
+    if (want_generic) memset(blob, 0, static_cast<size_t>(offs[15]) * 4);
+    if (want_cslab) memset(blob + cs_off, 0, static_cast<size_t>(off - cs_off) * 4);
+    else memset(blob + cs_off, 0, kCsHeaderWords * 4);
+    int32_t* ent_n = blob + offs[0];
+    float* ent_cnt = reinterpret_cast<float*>(blob + offs[1]);
+    int32_t* ent_idx = blob + offs[2];
+    float* ent_wlo = reinterpret_cast<float*>(blob + offs[3]);
+    float* ent_whi = reinterpret_cast<float*>(blob + offs[4]);
+    float* ent_g = reinterpret_cast<float*>(blob + offs[5]);
+    int32_t* tail_idx = blob + offs[6];
+    float* tail_wlo = reinterpret_cast<float*>(blob + offs[7]);
+    float* tail_whi = reinterpret_cast<float*>(blob + offs[8]);
+    float* tail_cwlo = reinterpret_cast<float*>(blob + offs[9]);
+    float* tail_cwhi = reinterpret_cast<float*>(blob + offs[10]);
+    float* gp = reinterpret_cast<float*>(blob + offs[11]);
+    int32_t* tT_idx = blob + offs[12];
+    float* tT_wlo = reinterpret_cast<float*>(blob + offs[13]);
+    float* tT_whi = reinterpret_cast<float*>(blob + offs[14]);
+    if (want_generic) {
+        for (int k = 0; k < K; ++k) {
+            const Entry* row = ent.data() + static_cast<size_t>(k) * C;
+            for (int e = 0; e < E; ++e) {
+                const int64_t i = static_cast<int64_t>(e) * K + k;
+                if (e < ent_count[k]) {
+                    const Entry& x = row[e];
+                    ent_n[i] = x.n, ent_cnt[i] = x.cnt;
+                    ent_idx[i] = x.l.lo | (x.l.hi << 16);
+                    ent_wlo[i] = x.l.wlo, ent_whi[i] = x.l.whi;
+                    ent_g[i] = gpow[x.n];
+                } else {
+                    ent_g[i] = gpow[0];  // padding slots: n = 0, weight 0, gamma^0 like the NumPy builder
+                }
+            }
+        }
+        for (int n = 0; n <= nmax; ++n) gp[n] = gpow[n];
+    }
+
+    // ---- tails: horizon h_k - m for m = N - t; used for m <= largest entry of the horizon.  One pass per horizon
+    // writes the horizon-major folded tables and the interleaved records, a second one the length-major tables of the
+    // generic kernel.
+    std::vector<unsigned char>& beyond_tab = sc.beyond;
+    std::vector<uint32_t>& tail_mask = sc.tail_mask;
+    if (want_cslab) beyond_tab.assign(static_cast<size_t>(K) * (nmax + 1), 0);
+    tail_mask.assign(K, 0);
+    {
+        const double inv_c = 1.0 / static_cast<double>(C);
+        // pass 1, horizon-major (every stream sequential): multiplicities beyond m, folded weights, the horizon-major
+        // tables and the interleaved records; the plain lerp weights are parked for pass 2
+        std::vector<float>& park = sc.park;  // [K][tail_pitch] x {wlo, whi}
+        if (want_generic) park.resize(static_cast<size_t>(K) * tpitch * 2);
+        for (int k = 0; k < K; ++k) {
+            const Entry* row = ent.data() + static_cast<size_t>(k) * C;
+            const int ne = ent_count[k], maxn = k_nmax[k];
+            double beyond = 0.0;  // multiplicity of the entries that run past m
+            for (int i = 0; i < ne; ++i) beyond += row[i].cnt;
+            int e = 0;
+            uint32_t mask = 0;
+            const Lerp* slots = tc.slots.data() + k * cpitch;
+            const unsigned char* oks = tc.ok.data() + k * cpitch;
+            const int64_t dst0 = static_cast<int64_t>(k) * tpitch;
+            unsigned bad = 0;
+            for (int m = 1; m <= maxn; ++m) {
+                while (e < ne && row[e].n <= m) beyond -= row[e++].cnt;
+                bad |= oks[m] ^ 1u;
+                const Lerp l = slots[m];
+                const int64_t dst = dst0 + m;
+                const int32_t idx = l.lo | (l.hi << 16);
+                const double scale = beyond * static_cast<double>(gpow[m]);
+                const float cwlo = static_cast<float>(static_cast<double>(l.wlo) * scale);
+                const float cwhi = static_cast<float>(static_cast<double>(l.whi) * scale);
+                if (want_generic) {
+                    tT_idx[dst] = idx, tT_wlo[dst] = cwlo, tT_whi[dst] = cwhi;
+                    park[2 * dst] = l.wlo, park[2 * dst + 1] = l.whi;
+                }
+                const float wl = static_cast<float>(static_cast<double>(cwlo) * inv_c);
+                const float wh = static_cast<float>(static_cast<double>(cwhi) * inv_c);
+                t4[4 * dst] = idx;
+                memcpy(t4 + 4 * dst + 1, &wl, 4), memcpy(t4 + 4 * dst + 2, &wh, 4);
+                if (want_cslab) {
+                    beyond_tab[static_cast<size_t>(k) * (nmax + 1) + m] = static_cast<unsigned char>(std::min(beyond, 255.0));
+                    // value columns of the final row this tail bootstrap reads (column slab kernel: job masks)
+                    mask |= (cwlo != 0.f && l.lo < V) ? 1u << (l.lo / 32 & 31) : 0u;
+                    mask |= (cwhi != 0.f && l.hi < V) ? 1u << (l.hi / 32 & 31) : 0u;
+                }
+            }
+            if (bad) {
+                set_error("index %d is out of bounds for axis 0 with size %d", V, V);
+                return PPO_ERR_UNSUPPORTED;
+            }
+            tail_mask[k] = mask;
+        }
+        // pass 2: the length-major tables of the generic kernel, transposed in blocks of 16 horizons (one cache line
+        // per table and tail length)
+        for (int kb = 0; kb < K && want_generic; kb += 16) {
+            const int ke = std::min(kb + 16, K);
+            int bmax = 0;
+            for (int k = kb; k < ke; ++k) bmax = std::max(bmax, k_nmax[k]);
+            for (int m = 1; m <= bmax; ++m)
+                for (int k = kb; k < ke; ++k) {
+                    // (rows beyond the horizon's largest n-step hold zeros in both layouts)
+                    const int64_t i = static_cast<int64_t>(m) * K + k, src = static_cast<int64_t>(k) * tpitch + m;
+                    tail_idx[i] = tT_idx[src], tail_cwlo[i] = tT_wlo[src], tail_cwhi[i] = tT_whi[src];
+                    tail_wlo[i] = m <= k_nmax[k] ? park[2 * src] : 0.f;
+                    tail_whi[i] = m <= k_nmax[k] ? park[2 * src + 1] : 0.f;
+                }
+        }
     }
 
     {
@@ -367,14 +394,14 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
         hdr[0] = kCsConstMagic, hdr[1] = -1, hdr[2] = static_cast<int32_t>(steps), hdr[3] = V;
         const int jobs = (K + 3) / 4;
         hdr[4] = jobs;
-        bool ok = K <= kCsMaxK && K % 4 == 0 && ek <= kCsMaxEntries && V % 32 == 0 && V <= 128 && steps % 128 == 0 &&
-                  steps <= 256;
+        bool ok = want_cslab && K <= kCsMaxK && K % 4 == 0 && ek <= kCsMaxEntries && V % 32 == 0 && V <= 128 &&
+                  steps % 128 == 0 && steps <= 256;
         CsHorizon* hzw = reinterpret_cast<CsHorizon*>(hdr + kCsHeaderWords);
         uint32_t* jobw = reinterpret_cast<uint32_t*>(hzw + K);
         int32_t* vhw = reinterpret_cast<int32_t*>(jobw + pad(jobs));  // [128] value horizons (the kernel interpolates with them)
         CsEntry* ce = reinterpret_cast<CsEntry*>(vhw + 128);
         uint32_t* nib = reinterpret_cast<uint32_t*>(ce + ek + 1);  // multiplicities of the n-steps beyond m, 4 bits each
-        for (int j = 0; j < V && j < 128; ++j)
+        for (int j = 0; j < V && j < 128 && want_cslab; ++j)
             vhw[j] = static_cast<int32_t>(std::min<int64_t>(std::max<int64_t>(value_horizons[j], 0), INT32_MAX));
         auto group_of = [&](int col) { return col < V ? col / 32 : (col == V ? kCsSpecial : -1); };
         int total = 0;
@@ -464,6 +491,9 @@ extern "C" int ppo_tvf_tables_build(double gamma, int64_t steps, const int64_t* 
             hdr[1] = total;
         }
     }
+    layout->sections = (want_generic ? PPO_TVF_TABLES_GENERIC : 0) | (want_tslab ? PPO_TVF_TABLES_TSLAB : 0) |
+                       (want_cslab ? PPO_TVF_TABLES_CSLAB : 0);
+    layout->reserved = 0;
     layout->tail_pitch = static_cast<int32_t>(tpitch);
     layout->cslab_offset_words = cs_off;
     layout->gamma = gamma;

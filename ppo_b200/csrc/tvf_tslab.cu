@@ -73,11 +73,6 @@ struct TsParams {
     int val_pitch;           // words per array
     const TsHorizon* hz;  // [K] device copies of the launch constants (inside the packed table blob)
     const TsEntry* ent;   // [n_ent]
-    // the same constants in the kernel-parameter (constant) bank: the consumers read them with warp-uniform LDC loads,
-    // which cost no shared-memory wavefront (31.5 M of the 105 M wavefronts of a launch were broadcast constant reads)
-    int cbank;                        // 1: consumers read pe / ph below; 0: the packed copies in shared memory
-    uint2 ph[kTsMaxK];                // {beg | cnt << 12 | maxn << 20, rscale}
-    uint4 pe[kTsMaxEntries + 4];      // {off | n << 18, wlo, whi, 0}
     const uint4* tail4;   // [K][tail_pitch] folded tail records {idx lo | hi << 16, cwlo, cwhi, 0}
 };
 
@@ -202,35 +197,9 @@ __device__ __forceinline__ void ts_eval(uint32_t cent, uint32_t base, uint32_t p
     }
 }
 
-// The same with the entry constants taken from the kernel-parameter bank (`e` points at the first of G entries).
-template <int G, int PITCH4>
-__device__ __forceinline__ void ts_eval_c(const uint4* e, uint32_t base, uint32_t p4, uint32_t lim0, uint32_t lim1,
-                                          float& acc0, float& acc1) {
-    uint4 c[G];
-#pragma unroll
-    for (int i = 0; i < G; ++i) c[i] = e[i];
-    float lo0[G], hi0[G], lo1[G], hi1[G];
-#pragma unroll
-    for (int i = 0; i < G; ++i) {
-        const uint32_t a = base + (c[i].x & kTsOffMask);
-        if (PITCH4) {
-            lo0[i] = ts_ldsi<0>(a), hi0[i] = ts_ldsi<PITCH4>(a);
-            lo1[i] = ts_ldsi<kTsRows * 4>(a), hi1[i] = ts_ldsi<PITCH4 + kTsRows * 4>(a);
-        } else {
-            const uint32_t ah = a + p4;
-            lo0[i] = ts_ldsi<0>(a), hi0[i] = ts_ldsi<0>(ah);
-            lo1[i] = ts_ldsi<kTsRows * 4>(a), hi1[i] = ts_ldsi<kTsRows * 4>(ah);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < G; ++i) {
-        const float wlo = __uint_as_float(c[i].y), whi = __uint_as_float(c[i].z);
-        ts_fma_ifw(acc0, lo0[i], hi0[i], wlo, whi, c[i].x, lim0);
-        ts_fma_ifw(acc1, lo1[i], hi1[i], wlo, whi, c[i].x, lim1);
-    }
-}
-
-template <int V, int PITCH>
+// GAE: the optional GAE + TD(lambda) stage of the scan warp is compiled in (a separate instantiation: the default
+// kernel is sensitive to code size)
+template <int V, int PITCH, bool GAE>
 __global__ void __launch_bounds__(kTsThreads, 1)
 tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUtensorMap vmap,
                  const __grid_constant__ CUtensorMap omap) {
@@ -316,7 +285,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
         __shared__ uint32_t warp_total[kTsMaxK / 32];
         const int k = threadIdx.x;  // K <= 128 < blockDim.x
         uint4 h = make_uint4(0, 0, 0, 0);
-        if (k < K && !q.cbank) h = __ldg(reinterpret_cast<const uint4*>(q.hz) + k);  // beg, cnt, rscale, maxn
+        if (k < K) h = __ldg(reinterpret_cast<const uint4*>(q.hz) + k);  // beg, cnt, rscale, maxn
         const uint32_t padded = (h.y + 3u) & ~3u;
         uint32_t incl = padded;
 #pragma unroll
@@ -326,7 +295,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
         }
         if (lane == 31 && warp < kTsMaxK / 32) warp_total[warp] = incl;
         __syncthreads();
-        if (k < K && !q.cbank) {
+        if (k < K) {
             uint32_t pbeg = incl - padded;
             for (int j = 0; j < warp; ++j) pbeg += warp_total[j];
             *reinterpret_cast<uint2*>(smem + q.off_hz + k * 8) = make_uint2(pbeg | (h.y << 12) | (h.w << 20), h.z);
@@ -449,7 +418,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                 if (row == N - 1) gs_sv += vn, gs_qv += static_cast<double>(vn) * vn, gs_nv += 1.0;  // the final estimate, row N
             }
         };
-        for (int e = 0; e < (q.want_gae ? nenv + 2 : nenv); ++e) {
+        for (int e = 0; e < (GAE ? nenv + 2 : nenv); ++e) {
             const uint32_t par = static_cast<uint32_t>(e & 1);
             if (e >= nenv) {
                 // the GAE stage of the last two envs: wait until they have left the pipeline
@@ -502,10 +471,10 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                     l = dn[i] ? 0 : l + 1;
                     ts_sts(rt + static_cast<uint32_t>(row) * 4u, static_cast<float>(x));
                     ts_sts_s32(lt + static_cast<uint32_t>(row) * 4u, l);
-                    if (q.want_gae && row < N) ts_sts(gslot(e, 1) + gpad(row), rr[i]);  // for the GAE stage, two envs later
+                    if (GAE && row < N) ts_sts(gslot(e, 1) + gpad(row), rr[i]);  // for the GAE stage, two envs later
                 }
             }
-            if (q.want_gae) {
+            if (GAE) {
                 // terminal bits of the env, one word per 32 rows (lane l owns rows [l * RPL, (l + 1) * RPL))
                 uint32_t mine = 0;
 #pragma unroll
@@ -530,9 +499,9 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
             if (lane == 0) mbar_arrive(&rfull[par]);
             if (lane == 0 && e == 0) ts_stamp(q, 2);  // first R / lim tables ready
             // env e - 2 has left the pipeline (its tables were released above): its value column is complete
-            if (q.want_gae && e >= 2) gae_env(e - 2);
+            if (GAE && e >= 2) gae_env(e - 2);
         }
-        if (q.want_gae) {
+        if (GAE) {
             // per-CTA record, then the last CTA folds all records in index order (deterministic, no float atomics)
             double rec[PPO_STATS_LEN];
 #pragma unroll
@@ -601,7 +570,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
             }
             mbar_wait_sleep(&rfull[par], (static_cast<uint32_t>(e) >> 1) & 1u, kTsPollNs);
             // (the value column slot e % 3 was read by the GAE stage of env e - 3, which ran before these tables were released)
-            if (q.want_gae && xw == 0 && lane == 31) ts_sts(gslot(e, 0) + gpad(0), row0_val);
+            if (GAE && xw == 0 && lane == 31) ts_sts(gslot(e, 0) + gpad(0), row0_val);
             const uint32_t rt = rt_a + par * rt_bytes;
             // slab of this env; it was last used by env e - nslab (the j-th use of a slab waits for use j - 1)
             const int sl = e % q.nslab;
@@ -661,7 +630,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                     const int i = c * kTsRows + xw + rl * kTsXform;
                     if ((lane & 3) == 0 && i < N) {
                         q.value_out[static_cast<int64_t>(i + 1) * q.vo_rs + env0 + e] = k1;
-                        if (q.want_gae) ts_sts(gslot(e, 0) + gpad(i + 1), k1);
+                        if (GAE) ts_sts(gslot(e, 0) + gpad(i + 1), k1);
                     }
                 } else if (q.want_value == 1 && lane == 31) {
 #pragma unroll
@@ -669,7 +638,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                         const int i = c * kTsRows + xw + rl * kTsXform;
                         if (i < N) {
                             q.value_out[static_cast<int64_t>(i + 1) * q.vo_rs + env0 + e] = part[rl];
-                            if (q.want_gae) ts_sts(gslot(e, 0) + gpad(i + 1), part[rl]);
+                            if (GAE) ts_sts(gslot(e, 0) + gpad(i + 1), part[rl]);
                         }
                     }
                 }
@@ -742,10 +711,7 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
                 for (int quad = (cw + s) % kTsConsumers; quad < q.kq; quad += kTsConsumers) {
                     float o0[4], o1[4];
                     uint2 hz[4];  // {beg | cnt << 12 | maxn << 20, rscale} of the quad's four horizons: two 16-byte reads
-                    if (q.cbank) {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) hz[u] = q.ph[quad * 4 + u];
-                    } else {
+                    {
                         const uint4 a = ts_lds128(hz_a + static_cast<uint32_t>(quad) * 32u);
                         const uint4 b = ts_lds128(hz_a + static_cast<uint32_t>(quad) * 32u + 16u);
                         hz[0] = make_uint2(a.x, a.y), hz[1] = make_uint2(a.z, a.w);
@@ -781,18 +747,11 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         float acc0 = tacc0[u], acc1 = tacc1[u];
+                        uint32_t ce = ent_a + (hz[u].x & 0xfffu) * kTsEntBytes;
                         int left = (q.dbg & 8) ? 0 : static_cast<int>((hz[u].x >> 12) & 0xffu);
-                        if (q.cbank) {
-                            const uint4* pe = q.pe + (hz[u].x & 0xfffu);
-                            for (; left >= 4; left -= 4, pe += 4) ts_eval_c<4, PITCH4>(pe, base, P4, key0, key1, acc0, acc1);
-                            if (left >= 2) ts_eval_c<2, PITCH4>(pe, base, P4, key0, key1, acc0, acc1), pe += 2, left -= 2;
-                            if (left >= 1) ts_eval_c<1, PITCH4>(pe, base, P4, key0, key1, acc0, acc1);
-                        } else {
-                            uint32_t ce = ent_a + (hz[u].x & 0xfffu) * kTsEntBytes;
-                            for (; left >= 4; left -= 4, ce += 4 * kTsEntBytes) ts_eval<4, PITCH4>(ce, base, P4, key0, key1, acc0, acc1);
-                            if (left >= 2) ts_eval<2, PITCH4>(ce, base, P4, key0, key1, acc0, acc1), ce += 2 * kTsEntBytes, left -= 2;
-                            if (left >= 1) ts_eval<1, PITCH4>(ce, base, P4, key0, key1, acc0, acc1);
-                        }
+                        for (; left >= 4; left -= 4, ce += 4 * kTsEntBytes) ts_eval<4, PITCH4>(ce, base, P4, key0, key1, acc0, acc1);
+                        if (left >= 2) ts_eval<2, PITCH4>(ce, base, P4, key0, key1, acc0, acc1), ce += 2 * kTsEntBytes, left -= 2;
+                        if (left >= 1) ts_eval<1, PITCH4>(ce, base, P4, key0, key1, acc0, acc1);
                         const float rs = __uint_as_float(hz[u].y);
                         o0[u] = fmaf(rs, R0, acc0);  // the entry and tail weights carry the 1 / C of the average
                         o1[u] = fmaf(rs, R1, acc1);
@@ -895,14 +854,21 @@ tvf_tslab_kernel(const __grid_constant__ TsParams q, const __grid_constant__ CUt
 
 static uint32_t ts_align(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
+template <int V, int PITCH, bool GAE>
+static int ts_launch_one(const TsParams& q, const CUtensorMap& vmap, const CUtensorMap& omap, int64_t grid,
+                         cudaStream_t stream) {
+    PPO_CUDA(cudaFuncSetAttribute(tvf_tslab_kernel<V, PITCH, GAE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(q.smem_total)));
+    tvf_tslab_kernel<V, PITCH, GAE><<<static_cast<unsigned>(grid), kTsThreads, q.smem_total, stream>>>(q, vmap, omap);
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
 template <int V, int PITCH>
 static int ts_launch_variant(const TsParams& q, const CUtensorMap& vmap, const CUtensorMap& omap, int64_t grid,
                              cudaStream_t stream) {
-    PPO_CUDA(cudaFuncSetAttribute(tvf_tslab_kernel<V, PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(q.smem_total)));
-    tvf_tslab_kernel<V, PITCH><<<static_cast<unsigned>(grid), kTsThreads, q.smem_total, stream>>>(q, vmap, omap);
-    PPO_CUDA(cudaGetLastError());
-    return PPO_OK;
+    return q.want_gae ? ts_launch_one<V, PITCH, true>(q, vmap, omap, grid, stream)
+                      : ts_launch_one<V, PITCH, false>(q, vmap, omap, grid, stream);
 }
 
 // stats / partials / ticket: optional fused statistics of the longest horizon (workspace layout of tvf.cu).
@@ -920,8 +886,7 @@ int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsign
     if (K > kTsMaxK || K % 32 != 0) return unsupported("required horizons must be a multiple of 32, at most 128");
     if (N > kTsMaxChunks * kTsRows) return unsupported("more than 512 steps");
     if (!p.tab.host_blob || !p.tab.dev_blob) return unsupported("tables carry no host mirror (ppo_tvf_tables_build)");
-    if (!p.tab.tailT_idx || !p.tab.tailT_cwlo || !p.tab.tailT_cwhi || p.tab.tail_pitch <= nmax)
-        return unsupported("horizon-major tail tables missing");
+    if (p.tab.tail_pitch <= nmax) return unsupported("tail records missing (tail_pitch)");
     if (!(p.tab.gamma > 0.0)) return unsupported("tables carry no gamma");
     if ((reinterpret_cast<uintptr_t>(p.vs) & 15) || (p.vs_es * 4) % 16 || (p.vs_rs * 4) % 16 || p.vs_es < V)
         return unsupported("value samples are not 16-byte aligned / strided");
@@ -930,8 +895,7 @@ int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsign
     if (static_cast<int64_t>(K) * E > kTsMaxEntries) return unsupported("more than 1024 (horizon, n-step) entries");
     if (E > 255 || nmax > 1023) return unsupported("more than 255 n-steps per horizon or an n-step above 1023");
 
-    static thread_local TsParams q;  // 20 KB with the constant-bank copies: not on the stack
-    q = TsParams{};
+    TsParams q{};
     q.p = p;
     q.gamma = p.tab.gamma;
     q.nc = (N + kTsRows - 1) / kTsRows;
@@ -958,24 +922,6 @@ int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsign
     q.ent = reinterpret_cast<const TsEntry*>(dhdr + 4 + 4 * K);
     q.tail4 = reinterpret_cast<const uint4*>(dhdr + (4 + 4 * K + 4 * static_cast<int64_t>(E) * K + 3) / 4 * 4);
     q.n_ent = total;
-    {
-        const char* cb = getenv("PPO_TSLAB_CBANK");
-        q.cbank = cb ? atoi(cb) : 0;  // (opt-in until measured on the GPU)
-        const TsHorizon* hh = reinterpret_cast<const TsHorizon*>(hdr + 4);
-        const TsEntry* he = reinterpret_cast<const TsEntry*>(hdr + 4 + 4 * K);
-        for (int k = 0; k < K; ++k) {
-            uint32_t rs;
-            memcpy(&rs, &hh[k].rscale, 4);
-            q.ph[k] = make_uint2(static_cast<uint32_t>(hh[k].beg) | (static_cast<uint32_t>(hh[k].cnt) << 12) |
-                                     (static_cast<uint32_t>(hh[k].maxn) << 20), rs);
-        }
-        for (int i = 0; i < total; ++i) {
-            uint32_t a, b;
-            memcpy(&a, &he[i].wlo, 4), memcpy(&b, &he[i].whi, 4);
-            q.pe[i] = make_uint4(he[i].off | (static_cast<uint32_t>(he[i].n) << kTsOffBits), a, b, 0u);
-        }
-        for (int i = total; i < total + 4; ++i) q.pe[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
 
     int dev = 0, max_smem = 0;
     PPO_CUDA(cudaGetDevice(&dev));

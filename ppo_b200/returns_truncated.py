@@ -35,7 +35,11 @@ class _CLayout(ctypes.Structure):
     """``ppo_tvf_table_layout`` of include/ppo_b200.h."""
     _fields_ = [("n_entries", ctypes.c_int32), ("nmax", ctypes.c_int32), ("total_words", ctypes.c_int64),
                 ("offset_words", ctypes.c_int64 * 16), ("inv_c", ctypes.c_float), ("tail_pitch", ctypes.c_int32),
-                ("gamma", ctypes.c_double), ("cslab_offset_words", ctypes.c_int64)]
+                ("gamma", ctypes.c_double), ("cslab_offset_words", ctypes.c_int64),
+                ("sections", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+TABLES_GENERIC, TABLES_TSLAB, TABLES_CSLAB, TABLES_ALL = 1, 2, 4, 7  # PPO_TVF_TABLES_* of include/ppo_b200.h
 
 
 class _CExtras(ctypes.Structure):
@@ -90,11 +94,13 @@ class NativeTables:
 
 
 def build_tables(gamma, steps, required_horizons, value_sample_horizons, n_step_samples,
-                 use_log_interpolation=False, host=None):
+                 use_log_interpolation=False, host=None, sections=TABLES_ALL):
     """Resolve a ``[K, C]`` n-step sample table into the packed index tables (host side of ``ppo_tvf_targets``).
     Raises like the reference: ``AssertionError`` for an n-step outside ``1..N`` (rl/returns_truncated.py:597),
     ``IndexError`` for a bootstrap horizon beyond the last value horizon (:157).
-    ``host``: an int32 CPU tensor to build into (reused when large enough; see :class:`TableRing`)."""
+    ``host``: an int32 CPU tensor to build into (reused when large enough; see :class:`TableRing`).
+    ``sections``: ``TABLES_*`` bits (``ppo_tvf_tables_build_ex``): ``TABLES_TSLAB`` alone writes only what the transposed
+    slab kernel reads -- when that kernel can serve the table; the builder adds the generic tables itself otherwise."""
     lib = _lib.load()
     req = required_horizons if _is_i64_vector(required_horizons) else \
         np.ascontiguousarray(np.asarray(required_horizons).reshape(-1), dtype=np.int64)
@@ -109,9 +115,9 @@ def build_tables(gamma, steps, required_horizons, value_sample_horizons, n_step_
     if host is None or host.numel() < words:
         host = torch.empty(max(words, 16), dtype=torch.int32, pin_memory=torch.cuda.is_available())
     layout = _CLayout()
-    rc = lib.ppo_tvf_tables_build(float(gamma), int(steps), req.ctypes.data, len(req), vsh.ctypes.data, len(vsh),
-                                  samples.ctypes.data, samples.shape[1], int(bool(use_log_interpolation)),
-                                  host.data_ptr(), host.numel(), ctypes.byref(layout))
+    rc = lib.ppo_tvf_tables_build_ex(float(gamma), int(steps), req.ctypes.data, len(req), vsh.ctypes.data, len(vsh),
+                                     samples.ctypes.data, samples.shape[1], int(bool(use_log_interpolation)),
+                                     int(sections), host.data_ptr(), host.numel(), ctypes.byref(layout))
     if rc == _lib.PPO_ERR_BAD_ARG:
         raise AssertionError(lib.ppo_last_error().decode("utf-8", "replace"))
     if rc == _lib.PPO_ERR_UNSUPPORTED:
@@ -130,29 +136,58 @@ def _is_i64_vector(a):
 
 class TableRing:
     """Rotating (pinned host blob, device blob) pairs for a pass that rebuilds its tables every rollout
-    (``rl/returns_truncated.py:85-129`` draws a new sample table per call): no allocation per rebuild, the upload is
-    one asynchronous copy on the current stream, and a host blob is rewritten only after the copy that read it has
-    finished (an event per slot; with three slots the wait is over long before the slot comes round again)."""
+    (``rl/returns_truncated.py:85-129`` draws a new sample table per call): no allocation per rebuild, and the upload
+    is one asynchronous copy on a side stream, so it overlaps the kernels of the previous pass instead of sitting
+    between two passes on the compute stream.  Ordering, all with events and no host waits in the steady state:
+
+    * the compute stream waits for the copy before the launch that reads the blob (:meth:`before_launch`);
+    * the copy into a device blob waits for the last launch that read that blob (:meth:`after_launch` records it);
+    * a host blob is rewritten only after the copy that read it has finished (three slots: over long before the slot
+      comes round again)."""
 
     def __init__(self, device, slots=3):
         self.device = device
-        self.slots = [dict(host=None, dev=None, event=None) for _ in range(slots)]
+        self.slots = [dict(host=None, dev=None, copied=None, used=None) for _ in range(slots)]
         self.i = 0
+        self.current = None
+        self._pending = False
+        self.copy_stream = torch.cuda.Stream(device=device)
 
-    def build(self, gamma, steps, req, vsh, n_step_samples, use_log):
+    def build(self, gamma, steps, req, vsh, n_step_samples, use_log, sections=TABLES_ALL):
         slot = self.slots[self.i]
         self.i = (self.i + 1) % len(self.slots)
-        if slot["event"] is not None:
-            slot["event"].synchronize()
-        tabs = build_tables(gamma, steps, req, vsh, n_step_samples, use_log, host=slot["host"])
+        if slot["copied"] is not None:
+            slot["copied"].synchronize()
+        tabs = build_tables(gamma, steps, req, vsh, n_step_samples, use_log, host=slot["host"], sections=sections)
         slot["host"] = tabs.host
         if slot["dev"] is None or slot["dev"].numel() < tabs.host.numel():
             slot["dev"] = torch.empty(tabs.host.numel(), dtype=torch.int32, device=self.device)
-        ctab, keep = _upload_tables(tabs, self.device, dev_blob=slot["dev"])
-        if slot["event"] is None:
-            slot["event"] = torch.cuda.Event()
-        slot["event"].record()
+            slot["used"] = None
+        with torch.cuda.stream(self.copy_stream):
+            if slot["used"] is not None:
+                self.copy_stream.wait_event(slot["used"])
+            else:  # first use of this device blob: it was allocated on the compute stream
+                self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+            ctab, keep = _upload_tables(tabs, self.device, dev_blob=slot["dev"])
+            if slot["copied"] is None:
+                slot["copied"] = torch.cuda.Event()
+            slot["copied"].record(self.copy_stream)
+        self.current = slot
+        self._pending = True
         return tabs, ctab, keep
+
+    def before_launch(self):
+        """The compute stream waits for the upload of the current tables (once per upload)."""
+        if self.current is not None and self._pending:
+            torch.cuda.current_stream(self.device).wait_event(self.current["copied"])
+            self._pending = False
+
+    def after_launch(self):
+        """Marks the current device blob as read by the launches enqueued so far."""
+        if self.current is not None:
+            if self.current["used"] is None:
+                self.current["used"] = torch.cuda.Event()
+            self.current["used"].record(torch.cuda.current_stream(self.device))
 
 
 def _upload_tables(tabs, device, dev_blob=None):
@@ -162,14 +197,19 @@ def _upload_tables(tabs, device, dev_blob=None):
     c = _CTables()
     if isinstance(tabs, NativeTables):
         n = int(tabs.layout.total_words)
+        generic = bool(tabs.layout.sections & TABLES_GENERIC)
+        first = 0 if generic else int(tabs.layout.offset_words[15])  # unwritten sections are not uploaded either
         if dev_blob is not None:
             blob = dev_blob[:n]
-            blob.copy_(tabs.host[:n], non_blocking=True)
-        else:
+            blob[first:].copy_(tabs.host[first:n], non_blocking=True)
+        elif generic:
             blob = tabs.host[:n].to(device, non_blocking=True)
+        else:
+            blob = torch.empty(n, dtype=torch.int32, device=device)
+            blob[first:].copy_(tabs.host[first:n], non_blocking=True)
         base = blob.data_ptr()
         for i, name in enumerate(_TABLE_NAMES):
-            setattr(c, name, base + 4 * int(tabs.layout.offset_words[i]))
+            setattr(c, name, base + 4 * int(tabs.layout.offset_words[i]) if generic else None)
         c.n_entries, c.nmax, c.inv_c = tabs.n_entries, tabs.nmax, float(tabs.inv_c)
         c.tail_pitch, c.gamma = tabs.layout.tail_pitch, tabs.layout.gamma
         c.host_blob, c.dev_blob = tabs.host.data_ptr(), base

@@ -377,6 +377,12 @@ class ReturnPass:
                     self.global_stats = box.global_stats
         self._ctab = self._blob = None
         self._ring = _rt.TableRing(self.device)
+        # Every section of the tables until a pass has run on the transposed slab kernel; from then on only what that
+        # kernel reads (a third of the host work per rebuild).  The builder itself falls back to all sections for a
+        # table the slab kernel cannot serve, and run() rebuilds if the kernel declines a lean table at launch.
+        self._sections = _rt.TABLES_ALL
+        self._lean_tables = False
+        self._samples = None
         self._hz64 = np.ascontiguousarray(self.horizons.reshape(-1), dtype=np.int64)
         # GAE inside the target launch (the transposed slab kernel's scan warp): measured slower than the separate
         # cooperative GAE launch on B200 (0.536 vs 0.506 ms per pass at 256 x 4096 x 128: the target kernel is issue
@@ -414,8 +420,10 @@ class ReturnPass:
     def set_samples(self, n_step_samples):
         """Resolve and upload a new ``[K, C]`` sample table: host integers only (about 0.3 ms for 128 horizons x 8
         samples), into rotating pinned/device blobs, one asynchronous copy on the current stream -- call it per pass."""
+        self._samples = n_step_samples
         tabs, self._ctab, self._blob = self._ring.build(self.tvf_gamma, self.steps, self._hz64, self._hz64,
-                                                        n_step_samples, self.use_log)
+                                                        n_step_samples, self.use_log, sections=self._sections)
+        self._lean_tables = not tabs.layout.sections & _rt.TABLES_GENERIC
         return tabs
 
     def run(self, rewards, values, dones, value_samples, tvf_events=None):
@@ -434,6 +442,7 @@ class ReturnPass:
         n, a, k = self.steps, self.envs, self.n_h
 
         def targets(extras):
+            self._ring.before_launch()  # the tables' upload runs on a side stream
             if tvf_events is not None:  # (start, end) around the target launch(es)
                 tvf_events[0].record()
             # targets + statistics of the longest horizon (+ value estimate): one launch on the transposed slab
@@ -443,12 +452,26 @@ class ReturnPass:
                 value_samples.data_ptr(), value_samples.stride(0), value_samples.stride(1), n, a, k, k,
                 ctypes.byref(self._ctab), self.tvf_path, self.tvf_returns.data_ptr(), self.tvf_stats.data_ptr(),
                 self.ws_tvf.data_ptr(), self.ws_tvf.numel(), ctypes.byref(extras) if extras is not None else None, s)
+            if rc == _lib.PPO_ERR_UNSUPPORTED and self._lean_tables:
+                # the slab kernel declined at launch (e.g. buffer alignment): all sections from now on, and once more
+                self._sections = _rt.TABLES_ALL
+                self.set_samples(self._samples)
+                self._ring.before_launch()
+                rc = lib.ppo_tvf_targets_ex(
+                    rewards.data_ptr(), rewards.stride(0), dones.data_ptr(), _lib.DONE_U8, dones.stride(0),
+                    value_samples.data_ptr(), value_samples.stride(0), value_samples.stride(1), n, a, k, k,
+                    ctypes.byref(self._ctab), self.tvf_path, self.tvf_returns.data_ptr(), self.tvf_stats.data_ptr(),
+                    self.ws_tvf.data_ptr(), self.ws_tvf.numel(), ctypes.byref(extras) if extras is not None else None, s)
             _lib.check(rc, "ppo_tvf_targets")
             last = lib.ppo_tvf_last_path()
             self.tvf_kernel = {1: "generic", 2: "ring", 3: "tslab", 4: "cslab"}.get(last & 0xff, "?")
+            if self.tvf_kernel == "tslab" and self.tvf_path == _rt.PATH_AUTO and self._sections == _rt.TABLES_ALL \
+                    and os.environ.get("PPO_TVF_LEAN_TABLES", "1") != "0":
+                self._sections = _rt.TABLES_TSLAB
             self._tvf_launches = 1 + (0 if last & 0x100 else 1) + (1 if extras is not None and not last & 0x200 else 0)
             if tvf_events is not None:
                 tvf_events[1].record()
+            self._ring.after_launch()
 
         if values is None:
             if self.value_estimates is None:

@@ -27,8 +27,13 @@ def v_trace_trust_region(behaviour_log_policy, target_log_policy):
 
 
 def importance_sampling_v_trace(behaviour_log_policy, target_log_policy, actions, rewards, dones,
-                                target_value_estimates, target_value_final_estimate, gamma, lamb=1.0):
-    """V-trace targets ``(vs, weighted_advantages, cs)``, each ``[N, B]`` (reference: ``rl/vtrace.py:44-114``)."""
+                                target_value_estimates, target_value_final_estimate, gamma, lamb=1.0, check=True):
+    """V-trace targets ``(vs, weighted_advantages, cs)``, each ``[N, B]`` (reference: ``rl/vtrace.py:44-114``).
+
+    An action outside ``[-A, A)`` raises ``IndexError`` like the reference's fancy index (``rl/vtrace.py:90``): host
+    arrays are checked before the upload, device tensors by the kernel itself (it clamps the index and raises a flag
+    word that is read back after the launch -- one 4-byte copy and a stream synchronisation; ``check=False`` skips the
+    read for callers that must stay asynchronous, the clamp stays)."""
     device = dev.require_cuda()
     lib = _lib.load()
     np_like = dev.is_numpy_like(behaviour_log_policy)
@@ -37,7 +42,8 @@ def importance_sampling_v_trace(behaviour_log_policy, target_log_policy, actions
     if beh.dim() != 3 or beh.shape != tgt.shape:
         raise ValueError(f"log policies must both be [N, B, A], got {tuple(beh.shape)} and {tuple(tgt.shape)}")
     steps, batch, n_act = beh.shape
-    if np_like:
+    act_on_host = dev.is_numpy_like(actions)
+    if act_on_host:
         a_host = np.asarray(actions)
         if a_host.size and (a_host.min() < -n_act or a_host.max() >= n_act):  # rl/vtrace.py:90 would raise IndexError
             raise IndexError(f"index {int(a_host.max())} is out of bounds for axis 2 with size {n_act}")
@@ -58,8 +64,11 @@ def importance_sampling_v_trace(behaviour_log_policy, target_log_policy, actions
     vs = torch.empty((steps, batch), dtype=torch.float32, device=device)
     adv = torch.empty_like(vs)
     cs = torch.empty_like(vs)
+    bad = torch.zeros(1, dtype=torch.int32, device=device) if check and not act_on_host else None
     rc = lib.ppo_vtrace(dev.ptr(beh), dev.ptr(tgt), dev.ptr(act), act.element_size(), dev.ptr(r), dev.ptr(d), kind,
                         dev.ptr(v), dev.ptr(fin), steps, batch, n_act, float(gamma), float(lamb),
-                        dev.ptr(vs), dev.ptr(adv), dev.ptr(cs), dev.stream_ptr())
+                        dev.ptr(vs), dev.ptr(adv), dev.ptr(cs), dev.ptr(bad), dev.stream_ptr())
     _lib.check(rc, "ppo_vtrace")
+    if bad is not None and int(bad.item()):
+        raise IndexError(f"an action index is out of bounds for axis 2 with size {n_act}")
     return dev.like_input(vs, np_like), dev.like_input(adv, np_like), dev.like_input(cs, np_like)

@@ -90,6 +90,41 @@ def test_return_pass_resident_and_pinned_out():
     assert torch.equal(out["advantage"], rp.advantage.cpu())
 
 
+def test_return_pass_rebuilds_lean_tables_per_pass():
+    """A pass that redraws its sample table every rollout: after the first pass on the transposed slab kernel only the
+    slab section of the tables is rebuilt and uploaded; the targets must be those of a full build, a table the slab
+    kernel cannot serve (fixed n-step: the ring kernel's case) must still run, and the ring of blobs must survive
+    more rebuilds than it has slots."""
+    steps, envs = 128, 96
+    hz = oracle.get_value_head_horizons(128, 30000)
+    r, d, _ = synthetic.rollout(steps, envs, seed=5)
+    vs = synthetic.value_samples(steps, envs, len(hz), seed=5)
+    dr, dd, dvs = torch.from_numpy(r).cuda(), torch.from_numpy(d).cuda().view(torch.uint8), torch.from_numpy(vs).cuda()
+    rp = rollout.ReturnPass(steps, envs, hz, 0.999, 0.99997, 0.95, 0.9)
+    for i in range(5):
+        table = rt.draw_n_step_samples("exponential", "advanced", hz, steps, 20, 8, seed=10 + i)
+        tabs = rp.set_samples(table)
+        assert bool(tabs.layout.sections & rt.TABLES_GENERIC) == (i == 0)
+        rp.run(dr, None, dd, dvs)
+        assert rp.tvf_kernel == "tslab"
+        fresh = rollout.ReturnPass(steps, envs, hz, 0.999, 0.99997, 0.95, 0.9)
+        fresh.set_samples(table)
+        fresh.run(dr, None, dd, dvs)
+        torch.cuda.synchronize()
+        assert torch.equal(rp.tvf_returns, fresh.tvf_returns) and torch.equal(rp.advantages, fresh.advantages)
+        assert torch.equal(rp.tvf_stats, fresh.tvf_stats)
+    ref = oracle.sampled_return_multi(0.99997, r, d, hz, hz, vs, n_step_samples=table)
+    assert rel_err(rp.tvf_returns.cpu().numpy(), ref) <= TOL
+    fixed = rt.draw_n_step_samples("fixed", "advanced", hz, steps, 20, 8)
+    tabs = rp.set_samples(fixed)
+    assert tabs.layout.sections & rt.TABLES_GENERIC  # the builder kept the generic tables for this one
+    rp.run(dr, None, dd, dvs)
+    torch.cuda.synchronize()
+    assert rp.tvf_kernel != "tslab"
+    ref = oracle.sampled_return_multi(0.99997, r, d, hz, hz, vs, n_step_samples=fixed)
+    assert rel_err(rp.tvf_returns.cpu().numpy(), ref) <= TOL
+
+
 def test_env_sharding_is_exact_on_one_gpu():
     """Two env shards processed separately + summed moments == the unsharded pass (the N > 1 data path without NCCL)."""
     steps, envs = 80, 130

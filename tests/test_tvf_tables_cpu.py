@@ -200,3 +200,31 @@ def test_native_builder_reuses_a_host_blob(built_library):
     n = int(fresh.layout.total_words)
     assert int(again.layout.total_words) == n
     assert np.array_equal(fresh.host.numpy()[:n], again.host.numpy()[:n])
+
+
+def test_lean_sections_write_the_same_slab_constants(built_library):
+    """ppo_tvf_tables_build_ex with the slab section only: same words where the slab kernel reads, the generic tables
+    skipped -- unless the slab kernel could not serve the table, then the builder writes them regardless."""
+    from ppo_b200 import returns_truncated as rt
+    hz = oracle.get_value_head_horizons(128, 30000)
+    table = rt.draw_n_step_samples("exponential", "advanced", hz, 256, 20, 8, seed=2)
+    full = rt.build_tables(0.99997, 256, hz, hz, table, False)
+    lean = rt.build_tables(0.99997, 256, hz, hz, table, False, sections=rt.TABLES_TSLAB)
+    assert full.layout.sections == rt.TABLES_ALL and lean.layout.sections == rt.TABLES_TSLAB
+    lo, hi = int(full.layout.offset_words[15]), int(full.layout.cslab_offset_words)
+    assert (int(lean.layout.offset_words[15]), int(lean.layout.cslab_offset_words)) == (lo, hi)
+    assert np.array_equal(full.host.numpy()[lo:hi], lean.host.numpy()[lo:hi])
+    assert (lean.n_entries, lean.nmax, lean.inv_c) == (full.n_entries, full.nmax, full.inv_c)
+    # the column slab header is invalidated, so that kernel refuses lean tables
+    assert lean.host.numpy()[hi + 1] != full.host.numpy()[hi + 1] or full.host.numpy()[hi + 1] < 0
+    # a fixed n-step table (one entry per horizon: the ring kernel's case) keeps its generic tables
+    fixed = rt.draw_n_step_samples("fixed", "advanced", hz, 256, 20, 8)
+    lean_fixed = rt.build_tables(0.99997, 256, hz, hz, fixed, False, sections=rt.TABLES_TSLAB)
+    full_fixed = rt.build_tables(0.99997, 256, hz, hz, fixed, False)
+    assert lean_fixed.layout.sections & rt.TABLES_GENERIC
+    n_fixed = int(full_fixed.layout.cslab_offset_words)
+    assert np.array_equal(lean_fixed.host.numpy()[:n_fixed], full_fixed.host.numpy()[:n_fixed])
+    # so do shapes the slab kernel does not take (48 horizons)
+    hz48 = oracle.get_value_head_horizons(48, 3000)
+    t48 = rt.draw_n_step_samples("exponential", "advanced", hz48, 64, 12, 6, seed=1)
+    assert rt.build_tables(0.999, 64, hz48, hz48, t48, False, sections=rt.TABLES_TSLAB).layout.sections & rt.TABLES_GENERIC

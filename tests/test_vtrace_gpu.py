@@ -25,6 +25,46 @@ def test_vtrace_vs_oracle(steps, envs, n_act, lamb):
     assert np.abs(got[2] - ref[2]).max() <= 2e-7
 
 
+@pytest.mark.parametrize("ew", ["8", "16", "32"])
+@pytest.mark.parametrize("steps,envs", [(256, 512), (37, 45), (600, 24), (3, 9)])
+def test_vtrace_env_tile_widths(monkeypatch, ew, steps, envs):
+    """Every env-tile width of the kernel (the launcher picks one by occupancy) gives the oracle's answer, for chunk
+    lengths that are register-cached (<= 16 steps per chunk) and that are not (600 steps over 16 chunks)."""
+    monkeypatch.setenv("PPO_VTRACE_EW", ew)
+    r, d, v = synthetic.rollout(steps, envs, seed=steps + envs)
+    beh, tgt, act = synthetic.policies(steps, envs, 18, seed=envs)
+    ref = oracle.importance_sampling_v_trace(beh, tgt, act, r, d, v[:-1], v[-1], 0.999, 0.95)
+    got = vtrace.importance_sampling_v_trace(beh, tgt, act, r, d, v[:-1], v[-1], 0.999, 0.95)
+    for g, f, name in zip(got, ref, ("vs", "adv", "cs")):
+        assert rel_err(g, f) <= TOL, name
+
+
+def test_vtrace_device_actions_out_of_range_raise():
+    """rl/vtrace.py:90 indexes with the actions, so an out-of-range action is an IndexError; for device tensors the
+    kernel itself checks (clamped read + flag word)."""
+    steps, envs, n_act = 32, 40, 6
+    r, d, v = synthetic.rollout(steps, envs, seed=1)
+    beh, tgt, act = synthetic.policies(steps, envs, n_act, seed=1)
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    args = [cu(beh), cu(tgt), None, cu(r), cu(d), cu(v[:-1].copy()), cu(v[-1].copy()), 0.99, 0.9]
+    good = vtrace.importance_sampling_v_trace(*(args[:2] + [cu(act)] + args[3:]))
+    for where, value in (((0, 0), n_act), ((steps - 1, envs - 1), -n_act - 1), ((5, 7), 2 ** 40)):
+        bad = act.astype(np.int64).copy()
+        bad[where] = value
+        with pytest.raises(IndexError):
+            vtrace.importance_sampling_v_trace(*(args[:2] + [cu(bad)] + args[3:]))
+        # check=False: no read-back, the index is clamped (no fault, the other envs are untouched)
+        out = vtrace.importance_sampling_v_trace(*(args[:2] + [cu(bad)] + args[3:]), check=False)
+        torch.cuda.synchronize()
+        keep = np.ones(envs, dtype=bool)
+        keep[where[1]] = False
+        assert np.array_equal(out[0].cpu().numpy()[:, keep], good[0].cpu().numpy()[:, keep])
+    # the most negative valid index still wraps like NumPy
+    ok = act.astype(np.int64).copy()
+    ok[0, 0] = -n_act
+    vtrace.importance_sampling_v_trace(*(args[:2] + [cu(ok)] + args[3:]))
+
+
 def test_vtrace_on_policy_identities():
     # rl/unit_tests.py:61-87: with pi == mu and lambda = 1, vs == bootstrapped returns and adv == GAE(lambda=1)
     steps, envs = 64, 48

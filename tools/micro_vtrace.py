@@ -20,7 +20,7 @@ def run(n, b, act=18, sets=4, iters=40):
     def launch(i):
         beh, tgt, a, r, d, v, o = bufs[i % sets]
         _lib.check(lib.ppo_vtrace(beh.data_ptr(), tgt.data_ptr(), a.data_ptr(), 8, r.data_ptr(), d.data_ptr(), 1, v.data_ptr(),
-                                  v[n].data_ptr(), n, b, act, 0.999, 1.0, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), s), "vt")
+                                  v[n].data_ptr(), n, b, act, 0.999, 1.0, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), None, s), "vt")
     for i in range(6): launch(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
