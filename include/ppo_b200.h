@@ -168,6 +168,16 @@ int ppo_gae_normalized_peers(const float* rewards, int64_t reward_row_stride,
 int ppo_adv_normalize(const float* adv, int64_t count, const double* stats,
                       double eps, double clip, float* out, void* stream);
 
+/*
+ * Extrinsic + intrinsic advantage, rl/rollout.py:1225-1231: out = ext_adv + float32(scale) * int_adv (out may alias
+ * ext_adv), and a statistics record of the result: the ADV_* slots hold count / sum / sumsq / min / max / zeros of the
+ * sum (feed it to ppo_adv_normalize, after the cross-GPU exchange when sharded), the RET_* slots the same of the
+ * scaled intrinsic part (`adv_int` and, with the extrinsic record of ppo_gae, `adv_ratio` of the reference's log).
+ * workspace: ppo_gae_workspace_bytes(0) bytes, zeroed once (left reusable).
+ */
+int ppo_adv_combine(const float* ext_adv, const float* int_adv, double scale, int64_t count, float* out,
+                    double* stats, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Statistics records [n_records][PPO_STATS_LEN] of disjoint env blocks or ranks -> one record: sums are added in
  * record order, min / max are reduced (out may alias records[0]).  Used for the env-blocked host pipeline and, after an
  * all-gather of the per-rank records, for the cross-GPU return statistics. */
@@ -463,6 +473,11 @@ int ppo_row_sums(const double* x, int64_t steps, int64_t envs, const double* row
                  void* stream);
 int ppo_rms_fold(const double* row_sums, const double* row_sq, int64_t steps, double total_envs, double* rms,
                  double* row_var, void* stream);
+/* The same merges plus the wrapper's mode "ema" (rl/wrappers.py:878-881): after every step
+ * alpha = 1 - total_envs / min(count, ema_horizon), *ema_var = alpha * *ema_var + (1 - alpha) * var_over_envs(x_t);
+ * row_var (optional) then records the EMA variance after each step. */
+int ppo_rms_fold_ema(const double* row_sums, const double* row_sq, int64_t steps, double total_envs, double* rms,
+                     double* ema_var, double ema_horizon, double* row_var, void* stream);
 int ppo_scale_rewards(const float* rewards, int64_t reward_row_stride, int64_t steps, int64_t envs, const double* var,
                       int per_row, int mode, double eps, double clip, double scale, const double* center_stats,
                       float* out, unsigned long long* clips, void* stream);

@@ -4,7 +4,7 @@ Restates, in the reference's own order of operations:
 
 * ``RunningMeanStd`` / ``update_mean_var_count_from_moments``  (``rl/utils.py:379-396, 414-443``)
 * ``Runner.calculate_intrinsic_returns``                      (``rl/rollout.py:1140-1180``)
-* ``VecNormalizeRewardWrapper.step`` run over a whole rollout  (``rl/wrappers.py:795-895``), mode "rms", no episodic
+* ``VecNormalizeRewardWrapper.step`` run over a whole rollout  (``rl/wrappers.py:795-899``), modes "rms" / "ema" / "custom", no episodic
   discounting (``ed_type=None``), identity ``returns_transform``
 
 Pinned against outputs of the reference's own source for these pieces, executed by ``tests/golden/make_golden.py``
@@ -63,20 +63,32 @@ def intrinsic_returns(int_rewards, int_value, terminals, gamma_int, lambda_polic
     return adv, adv + int_value[:steps], int_rewards, scale
 
 
-def vec_normalize_rewards(rewards, dones, gamma, current_returns, rms, clip=10.0, scale=1.0, epsilon=1e-2):
+def vec_normalize_rewards(rewards, dones, gamma, current_returns, rms, clip=10.0, scale=1.0, epsilon=1e-2, mode="rms",
+                          ret_var=0.0, ema_horizon=5e6):
     """rl/wrappers.py:825-885 applied to each row of a [N, A] rollout in order.  ``current_returns`` [A] and ``rms``
-    are updated in place.  Returns (scaled rewards [N, A], number of clipped elements)."""
+    are updated in place.  Returns (scaled rewards [N, A], number of clipped elements) for mode "rms" and, for the
+    modes "ema" / "custom" (:878-881, :893-899), additionally the final ``ret_var``."""
     rewards = np.asarray(rewards)
     out = np.zeros(rewards.shape, dtype=np.float64)
     clips = 0
     for t in range(rewards.shape[0]):
         current_returns[:] = rewards[t] + gamma * current_returns * (1 - dones[t])  # :847
         rms.update(current_returns)  # :856 (norms = 1, identity transform)
-        std = math.sqrt(rms.var + epsilon)  # :893-895
+        if mode == "ema":  # :878-881
+            alpha = 1 - (len(dones[t]) / min(rms.count, ema_horizon))
+            ret_var = alpha * ret_var + (1 - alpha) * np.var(current_returns)
+        if mode == "rms":
+            std = math.sqrt(rms.var + epsilon)  # :893-895
+        elif mode in ("ema", "custom"):
+            std = math.sqrt(ret_var + epsilon)  # :896-897
+        else:
+            raise ValueError(f"Invalid mode {mode}")  # :899
         scaled = rewards[t] / std  # :863
         if clip is not None and clip >= 0:  # :866-873
             clipped = np.clip(scaled, -clip, +clip)
             clips += int(np.sum(clipped != scaled))
             scaled = clipped
         out[t] = scaled * scale  # :875
-    return out, clips
+    if mode == "rms":
+        return out, clips
+    return out, clips, ret_var

@@ -43,6 +43,7 @@ _SIGNATURES = {
                                    c_i64, c_i64, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                    c_i64, c_ptr]),
     "ppo_adv_normalize": (c_int, [c_ptr, c_i64, c_ptr, c_dbl, c_dbl, c_ptr, c_ptr]),
+    "ppo_adv_combine": (c_int, [c_ptr, c_ptr, c_dbl, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "ppo_moments": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
     "ppo_tvf_workspace_bytes": (c_i64, [c_i64, c_i64]),
     "ppo_tvf_tables_words": (c_i64, [c_i64, c_i64, c_i64]),
@@ -71,6 +72,7 @@ _SIGNATURES = {
     "ppo_return_tracker_scan": (c_int, [c_ptr, c_i64, c_ptr, c_int, c_i64, c_i64, c_i64, c_dbl, c_ptr, c_ptr, c_ptr]),
     "ppo_row_sums": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_dbl, c_ptr, c_ptr]),
     "ppo_rms_fold": (c_int, [c_ptr, c_ptr, c_i64, c_dbl, c_ptr, c_ptr, c_ptr]),
+    "ppo_rms_fold_ema": (c_int, [c_ptr, c_ptr, c_i64, c_dbl, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr]),
     "ppo_gather_rows": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr]),
     "ppo_tvf_value_loss": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_i64, c_dbl, c_ptr,
                                    c_ptr, c_ptr]),

@@ -704,6 +704,31 @@ __global__ void __launch_bounds__(512) moments_kernel(const MomentsParams p) {
     publish_stats(ts, p.io, red);
 }
 
+// Extrinsic + intrinsic advantage (rl/rollout.py:1225-1231): out = ext + float32(scale) * int, with the statistics of
+// the sum in the ADV_* slots (what the normalisation needs) and of the scaled intrinsic part in the RET_* slots
+// (`adv_int`, `adv_ratio` of the reference's log).
+struct CombineParams {
+    const float* ext;
+    const float* intr;
+    float scale;
+    float* out;
+    int64_t count;
+    ScanStatsIo io;
+};
+
+__global__ void __launch_bounds__(512) adv_combine_kernel(const CombineParams p) {
+    __shared__ double red[32][PPO_STATS_LEN];
+    ThreadStats ts;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.count; i += stride) {
+        const float b = __fmul_rn(p.scale, __ldg(p.intr + i));
+        const float x = __fadd_rn(__ldg(p.ext + i), b);
+        p.out[i] = x;
+        ts.add(x, b);
+    }
+    publish_stats(ts, p.io, red);
+}
+
 struct NormParams {
     const float* x;
     float* out;
@@ -1071,6 +1096,25 @@ extern "C" int ppo_moments(const float* x, int64_t count, double* stats, void* w
     if (rc != PPO_OK) return rc;
     p.io.stats = stats;
     moments_kernel<<<static_cast<unsigned>(blocks), 512, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+extern "C" int ppo_adv_combine(const float* ext_adv, const float* int_adv, double scale, int64_t count, float* out,
+                               double* stats, void* workspace, int64_t workspace_bytes, void* stream) {
+    PPO_REQUIRE(count >= 0 && stats != nullptr, "ppo_adv_combine: bad arguments");
+    PPO_REQUIRE(count == 0 || (ext_adv && int_adv && out), "ppo_adv_combine: null pointer");
+    int64_t blocks = (count + 512 * 8 - 1) / (512 * 8);
+    if (blocks < 1) blocks = 1;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 2;
+    if (blocks > cap) blocks = cap;
+    if (blocks > kMomentsMaxBlocks) blocks = kMomentsMaxBlocks;
+    CombineParams p{};
+    p.ext = ext_adv, p.intr = int_adv, p.scale = static_cast<float>(scale), p.out = out, p.count = count;
+    int rc = split_workspace(workspace, workspace_bytes, blocks, &p.io);
+    if (rc != PPO_OK) return rc;
+    p.io.stats = stats;
+    adv_combine_kernel<<<static_cast<unsigned>(blocks), 512, 0, static_cast<cudaStream_t>(stream)>>>(p);
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;
 }

@@ -120,10 +120,14 @@ __global__ void __launch_bounds__(256) row_sum_kernel(const double* __restrict__
 }
 
 // rl/utils.py:379-396 applied N times in order; rms = {mean, var, count}
+// ema_var (optional, in / out): the wrapper's mode "ema" (rl/wrappers.py:878-881) -- after every merge
+//   alpha = 1 - n / min(count, ema_horizon);  ema = alpha * ema + (1 - alpha) * var_over_envs(x_t)
+// and row_var then records the EMA instead of the running variance.
 __global__ void rms_fold_kernel(const double* __restrict__ row_sum, const double* __restrict__ row_sq, int64_t steps,
-                                double n, double* rms, double* row_var) {
+                                double n, double* rms, double* row_var, double* ema_var, double ema_horizon) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double mean = rms[0], var = rms[1], count = rms[2];
+    double ema = ema_var ? *ema_var : 0.0;
     for (int64_t t = 0; t < steps; ++t) {
         const double bm = row_sum[t] / n, bv = row_sq[t] / n;
         const double delta = __dsub_rn(bm, mean);
@@ -133,9 +137,14 @@ __global__ void rms_fold_kernel(const double* __restrict__ row_sum, const double
         const double cross = __ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(delta, delta), count), n), tot);
         const double m2 = __dadd_rn(__dadd_rn(m_a, m_b), cross);
         mean = new_mean, var = __ddiv_rn(m2, tot), count = tot;
-        if (row_var) row_var[t] = var;
+        if (ema_var) {
+            const double alpha = 1.0 - n / fmin(count, ema_horizon);
+            ema = alpha * ema + (1.0 - alpha) * bv;
+        }
+        if (row_var) row_var[t] = ema_var ? ema : var;
     }
     rms[0] = mean, rms[1] = var, rms[2] = count;
+    if (ema_var) *ema_var = ema;
 }
 
 struct ScaleParams {
@@ -214,7 +223,18 @@ extern "C" int ppo_rms_fold(const double* row_sums, const double* row_sq, int64_
                             double* rms, double* row_var, void* stream) {
     PPO_REQUIRE(steps >= 0 && total_envs > 0.0, "ppo_rms_fold: bad shape");
     PPO_REQUIRE(rms && (steps == 0 || (row_sums && row_sq)), "ppo_rms_fold: null pointer");
-    rms_fold_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(row_sums, row_sq, steps, total_envs, rms, row_var);
+    rms_fold_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(row_sums, row_sq, steps, total_envs, rms, row_var,
+                                                                     nullptr, 0.0);
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+extern "C" int ppo_rms_fold_ema(const double* row_sums, const double* row_sq, int64_t steps, double total_envs,
+                                double* rms, double* ema_var, double ema_horizon, double* row_var, void* stream) {
+    PPO_REQUIRE(steps >= 0 && total_envs > 0.0 && ema_horizon > 0.0, "ppo_rms_fold_ema: bad shape");
+    PPO_REQUIRE(rms && ema_var && (steps == 0 || (row_sums && row_sq)), "ppo_rms_fold_ema: null pointer");
+    rms_fold_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(row_sums, row_sq, steps, total_envs, rms, row_var,
+                                                                     ema_var, ema_horizon);
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;
 }

@@ -86,8 +86,9 @@ class RunningMeanStd:
         self.state.copy_(torch.as_tensor([float(v) for v in state], dtype=torch.float64))
 
 
-def _fold_rows(x, rms_state, group, row_var):
-    """Merge every row of the float64 [N, A] tracker ``x`` into ``rms_state`` in row order."""
+def _fold_rows(x, rms_state, group, row_var, ema=None):
+    """Merge every row of the float64 [N, A] tracker ``x`` into ``rms_state`` in row order.  ``ema``: ``(ema_var device
+    scalar, ema_horizon)`` for the wrapper's mode "ema" (``row_var`` then records the EMA variance per step)."""
     lib = _lib.load()
     steps, envs = x.shape
     s = dev.stream_ptr()
@@ -100,11 +101,15 @@ def _fold_rows(x, rms_state, group, row_var):
     _lib.check(lib.ppo_row_sums(dev.ptr(x), steps, envs, dev.ptr(sums), total, dev.ptr(sq), s), "ppo_row_sums")
     if _world(group) > 1:
         dist.all_reduce(sq, op=dist.ReduceOp.SUM, group=group)
+    if ema is not None:
+        _lib.check(lib.ppo_rms_fold_ema(dev.ptr(sums), dev.ptr(sq), steps, total, dev.ptr(rms_state), dev.ptr(ema[0]),
+                                        float(ema[1]), dev.ptr(row_var), s), "ppo_rms_fold_ema")
+        return
     _lib.check(lib.ppo_rms_fold(dev.ptr(sums), dev.ptr(sq), steps, total, dev.ptr(rms_state), dev.ptr(row_var), s),
                "ppo_rms_fold")
 
 
-def track_returns(rewards, dones, gamma, carry, rms, group=None, want_row_var=False):
+def track_returns(rewards, dones, gamma, carry, rms, group=None, want_row_var=False, ema=None):
     """The tracker scan + the N moment merges.  ``carry`` (float64 device tensor [A]) and ``rms`` are updated in
     place; returns (rewards on the device, running variance after each step [N] or None)."""
     device = dev.require_cuda()
@@ -127,7 +132,7 @@ def track_returns(rewards, dones, gamma, carry, rms, group=None, want_row_var=Fa
     _lib.check(rc, "ppo_return_tracker_scan")
     row_var = torch.empty(steps, dtype=torch.float64, device=device) if want_row_var else None
     if steps and envs:
-        _fold_rows(x, rms.state, group, row_var)
+        _fold_rows(x, rms.state, group, row_var, ema=ema)
     return r, row_var
 
 
@@ -187,16 +192,22 @@ class IntrinsicReturns:
 
 
 class VecNormalizeRewards:
-    """``VecNormalizeRewardWrapper`` (``rl/wrappers.py:795-919``, mode "rms", ``ed_type=None``) over whole rollouts:
-    rewards are divided by the running return std AS OF THEIR OWN STEP, clipped and scaled."""
+    """``VecNormalizeRewardWrapper`` (``rl/wrappers.py:795-919``, ``ed_type=None``) over whole rollouts: rewards are
+    divided by the return std AS OF THEIR OWN STEP, clipped and scaled.  ``mode``: "rms" (running variance over the
+    whole history, what ``rl/envs.py:160-165`` configures), "ema" (``ret_var`` follows the variance of the tracker over
+    the envs with ``alpha = 1 - A / min(count, ema_horizon)``, :878-881) or "custom" (the caller sets ``ret_var``).
+    Episodic-discounting normalisers (``ed_type``) are not provided."""
 
-    def __init__(self, num_envs, initial_state=None, gamma=1.0, clip=10.0, scale=1.0, mode="rms", device=None):
-        if mode != "rms":
-            raise ValueError(f"Invalid mode {mode}: only 'rms' is provided")
+    def __init__(self, num_envs, initial_state=None, gamma=1.0, clip=10.0, scale=1.0, mode="rms", ema_horizon=5e6,
+                 device=None):
+        if mode not in ("rms", "ema", "custom"):
+            raise ValueError(f"Invalid mode {mode}")
         self.device = device or dev.require_cuda()
         self.clip, self.epsilon, self.gamma, self.scale = clip, 1e-2, gamma, scale
+        self.mode, self.ema_horizon = mode, float(ema_horizon)
         self.current_returns = torch.zeros(num_envs, dtype=torch.float64, device=self.device)
         self.ret_rms = RunningMeanStd(shape=(), device=self.device)
+        self._ret_var = torch.zeros(1, dtype=torch.float64, device=self.device)
         if initial_state is not None:
             self.ret_rms.restore_state(initial_state)
 
@@ -208,25 +219,40 @@ class VecNormalizeRewards:
         return self.ret_rms.mean
 
     @property
+    def ret_var(self):
+        return float(self._ret_var.item())
+
+    @ret_var.setter
+    def ret_var(self, value):
+        self._ret_var.fill_(float(value))
+
+    @property
     def std(self):
-        return float(np.sqrt(self.ret_rms.var + self.epsilon))
+        if self.mode == "rms":
+            return float(np.sqrt(self.ret_rms.var + self.epsilon))
+        return float(np.sqrt(self.ret_var + self.epsilon))
 
     def normalize_rollout(self, rewards, dones, group=None):
         """[N, A] raw rewards and dones -> (scaled rewards [N, A] float32, number of clipped elements as a device
         counter)."""
         np_like = dev.is_numpy_like(rewards)
+        ema = (self._ret_var, self.ema_horizon) if self.mode == "ema" else None
         r, row_var = track_returns(rewards, dones, self.gamma, self.current_returns, self.ret_rms, group=group,
-                                   want_row_var=True)
+                                   want_row_var=self.mode != "custom", ema=ema)
         clips = torch.zeros(1, dtype=torch.int64, device=self.device)
         clip = -1.0 if self.clip is None else float(self.clip)
-        out = _scale(r, row_var, True, _lib.SCALE_WRAPPER, self.epsilon, clip, self.scale, None, clips)
+        if self.mode == "custom":  # one fixed variance for the whole rollout
+            out = _scale(r, self._ret_var, False, _lib.SCALE_WRAPPER, self.epsilon, clip, self.scale, None, clips)
+        else:
+            out = _scale(r, row_var, True, _lib.SCALE_WRAPPER, self.epsilon, clip, self.scale, None, clips)
         return dev.like_input(out, np_like), clips
 
     def save_state(self, buffer):
         buffer["ret_rms"] = self.ret_rms.save_state()
-        buffer["ret_var"] = 0.0
+        buffer["ret_var"] = self.ret_var
         buffer["current_returns"] = self.current_returns.cpu().numpy()
 
     def restore_state(self, buffer):
+        self.ret_var = buffer.get("ret_var", 0.0)
         self.ret_rms.restore_state(buffer["ret_rms"])
         self.current_returns.copy_(torch.as_tensor(np.asarray(buffer["current_returns"], dtype=np.float64)))

@@ -393,6 +393,7 @@ class ReturnPass:
         self._tvf_launches = 2
         self.tvf_kernel = "?"
         self.value_estimates = self._value_weights = None
+        self.ext_advantage = self.combined_stats = None  # allocated by the first pass with an intrinsic advantage
 
     def close(self):
         """Release the peer mailboxes (env-sharded passes).  Collective in spirit: call it on every rank once no rank
@@ -411,6 +412,12 @@ class ReturnPass:
         allreduce_stats(self._gstats, self.group)
         return self._gstats
 
+    def adv_ratio(self):
+        """``((ext_advantage**2).mean() / (int_advantage**2).mean())**0.5`` of the last pass with an intrinsic advantage
+        (``adv_ratio`` of ``rl/rollout.py:1230``), from the two statistics records (host float; synchronises)."""
+        ext, comb = self.stats.cpu().numpy(), self.combined_stats.cpu().numpy()
+        return float(np.sqrt(ext[_lib.STAT_ADV_SUMSQ] / comb[_lib.STAT_RET_SUMSQ]))
+
     def check_peers(self):
         """Raise ``TimeoutError`` if the in-kernel peer exchange of an earlier pass gave up on a rank that never launched
         (call after the stream has drained; see :class:`PeerMailbox`)."""
@@ -426,7 +433,7 @@ class ReturnPass:
         self._lean_tables = not tabs.layout.sections & _rt.TABLES_GENERIC
         return tabs
 
-    def run(self, rewards, values, dones, value_samples, tvf_events=None):
+    def run(self, rewards, values, dones, value_samples, tvf_events=None, int_advantage=None, ir_scale=1.0):
         """``rewards [N, A] f32``, ``values [N+1, A] f32`` (row N = final estimate; any strides with a
         unit-stride env axis or a strided view of the value-sample buffer) or ``None``, ``dones [N, A] uint8``,
         ``value_samples [N+1, A, K] f32`` -- all CUDA tensors of this rank's env block.
@@ -434,7 +441,12 @@ class ReturnPass:
         ``values=None`` is the reference's own data flow (``rl/rollout.py:1196``): the estimate GAE reads is taken
         off the value curves (``rl/tvf.py:303-360``: last horizon for the TVF gamma, rediscounted otherwise).  The
         target launch then runs first and writes ``self.value_estimates [N+1, A]`` as a by-product of the value rows
-        it streams, and GAE reads that contiguous buffer."""
+        it streams, and GAE reads that contiguous buffer.
+
+        ``int_advantage [N, A] f32`` (``use_intrinsic_rewards``, ``rl/rollout.py:1225-1231``; e.g. the output of
+        ``normalization.IntrinsicReturns``): ``advantage = ext_advantage + ir_scale * int_advantage`` and the
+        normalisation runs on the sum.  ``ext_advantage`` keeps the extrinsic part, ``stats`` its record,
+        ``combined_stats`` the record of the sum (ADV slots) and of the scaled intrinsic part (RET slots)."""
         assert self._ctab is not None, "call set_samples() first"
         if self.peers is not None:
             self.peers.check()  # an earlier pass that gave up on a peer (host word, no synchronisation)
@@ -483,7 +495,7 @@ class ReturnPass:
             # recurrences of an env as soon as its value column is complete): what is left is the normalisation
             gae_req = dict(gamma=self.gamma, lambda_adv=self.lambda_policy, lambda_ret=self.lambda_value,
                            adv=self.advantage, ret=self.ext_returns, stats=self.stats, workspace=self.ws_gae) \
-                if self.fuse_gae else None
+                if self.fuse_gae and int_advantage is None else None
             extras, _keep = _rt._extras(self.value_estimates, self._value_weights, gae=gae_req)
             targets(extras)
             values = self.value_estimates
@@ -495,6 +507,35 @@ class ReturnPass:
                 self.kernel_launches_per_pass = self._tvf_launches + 1
                 return self
         self.gae_fused = False
+        if int_advantage is not None:
+            # extrinsic scan -> combine (+ statistics of the sum) -> exchange when sharded -> normalisation
+            if self.ext_advantage is None:
+                self.ext_advantage = torch.empty_like(self.advantage)
+                self.combined_stats = torch.zeros(_lib.STATS_LEN, dtype=torch.float64, device=self.device)
+            assert tuple(int_advantage.shape) == (n, a) and int_advantage.is_contiguous() and \
+                int_advantage.dtype == torch.float32, "int_advantage must be a contiguous float32 [N, A] CUDA tensor"
+            rc = lib.ppo_gae(rewards.data_ptr(), rewards.stride(0), values.data_ptr(), values.stride(0),
+                             values.stride(1), values[n].data_ptr(), values.stride(1), dones.data_ptr(), _lib.DONE_U8,
+                             dones.stride(0), n, a, self.gamma, self.lambda_policy, self.lambda_value,
+                             self.ext_advantage.data_ptr(), self.ext_returns.data_ptr(), self.stats.data_ptr(),
+                             self.ws_gae.data_ptr(), self.ws_gae.numel(), s)
+            _lib.check(rc, "ppo_gae")
+            rc = lib.ppo_adv_combine(self.ext_advantage.data_ptr(), int_advantage.data_ptr(), float(ir_scale), n * a,
+                                     self.advantage.data_ptr(), self.combined_stats.data_ptr(), self.ws_gae.data_ptr(),
+                                     self.ws_gae.numel(), s)
+            _lib.check(rc, "ppo_adv_combine")
+            record = self.combined_stats
+            if self.sharded:
+                self.global_stats = self._gstats
+                self._gstats.copy_(self.combined_stats)
+                record = allreduce_stats(self._gstats, self.group)
+            rc = lib.ppo_adv_normalize(self.advantage.data_ptr(), n * a, record.data_ptr(), self.eps, self.clip,
+                                       self.advantages.data_ptr(), s)
+            _lib.check(rc, "ppo_adv_normalize")
+            if values is not self.value_estimates:
+                targets(None)
+            self.kernel_launches_per_pass = self._tvf_launches + 3 + (1 if self.sharded else 0)
+            return self
         gae_launches = 2
         peer_rc = 0
         if self.sharded and self.peers is not None and values.stride(1) == 1:

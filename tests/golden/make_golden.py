@@ -171,8 +171,12 @@ def normalization_vectors(root, ref):
             return None, rewards[t], dones[t], [{} for _ in range(envs)]
 
     for tag, kwargs in [("default", dict(gamma=0.99)), ("noclip", dict(gamma=0.999, clip=-1, scale=0.5)),
-                        ("tight", dict(gamma=0.9, clip=1.0))]:
+                        ("tight", dict(gamma=0.9, clip=1.0)),
+                        ("ema", dict(gamma=0.99, mode="ema", ema_horizon=200.0)),
+                        ("custom", dict(gamma=0.99, mode="custom", clip=3.0))]:
         w = wns["VecNormalizeRewardWrapper"](Env(), **kwargs)
+        if tag == "custom":
+            w.ret_var = 6.25  # "custom requires setting of ret_std" (rl/wrappers.py:821)
         rows, clips = [], 0
         for t in range(steps):
             _, scaled, _, infos = w.step(None)
@@ -182,6 +186,7 @@ def normalization_vectors(root, ref):
         out[f"vn_{tag}_clips"] = np.asarray(clips)
         out[f"vn_{tag}_returns"] = np.asarray(w.current_returns, dtype=np.float64)
         out[f"vn_{tag}_rms"] = np.asarray([w.ret_rms.mean, w.ret_rms.var, w.ret_rms.count], dtype=np.float64)
+        out[f"vn_{tag}_ret_var"] = np.asarray(w.ret_var, dtype=np.float64)
 
     # ---- TVFRunnerModule.on_train_value_minibatch (rl/tvf.py:32-77): per-sample loss and its gradient (autograd)
     import torch

@@ -55,11 +55,16 @@ def test_intrinsic_returns_golden(golden_norm, tag, normalize, center, propagati
 
 
 @pytest.mark.parametrize("tag,kwargs", [("default", dict(gamma=0.99)), ("noclip", dict(gamma=0.999, clip=-1, scale=0.5)),
-                                        ("tight", dict(gamma=0.9, clip=1.0))])
+                                        ("tight", dict(gamma=0.9, clip=1.0)),
+                                        ("ema", dict(gamma=0.99, mode="ema", ema_horizon=200.0)),
+                                        ("custom", dict(gamma=0.99, mode="custom", clip=3.0))])
 def test_vec_normalize_rewards_golden(golden_norm, tag, kwargs):
     g = golden_norm
     w = nz.VecNormalizeRewards(g["vn_in_rewards"].shape[1], **kwargs)
+    if tag == "custom":
+        w.ret_var = 6.25
     scaled, clips = w.normalize_rollout(g["vn_in_rewards"], g["vn_in_dones"])
+    assert abs(w.ret_var - float(g[f"vn_{tag}_ret_var"])) <= 1e-9 * max(1.0, float(g[f"vn_{tag}_ret_var"]))
     assert rel_err(scaled, g[f"vn_{tag}_scaled"]) <= 1e-6
     assert int(clips.item()) == int(g[f"vn_{tag}_clips"])
     assert close64(w.current_returns.cpu().numpy(), g[f"vn_{tag}_returns"])

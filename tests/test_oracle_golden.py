@@ -198,6 +198,14 @@ def test_vec_normalize_rewards(golden_norm):
                                                      clip=kwargs.get("clip", 10.0), scale=kwargs.get("scale", 1.0))
         assert same(scaled, g[f"vn_{tag}_scaled"]) and clips == int(g[f"vn_{tag}_clips"]), tag
         assert same(cur, g[f"vn_{tag}_returns"]) and same(rms.state(), g[f"vn_{tag}_rms"])
+    # modes "ema" and "custom" (rl/wrappers.py:878-881, :896-897)
+    for tag, kwargs in [("ema", dict(mode="ema", ema_horizon=200.0)), ("custom", dict(mode="custom", ret_var=6.25, clip=3.0))]:
+        cur, rms = np.zeros(g["vn_in_rewards"].shape[1], dtype=np.float64), oracle.RunningMeanStd()
+        scaled, clips, ret_var = oracle.vec_normalize_rewards(g["vn_in_rewards"], g["vn_in_dones"], 0.99, cur, rms, **kwargs)
+        assert same(scaled, g[f"vn_{tag}_scaled"]) and clips == int(g[f"vn_{tag}_clips"]), tag
+        assert same(cur, g[f"vn_{tag}_returns"]) and same(rms.state(), g[f"vn_{tag}_rms"])
+        # (the reference takes np.var of its float32-turned-float64 tracker: same bits here)
+        assert same(np.asarray(ret_var, dtype=np.float64), g[f"vn_{tag}_ret_var"]), tag
 
 
 LOSS_CASES = [("all", "off", None, None), ("hweighted", "h_weighted", None, None), ("single", "h_weighted", [5], 5),

@@ -125,6 +125,41 @@ def test_return_pass_rebuilds_lean_tables_per_pass():
     assert rel_err(rp.tvf_returns.cpu().numpy(), ref) <= TOL
 
 
+def test_return_pass_combines_intrinsic_advantage():
+    """rl/rollout.py:1225-1231: advantage = ext_advantage + ir.scale * int_advantage, normalised as a whole."""
+    steps, envs = 96, 160
+    hz = oracle.get_value_head_horizons(128, 30000)
+    r, d, v = synthetic.rollout(steps, envs, seed=21)
+    vs = synthetic.value_samples(steps, envs, len(hz), seed=21)
+    rng = np.random.RandomState(3)
+    int_adv = rng.normal(0.05, 0.3, [steps, envs]).astype(np.float32)
+    table = rt.draw_n_step_samples("exponential", "advanced", hz, steps, 20, 8, seed=1)
+    cu = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()  # noqa: E731
+    rp = rollout.ReturnPass(steps, envs, hz, 0.999, 0.99997, 0.95, 0.9, advantage_clipping=3.0)
+    rp.set_samples(table)
+    for _ in range(2):
+        rp.run(cu(r), cu(v), cu(d).view(torch.uint8), cu(vs), int_advantage=cu(int_adv), ir_scale=0.3)
+    torch.cuda.synchronize()
+    ext = oracle.gae(r, v[:-1], v[-1], d, 0.999, 0.95)
+    comb = ext + np.float32(0.3) * int_adv
+    assert np.array_equal(rp.ext_advantage.cpu().numpy(), ext)
+    assert np.array_equal(rp.advantage.cpu().numpy(), comb)
+    want = np.clip(oracle.normalize_advantages(comb), -3.0, 3.0)
+    assert rel_err(rp.advantages.cpu().numpy(), want.reshape(-1)) <= TOL
+    assert rel_err(rp.ext_returns.cpu().numpy(), oracle.td_lambda(r, v[:-1], v[-1], d, 0.999, 0.9)) <= TOL
+    ref = oracle.sampled_return_multi(0.99997, r, d, hz, hz, vs, n_step_samples=table)
+    assert rel_err(rp.tvf_returns.cpu().numpy(), ref) <= TOL
+    s = rollout.stats_summary(rp.combined_stats)
+    np.testing.assert_allclose(s["adv_mean"], comb.astype(np.float64).mean(), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(s["ret_std"], (np.float32(0.3) * int_adv).astype(np.float64).std(), rtol=1e-9)
+    want_ratio = ((ext.astype(np.float64) ** 2).mean() / ((np.float32(0.3) * int_adv).astype(np.float64) ** 2).mean()) ** 0.5
+    np.testing.assert_allclose(rp.adv_ratio(), want_ratio, rtol=1e-9)
+    # the plain pass on the same object still normalises the extrinsic advantage alone
+    rp.run(cu(r), cu(v), cu(d).view(torch.uint8), cu(vs))
+    torch.cuda.synchronize()
+    assert rel_err(rp.advantages.cpu().numpy(), np.clip(oracle.normalize_advantages(ext), -3.0, 3.0).reshape(-1)) <= TOL
+
+
 def test_env_sharding_is_exact_on_one_gpu():
     """Two env shards processed separately + summed moments == the unsharded pass (the N > 1 data path without NCCL)."""
     steps, envs = 80, 130
