@@ -825,7 +825,8 @@ int launch_tvf_cslab(const TvfParams& p, double* stats, double* partials, unsign
     };
     if (N != 128 && N != 256) return unsupported("steps must be 128 or 256");
     if (V % 32 != 0 || V > 128) return unsupported("value horizons must be 32, 64, 96 or 128");
-    if (K > kCsMaxK || K % 32 != 0) return unsupported("required horizons must be a multiple of 32, at most 128");
+    // (32 horizons would be one team job per env: the two-team job rotation needs at least two)
+    if (K != 64 && K != 96 && K != 128) return unsupported("required horizons must be 64, 96 or 128");
     if (!p.tab.host_blob || !p.tab.dev_blob || !p.tab.gpow) return unsupported("tables carry no host mirror (ppo_tvf_tables_build)");
     if (p.tab.cslab_offset_words <= 0 || p.tab.tslab_offset_words <= 0)
         return unsupported("tables carry no launch constants for this kernel");

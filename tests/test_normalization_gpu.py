@@ -132,7 +132,7 @@ def test_error_behaviour():
     with pytest.raises(ValueError):
         nz.RunningMeanStd(shape=(3,))
     with pytest.raises(ValueError):
-        nz.VecNormalizeRewards(4, mode="ema")
+        nz.VecNormalizeRewards(4, mode="median")
     ir = nz.IntrinsicReturns(4)
     with pytest.raises(ValueError):
         ir.calculate_intrinsic_returns(np.zeros([3, 4], np.float32), np.zeros([3, 4], np.float32),
