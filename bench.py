@@ -675,13 +675,18 @@ def run_ours(args):
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     achieved = alg_bytes / (tvf_avg_ms * 1e-3) / 1e9
-    traffic = None
+    # DRAM bytes per launch from the newest ncu --set full capture of THIS kernel (tools/ncu_traffic.py writes the file
+    # from the capture named in it); null when the file describes another kernel than the one that just ran
+    traffic = traffic_src = None
     tpath = os.path.join(ROOT, "profiles", "tvf_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        rec = json.load(open(tpath))
+        if rp.tvf_kernel in rec.get("kernel", ""):
+            traffic, traffic_src = rec.get("dram_bytes_per_launch"), f"profiles/tvf_traffic.json <- {rec.get('report')}"
     roofline = {"bound": "hbm", "kernel": f"ppo_tvf_targets_ex, {rp.tvf_kernel} kernel (targets + fused last-horizon "
                                           f"statistics + fused rediscounted value estimate)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": tvf_avg_ms,
                 "kernel_share_of_step": tvf_avg_ms / ms_per_step,
                 "units_per_launch": f"{steps} x {envs} x {n_h} targets at 8.06 B/target",
