@@ -228,3 +228,61 @@ def test_lean_sections_write_the_same_slab_constants(built_library):
     hz48 = oracle.get_value_head_horizons(48, 3000)
     t48 = rt.draw_n_step_samples("exponential", "advanced", hz48, 64, 12, 6, seed=1)
     assert rt.build_tables(0.999, 64, hz48, hz48, t48, False, sections=rt.TABLES_TSLAB).layout.sections & rt.TABLES_GENERIC
+
+
+def test_column_slab_section_restates_the_entries(built_library):
+    """The launch constants of the column slab kernel (csrc/tvf_common.cuh: CsHorizon, CsEntry) against the entry tables
+    they are derived from: per horizon the same (n-step, multiplicity, slot) set, sorted by shift (n - 1) % 4 then n,
+    byte offsets of the aligned row group, weights cnt * gamma^n * lerp / C, and job masks / arrival counts that agree."""
+    from ppo_b200 import returns_truncated as rt
+    steps, k_n, c_n = 256, 128, 8
+    hz = oracle.get_value_head_horizons(k_n, 30000)
+    table = rt.draw_n_step_samples("exponential", "advanced", hz, steps, 20, c_n, seed=3)
+    tabs = rt.build_tables(0.99997, steps, hz, hz, table, False)
+    words = tabs.host.numpy()
+    base = int(tabs.layout.cslab_offset_words)
+    hdr = words[base:base + 16]
+    assert hdr[0] == 0x43534c33 and hdr[2] == steps and hdr[3] == k_n and hdr[4] == k_n // 4
+    total = int(hdr[1])
+    hzw = words[base + 16:base + 16 + 8 * k_n].view(np.uint32).reshape(k_n, 8)
+    jobs = k_n // 4
+    jobw = words[base + 16 + 8 * k_n:base + 16 + 8 * k_n + jobs].view(np.uint32)
+    ent0 = base + 16 + 8 * k_n + (jobs + 3) // 4 * 4 + 128
+    ent = words[ent0:ent0 + 4 * (total + 1)].reshape(total + 1, 4)
+    e_n, e_cnt = tabs.table("ent_n").reshape(tabs.n_entries, k_n), tabs.table("ent_cnt").reshape(tabs.n_entries, k_n)
+    e_idx = tabs.table("ent_idx").reshape(tabs.n_entries, k_n)
+    e_wlo, e_whi = tabs.table("ent_wlo").reshape(tabs.n_entries, k_n), tabs.table("ent_whi").reshape(tabs.n_entries, k_n)
+    seen = 0
+    masks = np.zeros(jobs, dtype=np.uint32)
+    for k in range(k_n):
+        beg, maxn, live = int(hzw[k, 0] & 0x7ff), int(hzw[k, 0] >> 11 & 0x3ff), int(hzw[k, 0] >> 23 & 1)
+        counts = [int(hzw[k, 1] >> (8 * s) & 0xff) for s in range(4)]
+        rows = [e for e in range(tabs.n_entries) if e_cnt[e, k] > 0]
+        assert live == int(hz[k] > 0) and sum(counts) == len(rows) and beg == seen
+        want = sorted(rows, key=lambda e: ((int(e_n[e, k]) - 1) % 4, int(e_n[e, k])))
+        assert maxn == (max(int(e_n[e, k]) for e in rows) if rows else 0)
+        pos = beg
+        for s in range(4):
+            for _ in range(counts[s]):
+                e = want[pos - beg]
+                n = int(e_n[e, k])
+                w = int(ent[pos, 0].view(np.uint32)) if hasattr(ent[pos, 0], "view") else int(ent[pos, 0]) & 0xffffffff
+                assert (n - 1) % 4 == s and w >> 18 == n
+                lo, hi = int(e_idx[e, k]) & 0xffff, int(e_idx[e, k]) >> 16
+                wlo, whi = float(e_wlo[e, k]), float(e_whi[e, k])
+                col = k_n if (wlo == 0 and whi == 0) else lo
+                assert (w & 0x3fff0) == (col * steps + 4 * ((n - 1) // 4)) * 4
+                scale = float(e_cnt[e, k]) * 0.99997 ** n / c_n
+                a, b = (1.0, 0.0) if col == k_n else (wlo, whi if hi != lo else 0.0)
+                got = ent[pos, 1:3].view(np.float32)
+                np.testing.assert_allclose(got, [a * scale, b * scale], rtol=2e-7, atol=0)
+                for cc, ww in ((col, got[0]), (col + 1, got[1])):
+                    if ww != 0 and cc <= k_n:
+                        masks[k // 4] |= np.uint32(1 << (cc // 32 if cc < k_n else 4))
+                pos += 1
+        seen = pos
+    assert seen == total
+    # the kernel's job masks contain every column group the entries touch (tails may add value-column groups)
+    assert np.all((jobw & masks) == masks)
+    arrivals = [int(np.sum(jobw >> g & 1)) for g in range(5)]
+    assert list(hdr[5:10]) == arrivals
