@@ -601,3 +601,79 @@ def stats_summary(stats):
             "adv_sparsity": s[_lib.STAT_ADV_ZEROS] / n, "ret_sparsity": s[_lib.STAT_RET_ZEROS] / n,
             "adv_mean": adv_mean, "adv_std": adv_std, "adv_min": s[_lib.STAT_ADV_MIN], "adv_max": s[_lib.STAT_ADV_MAX],
             "ret_mean": ret_mean, "ret_std": ret_std, "ret_min": s[_lib.STAT_RET_MIN], "ret_max": s[_lib.STAT_RET_MAX]}
+
+
+class RolloutBuffers:
+    """Device-resident form of the rollout buffers the return stage consumes (``rl/rollout.py:646-680``,
+    ``rl/tvf.py:27-30``) and of the writes ``Runner.generate_rollout`` makes into them once per env step
+    (``rl/rollout.py:790-813``) and once after the last step (``:878-892``).  The reference pulls every model output
+    to the host (``model_out["tvf_value"].cpu().numpy()``), trims it there and stores it in NumPy arrays, which the
+    return stage then uploads again; here the model outputs stay where the forward pass left them:
+
+      ``write_step(t, model_out, prev_time, ext_rewards, dones)``   rows ``t`` of ``tvf_untrimmed_value``, ``tvf_value``,
+                                                                    ``tvf_final_value``, ``all_time``, ``ext_rewards``,
+                                                                    ``terminals`` (+ ``value``, ``log_policy`` when given)
+      ``write_final(model_out, time)``                              row ``N`` of the value buffers
+      ``returns(pass_)``                                            ``ReturnPass.run`` on the buffers, no copies
+
+    ``tvf`` is a :class:`ppo_b200.tvf.TVFRunnerModule` (its ``trim_horizons`` does the trimming with the reference's
+    arguments); rewards, terminals and times come from the env workers as host arrays, 5 bytes per env and step.
+    """
+
+    def __init__(self, steps, envs, horizons, tvf, value_heads=1, trimming="off", trimming_mode="average", device=None):
+        self.device = device or dev.require_cuda()
+        self.steps, self.envs, self.tvf = int(steps), int(envs), tvf
+        self.trimming, self.trimming_mode = trimming, trimming_mode
+        k = len(horizons)
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.tvf_value = torch.zeros((steps + 1, envs, k, value_heads), **f32)
+        self.tvf_untrimmed_value = torch.zeros((steps + 1, envs, k, value_heads), **f32)
+        self.tvf_final_value = torch.zeros((steps + 1, envs), **f32)
+        self.ext_rewards = torch.zeros((steps, envs), **f32)
+        self.terminals = torch.zeros((steps, envs), dtype=torch.uint8, device=self.device)
+        self.all_time = torch.zeros((steps + 1, envs), dtype=torch.int32, device=self.device)
+        self.value = self.log_policy = None  # allocated by the first write that carries them
+        self.ttt_predictions = [[] for _ in range(envs)]
+
+    def _tvf_row(self, t, tvf_value, time):
+        tv = dev.to_device(tvf_value, torch.float32, self.device).detach()
+        if tv.dim() == 2:
+            tv = tv.unsqueeze(-1)
+        row = self.tvf_untrimmed_value[t]
+        row.copy_(tv)
+        row[:, 0, :] = 0  # "first value head should always be zero" (rl/rollout.py:792, :883)
+        trimmed, final, ttt = self.tvf.trim_horizons(row, time, method=self.trimming, mode=self.trimming_mode)
+        self.tvf_value[t].copy_(trimmed if trimmed.shape == row.shape else trimmed.expand_as(row))
+        if torch.is_tensor(final) or isinstance(final, np.ndarray):
+            self.tvf_final_value[t].copy_(dev.to_device(final, torch.float32, self.device))
+        else:
+            self.tvf_final_value[t].fill_(float(final))
+        if ttt is not None:  # rl/rollout.py:800-802
+            for a, x in enumerate(np.asarray(ttt)):
+                self.ttt_predictions[a].append(x)
+        self.all_time[t].copy_(torch.as_tensor(np.asarray(time), dtype=torch.int32), non_blocking=True)
+
+    def write_step(self, t, model_out, prev_time, ext_rewards, dones):
+        self._tvf_row(t, model_out["tvf_value"], prev_time)
+        self.ext_rewards[t].copy_(torch.as_tensor(np.asarray(ext_rewards, dtype=np.float32)), non_blocking=True)
+        self.terminals[t].copy_(torch.as_tensor(np.asarray(dones).astype(np.uint8)), non_blocking=True)
+        for name in ("value", "log_policy"):
+            if name in model_out:
+                x = model_out[name].detach()
+                if getattr(self, name) is None:
+                    rows = self.steps + 1 if name == "value" else self.steps
+                    setattr(self, name, torch.zeros((rows,) + tuple(x.shape), dtype=x.dtype, device=self.device))
+                getattr(self, name)[t].copy_(x)
+
+    def write_final(self, model_out, time):
+        self._tvf_row(self.steps, model_out["tvf_value"], time)
+        if "value" in model_out and self.value is not None:
+            self.value[self.steps].copy_(model_out["value"].detach())
+
+    def returns(self, pass_, value_head=0, **kwargs):
+        """One return pass over the buffers (``ReturnPass.run`` with ``values=None``: the estimate GAE reads comes off
+        the value curves, ``rl/rollout.py:1196``)."""
+        vs = self.tvf_value[..., value_head]
+        if not vs.is_contiguous():
+            vs = vs.contiguous()
+        return pass_.run(self.ext_rewards, None, self.terminals, vs, **kwargs)

@@ -160,6 +160,57 @@ def test_return_pass_combines_intrinsic_advantage():
     assert rel_err(rp.advantages.cpu().numpy(), np.clip(oracle.normalize_advantages(ext), -3.0, 3.0).reshape(-1)) <= TOL
 
 
+@pytest.mark.parametrize("method,mode", [("off", "average"), ("timelimit", "interpolate"), ("timelimit", "average"),
+                                         ("timelimit", "substitute")])
+def test_rollout_buffers_written_on_the_device(method, mode):
+    """The per-step writes of Runner.generate_rollout (rl/rollout.py:790-813, :878-892) with the model outputs left on
+    the device, against the same writes in NumPy through the oracle's trim_horizons; then one return pass straight off
+    the buffers against the oracle on the NumPy buffers."""
+    import types
+    from ppo_b200 import tvf as tvf_mod
+    steps, envs, timeout = 32, 40, 300
+    hz = oracle.get_value_head_horizons(128, 30000)
+    log = types.SimpleNamespace(watch_stats=lambda *a, **k: None, watch_mean=lambda *a, **k: None)
+    runner = types.SimpleNamespace(ext_rewards=np.zeros([steps, envs], np.float32), terminals=None, all_obs=None,
+                                   tvf_horizons=list(hz), value_heads=["ext"], N=steps, log=log, episode_length_buffer=[])
+    args = types.SimpleNamespace(env=types.SimpleNamespace(timeout=timeout),
+                                 tvf=types.SimpleNamespace(eta_percentile=90, eta_buffer=32, eta_minh=128, trim_clip=-1))
+    mod = tvf_mod.TVFRunnerModule(runner, args)
+    bufs = rollout.RolloutBuffers(steps, envs, hz, mod, trimming=method, trimming_mode=mode)
+    rng = np.random.RandomState(4)
+    r, d, _ = synthetic.rollout(steps, envs, seed=4)
+    time = rng.randint(0, timeout - 20, size=envs)
+    want_v = np.zeros([steps + 1, envs, len(hz), 1], np.float32)
+    want_u, want_f = np.zeros_like(want_v), np.zeros([steps + 1, envs], np.float32)
+    for t in range(steps + 1):
+        out = rng.normal(0.3, 0.5, [envs, len(hz), 1]).astype(np.float32)
+        ref_in = out.copy()
+        ref_in[:, 0, :] = 0
+        want_u[t] = ref_in
+        new, fin, _ = oracle.trim_horizons(hz, ref_in, time, method, mode, timeout=timeout)
+        want_v[t], want_f[t] = new, fin
+        model_out = {"tvf_value": torch.from_numpy(out).cuda(), "value": torch.from_numpy(out[:, -1, :]).cuda()}
+        if t < steps:
+            bufs.write_step(t, model_out, time, r[t], d[t])
+            time = np.where(d[t], 0, time + 1)
+        else:
+            bufs.write_final(model_out, time)
+    torch.cuda.synchronize()
+    assert np.array_equal(bufs.tvf_untrimmed_value.cpu().numpy(), want_u)
+    assert rel_err(bufs.tvf_value.cpu().numpy(), want_v) <= 1e-6
+    assert rel_err(bufs.tvf_final_value.cpu().numpy(), want_f) <= 1e-6 or method == "off"
+    assert np.array_equal(bufs.ext_rewards.cpu().numpy(), r) and np.array_equal(bufs.terminals.cpu().numpy() != 0, d)
+    assert bufs.value.shape == (steps + 1, envs, 1)
+    table = rt.draw_n_step_samples("exponential", "advanced", hz, steps, 20, 8, seed=1)
+    rp = rollout.ReturnPass(steps, envs, hz, 0.999, 0.999, 0.95, 0.9)
+    rp.set_samples(table)
+    bufs.returns(rp)
+    torch.cuda.synchronize()
+    vs = bufs.tvf_value.cpu().numpy()[..., 0]
+    assert rel_err(rp.tvf_returns.cpu().numpy(), oracle.sampled_return_multi(0.999, r, d, hz, hz, vs, n_step_samples=table)) <= TOL
+    assert rel_err(rp.advantage.cpu().numpy(), oracle.gae(r, vs[:-1, :, -1], vs[-1, :, -1], d, 0.999, 0.95)) <= TOL
+
+
 def test_env_sharding_is_exact_on_one_gpu():
     """Two env shards processed separately + summed moments == the unsharded pass (the N > 1 data path without NCCL)."""
     steps, envs = 80, 130
