@@ -1060,6 +1060,7 @@ extern "C" int ppo_discounted_returns(const float* rewards, int64_t reward_row_s
     return PPO_OK;
 }
 
+namespace ppo {
 // Records of disjoint env blocks (or ranks) -> one record: sums add in record order, min / max reduce.
 __global__ void merge_stats_kernel(const double* __restrict__ records, int64_t n, double* __restrict__ out) {
     const int j = threadIdx.x;
@@ -1073,6 +1074,7 @@ __global__ void merge_stats_kernel(const double* __restrict__ records, int64_t n
     }
     out[j] = j <= PPO_STAT_RET_ZEROS ? acc : 0.0;
 }
+}  // namespace ppo
 
 extern "C" int ppo_merge_stats(const double* records, int64_t n_records, double* out, void* stream) {
     PPO_REQUIRE(n_records >= 1 && records && out, "ppo_merge_stats: bad arguments");

@@ -198,33 +198,6 @@ def stamps():
                   f"before grant {us(c + 9):7.2f} granted {us(c + 10):7.2f} written {us(c + 3):7.2f} stored {us(c + 4):7.2f}")
 
 
-def tslab_ctas():
-    """Per-CTA durations of the transposed slab kernel (PPO_TVF_DEBUG=64)."""
-    lib = _lib.load()
-    dev = torch.device("cuda")
-    hz = tvf_mod.get_value_head_horizons(128, 30000)
-    steps, envs = 256, 4096
-    g = torch.Generator(device=dev)
-    g.manual_seed(0)
-    r = torch.randint(-1, 3, (steps, envs), device=dev, generator=g).float()
-    d = (torch.rand((steps, envs), device=dev, generator=g) < 3 / 101).view(torch.uint8)
-    vs = torch.randn((steps + 1, envs, 128), device=dev, generator=g) * 0.4 + 0.1
-    out = torch.empty((steps, envs, 128), device=dev)
-    table = rt.draw_n_step_samples("exponential", "advanced", hz, steps, 20, 8, seed=1)
-    tabs = rt.build_tables(0.99997, steps, hz, hz, table)
-    ctab, blob = rt._upload_tables(tabs, dev)
-    for _ in range(2):
-        launch(lib, rt.PATH_TSLAB, r, d, vs, ctab, out)
-    buf = (ctypes.c_ulonglong * 320)()
-    lib.ppo_tvf_debug_cta_times.argtypes = [ctypes.c_void_p]
-    lib.ppo_tvf_debug_cta_times(buf)
-    t = np.array(buf[:], dtype=np.float64)
-    st, en = t[:148], t[160:160 + 148]
-    dur = (en - st) / 1e3
-    print("tslab CTA duration (us): min %.1f median %.1f max %.1f; kernel span %.1f" % (dur.min(), np.median(dur), dur.max(), (en.max() - st.min()) / 1e3))
-    print("slowest:", np.argsort(-dur)[:10].tolist(), np.sort(-dur)[:10].round(1).tolist())
-
-
 if __name__ == "__main__":
     args = sys.argv[1:] or ["check", "time"]
     rc = 0
@@ -234,6 +207,4 @@ if __name__ == "__main__":
         timing("full" in args)
     if "stamps" in args:
         stamps()
-    if "tslab_ctas" in args:
-        tslab_ctas()
     sys.exit(1 if rc else 0)
