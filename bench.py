@@ -379,7 +379,7 @@ def other_configs(device, peak_gbs, iters=40):
         ir.calculate_intrinsic_returns(r, v, d, 0.99, LAMBDA_POLICY, normalize=True, center=False)
     # r 4 + done 1 in, tracker rows 8 out + 8 + 8 re-read (two row passes), r 4 in + scaled r 4 out, GAE 13 in + 8 out
     res = timed(f3, n * a * 58, n * a)
-    res["note"] = ("tracker scan + 2 row-moment passes + fold + scale + GAE (6 launches) through the Python API; "
+    res["note"] = ("tracker scan, row moments + fold (one launch), scale, GAE (4 launches) through the Python API; "
                    "58 B per (t, env) incl. the float64 tracker rows; the working set (60 MB) stays in L2")
     out["f3_intrinsic_returns_256x4096"] = res
     return out

@@ -478,6 +478,11 @@ int ppo_rms_fold(const double* row_sums, const double* row_sq, int64_t steps, do
  * row_var (optional) then records the EMA variance after each step. */
 int ppo_rms_fold_ema(const double* row_sums, const double* row_sq, int64_t steps, double total_envs, double* rms,
                      double* ema_var, double ema_horizon, double* row_var, void* stream);
+/* One GPU, no exchange: ppo_row_sums twice + ppo_rms_fold(_ema) in ONE launch (a CTA per row makes both passes, the
+ * last CTA to finish runs the merges); bit-identical to the three launches.  row_sums / row_sq [steps] are scratch
+ * outputs, ema_var may be NULL, ticket is a zeroed device word (left zero). */
+int ppo_row_moments_fold(const double* x, int64_t steps, int64_t envs, double* row_sums, double* row_sq, double* rms,
+                         double* ema_var, double ema_horizon, double* row_var, unsigned int* ticket, void* stream);
 int ppo_scale_rewards(const float* rewards, int64_t reward_row_stride, int64_t steps, int64_t envs, const double* var,
                       int per_row, int mode, double eps, double clip, double scale, const double* center_stats,
                       float* out, unsigned long long* clips, void* stream);

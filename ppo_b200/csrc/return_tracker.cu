@@ -123,13 +123,10 @@ __global__ void __launch_bounds__(256) row_sum_kernel(const double* __restrict__
 // ema_var (optional, in / out): the wrapper's mode "ema" (rl/wrappers.py:878-881) -- after every merge
 //   alpha = 1 - n / min(count, ema_horizon);  ema = alpha * ema + (1 - alpha) * var_over_envs(x_t)
 // and row_var then records the EMA instead of the running variance.
-__global__ void rms_fold_kernel(const double* __restrict__ row_sum, const double* __restrict__ row_sq, int64_t steps,
-                                double n, double* rms, double* row_var, double* ema_var, double ema_horizon) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double mean = rms[0], var = rms[1], count = rms[2];
-    double ema = ema_var ? *ema_var : 0.0;
-    for (int64_t t = 0; t < steps; ++t) {
-        const double bm = row_sum[t] / n, bv = row_sq[t] / n;
+struct RmsFold {
+    double mean, var, count, ema;
+    // one merge of rl/utils.py:379-396 with the batch moments (bm, bv) of n samples; returns the variance to record
+    __device__ __forceinline__ double step(double bm, double bv, double n, bool use_ema, double ema_horizon) {
         const double delta = __dsub_rn(bm, mean);
         const double tot = __dadd_rn(count, n);
         const double new_mean = __dadd_rn(mean, __ddiv_rn(__dmul_rn(delta, n), tot));
@@ -137,14 +134,89 @@ __global__ void rms_fold_kernel(const double* __restrict__ row_sum, const double
         const double cross = __ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(delta, delta), count), n), tot);
         const double m2 = __dadd_rn(__dadd_rn(m_a, m_b), cross);
         mean = new_mean, var = __ddiv_rn(m2, tot), count = tot;
-        if (ema_var) {
+        if (use_ema) {
             const double alpha = 1.0 - n / fmin(count, ema_horizon);
             ema = alpha * ema + (1.0 - alpha) * bv;
         }
-        if (row_var) row_var[t] = ema_var ? ema : var;
+        return use_ema ? ema : var;
     }
-    rms[0] = mean, rms[1] = var, rms[2] = count;
-    if (ema_var) *ema_var = ema;
+};
+
+__global__ void rms_fold_kernel(const double* __restrict__ row_sum, const double* __restrict__ row_sq, int64_t steps,
+                                double n, double* rms, double* row_var, double* ema_var, double ema_horizon) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    RmsFold f{rms[0], rms[1], rms[2], ema_var ? *ema_var : 0.0};
+    for (int64_t t = 0; t < steps; ++t) {
+        const double v = f.step(row_sum[t] / n, row_sq[t] / n, n, ema_var != nullptr, ema_horizon);
+        if (row_var) row_var[t] = v;
+    }
+    rms[0] = f.mean, rms[1] = f.var, rms[2] = f.count;
+    if (ema_var) *ema_var = f.ema;
+}
+
+// One GPU (no exchange of the row vectors): both passes of a row in one CTA -- the row sum, then the squared deviations
+// from the row mean out of L1 / L2 -- and the N sequential merges by the last CTA to finish (ticket), which first
+// stages the row vectors in shared memory (a dependent L2 load per merge would triple the chain).  Same reduction
+// order as row_sum_kernel, so the result is bit-identical to the three launches.
+constexpr int kFoldStage = 512;
+__global__ void __launch_bounds__(256) row_moments_fold_kernel(const double* __restrict__ x, int64_t steps, int64_t envs,
+                                                               double* row_sum, double* row_sq, double* rms,
+                                                               double* row_var, double* ema_var, double ema_horizon,
+                                                               unsigned int* ticket) {
+    __shared__ double red[8];
+    __shared__ double s_c;
+    __shared__ bool s_last;
+    __shared__ double stage[2][kFoldStage];
+    const int64_t t = blockIdx.x;
+    const double* row = x + t * envs;
+    const double n = static_cast<double>(envs);
+    double total[2];
+    for (int pass = 0; pass < 2; ++pass) {
+        const double c = pass ? s_c : 0.0;
+        double acc = 0.0;
+        for (int64_t a = threadIdx.x; a < envs; a += blockDim.x) {
+            const double v = __ldcg(row + a) - c;
+            acc += pass ? v * v : v;
+        }
+        acc = warp_sum_f64(acc);
+        __syncthreads();  // red[] of the previous pass has been read
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int i = 0; i < 8; ++i) s += red[i];
+            total[pass] = s;
+            if (pass == 0) s_c = s / n;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        row_sum[t] = total[0], row_sq[t] = total[1];
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    RmsFold f{rms[0], rms[1], rms[2], ema_var ? *ema_var : 0.0};
+    for (int64_t t0 = 0; t0 < steps; t0 += kFoldStage) {
+        const int m = static_cast<int>(min(static_cast<int64_t>(kFoldStage), steps - t0));
+        for (int i = threadIdx.x; i < m; i += blockDim.x)
+            stage[0][i] = __ldcg(row_sum + t0 + i), stage[1][i] = __ldcg(row_sq + t0 + i);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < m; ++i) {
+                const double v = f.step(stage[0][i] / n, stage[1][i] / n, n, ema_var != nullptr, ema_horizon);
+                if (row_var) row_var[t0 + i] = v;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        rms[0] = f.mean, rms[1] = f.var, rms[2] = f.count;
+        if (ema_var) *ema_var = f.ema;
+        *ticket = 0u;
+    }
 }
 
 struct ScaleParams {
@@ -225,6 +297,19 @@ extern "C" int ppo_rms_fold(const double* row_sums, const double* row_sq, int64_
     PPO_REQUIRE(rms && (steps == 0 || (row_sums && row_sq)), "ppo_rms_fold: null pointer");
     rms_fold_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(row_sums, row_sq, steps, total_envs, rms, row_var,
                                                                      nullptr, 0.0);
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+extern "C" int ppo_row_moments_fold(const double* x, int64_t steps, int64_t envs, double* row_sums, double* row_sq,
+                                    double* rms, double* ema_var, double ema_horizon, double* row_var,
+                                    unsigned int* ticket, void* stream) {
+    PPO_REQUIRE(steps >= 0 && envs >= 1, "ppo_row_moments_fold: bad shape");
+    if (steps == 0) return PPO_OK;
+    PPO_REQUIRE(x && row_sums && row_sq && rms && ticket, "ppo_row_moments_fold: null pointer");
+    PPO_REQUIRE(!ema_var || ema_horizon > 0.0, "ppo_row_moments_fold: ema_horizon must be positive");
+    row_moments_fold_kernel<<<static_cast<unsigned>(steps), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, steps, envs, row_sums, row_sq, rms, row_var, ema_var, ema_horizon, ticket);
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;
 }

@@ -94,6 +94,13 @@ def _fold_rows(x, rms_state, group, row_var, ema=None):
     s = dev.stream_ptr()
     sums = torch.empty(steps, dtype=torch.float64, device=x.device)
     sq = torch.empty(steps, dtype=torch.float64, device=x.device)
+    if _world(group) == 1:  # nothing to exchange: both row passes and the merges in one launch
+        ws = dev.workspace(256, x.device)
+        rc = lib.ppo_row_moments_fold(dev.ptr(x), steps, envs, dev.ptr(sums), dev.ptr(sq), dev.ptr(rms_state),
+                                      dev.ptr(ema[0]) if ema is not None else None, float(ema[1]) if ema is not None else 0.0,
+                                      dev.ptr(row_var), dev.ptr(ws), s)
+        _lib.check(rc, "ppo_row_moments_fold")
+        return
     total = float(global_env_count(envs, group, x.device))  # the true count: shards need not be equal
     _lib.check(lib.ppo_row_sums(dev.ptr(x), steps, envs, 0, total, dev.ptr(sums), s), "ppo_row_sums")
     if _world(group) > 1:
