@@ -125,6 +125,10 @@ int ppo_gae_normalized(const float* rewards, int64_t reward_row_stride,
                        float* adv_out, float* ret_out, float* norm_out, double* stats,
                        void* workspace, int64_t workspace_bytes, void* stream);
 
+/* 1 when ppo_gae_normalized / ppo_gae_normalized_peers would take the single cooperative launch for this shard shape
+ * on the current device (nothing is launched): ranks agree on it (all-reduce MIN) before relying on the peer exchange. */
+int ppo_gae_normalized_fits(int64_t steps, int64_t envs, int done_kind, int64_t value_env_stride);
+
 /*
  * Env-sharded form of ppo_gae_normalized (one process per GPU, envs split over `world` GPUs of one NVLink domain): the
  * exchange of the advantage moments -- the only cross-GPU step of the path, SURVEY 8e -- happens INSIDE the launch
@@ -144,10 +148,6 @@ int ppo_gae_normalized(const float* rewards, int64_t reward_row_stride,
  * the stream has drained -- non-zero means the normalised advantages of that launch are NaN and the pass must be
  * repeated, e.g. with the all-reduce path, after the ranks have met at a host barrier).
  */
-/* 1 when ppo_gae_normalized / ppo_gae_normalized_peers would take the single cooperative launch for this shard shape
- * on the current device (nothing is launched): ranks agree on it (all-reduce MIN) before relying on the peer exchange. */
-int ppo_gae_normalized_fits(int64_t steps, int64_t envs, int done_kind, int64_t value_env_stride);
-
 int ppo_gae_normalized_peers(const float* rewards, int64_t reward_row_stride,
                              const float* values, int64_t value_row_stride, int64_t value_env_stride,
                              const float* final_value, int64_t final_env_stride,
