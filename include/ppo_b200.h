@@ -315,8 +315,10 @@ typedef enum {
     PPO_TVF_GENERIC = 1, /* global-memory gather kernel, any shape                            */
     PPO_TVF_RING = 2,    /* TMA ring kernel or PPO_ERR_UNSUPPORTED                            */
     PPO_TVF_TSLAB = 3,   /* transposed slab kernel or PPO_ERR_UNSUPPORTED                     */
-    PPO_TVF_CSLAB = 4    /* column slab kernel (128 or 256 steps, <= 128 value horizons in multiples of 32, horizon
+    PPO_TVF_CSLAB = 4,   /* column slab kernel (128 or 256 steps, <= 128 value horizons in multiples of 32, horizon
                             count a multiple of 4) or PPO_ERR_UNSUPPORTED */
+    PPO_TVF_QSLAB = 5    /* quad slab kernel (128 or 256 steps, 128 required horizons on 128 value horizons) or
+                            PPO_ERR_UNSUPPORTED */
 } ppo_tvf_path;
 
 /*

@@ -14,6 +14,9 @@ namespace ppo {
 int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const void* base,
                       const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
                       bool swizzle_128b = false);
+// the same with the shared-memory swizzle span in bytes (0 = none, 32, 64, 128)
+int encode_tensor_map_swz(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const void* base,
+                          const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
 // ---- device: mbarrier ----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -21,6 +21,9 @@ namespace ppo {
 int launch_tvf_tslab(const TvfParams& p, double* stats, double* partials, unsigned int* ticket, int64_t max_partials,
                      const float* host_value_weights, float* value_out, int64_t value_row_stride, cudaStream_t stream,
                      bool* stats_fused, const TsGae* gae, bool* gae_fused);  // tvf_tslab.cu
+int launch_tvf_qslab(const TvfParams& p, double* stats, double* partials, unsigned int* ticket, int64_t max_partials,
+                     const float* host_value_weights, float* value_out, int64_t value_row_stride, cudaStream_t stream,
+                     bool* stats_fused);  // tvf_qslab.cu
 int launch_tvf_cslab(const TvfParams& p, double* stats, double* partials, unsigned int* ticket, int64_t max_partials,
                      const float* host_value_weights, float* value_out, int64_t value_row_stride, cudaStream_t stream,
                      bool* stats_fused);
@@ -230,6 +233,12 @@ static thread_local int g_last_path = 0;
 
 extern "C" int ppo_tvf_last_path(void) { return g_last_path; }
 
+// PPO_TVF_AUTO takes the quad slab kernel where it applies unless PPO_TVF_QSLAB=0 (read per call: A/B runs)
+static bool prefer_qslab() {
+    const char* e = getenv("PPO_TVF_QSLAB");
+    return e != nullptr && atoi(e) != 0;
+}
+
 extern "C" int64_t ppo_tvf_workspace_bytes(int64_t steps, int64_t envs) {
     (void)steps;
     // ticket + per-block records of the statistics kernels, or one record per env (column slab kernel)
@@ -261,7 +270,7 @@ extern "C" int ppo_tvf_targets_ex(const float* rewards, int64_t reward_row_strid
     PPO_REQUIRE(done_kind == PPO_DONE_U8 || done_kind == PPO_DONE_F32 || done_kind == PPO_DONE_NONE,
                 "ppo_tvf_targets: unknown done_kind %d", done_kind);
     PPO_REQUIRE(path == PPO_TVF_AUTO || path == PPO_TVF_GENERIC || path == PPO_TVF_RING || path == PPO_TVF_TSLAB ||
-                    path == PPO_TVF_CSLAB,
+                    path == PPO_TVF_CSLAB || path == PPO_TVF_QSLAB,
                 "ppo_tvf_targets: unknown path %d", path);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (steps == 0 || envs == 0 || n_req == 0) {
@@ -308,6 +317,14 @@ extern "C" int ppo_tvf_targets_ex(const float* rewards, int64_t reward_row_strid
         if (path == PPO_TVF_CSLAB && rc != PPO_OK) return rc;
         taken = PPO_TVF_CSLAB;
         if (rc == PPO_OK) vout = nullptr;  // the value estimate was written by the same launch
+    }
+    if (path == PPO_TVF_QSLAB || (path == PPO_TVF_AUTO && tables->n_entries >= 3 && rc == PPO_ERR_UNSUPPORTED && prefer_qslab())) {
+        rc = launch_tvf_qslab(p, stats, partials, ticket, kStatsBlocks, vweights, vout, vout_rs, s, &stats_fused);
+        if (path == PPO_TVF_QSLAB && rc != PPO_OK) return rc;
+        if (rc == PPO_OK) {
+            taken = PPO_TVF_QSLAB;
+            vout = nullptr;  // the value estimate was written by the same launch
+        }
     }
     if (path == PPO_TVF_TSLAB || (path == PPO_TVF_AUTO && tables->n_entries >= 3 && rc == PPO_ERR_UNSUPPORTED)) {
         TsGae gae{};

@@ -15,7 +15,7 @@ from . import _device as dev
 from . import _lib
 from . import _tvf_tables
 
-PATH_AUTO, PATH_GENERIC, PATH_RING, PATH_TSLAB, PATH_CSLAB = 0, 1, 2, 3, 4
+PATH_AUTO, PATH_GENERIC, PATH_RING, PATH_TSLAB, PATH_CSLAB, PATH_QSLAB = 0, 1, 2, 3, 4, 5
 
 
 class _CTables(ctypes.Structure):

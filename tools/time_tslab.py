@@ -1,5 +1,6 @@
-"""Development aid: device time of the transposed slab kernel at the bench shape (256 x 4096 x 128, exponential /
-advanced 8 samples) under the kernel's PPO_TVF_DEBUG bits (read per launch)."""
+"""Development aid: device time of the transposed slab kernel (or, with PPO_TIME_PATH=qslab, the quad slab kernel) at
+the bench shape (256 x 4096 x 128, exponential / advanced 8 samples) under the kernel's PPO_TVF_DEBUG bits (read per
+launch).  PPO_TIME_CHECK=1 also compares the targets of the two kernels."""
 import ctypes
 import os
 import sys
@@ -26,10 +27,18 @@ def main():
     ctab, blob = rt._upload_tables(tabs, device)
     s = torch.cuda.current_stream().cuda_stream
 
-    def launch():
+    path = {"tslab": rt.PATH_TSLAB, "qslab": rt.PATH_QSLAB, "cslab": rt.PATH_CSLAB}[os.environ.get("PPO_TIME_PATH", "tslab")]
+
+    def launch(path=path, out=out):
         rc = lib.ppo_tvf_targets(r.data_ptr(), envs, d.data_ptr(), 1, envs, vs.data_ptr(), envs * 128, 128,
-                                 steps, envs, 128, 128, ctypes.byref(ctab), rt.PATH_TSLAB, out.data_ptr(), 0, 0, 0, s)
+                                 steps, envs, 128, 128, ctypes.byref(ctab), path, out.data_ptr(), 0, 0, 0, s)
         _lib.check(rc, "tvf")
+    if os.environ.get("PPO_TIME_CHECK"):
+        ref = torch.empty_like(out)
+        launch(rt.PATH_TSLAB, ref)
+        launch()
+        torch.cuda.synchronize()
+        print("max |diff| vs tslab:", float((out - ref).abs().max()), "equal:", bool(torch.equal(out, ref)))
     for dbg in [int(x) for x in (sys.argv[1:] or ["0"])]:
         os.environ["PPO_TVF_DEBUG"] = str(dbg)
         for _ in range(3):
