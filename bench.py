@@ -298,7 +298,7 @@ def other_configs(device, peak_gbs, iters=40):
                                            n, a, k, k, ctypes.byref(ctab), rt.PATH_AUTO, tg.data_ptr(), 0, 0, 0,
                                            stream), "ppo_tvf_targets")
         res = timed(c3, nbytes, n * a * k)
-        res["kernel"] = {1: "generic", 2: "ring", 3: "tslab", 4: "cslab"}.get(lib.ppo_tvf_last_path() & 0xff)
+        res["kernel"] = {1: "generic", 2: "ring", 3: "tslab", 4: "cslab", 5: "qslab"}.get(lib.ppo_tvf_last_path() & 0xff)
         out[f"c3_tvf_128x1024x128_{name}"] = res
         del keep
     del bufs
@@ -320,7 +320,7 @@ def other_configs(device, peak_gbs, iters=40):
                        "ppo_tvf_targets")
         try:
             res = timed(c5, nbytes, n * a * k)
-            res["kernel"] = {1: "generic", 2: "ring", 3: "tslab", 4: "cslab"}.get(lib.ppo_tvf_last_path() & 0xff)
+            res["kernel"] = {1: "generic", 2: "ring", 3: "tslab", 4: "cslab", 5: "qslab"}.get(lib.ppo_tvf_last_path() & 0xff)
         except Exception as e:  # a path that declines this shape is reported, not hidden
             res = {"error": repr(e)}
         res["note"] = "1.07 GB per launch (> L2), targets only (no statistics, no value estimate)"

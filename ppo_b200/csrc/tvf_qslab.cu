@@ -45,6 +45,7 @@ constexpr uint32_t kQsOffMask = 0x3ffffu;
 constexpr int kQsOffBits = 18;
 constexpr int kQsEntBytes = 12;
 constexpr int kQsMaxTiles = 8;
+constexpr unsigned int kQsRing = 32;  // job ring of the store warp (more slots than tiles)
 
 struct QsParams {
     TvfParams p;
@@ -54,7 +55,7 @@ struct QsParams {
     int arrivals[kQsGroups];     // units (oct, half of the rows) of an env that read the column group
     unsigned char need[kQsQuads / 2];  // column groups an oct (eight consecutive horizons) reads (bit g)
     int64_t env_base, env_rem;
-    uint32_t off_stage, off_tile, off_ent, off_hz, off_rtab, off_lim, off_fr, off_misc, off_bar, smem_total;
+    uint32_t off_stage, off_tile, off_ent, off_hz, off_rtab, off_lim, off_fr, off_misc, off_stat, off_bar, smem_total;
     int ntile;  // output tiles of (N / 2 rows x 32 bytes) in shared memory, handed out through a bit mask
     float* value_out;  // [N + 1, A] value estimate sum_j vw[j] * V[r, a, j] (want_value), row stride vo_rs
     int64_t vo_rs;
@@ -220,6 +221,8 @@ tvf_qslab_kernel(const __grid_constant__ QsParams q, const __grid_constant__ CUt
     const uint32_t fr_a = smem_u32(smem + q.off_fr);
     int* unit_counter = reinterpret_cast<int*>(smem + q.off_misc);
     unsigned int* tile_free = reinterpret_cast<unsigned int*>(smem + q.off_misc + 16);  // bit b: output tile b is free
+    unsigned int* ring_tail = reinterpret_cast<unsigned int*>(smem + q.off_misc + 32);  // jobs published so far
+    unsigned int* ring = reinterpret_cast<unsigned int*>(smem + q.off_misc + 64);       // [kQsRing] job words of filled tiles
     const uint32_t tile_a = smem_u32(smem + q.off_tile);
 
     const int64_t bidx = blockIdx.x;
@@ -288,12 +291,45 @@ tvf_qslab_kernel(const __grid_constant__ QsParams q, const __grid_constant__ CUt
         }
     }
     if (threadIdx.x == 0) *tile_free = (1u << q.ntile) - 1u;
+    if (threadIdx.x < kQsConsumers) {
+        double* rec = reinterpret_cast<double*>(smem + q.off_stat) + threadIdx.x * 8;
+        rec[3] = INFINITY, rec[4] = -INFINITY;
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
     if (warp >= kQsConsumers + kQsXform) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");  // second helper warpgroup
-    if (warp > kQsConsumers + kQsXform + 1) {
-        // idle warps of the second helper warpgroup
+    if (warp > kQsConsumers + kQsXform + 2) {
+        // idle warp of the second helper warpgroup
+    } else if (warp == kQsConsumers + kQsXform + 2) {
+        // ------------------------------------------------------------------ store warp
+        // Takes the filled output tiles in the order the consumers publish them, issues one tensor store per tile
+        // and frees a tile as soon as its store has read it (stores complete in order; two may be pending).
+        if (lane == 0 && !(q.dbg & 1)) {
+            const int total = nenv * KQ;
+            unsigned int open[2] = {0u, 0u};  // tiles of the two youngest stores
+            for (int n = 0; n < total; ++n) {
+                volatile unsigned int* slot = ring + (static_cast<unsigned int>(n) % kQsRing);
+                unsigned int job;
+                while (((job = *slot) & 0x80000000u) == 0u) __nanosleep(100);
+                *slot = 0u;
+                __threadfence_block();
+                const unsigned int tb = (job >> 24) & 0x7fu, oct = (job >> 20) & 0xfu, half = (job >> 19) & 1u, e = job & 0x7ffffu;
+                qs_tma_store_3d(&omap, tile_a + tb * ((N / 2) * 32u), static_cast<int>(oct * 8),
+                                static_cast<int>(env0 + e), static_cast<int>(half * (N / 2)));
+                qs_bulk_commit();
+                if (n >= 2) {
+                    asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+                    atomicOr(tile_free, 1u << open[0]);
+                }
+                open[0] = open[1], open[1] = tb;
+                if (n == 0) open[0] = tb;
+            }
+            qs_bulk_wait_read();
+            if (total >= 2) atomicOr(tile_free, 1u << open[0]);
+            if (total >= 1) atomicOr(tile_free, 1u << open[1]);
+            qs_bulk_wait_all();
+        }
     } else if (warp == kQsConsumers + kQsXform + 1) {
         // ------------------------------------------------------------------ TMA producer: groups highest first
         if (lane == 0) {
@@ -470,7 +506,7 @@ tvf_qslab_kernel(const __grid_constant__ QsParams q, const __grid_constant__ CUt
         // Units (env, oct, half) are drawn from a shared counter: env order, highest horizons first, 32 units per env.
         // A unit is eight consecutive horizons (two quads, evaluated one after the other) for one half of the env's
         // rows: a thread carries rows half * N / 2 + lane + 32 i, i < RH, and leaves 32 contiguous bytes per row -- a
-        // whole sector (16-byte stores of single quads cost a read-modify-write in L2: 783 instead of 502 us).
+        // whole sector (16-byte global stores reach L2 as partial-sector writes: 734 instead of 363 us).
         // Phase argument for the parity waits below: units are drawn in order and the transform warps load in order,
         // so a warp that holds a unit of env e + 1 which reads group g can only exist when every unit of env e that
         // reads g has been drawn and either finished or holds another warp; with 16 warps and 32 units per env at
@@ -478,24 +514,8 @@ tvf_qslab_kernel(const __grid_constant__ QsParams q, const __grid_constant__ CUt
         // so gfull[g] has completed phase e and a wait for phase e + 1 cannot alias.  (128 horizons only.)
         asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
         constexpr int RH = RG / 2;
-        double st_n = 0.0, st_s = 0.0, st_q = 0.0, st_z = 0.0;
-        float st_mn = INFINITY, st_mx = -INFINITY;
-        const int total_units = nenv * KQ;
         constexpr uint32_t TILE_BYTES = (N / 2) * 32;
-        // Results leave through a pool of output tiles (N / 2 rows x 32 bytes, TMA 32-byte swizzle: conflict-free
-        // 16-byte stores) and one tensor store per unit, issued by the warp itself.  The tile goes back to the pool
-        // once the store has read it -- checked a little into the next unit, when that costs no wait, but before any
-        // wait that may depend on other units finishing (they may need a tile to finish).
-        int pending = -1;
-        auto release_tile = [&]() {
-            if (pending >= 0) {
-                if (lane == 0) {
-                    qs_bulk_wait_read();
-                    atomicOr(tile_free, 1u << pending);
-                }
-                pending = -1;
-            }
-        };
+        const int total_units = nenv * KQ;
         for (;;) {
             int u = 0;
             if (lane == 0) u = atomicAdd(unit_counter, 1);
@@ -504,21 +524,11 @@ tvf_qslab_kernel(const __grid_constant__ QsParams q, const __grid_constant__ CUt
             const int e = u / KQ, j = u - e * KQ;
             const int oct = KQ / 2 - 1 - (j >> 1), half = j & 1;
             const uint32_t par = static_cast<uint32_t>(e & 1);
-            const int64_t env = env0 + e;
+            mbar_wait(&rfull[par], (static_cast<uint32_t>(e) >> 1) & 1u);
             const uint32_t need = q.need[oct];
-            {
-                bool ready = mbar_try_wait(&rfull[par], (static_cast<uint32_t>(e) >> 1) & 1u);
 #pragma unroll
-                for (int g = kQsGroups - 1; g >= 0; --g)
-                    if ((need >> g) & 1u) ready = ready && mbar_try_wait(&gfull[g], par);
-                if (!ready) {
-                    release_tile();
-                    mbar_wait(&rfull[par], (static_cast<uint32_t>(e) >> 1) & 1u);
-#pragma unroll
-                    for (int g = kQsGroups - 1; g >= 0; --g)
-                        if ((need >> g) & 1u) mbar_wait(&gfull[g], par);
-                }
-            }
+            for (int g = kQsGroups - 1; g >= 0; --g)
+                if ((need >> g) & 1u) mbar_wait(&gfull[g], par);
             const uint32_t rt = rt_a + par * RT_BYTES, lt = lim_a + par * RT_BYTES;
             const int t0 = half * (N / 2) + lane;  // the thread's rows: t0 + 32 i
             const uint32_t base_lane = wt_a + static_cast<uint32_t>(t0) * 4u;
@@ -533,22 +543,7 @@ tvf_qslab_kernel(const __grid_constant__ QsParams q, const __grid_constant__ CUt
                 if (m <= nmax && lim == m) endmask |= 1u << i;
             }
             const bool any_end = __any_sync(0xffffffffu, endmask != 0u) && !(q.dbg & 16);
-            float R[RH];
-#pragma unroll
-            for (int i = 0; i < RH; ++i) R[i] = qs_lds(rt + static_cast<uint32_t>(t0 + 32 * i) * 4u);
-            float* orow = p.out + (static_cast<int64_t>(t0) * p.envs + env) * kQsK + oct * 8;
-            const int64_t ostep = 32 * p.envs * kQsK;
             float4 prev[RH];  // the lower quad of the oct, kept until the upper one is ready
-            int tb_last = 0;
-            uint4 rec[RH];    // tail records of the horizon about to be evaluated (rows alive to the end)
-            if (any_end) {
-                const uint4* trow = q.tail4 + static_cast<int64_t>(oct * 8) * q.tail_pitch;
-#pragma unroll
-                for (int i = 0; i < RH; ++i) {
-                    rec[i] = make_uint4(0u, 0u, 0u, 0u);
-                    if ((endmask >> i) & 1u) rec[i] = __ldg(trow + (N - (t0 + 32 * i)));
-                }
-            }
 #pragma unroll 1
             for (int qq = 0; qq < 2; ++qq) {
                 float o[4][RH];
@@ -562,26 +557,19 @@ tvf_qslab_kernel(const __grid_constant__ QsParams q, const __grid_constant__ CUt
 #pragma unroll
                     for (int i = 0; i < RH; ++i) acc[i] = 0.f;
                     // rows whose n-step windows run off the rollout: one folded bootstrap from the final row (host
-                    // weights, one 16-byte record per (horizon, rows left); zero beyond the horizon's largest n-step).
-                    // The records were requested one horizon ago; the next horizon's are requested now, so their L2
-                    // latency hides behind this horizon's gathers.
-                    if (any_end) {
-                        if (maxn > 1) {
+                    // weights, one 16-byte record per (horizon, rows left); records exist for rows left < the horizon's
+                    // largest n-step)
+                    if (any_end && maxn > 1) {
+                        const uint4* trow = q.tail4 + static_cast<int64_t>(k) * q.tail_pitch;
 #pragma unroll
-                            for (int i = 0; i < RH; ++i) {
-                                const int m = N - (t0 + 32 * i);
-                                if (((endmask >> i) & 1u) && m < maxn) {
-                                    const float v0 = qs_lds(fr_a + (rec[i].x & 0xffffu) * 4u);
-                                    const float v1 = qs_lds(fr_a + (rec[i].x >> 16) * 4u);
-                                    acc[i] = fmaf(v1, __uint_as_float(rec[i].z), v0 * __uint_as_float(rec[i].y));
-                                }
+                        for (int i = 0; i < RH; ++i) {
+                            const int m = N - (t0 + 32 * i);
+                            if (((endmask >> i) & 1u) && m < maxn) {
+                                const uint4 r = __ldg(trow + m);
+                                const float v0 = qs_lds(fr_a + (r.x & 0xffffu) * 4u);
+                                const float v1 = qs_lds(fr_a + (r.x >> 16) * 4u);
+                                acc[i] = fmaf(v1, __uint_as_float(r.z), v0 * __uint_as_float(r.y));
                             }
-                        }
-                        if (qq * 4 + u4 < 7) {
-                            const uint4* trow = q.tail4 + static_cast<int64_t>(k + 1) * q.tail_pitch;
-#pragma unroll
-                            for (int i = 0; i < RH; ++i)
-                                if ((endmask >> i) & 1u) rec[i] = __ldg(trow + (N - (t0 + 32 * i)));
                         }
                     }
                     uint32_t ce = ent_a + (hz.x & 0xfffu) * kQsEntBytes;
@@ -590,64 +578,81 @@ tvf_qslab_kernel(const __grid_constant__ QsParams q, const __grid_constant__ CUt
                     if (left >= 2) qs_eval<2, RH, PITCH4>(ce, base_lane, key, acc), ce += 2 * kQsEntBytes, left -= 2;
                     if (left >= 1) qs_eval<1, RH, PITCH4>(ce, base_lane, key, acc);
                     rs[u4] = __uint_as_float(hz.y);
-                    if (u4 == 0) release_tile();  // (the previous unit's store has read its tile long ago)
                 }
                 // out = rscale * R(t) + acc (the entry and tail weights carry the 1 / C of the sample average)
-                int tb = 0;
-                if (qq == 1 && !(q.dbg & 1)) {
-                    if (lane == 0) {
-                        for (;;) {
-                            const unsigned int m = *reinterpret_cast<volatile unsigned int*>(tile_free);
-                            if (m != 0u) {
-                                tb = __ffs(static_cast<int>(m)) - 1;
-                                if (atomicAnd(tile_free, ~(1u << tb)) & (1u << tb)) break;
-                            } else {
-                                __nanosleep(40);
+                if (qq == 0) {
+#pragma unroll
+                    for (int i = 0; i < RH; ++i) {
+                        const float R = qs_lds(rt + static_cast<uint32_t>(t0 + 32 * i) * 4u);
+                        prev[i].x = fmaf(rs[0], R, o[0][i]), prev[i].y = fmaf(rs[1], R, o[1][i]);
+                        prev[i].z = fmaf(rs[2], R, o[2][i]), prev[i].w = fmaf(rs[3], R, o[3][i]);
+                    }
+                } else {
+                    // Both quads are ready: take a free output tile (N / 2 rows x 32 bytes, TMA 32-byte swizzle:
+                    // conflict-free 16-byte stores), fill it and hand it to the store warp.  Nothing blocks between
+                    // taking the tile and handing it over, and the store warp frees it as soon as the tensor store
+                    // has read it, so a handful of tiles serves sixteen warps.
+                    int tb = 0;
+                    if (!(q.dbg & 1)) {
+                        if (lane == 0) {
+                            for (;;) {
+                                const unsigned int m = *reinterpret_cast<volatile unsigned int*>(tile_free);
+                                if (m != 0u) {
+                                    tb = __ffs(static_cast<int>(m)) - 1;
+                                    if (atomicAnd(tile_free, ~(1u << tb)) & (1u << tb)) break;
+                                } else {
+                                    __nanosleep(40);
+                                }
                             }
                         }
+                        tb = __shfl_sync(0xffffffffu, tb, 0);
                     }
-                    tb = __shfl_sync(0xffffffffu, tb, 0);
-                    tb_last = tb;
-                }
-                const uint32_t tile = tile_a + static_cast<uint32_t>(tb) * TILE_BYTES;
+                    const uint32_t tile = tile_a + static_cast<uint32_t>(tb) * TILE_BYTES;
+                    float smn = INFINITY, smx = -INFINITY;
+                    double ssum = 0.0, ssq = 0.0, szero = 0.0;
 #pragma unroll
-                for (int i = 0; i < RH; ++i) {
-                    float4 v;
-                    v.x = fmaf(rs[0], R[i], o[0][i]), v.y = fmaf(rs[1], R[i], o[1][i]);
-                    v.z = fmaf(rs[2], R[i], o[2][i]), v.w = fmaf(rs[3], R[i], o[3][i]);
-                    if (qq == 0) {
-                        prev[i] = v;
-                    } else {
+                    for (int i = 0; i < RH; ++i) {
+                        const float R = qs_lds(rt + static_cast<uint32_t>(t0 + 32 * i) * 4u);
+                        float4 v;
+                        v.x = fmaf(rs[0], R, o[0][i]), v.y = fmaf(rs[1], R, o[1][i]);
+                        v.z = fmaf(rs[2], R, o[2][i]), v.w = fmaf(rs[3], R, o[3][i]);
                         if (!(q.dbg & 1)) {
-                            if (q.dbg & 32) {
-                                qs_stg256(orow + i * ostep, prev[i], v);  // (development: straight from the registers)
-                            } else {
-                                const uint32_t row = static_cast<uint32_t>(lane + 32 * i);
-                                const uint32_t sw = (row >> 2) & 1u;
-                                qs_sts128(tile + row * 32u + (sw << 4), prev[i]);
-                                qs_sts128(tile + row * 32u + ((sw ^ 1u) << 4), v);
-                            }
+                            const uint32_t row = static_cast<uint32_t>(lane + 32 * i);
+                            const uint32_t sw = (row >> 2) & 1u;
+                            qs_sts128(tile + row * 32u + (sw << 4), prev[i]);
+                            qs_sts128(tile + row * 32u + ((sw ^ 1u) << 4), v);
                         }
                         if (q.want_stats && oct == KQ / 2 - 1) {
                             const float x = v.w;
-                            st_n += 1.0, st_s += x, st_q += static_cast<double>(x) * x, st_z += x == 0.f ? 1.0 : 0.0;
-                            st_mn = fminf(st_mn, x), st_mx = fmaxf(st_mx, x);
+                            ssum += x, ssq += static_cast<double>(x) * x, szero += x == 0.f ? 1.0 : 0.0;
+                            smn = fminf(smn, x), smx = fmaxf(smx, x);
                         }
                     }
-                }
-            }
-            if (!(q.dbg & 1)) {
-                if (q.dbg & 32) {
-                    if (lane == 0) atomicOr(tile_free, 1u << tb_last);
-                } else {
-                    qs_fence_async();  // tile writes -> visible to the async proxy
-                    __syncwarp();
-                    if (lane == 0) {
-                        qs_tma_store_3d(&omap, tile_a + static_cast<uint32_t>(tb_last) * TILE_BYTES, oct * 8,
-                                        static_cast<int>(env), half * (N / 2));
-                        qs_bulk_commit();
+                    if (!(q.dbg & 1)) {
+                        qs_fence_async();  // tile writes -> visible to the async proxy
+                        __syncwarp();
+                        if (lane == 0) {
+                            // job word: valid | tile | oct | half | local env
+                            const unsigned int job = 0x80000000u | (static_cast<unsigned int>(tb) << 24) |
+                                                     (static_cast<unsigned int>(oct) << 20) |
+                                                     (static_cast<unsigned int>(half) << 19) | static_cast<unsigned int>(e);
+                            __threadfence_block();
+                            const unsigned int slot = atomicAdd(ring_tail, 1u) % kQsRing;
+                            // (a slot is free again long before the ring comes round: at most ntile jobs are open)
+                            *reinterpret_cast<volatile unsigned int*>(ring + slot) = job;
+                        }
                     }
-                    pending = tb_last;
+                    if (q.want_stats && oct == KQ / 2 - 1) {
+                        // statistics of the longest horizon: folded per warp into a shared-memory record (two units per
+                        // env carry it; registers stay with the gather loop)
+                        ssum = warp_sum_f64(ssum), ssq = warp_sum_f64(ssq), szero = warp_sum_f64(szero);
+                        smn = warp_min_f32(smn), smx = warp_max_f32(smx);
+                        if (lane == 0) {
+                            double* rec = reinterpret_cast<double*>(smem + q.off_stat) + warp * 8;
+                            rec[0] += 32.0 * RH, rec[1] += ssum, rec[2] += ssq, rec[5] += szero;
+                            rec[3] = fmin(rec[3], static_cast<double>(smn)), rec[4] = fmax(rec[4], static_cast<double>(smx));
+                        }
+                    }
                 }
             }
             __syncwarp();
@@ -658,21 +663,11 @@ tvf_qslab_kernel(const __grid_constant__ QsParams q, const __grid_constant__ CUt
                 mbar_arrive(&rempty[par]);
             }
         }
-        release_tile();
-        if (lane == 0) qs_bulk_wait_all();
         if (q.want_stats) {
-            // per-CTA record: the staging ring is idle by now (every chunk has been transposed and consumed)
+            // per-CTA record from the per-warp records
             asm volatile("bar.sync 1, %0;" ::"n"(kQsConsumers * 32) : "memory");
-            double* red = reinterpret_cast<double*>(smem + q.off_stage);
+            const double* red = reinterpret_cast<const double*>(smem + q.off_stat);
             const int cw = warp;
-            const double n = warp_sum_f64(st_n), sm = warp_sum_f64(st_s), sq = warp_sum_f64(st_q), sz = warp_sum_f64(st_z);
-            const float mn = warp_min_f32(st_mn), mx = warp_max_f32(st_mx);
-            if (lane == 0) {
-                red[cw * 8 + 0] = n, red[cw * 8 + 1] = sm, red[cw * 8 + 2] = sq;
-                red[cw * 8 + 3] = static_cast<double>(mn), red[cw * 8 + 4] = static_cast<double>(mx);
-                red[cw * 8 + 5] = sz;
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(kQsConsumers * 32) : "memory");
             if (cw == 0) {
                 double an = 0, as = 0, aq = 0, az = 0, amn = INFINITY, amx = -INFINITY;
                 if (lane < kQsConsumers) {
@@ -825,11 +820,12 @@ int launch_tvf_qslab(const TvfParams& p, double* stats, double* partials, unsign
     const uint32_t hz_bytes = qs_align(static_cast<uint32_t>(K) * 8u, 128);
     const uint32_t rt_bytes = 2u * (static_cast<uint32_t>(N) + 32u) * 4u;  // two env parities
     const uint32_t fr_bytes = qs_align(static_cast<uint32_t>(V) * 4u, 128);
-    const uint32_t misc_bytes = 128;
+    const uint32_t misc_bytes = 256, stat_bytes = kQsConsumers * 8 * 8;
     const uint32_t bar_bytes = (2 * kQsMaxStages + 2 * kQsGroups + 4) * 8u;
     const uint32_t tile_bytes = static_cast<uint32_t>(N / 2) * 32u;
     q.ntile = kQsMaxTiles;
-    const uint32_t rest = q.ntile * tile_bytes + ent_bytes + hz_bytes + 2 * rt_bytes + fr_bytes + misc_bytes + bar_bytes;
+    if (const char* t = getenv("PPO_QS_TILES")) q.ntile = std::max(1, std::min(kQsMaxTiles, atoi(t)));  // (development)
+    const uint32_t rest = q.ntile * tile_bytes + ent_bytes + hz_bytes + 2 * rt_bytes + fr_bytes + misc_bytes + stat_bytes + bar_bytes;
     int nstage = 0;
     while (nstage < kQsMaxStages && wt_bytes + rest + static_cast<uint32_t>(nstage + 1) * kQsChunkBytes <= static_cast<uint32_t>(max_smem))
         ++nstage;
@@ -843,7 +839,8 @@ int launch_tvf_qslab(const TvfParams& p, double* stats, double* partials, unsign
     q.off_lim = q.off_rtab + rt_bytes;
     q.off_fr = q.off_lim + rt_bytes;
     q.off_misc = q.off_fr + fr_bytes;
-    q.off_bar = q.off_misc + misc_bytes;
+    q.off_stat = q.off_misc + misc_bytes;
+    q.off_bar = q.off_stat + stat_bytes;
     q.smem_total = q.off_bar + bar_bytes;
 
     CUtensorMap vmap;  // value samples [N + 1, A, V]: 128 rows x 32 columns per load, 128-byte swizzle

@@ -476,8 +476,8 @@ class ReturnPass:
                     self.ws_tvf.data_ptr(), self.ws_tvf.numel(), ctypes.byref(extras) if extras is not None else None, s)
             _lib.check(rc, "ppo_tvf_targets")
             last = lib.ppo_tvf_last_path()
-            self.tvf_kernel = {1: "generic", 2: "ring", 3: "tslab", 4: "cslab"}.get(last & 0xff, "?")
-            if self.tvf_kernel == "tslab" and self.tvf_path == _rt.PATH_AUTO and self._sections == _rt.TABLES_ALL \
+            self.tvf_kernel = {1: "generic", 2: "ring", 3: "tslab", 4: "cslab", 5: "qslab"}.get(last & 0xff, "?")
+            if self.tvf_kernel in ("tslab", "qslab") and self.tvf_path == _rt.PATH_AUTO and self._sections == _rt.TABLES_ALL \
                     and os.environ.get("PPO_TVF_LEAN_TABLES", "1") != "0":
                 self._sections = _rt.TABLES_TSLAB
             self._tvf_launches = 1 + (0 if last & 0x100 else 1) + (1 if extras is not None and not last & 0x200 else 0)
