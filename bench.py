@@ -325,6 +325,22 @@ def other_configs(device, peak_gbs, iters=40):
             res = {"error": repr(e)}
         res["note"] = "1.07 GB per launch (> L2), targets only (no statistics, no value estimate)"
         out[f"c5_tvf_256x4096x128_fixed_n_step_20_{name}"] = res
+    del keep
+    # ---- the same shape with the headline's sample table (exponential / advanced, 8 samples), targets only, on each of
+    # the three slab kernels explicitly: PATH_AUTO takes the transposed slab kernel; the other two are kept honest here
+    table = rt.draw_n_step_samples("exponential", "advanced", hz, n, N_STEP, SAMPLES, seed=SAMPLE_SEED)
+    ctab, keep = rt._upload_tables(rt.build_tables(TVF_GAMMA, n, hz, hz, table), device)
+    for name, path in (("tslab", rt.PATH_TSLAB), ("qslab", rt.PATH_QSLAB), ("cslab", rt.PATH_CSLAB)):
+        def c5s(i):
+            _lib.check(lib.ppo_tvf_targets(r.data_ptr(), a, d.data_ptr(), _lib.DONE_U8, a, vs.data_ptr(), a * k, k,
+                                           n, a, k, k, ctypes.byref(ctab), path, tg.data_ptr(), 0, 0, 0, stream),
+                       "ppo_tvf_targets")
+        try:
+            res = timed(c5s, nbytes, n * a * k)
+        except Exception as e:
+            res = {"error": repr(e)}
+        res["note"] = "targets only (no statistics, no value estimate), explicit kernel path"
+        out[f"c5_tvf_256x4096x128_exponential_advanced_8_{name}"] = res
     del r, d, vs, tg, keep
 
     # ---- c1: GAE over 128 steps x 128 envs (the reference's own CPU-sized case): one launch, latency bound

@@ -4,21 +4,29 @@
 //   W[r, j] = V[r, j] - R(r),  R = discounted reward-to-go inside the rollout,  lim(t) = steps to the first terminal
 // (the return form of tvf_tslab.cu; rl/returns_truncated.py:558-693), on the same transposed slab W^T[col][row] of ONE
 // env, with the same launch constants (the transposed slab section of the table blob) and the same conflict-free
-// 4-byte gathers (lane <-> time row, 32 consecutive words per gather).  What differs is who owns what:
-//   * A consumer warp owns four consecutive horizons ("quad") for ALL rows of the env -- a thread carries rows
-//     lane + 32 i, i < N / 32 -- so the constants of an entry are fetched once per env instead of once per 64-row
-//     step (a quarter of the constant wavefronts), an entry costs 43 instructions for 16 gathers instead of 55, and
-//     there are no per-step hand-offs at all.
-//   * Quads are drawn from a shared counter in env order, highest horizons first.  Horizon k reads value columns
-//     near k, so the slab is refilled in column groups of 32, highest group first: a group is released when the last
-//     quad that reads it has finished (arrival counts from the tables), and the next env's columns stream in (TMA,
-//     128-byte swizzle -> transposing writes, lane <-> row) behind the quads that still work on the low horizons.
-//     Half of an env's work separates the release of a group from its next use, so nobody waits in the steady state.
-//   * Results leave the registers as 16-byte global stores (four horizons of one row); the two quads of a 32-byte
-//     sector are evaluated at about the same time by different warps and meet in L2.  No output tile, no store warp.
-// Warp roles: 0-15 consumers, 16-19 transform (+ the value estimate for GAE as a by-product), 20 scan (R and lim
-// tables, float64), 21 TMA producer, 22-23 idle (setmaxnreg works on whole warpgroups).  Registers move from the
-// helper warps to the consumers: 80 per thread at launch -> 96 / 48 (768 x 80 registers in the CTA pool).
+// 4-byte gathers (lane <-> time row, 32 consecutive words per gather) -- and bit-identical targets.  What differs is
+// who owns what:
+//   * A consumer warp owns eight consecutive horizons (two quads, one after the other) for HALF of the env's rows -- a
+//     thread carries rows half * N / 2 + lane + 32 i, i < N / 64 -- so the constants of an entry are fetched twice per
+//     env instead of once per 64-row step, an entry costs 23 instructions for 8 gathers instead of 27.5, and there are
+//     no per-step hand-offs between the consumer warps at all.
+//   * Units (env, eight horizons, half) are drawn from a shared counter in env order, highest horizons first.  Horizon
+//     k reads value columns near k, so the slab is refilled in column groups of 32, highest group first: a group is
+//     released when the last unit that reads it has finished (arrival counts from the tables), and the next env's
+//     columns stream in (TMA, 128-byte swizzle -> transposing writes, lane <-> row, the value estimate for GAE as a
+//     thread-local dot product) behind the units that still work on the low horizons.  Half of an env's work separates
+//     the release of a group from its next use.
+//   * Results leave as one tensor store per unit (N / 2 rows x 32 bytes: whole sectors) from a small pool of output
+//     tiles; a store warp issues the stores in the order the consumers publish the tiles and frees a tile as soon as
+//     its store has read it, so no consumer ever waits for another consumer.
+// Measured on B200 at 256 x 4096 x 128, eight exponential samples per horizon: 470 us against 452 us of
+// the transposed slab kernel, with 84 M shared-memory wavefronts and 281 M instructions against 105 M / 352 M; 363 us
+// without the output path.  What the output path taught: 16-byte global stores straight from the registers reach L2 as
+// partial-sector writes (734 us), 32-byte stores (st.global.v8.f32, one sector per lane) 470 us, tiles + tensor stores
+// the same.  PPO_TVF_AUTO does not select this kernel.
+// Warp roles: 0-15 consumers, 16-19 transform, 20 scan (R and lim tables, float64), 21 TMA producer, 22 store warp,
+// 23 idle (setmaxnreg works on whole warpgroups).  Registers move from the helper warps to the consumers: 80 per
+// thread at launch -> 96 / 48 (the CTA pool is 768 x 80 registers: 16 x 32 x 96 + 8 x 32 x 48).
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -51,7 +59,7 @@ struct QsParams {
     TvfParams p;
     double gamma;
     int tail_pitch, want_stats, want_value, nstage, n_ent;
-    int dbg;  // development switches (PPO_TVF_DEBUG): 1 no stores, 2 no TMA loads, 4 no transform, 8 no entry loop, 16 no tail term
+    int dbg;  // development switches (PPO_TVF_DEBUG): 1 no stores, 2 no TMA loads, 4 no transform
     int arrivals[kQsGroups];     // units (oct, half of the rows) of an env that read the column group
     unsigned char need[kQsQuads / 2];  // column groups an oct (eight consecutive horizons) reads (bit g)
     int64_t env_base, env_rem;
@@ -124,14 +132,6 @@ __device__ __forceinline__ void qs_bulk_wait_read() { asm volatile("cp.async.bul
 __device__ __forceinline__ void qs_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void qs_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// One 32-byte store per lane: a whole sector.  (Two 16-byte stores reach L2 as partial-sector writes, which cost it a
-// read-modify-write each: 734 us per pass instead of 363 us without the stores.)
-__device__ __forceinline__ void qs_stg256(float* dst, const float4& a, const float4& b) {
-    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"(a.x), "f"(a.y), "f"(a.z),
-                 "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
-                 : "memory");
-}
-
 // acc += [n <= lim] * (lo * wlo + hi * whi), the predicate taken on the packed entry word: w = n << 18 | off and
 // key = (lim + 1) << 18, so n <= lim  <=>  w < key.
 __device__ __forceinline__ void qs_fma_if(float& acc, float lo, float hi, float wlo, float whi, uint32_t w, uint32_t key) {
@@ -152,15 +152,35 @@ __device__ __forceinline__ void qs_gather(uint32_t a, float (&lo)[RG], float (&h
     }
 }
 
-// One entry for the thread's RG rows: 2 RG gathers, all issued before the first use.
+// One entry for the thread's RG rows: 2 RG gathers, all issued before the first use, then the multiply-adds row by row
+// within each slot (the four row chains are independent: no multiply-add waits for the one before it).
 template <int RG, int PITCH4>
 __device__ __forceinline__ void qs_entry(uint32_t w, float wlo, float whi, uint32_t base, const uint32_t (&key)[RG],
                                          float (&acc)[RG]) {
     const uint32_t a = base + (w & kQsOffMask);
     float lo[RG], hi[RG];
     qs_gather<0, RG, PITCH4>(a, lo, hi);
+    if constexpr (RG == 4) {
+        asm("{\n\t.reg .pred p0, p1, p2, p3;\n\t"
+            "setp.lt.u32 p0, %14, %15;\n\t"
+            "setp.lt.u32 p1, %14, %16;\n\t"
+            "setp.lt.u32 p2, %14, %17;\n\t"
+            "setp.lt.u32 p3, %14, %18;\n\t"
+            "@p0 fma.rn.f32 %0, %4, %12, %0;\n\t"
+            "@p1 fma.rn.f32 %1, %5, %12, %1;\n\t"
+            "@p2 fma.rn.f32 %2, %6, %12, %2;\n\t"
+            "@p3 fma.rn.f32 %3, %7, %12, %3;\n\t"
+            "@p0 fma.rn.f32 %0, %8, %13, %0;\n\t"
+            "@p1 fma.rn.f32 %1, %9, %13, %1;\n\t"
+            "@p2 fma.rn.f32 %2, %10, %13, %2;\n\t"
+            "@p3 fma.rn.f32 %3, %11, %13, %3;\n\t}"
+            : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3])
+            : "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(lo[3]), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(hi[3]), "f"(wlo),
+              "f"(whi), "r"(w), "r"(key[0]), "r"(key[1]), "r"(key[2]), "r"(key[3]));
+    } else {
 #pragma unroll
-    for (int i = 0; i < RG; ++i) qs_fma_if(acc[i], lo[i], hi[i], wlo, whi, w, key[i]);
+        for (int i = 0; i < RG; ++i) qs_fma_if(acc[i], lo[i], hi[i], wlo, whi, w, key[i]);
+    }
 }
 
 // G entries of one horizon; `cent` is 16-byte aligned for G = 4 and G = 2 and 8-byte aligned for G = 1 (the packed
@@ -307,27 +327,31 @@ tvf_qslab_kernel(const __grid_constant__ QsParams q, const __grid_constant__ CUt
         // and frees a tile as soon as its store has read it (stores complete in order; two may be pending).
         if (lane == 0 && !(q.dbg & 1)) {
             const int total = nenv * KQ;
-            unsigned int open[2] = {0u, 0u};  // tiles of the two youngest stores
+            int open = -1;  // tile of the youngest store, not yet known to have been read
             for (int n = 0; n < total; ++n) {
                 volatile unsigned int* slot = ring + (static_cast<unsigned int>(n) % kQsRing);
                 unsigned int job;
-                while (((job = *slot) & 0x80000000u) == 0u) __nanosleep(100);
+                while (((job = *slot) & 0x80000000u) == 0u) {
+                    if (open >= 0) {  // nothing to do: give the last tile back now
+                        qs_bulk_wait_read();
+                        atomicOr(tile_free, 1u << open);
+                        open = -1;
+                    } else {
+                        __nanosleep(100);
+                    }
+                }
                 *slot = 0u;
                 __threadfence_block();
                 const unsigned int tb = (job >> 24) & 0x7fu, oct = (job >> 20) & 0xfu, half = (job >> 19) & 1u, e = job & 0x7ffffu;
                 qs_tma_store_3d(&omap, tile_a + tb * ((N / 2) * 32u), static_cast<int>(oct * 8),
                                 static_cast<int>(env0 + e), static_cast<int>(half * (N / 2)));
                 qs_bulk_commit();
-                if (n >= 2) {
-                    asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
-                    atomicOr(tile_free, 1u << open[0]);
+                if (open >= 0) {
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the store before this one has read its tile
+                    atomicOr(tile_free, 1u << open);
                 }
-                open[0] = open[1], open[1] = tb;
-                if (n == 0) open[0] = tb;
+                open = static_cast<int>(tb);
             }
-            qs_bulk_wait_read();
-            if (total >= 2) atomicOr(tile_free, 1u << open[0]);
-            if (total >= 1) atomicOr(tile_free, 1u << open[1]);
             qs_bulk_wait_all();
         }
     } else if (warp == kQsConsumers + kQsXform + 1) {
@@ -542,7 +566,7 @@ tvf_qslab_kernel(const __grid_constant__ QsParams q, const __grid_constant__ CUt
                 const int m = N - t;
                 if (m <= nmax && lim == m) endmask |= 1u << i;
             }
-            const bool any_end = __any_sync(0xffffffffu, endmask != 0u) && !(q.dbg & 16);
+            const bool any_end = __any_sync(0xffffffffu, endmask != 0u);
             float4 prev[RH];  // the lower quad of the oct, kept until the upper one is ready
 #pragma unroll 1
             for (int qq = 0; qq < 2; ++qq) {
@@ -573,7 +597,7 @@ tvf_qslab_kernel(const __grid_constant__ QsParams q, const __grid_constant__ CUt
                         }
                     }
                     uint32_t ce = ent_a + (hz.x & 0xfffu) * kQsEntBytes;
-                    int left = (q.dbg & 8) ? 0 : static_cast<int>((hz.x >> 12) & 0xffu);
+                    int left = static_cast<int>((hz.x >> 12) & 0xffu);
                     for (; left >= 4; left -= 4, ce += 4 * kQsEntBytes) qs_eval<4, RH, PITCH4>(ce, base_lane, key, acc);
                     if (left >= 2) qs_eval<2, RH, PITCH4>(ce, base_lane, key, acc), ce += 2 * kQsEntBytes, left -= 2;
                     if (left >= 1) qs_eval<1, RH, PITCH4>(ce, base_lane, key, acc);
