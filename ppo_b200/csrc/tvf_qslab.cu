@@ -20,7 +20,7 @@
 //     tiles; a store warp issues the stores in the order the consumers publish the tiles and frees a tile as soon as
 //     its store has read it, so no consumer ever waits for another consumer.
 // Measured on B200 at 256 x 4096 x 128, eight exponential samples per horizon: 470 us against 452 us of
-// the transposed slab kernel, with 84 M shared-memory wavefronts and 281 M instructions against 105 M / 352 M; 363 us
+// the transposed slab kernel, with 96 M shared-memory wavefronts and 319 M instructions against 105 M / 352 M; 363 us
 // without the output path.  What the output path taught: 16-byte global stores straight from the registers reach L2 as
 // partial-sector writes (734 us), 32-byte stores (st.global.v8.f32, one sector per lane) 470 us, tiles + tensor stores
 // the same.  PPO_TVF_AUTO does not select this kernel.
