@@ -236,7 +236,7 @@ extern "C" int ppo_tvf_last_path(void) { return g_last_path; }
 // PPO_TVF_AUTO takes the quad slab kernel where it applies unless PPO_TVF_QSLAB=0 (read per call: A/B runs)
 static bool prefer_qslab() {
     const char* e = getenv("PPO_TVF_QSLAB");
-    return e != nullptr && atoi(e) != 0;
+    return e == nullptr || atoi(e) != 0;
 }
 
 extern "C" int64_t ppo_tvf_workspace_bytes(int64_t steps, int64_t envs) {
@@ -318,9 +318,13 @@ extern "C" int ppo_tvf_targets_ex(const float* rewards, int64_t reward_row_strid
         taken = PPO_TVF_CSLAB;
         if (rc == PPO_OK) vout = nullptr;  // the value estimate was written by the same launch
     }
-    if (path == PPO_TVF_QSLAB || (path == PPO_TVF_AUTO && tables->n_entries >= 3 && rc == PPO_ERR_UNSUPPORTED && prefer_qslab())) {
+    // (a caller that asks for the fused GAE stage gets the transposed slab kernel, the only one that has it)
+    const bool wants_gae = extras && extras->gae_enable;
+    if (path == PPO_TVF_QSLAB ||
+        (path == PPO_TVF_AUTO && tables->n_entries >= 3 && rc == PPO_ERR_UNSUPPORTED && !wants_gae && prefer_qslab())) {
         rc = launch_tvf_qslab(p, stats, partials, ticket, kStatsBlocks, vweights, vout, vout_rs, s, &stats_fused);
         if (path == PPO_TVF_QSLAB && rc != PPO_OK) return rc;
+        if (rc != PPO_OK && rc != PPO_ERR_UNSUPPORTED) return rc;
         if (rc == PPO_OK) {
             taken = PPO_TVF_QSLAB;
             vout = nullptr;  // the value estimate was written by the same launch

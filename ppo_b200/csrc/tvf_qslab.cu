@@ -183,21 +183,18 @@ __device__ __forceinline__ void qs_entry(uint32_t w, float wlo, float whi, uint3
     }
 }
 
-// G entries of one horizon; `cent` is 16-byte aligned for G = 4 and G = 2 and 8-byte aligned for G = 1 (the packed
-// 12-byte entries of tvf_tslab.cu: four entries = three broadcast 16-byte reads).
+// G = 2 or 1 entries of one horizon (the packed 12-byte entries of tvf_tslab.cu; `cent` is 8-byte aligned): a pair is
+// three broadcast 8-byte reads, one wavefront each -- 1.5 wavefronts per entry like the 16-byte reads of four entries
+// there, at half the registers (measured 461 us against 474 us with groups of four).
 template <int G, int RG, int PITCH4>
 __device__ __forceinline__ void qs_eval(uint32_t cent, uint32_t base, const uint32_t (&key)[RG], float (&acc)[RG]) {
     uint32_t w[3 * G];
-    if (G == 4) {
+    if (G == 2) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            const uint4 v = qs_lds128(cent + i * 16);
-            w[4 * i] = v.x, w[4 * i + 1] = v.y, w[4 * i + 2] = v.z, w[4 * i + 3] = v.w;
+            const uint2 u = qs_lds64(cent + i * 8);
+            w[2 * i] = u.x, w[2 * i + 1] = u.y;
         }
-    } else if (G == 2) {
-        const uint4 v = qs_lds128(cent);
-        const uint2 u = qs_lds64(cent + 16);
-        w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w, w[4] = u.x, w[5] = u.y;
     } else {
         const uint2 u = qs_lds64(cent);
         w[0] = u.x, w[1] = u.y, w[2] = qs_lds_u32(cent + 8);
@@ -243,6 +240,7 @@ tvf_qslab_kernel(const __grid_constant__ QsParams q, const __grid_constant__ CUt
     unsigned int* tile_free = reinterpret_cast<unsigned int*>(smem + q.off_misc + 16);  // bit b: output tile b is free
     unsigned int* ring_tail = reinterpret_cast<unsigned int*>(smem + q.off_misc + 32);  // jobs published so far
     unsigned int* ring = reinterpret_cast<unsigned int*>(smem + q.off_misc + 64);       // [kQsRing] job words of filled tiles
+    unsigned int* gcount = reinterpret_cast<unsigned int*>(smem + q.off_misc + 192);    // [5] transform-warp arrivals per column group, ever
     const uint32_t tile_a = smem_u32(smem + q.off_tile);
 
     const int64_t bidx = blockIdx.x;
@@ -341,7 +339,6 @@ tvf_qslab_kernel(const __grid_constant__ QsParams q, const __grid_constant__ CUt
                     }
                 }
                 *slot = 0u;
-                __threadfence_block();
                 const unsigned int tb = (job >> 24) & 0x7fu, oct = (job >> 20) & 0xfu, half = (job >> 19) & 1u, e = job & 0x7ffffu;
                 qs_tma_store_3d(&omap, tile_a + tb * ((N / 2) * 32u), static_cast<int>(oct * 8),
                                 static_cast<int>(env0 + e), static_cast<int>(half * (N / 2)));
@@ -499,7 +496,11 @@ tvf_qslab_kernel(const __grid_constant__ QsParams q, const __grid_constant__ CUt
                     if (lane == 0) mbar_arrive(&sempty[slot]);
                     if (++slot == q.nstage) slot = 0, spar ^= 1;
                 }
-                if (lane == 0) mbar_arrive(&gfull[g]);
+                if (lane == 0) {
+                    __threadfence_block();
+                    atomicAdd(gcount + g, 1u);
+                    mbar_arrive(&gfull[g]);
+                }
             }
             // the -R column (index V) last: its readers are the lowest horizons, the last quads of an env; column
             // V + 1 stays zero
@@ -508,7 +509,11 @@ tvf_qslab_kernel(const __grid_constant__ QsParams q, const __grid_constant__ CUt
             for (int c = 0; c < NCH; ++c)
                 qs_sts(wt_a + static_cast<uint32_t>(V * P + c * kQsChunkRows + rloc) * 4u, -Rr[c]);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&gfull[kQsSpecial]);
+            if (lane == 0) {
+                __threadfence_block();
+                atomicAdd(gcount + kQsSpecial, 1u);
+                mbar_arrive(&gfull[kQsSpecial]);
+            }
             if (wv) {
 #pragma unroll
                 for (int c = 0; c < NCH; ++c)
@@ -552,7 +557,13 @@ tvf_qslab_kernel(const __grid_constant__ QsParams q, const __grid_constant__ CUt
             const uint32_t need = q.need[oct];
 #pragma unroll
             for (int g = kQsGroups - 1; g >= 0; --g)
-                if ((need >> g) & 1u) mbar_wait(&gfull[g], par);
+                if ((need >> g) & 1u) {
+                    mbar_wait(&gfull[g], par);
+                    // the arrival count is the authority (a parity wait can only tell two neighbouring phases apart; the
+                    // argument above says that is enough -- this makes a table that breaks it cost a poll, not the data)
+                    while (*reinterpret_cast<volatile unsigned int*>(gcount + g) < static_cast<unsigned int>(kQsXform * (e + 1)))
+                        __nanosleep(20);
+                }
             const uint32_t rt = rt_a + par * RT_BYTES, lt = lim_a + par * RT_BYTES;
             const int t0 = half * (N / 2) + lane;  // the thread's rows: t0 + 32 i
             const uint32_t base_lane = wt_a + static_cast<uint32_t>(t0) * 4u;
@@ -568,6 +579,7 @@ tvf_qslab_kernel(const __grid_constant__ QsParams q, const __grid_constant__ CUt
             }
             const bool any_end = __any_sync(0xffffffffu, endmask != 0u);
             float4 prev[RH];  // the lower quad of the oct, kept until the upper one is ready
+
 #pragma unroll 1
             for (int qq = 0; qq < 2; ++qq) {
                 float o[4][RH];
@@ -598,8 +610,7 @@ tvf_qslab_kernel(const __grid_constant__ QsParams q, const __grid_constant__ CUt
                     }
                     uint32_t ce = ent_a + (hz.x & 0xfffu) * kQsEntBytes;
                     int left = static_cast<int>((hz.x >> 12) & 0xffu);
-                    for (; left >= 4; left -= 4, ce += 4 * kQsEntBytes) qs_eval<4, RH, PITCH4>(ce, base_lane, key, acc);
-                    if (left >= 2) qs_eval<2, RH, PITCH4>(ce, base_lane, key, acc), ce += 2 * kQsEntBytes, left -= 2;
+                    for (; left >= 2; left -= 2, ce += 2 * kQsEntBytes) qs_eval<2, RH, PITCH4>(ce, base_lane, key, acc);
                     if (left >= 1) qs_eval<1, RH, PITCH4>(ce, base_lane, key, acc);
                     rs[u4] = __uint_as_float(hz.y);
                 }
@@ -660,7 +671,7 @@ tvf_qslab_kernel(const __grid_constant__ QsParams q, const __grid_constant__ CUt
                             const unsigned int job = 0x80000000u | (static_cast<unsigned int>(tb) << 24) |
                                                      (static_cast<unsigned int>(oct) << 20) |
                                                      (static_cast<unsigned int>(half) << 19) | static_cast<unsigned int>(e);
-                            __threadfence_block();
+                            // (every lane's tile writes are fenced above and ordered before this store by the warp barrier)
                             const unsigned int slot = atomicAdd(ring_tail, 1u) % kQsRing;
                             // (a slot is free again long before the ring comes round: at most ntile jobs are open)
                             *reinterpret_cast<volatile unsigned int*>(ring + slot) = job;

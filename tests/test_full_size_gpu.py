@@ -30,7 +30,7 @@ def full():
     rp.set_samples(table)
     rp.run(r, None, d, vs)
     torch.cuda.synchronize()
-    assert rp.tvf_kernel == "tslab"
+    assert rp.tvf_kernel == "qslab"  # (PATH_AUTO at 256 steps x 128 horizons; PPO_TVF_QSLAB=0 gives the transposed slab kernel)
     return dict(hz=hz, r=r, d=d, vs=vs, table=table, rp=rp)
 
 

@@ -106,7 +106,7 @@ def test_return_pass_rebuilds_lean_tables_per_pass():
         tabs = rp.set_samples(table)
         assert bool(tabs.layout.sections & rt.TABLES_GENERIC) == (i == 0)
         rp.run(dr, None, dd, dvs)
-        assert rp.tvf_kernel == "tslab"
+        assert rp.tvf_kernel in ("tslab", "qslab")  # (qslab at 128 / 256 steps x 128 horizons)
         fresh = rollout.ReturnPass(steps, envs, hz, 0.999, 0.99997, 0.95, 0.9)
         fresh.set_samples(table)
         fresh.run(dr, None, dd, dvs)
@@ -120,7 +120,7 @@ def test_return_pass_rebuilds_lean_tables_per_pass():
     assert tabs.layout.sections & rt.TABLES_GENERIC  # the builder kept the generic tables for this one
     rp.run(dr, None, dd, dvs)
     torch.cuda.synchronize()
-    assert rp.tvf_kernel != "tslab"
+    assert rp.tvf_kernel not in ("tslab", "qslab")
     ref = oracle.sampled_return_multi(0.99997, r, d, hz, hz, vs, n_step_samples=fixed)
     assert rel_err(rp.tvf_returns.cpu().numpy(), ref) <= TOL
 
