@@ -233,10 +233,12 @@ static thread_local int g_last_path = 0;
 
 extern "C" int ppo_tvf_last_path(void) { return g_last_path; }
 
-// PPO_TVF_AUTO takes the quad slab kernel where it applies unless PPO_TVF_QSLAB=0 (read per call: A/B runs)
+// PPO_TVF_AUTO takes the quad slab kernel where it applies only with PPO_TVF_QSLAB=1 (read per call: A/B runs).  At
+// 256 steps the two kernels tie within the box-to-box spread (0.503-0.507 against 0.509-0.511 ms per bench pass), at 128
+// steps x 1024 envs the transposed slab kernel is faster (76 against 93 us): the older kernel stays the default.
 static bool prefer_qslab() {
     const char* e = getenv("PPO_TVF_QSLAB");
-    return e == nullptr || atoi(e) != 0;
+    return e != nullptr && atoi(e) != 0;
 }
 
 extern "C" int64_t ppo_tvf_workspace_bytes(int64_t steps, int64_t envs) {

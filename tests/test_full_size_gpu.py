@@ -30,7 +30,7 @@ def full():
     rp.set_samples(table)
     rp.run(r, None, d, vs)
     torch.cuda.synchronize()
-    assert rp.tvf_kernel == "qslab"  # (PATH_AUTO at 256 steps x 128 horizons; PPO_TVF_QSLAB=0 gives the transposed slab kernel)
+    assert rp.tvf_kernel in ("tslab", "qslab")  # (PATH_AUTO; the quad slab kernel with PPO_TVF_QSLAB=1)
     return dict(hz=hz, r=r, d=d, vs=vs, table=table, rp=rp)
 
 

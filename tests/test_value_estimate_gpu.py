@@ -130,7 +130,11 @@ def test_return_pass_with_values_from_the_curves(gamma):
     res2 = rollout.calculate_returns(torch.from_numpy(r).pin_memory(), None, torch.from_numpy(d).pin_memory(), gamma,
                                      0.95, 0.9, tvf=pinned, out=out)
     assert torch.equal(out["advantage"], torch.from_numpy(res["advantage"])) and torch.equal(out["tvf_returns"], rp.tvf_returns.cpu())
-    assert torch.equal(res2["value_estimates"].cpu(), rp.value_estimates.cpu())
+    # (the pass without the fusion and calculate_returns take the same kernel -- bit-identical estimates; the fused pass
+    # always runs on the transposed slab kernel, and the quad slab kernel (PPO_TVF_QSLAB=1) adds the 128 products of a
+    # row in another order)
+    assert torch.equal(res2["value_estimates"].cpu(), rp2.value_estimates.cpu())
+    assert rel_err(res2["value_estimates"].cpu().numpy(), rp.value_estimates.cpu().numpy()) <= 1e-6
 
 
 def test_runner_module_value_estimate_and_returns():
