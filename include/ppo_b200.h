@@ -486,6 +486,17 @@ int ppo_rms_fold_ema(const double* row_sums, const double* row_sq, int64_t steps
  * outputs, ema_var may be NULL, ticket is a zeroed device word (left zero). */
 int ppo_row_moments_fold(const double* x, int64_t steps, int64_t envs, double* row_sums, double* row_sq, double* rms,
                          double* ema_var, double ema_horizon, double* row_var, unsigned int* ticket, void* stream);
+/* ReturnTracker.update of rl/wrappers.py:737-755 (the multi-env reward normaliser, :946-971) over the N steps of a
+ * rollout: only the envs with mask[t, a] != 0 move (float32 state `carry` [A], rounded after every step like the
+ * reference's in-place NumPy assignment), and the running moments rms = {mean, var, count} take the float32 batch mean /
+ * variance of the masked envs of every step in order (a step without masked envs changes nothing, :750-751).
+ * tracker_out [N, A] f64 (scratch: the state after each step), row_records [3 N] f64 (scratch: count, mean, variance per
+ * step), row_var [N] f64 (optional: the running variance after each step -- what step t's masked rewards are divided
+ * by), ticket: a zeroed device word (left zero).  Two launches. */
+int ppo_return_tracker_masked(const float* rewards, int64_t reward_row_stride, const void* dones, int done_kind,
+                              int64_t done_row_stride, const unsigned char* mask, int64_t mask_row_stride, int64_t steps,
+                              int64_t envs, double gamma, float* carry, double* tracker_out, double* row_records,
+                              double* rms, double* row_var, unsigned int* ticket, void* stream);
 int ppo_scale_rewards(const float* rewards, int64_t reward_row_stride, int64_t steps, int64_t envs, const double* var,
                       int per_row, int mode, double eps, double clip, double scale, const double* center_stats,
                       float* out, unsigned long long* clips, void* stream);

@@ -29,5 +29,6 @@ from .tvf_np import (  # noqa: F401
     trim_horizons,
 )
 from .vtrace_np import importance_sampling_v_trace, v_trace_trust_region  # noqa: F401
-from .normalization_np import RunningMeanStd, intrinsic_returns, vec_normalize_rewards  # noqa: F401
+from .normalization_np import (RunningMeanStd, intrinsic_returns, vec_normalize_rewards, return_tracker_update,  # noqa: F401
+                               episodic_normalization_constant)
 from .train_np import tvf_value_loss  # noqa: F401

@@ -63,17 +63,52 @@ def intrinsic_returns(int_rewards, int_value, terminals, gamma_int, lambda_polic
     return adv, adv + int_value[:steps], int_rewards, scale
 
 
+def episodic_normalization_constant(k, discount_type, gamma=1.0, discount_bias=1.0):
+    """``EpisodicDiscounting.get_normalization_constant`` (rl/wrappers.py:52-72).  The reward wrapper calls it with the
+    default ``gamma=1.0`` (:872), for which "finite" raises ZeroDivisionError (plain Python, :55) and "geometric" gives
+    infinite normalisers (an array divided by zero, :60) -- there too."""
+    k = k + discount_bias  # :53
+    if discount_type == "finite":
+        m = 1 / (1 - gamma)  # :55
+        return np.clip(m - k, 0, float("inf")) + 1  # :56-58
+    if discount_type == "geometric":
+        return (gamma ** k) / (1 - gamma)  # :60
+    if discount_type == "quadratic":
+        return 1 / k  # :62
+    if discount_type == "power":
+        return (1 / 1e-1) * (k ** -1e-1)  # :64-65
+    if discount_type == "harmonic":
+        return 1 / np.log(k)  # :67
+    if discount_type == "none":
+        return 1.0  # :69
+    raise ValueError(f"Invalid discount_type {discount_type}")  # :71
+
+
+def return_tracker_update(current_returns, rms, rewards, dones, mask, gamma):
+    """``ReturnTracker.update`` (rl/wrappers.py:749-755): only the masked envs move, ``current_returns`` keeps its dtype
+    (float32 in the reference, :743), the running moments take the masked envs' batch."""
+    mask = np.asarray(mask, dtype=bool)
+    if sum(mask) == 0:  # :750-751
+        return
+    current_returns[mask] = rewards[mask] + gamma * current_returns[mask] * (1 - dones[mask])  # :754
+    rms.update(current_returns[mask])  # :755
+
+
 def vec_normalize_rewards(rewards, dones, gamma, current_returns, rms, clip=10.0, scale=1.0, epsilon=1e-2, mode="rms",
-                          ret_var=0.0, ema_horizon=5e6):
+                          ret_var=0.0, ema_horizon=5e6, ed_type=None, ed_bias=1.0, returns_transform=lambda x: x,
+                          times=None):
     """rl/wrappers.py:825-885 applied to each row of a [N, A] rollout in order.  ``current_returns`` [A] and ``rms``
     are updated in place.  Returns (scaled rewards [N, A], number of clipped elements) for mode "rms" and, for the
-    modes "ema" / "custom" (:878-881, :893-899), additionally the final ``ret_var``."""
+    modes "ema" / "custom" (:878-881, :893-899), additionally the final ``ret_var``.  ``ed_type`` / ``times`` [N, A]:
+    the episodic-discounting normalisers of :870-876 (``times`` are the envs' ``info['time']``)."""
     rewards = np.asarray(rewards)
     out = np.zeros(rewards.shape, dtype=np.float64)
     clips = 0
     for t in range(rewards.shape[0]):
         current_returns[:] = rewards[t] + gamma * current_returns * (1 - dones[t])  # :847
-        rms.update(current_returns)  # :856 (norms = 1, identity transform)
+        norms = 1 if ed_type is None else \
+            episodic_normalization_constant(np.asarray(times[t]), ed_type, discount_bias=ed_bias)  # :870-874
+        rms.update(returns_transform(current_returns / norms))  # :876
         if mode == "ema":  # :878-881
             alpha = 1 - (len(dones[t]) / min(rms.count, ema_horizon))
             ret_var = alpha * ret_var + (1 - alpha) * np.var(current_returns)

@@ -74,6 +74,8 @@ _SIGNATURES = {
     "ppo_rms_fold": (c_int, [c_ptr, c_ptr, c_i64, c_dbl, c_ptr, c_ptr, c_ptr]),
     "ppo_rms_fold_ema": (c_int, [c_ptr, c_ptr, c_i64, c_dbl, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr]),
     "ppo_row_moments_fold": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr]),
+    "ppo_return_tracker_masked": (c_int, [c_ptr, c_i64, c_ptr, c_int, c_i64, c_ptr, c_i64, c_i64, c_i64, c_dbl, c_ptr, c_ptr,
+                                          c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ppo_gather_rows": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr]),
     "ppo_tvf_value_loss": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_i64, c_dbl, c_ptr,
                                    c_ptr, c_ptr]),

@@ -255,6 +255,102 @@ __global__ void __launch_bounds__(256) scale_rewards_kernel(const ScaleParams p)
     }
 }
 
+// ---- ReturnTracker of rl/wrappers.py:737-755 (the multi-env reward normaliser, :946-971): the same forward
+// recurrence, but only the envs of a per-step MASK move, the state is float32 and is rounded after every step, and
+// the running moments take the batch moments of the masked envs only (a step without masked envs changes nothing).
+// The reference's arithmetic, step by step (NumPy, rewards float32):  gamma * cur -> float32;  * (1 - dones) -> float64
+// for boolean dones (int64 mask), float32 for float32 dones;  rewards + that -> float64 / float32;  stored as float32.
+struct MaskedTrackerParams {
+    const float* rewards;
+    int64_t r_rs;
+    const void* dones;
+    int done_kind;
+    int64_t d_rs;
+    const unsigned char* mask;
+    int64_t m_rs;
+    int64_t steps, envs;
+    float gamma32;
+    float* carry;  // [A] float32 in / out (ReturnTracker.current_returns)
+    double* x;     // [N, A] the state after every step (unchanged where the mask is off)
+};
+
+__global__ void __launch_bounds__(128) masked_tracker_scan_kernel(const MaskedTrackerParams p) {
+    const int64_t env = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (env >= p.envs) return;
+    float cur = p.carry[env];
+    for (int64_t t = 0; t < p.steps; ++t) {
+        if (__ldg(p.mask + t * p.m_rs + env)) {
+            const float r = __ldg(p.rewards + t * p.r_rs + env);
+            const float gc = __fmul_rn(p.gamma32, cur);
+            if (p.done_kind == PPO_DONE_F32) {
+                const float d = __ldg(static_cast<const float*>(p.dones) + t * p.d_rs + env);
+                cur = __fadd_rn(r, __fmul_rn(gc, __fsub_rn(1.0f, d)));
+            } else {
+                const bool d = p.done_kind == PPO_DONE_U8 && __ldg(static_cast<const unsigned char*>(p.dones) + t * p.d_rs + env) != 0;
+                cur = static_cast<float>(__dadd_rn(static_cast<double>(r), d ? 0.0 : static_cast<double>(gc)));
+            }
+        }
+        p.x[t * p.envs + env] = static_cast<double>(cur);
+    }
+    p.carry[env] = cur;
+}
+
+// One CTA per step: count, mean and variance of the masked envs (np.mean / np.var of a float32 vector: the results are
+// rounded to float32 like NumPy's), then the last CTA to finish merges the rows in order (rl/utils.py:379-396), skipping
+// the rows without a masked env (rl/wrappers.py:750-751); row_var records the running variance after every step.
+__global__ void __launch_bounds__(256) masked_row_moments_fold_kernel(const double* __restrict__ x,
+                                                                      const unsigned char* __restrict__ mask, int64_t m_rs,
+                                                                      int64_t steps, int64_t envs, double* row_rec,
+                                                                      double* rms, double* row_var, unsigned int* ticket) {
+    __shared__ double red[8], redn[8];
+    __shared__ double s_c;
+    __shared__ bool s_last;
+    const int64_t t = blockIdx.x;
+    const double* row = x + t * envs;
+    const unsigned char* mrow = mask + t * m_rs;
+    double total[2] = {0.0, 0.0}, count = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const double c = pass ? s_c : 0.0;
+        double acc = 0.0, n = 0.0;
+        for (int64_t a = threadIdx.x; a < envs; a += blockDim.x) {
+            if (__ldg(mrow + a)) {
+                const double v = __ldcg(row + a) - c;
+                acc += pass ? v * v : v;
+                n += 1.0;
+            }
+        }
+        acc = warp_sum_f64(acc), n = warp_sum_f64(n);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc, redn[threadIdx.x >> 5] = n;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0, m = 0.0;
+            for (int i = 0; i < 8; ++i) s += red[i], m += redn[i];
+            total[pass] = s, count = m;
+            if (pass == 0) s_c = m > 0.0 ? static_cast<double>(static_cast<float>(s / m)) : 0.0;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        row_rec[3 * t] = count;
+        row_rec[3 * t + 1] = s_c;                                                                    // float32 mean
+        row_rec[3 * t + 2] = count > 0.0 ? static_cast<double>(static_cast<float>(total[1] / count)) : 0.0;  // float32 var
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last || threadIdx.x != 0) return;
+    __threadfence();
+    RmsFold f{rms[0], rms[1], rms[2], 0.0};
+    for (int64_t i = 0; i < steps; ++i) {
+        const double n = __ldcg(row_rec + 3 * i);
+        if (n > 0.0) f.step(__ldcg(row_rec + 3 * i + 1), __ldcg(row_rec + 3 * i + 2), n, false, 1.0);
+        if (row_var) row_var[i] = f.var;
+    }
+    rms[0] = f.mean, rms[1] = f.var, rms[2] = f.count;
+    *ticket = 0u;
+}
+
 }  // namespace ppo
 
 using namespace ppo;
@@ -336,6 +432,30 @@ extern "C" int ppo_scale_rewards(const float* rewards, int64_t reward_row_stride
     const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
     if (blocks > cap) blocks = cap;
     scale_rewards_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    PPO_CUDA(cudaGetLastError());
+    return PPO_OK;
+}
+
+extern "C" int ppo_return_tracker_masked(const float* rewards, int64_t reward_row_stride, const void* dones,
+                                         int done_kind, int64_t done_row_stride, const unsigned char* mask,
+                                         int64_t mask_row_stride, int64_t steps, int64_t envs, double gamma,
+                                         float* carry, double* tracker_out, double* row_records, double* rms,
+                                         double* row_var, unsigned int* ticket, void* stream) {
+    PPO_REQUIRE(steps >= 0 && envs >= 0, "ppo_return_tracker_masked: negative shape [%lld, %lld]", (long long)steps,
+                (long long)envs);
+    PPO_REQUIRE(done_kind == PPO_DONE_NONE || done_kind == PPO_DONE_U8 || done_kind == PPO_DONE_F32,
+                "ppo_return_tracker_masked: unknown done_kind %d", done_kind);
+    if (steps == 0 || envs == 0) return PPO_OK;
+    PPO_REQUIRE(rewards && mask && carry && tracker_out && row_records && rms && ticket,
+                "ppo_return_tracker_masked: null pointer");
+    PPO_REQUIRE(done_kind == PPO_DONE_NONE || dones, "ppo_return_tracker_masked: dones is null but done_kind=%d", done_kind);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    MaskedTrackerParams p{rewards, reward_row_stride, dones, done_kind, done_row_stride, mask, mask_row_stride, steps, envs,
+                          static_cast<float>(gamma), carry, tracker_out};
+    masked_tracker_scan_kernel<<<static_cast<unsigned>((envs + 127) / 128), 128, 0, s>>>(p);
+    PPO_CUDA(cudaGetLastError());
+    masked_row_moments_fold_kernel<<<static_cast<unsigned>(steps), 256, 0, s>>>(tracker_out, mask, mask_row_stride, steps,
+                                                                              envs, row_records, rms, row_var, ticket);
     PPO_CUDA(cudaGetLastError());
     return PPO_OK;
 }

@@ -116,9 +116,12 @@ def _fold_rows(x, rms_state, group, row_var, ema=None):
                "ppo_rms_fold")
 
 
-def track_returns(rewards, dones, gamma, carry, rms, group=None, want_row_var=False, ema=None):
+def track_returns(rewards, dones, gamma, carry, rms, group=None, want_row_var=False, ema=None, transform=None):
     """The tracker scan + the N moment merges.  ``carry`` (float64 device tensor [A]) and ``rms`` are updated in
-    place; returns (rewards on the device, running variance after each step [N] or None)."""
+    place; returns (rewards on the device, running variance after each step [N] or None).  ``transform`` (optional): a
+    callable applied to the float64 [N, A] tracker rows on the device before they enter the running moments
+    (``returns_transform(current_returns / norms)``, ``rl/wrappers.py:876``); the EMA of the wrapper's mode "ema" keeps
+    following the variance of the untransformed tracker (:881)."""
     device = dev.require_cuda()
     lib = _lib.load()
     r = dev.env_contiguous(dev.to_device(rewards, torch.float32, device))
@@ -139,8 +142,95 @@ def track_returns(rewards, dones, gamma, carry, rms, group=None, want_row_var=Fa
     _lib.check(rc, "ppo_return_tracker_scan")
     row_var = torch.empty(steps, dtype=torch.float64, device=device) if want_row_var else None
     if steps and envs:
-        _fold_rows(x, rms.state, group, row_var, ema=ema)
+        if transform is None:
+            _fold_rows(x, rms.state, group, row_var, ema=ema)
+        else:
+            y = transform(x).to(torch.float64).contiguous()
+            if tuple(y.shape) != (steps, envs):
+                raise ValueError(f"the returns transform must keep the shape {(steps, envs)}, got {tuple(y.shape)}")
+            if ema is None:
+                _fold_rows(y, rms.state, group, row_var)
+            else:
+                # the moments take the transformed returns; the EMA weights only need the counts after each merge, which
+                # are the same for any data, so the raw tracker is folded into a scratch copy of the state
+                scratch = rms.state.clone()
+                _fold_rows(y, rms.state, group, None)
+                _fold_rows(x, scratch, group, row_var, ema=ema)
     return r, row_var
+
+
+def episodic_normalization_constant(times, discount_type, gamma=1.0, discount_bias=1.0):
+    """``EpisodicDiscounting.get_normalization_constant`` (``rl/wrappers.py:52-72``) on a device tensor of env times.
+    With the wrapper's ``gamma=1.0`` (:872) "finite" raises ZeroDivisionError (plain Python arithmetic, :55) and
+    "geometric" gives infinite normalisers (:60), like the reference."""
+    k = times.to(torch.float64) + float(discount_bias)
+    if discount_type == "finite":
+        m = 1 / (1 - gamma)
+        return torch.clamp(m - k, min=0.0) + 1
+    if discount_type == "geometric":
+        return (gamma ** k) / (1 - gamma)
+    if discount_type == "quadratic":
+        return 1 / k
+    if discount_type == "power":
+        return (1 / 1e-1) * (k ** -1e-1)
+    if discount_type == "harmonic":
+        return 1 / torch.log(k)
+    if discount_type == "none":
+        return torch.ones_like(k)
+    raise ValueError(f"Invalid discount_type {discount_type}")
+
+
+class ReturnTracker:
+    """``ReturnTracker`` of ``rl/wrappers.py:737-755`` (one per env type in the multi-env reward normaliser, :946-971):
+    float32 ``current_returns`` [A] and ``ret_rms`` on the device.  ``update`` is the reference's per-step call;
+    ``update_rollout`` takes the N steps of a rollout in one go (two launches, ``ppo_return_tracker_masked``) and
+    returns the running variance after every step."""
+
+    def __init__(self, num_envs, gamma, device=None):
+        self.device = device or dev.require_cuda()
+        self.ret_rms = RunningMeanStd(shape=(), device=self.device)
+        self.current_returns = torch.zeros(num_envs, dtype=torch.float32, device=self.device)
+        self.gamma = gamma
+
+    def reset(self):
+        self.current_returns.zero_()
+
+    def update(self, rewards, dones, mask):
+        """One step: rewards / dones / mask are [A] (``rl/wrappers.py:749-755``)."""
+        def row(a, dtype=None):
+            t = torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a)
+            return t.reshape(1, -1) if dtype is None else t.to(dtype).reshape(1, -1)
+        self.update_rollout(row(rewards), row(dones), row(mask))
+
+    def update_rollout(self, rewards, dones, mask):
+        """[N, A] rewards, dones and per-step masks -> the running variance after each step [N] (float64, device)."""
+        lib = _lib.load()
+        device = self.device
+        r = dev.env_contiguous(dev.to_device(rewards, torch.float32, device))
+        if r.dim() != 2 or r.shape[1] != self.current_returns.numel():
+            raise ValueError(f"rewards must be [N, {self.current_returns.numel()}], got {tuple(r.shape)}")
+        steps, envs = r.shape
+        d, kind = dev.done_tensor(dones, device)
+        if d is not None:
+            if tuple(d.shape) != (steps, envs):
+                raise ValueError(f"operands could not be broadcast together: dones {tuple(d.shape)} vs {(steps, envs)}")
+            d = dev.env_contiguous(d)
+        m = torch.as_tensor(np.asarray(mask) if not isinstance(mask, torch.Tensor) else mask)
+        if tuple(m.shape) != (steps, envs):
+            raise ValueError(f"mask must be [N, A] = {(steps, envs)}, got {tuple(m.shape)}")
+        m = (m != 0).to(device=device, dtype=torch.uint8).contiguous()
+        row_var = torch.empty(steps, dtype=torch.float64, device=device)
+        if steps == 0 or envs == 0:
+            return row_var
+        x = torch.empty((steps, envs), dtype=torch.float64, device=device)
+        rec = torch.empty(3 * steps, dtype=torch.float64, device=device)
+        ws = dev.workspace(256, device)
+        rc = lib.ppo_return_tracker_masked(dev.ptr(r), r.stride(0), dev.ptr(d), kind, d.stride(0) if d is not None else 0,
+                                           dev.ptr(m), m.stride(0), steps, envs, float(self.gamma),
+                                           dev.ptr(self.current_returns), dev.ptr(x), dev.ptr(rec),
+                                           dev.ptr(self.ret_rms.state), dev.ptr(row_var), dev.ptr(ws), dev.stream_ptr())
+        _lib.check(rc, "ppo_return_tracker_masked")
+        return row_var
 
 
 def _scale(r, var, per_row, mode, eps, clip, scale, center_stats, clips):
@@ -199,16 +289,19 @@ class IntrinsicReturns:
 
 
 class VecNormalizeRewards:
-    """``VecNormalizeRewardWrapper`` (``rl/wrappers.py:795-919``, ``ed_type=None``) over whole rollouts: rewards are
+    """``VecNormalizeRewardWrapper`` (``rl/wrappers.py:795-919``) over whole rollouts: rewards are
     divided by the return std AS OF THEIR OWN STEP, clipped and scaled.  ``mode``: "rms" (running variance over the
     whole history, what ``rl/envs.py:160-165`` configures), "ema" (``ret_var`` follows the variance of the tracker over
     the envs with ``alpha = 1 - A / min(count, ema_horizon)``, :878-881) or "custom" (the caller sets ``ret_var``).
-    Episodic-discounting normalisers (``ed_type``) are not provided."""
+    ``returns_transform`` (a callable on the device tensor of tracker rows) and the episodic-discounting normalisers
+    ``ed_type`` / ``ed_bias`` (:870-876; ``normalize_rollout`` then takes the envs' ``info['time']`` as ``times``
+    [N, A]) shape what enters the running moments, like in the reference."""
 
-    def __init__(self, num_envs, initial_state=None, gamma=1.0, clip=10.0, scale=1.0, mode="rms", ema_horizon=5e6,
-                 device=None):
+    def __init__(self, num_envs, initial_state=None, gamma=1.0, clip=10.0, scale=1.0, returns_transform=None, mode="rms",
+                 ed_type=None, ed_bias=1.0, ema_horizon=5e6, device=None):
         if mode not in ("rms", "ema", "custom"):
             raise ValueError(f"Invalid mode {mode}")
+        self.returns_transform, self.ed_type, self.ed_bias = returns_transform, ed_type, ed_bias
         self.device = device or dev.require_cuda()
         self.clip, self.epsilon, self.gamma, self.scale = clip, 1e-2, gamma, scale
         self.mode, self.ema_horizon = mode, float(ema_horizon)
@@ -239,13 +332,24 @@ class VecNormalizeRewards:
             return float(np.sqrt(self.ret_rms.var + self.epsilon))
         return float(np.sqrt(self.ret_var + self.epsilon))
 
-    def normalize_rollout(self, rewards, dones, group=None):
+    def normalize_rollout(self, rewards, dones, group=None, times=None):
         """[N, A] raw rewards and dones -> (scaled rewards [N, A] float32, number of clipped elements as a device
-        counter)."""
+        counter).  ``times`` [N, A]: the envs' ``info['time']`` per step, needed with ``ed_type`` (missing infos count
+        as 0 like ``info.get('time', 0)``, :871)."""
         np_like = dev.is_numpy_like(rewards)
         ema = (self._ret_var, self.ema_horizon) if self.mode == "ema" else None
+        transform = None
+        if self.ed_type is not None or self.returns_transform is not None:
+            norms = None
+            if self.ed_type is not None:
+                if times is None:
+                    raise ValueError("ed_type needs the envs' times [N, A]")
+                t = torch.as_tensor(np.asarray(times) if not isinstance(times, torch.Tensor) else times).to(self.device)
+                norms = episodic_normalization_constant(t, self.ed_type, discount_bias=self.ed_bias)  # :872
+            f = self.returns_transform if self.returns_transform is not None else (lambda v: v)
+            transform = lambda x: f(x if norms is None else x / norms)  # noqa: E731  (:876)
         r, row_var = track_returns(rewards, dones, self.gamma, self.current_returns, self.ret_rms, group=group,
-                                   want_row_var=self.mode != "custom", ema=ema)
+                                   want_row_var=self.mode != "custom", ema=ema, transform=transform)
         clips = torch.zeros(1, dtype=torch.int64, device=self.device)
         clip = -1.0 if self.clip is None else float(self.clip)
         if self.mode == "custom":  # one fixed variance for the whole rollout

@@ -148,9 +148,11 @@ def normalization_vectors(root, ref):
             out[f"ir_{tag}_rms_{roll}"] = np.asarray([r.mean, r.var, r.count], dtype=np.float64)
 
     # ---- VecNormalizeRewardWrapper.step over a rollout, fed by a stand-in vector env
-    gym = types.SimpleNamespace(Wrapper=type("Wrapper", (), {"__init__": lambda self, env: setattr(self, "env", env)}))
+    gym = types.SimpleNamespace(Wrapper=type("Wrapper", (), {"__init__": lambda self, env: setattr(self, "env", env)}),
+                                Env=object)
     wns = {"np": np, "math": math, "gym": gym, "utils": types.SimpleNamespace(RunningMeanStd=rms_cls),
            "VectorEnv": object, "Optional": typing.Optional, "EpisodicDiscounting": None}
+    exec(reference_source(root, "rl/wrappers.py", "EpisodicDiscounting"), wns)  # (its static normalisation constants)
     exec(reference_source(root, "rl/wrappers.py", "VecNormalizeRewardWrapper"), wns)
     rng = np.random.RandomState(9)
     steps, envs = 50, 16
@@ -158,6 +160,13 @@ def normalization_vectors(root, ref):
     rewards = rewards.astype(np.float32)
     dones = rng.random_sample([steps, envs]) < 0.04
     out["vn_in_rewards"], out["vn_in_dones"] = rewards, dones
+    # env times for the episodic-discounting normalisers (rl/wrappers.py:870-874): steps since the env's last reset
+    times = np.zeros([steps, envs], dtype=np.int64)
+    clock = rng.randint(0, 40, size=envs)
+    for t in range(steps):
+        times[t] = clock
+        clock = np.where(dones[t], 0, clock + 1)
+    out["vn_in_times"] = times
 
     class Env:
         num_envs = envs
@@ -168,12 +177,15 @@ def normalization_vectors(root, ref):
         def step(self, actions):
             t = self.t
             self.t += 1
-            return None, rewards[t], dones[t], [{} for _ in range(envs)]
+            return None, rewards[t], dones[t], [{"time": int(times[t, a])} for a in range(envs)]
 
     for tag, kwargs in [("default", dict(gamma=0.99)), ("noclip", dict(gamma=0.999, clip=-1, scale=0.5)),
                         ("tight", dict(gamma=0.9, clip=1.0)),
                         ("ema", dict(gamma=0.99, mode="ema", ema_horizon=200.0)),
-                        ("custom", dict(gamma=0.99, mode="custom", clip=3.0))]:
+                        ("custom", dict(gamma=0.99, mode="custom", clip=3.0)),
+                        ("edquad", dict(gamma=0.99, ed_type="quadratic")),
+                        ("edharm", dict(gamma=0.99, ed_type="harmonic", ed_bias=2.0, mode="ema", ema_horizon=300.0)),
+                        ("edpower", dict(gamma=0.995, ed_type="power", returns_transform=lambda x: x * 0.5))]:
         w = wns["VecNormalizeRewardWrapper"](Env(), **kwargs)
         if tag == "custom":
             w.ret_var = 6.25  # "custom requires setting of ret_std" (rl/wrappers.py:821)
@@ -187,6 +199,26 @@ def normalization_vectors(root, ref):
         out[f"vn_{tag}_returns"] = np.asarray(w.current_returns, dtype=np.float64)
         out[f"vn_{tag}_rms"] = np.asarray([w.ret_rms.mean, w.ret_rms.var, w.ret_rms.count], dtype=np.float64)
         out[f"vn_{tag}_ret_var"] = np.asarray(w.ret_var, dtype=np.float64)
+
+    # ---- ReturnTracker.update (rl/wrappers.py:737-755) over a rollout with per-step env masks (two env types, as the
+    # multi-env reward normaliser :946-971 would call it; one step has no env of the type at all)
+    tns = {"np": np, "utils": types.SimpleNamespace(RunningMeanStd=rms_cls)}
+    exec(reference_source(root, "rl/wrappers.py", "ReturnTracker"), tns)
+    rng = np.random.RandomState(21)
+    steps, envs = 30, 12
+    rt_rewards = (rng.randint(-1, 3, size=[steps, envs]) * rng.choice([1.0, 10.0], size=[steps, envs])).astype(np.float32)
+    rt_dones = rng.random_sample([steps, envs]) < 0.08
+    rt_mask = rng.random_sample([steps, envs]) < 0.6
+    rt_mask[7] = False
+    out["rt_in_rewards"], out["rt_in_dones"], out["rt_in_mask"] = rt_rewards, rt_dones, rt_mask
+    tracker = tns["ReturnTracker"](envs, 0.99)
+    rows, states = [], []
+    for t in range(steps):
+        tracker.update(rt_rewards[t], rt_dones[t], rt_mask[t])
+        rows.append(tracker.current_returns.copy())
+        states.append([tracker.ret_rms.mean, tracker.ret_rms.var, tracker.ret_rms.count])
+    out["rt_returns"] = np.stack(rows)                       # float32, after every step
+    out["rt_states"] = np.asarray(states, dtype=np.float64)  # running moments after every step
 
     # ---- TVFRunnerModule.on_train_value_minibatch (rl/tvf.py:32-77): per-sample loss and its gradient (autograd)
     import torch

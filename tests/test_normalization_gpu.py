@@ -76,6 +76,72 @@ def test_vec_normalize_rewards_golden(golden_norm, tag, kwargs):
     assert close64(w2.ret_rms.save_state(), w.ret_rms.save_state()) and abs(w2.std - w.std) <= 1e-12 * w.std
 
 
+@pytest.mark.parametrize("tag,kwargs", [
+    ("edquad", dict(gamma=0.99, ed_type="quadratic")),
+    ("edharm", dict(gamma=0.99, ed_type="harmonic", ed_bias=2.0, mode="ema", ema_horizon=300.0)),
+    ("edpower", dict(gamma=0.995, ed_type="power", returns_transform=lambda x: x * 0.5))])
+def test_vec_normalize_rewards_episodic_discounting_golden(golden_norm, tag, kwargs):
+    """ed_type / ed_bias / returns_transform (rl/wrappers.py:870-876) against the reference's own wrapper."""
+    g = golden_norm
+    w = nz.VecNormalizeRewards(g["vn_in_rewards"].shape[1], **kwargs)
+    scaled, clips = w.normalize_rollout(g["vn_in_rewards"], g["vn_in_dones"], times=g["vn_in_times"])
+    assert rel_err(scaled, g[f"vn_{tag}_scaled"]) <= 1e-6
+    assert int(clips.item()) == int(g[f"vn_{tag}_clips"])
+    assert close64(w.current_returns.cpu().numpy(), g[f"vn_{tag}_returns"])
+    assert close64(w.ret_rms.save_state(), g[f"vn_{tag}_rms"])
+    assert abs(w.ret_var - float(g[f"vn_{tag}_ret_var"])) <= 1e-9 * max(1.0, float(g[f"vn_{tag}_ret_var"]))
+    with pytest.raises(ValueError, match="times"):
+        nz.VecNormalizeRewards(4, ed_type="quadratic").normalize_rollout(np.zeros((2, 4), np.float32), np.zeros((2, 4), bool))
+    with pytest.raises(ZeroDivisionError):
+        nz.episodic_normalization_constant(torch.arange(3, device="cuda"), "finite")
+    assert bool(torch.isinf(nz.episodic_normalization_constant(torch.arange(3, device="cuda"), "geometric")).all())
+    with pytest.raises(ValueError, match="Invalid discount_type"):
+        nz.episodic_normalization_constant(torch.arange(3, device="cuda"), "linear")
+
+
+def test_return_tracker_masked_golden(golden_norm):
+    """ReturnTracker (rl/wrappers.py:737-755): the whole rollout in one call, then step by step like the reference's
+    caller; float32 state bit for bit, running moments to the float32 rounding of NumPy's batch mean / variance."""
+    g = golden_norm
+    steps, envs = g["rt_in_rewards"].shape
+    tr = nz.ReturnTracker(envs, 0.99)
+    row_var = tr.update_rollout(g["rt_in_rewards"], g["rt_in_dones"], g["rt_in_mask"])
+    assert np.array_equal(tr.current_returns.cpu().numpy(), g["rt_returns"][-1])
+    assert close64(tr.ret_rms.save_state(), g["rt_states"][-1], tol=1e-6)
+    assert close64(row_var.cpu().numpy(), g["rt_states"][:, 1], tol=1e-6)
+    step = nz.ReturnTracker(envs, 0.99)
+    for t in range(steps):
+        step.update(g["rt_in_rewards"][t], g["rt_in_dones"][t], g["rt_in_mask"][t])
+        assert np.array_equal(step.current_returns.cpu().numpy(), g["rt_returns"][t]), t
+        assert close64(step.ret_rms.save_state(), g["rt_states"][t], tol=1e-6), t
+    assert torch.equal(step.current_returns, tr.current_returns) and torch.equal(step.ret_rms.state, tr.ret_rms.state)
+    tr.reset()
+    assert float(tr.current_returns.abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("steps,envs,kind", [(1, 1, "bool"), (64, 4096, "bool"), (300, 70, "f32"), (17, 1000, "none")])
+def test_return_tracker_masked_vs_oracle(steps, envs, kind):
+    rng = np.random.RandomState(steps + envs)
+    r = (rng.randint(-1, 3, size=[steps, envs]) * rng.choice([1.0, 7.0], size=[steps, envs])).astype(np.float32)
+    d = rng.random_sample([steps, envs]) < 0.05
+    dones = d if kind == "bool" else d.astype(np.float32) if kind == "f32" else None
+    mask = rng.random_sample([steps, envs]) < 0.5
+    mask[steps // 2] = False
+    cur, rms = np.zeros(envs, dtype=np.float32), oracle.RunningMeanStd()
+    var = []
+    for t in range(steps):
+        oracle.return_tracker_update(cur, rms, r[t], dones[t] if dones is not None else np.zeros(envs, bool), mask[t], 0.97)
+        var.append(rms.var)
+    tr = nz.ReturnTracker(envs, 0.97)
+    row_var = tr.update_rollout(r, dones, mask)
+    got = tr.current_returns.cpu().numpy()
+    assert np.max(np.abs(got - cur)) <= 1e-6 * max(np.max(np.abs(cur)), 1.0)  # (float32 dones: one float32 product more)
+    if kind != "f32":
+        assert np.array_equal(got, cur)
+    assert close64(tr.ret_rms.save_state(), rms.state(), tol=1e-5)
+    assert close64(row_var.cpu().numpy(), var, tol=1e-5)
+
+
 @pytest.mark.parametrize("steps,envs", [(1, 1), (5, 33), (256, 4096), (300, 70), (700, 40)])
 def test_trackers_vs_oracle(steps, envs):
     """Ragged shapes, more steps than one register pass (256), device tensors in -> device tensors out."""

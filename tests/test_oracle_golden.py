@@ -208,6 +208,39 @@ def test_vec_normalize_rewards(golden_norm):
         assert same(np.asarray(ret_var, dtype=np.float64), g[f"vn_{tag}_ret_var"]), tag
 
 
+def test_vec_normalize_rewards_episodic_discounting(golden_norm):
+    """The wrapper's ed_type / returns_transform (rl/wrappers.py:870-876, EpisodicDiscounting.get_normalization_constant
+    :52-72), bit for bit."""
+    g = golden_norm
+    for tag, gamma, kwargs in [("edquad", 0.99, dict(ed_type="quadratic")),
+                               ("edharm", 0.99, dict(ed_type="harmonic", ed_bias=2.0, mode="ema", ema_horizon=300.0)),
+                               ("edpower", 0.995, dict(ed_type="power", returns_transform=lambda x: x * 0.5))]:
+        cur, rms = np.zeros(g["vn_in_rewards"].shape[1], dtype=np.float64), oracle.RunningMeanStd()
+        res = oracle.vec_normalize_rewards(g["vn_in_rewards"], g["vn_in_dones"], gamma, cur, rms, times=g["vn_in_times"],
+                                           **kwargs)
+        assert same(res[0], g[f"vn_{tag}_scaled"]) and res[1] == int(g[f"vn_{tag}_clips"]), tag
+        assert same(cur, g[f"vn_{tag}_returns"]) and same(rms.state(), g[f"vn_{tag}_rms"]), tag
+        if len(res) == 3:
+            assert same(np.asarray(res[2], dtype=np.float64), g[f"vn_{tag}_ret_var"]), tag
+    with pytest.raises(ZeroDivisionError):  # the wrapper's gamma = 1.0 (:872): 1 / (1 - gamma) in plain Python (:55)
+        oracle.episodic_normalization_constant(np.arange(3), "finite")
+    with np.errstate(divide="ignore"):      # ... and an array divided by zero (:60): infinite normalisers, no exception
+        assert np.all(np.isinf(oracle.episodic_normalization_constant(np.arange(3), "geometric")))
+    with pytest.raises(ValueError):
+        oracle.episodic_normalization_constant(np.arange(3), "linear")
+
+
+def test_return_tracker_masked(golden_norm):
+    """ReturnTracker.update (rl/wrappers.py:737-755) with per-step env masks, bit for bit (float32 state)."""
+    g = golden_norm
+    cur, rms = np.zeros(g["rt_in_rewards"].shape[1], dtype=np.float32), oracle.RunningMeanStd()
+    for t in range(g["rt_in_rewards"].shape[0]):
+        oracle.return_tracker_update(cur, rms, g["rt_in_rewards"][t], g["rt_in_dones"][t], g["rt_in_mask"][t], 0.99)
+        assert cur.dtype == np.float32 and np.array_equal(cur, g["rt_returns"][t]), t
+        assert same(rms.state(), g["rt_states"][t]), t
+    assert np.array_equal(g["rt_states"][7], g["rt_states"][6])  # the step without a masked env changed nothing
+
+
 LOSS_CASES = [("all", "off", None, None), ("hweighted", "h_weighted", None, None), ("single", "h_weighted", [5], 5),
               ("prefix", "off", list(range(8)), -7)]
 
