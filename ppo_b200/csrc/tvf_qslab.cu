@@ -129,6 +129,11 @@ __device__ __forceinline__ void qs_tma_store_3d(const CUtensorMap* map, uint32_t
                  ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+// the three live words of a 16-byte tail record {slots, weight lo, weight hi, 0}
+__device__ __forceinline__ void qs_ldg_rec(const uint4* p, uint32_t& x, uint32_t& y, uint32_t& z) {
+    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "l"(p));
+    asm volatile("ld.global.nc.u32 %0, [%1+8];" : "=r"(z) : "l"(p));
+}
 __device__ __forceinline__ void qs_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void qs_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void qs_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -581,6 +586,15 @@ tvf_qslab_kernel(const __grid_constant__ QsParams q, const __grid_constant__ CUt
             }
             const bool any_end = __any_sync(0xffffffffu, endmask != 0u);
             float4 prev[RH];  // the lower quad of the oct, kept until the upper one is ready
+            uint32_t rx[RH], ry[RH], rz[RH];  // tail records of the horizon about to be evaluated (rows alive to the end)
+#pragma unroll
+            for (int i = 0; i < RH; ++i) rx[i] = 0u, ry[i] = 0u, rz[i] = 0u;
+            if (any_end) {
+                const uint4* trow = q.tail4 + static_cast<int64_t>(oct * 8) * q.tail_pitch;
+#pragma unroll
+                for (int i = 0; i < RH; ++i)
+                    if ((endmask >> i) & 1u) qs_ldg_rec(trow + (N - (t0 + 32 * i)), rx[i], ry[i], rz[i]);
+            }
 
 #pragma unroll 1
             for (int qq = 0; qq < 2; ++qq) {
@@ -596,18 +610,25 @@ tvf_qslab_kernel(const __grid_constant__ QsParams q, const __grid_constant__ CUt
                     for (int i = 0; i < RH; ++i) acc[i] = 0.f;
                     // rows whose n-step windows run off the rollout: one folded bootstrap from the final row (host
                     // weights, one 16-byte record per (horizon, rows left); records exist for rows left < the horizon's
-                    // largest n-step)
-                    if (any_end && maxn > 1) {
-                        const uint4* trow = q.tail4 + static_cast<int64_t>(k) * q.tail_pitch;
+                    // largest n-step).  The records were requested one horizon ago (463.9 -> 447.2 us: a unit of the
+                    // upper half no longer waits for L2 in front of every horizon's gathers).
+                    if (any_end) {
+                        if (maxn > 1) {
 #pragma unroll
-                        for (int i = 0; i < RH; ++i) {
-                            const int m = N - (t0 + 32 * i);
-                            if (((endmask >> i) & 1u) && m < maxn) {
-                                const uint4 r = __ldg(trow + m);
-                                const float v0 = qs_lds(fr_a + (r.x & 0xffffu) * 4u);
-                                const float v1 = qs_lds(fr_a + (r.x >> 16) * 4u);
-                                acc[i] = fmaf(v1, __uint_as_float(r.z), v0 * __uint_as_float(r.y));
+                            for (int i = 0; i < RH; ++i) {
+                                const int m = N - (t0 + 32 * i);
+                                if (((endmask >> i) & 1u) && m < maxn) {
+                                    const float v0 = qs_lds(fr_a + (rx[i] & 0xffffu) * 4u);
+                                    const float v1 = qs_lds(fr_a + (rx[i] >> 16) * 4u);
+                                    acc[i] = fmaf(v1, __uint_as_float(rz[i]), v0 * __uint_as_float(ry[i]));
+                                }
                             }
+                        }
+                        if (qq * 4 + u4 < 7) {  // the next horizon's records: their L2 latency hides behind this one's gathers
+                            const uint4* trow = q.tail4 + static_cast<int64_t>(k + 1) * q.tail_pitch;
+#pragma unroll
+                            for (int i = 0; i < RH; ++i)
+                                if ((endmask >> i) & 1u) qs_ldg_rec(trow + (N - (t0 + 32 * i)), rx[i], ry[i], rz[i]);
                         }
                     }
                     uint32_t ce = ent_a + (hz.x & 0xfffu) * kQsEntBytes;
