@@ -233,12 +233,14 @@ static thread_local int g_last_path = 0;
 
 extern "C" int ppo_tvf_last_path(void) { return g_last_path; }
 
-// PPO_TVF_AUTO takes the quad slab kernel where it applies only with PPO_TVF_QSLAB=1 (read per call: A/B runs).  At
-// 256 steps the two kernels tie within the box-to-box spread (0.503-0.507 against 0.509-0.511 ms per bench pass), at 128
-// steps x 1024 envs the transposed slab kernel is faster (76 against 93 us): the older kernel stays the default.
-static bool prefer_qslab() {
+// PPO_TVF_AUTO takes the quad slab kernel at 256 steps (x 128 horizons on 128 value horizons: the launcher checks the
+// rest) -- 0.492 against 0.511 ms per bench pass, same box, bit-identical targets; at 128 steps x 1024 envs the transposed
+// slab kernel is the faster one and stays.  PPO_TVF_QSLAB=0 / 1 in the environment forces the choice (read per call: A/B
+// runs).
+static bool prefer_qslab(int64_t steps) {
     const char* e = getenv("PPO_TVF_QSLAB");
-    return e != nullptr && atoi(e) != 0;
+    if (e != nullptr) return atoi(e) != 0;
+    return steps == 256;
 }
 
 extern "C" int64_t ppo_tvf_workspace_bytes(int64_t steps, int64_t envs) {
@@ -323,7 +325,7 @@ extern "C" int ppo_tvf_targets_ex(const float* rewards, int64_t reward_row_strid
     // (a caller that asks for the fused GAE stage gets the transposed slab kernel, the only one that has it)
     const bool wants_gae = extras && extras->gae_enable;
     if (path == PPO_TVF_QSLAB ||
-        (path == PPO_TVF_AUTO && tables->n_entries >= 3 && rc == PPO_ERR_UNSUPPORTED && !wants_gae && prefer_qslab())) {
+        (path == PPO_TVF_AUTO && tables->n_entries >= 3 && rc == PPO_ERR_UNSUPPORTED && !wants_gae && prefer_qslab(steps))) {
         rc = launch_tvf_qslab(p, stats, partials, ticket, kStatsBlocks, vweights, vout, vout_rs, s, &stats_fused);
         if (path == PPO_TVF_QSLAB && rc != PPO_OK) return rc;
         if (rc != PPO_OK && rc != PPO_ERR_UNSUPPORTED) return rc;
