@@ -19,13 +19,13 @@
 //   * Results leave as one tensor store per unit (N / 2 rows x 32 bytes: whole sectors) from a small pool of output
 //     tiles; a store warp issues the stores in the order the consumers publish the tiles and frees a tile as soon as
 //     its store has read it, so no consumer ever waits for another consumer.
-// Measured on B200 at 256 x 4096 x 128, eight exponential samples per horizon: 460-465 us against
-// 453-455 us of the transposed slab kernel for the targets alone, 0.505 against 0.510 ms per bench pass (statistics and
-// value estimate fused, a fresh table per pass) -- a tie within the box-to-box spread -- with 97 M shared-memory
-// wavefronts and 333 M instructions against 105 M / 352 M, and 363 us without the output path; at 128 steps x 1024 envs
-// it loses (93 against 76 us).  What the output path taught: 16-byte global stores straight from the registers reach L2
-// as partial-sector writes (734 us), 32-byte stores (st.global.v8.f32, one sector per lane) 470 us, tiles + tensor
-// stores 460-475 us.  PPO_TVF_AUTO selects this kernel only with PPO_TVF_QSLAB=1 in the environment.
+// Measured on B200 at 256 x 4096 x 128, eight exponential samples per horizon: 447-449 us against
+// 453-455 us of the transposed slab kernel for the targets alone, 0.492 against 0.511 ms per bench pass (statistics and
+// value estimate fused, a fresh table per pass; same box), with 94 M shared-memory wavefronts and 339 M instructions
+// against 105 M / 352 M, and 363-390 us without the output path; at 128 steps x 1024 envs it loses (93 against 76 us).
+// What the output path taught: 16-byte global stores straight from the registers reach L2 as partial-sector writes
+// (734 us), 32-byte stores (st.global.v8.f32, one sector per lane) 470 us, tiles + tensor stores 460-475 us (before the
+// tail records were fetched ahead).  PPO_TVF_AUTO selects this kernel at 256 steps (PPO_TVF_QSLAB=0 / 1 forces it).
 // Warp roles: 0-15 consumers, 16-19 transform, 20 scan (R and lim tables, float64), 21 TMA producer, 22 store warp,
 // 23 idle (setmaxnreg works on whole warpgroups).  Registers move from the helper warps to the consumers: 80 per
 // thread at launch -> 96 / 48 (the CTA pool is 768 x 80 registers: 16 x 32 x 96 + 8 x 32 x 48).

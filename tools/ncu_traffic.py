@@ -17,8 +17,8 @@ def main():
            "lsu_shared_wavefronts": num("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
            "lsu_shared_pipe_pct": num("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
            "shared_bank_conflicts": num("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
-           "note": "one ncu --set full capture, tools/prof_tvf.py 4096 advanced8 tslab (256 steps x 4096 envs x 128 "
-                   "horizons); writes still resident in L2 at kernel end are not in dram__bytes_write"}
+           "note": "one ncu --set full capture of the named kernel at the bench shape (256 steps x 4096 envs x 128 "
+                   "horizons, exponential / advanced 8 samples); writes still resident in L2 at kernel end are not in dram__bytes_write"}
     json.dump(rec, open(out, "w"), indent=1)
     print(json.dumps(rec, indent=1))
 
