@@ -116,6 +116,50 @@ def test_qslab_fuzz_against_the_generic_kernel(seed):
     assert rel_err(got, ref) <= TOL, (steps, envs, c)
 
 
+@pytest.mark.parametrize("kind", ["f32", "none", "cuda"])
+def test_qslab_done_kinds_and_device_inputs(kind):
+    """float32 terminals (rl/returns_truncated.py accepts 0 / 1 masks of either dtype), no terminals at all, and CUDA
+    tensors in -> CUDA tensor out."""
+    steps, envs = 256, 77
+    hz = oracle.get_value_head_horizons(128, 30000)
+    r, d, _ = synthetic.rollout(steps, envs, seed=31, done_prob=0.04)
+    vs = synthetic.value_samples(steps, envs, len(hz), seed=32)
+    table = oracle.draw_n_step_samples("exponential", "advanced", hz, steps, 20, 8, seed=7)
+    if kind == "none":
+        d = np.zeros_like(d)
+    ref = oracle.sampled_return_multi(0.99997, r, d, hz, hz, vs, n_step_samples=table)
+    if kind == "f32":
+        got = rt._calculate_sampled_return_multi_fast(0.99997, r, d.astype(np.float32), hz, hz, vs, n_step_samples=table,
+                                                      path=rt.PATH_QSLAB)
+    elif kind == "none":
+        got = rt._calculate_sampled_return_multi_fast(0.99997, r, d, hz, hz, vs, n_step_samples=table, path=rt.PATH_QSLAB)
+    else:
+        out = rt._calculate_sampled_return_multi_fast(0.99997, torch.from_numpy(r).cuda(), torch.from_numpy(d).cuda(), hz, hz,
+                                                      torch.from_numpy(vs).cuda(), n_step_samples=table, path=rt.PATH_QSLAB)
+        assert isinstance(out, torch.Tensor) and out.is_cuda
+        got = out.cpu().numpy()
+    assert _lib.load().ppo_tvf_last_path() & 0xff == rt.PATH_QSLAB
+    assert rel_err(got, ref) <= TOL
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_qslab_unsorted_required_horizons(seed):
+    """Required horizons in any order: the column groups a unit reads are then not monotone in the order the units are
+    drawn -- the case the arrival counts behind the parity waits exist for.  Against the generic kernel."""
+    rng = np.random.RandomState(700 + seed)
+    steps, envs = 256, int(rng.choice([5, 160, 301]))
+    vsh = oracle.get_value_head_horizons(128, 30000)
+    req = rng.permutation(vsh)  # every value horizon once, shuffled
+    table = rng.randint(1, 60, size=[128, 6])
+    r = rng.randint(-1, 3, size=[steps, envs]).astype(np.float32)
+    d = rng.rand(steps, envs) < 0.03
+    vs = rng.normal(0.1, 0.4, size=[steps + 1, envs, 128]).astype(np.float32)
+    ref = rt._calculate_sampled_return_multi_fast(0.9997, r, d, req, vsh, vs, n_step_samples=table, path=rt.PATH_GENERIC)
+    got = rt._calculate_sampled_return_multi_fast(0.9997, r, d, req, vsh, vs, n_step_samples=table, path=rt.PATH_QSLAB)
+    assert _lib.load().ppo_tvf_last_path() & 0xff == rt.PATH_QSLAB
+    assert rel_err(got, ref) <= TOL
+
+
 def test_qslab_is_deterministic_and_matches_the_transposed_slab_kernel():
     """Same arithmetic per target as tvf_tslab.cu (same constants, same order of the entries): bit-identical targets,
     and bit-identical from run to run although quads are handed out dynamically."""
