@@ -12,7 +12,7 @@ from ppo_b200 import returns_truncated as rt, _lib
 
 
 def main():
-    steps, envs = 256, 4096
+    steps, envs = [int(x) for x in os.environ.get("PPO_TIME_SHAPE", "256,4096").split(",")]
     lib = _lib.load()
     hz = _tvf_mod.get_value_head_horizons(128, 30000)
     device = torch.device("cuda")
