@@ -310,9 +310,10 @@ int ppo_tvf_tables_build_ex(double gamma, int64_t steps, const int64_t* required
 
 /* which TVF kernel ppo_tvf_targets may use */
 typedef enum {
-    PPO_TVF_AUTO = 0,    /* >= 3 n-steps per horizon: the quad slab kernel at 256 steps x 128 horizons (PPO_TVF_QSLAB=0 /
-                            1 in the environment forces the choice), else the transposed slab kernel; fewer: the TMA
-                            ring kernel; the generic kernel when the shape allows none of them */
+    PPO_TVF_AUTO = 0,    /* >= 3 n-steps per horizon: the quad slab kernel at 256 steps x 128 horizons and up to 4096
+                            envs per launch (PPO_TVF_QSLAB=0 / 1 in the environment forces the choice), else the
+                            transposed slab kernel; fewer: the TMA ring kernel; the generic kernel when the shape
+                            allows none of them */
     PPO_TVF_GENERIC = 1, /* global-memory gather kernel, any shape                            */
     PPO_TVF_RING = 2,    /* TMA ring kernel or PPO_ERR_UNSUPPORTED                            */
     PPO_TVF_TSLAB = 3,   /* transposed slab kernel or PPO_ERR_UNSUPPORTED                     */

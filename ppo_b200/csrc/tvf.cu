@@ -233,14 +233,17 @@ static thread_local int g_last_path = 0;
 
 extern "C" int ppo_tvf_last_path(void) { return g_last_path; }
 
-// PPO_TVF_AUTO takes the quad slab kernel at 256 steps (x 128 horizons on 128 value horizons: the launcher checks the
-// rest) -- 0.492 against 0.511 ms per bench pass, same box, bit-identical targets; at 128 steps x 1024 envs the transposed
-// slab kernel is the faster one and stays.  PPO_TVF_QSLAB=0 / 1 in the environment forces the choice (read per call: A/B
-// runs).
-static bool prefer_qslab(int64_t steps) {
+// PPO_TVF_AUTO takes the quad slab kernel at 256 steps and up to 4096 envs per launch (x 128 horizons on 128 value
+// horizons: the launcher checks the rest) -- 0.488 against 0.510 ms per bench pass, bit-identical targets; 125 / 228 /
+// 448 us against 127 / 238 / 453 us for the targets of 1024 / 2048 / 4096 envs.  Beyond that it falls off a cliff
+// (8192 envs: 1195 against 891 us, 16384: 2398 against 1757 us): its 128-row x 32-byte stores and 128-row x 128-byte
+// loads touch four times as many pages per byte as the transposed slab kernel's 32-row boxes, and past ~2 GB of
+// buffers the address translation no longer keeps up.  At 128 steps x 1024 envs the transposed slab kernel is the faster
+// one as well.  PPO_TVF_QSLAB=0 / 1 in the environment forces the choice (read per call: A/B runs).
+static bool prefer_qslab(int64_t steps, int64_t envs) {
     const char* e = getenv("PPO_TVF_QSLAB");
     if (e != nullptr) return atoi(e) != 0;
-    return steps == 256;
+    return steps == 256 && envs <= 4096;
 }
 
 extern "C" int64_t ppo_tvf_workspace_bytes(int64_t steps, int64_t envs) {
@@ -325,7 +328,7 @@ extern "C" int ppo_tvf_targets_ex(const float* rewards, int64_t reward_row_strid
     // (a caller that asks for the fused GAE stage gets the transposed slab kernel, the only one that has it)
     const bool wants_gae = extras && extras->gae_enable;
     if (path == PPO_TVF_QSLAB ||
-        (path == PPO_TVF_AUTO && tables->n_entries >= 3 && rc == PPO_ERR_UNSUPPORTED && !wants_gae && prefer_qslab(steps))) {
+        (path == PPO_TVF_AUTO && tables->n_entries >= 3 && rc == PPO_ERR_UNSUPPORTED && !wants_gae && prefer_qslab(steps, envs))) {
         rc = launch_tvf_qslab(p, stats, partials, ticket, kStatsBlocks, vweights, vout, vout_rs, s, &stats_fused);
         if (path == PPO_TVF_QSLAB && rc != PPO_OK) return rc;
         if (rc != PPO_OK && rc != PPO_ERR_UNSUPPORTED) return rc;

@@ -22,3 +22,4 @@ PPO_TIME_PATH=qslab timeout 120 python tools/time_tslab.py 0 > gpurun_out/plain_
 PPO_TIME_PATH=qslab timeout 300 ncu --set full --clock-control none --import-source on -k regex:qslab -s 3 -c 1 \
     -o gpurun_out/r02_qslab_4096_adv -f python tools/time_tslab.py 0 > gpurun_out/ncu_qslab.log 2>&1
 tail -2 gpurun_out/ncu_qslab.log
+timeout 600 python bench.py --scaling strong --steps 30 --warmup 5 --no-cpu-baseline --no-other-configs > gpurun_out/bench_strong.json 2> gpurun_out/bench_strong.err; echo "bench strong rc=$?"
