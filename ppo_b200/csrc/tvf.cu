@@ -236,9 +236,9 @@ extern "C" int ppo_tvf_last_path(void) { return g_last_path; }
 // PPO_TVF_AUTO takes the quad slab kernel at 256 steps and up to 4096 envs per launch (x 128 horizons on 128 value
 // horizons: the launcher checks the rest) -- 0.488 against 0.510 ms per bench pass, bit-identical targets; 125 / 228 /
 // 448 us against 127 / 238 / 453 us for the targets of 1024 / 2048 / 4096 envs.  Beyond that it falls off a cliff
-// (8192 envs: 1195 against 891 us, 16384: 2398 against 1757 us): its 128-row x 32-byte stores and 128-row x 128-byte
-// loads touch four times as many pages per byte as the transposed slab kernel's 32-row boxes, and past ~2 GB of
-// buffers the address translation no longer keeps up.  At 128 steps x 1024 envs the transposed slab kernel is the faster
+// (4608 envs: 553 against 513 us, 8192: 1195 against 891 us, 16384: 2398 against 1757 us): its 128-row x 32-byte stores
+// and 128-row x 128-byte loads visit a page four times as often per byte as the transposed slab kernel's 32-row boxes,
+// and past ~1.1 GB of buffers the address translation no longer keeps up.  At 128 steps x 1024 envs the transposed slab kernel is the faster
 // one as well.  PPO_TVF_QSLAB=0 / 1 in the environment forces the choice (read per call: A/B runs).
 static bool prefer_qslab(int64_t steps, int64_t envs) {
     const char* e = getenv("PPO_TVF_QSLAB");

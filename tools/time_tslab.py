@@ -20,8 +20,13 @@ def main():
     g.manual_seed(0)
     r = torch.randint(-1, 3, (steps, envs), device=device, generator=g).float()
     d = (torch.rand((steps, envs), device=device, generator=g) < 0.03).view(torch.uint8)
-    vs = torch.randn((steps + 1, envs, 128), device=device, generator=g) * 0.4 + 0.1
-    out = torch.empty((steps, envs, 128), device=device)
+    off = int(os.environ.get("PPO_TIME_OFFSET", "0")) // 4  # start the two big buffers this many bytes into their allocations
+    vs_all = torch.empty((steps + 1) * envs * 128 + off, device=device)
+    vs = vs_all[off:].view(steps + 1, envs, 128)
+    vs.copy_(torch.randn((steps + 1, envs, 128), device=device, generator=g) * 0.4 + 0.1)
+    out_all = torch.empty(steps * envs * 128 + off, device=device)
+    out = out_all[off:].view(steps, envs, 128)
+    print("alignment of the buffers within a 2 MB page:", vs.data_ptr() % (1 << 21), out.data_ptr() % (1 << 21))
     table = rt.draw_n_step_samples("exponential", "advanced", hz, steps, 20, 8, seed=1)
     tabs = rt.build_tables(0.99997, steps, hz, hz, table)
     ctab, blob = rt._upload_tables(tabs, device)
