@@ -782,6 +782,15 @@ static uint32_t qs_align(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 template <int RG>
 static int qs_launch_one(const QsParams& q, const CUtensorMap& vmap, const CUtensorMap& omap, int64_t grid,
                          cudaStream_t stream) {
+    // The consumers raise their register count to 96 out of the pool the CTA is launched with (768 threads x the
+    // kernel's register count): with fewer than 80 registers per thread at launch the request could never be granted
+    // and the kernel would hang, so a build that came out smaller declines (PATH_AUTO then takes the transposed slab kernel).
+    cudaFuncAttributes attr;
+    PPO_CUDA(cudaFuncGetAttributes(&attr, tvf_qslab_kernel<RG>));
+    if (attr.numRegs * kQsThreads < kQsConsumers * 32 * 96 + (kQsThreads - kQsConsumers * 32) * 48) {
+        set_error("ppo_tvf_targets: quad slab kernel unavailable: built with %d registers per thread, 80 required", attr.numRegs);
+        return PPO_ERR_UNSUPPORTED;
+    }
     PPO_CUDA(cudaFuncSetAttribute(tvf_qslab_kernel<RG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(q.smem_total)));
     tvf_qslab_kernel<RG><<<static_cast<unsigned>(grid), kQsThreads, q.smem_total, stream>>>(q, vmap, omap);
