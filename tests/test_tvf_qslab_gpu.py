@@ -175,6 +175,36 @@ def test_qslab_is_deterministic_and_matches_the_transposed_slab_kernel():
     assert np.array_equal(a, c)
 
 
+def test_path_auto_selection(monkeypatch):
+    """PATH_AUTO: the quad slab kernel at 256 steps and up to 4096 envs per launch, the transposed slab kernel beyond
+    (the env-count edge) and at 128 steps; PPO_TVF_QSLAB=0 / 1 forces the choice where both apply."""
+    lib = _lib.load()
+    hz = oracle.get_value_head_horizons(128, 30000)
+    dev = torch.device("cuda")
+
+    def run(steps, envs):
+        table = oracle.draw_n_step_samples("exponential", "advanced", hz, steps, 20, 8, seed=5)
+        ctab, keep = rt._upload_tables(rt.build_tables(0.99997, steps, hz, hz, table), dev)
+        r = torch.zeros((steps, envs), device=dev)
+        d = torch.zeros((steps, envs), dtype=torch.uint8, device=dev)
+        vs = torch.zeros((steps + 1, envs, 128), device=dev)
+        out = torch.empty((steps, envs, 128), device=dev)
+        rc = lib.ppo_tvf_targets(r.data_ptr(), envs, d.data_ptr(), _lib.DONE_U8, envs, vs.data_ptr(), envs * 128, 128, steps,
+                                 envs, 128, 128, ctypes.byref(ctab), rt.PATH_AUTO, out.data_ptr(), 0, 0, 0,
+                                 torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        torch.cuda.synchronize()
+        return lib.ppo_tvf_last_path() & 0xff
+
+    monkeypatch.delenv("PPO_TVF_QSLAB", raising=False)
+    assert run(256, 300) == rt.PATH_QSLAB and run(256, 4096) == rt.PATH_QSLAB
+    assert run(256, 4100) == rt.PATH_TSLAB and run(128, 300) == rt.PATH_TSLAB
+    monkeypatch.setenv("PPO_TVF_QSLAB", "0")
+    assert run(256, 300) == rt.PATH_TSLAB
+    monkeypatch.setenv("PPO_TVF_QSLAB", "1")
+    assert run(128, 300) == rt.PATH_QSLAB and run(256, 4100) == rt.PATH_QSLAB
+
+
 def test_qslab_declines_what_it_cannot_take():
     hz = oracle.get_value_head_horizons(128, 30000)
     r, d, _ = synthetic.rollout(100, 4, seed=1)
