@@ -640,6 +640,37 @@ def run_ours(args):
     targets_per_step = steps * envs * n_h * world
     value = targets_per_step / (ms_per_step * 1e-3)
 
+    # ---- what sharding adds to a step: the same pass on this rank's envs WITHOUT the exchange (a group of one), so
+    # that the wait in front of the in-kernel moment exchange (rank skew + one NVLink round trip) has a number
+    exchange = None
+    if world > 1:
+        solo_groups = [dist.new_group([r]) for r in range(world)]  # (collective: every rank creates every group)
+        solo = rollout.ReturnPass(steps, envs, hz, GAMMA, TVF_GAMMA, LAMBDA_POLICY, LAMBDA_VALUE, group=solo_groups[rank])
+        solo.set_samples(samples)
+        for _ in range(args.warmup):
+            solo.run(rewards, None, dones, value_samples)
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0.record()
+        for i in range(args.steps):
+            solo.run(rewards, None, dones, value_samples, tvf_events=evs[i])
+        t1.record()
+        barrier()
+        solo_step = t0.elapsed_time(t1) / args.steps
+        solo_rest = solo_step - sum(e[0].elapsed_time(e[1]) for e in evs) / len(evs)
+        shard_rest = fixed_ms_per_step - sum(fixed_tvf_ms) / len(fixed_tvf_ms)
+        t = torch.tensor([solo_rest, solo_step], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        exchange = {"rest_of_step_us": shard_rest * 1e3, "rest_of_step_unsharded_us": float(t[0].item()) * 1e3,
+                    "exchange_wait_us": (shard_rest - float(t[0].item())) * 1e3,
+                    "unsharded_ms_per_step": float(t[1].item()),
+                    "note": "rest of step = step - target kernel (GAE / TD(lambda) / statistics / normalisation launch and "
+                            "launch gaps), fixed sample table, max over ranks; unsharded = the same pass on this rank's "
+                            "envs in a group of one; the difference is the wait in front of the in-kernel moment "
+                            "exchange (rank skew of the target launch + one NVLink store / poll round trip)"}
+        del solo
+
     # ---- end to end through the public API with pinned host buffers
     host_in = {
         "rewards": rewards.cpu().pin_memory(),
@@ -749,6 +780,8 @@ def run_ours(args):
         }
         if check is not None:
             line["sharded_check"] = check
+        if exchange is not None:
+            line["sharded_step"] = exchange
         if vt_leg is not None:
             line["c4_vtrace_sharded"] = vt_leg
         if other is not None:
